@@ -1,0 +1,282 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (container only).
+
+Run from the repo root:   python oracle/gen_golden.py [sim] [env] [emotion] [nets] [learn]
+
+The reference (/root/reference) is imported through oracle/ref_shim.py (pymodbus stub +
+frozen clock).  All randomness is CPython `random` seeded per case,
+so a test can regenerate the identical Mersenne-Twister stream with `random.Random(seed)`
+and does not need the reference at run time; the fixtures hold only inputs, seeds and the
+reference's outputs.  Fixture provenance is recorded inside each file (`meta`).
+"""
+import contextlib
+import io
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+PARAM_ORDER = ["target_weight", "fast_weight", "medium_weight", "slow_weight", "fast_delay",
+               "medium_delay", "slow_delay", "fast_opening", "medium_opening", "slow_opening",
+               "unload_delay"]
+ACTION_ORDER = ["fast_weight", "medium_weight", "slow_weight", "fast_opening", "medium_opening",
+                "slow_opening", "fast_delay", "medium_delay", "slow_delay", "unload_delay"]
+
+# bounds tables (reference: WeightEnv.py:32-46, MutiConditionEnv.py:47-61, experiment_runner.py:417-478)
+BOUNDS = {
+    "single_25kg": dict(target_weight=25000, target_weight_err=25, target_time=2.5, bounds={
+        "fast_weight": (18000, 23000), "medium_weight": (0, 1), "slow_weight": (24900, 25025),
+        "fast_opening": (35, 60), "medium_opening": (3, 5), "slow_opening": (3, 7),
+        "fast_delay": (100, 300), "medium_delay": (100, 200), "slow_delay": (100, 200),
+        "unload_delay": (300, 500)}),
+    "multi_default": dict(target_weight=25000, target_weight_err=25, target_time=2.5, bounds={
+        "fast_weight": (7000, 18000), "medium_weight": (0, 1), "slow_weight": (24900, 25000),
+        "fast_opening": (35, 75), "medium_opening": (3, 5), "slow_opening": (5, 20),
+        "fast_delay": (100, 300), "medium_delay": (100, 200), "slow_delay": (100, 200),
+        "unload_delay": (300, 500)}),
+    "variant_25kg": dict(target_weight=25000, target_weight_err=25, target_time=2.5, bounds={
+        "fast_weight": (7000, 18000), "medium_weight": (0, 1), "slow_weight": (24900, 25000),
+        "fast_opening": (35, 75), "medium_opening": (3, 5), "slow_opening": (5, 20),
+        "fast_delay": (100, 300), "medium_delay": (100, 200), "slow_delay": (100, 200),
+        "unload_delay": (300, 500)}),
+    "variant_20kg": dict(target_weight=20000, target_weight_err=20, target_time=2.0, bounds={
+        "fast_weight": (6000, 15000), "medium_weight": (0, 1), "slow_weight": (19800, 20000),
+        "fast_opening": (30, 70), "medium_opening": (3, 5), "slow_opening": (5, 18),
+        "fast_delay": (80, 250), "medium_delay": (80, 180), "slow_delay": (80, 180),
+        "unload_delay": (280, 480)}),
+    "variant_15kg": dict(target_weight=15000, target_weight_err=15, target_time=1.5, bounds={
+        "fast_weight": (5000, 12000), "medium_weight": (0, 1), "slow_weight": (14800, 15000),
+        "fast_opening": (25, 65), "medium_opening": (2, 4), "slow_opening": (4, 15),
+        "fast_delay": (60, 200), "medium_delay": (60, 150), "slow_delay": (60, 150),
+        "unload_delay": (250, 450)}),
+}
+
+
+def _meta(what):
+    import platform
+    import numpy
+    return json.dumps({"what": what, "generator": "oracle/gen_golden.py",
+                       "reference": "Harrison-Ma/ERL-Fill @ /root/reference (unmodified, pymodbus stubbed, frozen clock)",
+                       "python": platform.python_version(), "numpy": numpy.__version__})
+
+
+@contextlib.contextmanager
+def _quiet():
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+# ----------------------------------------------------------------------------------------
+def gen_sim():
+    """E1 known-answer vectors: (11 int params, seed) -> (iterations, total_time, final_weight)."""
+    V = ref_shim.install()
+    rng = np.random.RandomState(1234)
+    cases = []
+    # the SURVEY section-4 KATs first
+    kat = dict(target_weight=25000, fast_weight=12000, medium_weight=0, slow_weight=24950,
+               fast_delay=200, medium_delay=150, slow_delay=150, fast_opening=55, medium_opening=4,
+               slow_opening=12, unload_delay=400)
+    for s in (0, 1, 2):
+        cases.append((dict(kat), s))
+    # random integer params inside every shipped bounds table
+    for name, cfg in BOUNDS.items():
+        for _ in range(60):
+            p = {"target_weight": cfg["target_weight"]}
+            for k, (lo, hi) in cfg["bounds"].items():
+                p[k] = int(rng.randint(lo, hi + 1))
+            cases.append((p, int(rng.randint(0, 2**31 - 1))))
+    # config-2 constant action
+    const = dict(target_weight=25000, fast_weight=18000, medium_weight=0, slow_weight=24900,
+                 fast_opening=35, medium_opening=3, slow_opening=3, fast_delay=100, medium_delay=100,
+                 slow_delay=100, unload_delay=300)
+    for s in range(5):
+        cases.append((dict(const), 100 + s))
+    # edge cases outside the shipped bounds: reachable medium stage, reversing motor, first-tick
+    # delay taken in the medium/slow stage, stagnation stop, iteration-cap stop, tiny targets
+    edge = [
+        dict(target_weight=25000, fast_weight=8000, medium_weight=16000, slow_weight=24900, fast_delay=120,
+             medium_delay=130, slow_delay=140, fast_opening=70, medium_opening=30, slow_opening=6, unload_delay=333),
+        dict(target_weight=25000, fast_weight=8000, medium_weight=16000, slow_weight=24900, fast_delay=120,
+             medium_delay=130, slow_delay=140, fast_opening=20, medium_opening=60, slow_opening=90, unload_delay=333),
+        dict(target_weight=1000, fast_weight=0, medium_weight=500, slow_weight=900, fast_delay=11,
+             medium_delay=22, slow_delay=33, fast_opening=40, medium_opening=10, slow_opening=3, unload_delay=5),
+        dict(target_weight=1000, fast_weight=0, medium_weight=0, slow_weight=900, fast_delay=11,
+             medium_delay=22, slow_delay=33, fast_opening=40, medium_opening=10, slow_opening=3, unload_delay=5),
+        dict(target_weight=25000, fast_weight=12000, medium_weight=0, slow_weight=24950, fast_delay=200,
+             medium_delay=150, slow_delay=150, fast_opening=0, medium_opening=4, slow_opening=12, unload_delay=400),
+        dict(target_weight=25000, fast_weight=12000, medium_weight=0, slow_weight=24950, fast_delay=200,
+             medium_delay=150, slow_delay=150, fast_opening=1, medium_opening=4, slow_opening=1, unload_delay=400),
+        dict(target_weight=25000, fast_weight=2000, medium_weight=0, slow_weight=24950, fast_delay=200,
+             medium_delay=150, slow_delay=150, fast_opening=50, medium_opening=4, slow_opening=2, unload_delay=400),
+        dict(target_weight=90000, fast_weight=60000, medium_weight=0, slow_weight=89000, fast_delay=0,
+             medium_delay=0, slow_delay=0, fast_opening=100, medium_opening=4, slow_opening=3, unload_delay=0),
+        dict(target_weight=500, fast_weight=0, medium_weight=0, slow_weight=0, fast_delay=1,
+             medium_delay=2, slow_delay=3, fast_opening=50, medium_opening=4, slow_opening=3, unload_delay=7),
+        dict(target_weight=25000, fast_weight=12000, medium_weight=0, slow_weight=24950, fast_delay=200,
+             medium_delay=150, slow_delay=150, fast_opening=2, medium_opening=4, slow_opening=99, unload_delay=400),
+    ]
+    for i, p in enumerate(edge):
+        for s in (7, 8):
+            cases.append((dict(p), 1000 + 10 * i + s))
+
+    params = np.zeros((len(cases), 11), np.int32)
+    seeds = np.zeros(len(cases), np.int64)
+    iters = np.zeros(len(cases), np.int32)
+    total_time = np.zeros(len(cases), np.float64)
+    final_weight = np.zeros(len(cases), np.float64)
+    peak_open = np.zeros(len(cases), np.float64)
+    peak_speed = np.zeros(len(cases), np.float64)
+    c = V.VirtualWeightController()
+    for i, (p, s) in enumerate(cases):
+        random.seed(s)
+        c.reset()
+        c.load_params(p)
+        with _quiet():
+            speeds, openings, weights, tt, fw = c.simulate_run()
+        params[i] = [p[k] for k in PARAM_ORDER]
+        seeds[i] = s
+        iters[i] = len(weights)
+        total_time[i] = tt
+        final_weight[i] = fw
+        peak_open[i] = max(openings)
+        peak_speed[i] = max(speeds)
+    np.savez_compressed(os.path.join(GOLD, "sim_golden.npz"), params=params, seeds=seeds, iters=iters,
+                        total_time=total_time, final_weight=final_weight, peak_open=peak_open,
+                        peak_speed=peak_speed, meta=_meta("E1 simulate_run KATs"))
+    print("sim:", len(cases), "cases; iters min/mean/max", iters.min(), iters.mean(), iters.max(),
+          "peak speed", peak_speed.max())
+
+
+# ----------------------------------------------------------------------------------------
+def _make_env(kind, name):
+    ref_shim.install()
+    if kind == "single":
+        import WeightEnv as W
+        env = W.WeightEnv()
+    else:
+        import MutiConditionEnv as M
+        cfg = BOUNDS[name]
+        if name == "multi_default":
+            env = M.MultiConditionWeightEnv({k: cfg[k] for k in ("target_weight", "target_weight_err", "target_time")})
+        else:
+            env = M.MultiConditionWeightEnv({**{k: cfg[k] for k in ("target_weight", "target_weight_err", "target_time")},
+                                             "bounds": dict(cfg["bounds"])})
+    return env
+
+
+def gen_env():
+    """E2/E3/E4 vectors: whole episodes of reset()+step() with seeded noise and recorded actions."""
+    out = {}
+    runs = []
+    rng = np.random.RandomState(4321)
+    plan = [("single", "single_25kg", 12, 40), ("multi", "multi_default", 12, 40),
+            ("multi", "variant_25kg", 8, 30), ("multi", "variant_20kg", 8, 30),
+            ("multi", "variant_15kg", 8, 30),
+            # long good-action runs that end by the mean(recent_errors) < 25 rule
+            ("multi", "variant_25kg", 60, 70), ("single", "single_25kg", 60, 70)]
+    for ri, (kind, name, max_steps, n_steps) in enumerate(plan):
+        env = _make_env(kind, name)
+        env.max_steps = max_steps
+        cfg = BOUNDS[name]
+        lo = np.array([cfg["bounds"][k][0] for k in ACTION_ORDER], np.float64)
+        hi = np.array([cfg["bounds"][k][1] for k in ACTION_ORDER], np.float64)
+        seed = 9000 + ri
+        random.seed(seed)
+        good = max_steps >= 60
+        rec = dict(actions=[], next_state=[], reward=[], reward_is_f32=[], done=[], final_weight=[],
+                   total_time=[], weight_error=[], reset_state=[], reset_before=[])
+        state = env.reset()
+        rec["reset_state"].append(state)
+        need_reset = False
+        for t in range(n_steps):
+            if need_reset:
+                state = env.reset()
+                rec["reset_state"].append(state)
+            rec["reset_before"].append(need_reset or t == 0)
+            if good:
+                # near-optimal action found by scanning the reference: small final error
+                a = (lo + hi) / 2
+                a[2] = cfg["target_weight"] - 12.0   # slow_weight
+                a[5] = lo[5] + 0.2 * (hi[5] - lo[5])
+                a = a + rng.uniform(-0.4, 0.4, 10)
+            else:
+                span = hi - lo
+                a = lo - 0.1 * span + rng.uniform(0, 1, 10) * 1.2 * span   # 10% outside on both sides
+                if t % 7 == 3:
+                    a[rng.randint(10)] = lo[rng.randint(10)]               # exactly-on-bound values
+            a32 = a.astype(np.float32)
+            with _quiet():
+                ns, r, d, info = env.step(a32.copy())
+            rec["actions"].append(a32)
+            rec["next_state"].append(ns)
+            rec["reward"].append(float(r))
+            rec["reward_is_f32"].append(isinstance(r, np.float32))
+            rec["done"].append(bool(d))
+            rec["final_weight"].append(info["final_weight"])
+            rec["total_time"].append(info["total_time"])
+            rec["weight_error"].append(info["weight_error"])
+            need_reset = bool(d)
+        key = f"run{ri}"
+        out[key + "_kind"] = kind
+        out[key + "_name"] = name
+        out[key + "_seed"] = seed
+        out[key + "_max_steps"] = max_steps
+        out[key + "_actions"] = np.array(rec["actions"], np.float32)
+        out[key + "_next_state"] = np.array(rec["next_state"], np.float32)
+        out[key + "_reward"] = np.array(rec["reward"], np.float64)
+        out[key + "_reward_is_f32"] = np.array(rec["reward_is_f32"], np.bool_)
+        out[key + "_done"] = np.array(rec["done"], np.bool_)
+        out[key + "_final_weight"] = np.array(rec["final_weight"], np.float64)
+        out[key + "_total_time"] = np.array(rec["total_time"], np.float64)
+        out[key + "_weight_error"] = np.array(rec["weight_error"], np.float64)
+        out[key + "_reset_state"] = np.array(rec["reset_state"], np.float32)
+        out[key + "_reset_before"] = np.array(rec["reset_before"], np.bool_)
+        runs.append(key)
+        print(key, kind, name, "steps", n_steps, "dones", int(np.sum(rec["done"])),
+              "f32 rewards", int(np.sum(rec["reward_is_f32"])),
+              "mean err", float(np.mean(rec["weight_error"])))
+    out["runs"] = np.array(runs)
+    out["bounds_json"] = json.dumps(BOUNDS)
+    out["meta"] = _meta("E2/E3/E4 env.reset/env.step episodes")
+    np.savez_compressed(os.path.join(GOLD, "env_golden.npz"), **out)
+
+
+# ----------------------------------------------------------------------------------------
+def gen_emotion():
+    """M1 vectors: EmotionModule.update over a reward/movement sequence (history + current_emotion)."""
+    ref_shim.install()
+    import torch
+    import EmotionModule as E
+    torch.manual_seed(0)
+    em = E.EmotionModule(device="cpu")
+    rng = np.random.RandomState(77)
+    rewards, moves, cur, returned = [], [], [], []
+    for t in range(64):
+        r = float(rng.choice([rng.uniform(-3000, 6000), rng.uniform(-2, 2), rng.uniform(-0.01, 0.01)]))
+        if t % 2 == 0:
+            r = np.float32(r)    # MutiConditionEnv returns np.float32 rewards on the [f32] path
+        mv = (rng.uniform(-1, 1, 2) * rng.choice([0.01, 0.3, 3.0])).astype(np.float32)
+        out = em.update(r, mv)
+        rewards.append(float(r)); moves.append(mv); cur.append(np.array(em.current_emotion, np.float64))
+        returned.append(np.array(out, np.float64))
+    hist = np.stack([h.numpy() for h in em.transformer.history])
+    np.savez_compressed(os.path.join(GOLD, "emotion_update_golden.npz"), rewards=np.array(rewards, np.float64),
+                        reward_was_f32=np.array([t % 2 == 0 for t in range(64)]),
+                        moves=np.array(moves, np.float32), current=np.array(cur), history_last20=hist,
+                        meta=_meta("M1 EmotionModule.update sequence"))
+    print("emotion: 64 updates, final", em.current_emotion)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    which = sys.argv[1:] or ["sim", "env", "emotion"]
+    os.chdir("/tmp")
+    for w in which:
+        {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion}[w]()
