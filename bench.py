@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the ERL-Fill hot path on B200 (contract: see README / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sim] [--n-env 4096]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU port of the reference path on the host cores
+
+One JSON line on stdout (rank 0).  A "step" is one lock-step pass of the workload over the batch of
+envs of every rank.  `value` is device-timed with inputs resident in HBM; `e2e` goes through the
+public Python API with pinned HOST buffers (H2D of the step's actions, D2H of state/reward/done
+inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENV_STEP_BYTES = 192          # algorithmic bytes per env-step
+L2_FLUSH_BYTES = 256 << 20    # > 126 MB L2
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------
+def _sim_setup(args, rank, device):
+    """configs[1] of BASELINE.json: batched WeightEnv rollout, PID-effective constant action."""
+    import torch
+    import erlfill_b200 as E
+    K = E.conditions
+    n = args.n_env
+    env = E.VecFillEnv([K.SINGLE_25KG], n, kind="single", max_steps=100, seed=0, device=device,
+                       env_id_base=rank * n)
+    if args.actions == "pid":
+        a_host = torch.tensor(K.PID_EFFECTIVE_ACTION, dtype=torch.float32).repeat(n, 1)
+    else:   # uniform in bounds (heavy divergence variant)
+        g = torch.Generator().manual_seed(1234 + rank)
+        lo = torch.tensor([K.SINGLE_25KG["bounds"][k][0] for k in E._lib.ACTION_ORDER], dtype=torch.float32)
+        hi = torch.tensor([K.SINGLE_25KG["bounds"][k][1] for k in E._lib.ACTION_ORDER], dtype=torch.float32)
+        a_host = lo + torch.rand(n, 10, generator=g) * (hi - lo)
+    a_host = a_host.contiguous().pin_memory()
+    a_dev = a_host.to(device)
+    env.reset()
+    return env, a_host, a_dev
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    import erlfill_b200 as E
+    E._lib.require_device()
+
+    env, a_host, a_dev = _sim_setup(args, rank, device)
+    n = args.n_env
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream()
+
+    def one_step():
+        env.step(a_dev)
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    env.tick_sum.zero_()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
+        starts[k].record(stream)
+        one_step()
+        ends[k].record(stream)
+    torch.cuda.synchronize()
+    wall1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = sum(per_step_ms)
+    ticks = int(env.tick_sum.item())
+    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    tk = torch.tensor([ticks], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tk, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item())
+    ticks_all = float(tk.item())
+    ms_per_step = total_ms / args.steps
+    value = n * world * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region ------------
+    ns_host = torch.empty(n, 2, dtype=torch.float32).pin_memory()
+    r_host = torch.empty(n, dtype=torch.float32).pin_memory()
+    d_host = torch.empty(n, dtype=torch.uint8).pin_memory()
+    a_in = torch.empty_like(a_dev)
+
+    def e2e_step():
+        a_in.copy_(a_host, non_blocking=True)
+        ns, r, d, _ = env.step(a_in)
+        ns_host.copy_(ns, non_blocking=True)
+        r_host.copy_(r, non_blocking=True)
+        d_host.copy_(d, non_blocking=True)
+        stream.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n * world * args.steps / (float(te.item()) * 1e-3)
+    h2d = a_host.numel() * 4
+    d2h = ns_host.numel() * 4 + r_host.numel() * 4 + d_host.numel()
+
+    if rank == 0:
+        peaks = _peaks()
+        kernel_s = ms_per_step * 1e-3
+        achieved = ENV_STEP_BYTES * n / kernel_s / 1e9
+        out = {
+            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: batched WeightEnv rollout, %d envs/GPU, %s action "
+                                   "(sim-kernel throughput), Philox noise" % (n, "PID-effective constant"
+                                                                              if args.actions == "pid" else "uniform-random"),
+                       "n_env_per_gpu": n, "actions": args.actions, "parallelism": "env-sharded x%d" % world,
+                       "l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
+                       "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+            "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / (n * world * args.steps),
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": args.steps, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                         "kernel": "env_step_kernel<false>", "algorithmic_bytes_per_env_step": ENV_STEP_BYTES,
+                         "note": "this kernel is FP64-issue/latency bound (about 14 DP instructions per 1 ms "
+                                 "tick, serial chain), not HBM bound: see fp64_issue"},
+            "fp64_issue": _issue_model(ticks_all / world / args.steps / kernel_s, clocks),
+            "wall_s_timed_region": wall1 - wall0,
+        }
+        out["cpu_baseline"] = cpu_baseline_sim(args, budget_s=args.cpu_budget)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _issue_model(ticks_per_s_per_gpu, clocks):
+    """Ticks/s against the FP64 issue ceiling: 148 SMs x 4 schedulers x 16 DP lanes/clk (B200 DP is half the
+    FP32 rate) / DP instructions per tick (14 counted in the SASS loop body)."""
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    dp_per_tick = 14
+    ceiling = 148 * 4 * 16 * mhz * 1e6 / dp_per_tick
+    return {"achieved_ticks_per_s": ticks_per_s_per_gpu, "ceiling_ticks_per_s": ceiling,
+            "frac": ticks_per_s_per_gpu / ceiling, "dp_instr_per_tick": dp_per_tick, "sm_mhz_used": mhz}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py may execute oracle/)
+# ------------------------------------------------------------------------------------------------
+def _cpu_sim_once(args, n_env, n_threads, steps):
+    import numpy as np
+    from oracle import oracle_lib as O
+    import erlfill_b200 as E
+    K = E.conditions
+    c = K.SINGLE_25KG
+    cond = [O.make_condition(c["target_weight"], c["target_weight_err"], c["target_time"], c["bounds"])]
+    env = O.BatchEnv(O.ENV_SINGLE, cond, n_env, max_steps=100, seed=0)
+    if args.actions == "pid":
+        a = np.tile(np.array(K.PID_EFFECTIVE_ACTION, np.float32), (n_env, 1))
+    else:
+        rng = np.random.RandomState(1234)
+        lo = np.array([c["bounds"][k][0] for k in O.ACTION_ORDER], np.float32)
+        hi = np.array([c["bounds"][k][1] for k in O.ACTION_ORDER], np.float32)
+        a = (lo + rng.uniform(0, 1, (n_env, 10)) * (hi - lo)).astype(np.float32)
+    t0 = time.perf_counter()
+    ticks = 0
+    for s in range(steps):
+        ticks += env.step(a, s, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    return n_env * steps / dt, ticks / dt, dt
+
+
+def cpu_baseline_sim(args, budget_s=12.0):
+    """C port of the reference path (oracle/erlfill_oracle.c), all host cores, bounded sample."""
+    import random
+    from oracle import oracle_lib as O, py_port
+    cores = O.lib().orc_max_threads()
+    rate, _, _ = _cpu_sim_once(args, 64 * cores, cores, 1)          # calibrate
+    n_env = max(64 * cores, int(rate * budget_s / 4) // 64 * 64)
+    v, tps, dt = _cpu_sim_once(args, n_env, cores, 4)
+    # the reference's own language: pure-Python restatement, one core, ~2 s
+    p = dict(zip(["target_weight", "fast_weight", "medium_weight", "slow_weight", "fast_delay", "medium_delay",
+                  "slow_delay", "fast_opening", "medium_opening", "slow_opening", "unload_delay"],
+                 [25000, 18000, 0, 24900, 100, 100, 100, 35, 3, 3, 300]))
+    rng = random.Random(0)
+    t0, runs = time.perf_counter(), 0
+    while time.perf_counter() - t0 < 2.0:
+        py_port.simulate_run(p, rng)
+        runs += 1
+    py_rate = runs / (time.perf_counter() - t0)
+    return {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d envs x 4 steps of the same workload, C oracle (pthreads over envs), %.1f s" % (n_env, dt),
+            "ticks_per_sec": tps,
+            "python_port_one_core": {"value": py_rate, "unit": "env-steps/s", "cores": 1,
+                                     "note": "pure-Python restatement of simulate_run (the reference is a CPython loop)"}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import oracle_lib as O
+    cores = O.lib().orc_max_threads()
+    n = args.n_env
+    # bounded sample: every "step" is one pass of the C port over n_ref envs of the same workload
+    rate, _, _ = _cpu_sim_once(args, 64 * cores, cores, 1)
+    per_step_budget = max(0.5, min(10.0, 120.0 / max(1, args.steps + args.warmup)))
+    n_ref = int(min(n, max(64 * cores, rate * per_step_budget)))
+    for _ in range(args.warmup):
+        _cpu_sim_once(args, n_ref, cores, 1)
+    t0 = time.perf_counter()
+    v, tps, dt = _cpu_sim_once(args, n_ref, cores, args.steps)
+    total = time.perf_counter() - t0
+    sample = "%d of %d envs per step (bounded sample), C port of the reference path, %d threads" % (n_ref, n, cores)
+    out = {"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "configs[1]: batched WeightEnv rollout, %d envs/GPU, %s action (sim-kernel "
+                                  "throughput)" % (n, "PID-effective constant" if args.actions == "pid" else "uniform-random"),
+                      "n_env_per_gpu": n, "actions": args.actions},
+           "ticks_per_sec": tps,
+           "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sim", choices=["sim"])
+    ap.add_argument("--n-env", type=int, default=4096)
+    ap.add_argument("--actions", default="pid", choices=["pid", "random"])
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,106 @@
+"""ctypes binding of erl-fill_b200/lib/liberlfill.so (the C ABI declared in include/erlfill.h).
+
+There is no CPU fallback: if the library is missing or the current device is not sm_100,
+`lib()` / `require_device()` raise.  Build with `python erl-fill_b200/build.py` (or
+`__graft_entry__.build()`).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "lib", "liberlfill.so")
+
+ACTION_DIM, STATE_DIM, EMOTION_DIM, RING, HIST = 10, 2, 3, 20, 20
+ENV_MULTI, ENV_SINGLE = 0, 1
+ACTION_ORDER = ("fast_weight", "medium_weight", "slow_weight", "fast_opening", "medium_opening",
+                "slow_opening", "fast_delay", "medium_delay", "slow_delay", "unload_delay")
+
+
+class ErlfillError(RuntimeError):
+    pass
+
+
+class Condition(C.Structure):
+    _fields_ = [("target_weight", C.c_int32), ("_pad", C.c_int32), ("target_weight_err", C.c_double),
+                ("target_time", C.c_double), ("lo", C.c_float * ACTION_DIM), ("hi", C.c_float * ACTION_DIM)]
+
+
+class EnvBatch(C.Structure):
+    _fields_ = [("n_env", C.c_int32), ("kind", C.c_int32), ("max_steps", C.c_int32), ("n_cond", C.c_int32),
+                ("env_id_base", C.c_uint32), ("_pad", C.c_uint32), ("seed", C.c_uint64),
+                ("d_cond", C.c_void_p), ("d_cond_id", C.c_void_p), ("d_step_counter", C.c_void_p),
+                ("d_episode_counter", C.c_void_p), ("d_ring_len", C.c_void_p), ("d_ring_head", C.c_void_p),
+                ("d_ring", C.c_void_p), ("d_obs", C.c_void_p)]
+
+
+class StepOut(C.Structure):
+    _fields_ = [("d_next_state", C.c_void_p), ("d_reward", C.c_void_p), ("d_done", C.c_void_p),
+                ("d_final_weight", C.c_void_p), ("d_total_time", C.c_void_p), ("d_ticks", C.c_void_p),
+                ("d_tick_sum", C.c_void_p)]
+
+
+class Noise(C.Structure):
+    _fields_ = [("d_u", C.c_void_p), ("rows", C.c_int32), ("_pad", C.c_int32), ("d_reset_u", C.c_void_p)]
+
+
+# every symbol include/erlfill.h declares (tests/test_abi.py checks the library exports them all)
+EXPORTS = [
+    "erlfill_version", "erlfill_last_cuda_error", "erlfill_last_cuda_error_string", "erlfill_device_ok",
+    "erlfill_env_reset", "erlfill_env_reset_from_replay", "erlfill_env_step",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ErlfillError(
+                f"{SO_PATH} is missing: build it with `python erl-fill_b200/build.py` "
+                "(there is no CPU fallback for the ERL-Fill hot path)")
+        L = C.CDLL(SO_PATH)
+        L.erlfill_last_cuda_error_string.restype = C.c_char_p
+        for name in EXPORTS:
+            getattr(L, name)
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        L = lib()
+        detail = ""
+        if rc == -2:
+            detail = f" (CUDA error {L.erlfill_last_cuda_error()}: {L.erlfill_last_cuda_error_string().decode()})"
+        raise ErlfillError(f"{what} failed with status {rc}{detail}")
+
+
+def require_device():
+    """Raise unless the current CUDA device can run the sm_100a kernels."""
+    import torch
+    if not torch.cuda.is_available():
+        raise ErlfillError("no CUDA device: the ERL-Fill B200 path has no CPU fallback")
+    if not lib().erlfill_device_ok():
+        raise ErlfillError("current CUDA device is not sm_100 (B200); liberlfill.so is built for sm_100a only")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None) as c_void_p."""
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def make_condition(target_weight, target_weight_err, target_time, bounds):
+    c = Condition()
+    c.target_weight = int(target_weight)
+    c.target_weight_err = float(target_weight_err)
+    c.target_time = float(target_time)
+    for i, k in enumerate(ACTION_ORDER):
+        lo, hi = bounds[k]
+        c.lo[i], c.hi[i] = float(lo), float(hi)
+    return c

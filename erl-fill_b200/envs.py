@@ -1,0 +1,243 @@
+"""Batched filling-line environments on the GPU, plus N=1 drop-ins with the reference's API.
+
+  VecFillEnv                 N independent envs on one GPU, torch tensors in/out, one fused CUDA
+                             kernel per lock-step step (csrc/env_step.cu through the C ABI).
+  WeightEnv()                drop-in for /root/reference/WeightEnv.py:21-588 (offline-sim branch)
+  MultiConditionWeightEnv()  drop-in for /root/reference/MutiConditionEnv.py:470-486
+
+The drop-ins keep the reference's duck-typed surface: `bounds`, `state_dim`,
+`action_dim`, `max_steps`, `target_weight`, `scale_centers/scale_ranges`, `attach_agent`, `reset()`,
+`step(action) -> (np.float32[2], float, bool, info)`, `normalize_action`.
+"""
+import ctypes as C
+import random
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import conditions as K
+
+MAX_DRAWS = 5002   # 1 system_delay + at most 5001 tick draws (VirtualWeightController.py:158)
+
+
+class VecFillEnv:
+    """N envs stepped in lock-step by one kernel launch.
+
+    conditions : list of dicts {target_weight, target_weight_err, target_time, bounds}
+    cond_id    : optional int32[N]; default env (env_id_base + i) uses condition (env_id_base + i) % len(conditions)
+    kind       : "multi" (MutiConditionEnv reward) or "single" (WeightEnv reward v2)
+    """
+
+    def __init__(self, conditions, n_env, kind="multi", max_steps=100, seed=0, device="cuda",
+                 env_id_base=0, cond_id=None, auto_reset=True):
+        L.require_device()
+        self.device = torch.device(device)
+        self.n_env = int(n_env)
+        self.kind = {"multi": L.ENV_MULTI, "single": L.ENV_SINGLE}[kind]
+        self.max_steps = int(max_steps)
+        self.seed = int(seed)
+        self.env_id_base = int(env_id_base)
+        self.auto_reset = bool(auto_reset)
+        self.conditions = list(conditions)
+        conds = (L.Condition * len(conditions))(*[
+            L.make_condition(c["target_weight"], c["target_weight_err"], c["target_time"], c["bounds"])
+            for c in conditions])
+        raw = np.frombuffer(bytes(conds), dtype=np.uint8).copy()
+        dev = self.device
+        self._d_cond = torch.from_numpy(raw).to(dev)
+        self._d_cond_id = None if cond_id is None else torch.as_tensor(cond_id, dtype=torch.int32, device=dev).contiguous()
+        n = self.n_env
+        self.step_counter = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.episode_counter = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.ring_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.ring_head = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.ring = torch.zeros(L.RING, n, dtype=torch.float64, device=dev)
+        self.obs = torch.zeros(n, 2, dtype=torch.float32, device=dev)
+        # step outputs (reused every step)
+        self.next_state = torch.zeros(n, 2, dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.final_weight = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.total_time = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.ticks = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.tick_sum = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.step_idx = 0
+        self._out = L.StepOut(L.ptr(self.next_state), L.ptr(self.reward), L.ptr(self.done),
+                              L.ptr(self.final_weight), L.ptr(self.total_time), L.ptr(self.ticks),
+                              L.ptr(self.tick_sum))
+
+    # -- C-ABI descriptor (rebuilt per call: max_steps is assigned by trainers at any time) ----
+    def _batch(self):
+        return L.EnvBatch(self.n_env, self.kind, int(self.max_steps), len(self.conditions), self.env_id_base, 0,
+                          self.seed, L.ptr(self._d_cond), L.ptr(self._d_cond_id), L.ptr(self.step_counter),
+                          L.ptr(self.episode_counter), L.ptr(self.ring_len), L.ptr(self.ring_head),
+                          L.ptr(self.ring), L.ptr(self.obs))
+
+    @staticmethod
+    def _noise(u=None, reset_u=None):
+        if u is None and reset_u is None:
+            return None, None
+        nz = L.Noise(L.ptr(u), 0 if u is None else int(u.shape[0]), 0, L.ptr(reset_u))
+        return nz, C.byref(nz)
+
+    def reset(self, mask=None, reset_u=None):
+        """Cold-start reset (MutiConditionEnv.py:135-164) of the masked envs (all if mask is None)."""
+        b = self._batch()
+        nz, nzp = self._noise(None, reset_u)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().erlfill_env_reset(C.byref(b), L.ptr(mask), C.c_uint32(0xFFFFFFFF - (self.step_idx & 0xFFFF)),
+                                              nzp, L.stream_ptr()), "erlfill_env_reset")
+        return self.obs
+
+    def reset_from_replay(self, replay_states, idx, mask=None):
+        """Replay branch of reset (MutiConditionEnv.py:145-154): idx int64[N,10] into replay_states[C,2]."""
+        b = self._batch()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().erlfill_env_reset_from_replay(C.byref(b), L.ptr(mask), L.ptr(replay_states), L.ptr(idx),
+                                                          L.stream_ptr()), "erlfill_env_reset_from_replay")
+        return self.obs
+
+    def step(self, actions, noise_u=None, reset_u=None, auto_reset=None):
+        """actions float32[N,10] (physical units) on the device.  Returns (next_state, reward, done, info);
+        `self.obs` is the observation to act on next (reset state where done and auto_reset)."""
+        if actions.dtype != torch.float32 or not actions.is_contiguous() or tuple(actions.shape) != (self.n_env, 10):
+            raise ValueError("actions must be a contiguous float32 tensor of shape [n_env, 10]")
+        if actions.device != self.obs.device:
+            raise ValueError("actions must live on the env's device")
+        b = self._batch()
+        nz, nzp = self._noise(noise_u, reset_u)
+        ar = self.auto_reset if auto_reset is None else bool(auto_reset)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().erlfill_env_step(C.byref(b), L.ptr(actions), C.c_uint32(self.step_idx & 0xFFFFFFFF),
+                                             C.c_int(int(ar)), nzp, C.byref(self._out), L.stream_ptr()),
+                    "erlfill_env_step")
+        self.step_idx += 1
+        info = {"final_weight": self.final_weight, "total_time": self.total_time, "ticks": self.ticks}
+        return self.next_state, self.reward, self.done, info
+
+
+# ----------------------------------------------------------------------------------------------
+# N = 1 drop-ins
+# ----------------------------------------------------------------------------------------------
+class _ScalarEnvBase:
+    """Shared implementation of the two reference env classes at N = 1.
+
+    noise="reference": the simulator consumes CPython's global `random` stream exactly like the
+    reference (one uniform(15,50), then one uniform(-1,1) per tick; VirtualWeightController.py:122,137),
+    so `random.seed(s)` reproduces the reference trajectory bit for bit.  noise="philox": in-kernel
+    counter-based noise (fast; statistically equivalent).
+    """
+    _kind = "multi"
+
+    def __init__(self, cfg, noise="reference", device="cuda", seed=0):
+        self.target_weight = cfg["target_weight"]
+        self.target_weight_err = cfg["target_weight_err"]
+        self.target_time = cfg["target_time"]
+        self.bounds = dict(cfg["bounds"])
+        self.max_steps = 100
+        self.state_dim = 2
+        self.action_dim = len(self.bounds)
+        self.state = None
+        self.agent = None
+        self.use_offline_sim = 1
+        self.episode_counter = 0
+        self.step_counter = 0
+        self._noise_mode = noise
+        self._device = device
+        self._seed = seed
+        self._vec = None
+        self._update_scaling_params()
+
+    def _update_scaling_params(self):
+        self.scale_centers, self.scale_ranges = {}, {}
+        for key, (low, high) in self.bounds.items():
+            self.scale_centers[key] = (high + low) / 2
+            self.scale_ranges[key] = (high - low) / 2
+
+    def _ensure(self):
+        if self._vec is None:
+            cfg = {"target_weight": self.target_weight, "target_weight_err": self.target_weight_err,
+                   "target_time": self.target_time, "bounds": self.bounds}
+            self._vec = VecFillEnv([cfg], 1, kind=self._kind, max_steps=self.max_steps, seed=self._seed,
+                                   device=self._device, auto_reset=False)
+            self._u = torch.zeros(MAX_DRAWS, 1, dtype=torch.float64, device=self._vec.device)
+            self._u_host = torch.zeros(MAX_DRAWS, 1, dtype=torch.float64).pin_memory()
+            self._ru = torch.zeros(2, 1, dtype=torch.float64, device=self._vec.device)
+        return self._vec
+
+    def normalize_action(self, action):
+        return {key: action[idx] * self.scale_ranges[key] + self.scale_centers[key]
+                for idx, key in enumerate(self.bounds)}
+
+    def attach_agent(self, agent):
+        self.agent = agent
+
+    def reset(self):
+        v = self._ensure()
+        if self.episode_counter == 0 or self.agent is None or len(self.agent.memory) < 10:
+            u0 = random.random()   # random.uniform(0, x) == 0 + x*random()
+            u1 = random.random()
+            self._ru.copy_(torch.tensor([[u0], [u1]], dtype=torch.float64))
+            v.reset(reset_u=self._ru)
+        else:
+            samples = random.sample(self.agent.memory.buffer, 10)
+            states = torch.tensor(np.stack([np.asarray(s[0], np.float32) for s in samples]), device=v.device)
+            idx = torch.arange(10, dtype=torch.int64, device=v.device).view(1, 10)
+            v.reset_from_replay(states, idx)
+        self.step_counter = 0
+        self.episode_counter += 1
+        return v.obs[0].cpu().numpy()
+
+    def step(self, action):
+        v = self._ensure()
+        v.max_steps = int(self.max_steps)
+        if isinstance(action, dict):
+            action = np.array([action[k] for k in L.ACTION_ORDER])
+        a = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, 10)).to(v.device)
+        if self._noise_mode == "reference":
+            st = random.getstate()
+            host = self._u_host.numpy()
+            host[0, 0] = random.uniform(15, 50)
+            for t in range(1, MAX_DRAWS):
+                host[t, 0] = random.uniform(-1, 1)
+            self._u.copy_(self._u_host, non_blocking=True)
+            ns, r, d, info = v.step(a, noise_u=self._u)
+            n_draws = int(info["ticks"][0].item())
+            random.setstate(st)
+            random.uniform(15, 50)
+            for _ in range(n_draws):
+                random.random()
+        else:
+            ns, r, d, info = v.step(a)
+        clipped = np.clip(np.asarray(action, dtype=np.float32), [self.bounds[k][0] for k in L.ACTION_ORDER],
+                          [self.bounds[k][1] for k in L.ACTION_ORDER]).astype(np.float32)
+        act = {k: clipped[i] for i, k in enumerate(L.ACTION_ORDER)}
+        act["target_weight"] = self.target_weight
+        fw = float(info["final_weight"][0].item())
+        tt = float(info["total_time"][0].item())
+        self.step_counter += 1
+        return (ns[0].cpu().numpy(), float(r[0].item()), bool(d[0].item()),
+                {"final_weight": fw, "weight_error": abs(fw - self.target_weight), "total_time": tt, "action": act})
+
+
+class WeightEnv(_ScalarEnvBase):
+    """Drop-in for WeightEnv.WeightEnv (WeightEnv.py:21-588), offline-simulator branch."""
+    _kind = "single"
+
+    def __init__(self, noise="reference", device="cuda", seed=0):
+        super().__init__(K.SINGLE_25KG, noise=noise, device=device, seed=seed)
+
+
+class MultiConditionWeightEnv(_ScalarEnvBase):
+    """Drop-in for MutiConditionEnv.MultiConditionWeightEnv (MutiConditionEnv.py:470-486)."""
+    _kind = "multi"
+
+    def __init__(self, config=None, noise="reference", device="cuda", seed=0):
+        cfg = dict(K.MULTI_CLASS_DEFAULT)
+        if config is not None:
+            for k in ("target_weight", "target_weight_err", "target_time"):
+                cfg[k] = config.get(k, cfg[k])
+            if "bounds" in config:
+                cfg["bounds"] = config["bounds"]
+        super().__init__(cfg, noise=noise, device=device, seed=seed)

@@ -1,0 +1,166 @@
+"""GPU parity of the fused env-step kernel (csrc/env_step.cu, called through the C ABI) against
+(1) fixtures from the unmodified reference and (2) the C oracle on the same Philox noise."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle_lib as O  # noqa: E402  (checker only)
+
+WIDE = {k: (-1e9, 1e9) for k in O.ACTION_ORDER}
+
+
+def _mt_uniform_pm1(rng, n):
+    return np.array([-1.0 + 2.0 * rng.random() for _ in range(n)], np.float64)
+
+
+def test_simulator_golden_bit_exact(golden_dir):
+    """E1: 328 reference runs (incl. stagnation / iteration-cap stops and a reachable medium stage),
+    Mersenne-Twister noise injected from HBM: tick count, total_time and final_weight bit-exact."""
+    import erlfill_b200 as E
+    g = np.load(os.path.join(golden_dir, "sim_golden.npz"))
+    n = len(g["seeds"])
+    rows = int(g["iters"].max()) + 2
+    u = np.zeros((rows, n), np.float64)
+    for i in range(n):
+        rng = random.Random(int(g["seeds"][i]))
+        u[0, i] = 15 + 35 * rng.random()
+        k = int(g["iters"][i]) + 1
+        u[1:1 + k, i] = _mt_uniform_pm1(rng, k)
+    conds = [{"target_weight": int(g["params"][i, 0]), "target_weight_err": 25, "target_time": 2.5, "bounds": WIDE}
+             for i in range(n)]
+    env = E.VecFillEnv(conds, n, kind="multi", cond_id=np.arange(n), auto_reset=False)
+    p = g["params"]
+    # action order: fast_w medium_w slow_w fast_open medium_open slow_open fast_delay medium_delay slow_delay unload
+    act = np.stack([p[:, 1], p[:, 2], p[:, 3], p[:, 7], p[:, 8], p[:, 9], p[:, 4], p[:, 5], p[:, 6], p[:, 10]], 1)
+    env.step(torch.tensor(act, dtype=torch.float32, device="cuda"), noise_u=torch.tensor(u, device="cuda"))
+    torch.cuda.synchronize()
+    assert np.array_equal(env.ticks.cpu().numpy(), g["iters"])
+    assert np.array_equal(env.total_time.cpu().numpy(), g["total_time"])
+    assert np.array_equal(env.final_weight.cpu().numpy(), g["final_weight"])
+    assert int(env.tick_sum.item()) == int(g["iters"].sum())
+
+
+def test_dropin_env_episodes_match_reference(golden_dir):
+    """E2/E3/E4 through the N=1 drop-in classes: seeded CPython `random` stream, whole episodes with
+    clipping, on-bound actions, both reward branches, done by step cap and by mean(recent_errors)<25."""
+    import erlfill_b200 as E
+    g = np.load(os.path.join(golden_dir, "env_golden.npz"))
+    B = json.loads(str(g["bounds_json"]))
+    n_f32 = n_done = 0
+    for key in g["runs"]:
+        name = str(g[key + "_name"])
+        if str(g[key + "_kind"]) == "single":
+            env = E.WeightEnv()
+        else:
+            cfg = {k: B[name][k] for k in ("target_weight", "target_weight_err", "target_time")}
+            if name != "multi_default":
+                cfg["bounds"] = {k: tuple(v) for k, v in B[name]["bounds"].items()}
+            env = E.MultiConditionWeightEnv(cfg)
+        env.max_steps = int(g[key + "_max_steps"])
+        random.seed(int(g[key + "_seed"]))
+        ri = 0
+        A = g[key + "_actions"]
+        for t in range(len(A)):
+            if g[key + "_reset_before"][t]:
+                s0 = env.reset()
+                assert s0.dtype == np.float32 and np.array_equal(s0, g[key + "_reset_state"][ri]), (key, t)
+                ri += 1
+            ns, r, d, info = env.step(A[t].copy())
+            assert info["final_weight"] == g[key + "_final_weight"][t], (key, t)
+            assert info["total_time"] == g[key + "_total_time"][t], (key, t)
+            assert info["weight_error"] == g[key + "_weight_error"][t]
+            assert np.array_equal(ns, g[key + "_next_state"][t])
+            assert d == bool(g[key + "_done"][t]), (key, t)
+            ref_r = np.float32(g[key + "_reward"][t])
+            if g[key + "_reward_is_f32"][t]:
+                n_f32 += 1
+                assert np.float32(r) == ref_r, (key, t, r, ref_r)
+            else:   # binary64 branch: device tanh vs libm tanh may differ in the last binary64 bit
+                assert abs(np.float32(r) - ref_r) <= np.spacing(np.abs(ref_r)), (key, t, r, ref_r)
+            n_done += int(d)
+    assert n_f32 >= 50 and n_done >= 15
+
+
+@pytest.mark.parametrize("kind,n_env,max_steps", [("multi", 3000, 7), ("single", 1111, 5)])
+def test_philox_batch_matches_oracle(kind, n_env, max_steps):
+    """Philox mode, ragged N (not a multiple of the CTA size), three conditions round-robin, random
+    actions 10 % outside the bounds, auto-reset: every output equals the C oracle's."""
+    import erlfill_b200 as E
+    K = E.conditions
+    cond_dicts = list(K.EXPERIMENT_3.values()) if kind == "multi" else [K.SINGLE_25KG]
+    seed, base = 0x1234ABCD5678, 777
+    env = E.VecFillEnv(cond_dicts, n_env, kind=kind, max_steps=max_steps, seed=seed, env_id_base=base)
+    oc = [O.make_condition(c["target_weight"], c["target_weight_err"], c["target_time"], c["bounds"]) for c in cond_dicts]
+    ref = O.BatchEnv(O.ENV_MULTI if kind == "multi" else O.ENV_SINGLE, oc, n_env, max_steps=max_steps, seed=seed,
+                     env_id_base=base)
+    rng = np.random.RandomState(0)
+    lo = np.array([[c["bounds"][k][0] for k in O.ACTION_ORDER] for c in cond_dicts])
+    hi = np.array([[c["bounds"][k][1] for k in O.ACTION_ORDER] for c in cond_dicts])
+    cid = (base + np.arange(n_env)) % len(cond_dicts)
+    total = 0
+    for step in range(2 * max_steps + 3):
+        span = hi[cid] - lo[cid]
+        a = (lo[cid] - 0.1 * span + rng.uniform(0, 1, (n_env, 10)) * 1.2 * span).astype(np.float32)
+        ns, r, d, info = env.step(torch.tensor(a, device="cuda"))
+        total += ref.step(a, step)
+        torch.cuda.synchronize()
+        assert np.array_equal(info["ticks"].cpu().numpy(), ref.ticks), step
+        assert np.array_equal(info["final_weight"].cpu().numpy(), ref.final_weight), step
+        assert np.array_equal(info["total_time"].cpu().numpy(), ref.total_time), step
+        assert np.array_equal(ns.cpu().numpy(), ref.next_state), step
+        assert np.array_equal(d.cpu().numpy(), ref.done), step
+        assert np.array_equal(env.obs.cpu().numpy(), ref.obs), step
+        rr = r.cpu().numpy()
+        assert np.all(np.abs(rr - ref.reward) <= np.spacing(np.abs(ref.reward))), step
+        assert (rr != ref.reward).mean() < 0.01
+    assert int(env.tick_sum.item()) == total
+    assert int(env.episode_counter.sum().item()) >= 2 * n_env
+
+
+def test_full_size_properties():
+    """Config-3 size (65,536 envs): determinism, shard invariance (two half-shards with env_id_base
+    equal one full batch) and tick accounting."""
+    import erlfill_b200 as E
+    K = E.conditions
+    conds = list(K.EXPERIMENT_3.values())
+    n = 65536
+    g = torch.Generator(device="cpu").manual_seed(1)
+    lo = torch.tensor([[c["bounds"][k][0] for k in O.ACTION_ORDER] for c in conds], dtype=torch.float32)
+    hi = torch.tensor([[c["bounds"][k][1] for k in O.ACTION_ORDER] for c in conds], dtype=torch.float32)
+    cid = torch.arange(n) % 3
+    a = (lo[cid] + torch.rand(n, 10, generator=g) * (hi[cid] - lo[cid])).cuda()
+
+    def run(n_env, base, actions):
+        env = E.VecFillEnv(conds, n_env, kind="multi", seed=42, env_id_base=base)
+        env.step(actions.contiguous())
+        torch.cuda.synchronize()
+        return env
+
+    full = run(n, 0, a)
+    again = run(n, 0, a)
+    assert torch.equal(full.final_weight, again.final_weight) and torch.equal(full.reward, again.reward)
+    h0, h1 = run(n // 2, 0, a[: n // 2]), run(n // 2, n // 2, a[n // 2:])
+    assert torch.equal(torch.cat([h0.final_weight, h1.final_weight]), full.final_weight)
+    assert torch.equal(torch.cat([h0.reward, h1.reward]), full.reward)
+    assert int(full.tick_sum.item()) == int(full.ticks.sum().item())
+    t = full.ticks.float()
+    assert 600 < t.min() and t.max() <= 5001 and 900 < t.mean() < 1800
+    # spot-check 64 envs against the oracle
+    idx = np.linspace(0, n - 1, 64).astype(int)
+    for i in idx:
+        c = conds[i % 3]
+        oc = O.make_condition(c["target_weight"], c["target_weight_err"], c["target_time"], c["bounds"])
+        o = O.StepOut()
+        st = O.EnvState()
+        import ctypes as C
+        act = (C.c_float * 10)(*a[i].cpu().numpy().tolist())
+        O.lib().orc_env_step_philox(0, C.byref(oc), C.byref(st), 100, act, C.c_uint32(42), C.c_uint32(0),
+                                    C.c_uint32(int(i)), C.c_uint32(0), C.byref(o))
+        assert o.final_weight == float(full.final_weight[i].item())
+        assert o.ticks == int(full.ticks[i].item())

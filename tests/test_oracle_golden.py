@@ -173,3 +173,14 @@ def test_philox_known_answer():
     assert O.philox(0, 0, 0, 0, 0) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     assert O.philox(0xffffffffffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff) == \
         [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+
+
+def test_python_port_matches_golden(golden_dir):
+    from oracle import py_port
+    g = np.load(os.path.join(golden_dir, "sim_golden.npz"))
+    names = ["target_weight", "fast_weight", "medium_weight", "slow_weight", "fast_delay", "medium_delay",
+             "slow_delay", "fast_opening", "medium_opening", "slow_opening", "unload_delay"]
+    for i in range(0, len(g["seeds"]), 7):
+        p = {k: int(v) for k, v in zip(names, g["params"][i])}
+        n, tt, fw = py_port.simulate_run(p, random.Random(int(g["seeds"][i])))
+        assert (n, tt, fw) == (int(g["iters"][i]), g["total_time"][i], g["final_weight"][i])
