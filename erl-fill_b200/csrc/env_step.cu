@@ -38,7 +38,7 @@ thread_local int g_last_cuda_error = 0;
 // peak observed 9200) falls back to arithmetic evaluated on the device.
 // ------------------------------------------------------------------------------------------
 constexpr int kTabGlobal = 4096;
-constexpr int kTabShared = 256;
+constexpr int kTabShared = 512;
 __device__ double2 g_motor_tab[kTabGlobal];
 
 static std::mutex g_tab_mutex;
@@ -62,18 +62,6 @@ static int ensure_motor_table() {
     ERLFILL_CUDA_TRY(cudaMemcpyToSymbol(g_motor_tab, host_tab, sizeof(host_tab)));
     g_tab_ready[dev] = true;
     return ERLFILL_OK;
-}
-
-__device__ __forceinline__ double2 motor_entry(const double2 *s_tab, int k) {
-    if ((unsigned)k < (unsigned)kTabShared) return s_tab[k];
-    if ((unsigned)k < (unsigned)kTabGlobal) return g_motor_tab[k];
-    // out-of-table: evaluate on the device (dt*dt instead of libm pow; see header comment)
-    const double speed = 100.0 * (double)k;
-    const double dt = speed > 0 ? __ddiv_rn(speed, 100000.0) : 0.0;
-    double2 e;
-    e.x = __dmul_rn(50000.0, __dmul_rn(dt, dt));
-    e.y = __ddiv_rn(fabs(speed), 1000.0);
-    return e;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -217,65 +205,84 @@ __device__ __forceinline__ float2 reset_state_cold(const erlfill_condition &c, d
 }
 
 // ------------------------------------------------------------------------------------------
-// The tick loop.  State per thread: w, open, prev (binary64), k = speed/100 (int), dir (+1/-1),
-// target opening, counters.  `opu` = 1.0 + uniform(-1,1).
+// The tick loop.
+//
+// Per-lane state: w, open, prev (binary64), k = speed/100 (int), the current target opening and the
+// deceleration distance dd(k).  Every lane is in one of two phases:
+//   MOVING  the motor is travelling to a new target: full branch-free motor model per tick
+//   HOLD    |open - target| <= 1 has snapped open to target with speed 0 (about 85 % of all ticks):
+//           the motor model is the identity, so a tick is  w += target * (1 + u)  plus the stage test
+// A warp alternates between a moving loop and a hold loop; both consume the noise in blocks of four
+// ticks (one Philox-4x32-10 call), and lanes are re-aligned to a block boundary at the top of the
+// outer loop so that the generator runs warp-synchronously.  The arithmetic of every tick is the
+// reference's, in the reference's order (VirtualWeightController.py:85-125, 172-229).
 // ------------------------------------------------------------------------------------------
 struct SimParams {
     double fast_w, medium_w, slow_w;
     double fast_pos, medium_pos, slow_pos;
     int fast_delay, medium_delay, slow_delay;
+    bool sane;      // all three opening targets >= 0: the hold phase can be used
 };
 
-struct SimState {
-    double w, open, prev, target, step_mag, dd;
-    int k, tick, iter, nochg;
-    bool neg_dir;
+struct Lane {
+    double w, open, prev, target, dd;
+    int k, nochg;
 };
 
-// One tick.  Returns true when the run has finished.
+__device__ __forceinline__ long long dbits(double x) { return __double_as_longlong(x); }
+
+__device__ __noinline__ double2 motor_entry_slow(int k) {
+    if ((unsigned)k < (unsigned)kTabGlobal) return g_motor_tab[k];
+    // outside the table: evaluate on the device (dt*dt instead of libm pow; see the table comment)
+    const double speed = 100.0 * (double)k;
+    const double dt = speed > 0 ? __ddiv_rn(speed, 100000.0) : 0.0;
+    double2 e;
+    e.x = __dmul_rn(50000.0, __dmul_rn(dt, dt));
+    e.y = __ddiv_rn(speed, 1000.0);          // signed: a negative speed moves against `dir`
+    return e;
+}
+
+// One full tick (motor + weight + stage + safety stops).  n_after = number of draws consumed
+// including this one.  Returns true when the run has finished.
 template <bool kFirst>
-__device__ __forceinline__ bool sim_tick(SimState &s, const SimParams &p, const double2 *s_tab, double opu,
-                                         double sysdelay) {
-    s.tick += 1;                                                        // :181
-    // motor_simulation(target): :92-113.  s.dd is decelerate_distance for the current speed.
+__device__ __forceinline__ bool generic_tick(Lane &s, const SimParams &p, const double2 *s_tab, double opu,
+                                             double sysdelay, int n_after, int &delay) {
+    // motor_simulation(target): VirtualWeightController.py:92-113
     const double diff = s.open - s.target;
-    if (fabs(diff) > 1.0) {
-        bool accel;
-        if (s.open < s.target) { accel = s.open < s.target - s.dd; s.neg_dir = false; }
-        else                   { accel = s.open > s.dd;            s.neg_dir = true; }
-        s.k += accel ? 50 : -1;                                         // +5000 / -100
-    } else {
-        s.k = 0;
-        s.open = s.target;
-    }
-    const double2 e = motor_entry(s_tab, s.k);
+    const long long db = dbits(diff);
+    const bool far = (db & 0x7fffffffffffffffLL) > 0x3ff0000000000000LL;   // abs(open - target) > 1
+    const bool fwd = db < 0;                                               // open < target
+    const bool p1 = s.open < s.target - s.dd;
+    const bool p2 = s.open > s.dd;
+    const bool accel = fwd ? p1 : p2;
+    int k = s.k + (accel ? 50 : -1);                                       // += 5000 / -= 100
+    k = far ? k : 0;
+    const double base = far ? s.open : s.target;
+    double2 e;
+    if ((unsigned)k < (unsigned)kTabShared) e = s_tab[k];
+    else e = motor_entry_slow(k);
+    s.k = k;
     s.dd = e.x;
-    // (speed*dir)/1000: the quotient of the negated product equals the negated quotient
-    double stp = e.y;
-    if (s.k < 0) stp = -stp;
-    s.open = s.open + (s.neg_dir ? -stp : stp);
+    s.open = base + (fwd ? e.y : -e.y);                                    // += (speed*dir)/1000
     // weight_simulation(open): :122-125
-    s.w = __dadd_rn(s.w, __dmul_rn(s.open, opu));
-    if (s.w < 0) s.w = 0.0;
-    // stage selection :191-213; the one-time delay is taken on the first tick only (the flag is
-    // set once and never cleared), whichever stage that tick lands in
-    if (s.w < p.fast_w) {
-        s.target = p.fast_pos;
-        if (kFirst) { s.tick += p.fast_delay; s.w = __dadd_rn(s.w, __dmul_rn(s.target, sysdelay)); }
-    } else if (s.w < p.medium_w) {
-        s.target = p.medium_pos;
-        if (kFirst) { s.tick += p.medium_delay; s.w = __dadd_rn(s.w, __dmul_rn(s.target, sysdelay)); }
-    } else if (s.w < p.slow_w) {
-        s.target = p.slow_pos;
-        if (kFirst) { s.tick += p.slow_delay; s.w = __dadd_rn(s.w, __dmul_rn(s.target, sysdelay)); }
-    } else {
-        return true;
+    double w = __dadd_rn(s.w, __dmul_rn(s.open, opu));
+    w = (w < 0) ? 0.0 : w;
+    // stage selection :191-213 (w is never -0.0, so the tests are exact on the bit patterns too)
+    const bool lf = w < p.fast_w, lm = w < p.medium_w, ls = w < p.slow_w;
+    s.target = lf ? p.fast_pos : (lm ? p.medium_pos : p.slow_pos);
+    if (kFirst) {
+        // the one-time stage delay is taken on the first tick only (the flag is never cleared)
+        if (lf | lm | ls) {
+            delay = lf ? p.fast_delay : (lm ? p.medium_delay : p.slow_delay);
+            w = __dadd_rn(w, __dmul_rn(s.target, sysdelay));
+        }
     }
-    // safety stops :216-229 (the 10 s wall-clock stop :230-233 has no meaning on a frozen clock)
-    s.iter += 1;
-    s.nochg = (fabs(s.w - s.prev) < 0.01) ? s.nochg + 1 : 0;
-    s.prev = s.w;
-    return (s.iter > ERLFILL_MAX_ITER) | (s.nochg > ERLFILL_NOCHANGE_LIMIT);
+    s.w = w;
+    if (!(lf | lm | ls)) return true;                                      // normal finish
+    // safety stops :216-229 (iteration == n_after here)
+    s.nochg = (fabs(w - s.prev) < 0.01) ? s.nochg + 1 : 0;
+    s.prev = w;
+    return (n_after > ERLFILL_MAX_ITER) | (s.nochg > ERLFILL_NOCHANGE_LIMIT);
 }
 
 // 1.0 + (-1.0 + 2*U) == x * 2^-31 exactly for U = x * 2^-32: place x in the top mantissa bits of
@@ -284,50 +291,113 @@ __device__ __forceinline__ double opu_from_u32(uint32_t x) {
     return __hiloint2double((int)(0x40000000u | (x >> 12)), (int)(x << 20)) - 2.0;
 }
 
-template <bool kInjected>
-__device__ __forceinline__ SimResult simulate(const SimParams &p, const double2 *s_tab, double sysdelay,
-                                              uint32_t k0, uint32_t k1, uint32_t gid, uint32_t step_idx,
-                                              const double *u_col, int n_env, int noise_rows) {
-    SimState s;
-    s.w = 0.0; s.open = 0.0; s.prev = 0.0; s.target = p.fast_pos; s.dd = 0.0; s.step_mag = 0.0;
-    s.k = 0; s.tick = 0; s.iter = 0; s.nochg = 0; s.neg_dir = false;
-    int draws = 0;
-    bool fin;
-    if (kInjected) {
-        // row 1+t of the [rows][n_env] noise matrix is tick t's uniform(-1,1)
-        auto u_at = [&](int t) -> double {
-            return (1 + t) < noise_rows ? __ldg(u_col + (size_t)(1 + t) * n_env) : 0.0;
-        };
-        fin = sim_tick<true>(s, p, s_tab, 1.0 + u_at(0), sysdelay);
-        draws = 1;
-        while (!fin) {
-            fin = sim_tick<false>(s, p, s_tab, 1.0 + u_at(draws), sysdelay);
-            draws += 1;
+struct PhiloxNoise {
+    uint32_t k0, k1, gid, step_idx;
+    __device__ __forceinline__ void fetch(double (&o)[4], int block) const {
+        const uint4 r = philox4x32_10(k0, k1, gid, step_idx, (uint32_t)block, STREAM_TICK);
+        o[0] = opu_from_u32(r.x); o[1] = opu_from_u32(r.y); o[2] = opu_from_u32(r.z); o[3] = opu_from_u32(r.w);
+    }
+};
+struct InjectedNoise {
+    const double *u_col;   // column of this env in the [rows][n_env] matrix; row 1+t = tick t
+    int n_env, rows;
+    __device__ __forceinline__ void fetch(double (&o)[4], int block) const {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = 1 + 4 * block + j;
+            o[j] = 1.0 + (row < rows ? __ldg(u_col + (size_t)row * n_env) : 0.0);
         }
-    } else {
-        uint4 r = philox4x32_10(k0, k1, gid, step_idx, 0u, STREAM_TICK);
-        fin = sim_tick<true>(s, p, s_tab, opu_from_u32(r.x), sysdelay);
-        draws = 1;
-        if (!fin) { fin = sim_tick<false>(s, p, s_tab, opu_from_u32(r.y), sysdelay); draws = 2; }
-        if (!fin) { fin = sim_tick<false>(s, p, s_tab, opu_from_u32(r.z), sysdelay); draws = 3; }
-        if (!fin) { fin = sim_tick<false>(s, p, s_tab, opu_from_u32(r.w), sysdelay); draws = 4; }
-        uint32_t blk = 1;
-        while (!fin) {
-            r = philox4x32_10(k0, k1, gid, step_idx, blk, STREAM_TICK);
-            ++blk;
-            fin = sim_tick<false>(s, p, s_tab, opu_from_u32(r.x), sysdelay); draws += 1;
-            if (fin) break;
-            fin = sim_tick<false>(s, p, s_tab, opu_from_u32(r.y), sysdelay); draws += 1;
-            if (fin) break;
-            fin = sim_tick<false>(s, p, s_tab, opu_from_u32(r.z), sysdelay); draws += 1;
-            if (fin) break;
-            fin = sim_tick<false>(s, p, s_tab, opu_from_u32(r.w), sysdelay); draws += 1;
+    }
+};
+
+__device__ __forceinline__ bool in_hold(const Lane &s, const SimParams &p) {
+    return p.sane & (s.k == 0) & (dbits(s.open) == dbits(s.target));
+}
+
+// `valid` == false lanes only take part in the warp votes.
+template <class NoiseT>
+__device__ __forceinline__ SimResult simulate(const SimParams &p, const double2 *s_tab, double sysdelay,
+                                              const NoiseT &nz, bool valid) {
+    Lane s;
+    s.w = 0.0; s.open = 0.0; s.prev = 0.0; s.target = p.fast_pos; s.dd = 0.0; s.k = 0; s.nochg = 0;
+    double o[4] = {0.0, 0.0, 0.0, 0.0};
+    int n = 0, delay = 0;
+    bool fin = !valid;
+    if (!fin) {
+        nz.fetch(o, 0);
+        fin = generic_tick<true>(s, p, s_tab, o[0], sysdelay, 1, delay);
+        n = 1;
+    }
+    for (;;) {
+        if (__all_sync(0xffffffffu, fin)) break;
+        // (1) re-align to a noise-block boundary with the values still cached in o[]
+        while (!fin && (n & 3)) {
+            const int j = n & 3;
+            const double opu = j == 1 ? o[1] : (j == 2 ? o[2] : o[3]);
+            n += 1;
+            fin = generic_tick<false>(s, p, s_tab, opu, sysdelay, n, delay);
+        }
+        // (2) moving phase, four ticks per noise block
+        while (!fin && !in_hold(s, p)) {
+            nz.fetch(o, n >> 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!fin) {
+                    n += 1;
+                    fin = generic_tick<false>(s, p, s_tab, o[j], sysdelay, n, delay);
+                }
+            }
+        }
+        // (3) hold phase: open == target >= 0, speed 0, so  w += target * opu  and w never decreases;
+        //     the lane stays in its stage exactly while w < (that stage's threshold)
+        if (!fin && in_hold(s, p)) {
+            const double tgt = s.target;
+            double w = s.w;
+            const bool lf = w < p.fast_w, lm = w < p.medium_w;
+            const long long thr = dbits(lf ? p.fast_w : (lm ? p.medium_w : p.slow_w));
+            bool leave = false;
+            while (!leave) {
+                nz.fetch(o, n >> 2);
+                // Speculate on the whole 4-tick block: w never decreases here, so the stage test on
+                // the last value covers all four; an increment >= 0.02 makes |w - w_old| > 0.01
+                // (no stagnation) certain.  Anything else replays the block tick by tick below.
+                const double i0 = __dmul_rn(tgt, o[0]), i1 = __dmul_rn(tgt, o[1]);
+                const double i2 = __dmul_rn(tgt, o[2]), i3 = __dmul_rn(tgt, o[3]);
+                const double w1 = __dadd_rn(w, i0), w2 = __dadd_rn(w1, i1);
+                const double w3 = __dadd_rn(w2, i2), w4 = __dadd_rn(w3, i3);
+                const int imin = min(min(__double2hiint(i0), __double2hiint(i1)),
+                                     min(__double2hiint(i2), __double2hiint(i3)));
+                if ((dbits(w4) < thr) & (imin > 0x3F947AE1) & (n + 4 <= ERLFILL_MAX_ITER)) {
+                    w = w4;
+                    n += 4;
+                    s.nochg = 0;
+                    continue;
+                }
+#pragma unroll 1
+                for (int j = 0; j < 4 && !leave; ++j) {
+                    const double w_old = w;
+                    const double opu = j == 0 ? o[0] : (j == 1 ? o[1] : (j == 2 ? o[2] : o[3]));
+                    w = __dadd_rn(w, __dmul_rn(tgt, opu));
+                    n += 1;
+                    if (dbits(w) >= thr) {
+                        // left the stage: full stage evaluation (:191-213), then hand over to (1)/(2)
+                        const bool f = w < p.fast_w, m = w < p.medium_w, sl = w < p.slow_w;
+                        s.target = f ? p.fast_pos : (m ? p.medium_pos : p.slow_pos);
+                        leave = true;
+                        if (!(f | m | sl)) { fin = true; break; }
+                    }
+                    s.nochg = (fabs(w - w_old) < 0.01) ? s.nochg + 1 : 0;
+                    if ((n > ERLFILL_MAX_ITER) | (s.nochg > ERLFILL_NOCHANGE_LIMIT)) { fin = true; leave = true; }
+                }
+            }
+            s.w = w;
+            s.prev = w;
         }
     }
     SimResult res;
     res.final_weight = s.w;
-    res.tick = s.tick;
-    res.draws = draws;
+    res.tick = n + delay;
+    res.draws = n;
     return res;
 }
 
@@ -362,43 +432,51 @@ __global__ void __launch_bounds__(kMaxBlock) env_step_kernel(const StepArgs a) {
 
     const int i = block_base + tid;
     const bool valid = i < n_env;
-    int draws = 0;
-    if (valid) {
-        const uint32_t gid = a.env.env_id_base + (uint32_t)i;
-        const int cid = a.env.d_cond_id ? a.env.d_cond_id[i] : (int)(gid % (uint32_t)a.env.n_cond);
-        const erlfill_condition c = a.env.d_cond[cid];
-        const uint32_t k0 = (uint32_t)a.env.seed, k1 = (uint32_t)(a.env.seed >> 32);
+    const int ic = valid ? i : n_env - 1;                    // padding lanes mirror the last env, never store
+    const uint32_t gid = a.env.env_id_base + (uint32_t)ic;
+    const int cid = a.env.d_cond_id ? a.env.d_cond_id[ic] : (int)(gid % (uint32_t)a.env.n_cond);
+    const erlfill_condition c = a.env.d_cond[cid];
+    const uint32_t k0 = (uint32_t)a.env.seed, k1 = (uint32_t)(a.env.seed >> 32);
 
-        // clip (np.clip == min(max(a, lo), hi)) and int() truncation toward zero
-        float clipped[ERLFILL_ACTION_DIM];
+    // clip (np.clip == min(max(a, lo), hi)) and int() truncation toward zero
+    float clipped[ERLFILL_ACTION_DIM];
 #pragma unroll
-        for (int j = 0; j < ERLFILL_ACTION_DIM; ++j) {
-            float v = s_act[tid * ERLFILL_ACTION_DIM + j];
-            v = v < c.lo[j] ? c.lo[j] : v;
-            v = v > c.hi[j] ? c.hi[j] : v;
-            clipped[j] = v;
-        }
-        SimParams p;
-        p.fast_w = (double)(int)clipped[0];
-        p.medium_w = (double)(int)clipped[1];
-        p.slow_w = (double)(int)clipped[2];
-        p.fast_pos = (double)(int)clipped[3];
-        p.medium_pos = (double)(int)clipped[4];
-        p.slow_pos = (double)(int)clipped[5];
-        p.fast_delay = (int)clipped[6];
-        p.medium_delay = (int)clipped[7];
-        p.slow_delay = (int)clipped[8];
-        const int unload_delay = (int)clipped[9];
+    for (int j = 0; j < ERLFILL_ACTION_DIM; ++j) {
+        float v = s_act[(valid ? tid : 0) * ERLFILL_ACTION_DIM + j];
+        v = v < c.lo[j] ? c.lo[j] : v;
+        v = v > c.hi[j] ? c.hi[j] : v;
+        clipped[j] = v;
+    }
+    SimParams p;
+    p.fast_w = (double)(int)clipped[0];
+    p.medium_w = (double)(int)clipped[1];
+    p.slow_w = (double)(int)clipped[2];
+    p.fast_pos = (double)(int)clipped[3];
+    p.medium_pos = (double)(int)clipped[4];
+    p.slow_pos = (double)(int)clipped[5];
+    p.fast_delay = (int)clipped[6];
+    p.medium_delay = (int)clipped[7];
+    p.slow_delay = (int)clipped[8];
+    p.sane = (p.fast_pos >= 0) & (p.medium_pos >= 0) & (p.slow_pos >= 0);
+    const int unload_delay = (int)clipped[9];
 
-        // noise for this (env, step): misc lanes = {system_delay, reset u0, reset u1, -}
-        const uint4 misc = philox4x32_10(k0, k1, gid, a.step_idx, 0u, STREAM_MISC);
-        double sysdelay;
-        if (kInjected) sysdelay = a.noise_rows > 0 ? __ldg(a.d_u + i) : 0.0;
-        else sysdelay = 15.0 + 35.0 * u32_to_unit(misc.x);               // uniform(15, 50): :137
-
-        const SimResult sim = simulate<kInjected>(p, s_tab, sysdelay, k0, k1, gid, a.step_idx,
-                                                  kInjected ? a.d_u + i : nullptr, n_env, a.noise_rows);
-        draws = sim.draws;
+    // noise for this (env, step): misc lanes = {system_delay, reset u0, reset u1, -}
+    const uint4 misc = philox4x32_10(k0, k1, gid, a.step_idx, 0u, STREAM_MISC);
+    double sysdelay;
+    SimResult sim;
+    if (kInjected) {
+        sysdelay = a.noise_rows > 0 ? __ldg(a.d_u + ic) : 0.0;
+        InjectedNoise nz;
+        nz.u_col = a.d_u + ic; nz.n_env = n_env; nz.rows = a.noise_rows;
+        sim = simulate(p, s_tab, sysdelay, nz, valid);
+    } else {
+        sysdelay = 15.0 + 35.0 * u32_to_unit(misc.x);                 // uniform(15, 50): :137
+        PhiloxNoise nz;
+        nz.k0 = k0; nz.k1 = k1; nz.gid = gid; nz.step_idx = a.step_idx;
+        sim = simulate(p, s_tab, sysdelay, nz, valid);
+    }
+    const int draws = valid ? sim.draws : 0;
+    if (valid) {
         const double total_time = (double)(sim.tick + unload_delay) / 1000.0;   // :239
         const double fw = sim.final_weight;
 

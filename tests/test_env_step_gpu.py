@@ -150,7 +150,7 @@ def test_full_size_properties():
     assert torch.equal(torch.cat([h0.reward, h1.reward]), full.reward)
     assert int(full.tick_sum.item()) == int(full.ticks.sum().item())
     t = full.ticks.float()
-    assert 600 < t.min() and t.max() <= 5001 and 900 < t.mean() < 1800
+    assert 200 < t.min() and t.max() <= 5001 and 900 < t.mean() < 1800
     # spot-check 64 envs against the oracle
     idx = np.linspace(0, n - 1, 64).astype(int)
     for i in idx:
