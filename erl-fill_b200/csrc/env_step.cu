@@ -293,9 +293,16 @@ __device__ __forceinline__ double opu_from_u32(uint32_t x) {
 
 struct PhiloxNoise {
     uint32_t k0, k1, gid, step_idx;
-    __device__ __forceinline__ void fetch(double (&o)[4], int block) const {
-        const uint4 r = philox4x32_10(k0, k1, gid, step_idx, (uint32_t)block, STREAM_TICK);
+    __device__ __forceinline__ void fetch_raw(uint4 &r, int block) const {
+        r = philox4x32_10(k0, k1, gid, step_idx, (uint32_t)block, STREAM_TICK);
+    }
+    __device__ __forceinline__ void convert(double (&o)[4], const uint4 &r) const {
         o[0] = opu_from_u32(r.x); o[1] = opu_from_u32(r.y); o[2] = opu_from_u32(r.z); o[3] = opu_from_u32(r.w);
+    }
+    __device__ __forceinline__ void fetch(double (&o)[4], int block) const {
+        uint4 r;
+        fetch_raw(r, block);
+        convert(o, r);
     }
 };
 struct InjectedNoise {
@@ -308,6 +315,9 @@ struct InjectedNoise {
             o[j] = 1.0 + (row < rows ? __ldg(u_col + (size_t)row * n_env) : 0.0);
         }
     }
+    // the "raw" form of a block is just its index; the loads happen in convert()
+    __device__ __forceinline__ void fetch_raw(uint4 &r, int block) const { r.x = (uint32_t)block; }
+    __device__ __forceinline__ void convert(double (&o)[4], const uint4 &r) const { fetch(o, (int)r.x); }
 };
 
 __device__ __forceinline__ bool in_hold(const Lane &s, const SimParams &p) {
@@ -356,21 +366,33 @@ __device__ __forceinline__ SimResult simulate(const SimParams &p, const double2 
             const bool lf = w < p.fast_w, lm = w < p.medium_w;
             const long long thr = dbits(lf ? p.fast_w : (lm ? p.medium_w : p.slow_w));
             bool leave = false;
+            uint4 raw;
+            nz.fetch_raw(raw, n >> 2);
             while (!leave) {
-                nz.fetch(o, n >> 2);
+                nz.convert(o, raw);
+                // prefetch the next block's noise: independent of the weight chain below, so the
+                // generator's serial rounds overlap the FP64 adds even with one warp per scheduler
+                nz.fetch_raw(raw, (n >> 2) + 1);
                 // Speculate on the whole 4-tick block: w never decreases here, so the stage test on
-                // the last value covers all four; an increment >= 0.02 makes |w - w_old| > 0.01
-                // (no stagnation) certain.  Anything else replays the block tick by tick below.
+                // the last value covers all four.  An increment >= 0.02 makes |w - w_old| > 0.01
+                // certain; smaller ones get the exact test.  Stage exits, the iteration cap and a
+                // stagnation count near its limit replay the block tick by tick below.
                 const double i0 = __dmul_rn(tgt, o[0]), i1 = __dmul_rn(tgt, o[1]);
                 const double i2 = __dmul_rn(tgt, o[2]), i3 = __dmul_rn(tgt, o[3]);
                 const double w1 = __dadd_rn(w, i0), w2 = __dadd_rn(w1, i1);
                 const double w3 = __dadd_rn(w2, i2), w4 = __dadd_rn(w3, i3);
                 const int imin = min(min(__double2hiint(i0), __double2hiint(i1)),
                                      min(__double2hiint(i2), __double2hiint(i3)));
-                if ((dbits(w4) < thr) & (imin > 0x3F947AE1) & (n + 4 <= ERLFILL_MAX_ITER)) {
+                if ((dbits(w4) < thr) & (n + 4 <= ERLFILL_MAX_ITER) & (s.nochg + 4 <= ERLFILL_NOCHANGE_LIMIT)) {
+                    int nc = 0;
+                    if (imin <= 0x3F947AE1) {
+                        const bool c0 = fabs(w1 - w) < 0.01, c1 = fabs(w2 - w1) < 0.01;
+                        const bool c2 = fabs(w3 - w2) < 0.01, c3 = fabs(w4 - w3) < 0.01;
+                        nc = c3 ? (c2 ? (c1 ? (c0 ? s.nochg + 4 : 3) : 2) : 1) : 0;
+                    }
+                    s.nochg = nc;
                     w = w4;
                     n += 4;
-                    s.nochg = 0;
                     continue;
                 }
 #pragma unroll 1

@@ -274,9 +274,168 @@ def gen_emotion():
     print("emotion: 64 updates, final", em.current_emotion)
 
 
+# ----------------------------------------------------------------------------------------
+def _build_agent(seed=0):
+    """Reference construction order (experiment_runner.py:481-484,508-510): env, DDPGAgent, EmotionModule."""
+    ref_shim.install()
+    import torch
+    import MutiConditionEnv as M
+    import ddpg_agent as D
+    import EmotionModule as E
+    torch.manual_seed(seed)
+    cfg = BOUNDS["variant_25kg"]
+    env = M.MultiConditionWeightEnv({**{k: cfg[k] for k in ("target_weight", "target_weight_err", "target_time")},
+                                     "bounds": dict(cfg["bounds"])})
+    agent = D.DDPGAgent(env, device="cpu", use_td_error=True)
+    agent.emotion = E.EmotionModule(device="cpu")
+    env.attach_agent(agent)
+    return env, agent
+
+
+def _sd(module, prefix):
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def _replay_masks(seed, shapes_p):
+    """Re-draw, with torch's CPU generator, the keep-masks at::dropout draws for the given shapes in
+    the given order: empty_like(x).bernoulli_(1 - p)."""
+    import torch
+    torch.manual_seed(seed)
+    return [torch.empty(shape).bernoulli_(1 - p) for shape, p in shapes_p]
+
+
+def gen_nets():
+    """A1 / U1 / M2 vectors from the real nn.Modules, eval() and train() (dropout masks replayed)."""
+    import torch
+    env, agent = _build_agent(0)
+    out = {}
+    out.update(_sd(agent.actor, "actor."))
+    out.update(_sd(agent.critic, "critic."))
+    out.update(_sd(agent.emotion.transformer, "trans."))
+    g = torch.Generator().manual_seed(5)
+    B = 48
+    state = torch.rand(B, 2, generator=g) * 5
+    emotion = torch.rand(B, 3, generator=g)
+    emotion[0] = torch.tensor([0.5, 0.5, 0.0])
+    action = torch.rand(B, 10, generator=g) * 2 - 1
+    seqs = torch.rand(12, 20, 3, generator=g)
+    seqs[0, :15] = seqs[0, 15]                      # front-padded history
+    seq1 = torch.tensor([[[0.5, 0.5, 0.0]]])        # empty history: S = 1
+    seq7 = torch.rand(3, 7, 3, generator=g)         # shorter sequences are legal for the module
+    out.update(state=state.numpy(), emotion=emotion.numpy(), action=action.numpy(), seqs=seqs.numpy(),
+               seq1=seq1.numpy(), seq7=seq7.numpy())
+    tr = agent.emotion.transformer
+    with torch.no_grad():
+        for m in (agent.actor, agent.critic, tr):
+            m.eval()
+        out["actor_eval"] = agent.actor(state, emotion).numpy()
+        out["critic_eval"] = agent.critic(state, action, emotion).numpy()
+        # the fused "fast path" of nn.TransformerEncoder only exists in eval(); the reference never
+        # calls eval(), so the eval golden is taken through the same (slow) code path
+        torch.backends.mha.set_fastpath_enabled(False)
+        out["trans_eval"] = tr(seqs).numpy()
+        out["trans_eval_s1"] = tr(seq1).numpy()
+        out["trans_eval_s7"] = tr(seq7).numpy()
+        for m in (agent.actor, agent.critic, tr):
+            m.train()
+        torch.manual_seed(101)
+        out["actor_train"] = agent.actor(state, emotion).numpy()
+        am = _replay_masks(101, [((B, 128), 0.2), ((B, 128), 0.2)])
+        out["actor_m1"], out["actor_m2"] = am[0].numpy(), am[1].numpy()
+        torch.manual_seed(102)
+        out["critic_train"] = agent.critic(state, action, emotion).numpy()
+        cm = _replay_masks(102, [((B, 256), 0.2), ((B, 256), 0.2)])
+        out["critic_m1"], out["critic_m2"] = cm[0].numpy(), cm[1].numpy()
+        torch.manual_seed(103)
+        nb = seqs.shape[0]
+        out["trans_train"] = tr(seqs).numpy()
+        shapes = []
+        for _ in range(4):
+            # module layout is [S, B, .] (batch_first=False); attention probs are [B, heads, S, S]
+            shapes += [((nb, 4, 20, 20), 0.3), ((20, nb, 32), 0.3), ((20, nb, 2048), 0.3), ((20, nb, 32), 0.3)]
+        tm = _replay_masks(103, shapes)
+        for l in range(4):
+            out[f"trans_attn{l}"] = tm[4 * l].numpy().astype(np.uint8)
+            out[f"trans_d1_{l}"] = tm[4 * l + 1].permute(1, 0, 2).numpy().astype(np.uint8)
+            out[f"trans_ff{l}"] = np.packbits(tm[4 * l + 2].permute(1, 0, 2).numpy().astype(np.uint8), axis=-1)
+            out[f"trans_d2_{l}"] = tm[4 * l + 3].permute(1, 0, 2).numpy().astype(np.uint8)
+    out["meta"] = _meta("A1/U1/M2 forwards of the reference nn.Modules (torch.manual_seed(0) construction)")
+    np.savez_compressed(os.path.join(GOLD, "nets_golden.npz"), **out)
+    print("nets: actor_eval[0]", out["actor_eval"][0][:4], "trans_eval[0]", out["trans_eval"][0],
+          "s1", out["trans_eval_s1"])
+
+
+def gen_learn():
+    """U2-U5 vectors: DDPGAgent.learn() three times on an injected replay buffer, eval-mode networks
+    (dropout off) so the update is deterministic; weights, Adam state, losses and LRs recorded."""
+    import torch
+    env, agent = _build_agent(0)
+    for m in (agent.actor, agent.actor_target, agent.critic, agent.critic_target, agent.emotion.transformer):
+        m.eval()
+    torch.backends.mha.set_fastpath_enabled(False)
+    g = np.random.RandomState(9)
+    B = 128
+    agent.batch_size = B
+    n_buf = 600
+    buf = dict(states=(g.rand(n_buf, 2) * 5).astype(np.float32), actions=(g.rand(n_buf, 10) * 2 - 1).astype(np.float32),
+               rewards=g.uniform(-3000, 6000, n_buf), next_states=(g.rand(n_buf, 2) * 5).astype(np.float32),
+               dones=(g.rand(n_buf) < 0.05), emotions=g.rand(n_buf, 3).astype(np.float32))
+    for i in range(n_buf):
+        agent.memory.buffer.append((buf["states"][i], buf["actions"][i], float(buf["rewards"][i]),
+                                    buf["next_states"][i], bool(buf["dones"][i]), buf["emotions"][i], float("nan")))
+        agent.memory.priorities.append(1e-4)
+    # emotion history so that get_emotion() inside learn() (:466) is a real S=20 call
+    for t in range(25):
+        agent.emotion.update(float(g.uniform(-2000, 4000)), (g.rand(2) - 0.5).astype(np.float32))
+    out = {}
+    out.update(_sd(agent.actor, "a0."))
+    out.update(_sd(agent.critic, "c0."))
+    out.update(_sd(agent.emotion.transformer, "trans."))
+    out["history"] = np.stack([h.numpy() for h in agent.emotion.transformer.history])
+    for k, v in buf.items():
+        out["buf_" + k] = np.asarray(v)
+    agent.train_step = 7
+    np.random.seed(2024)
+    idx_all, closs, aloss, lrs, next_emotions = [], [], [], [], []
+    orig_choice = np.random.choice
+    orig_get = agent.emotion.get_emotion
+
+    def tap_choice(n, size, p=None):
+        r = orig_choice(n, size, p=p)
+        idx_all.append(np.array(r))
+        return r
+
+    def tap_get():
+        e = orig_get()
+        next_emotions.append(np.array(e))
+        return e
+    np.random.choice = tap_choice
+    agent.emotion.get_emotion = tap_get
+    try:
+        for it in range(3):
+            loss = agent.learn()
+            closs.append(loss["critic_loss"]); aloss.append(loss["actor_loss"])
+            lrs.append((agent.critic_optim.param_groups[0]["lr"], agent.actor_optim.param_groups[0]["lr"]))
+            out.update(_sd(agent.actor, f"a{it + 1}."))
+            out.update(_sd(agent.critic, f"c{it + 1}."))
+            out.update(_sd(agent.actor_target, f"at{it + 1}."))
+            out.update(_sd(agent.critic_target, f"ct{it + 1}."))
+    finally:
+        np.random.choice = orig_choice
+    out["idx"] = np.array(idx_all)
+    out["critic_loss"] = np.array(closs)
+    out["actor_loss"] = np.array(aloss)
+    out["lrs"] = np.array(lrs)
+    out["next_emotion"] = np.array(next_emotions)
+    out["train_step"] = 7
+    out["meta"] = _meta("U2-U5 DDPGAgent.learn x3, eval-mode nets, B=128, injected buffer")
+    np.savez_compressed(os.path.join(GOLD, "learn_golden.npz"), **out)
+    print("learn: critic_loss", closs, "actor_loss", aloss, "lrs", lrs)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["sim", "env", "emotion"]
     os.chdir("/tmp")
     for w in which:
-        {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion}[w]()
+        {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion, "nets": gen_nets, "learn": gen_learn}[w]()

@@ -1,0 +1,203 @@
+"""Plain PyTorch fp32 restatement of the reference networks — TEST INFRASTRUCTURE ONLY.
+
+Functional forms (weights passed as a dict keyed like the reference's state_dict, dropout masks
+passed explicitly) of:
+  A1  Actor.forward                (DifferentModules/ddpg_agent.py:73-122)
+  U1  Critic.forward               (DifferentModules/ddpg_agent.py:163-183)
+  M2  EmotionTransformer.forward   (EmotionModule.py:48-71) = embedding + learned positions +
+      4 x nn.TransformerEncoderLayer(d=32, heads=4, ff=2048, post-norm, relu) + last token + fc_out
+  U2-U5 DDPGAgent.learn            (DifferentModules/ddpg_agent.py:422-512) as one function on
+      explicit tensors, using autograd on the functional forms above.
+
+Parity status: pinned against tests/golden/nets_golden.npz, produced by oracle/gen_golden.py from
+the unmodified reference modules both in eval() and in train() mode (dropout masks replayed from
+torch's CPU generator); see tests/test_nets_oracle.py.
+
+Dropout convention: a mask is the 0/1 keep tensor; the kept activations are scaled by 1/(1-p)
+exactly like at::dropout (input * (mask / (1 - p))).  masks=None means eval mode.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+ACTOR_P = 0.2      # ddpg_agent.py:30,40,43
+CRITIC_P = 0.2     # ddpg_agent.py:139,150,155
+TRANS_P = 0.3      # EmotionModule.py:9,35
+N_LAYERS, D_MODEL, N_HEAD, D_FF, MAX_LEN = 4, 32, 4, 2048, 20
+
+
+def _drop(x, mask, p):
+    if mask is None:
+        return x
+    return x * (mask / (1.0 - p))
+
+
+# ---------------------------------------------------------------------------------------------
+def actor_forward(W, state, emotion, masks=None, return_base=False):
+    """masks: None or (m1[B,128], m2[B,128]) keep-masks of the two Dropout(0.2) layers."""
+    if emotion.dim() == 1:
+        emotion = emotion.unsqueeze(0)
+    if state.dim() == 1:
+        state = state.unsqueeze(0)
+    if emotion.size(0) != state.size(0):
+        emotion = emotion.expand(state.size(0), -1)
+    m1, m2 = masks if masks is not None else (None, None)
+    x = torch.cat([state, emotion], dim=1)
+    x = F.linear(x, W["input_layer.weight"], W["input_layer.bias"])
+    x = F.leaky_relu(x, 0.1)
+    x = _drop(x, m1, ACTOR_P)
+    x = F.relu(F.linear(x, W["hidden.2.weight"], W["hidden.2.bias"]))
+    x = _drop(x, m2, ACTOR_P)
+    x = F.relu(F.linear(x, W["hidden.5.weight"], W["hidden.5.bias"]))
+    x = F.linear(x, W["hidden.7.weight"], W["hidden.7.bias"])
+    base = F.softsign(x)
+    curiosity, conserv, anxiety = emotion[:, 0:1], emotion[:, 1:2], emotion[:, 2:3]
+    raw_effect = torch.tanh((emotion @ W["emotion_weights"]) * 1.5)
+    alpha = 0.1 + 0.9 * anxiety
+    alpha = alpha * (1.0 - 0.5 * conserv)
+    alpha = alpha * (1.0 + 0.5 * curiosity)
+    alpha = torch.clamp(alpha, min=0.01, max=1)
+    modulator = (1 - torch.abs(base)) ** 2
+    sign_flip = -torch.sign(base)
+    raw_action = base + alpha * raw_effect * sign_flip * modulator
+    out = raw_action * W["scale_params"] + W["offset_params"]
+    return (out, base) if return_base else out
+
+
+def critic_forward(W, state, action, emotion, masks=None):
+    """masks: None or (m1[B,256], m2[B,256]).  Emotion is standardised with BATCH statistics
+    (unbiased std), ddpg_agent.py:176 — B = 1 gives NaN, all-equal rows give 0."""
+    m1, m2 = masks if masks is not None else (None, None)
+    emotion = (emotion - emotion.mean(dim=0, keepdim=True)) / (emotion.std(dim=0, keepdim=True) + 1e-6)
+    x = torch.cat([state, action, emotion], dim=1)
+    x = F.linear(x, W["net.0.weight"], W["net.0.bias"])
+    x = F.layer_norm(x, (256,), W["net.1.weight"], W["net.1.bias"], 1e-5)
+    x = _drop(F.leaky_relu(x, 0.1), m1, CRITIC_P)
+    x = F.linear(x, W["net.4.weight"], W["net.4.bias"])
+    x = F.layer_norm(x, (256,), W["net.5.weight"], W["net.5.bias"], 1e-5)
+    x = _drop(F.relu(x), m2, CRITIC_P)
+    x = F.relu(F.linear(x, W["net.8.weight"], W["net.8.bias"]))
+    q = F.linear(x, W["net.10.weight"], W["net.10.bias"])
+    return torch.clamp(q, -1e6, 1e6)
+
+
+def transformer_forward(W, seq, masks=None):
+    """seq: [B, S, 3] (S <= 20).  masks: None or a list of 4 dicts with keep-masks
+    {"attn": [B,4,S,S], "d1": [B,S,32], "ff": [B,S,2048], "d2": [B,S,32]}.  Returns [B, 3]."""
+    B, S, _ = seq.shape
+    x = F.linear(seq, W["embedding.weight"], W["embedding.bias"])            # [B,S,32]
+    x = x + W["positional_encoding"][:S].unsqueeze(0)
+    hd = D_MODEL // N_HEAD
+    for l in range(N_LAYERS):
+        pre = f"transformer_encoder.layers.{l}."
+        m = masks[l] if masks is not None else {}
+        qkv = F.linear(x, W[pre + "self_attn.in_proj_weight"], W[pre + "self_attn.in_proj_bias"])
+        q, k, v = qkv.split(D_MODEL, dim=-1)
+        q = q.view(B, S, N_HEAD, hd).transpose(1, 2)
+        k = k.view(B, S, N_HEAD, hd).transpose(1, 2)
+        v = v.view(B, S, N_HEAD, hd).transpose(1, 2)
+        att = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+        att = _drop(att, m.get("attn"), TRANS_P)
+        a = (att @ v).transpose(1, 2).reshape(B, S, D_MODEL)
+        a = F.linear(a, W[pre + "self_attn.out_proj.weight"], W[pre + "self_attn.out_proj.bias"])
+        x = F.layer_norm(x + _drop(a, m.get("d1"), TRANS_P), (D_MODEL,), W[pre + "norm1.weight"],
+                         W[pre + "norm1.bias"], 1e-5)
+        h = F.relu(F.linear(x, W[pre + "linear1.weight"], W[pre + "linear1.bias"]))
+        h = _drop(h, m.get("ff"), TRANS_P)
+        h = F.linear(h, W[pre + "linear2.weight"], W[pre + "linear2.bias"])
+        x = F.layer_norm(x + _drop(h, m.get("d2"), TRANS_P), (D_MODEL,), W[pre + "norm2.weight"],
+                         W[pre + "norm2.bias"], 1e-5)
+    out = F.linear(x[:, -1], W["fc_out.weight"], W["fc_out.bias"])
+    return torch.tanh(out) * 0.5 + 0.5
+
+
+def pad_history(history, max_len=MAX_LEN):
+    """EmotionTransformer.get_state (EmotionModule.py:83-102): front-pad with the OLDEST entry; an
+    empty history gives the single neutral token [0.5, 0.5, 0.0] (sequence length 1)."""
+    if len(history) == 0:
+        return torch.tensor([[[0.5, 0.5, 0.0]]], dtype=torch.float32)
+    h = [torch.as_tensor(x, dtype=torch.float32) for x in history][-max_len:]
+    padded = [h[0]] * (max_len - len(h)) + h
+    return torch.stack(padded).unsqueeze(0)
+
+
+# ---------------------------------------------------------------------------------------------
+ACTOR_PARAM_ORDER = ["emotion_weights", "input_layer.weight", "input_layer.bias", "hidden.2.weight",
+                     "hidden.2.bias", "hidden.5.weight", "hidden.5.bias", "hidden.7.weight", "hidden.7.bias"]
+CRITIC_PARAM_ORDER = ["net.0.weight", "net.0.bias", "net.1.weight", "net.1.bias", "net.4.weight", "net.4.bias",
+                      "net.5.weight", "net.5.bias", "net.8.weight", "net.8.bias", "net.10.weight", "net.10.bias"]
+
+
+def _clip_grad_norm_(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_ (norm of per-tensor norms, coef clamped to 1, eps 1e-6)."""
+    total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g, 2.0) for g in grads]), 2.0)
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return [g * coef for g in grads], total
+
+
+def adam_step(params, grads, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8):
+    """torch.optim.Adam (no weight decay, no amsgrad), single-tensor formulation."""
+    out = []
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    for p, g, mi, vi in zip(params, grads, m, v):
+        mi.mul_(b1).add_(g, alpha=1 - b1)
+        vi.mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (vi.sqrt() / math.sqrt(bc2)).add_(eps)
+        out.append(p - (lr / bc1) * (mi / denom))
+    return out
+
+
+def ddpg_learn(actor, actor_t, critic, critic_t, opt, batch, next_emotion, train_step,
+               masks=None, gamma=0.99, tau=0.01, actor_lr=1e-4, critic_lr=1e-3, lr_decay=0.999):
+    """One DDPGAgent.learn() (ddpg_agent.py:436-512) on explicit tensors.
+
+    actor/actor_t/critic/critic_t: weight dicts (updated in place); opt: {"am","av","cm","cv","step"}
+    Adam state; batch: dict(states[B,2], actions[B,10] normalised, rewards[B], next_states[B,2],
+    dones[B], emotions[B,3]); next_emotion[3] = the fresh get_emotion() of :466.
+    masks: None (eval) or dict with keys at_/ct_/c_/a_/c2_ -> mask pairs for the five forwards.
+    Returns (critic_loss, actor_loss, lrs)."""
+    mk = masks or {}
+    s, a, r = batch["states"], batch["actions"], batch["rewards"].unsqueeze(1) * 0.01
+    s2, d, e = batch["next_states"], batch["dones"].unsqueeze(1), batch["emotions"]
+    anxiety, conserv, curiosity = e[:, 2].mean().item(), e[:, 1].mean().item(), e[:, 0].mean().item()
+    actor_factor = 1.0 + 0.8 * curiosity - 0.4 * conserv + 0.2 * anxiety
+    critic_factor = 1.0 - 0.3 * anxiety + 0.6 * conserv
+    decay = lr_decay ** train_step
+    c_lr = float(min(max(critic_lr * critic_factor * decay, critic_lr * 0.1), critic_lr * 3))
+    a_lr = float(min(max(actor_lr * actor_factor * decay, actor_lr * 0.1), actor_lr * 3))
+    with torch.no_grad():
+        ne = next_emotion.view(1, 3).expand(s2.size(0), -1)
+        a2 = actor_forward(actor_t, s2, ne, mk.get("at"))
+        tq = critic_forward(critic_t, s2, a2, ne, mk.get("ct"))
+        y = r + (1 - d) * gamma * tq
+    cp = [critic[k].clone().requires_grad_(True) for k in CRITIC_PARAM_ORDER]
+    cw = dict(zip(CRITIC_PARAM_ORDER, cp))
+    q = critic_forward(cw, s, a, e, mk.get("c"))
+    critic_loss = F.smooth_l1_loss(q, y)
+    cg = torch.autograd.grad(critic_loss, cp)
+    cg, _ = _clip_grad_norm_(list(cg), 5.0)
+    opt["step"] += 1
+    new_c = adam_step([p.detach() for p in cp], cg, opt["cm"], opt["cv"], opt["step"], c_lr)
+    for k, p in zip(CRITIC_PARAM_ORDER, new_c):
+        critic[k] = p
+    ap = [actor[k].clone().requires_grad_(True) for k in ACTOR_PARAM_ORDER]
+    aw = dict(zip(ACTOR_PARAM_ORDER, ap))
+    aw["scale_params"], aw["offset_params"] = actor["scale_params"], actor["offset_params"]
+    act_out = actor_forward(aw, s, e, mk.get("a"))
+    actor_loss = -critic_forward(critic, s, act_out, e, mk.get("c2")).mean()
+    actor_loss = actor_loss - 0.03 * torch.std(act_out, dim=1).mean()
+    l2 = torch.tensor(0.0)
+    for p in ap:
+        l2 = l2 + torch.norm(p, p=2)
+    actor_loss = actor_loss + 1e-4 * l2
+    ag = torch.autograd.grad(actor_loss, ap)
+    ag, _ = _clip_grad_norm_(list(ag), 5.0)
+    new_a = adam_step([p.detach() for p in ap], ag, opt["am"], opt["av"], opt["step"], a_lr)
+    for k, p in zip(ACTOR_PARAM_ORDER, new_a):
+        actor[k] = p
+    for k in ACTOR_PARAM_ORDER:
+        actor_t[k] = tau * actor[k] + (1 - tau) * actor_t[k]
+    for k in CRITIC_PARAM_ORDER:
+        critic_t[k] = tau * critic[k] + (1 - tau) * critic_t[k]
+    return critic_loss.item(), actor_loss.item(), (c_lr, a_lr)
