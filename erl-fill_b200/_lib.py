@@ -43,10 +43,39 @@ class Noise(C.Structure):
     _fields_ = [("d_u", C.c_void_p), ("rows", C.c_int32), ("_pad", C.c_int32), ("d_reset_u", C.c_void_p)]
 
 
+class ActorWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w_in", "b_in", "w_h2", "b_h2", "w_h5", "b_h5", "w_h7", "b_h7",
+                                           "emotion_weights", "scale", "offset")]
+
+
+class OU(C.Structure):
+    _fields_ = [("d_state", C.c_void_p), ("d_sigma", C.c_void_p), ("d_randn", C.c_void_p),
+                ("d_final_action", C.c_void_p), ("seed", C.c_uint64), ("env_id_base", C.c_uint32),
+                ("step_idx", C.c_uint32)]
+
+
+class EmotionState(C.Structure):
+    _fields_ = [("d_current", C.c_void_p), ("d_history", C.c_void_p), ("d_hist_len", C.c_void_p),
+                ("d_hist_head", C.c_void_p)]
+
+
+class TransformerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("emb_w", "emb_b", "pos", "in_proj_w", "in_proj_b", "out_proj_w",
+                                           "out_proj_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b", "norm1_w",
+                                           "norm1_b", "norm2_w", "norm2_b", "fc_w", "fc_b")]
+
+
+class TransformerMasks(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("attn", "d1", "ff", "d2")]
+
+
+DROPOUT_OFF, DROPOUT_PHILOX, DROPOUT_MASK = 0, 1, 2
+
 # every symbol include/erlfill.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTS = [
     "erlfill_version", "erlfill_last_cuda_error", "erlfill_last_cuda_error_string", "erlfill_device_ok",
     "erlfill_env_reset", "erlfill_env_reset_from_replay", "erlfill_env_step",
+    "erlfill_actor_forward", "erlfill_emotion_update", "erlfill_episode_end", "erlfill_emotion_forward",
 ]
 
 _lib = None

@@ -123,6 +123,90 @@ int erlfill_env_step(const erlfill_env_batch *env, const float *d_actions, uint3
                      int auto_reset, const erlfill_noise *noise, const erlfill_step_out *out,
                      void *stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Policy side of the rollout                                                                  */
+/* ------------------------------------------------------------------------------------------ */
+typedef enum { ERLFILL_DROPOUT_OFF = 0,     /* module.eval() */
+               ERLFILL_DROPOUT_PHILOX = 1,  /* train() mode, keep-masks from Philox (row, call_idx, col/4, DROPOUT+layer) */
+               ERLFILL_DROPOUT_MASK = 2     /* train() mode, keep-masks injected by the caller (parity tests) */
+} erlfill_dropout_mode;
+
+/* Actor parameters, device pointers, each in the reference state_dict layout [out][in]
+ * (ddpg_agent.py:31-56): input_layer, hidden.2, hidden.5, hidden.7, emotion_weights[3][10],
+ * buffers scale_params[10] / offset_params[10]. */
+typedef struct {
+    const float *w_in, *b_in;      /* [128][5], [128] */
+    const float *w_h2, *b_h2;      /* [128][128], [128] */
+    const float *w_h5, *b_h5;      /* [64][128], [64] */
+    const float *w_h7, *b_h7;      /* [10][64], [10] */
+    const float *emotion_weights;  /* [3][10] */
+    const float *scale, *offset;   /* [10], [10] */
+} erlfill_actor_weights;
+
+/* OU exploration state, one process per env (ddpg_agent.py:735-785). */
+typedef struct {
+    float *d_state;                /* [n][10] in/out */
+    const float *d_sigma;          /* [n] current sigma as binary32 (sigma * randn is a binary32 product) */
+    const float *d_randn;          /* [n][10] injected N(0,1) draws, or NULL => Philox Box-Muller (STREAM_OU) */
+    float *d_final_action;         /* [n][10] clip(scaled + noise*scale, offset-scale, offset+scale) */
+    uint64_t seed;
+    uint32_t env_id_base, step_idx;
+} erlfill_ou;
+
+/* Per-env EmotionModule state (EmotionModule.py:105-162): current_emotion (binary64) and the 20-deep
+ * history of binary32 vectors the transformer reads. */
+typedef struct {
+    double *d_current;             /* [3][n] */
+    float *d_history;              /* [20][3][n] ring */
+    int32_t *d_hist_len;           /* [n] */
+    int32_t *d_hist_head;          /* [n] slot of the oldest entry */
+} erlfill_emotion_state;
+
+/* A1 (+A2 when ou != NULL) — Actor.forward (ddpg_agent.py:73-122); with ou also OUNoise.sample and
+ * DDPGAgent.act's clip (:348-356, :768-778).  d_emotion is [n][3], or [3] when emotion_broadcast. */
+int erlfill_actor_forward(const erlfill_actor_weights *w, int n_rows, const float *d_state, const float *d_emotion,
+                          int emotion_broadcast, int dropout_mode, uint64_t seed, uint32_t call_idx,
+                          uint32_t row_id_base, const uint8_t *d_mask1, const uint8_t *d_mask2,
+                          float *d_scaled_action, float *d_base_action, const erlfill_ou *ou, void *stream);
+
+/* M1 — EmotionModule.update(reward, next_state - state) (EmotionModule.py:121-162) for every env. */
+int erlfill_emotion_update(int n_env, const float *d_reward, const float *d_state, const float *d_next_state,
+                           const erlfill_emotion_state *emo, void *stream);
+
+/* train_ddpg's per-episode `ou_noise.reset(); ou_noise.anneal()` (ddpg_agent.py:633-634) for envs with done. */
+int erlfill_episode_end(int n_env, const uint8_t *d_done, float *d_ou_state, float *d_sigma, double *d_sigma64,
+                        void *stream);
+
+/* EmotionTransformer parameters (EmotionModule.py:27-40), device pointers, per-layer tensors stacked on a
+ * leading [4] axis, each slice in the reference state_dict layout. */
+typedef struct {
+    const float *emb_w, *emb_b;            /* embedding [32][3], [32] */
+    const float *pos;                      /* positional_encoding [20][32] */
+    const float *in_proj_w, *in_proj_b;    /* [4][96][32], [4][96] */
+    const float *out_proj_w, *out_proj_b;  /* [4][32][32], [4][32] */
+    const float *lin1_w, *lin1_b;          /* [4][2048][32], [4][2048] */
+    const float *lin2_w, *lin2_b;          /* [4][32][2048], [4][32] */
+    const float *norm1_w, *norm1_b;        /* [4][32] */
+    const float *norm2_w, *norm2_b;        /* [4][32] */
+    const float *fc_w, *fc_b;              /* fc_out [3][32], [3] */
+} erlfill_transformer_weights;
+
+/* Injected keep-masks for ERLFILL_DROPOUT_MASK (uint8 0/1), in at::dropout's draw order per layer:
+ * attention probabilities, dropout1, FFN hidden dropout, dropout2. */
+typedef struct {
+    const uint8_t *attn;                   /* [4][n][4][S][S] */
+    const uint8_t *d1;                     /* [4][n][S][32] */
+    const uint8_t *ff;                     /* [4][n][S][2048] */
+    const uint8_t *d2;                     /* [4][n][S][32] */
+} erlfill_transformer_masks;
+
+/* M2 — EmotionModule.get_emotion = EmotionTransformer.forward(get_state()) (EmotionModule.py:48-71, 83-102,
+ * 164-175), fp32.  Sequence source: d_seq [n][seq_len][3] if non-NULL, else the history ring in `emo`
+ * (front-padded with the oldest entry to 20; the neutral token [0.5,0.5,0] alone when empty).  d_out [n][3]. */
+int erlfill_emotion_forward(const erlfill_transformer_weights *w, int n_env, const float *d_seq, int seq_len,
+                            const erlfill_emotion_state *emo, int dropout_mode, uint64_t seed, uint32_t call_idx,
+                            uint32_t row_id_base, const erlfill_transformer_masks *masks, float *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
