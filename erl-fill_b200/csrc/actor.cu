@@ -242,12 +242,13 @@ __global__ void __launch_bounds__(kThreads, 1) actor_forward_kernel(const ActorA
                     g = (float)((c & 1) ? rad * sin(ang) : rad * cos(ang));
                 }
                 float st = a.ou.d_state[(size_t)row * 10 + c];
-                float dx = 0.15f * (0.0f - st);
-                dx = dx + a.ou.d_sigma[row] * g;
-                st = st + dx;
+                // numpy evaluates every product and sum separately in binary32: no FMA contraction here
+                float dx = __fmul_rn(0.15f, __fsub_rn(0.0f, st));
+                dx = __fadd_rn(dx, __fmul_rn(a.ou.d_sigma[row], g));
+                st = __fadd_rn(st, dx);
                 a.ou.d_state[(size_t)row * 10 + c] = st;
-                float fa = scaled + st * scale;
-                const float lo = offset - scale, hi = offset + scale;
+                float fa = __fadd_rn(scaled, __fmul_rn(st, scale));
+                const float lo = __fsub_rn(offset, scale), hi = __fadd_rn(offset, scale);
                 fa = fa < lo ? lo : fa;
                 fa = fa > hi ? hi : fa;
                 a.ou.d_final_action[(size_t)row * 10 + c] = fa;

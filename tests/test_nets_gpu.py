@@ -57,9 +57,14 @@ def test_actor_ragged_large_batch_and_philox_dropout(G):
     n = 64 * 150 + 37
     s, e = torch.rand(n, 2, generator=g) * 5, torch.rand(n, 3, generator=g)
     out = nets.actor_forward(P, s.cuda(), e.cuda())
-    ref = R.actor_forward(W, s, e)
+    ref, ref_base = R.actor_forward(W, s, e, return_base=True)
     scale = W["scale_params"].numpy()
-    assert np.all(np.abs(out.cpu().numpy() - ref.numpy()) <= 2e-5 * scale[None, :] + 1e-6)
+    # contract: 1e-5 relative on the physical value (one binary32 ulp of 24950 is 3.9e-5 of its range)
+    # plus 2e-5 of the action range
+    err = np.abs(out.cpu().numpy() - ref.numpy()) - 1e-5 * np.abs(ref.numpy())
+    # -sign(base) (ddpg_agent.py:113) is discontinuous at base == 0: leave out the rows that sit on it
+    ok = np.abs(ref_base.numpy()) > 1e-4
+    assert ok.mean() > 0.999 and (err / scale[None, :])[ok].max() <= 2e-5, (ok.mean(), (err / scale[None, :])[ok].max())
     # Philox dropout: deterministic in (seed, call_idx, row id), independent of batch split, keep rate 0.8
     a = nets.actor_forward(P, s.cuda(), e.cuda(), dropout=L.DROPOUT_PHILOX, seed=11, call_idx=5)
     b = nets.actor_forward(P, s.cuda(), e.cuda(), dropout=L.DROPOUT_PHILOX, seed=11, call_idx=5)
