@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "lib", "liberlfill.so")
 
-ACTION_DIM, STATE_DIM, EMOTION_DIM, RING, HIST = 10, 2, 3, 20, 20
+ACTION_DIM, STATE_DIM, EMOTION_DIM, RING, HIST, REC = 10, 2, 3, 20, 20, 20
 ENV_MULTI, ENV_SINGLE = 0, 1
 ACTION_ORDER = ("fast_weight", "medium_weight", "slow_weight", "fast_opening", "medium_opening",
                 "slow_opening", "fast_delay", "medium_delay", "slow_delay", "unload_delay")
@@ -69,6 +69,20 @@ class TransformerMasks(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("attn", "d1", "ff", "d2")]
 
 
+class DDPGNets(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("actor", "actor_target", "critic", "critic_target", "actor_m", "actor_v",
+                                           "critic_m", "critic_v", "scale", "offset")]
+
+
+class DDPGHyper(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("adam_step", C.c_int32), ("gamma", C.c_float), ("tau", C.c_float),
+                ("max_grad_norm", C.c_float), ("_pad", C.c_float), ("critic_lr", C.c_double),
+                ("actor_lr", C.c_double), ("lr_decay", C.c_double)]
+
+
+PHASE_CRITIC_GRAD, PHASE_CRITIC_APPLY, PHASE_ACTOR_GRAD, PHASE_ACTOR_APPLY, PHASE_ALL = 1, 2, 4, 8, 15
+ACTOR_PARAMS, CRITIC_PARAMS = 26216, 103937
+
 DROPOUT_OFF, DROPOUT_PHILOX, DROPOUT_MASK = 0, 1, 2
 
 # every symbol include/erlfill.h declares (tests/test_abi.py checks the library exports them all)
@@ -76,6 +90,8 @@ EXPORTS = [
     "erlfill_version", "erlfill_last_cuda_error", "erlfill_last_cuda_error_string", "erlfill_device_ok",
     "erlfill_env_reset", "erlfill_env_reset_from_replay", "erlfill_env_step",
     "erlfill_actor_forward", "erlfill_emotion_update", "erlfill_episode_end", "erlfill_emotion_forward",
+    "erlfill_replay_insert", "erlfill_replay_sample", "erlfill_replay_gather",
+    "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_update",
 ]
 
 _lib = None
@@ -90,6 +106,7 @@ def lib():
                 "(there is no CPU fallback for the ERL-Fill hot path)")
         L = C.CDLL(SO_PATH)
         L.erlfill_last_cuda_error_string.restype = C.c_char_p
+        L.erlfill_ddpg_workspace_bytes.restype = C.c_size_t
         for name in EXPORTS:
             getattr(L, name)
         _lib = L

@@ -1,0 +1,171 @@
+"""Host side of the ER-DDPG update (csrc/update.cu) and the replay buffer (csrc/replay.cu).
+
+DDPGLearner owns the flat parameter / Adam buffers in the reference's parameters() order and exposes
+per-tensor views keyed like the reference state_dict (ddpg_agent.py:526-560), so checkpoints interchange.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+ACTOR_LAYOUT = [("emotion_weights", (3, 10)), ("input_layer.weight", (128, 5)), ("input_layer.bias", (128,)),
+                ("hidden.2.weight", (128, 128)), ("hidden.2.bias", (128,)), ("hidden.5.weight", (64, 128)),
+                ("hidden.5.bias", (64,)), ("hidden.7.weight", (10, 64)), ("hidden.7.bias", (10,))]
+CRITIC_LAYOUT = [("net.0.weight", (256, 15)), ("net.0.bias", (256,)), ("net.1.weight", (256,)), ("net.1.bias", (256,)),
+                 ("net.4.weight", (256, 256)), ("net.4.bias", (256,)), ("net.5.weight", (256,)), ("net.5.bias", (256,)),
+                 ("net.8.weight", (128, 256)), ("net.8.bias", (128,)), ("net.10.weight", (1, 128)), ("net.10.bias", (1,))]
+
+
+def _views(flat, layout):
+    out, o = {}, 0
+    for name, shape in layout:
+        n = 1
+        for d in shape:
+            n *= d
+        out[name] = flat[o:o + n].view(*shape)
+        o += n
+    assert o == flat.numel()
+    return out
+
+
+class FlatNet:
+    def __init__(self, layout, total, device):
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.views = _views(self.flat, layout)
+        self.layout = layout
+
+    def load(self, sd):
+        for name, _ in self.layout:
+            self.views[name].copy_(torch.as_tensor(sd[name]).to(self.flat.device, torch.float32))
+
+    def state_dict(self):
+        return {k: v.clone() for k, v in self.views.items()}
+
+
+class ReplayBuffer:
+    """[capacity][20] binary32 records on the device (layout in include/erlfill.h)."""
+
+    def __init__(self, capacity, device="cuda"):
+        self.capacity = int(capacity)
+        self.device = torch.device(device)
+        self.buf = torch.zeros(self.capacity, L.REC, dtype=torch.float32, device=self.device)
+        self.size = 0
+        self.inserted = 0       # total transitions ever inserted (ring position)
+
+    def __len__(self):
+        return self.size
+
+    def insert(self, state, action, reward, next_state, done, emotion, scale=None, offset=None, policy="ring"):
+        """R1.  policy "ring": FIFO ring (TD3/SAC deque semantics and the batched ER-DDPG loop);
+        "per_argmin": the reference's PrioritizedReplayBuffer.add with its all-equal priorities — append until
+        full, then always overwrite slot 0 (np.argmin of equal values)."""
+        n = state.shape[0]
+        pos = None
+        if policy == "per_argmin":
+            free = self.capacity - self.size
+            idx = [self.size + i if i < free else 0 for i in range(n)]
+            pos = torch.tensor(idx, dtype=torch.int64, device=self.device)
+            start = 0
+        else:
+            start = self.inserted % self.capacity
+        with torch.cuda.device(self.device):
+            L.check(L.lib().erlfill_replay_insert(C.c_int(n), L.ptr(self.buf), C.c_int64(self.capacity), C.c_int64(start),
+                                                  L.ptr(pos), L.ptr(state), L.ptr(action), L.ptr(reward), L.ptr(next_state),
+                                                  L.ptr(done), L.ptr(emotion), L.ptr(scale), L.ptr(offset), L.stream_ptr()),
+                    "erlfill_replay_insert")
+        self.inserted += n
+        self.size = min(self.capacity, self.size + n)
+
+    def sample_indices(self, batch, seed, update_idx, stream_id=0, out=None):
+        if out is None:
+            out = torch.empty(batch, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().erlfill_replay_sample(C.c_int(batch), C.c_int64(self.size), C.c_uint64(seed),
+                                                  C.c_uint32(update_idx & 0xFFFFFFFF), C.c_uint32(stream_id), L.ptr(out),
+                                                  L.stream_ptr()), "erlfill_replay_sample")
+        return out
+
+    def gather(self, idx, out=None):
+        b = idx.shape[0]
+        if out is None:
+            out = torch.empty(b, L.REC, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().erlfill_replay_gather(C.c_int(b), L.ptr(self.buf), L.ptr(idx), L.ptr(out), L.stream_ptr()),
+                    "erlfill_replay_gather")
+        return out
+
+
+class DDPGLearner:
+    """Flat-buffer ER-DDPG networks + optimiser state and the fused update (DDPGAgent.learn)."""
+
+    def __init__(self, actor_sd, critic_sd, device="cuda", batch_size=128, gamma=0.99, tau=0.01, actor_lr=1e-4,
+                 critic_lr=1e-3, lr_decay_rate=0.999):
+        self.device = torch.device(device)
+        d = self.device
+        self.actor = FlatNet(ACTOR_LAYOUT, L.ACTOR_PARAMS, d)
+        self.actor_target = FlatNet(ACTOR_LAYOUT, L.ACTOR_PARAMS, d)
+        self.critic = FlatNet(CRITIC_LAYOUT, L.CRITIC_PARAMS, d)
+        self.critic_target = FlatNet(CRITIC_LAYOUT, L.CRITIC_PARAMS, d)
+        self.actor.load(actor_sd); self.actor_target.load(actor_sd)
+        self.critic.load(critic_sd); self.critic_target.load(critic_sd)
+        self.scale = torch.as_tensor(actor_sd["scale_params"]).to(d, torch.float32).contiguous()
+        self.offset = torch.as_tensor(actor_sd["offset_params"]).to(d, torch.float32).contiguous()
+        self.actor_m = torch.zeros(L.ACTOR_PARAMS, device=d); self.actor_v = torch.zeros(L.ACTOR_PARAMS, device=d)
+        self.critic_m = torch.zeros(L.CRITIC_PARAMS, device=d); self.critic_v = torch.zeros(L.CRITIC_PARAMS, device=d)
+        self.gamma, self.tau, self.actor_lr, self.critic_lr, self.lr_decay_rate = gamma, tau, actor_lr, critic_lr, lr_decay_rate
+        self.adam_step = 0
+        self.report = torch.zeros(4, dtype=torch.float32, device=d)
+        self._ws, self._ws_batch = None, 0
+        self.batch_size = batch_size
+
+    def _workspace(self, batch):
+        if self._ws is None or self._ws_batch != batch:
+            nbytes = L.lib().erlfill_ddpg_workspace_bytes(C.c_int(batch))
+            self._ws = torch.zeros((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+            self._ws_batch = batch
+        return self._ws
+
+    def grad_buckets(self, batch):
+        """(critic_bucket, actor_bucket) tensors aliasing the gradient buckets in the workspace."""
+        ws = self._workspace(batch)
+        cg, ag = C.c_void_p(), C.c_void_p()
+        cl, al = C.c_int(), C.c_int()
+        L.check(L.lib().erlfill_ddpg_grad_buckets(L.ptr(ws), C.c_int(batch), C.byref(cg), C.byref(cl), C.byref(ag), C.byref(al)),
+                "erlfill_ddpg_grad_buckets")
+        co = (cg.value - ws.data_ptr()) // 4
+        ao = (ag.value - ws.data_ptr()) // 4
+        return ws[co:co + cl.value], ws[ao:ao + al.value]
+
+    def actor_struct(self, target=False):
+        """erlfill_actor_weights pointing into the flat buffer (rollout kernel reads the live parameters)."""
+        v = (self.actor_target if target else self.actor).views
+        return L.ActorWeights(L.ptr(v["input_layer.weight"]), L.ptr(v["input_layer.bias"]), L.ptr(v["hidden.2.weight"]),
+                              L.ptr(v["hidden.2.bias"]), L.ptr(v["hidden.5.weight"]), L.ptr(v["hidden.5.bias"]),
+                              L.ptr(v["hidden.7.weight"]), L.ptr(v["hidden.7.bias"]), L.ptr(v["emotion_weights"]),
+                              L.ptr(self.scale), L.ptr(self.offset))
+
+    def update(self, batch, next_emotion, train_step, phases=L.PHASE_ALL, allreduce=None):
+        """One learn() on a gathered batch [B,20].  allreduce(tensor): optional in-place averaging callback
+        applied to the critic bucket and then the actor bucket (data-parallel)."""
+        B = batch.shape[0]
+        ws = self._workspace(B)
+        if phases & L.PHASE_CRITIC_GRAD:
+            self.adam_step += 1
+        nets = L.DDPGNets(L.ptr(self.actor.flat), L.ptr(self.actor_target.flat), L.ptr(self.critic.flat),
+                          L.ptr(self.critic_target.flat), L.ptr(self.actor_m), L.ptr(self.actor_v), L.ptr(self.critic_m),
+                          L.ptr(self.critic_v), L.ptr(self.scale), L.ptr(self.offset))
+        hyper = L.DDPGHyper(B, self.adam_step, self.gamma, self.tau, 5.0, 0.0, self.critic_lr, self.actor_lr,
+                            self.lr_decay_rate ** train_step)
+
+        def run(ph):
+            with torch.cuda.device(self.device):
+                L.check(L.lib().erlfill_ddpg_update(C.byref(nets), C.byref(hyper), L.ptr(batch), L.ptr(next_emotion), L.ptr(ws),
+                                                    C.c_int(ph), L.ptr(self.report), L.stream_ptr()), "erlfill_ddpg_update")
+        if allreduce is None:
+            run(phases)
+        else:
+            cb, ab = self.grad_buckets(B)
+            run(L.PHASE_CRITIC_GRAD); allreduce(cb); run(L.PHASE_CRITIC_APPLY)
+            run(L.PHASE_ACTOR_GRAD); allreduce(ab); run(L.PHASE_ACTOR_APPLY)
+        return self.report

@@ -20,6 +20,7 @@
 #ifndef ERLFILL_H_
 #define ERLFILL_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -34,6 +35,7 @@ extern "C" {
 #define ERLFILL_HIST 20              /* EmotionTransformer max_len: EmotionModule.py:9,43 */
 #define ERLFILL_MAX_ITER 5000        /* VirtualWeightController.py:158 */
 #define ERLFILL_NOCHANGE_LIMIT 500   /* VirtualWeightController.py:159 */
+#define ERLFILL_REC 20               /* floats per replay record (19 used + 1 pad = 80 B) */
 
 typedef enum {
     ERLFILL_OK = 0,
@@ -206,6 +208,69 @@ typedef struct {
 int erlfill_emotion_forward(const erlfill_transformer_weights *w, int n_env, const float *d_seq, int seq_len,
                             const erlfill_emotion_state *emo, int dropout_mode, uint64_t seed, uint32_t call_idx,
                             uint32_t row_id_base, const erlfill_transformer_masks *masks, float *d_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Replay buffer: [capacity][ERLFILL_REC] binary32 rows                                        */
+/*   [0:2] state [2:12] normalised action [12] reward [13:15] next_state [15] done [16:19] emotion [19] pad */
+/* ------------------------------------------------------------------------------------------ */
+
+/* R1 — DDPGAgent.remember + PrioritizedReplayBuffer.add (ddpg_agent.py:359-395, 206-226) for n transitions.
+ * Row of transition i: d_pos[i] if d_pos != NULL, else (start + i) % capacity.  When d_scale/d_offset are
+ * given the physical action is normalised clip((a-offset)/scale, -1, 1) (ddpg_agent.py:373-375); pass NULL
+ * for both to store d_action as is.  (The TD-error priority of the reference is NaN by construction and
+ * every priority is 1e-4, SURVEY.md section 0.7, so no priority array exists.) */
+int erlfill_replay_insert(int n, float *d_buf, int64_t capacity, int64_t start, const int64_t *d_pos,
+                          const float *d_state, const float *d_action, const float *d_reward,
+                          const float *d_next_state, const uint8_t *d_done, const float *d_emotion,
+                          const float *d_scale, const float *d_offset, void *stream);
+
+/* R2 — PrioritizedReplayBuffer.sample's index draw (ddpg_agent.py:228-254) with equal priorities:
+ * idx[i] = floor(U_i * n_valid), U from Philox (i/4, update_idx, stream_id, SAMPLE)[i%4]. */
+int erlfill_replay_sample(int batch, int64_t n_valid, uint64_t seed, uint32_t update_idx, uint32_t stream_id,
+                          int64_t *d_idx, void *stream);
+
+/* R2 — minibatch assembly (ddpg_agent.py:434-442): d_out[b][:] = d_buf[d_idx[b]][:]. */
+int erlfill_replay_gather(int batch, const float *d_buf, const int64_t *d_idx, float *d_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* ER-DDPG update                                                                              */
+/* ------------------------------------------------------------------------------------------ */
+/* Flat fp32 parameter buffers in the reference's parameters() order.
+ * actor (26,216): emotion_weights[3][10] | input_layer.weight[128][5] .bias[128] | hidden.2.weight[128][128] .bias |
+ *                 hidden.5.weight[64][128] .bias | hidden.7.weight[10][64] .bias
+ * critic (103,937): net.0.weight[256][15] .bias | net.1 (LayerNorm) weight, bias | net.4.weight[256][256] .bias |
+ *                 net.5 weight, bias | net.8.weight[128][256] .bias | net.10.weight[1][128] .bias */
+#define ERLFILL_ACTOR_PARAMS 26216
+#define ERLFILL_CRITIC_PARAMS 103937
+typedef struct {
+    float *actor, *actor_target, *critic, *critic_target;
+    float *actor_m, *actor_v, *critic_m, *critic_v;    /* Adam moments */
+    const float *scale, *offset;                       /* actor scale_params / offset_params [10] */
+} erlfill_ddpg_nets;
+
+typedef struct {
+    int32_t batch;
+    int32_t adam_step;        /* 1-based optimiser step of this update */
+    float gamma, tau, max_grad_norm, _pad;
+    double critic_lr, actor_lr;   /* base rates (1e-3, 1e-4) */
+    double lr_decay;              /* lr_decay_rate ** train_step (ddpg_agent.py:455) */
+} erlfill_ddpg_hyper;
+
+typedef enum { ERLFILL_PHASE_CRITIC_GRAD = 1, ERLFILL_PHASE_CRITIC_APPLY = 2, ERLFILL_PHASE_ACTOR_GRAD = 4,
+               ERLFILL_PHASE_ACTOR_APPLY = 8, ERLFILL_PHASE_ALL = 15 } erlfill_ddpg_phase;
+
+/* bytes of the caller-provided device workspace for a given minibatch size */
+size_t erlfill_ddpg_workspace_bytes(int batch);
+/* device addresses/lengths of the two flat gradient buckets inside the workspace (data-parallel: all-reduce
+ * (average) the critic bucket between CRITIC_GRAD and CRITIC_APPLY and the actor bucket between ACTOR_GRAD and
+ * ACTOR_APPLY; the critic bucket carries the 3 batch emotion means that set the learning rates in its tail). */
+int erlfill_ddpg_grad_buckets(void *d_workspace, int batch, float **critic_grad, int *critic_len,
+                              float **actor_grad, int *actor_len);
+/* U1-U5 — DDPGAgent.learn (ddpg_agent.py:422-512), dropout off.  d_batch [B][ERLFILL_REC] gathered records,
+ * d_next_emotion [3] the agent's fresh emotion (:466).  d_report (optional) [4] = critic_loss, actor_loss,
+ * critic_lr, actor_lr. */
+int erlfill_ddpg_update(const erlfill_ddpg_nets *nets, const erlfill_ddpg_hyper *hyper, const float *d_batch,
+                        const float *d_next_emotion, void *d_workspace, int phases, float *d_report, void *stream);
 
 #ifdef __cplusplus
 }

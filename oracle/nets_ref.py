@@ -65,11 +65,16 @@ def actor_forward(W, state, emotion, masks=None, return_base=False):
     return (out, base) if return_base else out
 
 
-def critic_forward(W, state, action, emotion, masks=None):
+def critic_forward(W, state, action, emotion, masks=None, pre_normalized=None):
     """masks: None or (m1[B,256], m2[B,256]).  Emotion is standardised with BATCH statistics
-    (unbiased std), ddpg_agent.py:176 — B = 1 gives NaN, all-equal rows give 0."""
+    (unbiased std), ddpg_agent.py:176 — B = 1 gives NaN; all-equal rows give (e-mean)/1e-6, i.e. torch's
+    summation rounding noise amplified by 1e6 (0 in exact arithmetic).  pre_normalized: use this tensor as
+    the standardised emotion instead (the CUDA path defines the all-equal case as exactly 0)."""
     m1, m2 = masks if masks is not None else (None, None)
-    emotion = (emotion - emotion.mean(dim=0, keepdim=True)) / (emotion.std(dim=0, keepdim=True) + 1e-6)
+    if pre_normalized is not None:
+        emotion = pre_normalized
+    else:
+        emotion = (emotion - emotion.mean(dim=0, keepdim=True)) / (emotion.std(dim=0, keepdim=True) + 1e-6)
     x = torch.cat([state, action, emotion], dim=1)
     x = F.linear(x, W["net.0.weight"], W["net.0.bias"])
     x = F.layer_norm(x, (256,), W["net.1.weight"], W["net.1.bias"], 1e-5)
@@ -149,7 +154,8 @@ def adam_step(params, grads, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8):
 
 
 def ddpg_learn(actor, actor_t, critic, critic_t, opt, batch, next_emotion, train_step,
-               masks=None, gamma=0.99, tau=0.01, actor_lr=1e-4, critic_lr=1e-3, lr_decay=0.999):
+               masks=None, gamma=0.99, tau=0.01, actor_lr=1e-4, critic_lr=1e-3, lr_decay=0.999,
+               exact_target_emotion=False):
     """One DDPGAgent.learn() (ddpg_agent.py:436-512) on explicit tensors.
 
     actor/actor_t/critic/critic_t: weight dicts (updated in place); opt: {"am","av","cm","cv","step"}
@@ -169,7 +175,8 @@ def ddpg_learn(actor, actor_t, critic, critic_t, opt, batch, next_emotion, train
     with torch.no_grad():
         ne = next_emotion.view(1, 3).expand(s2.size(0), -1)
         a2 = actor_forward(actor_t, s2, ne, mk.get("at"))
-        tq = critic_forward(critic_t, s2, a2, ne, mk.get("ct"))
+        tq = critic_forward(critic_t, s2, a2, ne, mk.get("ct"),
+                            pre_normalized=torch.zeros_like(ne) if exact_target_emotion else None)
         y = r + (1 - d) * gamma * tq
     cp = [critic[k].clone().requires_grad_(True) for k in CRITIC_PARAM_ORDER]
     cw = dict(zip(CRITIC_PARAM_ORDER, cp))
