@@ -14,4 +14,7 @@ def __getattr__(name):
     if name in ("VecFillEnv", "WeightEnv", "MultiConditionWeightEnv"):
         from . import envs
         return getattr(envs, name)
+    if name == "VecERDDPG":
+        from . import agents
+        return agents.VecERDDPG
     raise AttributeError(name)

@@ -581,8 +581,9 @@ __global__ void env_reset_kernel(const erlfill_env_batch env, const uint8_t *d_m
     env.d_ring_head[i] = 0;
 }
 
-__global__ void env_reset_replay_kernel(const erlfill_env_batch env, const uint8_t *d_mask,
-                                        const float *d_replay_states, const int64_t *d_idx) {
+__global__ void env_reset_replay_kernel(const erlfill_env_batch env, const uint8_t *d_mask, const float *d_replay,
+                                        int row_stride, int64_t n_valid, const int64_t *d_idx, uint32_t step_idx,
+                                        int update_counters) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= env.n_env) return;
     if (d_mask && !d_mask[i]) return;
@@ -590,19 +591,29 @@ __global__ void env_reset_replay_kernel(const erlfill_env_batch env, const uint8
     const int cid = env.d_cond_id ? env.d_cond_id[i] : (int)(gid % (uint32_t)env.n_cond);
     const erlfill_condition c = env.d_cond[cid];
     // np.mean(list of 10 f32[2], axis=0): row-sequential binary32 adds, then /10 (MutiConditionEnv.py:147-148)
-    const float2 *st = reinterpret_cast<const float2 *>(d_replay_states);
-    float2 acc = st[d_idx[(size_t)i * 10]];
-    for (int j = 1; j < 10; ++j) {
-        const float2 v = st[d_idx[(size_t)i * 10 + j]];
-        acc.x += v.x; acc.y += v.y;
+    float2 acc = make_float2(0.f, 0.f);
+    uint4 r = make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < 10; ++j) {
+        int64_t row;
+        if (d_idx) row = d_idx[(size_t)i * 10 + j];
+        else {
+            // batched loop: 10 draws with replacement, floor(U * n_valid), Philox (env, step, 1 + j/4, MISC)
+            if ((j & 3) == 0) r = philox4x32_10((uint32_t)env.seed, (uint32_t)(env.seed >> 32), gid, step_idx, 1u + (uint32_t)(j >> 2), STREAM_MISC);
+            const uint32_t x = (j & 3) == 0 ? r.x : ((j & 3) == 1 ? r.y : ((j & 3) == 2 ? r.z : r.w));
+            row = (int64_t)(((unsigned long long)x * (unsigned long long)n_valid) >> 32);
+        }
+        const float2 v = *reinterpret_cast<const float2 *>(d_replay + (size_t)row * row_stride);
+        if (j == 0) acc = v; else { acc.x += v.x; acc.y += v.y; }
     }
     const float raw0 = acc.x / 10.f, raw1 = acc.y / 10.f;
     reinterpret_cast<float2 *>(env.d_obs)[i] =
         make_float2(raw0 / (float)c.target_weight_err, raw1 / (float)c.target_time);   // normalised again: :151-154
-    env.d_step_counter[i] = 0;
-    env.d_episode_counter[i] += 1;
-    env.d_ring_len[i] = 0;
-    env.d_ring_head[i] = 0;
+    if (update_counters) {
+        env.d_step_counter[i] = 0;
+        env.d_episode_counter[i] += 1;
+        env.d_ring_len[i] = 0;
+        env.d_ring_head[i] = 0;
+    }
 }
 
 static int pick_block(int n_env) {
@@ -650,11 +661,14 @@ int erlfill_env_reset(const erlfill_env_batch *env, const uint8_t *d_mask, uint3
     return ERLFILL_OK;
 }
 
-int erlfill_env_reset_from_replay(const erlfill_env_batch *env, const uint8_t *d_mask,
-                                  const float *d_replay_states, const int64_t *d_idx, void *stream) {
-    if (!env_ok(env) || !d_replay_states || !d_idx) return ERLFILL_ERR_ARG;
+int erlfill_env_reset_from_replay(const erlfill_env_batch *env, const uint8_t *d_mask, const float *d_replay,
+                                  int row_stride, int64_t n_valid, const int64_t *d_idx, uint32_t step_idx,
+                                  int update_counters, void *stream) {
+    if (!env_ok(env) || !d_replay || row_stride < 2 || (row_stride & 1)) return ERLFILL_ERR_ARG;
+    if (!d_idx && (n_valid <= 0 || n_valid > 0xFFFFFFFFLL)) return ERLFILL_ERR_ARG;
     const int block = 128, grid = (env->n_env + block - 1) / block;
-    env_reset_replay_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*env, d_mask, d_replay_states, d_idx);
+    env_reset_replay_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*env, d_mask, d_replay, row_stride, n_valid, d_idx,
+                                                                       step_idx, update_counters);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
 }

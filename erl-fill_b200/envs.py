@@ -90,12 +90,15 @@ class VecFillEnv:
                                               nzp, L.stream_ptr()), "erlfill_env_reset")
         return self.obs
 
-    def reset_from_replay(self, replay_states, idx, mask=None):
-        """Replay branch of reset (MutiConditionEnv.py:145-154): idx int64[N,10] into replay_states[C,2]."""
+    def reset_from_replay(self, replay_rows, idx=None, mask=None, n_valid=0, update_counters=True):
+        """Replay branch of reset (MutiConditionEnv.py:145-154).  replay_rows: [C, stride] float32 whose first
+        two columns are stored states; idx int64[N,10] row indices or None (Philox draws over n_valid rows)."""
         b = self._batch()
         with torch.cuda.device(self.device):
-            L.check(L.lib().erlfill_env_reset_from_replay(C.byref(b), L.ptr(mask), L.ptr(replay_states), L.ptr(idx),
-                                                          L.stream_ptr()), "erlfill_env_reset_from_replay")
+            L.check(L.lib().erlfill_env_reset_from_replay(
+                C.byref(b), L.ptr(mask), L.ptr(replay_rows), C.c_int(replay_rows.shape[1]), C.c_int64(int(n_valid)),
+                L.ptr(idx), C.c_uint32(self.step_idx & 0xFFFFFFFF), C.c_int(int(update_counters)), L.stream_ptr()),
+                "erlfill_env_reset_from_replay")
         return self.obs
 
     def step(self, actions, noise_u=None, reset_u=None, auto_reset=None):

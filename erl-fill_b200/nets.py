@@ -115,7 +115,7 @@ def emotion_update(emo, reward, state, next_state):
 
 
 def emotion_forward(params, seq=None, emo=None, dropout=L.DROPOUT_OFF, masks=None, seed=0, call_idx=0,
-                    row_id_base=0, out=None):
+                    row_id_base=0, out=None, precision="fp32"):
     """M2: [n,3] emotion vectors from explicit sequences seq[n,S,3] or from the history rings in `emo`."""
     if seq is not None:
         n, S = seq.shape[0], seq.shape[1]
@@ -125,6 +125,8 @@ def emotion_forward(params, seq=None, emo=None, dropout=L.DROPOUT_OFF, masks=Non
         n, S, dev = emo.n, L.HIST, emo.history.device
     if out is None:
         out = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    if precision != "fp32":
+        raise L.ErlfillError("emotion_forward: only the fp32 path is built in this revision")
     w = params.struct()
     es = emo.struct() if emo is not None else None
     ms = None

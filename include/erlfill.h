@@ -112,9 +112,13 @@ int erlfill_env_reset(const erlfill_env_batch *env, const uint8_t *d_mask, uint3
                       const erlfill_noise *noise, void *stream);
 
 /* E4 — replay branch: state = mean of 10 stored states, normalised again (MutiConditionEnv.py:145-154).
- * d_replay_states:[capacity][2]; d_idx:[n_env][10] int64 indices into it. */
-int erlfill_env_reset_from_replay(const erlfill_env_batch *env, const uint8_t *d_mask,
-                                  const float *d_replay_states, const int64_t *d_idx, void *stream);
+ * d_replay: rows of `row_stride` floats whose first two are the stored state (row_stride = 2 for a plain
+ * [n][2] array, ERLFILL_REC for the replay buffer).  d_idx:[n_env][10] int64 row indices (the N=1 drop-in
+ * passes random.sample's), or NULL: 10 Philox draws floor(U*n_valid) with replacement per env.
+ * update_counters = 0 when the env-step kernel's auto-reset already reset the episode counters. */
+int erlfill_env_reset_from_replay(const erlfill_env_batch *env, const uint8_t *d_mask, const float *d_replay,
+                                  int row_stride, int64_t n_valid, const int64_t *d_idx, uint32_t step_idx,
+                                  int update_counters, void *stream);
 
 /* E1+E2/E3 (+E4 when auto_reset) — one filling cycle per env:
  * clip (MutiConditionEnv.py:365-367) -> int() truncation (VirtualWeightController.py:71-83) ->

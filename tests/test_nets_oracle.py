@@ -103,3 +103,15 @@ def test_learn_three_updates(golden_dir):
         for k in R.CRITIC_PARAM_ORDER:
             torch.testing.assert_close(critic[k], T(g[f"c{it + 1}.{k}"]), rtol=2e-4, atol=5e-6)
             torch.testing.assert_close(critic_t[k], T(g[f"ct{it + 1}.{k}"]), rtol=2e-4, atol=5e-6)
+
+
+def test_init_reproduces_reference_construction(G):
+    """erl-fill_b200/init.py consumes torch's RNG in the reference's order: same seed, same weights."""
+    import erlfill_b200
+    from erlfill_b200 import init, conditions as K
+    a, c, t = init.er_ddpg_state_dicts(K.EXPERIMENT_3["variant_25kg"]["bounds"], seed=0)
+    for prefix, sd in (("actor.", a), ("critic.", c), ("trans.", t)):
+        ref = load_weights(G, prefix)
+        assert set(ref) == set(sd), (prefix, set(ref) ^ set(sd))
+        for k in ref:
+            assert torch.equal(ref[k], sd[k]), prefix + k
