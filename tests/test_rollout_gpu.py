@@ -15,7 +15,7 @@ def test_rollout_matches_oracle_composition():
     conds = list(K.EXPERIMENT_3.values())[:1]          # one condition: the actor's scaling matches its bounds
     n, seed = 96, 5
     env = E.VecFillEnv(conds, n, kind="multi", max_steps=6, seed=seed, env_id_base=10)
-    agent = E.VecERDDPG(env, seed=seed, batch_size=64, memory_size=512)
+    agent = E.VecERDDPG(env, seed=seed, batch_size=64, memory_size=1024)
     a_sd, c_sd, t_sd = E.init.er_ddpg_state_dicts(conds[0]["bounds"], seed=seed)
     c = conds[0]
     oc = [O.make_condition(c["target_weight"], c["target_weight_err"], c["target_time"], c["bounds"])]
