@@ -84,11 +84,12 @@ PHASE_CRITIC_GRAD, PHASE_CRITIC_APPLY, PHASE_ACTOR_GRAD, PHASE_ACTOR_APPLY, PHAS
 ACTOR_PARAMS, CRITIC_PARAMS = 26216, 103937
 
 DROPOUT_OFF, DROPOUT_PHILOX, DROPOUT_MASK = 0, 1, 2
+SIM_AUTO, SIM_THREAD_PER_ENV, SIM_WARP_PER_ENV = 0, 1, 2
 
 # every symbol include/erlfill.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTS = [
     "erlfill_version", "erlfill_last_cuda_error", "erlfill_last_cuda_error_string", "erlfill_device_ok",
-    "erlfill_env_reset", "erlfill_env_reset_from_replay", "erlfill_env_step",
+    "erlfill_env_reset", "erlfill_env_reset_from_replay", "erlfill_env_step", "erlfill_env_step_set_mode",
     "erlfill_actor_forward", "erlfill_emotion_update", "erlfill_episode_end", "erlfill_emotion_forward",
     "erlfill_replay_insert", "erlfill_replay_sample", "erlfill_replay_gather",
     "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_update",

@@ -244,7 +244,7 @@ __device__ __noinline__ double2 motor_entry_slow(int k) {
 
 // One full tick (motor + weight + stage + safety stops).  n_after = number of draws consumed
 // including this one.  Returns true when the run has finished.
-template <bool kFirst>
+template <bool kFirst, int kTabN = kTabShared>
 __device__ __forceinline__ bool generic_tick(Lane &s, const SimParams &p, const double2 *s_tab, double opu,
                                              double sysdelay, int n_after, int &delay) {
     // motor_simulation(target): VirtualWeightController.py:92-113
@@ -259,7 +259,7 @@ __device__ __forceinline__ bool generic_tick(Lane &s, const SimParams &p, const 
     k = far ? k : 0;
     const double base = far ? s.open : s.target;
     double2 e;
-    if ((unsigned)k < (unsigned)kTabShared) e = s_tab[k];
+    if ((unsigned)k < (unsigned)kTabN) e = s_tab[k];
     else e = motor_entry_slow(k);
     s.k = k;
     s.dd = e.x;
@@ -423,6 +423,66 @@ __device__ __forceinline__ SimResult simulate(const SimParams &p, const double2 
     return res;
 }
 
+// Reward, state, done rule, auto-reset and all stores of one env (E2/E3/E4 after the simulator run).
+template <bool kInjected>
+__device__ __forceinline__ void finish_env(const StepArgs &a, int i, const erlfill_condition &c, const float *clipped,
+                                           const SimResult &sim, int unload_delay, const uint4 &misc) {
+    const int n_env = a.env.n_env;
+    const double total_time = (double)(sim.tick + unload_delay) / 1000.0;   // :239
+    const double fw = sim.final_weight;
+
+    double we, te;
+    const float reward = a.env.kind == ERLFILL_ENV_MULTI ? reward_multi(c, clipped, fw, total_time, we, te)
+                                                        : reward_single(c, clipped, fw, total_time, we, te);
+    const float2 ns = make_float2((float)(we / c.target_weight_err), (float)(te / c.target_time));
+
+    // recent_errors.append + done rule (MutiConditionEnv.py:445-452)
+    int step_counter = a.env.d_step_counter[i];
+    int ring_len = a.env.d_ring_len[i], ring_head = a.env.d_ring_head[i];
+    double *ring = a.env.d_ring + i;
+    if (ring_len < ERLFILL_RING) {
+        ring[(size_t)((ring_head + ring_len) % ERLFILL_RING) * n_env] = we;
+        ring_len += 1;
+    } else {
+        ring[(size_t)ring_head * n_env] = we;
+        ring_head = (ring_head + 1) % ERLFILL_RING;
+    }
+    bool done = step_counter >= a.env.max_steps;
+    if (!done && step_counter >= a.env.max_steps / 2 && ring_len == ERLFILL_RING) {
+        // np.mean over the deque, oldest first: pairwise_sum for n = 20
+        double r8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r8[j] = ring[(size_t)((ring_head + j) % ERLFILL_RING) * n_env];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r8[j] += ring[(size_t)((ring_head + 8 + j) % ERLFILL_RING) * n_env];
+        double res = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+#pragma unroll
+        for (int j = 16; j < 20; ++j) res += ring[(size_t)((ring_head + j) % ERLFILL_RING) * n_env];
+        done = (res / 20.0) < 25.0;
+    }
+    step_counter += 1;
+
+    float2 obs = ns;
+    if (done && a.auto_reset) {
+        double u0, u1;
+        if (kInjected && a.d_reset_u) { u0 = a.d_reset_u[i]; u1 = a.d_reset_u[n_env + i]; }
+        else { u0 = u32_to_unit(misc.y); u1 = u32_to_unit(misc.z); }
+        obs = reset_state_cold(c, u0, u1);
+        step_counter = 0; ring_len = 0; ring_head = 0;
+        a.env.d_episode_counter[i] += 1;
+    }
+    a.env.d_step_counter[i] = step_counter;
+    a.env.d_ring_len[i] = ring_len;
+    a.env.d_ring_head[i] = ring_head;
+    reinterpret_cast<float2 *>(a.env.d_obs)[i] = obs;
+    reinterpret_cast<float2 *>(a.out.d_next_state)[i] = ns;
+    a.out.d_reward[i] = reward;
+    a.out.d_done[i] = done ? 1 : 0;
+    if (a.out.d_final_weight) a.out.d_final_weight[i] = fw;
+    if (a.out.d_total_time) a.out.d_total_time[i] = total_time;
+    if (a.out.d_ticks) a.out.d_ticks[i] = sim.draws;
+}
+
 constexpr int kMaxBlock = 256;
 
 template <bool kInjected>
@@ -498,65 +558,231 @@ __global__ void __launch_bounds__(kMaxBlock) env_step_kernel(const StepArgs a) {
         sim = simulate(p, s_tab, sysdelay, nz, valid);
     }
     const int draws = valid ? sim.draws : 0;
-    if (valid) {
-        const double total_time = (double)(sim.tick + unload_delay) / 1000.0;   // :239
-        const double fw = sim.final_weight;
-
-        double we, te;
-        const float reward = a.env.kind == ERLFILL_ENV_MULTI ? reward_multi(c, clipped, fw, total_time, we, te)
-                                                            : reward_single(c, clipped, fw, total_time, we, te);
-        const float2 ns = make_float2((float)(we / c.target_weight_err), (float)(te / c.target_time));
-
-        // recent_errors.append + done rule (MutiConditionEnv.py:445-452)
-        int step_counter = a.env.d_step_counter[i];
-        int ring_len = a.env.d_ring_len[i], ring_head = a.env.d_ring_head[i];
-        double *ring = a.env.d_ring + i;
-        if (ring_len < ERLFILL_RING) {
-            ring[(size_t)((ring_head + ring_len) % ERLFILL_RING) * n_env] = we;
-            ring_len += 1;
-        } else {
-            ring[(size_t)ring_head * n_env] = we;
-            ring_head = (ring_head + 1) % ERLFILL_RING;
-        }
-        bool done = step_counter >= a.env.max_steps;
-        if (!done && step_counter >= a.env.max_steps / 2 && ring_len == ERLFILL_RING) {
-            // np.mean over the deque, oldest first: pairwise_sum for n = 20
-            double r8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r8[j] = ring[(size_t)((ring_head + j) % ERLFILL_RING) * n_env];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r8[j] += ring[(size_t)((ring_head + 8 + j) % ERLFILL_RING) * n_env];
-            double res = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
-#pragma unroll
-            for (int j = 16; j < 20; ++j) res += ring[(size_t)((ring_head + j) % ERLFILL_RING) * n_env];
-            done = (res / 20.0) < 25.0;
-        }
-        step_counter += 1;
-
-        float2 obs = ns;
-        if (done && a.auto_reset) {
-            double u0, u1;
-            if (kInjected && a.d_reset_u) { u0 = a.d_reset_u[i]; u1 = a.d_reset_u[n_env + i]; }
-            else { u0 = u32_to_unit(misc.y); u1 = u32_to_unit(misc.z); }
-            obs = reset_state_cold(c, u0, u1);
-            step_counter = 0; ring_len = 0; ring_head = 0;
-            a.env.d_episode_counter[i] += 1;
-        }
-        a.env.d_step_counter[i] = step_counter;
-        a.env.d_ring_len[i] = ring_len;
-        a.env.d_ring_head[i] = ring_head;
-        reinterpret_cast<float2 *>(a.env.d_obs)[i] = obs;
-        reinterpret_cast<float2 *>(a.out.d_next_state)[i] = ns;
-        a.out.d_reward[i] = reward;
-        a.out.d_done[i] = done ? 1 : 0;
-        if (a.out.d_final_weight) a.out.d_final_weight[i] = fw;
-        if (a.out.d_total_time) a.out.d_total_time[i] = total_time;
-        if (a.out.d_ticks) a.out.d_ticks[i] = sim.draws;
-    }
+    if (valid) finish_env<kInjected>(a, i, c, clipped, sim, unload_delay, misc);
     if (a.out.d_tick_sum) {
         __syncwarp();
         const int s = __reduce_add_sync(0xffffffffu, draws);
         if ((tid & 31) == 0 && s) atomicAdd(a.out.d_tick_sum, (unsigned long long)s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-per-env kernel (Philox noise).  One warp runs one env; the 32 lanes are 32 consecutive
+// Philox noise blocks (128 ticks), so nothing diverges and the generator runs 32-wide.
+//
+// HOLD phase (about 98 % of all ticks: open == target, an integer 0..255, speed 0), in exact
+// integer arithmetic.  A tick adds inc = target * (1 + u) with 1 + u = x * 2^-31 (x the tick's
+// 32-bit Philox word), so inc = P * 2^-31 with the integer P = target * x < 2^40: the binary64
+// product is exact.  While w stays inside its binade [2^e, 2^(e+1)), e <= 20, both w and every
+// inc are multiples of ulp(w) = 2^(e-52) and the sums stay below 2^(e+1), so every binary64 add of
+// the reference is exact too and  w_j = w_0 + 2^-31 * sum_{t<=j} P_t  holds bit for bit.  The
+// stage test w_j < thr therefore becomes the integer test  prefix_j < ceil((lim - w_0) * 2^31)
+// with lim = min(thr, 2^(e+1)) (lim - w_0 is exact: both are multiples of ulp(w_0) and the
+// difference is below 2^e).  A 128-tick super-block is then: one Philox call and four 64-bit
+// multiply/adds per lane, one warp reduction, one compare.  Only the tick that reaches `lim`
+// (stage exit, or w entering the next binade, where the reference's add may round) is replayed
+// with a real binary64 add from the exact predecessor value; the stagnation counter
+// (|dw| < 0.01  <=>  P <= 21474836) is kept with a warp max-reduction over tick indices.
+// MOVING phase / first tick / anything outside those preconditions: the generic tick of the
+// thread-per-env kernel, executed redundantly by all lanes with the noise word shuffled from the
+// lane that holds its block.
+// ------------------------------------------------------------------------------------------
+// out-of-line copy of the per-env epilogue: keeps its register needs (binary64 reward code) out of the
+// simulator loop's 64-register budget
+__device__ __noinline__ void finish_env_philox(const StepArgs &a, int i, const float *s_clipped, double fw, int tick, int draws,
+                                               const uint4 &misc) {
+    const uint32_t gid = a.env.env_id_base + (uint32_t)i;
+    const int cid = a.env.d_cond_id ? a.env.d_cond_id[i] : (int)(gid % (uint32_t)a.env.n_cond);
+    const erlfill_condition c = a.env.d_cond[cid];
+    float clipped[ERLFILL_ACTION_DIM];
+#pragma unroll
+    for (int j = 0; j < ERLFILL_ACTION_DIM; ++j) clipped[j] = s_clipped[j];
+    SimResult sim;
+    sim.final_weight = fw; sim.tick = tick; sim.draws = draws;
+    finish_env<false>(a, i, c, clipped, sim, (int)clipped[9], misc);
+}
+
+constexpr int kWarpsPerCta = 8;
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr unsigned long long kSmallIncMax = 21474836ull;   // P * 2^-31 < 0.01  <=>  P <= 21474836
+constexpr int kSuperTicks = 128;
+
+struct WarpNoise {
+    uint32_t k0, k1, gid, step_idx;
+    int b0;         // lane L holds noise block b0 + L
+    uint4 raw;
+    __device__ __forceinline__ void fill(int block0, int lane) {
+        b0 = block0;
+        raw = philox4x32_10(k0, k1, gid, step_idx, (uint32_t)(block0 + lane), STREAM_TICK);
+    }
+    // 1 + u of draw n (0-based); warp-uniform call
+    __device__ __forceinline__ double opu(int n, int lane) {
+        const int blk = n >> 2;
+        if ((unsigned)(blk - b0) >= 32u) fill(blk, lane);
+        const int k = n & 3;
+        const uint32_t sel = k == 0 ? raw.x : (k == 1 ? raw.y : (k == 2 ? raw.z : raw.w));
+        return opu_from_u32(__shfl_sync(kFullMask, sel, blk - b0));
+    }
+};
+
+__device__ __forceinline__ bool hold_fast_ok(const Lane &s, const SimParams &p, int n) {
+    return in_hold(s, p) & (s.target <= 255.0) & (s.w >= 1.0) & (s.w < 2097152.0) &
+           ((n & ~3) + kSuperTicks <= ERLFILL_MAX_ITER) & (s.nochg + kSuperTicks <= ERLFILL_NOCHANGE_LIMIT);
+}
+
+// One super-block of the hold phase: draws n .. 4*(n>>2)+127, or up to the tick that reaches `lim`.
+__device__ __forceinline__ void hold_superblock(Lane &s, const SimParams &p, WarpNoise &nz, int lane, int &n,
+                                                bool &fin) {
+    const double w0 = s.w;
+    const bool lf0 = w0 < p.fast_w, lm0 = w0 < p.medium_w;
+    const double thr = lf0 ? p.fast_w : (lm0 ? p.medium_w : p.slow_w);
+    const double bin_end = __longlong_as_double((dbits(w0) & 0x7ff0000000000000LL) + 0x0010000000000000LL);
+    const double lim = thr < bin_end ? thr : bin_end;
+    const unsigned long long Dc = (unsigned long long)ceil(__dmul_rn(__dsub_rn(lim, w0), 2147483648.0));
+    const int b0 = n >> 2, skip = n & 3;
+    if (nz.b0 != b0) nz.fill(b0, lane);
+    const uint32_t ti = (uint32_t)(int)s.target;
+    unsigned long long P0 = (unsigned long long)ti * nz.raw.x, P1 = (unsigned long long)ti * nz.raw.y;
+    unsigned long long P2 = (unsigned long long)ti * nz.raw.z;
+    const unsigned long long P3 = (unsigned long long)ti * nz.raw.w;
+    const bool l0 = lane == 0;
+    const bool r0 = !(l0 & (skip > 0)), r1 = !(l0 & (skip > 1)), r2 = !(l0 & (skip > 2));   // draws before n: masked
+    P0 = r0 ? P0 : 0ull; P1 = r1 ? P1 : 0ull; P2 = r2 ? P2 : 0ull;
+    const unsigned long long S1 = P0, S2 = S1 + P1, S3 = S2 + P2, S4 = S3 + P3;
+    const unsigned long long total = (unsigned long long)__reduce_add_sync(kFullMask, (unsigned)S4 & 0x1FFFFFu) +
+                                     ((unsigned long long)__reduce_add_sync(kFullMask, (unsigned)(S4 >> 21)) << 21);
+    const bool ns0 = P0 > kSmallIncMax, ns1 = P1 > kSmallIncMax, ns2 = P2 > kSmallIncMax, ns3 = P3 > kSmallIncMax;
+    const double kScale = 1.0 / 2147483648.0;
+    if (total < Dc) {
+        // the whole super-block stays below lim: every add was exact
+        s.w = __dadd_rn(w0, __dmul_rn((double)total, kScale));
+        const bool small_here = (r0 & !ns0) | (r1 & !ns1) | (r2 & !ns2) | !ns3;
+        if (__any_sync(kFullMask, small_here)) {
+            const int tl = ns3 ? 3 : (ns2 ? 2 : (ns1 ? 1 : (ns0 ? 0 : -1)));
+            const int t_last = __reduce_max_sync(kFullMask, tl < 0 ? -1 : 4 * lane + tl);
+            s.nochg = t_last < 0 ? s.nochg + (kSuperTicks - skip) : kSuperTicks - 1 - t_last;
+        } else {
+            s.nochg = 0;
+        }
+        s.prev = s.w;
+        n = 4 * b0 + kSuperTicks;
+        return;
+    }
+    // some tick reaches lim: locate it with an exclusive scan of the per-lane sums
+    unsigned long long incl = S4;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const unsigned long long excl = incl - S4;
+    const unsigned long long c0 = excl + S1, c1 = excl + S2, c2 = excl + S3, c3 = excl + S4;
+    const int kk = (int)(c0 < Dc) + (int)(c1 < Dc) + (int)(c2 < Dc) + (int)(c3 < Dc);
+    const unsigned cross = __ballot_sync(kFullMask, kk < 4);
+    const int Lj = __ffs((int)cross) - 1;
+    const int kj = __shfl_sync(kFullMask, kk, Lj);
+    const unsigned long long before_l = kk == 0 ? excl : (kk == 1 ? c0 : (kk == 2 ? c1 : c2));
+    const unsigned long long Pj_l = kk == 0 ? P0 : (kk == 1 ? P1 : (kk == 2 ? P2 : P3));
+    const unsigned long long before = __shfl_sync(kFullMask, before_l, Lj);
+    const unsigned long long Pj = __shfl_sync(kFullMask, Pj_l, Lj);
+    const int j = 4 * Lj + kj;                                   // index of the crossing tick in the super-block
+    const double w_prev = __dadd_rn(w0, __dmul_rn((double)before, kScale));           // exact
+    const double w_new = __dadd_rn(w_prev, __dmul_rn((double)Pj, kScale));            // the reference's (rounded) add
+    // stagnation run ending at tick j-1
+    const int tb = 4 * lane;
+    const int tl = (ns3 & (tb + 3 < j)) ? 3 : ((ns2 & (tb + 2 < j)) ? 2 : ((ns1 & (tb + 1 < j)) ? 1 : ((ns0 & (tb < j)) ? 0 : -1)));
+    const int t_last = __reduce_max_sync(kFullMask, tl < 0 ? -1 : tb + tl);
+    const int run_before = t_last < 0 ? s.nochg + (j - skip) : j - 1 - t_last;
+    n = 4 * b0 + j + 1;
+    s.w = w_new;
+    const bool f = w_new < p.fast_w, m = w_new < p.medium_w, sl = w_new < p.slow_w;
+    if (!(f | m | sl)) { fin = true; return; }                  // normal finish
+    s.target = f ? p.fast_pos : (m ? p.medium_pos : p.slow_pos);
+    s.nochg = (fabs(w_new - w_prev) < 0.01) ? run_before + 1 : 0;
+    s.prev = w_new;
+    fin = (n > ERLFILL_MAX_ITER) | (s.nochg > ERLFILL_NOCHANGE_LIMIT);
+}
+
+__device__ __forceinline__ SimResult simulate_warp(const SimParams &p, double sysdelay, WarpNoise &nz, int lane) {
+    Lane s;
+    s.w = 0.0; s.open = 0.0; s.prev = 0.0; s.target = p.fast_pos; s.dd = 0.0; s.k = 0; s.nochg = 0;
+    int n = 1, delay = 0;
+    nz.fill(0, lane);
+    bool fin = generic_tick<true, kTabGlobal>(s, p, g_motor_tab, nz.opu(0, lane), sysdelay, 1, delay);
+    while (!fin) {
+        if (hold_fast_ok(s, p, n)) {
+            hold_superblock(s, p, nz, lane, n, fin);
+        } else {
+            const double o = nz.opu(n, lane);
+            n += 1;
+            fin = generic_tick<false, kTabGlobal>(s, p, g_motor_tab, o, sysdelay, n, delay);
+        }
+    }
+    SimResult res;
+    res.final_weight = s.w;
+    res.tick = n + delay;
+    res.draws = n;
+    return res;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) env_step_warp_kernel(const StepArgs a) {
+    __shared__ float s_clip[kWarpsPerCta][ERLFILL_ACTION_DIM + 2];
+    __shared__ double s_fw[kWarpsPerCta];
+    __shared__ int s_tick[kWarpsPerCta], s_draws[kWarpsPerCta];
+    __shared__ uint4 s_misc[kWarpsPerCta];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_env = a.env.n_env;
+    const int i = blockIdx.x * kWarpsPerCta + warp;
+    const uint32_t k0 = (uint32_t)a.env.seed, k1 = (uint32_t)(a.env.seed >> 32);
+    if (i < n_env) {                                            // warp-uniform
+        const uint32_t gid = a.env.env_id_base + (uint32_t)i;
+        const int cid = a.env.d_cond_id ? a.env.d_cond_id[i] : (int)(gid % (uint32_t)a.env.n_cond);
+        const erlfill_condition *c = a.env.d_cond + cid;
+        float v = 0.f;
+        if (lane < ERLFILL_ACTION_DIM) {
+            v = __ldg(a.d_actions + (size_t)i * ERLFILL_ACTION_DIM + lane);
+            const float lo = c->lo[lane], hi = c->hi[lane];
+            v = v < lo ? lo : v;
+            v = v > hi ? hi : v;
+            s_clip[warp][lane] = v;
+        }
+        const int iv = (int)v;                                  // int() truncation (VirtualWeightController.py:71-83)
+        SimParams p;
+        p.fast_w = (double)__shfl_sync(kFullMask, iv, 0);
+        p.medium_w = (double)__shfl_sync(kFullMask, iv, 1);
+        p.slow_w = (double)__shfl_sync(kFullMask, iv, 2);
+        p.fast_pos = (double)__shfl_sync(kFullMask, iv, 3);
+        p.medium_pos = (double)__shfl_sync(kFullMask, iv, 4);
+        p.slow_pos = (double)__shfl_sync(kFullMask, iv, 5);
+        p.fast_delay = __shfl_sync(kFullMask, iv, 6);
+        p.medium_delay = __shfl_sync(kFullMask, iv, 7);
+        p.slow_delay = __shfl_sync(kFullMask, iv, 8);
+        p.sane = (p.fast_pos >= 0) & (p.medium_pos >= 0) & (p.slow_pos >= 0);
+        const uint4 misc = philox4x32_10(k0, k1, gid, a.step_idx, 0u, STREAM_MISC);
+        const double sysdelay = 15.0 + 35.0 * u32_to_unit(misc.x);         // uniform(15, 50): :137
+        WarpNoise nz;
+        nz.k0 = k0; nz.k1 = k1; nz.gid = gid; nz.step_idx = a.step_idx; nz.b0 = 0;
+        const SimResult sim = simulate_warp(p, sysdelay, nz, lane);
+        if (lane == 0) {
+            s_fw[warp] = sim.final_weight;
+            s_tick[warp] = sim.tick;
+            s_draws[warp] = sim.draws;
+            s_misc[warp] = misc;
+        }
+    }
+    __syncthreads();
+    // reward / done / reset / stores: the first kWarpsPerCta threads take one env each
+    if (threadIdx.x < 32) {
+        const int e = threadIdx.x, ie = blockIdx.x * kWarpsPerCta + e;
+        int draws = 0;
+        if (e < kWarpsPerCta && ie < n_env) {
+            draws = s_draws[e];
+            finish_env_philox(a, ie, s_clip[e], s_fw[e], s_tick[e], draws, s_misc[e]);
+        }
+        if (a.out.d_tick_sum) {
+            const int sum = __reduce_add_sync(kFullMask, draws);
+            if (e == 0 && sum) atomicAdd(a.out.d_tick_sum, (unsigned long long)sum);
+        }
     }
 }
 
@@ -627,6 +853,8 @@ static int pick_block(int n_env) {
     return 128;
 }
 
+static int g_env_step_mode = ERLFILL_SIM_AUTO;
+
 static bool env_ok(const erlfill_env_batch *e) {
     return e && e->n_env > 0 && e->n_cond > 0 && e->d_cond && e->d_step_counter && e->d_episode_counter &&
            e->d_ring_len && e->d_ring_head && e->d_ring && e->d_obs;
@@ -649,6 +877,13 @@ int erlfill_device_ok(void) {
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
     cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
     return (major == 10 && minor == 0) ? 1 : 0;
+}
+
+int erlfill_env_step_set_mode(int mode) {
+    if (mode != ERLFILL_SIM_AUTO && mode != ERLFILL_SIM_THREAD_PER_ENV && mode != ERLFILL_SIM_WARP_PER_ENV)
+        return ERLFILL_ERR_ARG;
+    g_env_step_mode = mode;
+    return ERLFILL_OK;
 }
 
 int erlfill_env_reset(const erlfill_env_batch *env, const uint8_t *d_mask, uint32_t step_idx,
@@ -692,8 +927,15 @@ int erlfill_env_step(const erlfill_env_batch *env, const float *d_actions, uint3
     a.actions_aligned16 = ((uintptr_t)d_actions & 15u) == 0;
     const int block = pick_block(env->n_env);
     const int grid = (env->n_env + block - 1) / block;
-    if (a.d_u) env_step_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(a);
-    else env_step_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(a);
+    if (a.d_u) {
+        // injected binary64 noise is not on the 2^-31 grid: thread-per-env kernel, binary64 throughout
+        env_step_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(a);
+    } else if (g_env_step_mode == ERLFILL_SIM_THREAD_PER_ENV) {
+        env_step_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(a);
+    } else {
+        const int wgrid = (env->n_env + kWarpsPerCta - 1) / kWarpsPerCta;
+        env_step_warp_kernel<<<wgrid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(a);
+    }
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
 }

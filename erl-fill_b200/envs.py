@@ -27,10 +27,13 @@ class VecFillEnv:
     conditions : list of dicts {target_weight, target_weight_err, target_time, bounds}
     cond_id    : optional int32[N]; default env (env_id_base + i) uses condition (env_id_base + i) % len(conditions)
     kind       : "multi" (MutiConditionEnv reward) or "single" (WeightEnv reward v2)
+    sim_mode   : "auto" | "warp" (one warp per env, integer hold phase) | "thread" (one thread per env)
     """
 
+    SIM_MODES = {"auto": L.SIM_AUTO, "thread": L.SIM_THREAD_PER_ENV, "warp": L.SIM_WARP_PER_ENV}
+
     def __init__(self, conditions, n_env, kind="multi", max_steps=100, seed=0, device="cuda",
-                 env_id_base=0, cond_id=None, auto_reset=True):
+                 env_id_base=0, cond_id=None, auto_reset=True, sim_mode="auto"):
         L.require_device()
         self.device = torch.device(device)
         self.n_env = int(n_env)
@@ -39,6 +42,7 @@ class VecFillEnv:
         self.seed = int(seed)
         self.env_id_base = int(env_id_base)
         self.auto_reset = bool(auto_reset)
+        self.sim_mode = self.SIM_MODES[sim_mode]      # which simulator kernel (bit-identical results; see erlfill.h)
         self.conditions = list(conditions)
         conds = (L.Condition * len(conditions))(*[
             L.make_condition(c["target_weight"], c["target_weight_err"], c["target_time"], c["bounds"])
@@ -112,6 +116,7 @@ class VecFillEnv:
         nz, nzp = self._noise(noise_u, reset_u)
         ar = self.auto_reset if auto_reset is None else bool(auto_reset)
         with torch.cuda.device(self.device):
+            L.check(L.lib().erlfill_env_step_set_mode(C.c_int(self.sim_mode)), "erlfill_env_step_set_mode")
             L.check(L.lib().erlfill_env_step(C.byref(b), L.ptr(actions), C.c_uint32(self.step_idx & 0xFFFFFFFF),
                                              C.c_int(int(ar)), nzp, C.byref(self._out), L.stream_ptr()),
                     "erlfill_env_step")

@@ -129,6 +129,11 @@ int erlfill_env_step(const erlfill_env_batch *env, const float *d_actions, uint3
                      int auto_reset, const erlfill_noise *noise, const erlfill_step_out *out,
                      void *stream);
 
+/* Which simulator kernel erlfill_env_step launches for Philox noise (injected noise always uses the
+ * thread-per-env binary64 kernel).  Both produce bit-identical results; AUTO = warp per env. */
+typedef enum { ERLFILL_SIM_AUTO = 0, ERLFILL_SIM_THREAD_PER_ENV = 1, ERLFILL_SIM_WARP_PER_ENV = 2 } erlfill_sim_mode;
+int erlfill_env_step_set_mode(int mode);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Policy side of the rollout                                                                  */
 /* ------------------------------------------------------------------------------------------ */

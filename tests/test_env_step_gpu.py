@@ -87,15 +87,16 @@ def test_dropin_env_episodes_match_reference(golden_dir):
     assert n_f32 >= 50 and n_done >= 15
 
 
+@pytest.mark.parametrize("sim_mode", ["warp", "thread"])
 @pytest.mark.parametrize("kind,n_env,max_steps", [("multi", 3000, 7), ("single", 1111, 5)])
-def test_philox_batch_matches_oracle(kind, n_env, max_steps):
+def test_philox_batch_matches_oracle(kind, n_env, max_steps, sim_mode):
     """Philox mode, ragged N (not a multiple of the CTA size), three conditions round-robin, random
     actions 10 % outside the bounds, auto-reset: every output equals the C oracle's."""
     import erlfill_b200 as E
     K = E.conditions
     cond_dicts = list(K.EXPERIMENT_3.values()) if kind == "multi" else [K.SINGLE_25KG]
     seed, base = 0x1234ABCD5678, 777
-    env = E.VecFillEnv(cond_dicts, n_env, kind=kind, max_steps=max_steps, seed=seed, env_id_base=base)
+    env = E.VecFillEnv(cond_dicts, n_env, kind=kind, max_steps=max_steps, seed=seed, env_id_base=base, sim_mode=sim_mode)
     oc = [O.make_condition(c["target_weight"], c["target_weight_err"], c["target_time"], c["bounds"]) for c in cond_dicts]
     ref = O.BatchEnv(O.ENV_MULTI if kind == "multi" else O.ENV_SINGLE, oc, n_env, max_steps=max_steps, seed=seed,
                      env_id_base=base)
@@ -136,8 +137,8 @@ def test_full_size_properties():
     cid = torch.arange(n) % 3
     a = (lo[cid] + torch.rand(n, 10, generator=g) * (hi[cid] - lo[cid])).cuda()
 
-    def run(n_env, base, actions):
-        env = E.VecFillEnv(conds, n_env, kind="multi", seed=42, env_id_base=base)
+    def run(n_env, base, actions, sim_mode="warp"):
+        env = E.VecFillEnv(conds, n_env, kind="multi", seed=42, env_id_base=base, sim_mode=sim_mode)
         env.step(actions.contiguous())
         torch.cuda.synchronize()
         return env
@@ -149,6 +150,10 @@ def test_full_size_properties():
     assert torch.equal(torch.cat([h0.final_weight, h1.final_weight]), full.final_weight)
     assert torch.equal(torch.cat([h0.reward, h1.reward]), full.reward)
     assert int(full.tick_sum.item()) == int(full.ticks.sum().item())
+    # the two simulator kernels (integer hold phase vs serial binary64) agree bit for bit on all 65,536 envs
+    thr = run(n, 0, a, sim_mode="thread")
+    for f in ("final_weight", "total_time", "ticks", "reward", "next_state", "done", "obs"):
+        assert torch.equal(getattr(thr, f), getattr(full, f)), f
     t = full.ticks.float()
     assert 200 < t.min() and t.max() <= 5001 and 900 < t.mean() < 1800
     # spot-check 64 envs against the oracle
@@ -164,3 +169,47 @@ def test_full_size_properties():
                                     C.c_uint32(int(i)), C.c_uint32(0), C.byref(o))
         assert o.final_weight == float(full.final_weight[i].item())
         assert o.ticks == int(full.ticks[i].item())
+
+
+@pytest.mark.parametrize("sim_mode", ["warp", "thread"])
+def test_simulator_edge_cases_philox(sim_mode):
+    """Philox noise, parameters the exactness argument of the integer hold phase singles out (thresholds on a
+    power of two, reachable medium stage, openings 0/1/2 with stagnation counting and the stagnation stop, the
+    iteration cap, openings above the fast-path limit) plus 500 random parameter sets: ticks, total_time and
+    final_weight equal the oracle's serial binary64 loop bit for bit."""
+    import erlfill_b200 as E
+    rng = random.Random(11)
+    cases = [[25000, 16384, 0, 24900, 100, 100, 100, 40, 3, 3, 300],
+             [25000, 8192, 16384, 24900, 100, 100, 100, 40, 17, 3, 300],
+             [25000, 16383, 16385, 16390, 100, 100, 100, 60, 30, 30, 300],
+             [25000, 12000, 0, 24950, 200, 150, 150, 55, 4, 1, 400],
+             [25000, 12000, 0, 24950, 200, 150, 150, 55, 4, 0, 400],
+             [25000, 12000, 0, 24950, 200, 150, 150, 55, 4, 2, 400],
+             [3000, 1000, 2000, 3000, 10, 10, 10, 1, 1, 1, 100],
+             [25000, 20000, 0, 24990, 100, 100, 100, 200, 3, 255, 300],
+             [25000, 20000, 0, 24990, 100, 100, 100, 300, 3, 5, 300],
+             [600000, 300000, 0, 600000, 100, 100, 100, 255, 3, 250, 300],
+             [25000, 0, 0, 24000, 100, 100, 100, 50, 3, 50, 300],
+             [100, 50, 0, 90, 1, 1, 1, 2, 2, 2, 1],
+             [25000, 12000, 0, 24950, 200, 150, 150, 0, 4, 12, 400],
+             [25000, 12000, 0, 24950, 200, 150, 150, -5, 4, 12, 400]]
+    for _ in range(500):
+        tw = rng.choice([25000, 20000, 15000])
+        cases.append([tw, rng.randint(3000, 23000), rng.choice([0, 1, rng.randint(0, tw)]), rng.randint(tw - 300, tw + 25),
+                      rng.randint(60, 300), rng.randint(60, 200), rng.randint(60, 200), rng.randint(1, 100),
+                      rng.randint(0, 30), rng.randint(0, 30), rng.randint(250, 500)])
+    p = np.array(cases, np.float64)
+    n = len(cases)
+    seed, base = 0xFEEDBEEF1234, 31
+    conds = [{"target_weight": int(c[0]), "target_weight_err": 25, "target_time": 2.5, "bounds": WIDE} for c in cases]
+    env = E.VecFillEnv(conds, n, kind="multi", cond_id=np.arange(n), auto_reset=False, seed=seed, env_id_base=base,
+                       sim_mode=sim_mode)
+    act = np.stack([p[:, 1], p[:, 2], p[:, 3], p[:, 7], p[:, 8], p[:, 9], p[:, 4], p[:, 5], p[:, 6], p[:, 10]], 1)
+    for step in range(2):
+        env.step(torch.tensor(act, dtype=torch.float32, device="cuda"))
+        torch.cuda.synchronize()
+        ticks, tt, fw = env.ticks.cpu().numpy(), env.total_time.cpu().numpy(), env.final_weight.cpu().numpy()
+        for i, c in enumerate(cases):
+            rn, rtt, rfw, _ = O.simulate_run_philox(c, seed, base + i, step)
+            assert (int(ticks[i]), float(tt[i])) == (rn, rtt), (i, c, step)
+            assert float(fw[i]).hex() == rfw.hex(), (i, c, step)
