@@ -84,7 +84,7 @@ def _sim_setup(args, rank, device):
     K = E.conditions
     n = args.n_env
     env = E.VecFillEnv([K.SINGLE_25KG], n, kind="single", max_steps=100, seed=0, device=device,
-                       env_id_base=rank * n)
+                       env_id_base=rank * n, sim_mode=args.sim_mode)
     if args.actions == "pid":
         a_host = torch.tensor(K.PID_EFFECTIVE_ACTION, dtype=torch.float32).repeat(n, 1)
     else:   # uniform in bounds (heavy divergence variant)
@@ -322,6 +322,7 @@ def main():
     ap.add_argument("--n-env", type=int, default=4096)
     ap.add_argument("--actions", default="pid", choices=["pid", "random"])
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--sim-mode", default="auto", choices=["auto", "warp", "thread"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

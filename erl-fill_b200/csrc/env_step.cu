@@ -41,6 +41,14 @@ constexpr int kTabGlobal = 4096;
 constexpr int kTabShared = 512;
 __device__ double2 g_motor_tab[kTabGlobal];
 
+// Motor trajectories from a hold state: g_traj[(A*101 + B)*64 + j] = opening after tick j+1 of the move from
+// opening A (speed 0) to target B, both integers 0..100; g_traj_len = number of ticks up to and including the
+// snap to B (0: no usable entry -- A == B, an opening below zero on the way, or k outside the motor table).
+constexpr int kTrajDim = 101;
+constexpr int kTrajLen = 64;
+__device__ double g_traj[kTrajDim * kTrajDim * kTrajLen];
+__device__ uint8_t g_traj_len[kTrajDim * kTrajDim];
+
 static std::mutex g_tab_mutex;
 static bool g_tab_ready[64] = {};
 
@@ -60,6 +68,38 @@ static int ensure_motor_table() {
         host_tab[k].y = speed / 1000;
     }
     ERLFILL_CUDA_TRY(cudaMemcpyToSymbol(g_motor_tab, host_tab, sizeof(host_tab)));
+    // trajectories: the generic tick's motor update (generic_tick below) iterated on the host with the same table
+    static double host_traj[kTrajDim * kTrajDim * kTrajLen];
+    static uint8_t host_len[kTrajDim * kTrajDim];
+    for (int A = 0; A < kTrajDim; ++A) {
+        for (int B = 0; B < kTrajDim; ++B) {
+            double *tr = host_traj + (size_t)(A * kTrajDim + B) * kTrajLen;
+            uint8_t &len = host_len[A * kTrajDim + B];
+            len = 0;
+            for (int j = 0; j < kTrajLen; ++j) tr[j] = 0.0;
+            if (A == B) continue;
+            double open = (double)A, dd = 0.0;
+            const double target = (double)B;
+            int k = 0, m = 0;
+            bool ok = true, snapped = false;
+            while (m < kTrajLen) {
+                const double diff = open - target;
+                const bool far = fabs(diff) > 1.0, fwd = diff < 0;
+                const bool accel = fwd ? (open < target - dd) : (open > dd);
+                k = far ? k + (accel ? 50 : -1) : 0;
+                if (k < 0 || k >= kTabGlobal) { ok = false; break; }
+                const double base = far ? open : target;
+                dd = host_tab[k].x;
+                open = base + (fwd ? host_tab[k].y : -host_tab[k].y);
+                if (open < 0.0) { ok = false; break; }
+                tr[m++] = open;
+                if (!far) { snapped = true; break; }
+            }
+            if (ok && snapped) len = (uint8_t)m;
+        }
+    }
+    ERLFILL_CUDA_TRY(cudaMemcpyToSymbol(g_traj, host_traj, sizeof(host_traj)));
+    ERLFILL_CUDA_TRY(cudaMemcpyToSymbol(g_traj_len, host_len, sizeof(host_len)));
     g_tab_ready[dev] = true;
     return ERLFILL_OK;
 }
@@ -587,136 +627,287 @@ __global__ void __launch_bounds__(kMaxBlock) env_step_kernel(const StepArgs a) {
 // thread-per-env kernel, executed redundantly by all lanes with the noise word shuffled from the
 // lane that holds its block.
 // ------------------------------------------------------------------------------------------
-// out-of-line copy of the per-env epilogue: keeps its register needs (binary64 reward code) out of the
-// simulator loop's 64-register budget
-__device__ __noinline__ void finish_env_philox(const StepArgs &a, int i, const float *s_clipped, double fw, int tick, int draws,
-                                               const uint4 &misc) {
-    const uint32_t gid = a.env.env_id_base + (uint32_t)i;
-    const int cid = a.env.d_cond_id ? a.env.d_cond_id[i] : (int)(gid % (uint32_t)a.env.n_cond);
-    const erlfill_condition c = a.env.d_cond[cid];
-    float clipped[ERLFILL_ACTION_DIM];
-#pragma unroll
-    for (int j = 0; j < ERLFILL_ACTION_DIM; ++j) clipped[j] = s_clipped[j];
-    SimResult sim;
-    sim.final_weight = fw; sim.tick = tick; sim.draws = draws;
-    finish_env<false>(a, i, c, clipped, sim, (int)clipped[9], misc);
-}
-
-constexpr int kWarpsPerCta = 8;
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr unsigned long long kSmallIncMax = 21474836ull;   // P * 2^-31 < 0.01  <=>  P <= 21474836
-constexpr int kSuperTicks = 128;
+constexpr int kNoiseBlocks = 2;                            // Philox blocks per lane
+constexpr int kWindow = 128 * kNoiseBlocks;                // draws held by the warp
 
 struct WarpNoise {
     uint32_t k0, k1, gid, step_idx;
-    int b0;         // lane L holds noise block b0 + L
-    uint4 raw;
+    int b0;         // the warp holds the draw window [4*b0, 4*b0 + kWindow): lane L has noise blocks b0 + 32*h + L
+    uint4 raw[kNoiseBlocks];
     __device__ __forceinline__ void fill(int block0, int lane) {
         b0 = block0;
-        raw = philox4x32_10(k0, k1, gid, step_idx, (uint32_t)(block0 + lane), STREAM_TICK);
+#pragma unroll
+        for (int h = 0; h < kNoiseBlocks; ++h)
+            raw[h] = philox4x32_10(k0, k1, gid, step_idx, (uint32_t)(block0 + 32 * h + lane), STREAM_TICK);
     }
-    // 1 + u of draw n (0-based); warp-uniform call
-    __device__ __forceinline__ double opu(int n, int lane) {
-        const int blk = n >> 2;
-        if ((unsigned)(blk - b0) >= 32u) fill(blk, lane);
-        const int k = n & 3;
-        const uint32_t sel = k == 0 ? raw.x : (k == 1 ? raw.y : (k == 2 ? raw.z : raw.w));
-        return opu_from_u32(__shfl_sync(kFullMask, sel, blk - b0));
+    // Philox word of draw t (0-based, inside the window); t may differ per lane
+    __device__ __forceinline__ uint32_t word(int t) const {
+        const int rel = t - 4 * b0, src = (rel >> 2) & 31, k = rel & 3, hh = rel >> 7;
+        uint32_t r = 0;
+#pragma unroll
+        for (int h = 0; h < kNoiseBlocks; ++h) {
+            const uint32_t xa = __shfl_sync(kFullMask, raw[h].x, src), xb = __shfl_sync(kFullMask, raw[h].y, src);
+            const uint32_t xc = __shfl_sync(kFullMask, raw[h].z, src), xd = __shfl_sync(kFullMask, raw[h].w, src);
+            const uint32_t v = k == 0 ? xa : (k == 1 ? xb : (k == 2 ? xc : xd));
+            r = hh == h ? v : r;
+        }
+        return r;
     }
 };
 
-__device__ __forceinline__ bool hold_fast_ok(const Lane &s, const SimParams &p, int n) {
-    return in_hold(s, p) & (s.target <= 255.0) & (s.w >= 1.0) & (s.w < 2097152.0) &
-           ((n & ~3) + kSuperTicks <= ERLFILL_MAX_ITER) & (s.nochg + kSuperTicks <= ERLFILL_NOCHANGE_LIMIT);
+__device__ __forceinline__ unsigned long long warp_sum_u44(unsigned long long v) {   // v < 2^44 per lane
+    return (unsigned long long)__reduce_add_sync(kFullMask, (unsigned)v & 0x3FFFFFu) +
+           ((unsigned long long)__reduce_add_sync(kFullMask, (unsigned)(v >> 22)) << 22);
 }
 
-// One super-block of the hold phase: draws n .. 4*(n>>2)+127, or up to the tick that reaches `lim`.
-__device__ __forceinline__ void hold_superblock(Lane &s, const SimParams &p, WarpNoise &nz, int lane, int &n,
-                                                bool &fin) {
-    const double w0 = s.w;
-    const bool lf0 = w0 < p.fast_w, lm0 = w0 < p.medium_w;
-    const double thr = lf0 ? p.fast_w : (lm0 ? p.medium_w : p.slow_w);
-    const double bin_end = __longlong_as_double((dbits(w0) & 0x7ff0000000000000LL) + 0x0010000000000000LL);
-    const double lim = thr < bin_end ? thr : bin_end;
-    const unsigned long long Dc = (unsigned long long)ceil(__dmul_rn(__dsub_rn(lim, w0), 2147483648.0));
-    const int b0 = n >> 2, skip = n & 3;
-    if (nz.b0 != b0) nz.fill(b0, lane);
+// sum of this lane's increments P = ti * x over the 4 draws of one noise block; draws with window index < skip
+// (already consumed) count as 0
+template <bool kMasked>
+__device__ __forceinline__ unsigned long long block_sum(uint32_t ti, const uint4 &r, int t0, int skip) {
+    unsigned long long a = (unsigned long long)ti * r.x, b = (unsigned long long)ti * r.y;
+    unsigned long long c = (unsigned long long)ti * r.z, d = (unsigned long long)ti * r.w;
+    if (kMasked) {
+        a = t0 + 0 >= skip ? a : 0ull; b = t0 + 1 >= skip ? b : 0ull;
+        c = t0 + 2 >= skip ? c : 0ull; d = t0 + 3 >= skip ? d : 0ull;
+    }
+    return (a + b) + (c + d);
+}
+
+// ---- hold phase ---------------------------------------------------------------------------
+// While w stays in one binade the reference's adds are exact (see the header of this section).  When w enters
+// the next binade its ulp doubles and the one add that crosses may round (a tie, round-half-even).  With
+// A = w/ulp0 the anchor in units of the ORIGINAL ulp (a multiple of 2^c after c crossings) the exact sum at
+// crossing c+1 is congruent to A modulo 4*2^c as long as the new binade is below 2^21 (the increments,
+// multiples of 2^-31, are multiples of 4*2^c*ulp0 there), so the tie resolves the same way whichever tick
+// crosses: A -> A -/+ 2^c when (A >> c) & 3 is 1 / 3.  The corrections of all binades below the stage
+// threshold are therefore folded into one anchor up front and the whole hold stretch is the integer test
+//     acc_j = sum_{t<=j} P_t  <  Dc = thr*2^31 - floor(A*ulp0*2^31)
+// over as many noise windows as it takes.  Only the draw that reaches thr is replayed with a real binary64 add
+// from its exact predecessor (whose anchor is the one of the binade the predecessor is in).
+// One boundary per tick is guaranteed by 2*target <= 2^e0.  tests/test_hold_superblock_model.py restates this
+// on the CPU against the oracle's serial loop.
+__device__ __forceinline__ double pow2d(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
+
+__device__ __forceinline__ unsigned long long round_anchor(unsigned long long A, int c) {
+    const unsigned r = (unsigned)(A >> c) & 3u;
+    const unsigned long long step = 1ull << c;
+    return (r & 1u) ? (r == 1u ? A - step : A + step) : A;
+}
+
+// w after `inc` (= acc * 2^-31, exact) has been added to the stretch's start value M * ulp0
+__device__ __forceinline__ double hold_value(unsigned long long M, int e0, double thr, double inc) {
+    const double u0 = pow2d(e0 - 52);
+    unsigned long long A = M;
+    int c = 0;
+    while (pow2d(e0 + c + 1) < thr && __dadd_rn(__dmul_rn((double)(long long)A, u0), inc) >= pow2d(e0 + c + 1)) {
+        A = round_anchor(A, c);
+        ++c;
+    }
+    return __dadd_rn(__dmul_rn((double)(long long)A, u0), inc);
+}
+
+__device__ __forceinline__ bool hold_caps_ok(const WarpNoise &nz, int n, int nochg) {
+    const int base = n >= 4 * nz.b0 + kWindow ? (n & ~3) : 4 * nz.b0;
+    return (base + kWindow <= ERLFILL_MAX_ITER) & (nochg + kWindow <= ERLFILL_NOCHANGE_LIMIT);
+}
+
+// Preconditions (checked by the caller): in_hold, target an integer 0..255, 1 <= w < thr <= 2^20,
+// 2*target <= 2^floor(log2 w), hold_caps_ok.
+__device__ __forceinline__ void hold_stretch(Lane &s, const SimParams &p, double thr, WarpNoise &nz, int lane, int &n,
+                                             bool &fin) {
+    const long long wb = dbits(s.w);
+    const int e0 = (int)((wb >> 52) & 0x7ff) - 1023;
+    const unsigned long long M = ((unsigned long long)wb & 0xFFFFFFFFFFFFFull) | (1ull << 52);
+    unsigned long long Dc;
+    {
+        unsigned long long A = M;
+        int c = 0;
+        while (pow2d(e0 + c + 1) < thr) { A = round_anchor(A, c); ++c; }
+        Dc = ((unsigned long long)(long long)thr << 31) - (A >> (21 - e0));
+    }
     const uint32_t ti = (uint32_t)(int)s.target;
-    unsigned long long P0 = (unsigned long long)ti * nz.raw.x, P1 = (unsigned long long)ti * nz.raw.y;
-    unsigned long long P2 = (unsigned long long)ti * nz.raw.z;
-    const unsigned long long P3 = (unsigned long long)ti * nz.raw.w;
-    const bool l0 = lane == 0;
-    const bool r0 = !(l0 & (skip > 0)), r1 = !(l0 & (skip > 1)), r2 = !(l0 & (skip > 2));   // draws before n: masked
-    P0 = r0 ? P0 : 0ull; P1 = r1 ? P1 : 0ull; P2 = r2 ? P2 : 0ull;
-    const unsigned long long S1 = P0, S2 = S1 + P1, S3 = S2 + P2, S4 = S3 + P3;
-    const unsigned long long total = (unsigned long long)__reduce_add_sync(kFullMask, (unsigned)S4 & 0x1FFFFFu) +
-                                     ((unsigned long long)__reduce_add_sync(kFullMask, (unsigned)(S4 >> 21)) << 21);
-    const bool ns0 = P0 > kSmallIncMax, ns1 = P1 > kSmallIncMax, ns2 = P2 > kSmallIncMax, ns3 = P3 > kSmallIncMax;
+    const uint32_t xs = ti ? (uint32_t)(kSmallIncMax / ti) : 0xffffffffu;   // increment < 0.01  <=>  x <= xs
     const double kScale = 1.0 / 2147483648.0;
-    if (total < Dc) {
-        // the whole super-block stays below lim: every add was exact
-        s.w = __dadd_rn(w0, __dmul_rn((double)total, kScale));
-        const bool small_here = (r0 & !ns0) | (r1 & !ns1) | (r2 & !ns2) | !ns3;
-        if (__any_sync(kFullMask, small_here)) {
-            const int tl = ns3 ? 3 : (ns2 ? 2 : (ns1 ? 1 : (ns0 ? 0 : -1)));
-            const int t_last = __reduce_max_sync(kFullMask, tl < 0 ? -1 : 4 * lane + tl);
-            s.nochg = t_last < 0 ? s.nochg + (kSuperTicks - skip) : kSuperTicks - 1 - t_last;
+    const int tb = 4 * lane;
+    unsigned long long acc = 0;
+    int nochg = s.nochg;
+    for (;;) {
+        if (n >= 4 * nz.b0 + kWindow) nz.fill(n >> 2, lane);
+        const int base = 4 * nz.b0;
+        if ((base + kWindow > ERLFILL_MAX_ITER) | (nochg + kWindow > ERLFILL_NOCHANGE_LIMIT)) break;
+        const int skip = n - base;
+        unsigned long long bs[kNoiseBlocks], lane_total = 0;
+        if (skip == 0) {
+#pragma unroll
+            for (int h = 0; h < kNoiseBlocks; ++h) { bs[h] = block_sum<false>(ti, nz.raw[h], 0, 0); lane_total += bs[h]; }
         } else {
-            s.nochg = 0;
+#pragma unroll
+            for (int h = 0; h < kNoiseBlocks; ++h) { bs[h] = block_sum<true>(ti, nz.raw[h], 128 * h + tb, skip); lane_total += bs[h]; }
         }
-        s.prev = s.w;
-        n = 4 * b0 + kSuperTicks;
+        const unsigned long long total = warp_sum_u44(lane_total);
+        if (acc + total < Dc) {
+            // every remaining draw of the window stays below thr
+            acc += total;
+            // stagnation counter: highest real draw whose increment is not small, whether any real draw is small
+            int tl = -1;
+            bool small_here = false;
+#pragma unroll
+            for (int h = 0; h < kNoiseBlocks; ++h) {
+                const uint32_t xv[4] = {nz.raw[h].x, nz.raw[h].y, nz.raw[h].z, nz.raw[h].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int t = 128 * h + tb + k;
+                    const bool real = t >= skip, sm = xv[k] <= xs;
+                    small_here |= real & sm;
+                    tl = (real & !sm) ? t : tl;
+                }
+            }
+            if (__any_sync(kFullMask, small_here)) {
+                const int t_last = __reduce_max_sync(kFullMask, tl);
+                nochg = t_last < 0 ? nochg + (kWindow - skip) : kWindow - 1 - t_last;
+            } else {
+                nochg = 0;
+            }
+            n = base + kWindow;
+            continue;
+        }
+        // some draw of this window reaches thr: find the noise block row, then the draw
+        int hx = 0;
+        unsigned long long row_before = acc;
+#pragma unroll
+        for (int h = 0; h < kNoiseBlocks - 1; ++h) {
+            const unsigned long long th = warp_sum_u44(bs[h]);
+            if (hx == h && row_before + th < Dc) { row_before += th; hx = h + 1; }
+        }
+        uint4 r = nz.raw[0];
+#pragma unroll
+        for (int h = 1; h < kNoiseBlocks; ++h) r = hx == h ? nz.raw[h] : r;
+        const int t0 = 128 * hx + tb;
+        const unsigned long long P0 = t0 + 0 >= skip ? (unsigned long long)ti * r.x : 0ull;
+        const unsigned long long P1 = t0 + 1 >= skip ? (unsigned long long)ti * r.y : 0ull;
+        const unsigned long long P2 = t0 + 2 >= skip ? (unsigned long long)ti * r.z : 0ull;
+        const unsigned long long P3 = t0 + 3 >= skip ? (unsigned long long)ti * r.w : 0ull;
+        const unsigned long long S1 = P0, S2 = S1 + P1, S3 = S2 + P2, S4 = S3 + P3;
+        unsigned long long incl = S4;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const unsigned long long excl = row_before + (incl - S4);
+        const unsigned long long c0 = excl + S1, c1 = excl + S2, c2 = excl + S3, c3 = excl + S4;
+        const int kk = (int)(c0 < Dc) + (int)(c1 < Dc) + (int)(c2 < Dc) + (int)(c3 < Dc);
+        const unsigned cross = __ballot_sync(kFullMask, kk < 4);
+        const int Lj = __ffs((int)cross) - 1;
+        const int kj = __shfl_sync(kFullMask, kk, Lj);
+        const unsigned long long before_l = kk == 0 ? excl : (kk == 1 ? c0 : (kk == 2 ? c1 : c2));
+        const unsigned long long Pj_l = kk == 0 ? P0 : (kk == 1 ? P1 : (kk == 2 ? P2 : P3));
+        const unsigned long long before = __shfl_sync(kFullMask, before_l, Lj);
+        const unsigned long long Pj = __shfl_sync(kFullMask, Pj_l, Lj);
+        const int j = 128 * hx + 4 * Lj + kj;                       // window index of the draw that reaches thr
+        const double w_prev = hold_value(M, e0, thr, __dmul_rn((double)(long long)before, kScale));   // exact
+        const double w_new = __dadd_rn(w_prev, __dmul_rn((double)(long long)Pj, kScale));   // the reference's (rounded) add
+        // stagnation run ending at draw j-1
+        int tlj = -1;
+#pragma unroll
+        for (int h = 0; h < kNoiseBlocks; ++h) {
+            const uint32_t xv[4] = {nz.raw[h].x, nz.raw[h].y, nz.raw[h].z, nz.raw[h].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int t = 128 * h + tb + k;
+                tlj = ((t >= skip) & (t < j) & (xv[k] > xs)) ? t : tlj;
+            }
+        }
+        const int t_last = __reduce_max_sync(kFullMask, tlj);
+        const int run_before = t_last < 0 ? nochg + (j - skip) : j - 1 - t_last;
+        n = base + j + 1;
+        s.w = w_new;
+        const bool f = w_new < p.fast_w, m = w_new < p.medium_w, sl = w_new < p.slow_w;
+        if (!(f | m | sl)) { fin = true; return; }              // normal finish
+        s.target = f ? p.fast_pos : (m ? p.medium_pos : p.slow_pos);
+        s.nochg = (fabs(w_new - w_prev) < 0.01) ? run_before + 1 : 0;
+        s.prev = w_new;
+        fin = (n > ERLFILL_MAX_ITER) | (s.nochg > ERLFILL_NOCHANGE_LIMIT);
         return;
     }
-    // some tick reaches lim: locate it with an exclusive scan of the per-lane sums
-    unsigned long long incl = S4;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long t = __shfl_up_sync(kFullMask, incl, d);
-        if (lane >= d) incl += t;
+    // a safety stop is within reach: hand the exact state to the generic ticks
+    s.w = hold_value(M, e0, thr, __dmul_rn((double)(long long)acc, kScale));
+    s.prev = s.w;
+    s.nochg = nochg;
+}
+
+// MOVING phase from a hold state (open == A, speed 0) to a new target B, A != B integers in 0..100: the motor
+// trajectory open_1..open_m (m <= 55, the last entry is the snap to B) does not depend on the noise, so it is
+// read from the host-built table g_traj.  Lane j forms the tick's increment open_j * (1 + u_j); the weight is
+// then accumulated by m dependent binary64 adds in the reference's order.  All increments are >= 0, so w is
+// non-decreasing and "same stage flags at both ends" means no stage change happened inside the phase; with
+// every increment >= 0.011 the stagnation counter is 0 afterwards.  Returns false (nothing committed) when a
+// precondition fails; the caller then runs generic ticks.
+__device__ __forceinline__ bool moving_phase(Lane &s, const SimParams &p, WarpNoise &nz, int lane, int &n, int &delay,
+                                             bool first, double sysdelay) {
+    const int A = (int)s.open, B = (int)s.target;
+    if (!((s.k == 0) & ((double)A == s.open) & ((double)B == s.target) & ((unsigned)A < (unsigned)kTrajDim) &
+          ((unsigned)B < (unsigned)kTrajDim)))
+        return false;
+    const int pair = A * kTrajDim + B;
+    const int m = g_traj_len[pair];
+    if (m == 0 || n + m > ERLFILL_MAX_ITER) return false;
+    const double w0 = s.w;
+    const bool lf = w0 < p.fast_w, lm = w0 < p.medium_w, ls = w0 < p.slow_w;
+    const double stage_target = lf ? p.fast_pos : (lm ? p.medium_pos : p.slow_pos);
+    if (!(lf | lm | ls) || dbits(stage_target) != dbits(s.target)) return false;
+    if (n + m > 4 * nz.b0 + kWindow) nz.fill(n >> 2, lane);
+    const double *tr = g_traj + (size_t)pair * kTrajLen;
+    const bool v_lo = lane < m, v_hi = lane + 32 < m;
+    const double o_lo = v_lo ? tr[lane] : 1.0;
+    const double p_lo = __dmul_rn(o_lo, opu_from_u32(nz.word(n + lane)));
+    double p_hi = 1.0;
+    if (m > 32) {
+        const double o_hi = v_hi ? tr[lane + 32] : 1.0;
+        p_hi = __dmul_rn(o_hi, opu_from_u32(nz.word(n + 32 + lane)));
     }
-    const unsigned long long excl = incl - S4;
-    const unsigned long long c0 = excl + S1, c1 = excl + S2, c2 = excl + S3, c3 = excl + S4;
-    const int kk = (int)(c0 < Dc) + (int)(c1 < Dc) + (int)(c2 < Dc) + (int)(c3 < Dc);
-    const unsigned cross = __ballot_sync(kFullMask, kk < 4);
-    const int Lj = __ffs((int)cross) - 1;
-    const int kj = __shfl_sync(kFullMask, kk, Lj);
-    const unsigned long long before_l = kk == 0 ? excl : (kk == 1 ? c0 : (kk == 2 ? c1 : c2));
-    const unsigned long long Pj_l = kk == 0 ? P0 : (kk == 1 ? P1 : (kk == 2 ? P2 : P3));
-    const unsigned long long before = __shfl_sync(kFullMask, before_l, Lj);
-    const unsigned long long Pj = __shfl_sync(kFullMask, Pj_l, Lj);
-    const int j = 4 * Lj + kj;                                   // index of the crossing tick in the super-block
-    const double w_prev = __dadd_rn(w0, __dmul_rn((double)before, kScale));           // exact
-    const double w_new = __dadd_rn(w_prev, __dmul_rn((double)Pj, kScale));            // the reference's (rounded) add
-    // stagnation run ending at tick j-1
-    const int tb = 4 * lane;
-    const int tl = (ns3 & (tb + 3 < j)) ? 3 : ((ns2 & (tb + 2 < j)) ? 2 : ((ns1 & (tb + 1 < j)) ? 1 : ((ns0 & (tb < j)) ? 0 : -1)));
-    const int t_last = __reduce_max_sync(kFullMask, tl < 0 ? -1 : tb + tl);
-    const int run_before = t_last < 0 ? s.nochg + (j - skip) : j - 1 - t_last;
-    n = 4 * b0 + j + 1;
-    s.w = w_new;
-    const bool f = w_new < p.fast_w, m = w_new < p.medium_w, sl = w_new < p.slow_w;
-    if (!(f | m | sl)) { fin = true; return; }                  // normal finish
-    s.target = f ? p.fast_pos : (m ? p.medium_pos : p.slow_pos);
-    s.nochg = (fabs(w_new - w_prev) < 0.01) ? run_before + 1 : 0;
-    s.prev = w_new;
-    fin = (n > ERLFILL_MAX_ITER) | (s.nochg > ERLFILL_NOCHANGE_LIMIT);
+    if (__any_sync(kFullMask, (v_lo & (p_lo < 0.011)) | (v_hi & (p_hi < 0.011)))) return false;
+    double w = __dadd_rn(w0, __shfl_sync(kFullMask, p_lo, 0));
+    if (first) w = __dadd_rn(w, __dmul_rn(s.target, sysdelay));            // one-time stage delay: :192-212
+    const int m_lo = m < 32 ? m : 32;
+    for (int j = 1; j < m_lo; ++j) w = __dadd_rn(w, __shfl_sync(kFullMask, p_lo, j));
+    for (int j = 32; j < m; ++j) w = __dadd_rn(w, __shfl_sync(kFullMask, p_hi, j - 32));
+    if (((w < p.fast_w) != lf) | ((w < p.medium_w) != lm) | ((w < p.slow_w) != ls)) return false;
+    if (first) delay = lf ? p.fast_delay : (lm ? p.medium_delay : p.slow_delay);
+    s.w = w; s.prev = w; s.nochg = 0;
+    s.open = s.target; s.k = 0; s.dd = 0.0;
+    n += m;
+    return true;
 }
 
 __device__ __forceinline__ SimResult simulate_warp(const SimParams &p, double sysdelay, WarpNoise &nz, int lane) {
     Lane s;
     s.w = 0.0; s.open = 0.0; s.prev = 0.0; s.target = p.fast_pos; s.dd = 0.0; s.k = 0; s.nochg = 0;
-    int n = 1, delay = 0;
+    int n = 0, delay = 0;
+    bool fin = false, first = true;
     nz.fill(0, lane);
-    bool fin = generic_tick<true, kTabGlobal>(s, p, g_motor_tab, nz.opu(0, lane), sysdelay, 1, delay);
     while (!fin) {
-        if (hold_fast_ok(s, p, n)) {
-            hold_superblock(s, p, nz, lane, n, fin);
-        } else {
-            const double o = nz.opu(n, lane);
-            n += 1;
-            fin = generic_tick<false, kTabGlobal>(s, p, g_motor_tab, o, sysdelay, n, delay);
+        if (in_hold(s, p)) {
+            const double thr = s.w < p.fast_w ? p.fast_w : (s.w < p.medium_w ? p.medium_w : p.slow_w);
+            const double bin_start = __longlong_as_double(dbits(s.w) & 0x7ff0000000000000LL);
+            if (!first & (s.target <= 255.0) & (s.w >= 1.0) & (thr <= 1048576.0) & (2.0 * s.target <= bin_start) &
+                hold_caps_ok(nz, n, s.nochg)) {
+                hold_stretch(s, p, thr, nz, lane, n, fin);
+                continue;
+            }
+        } else if (moving_phase(s, p, nz, lane, n, delay, first, sysdelay)) {
+            first = false;
+            continue;
         }
+        // generic tick (first tick without a table entry, openings outside 0..100, stage change while moving, ...)
+        if (n >= 4 * nz.b0 + kWindow) nz.fill(n >> 2, lane);
+        const double o = opu_from_u32(nz.word(n));
+        n += 1;
+        if (first) fin = generic_tick<true, kTabGlobal>(s, p, g_motor_tab, o, sysdelay, n, delay);
+        else fin = generic_tick<false, kTabGlobal>(s, p, g_motor_tab, o, sysdelay, n, delay);
+        first = false;
     }
     SimResult res;
     res.final_weight = s.w;
@@ -725,64 +916,76 @@ __device__ __forceinline__ SimResult simulate_warp(const SimParams &p, double sy
     return res;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) env_step_warp_kernel(const StepArgs a) {
-    __shared__ float s_clip[kWarpsPerCta][ERLFILL_ACTION_DIM + 2];
-    __shared__ double s_fw[kWarpsPerCta];
-    __shared__ int s_tick[kWarpsPerCta], s_draws[kWarpsPerCta];
-    __shared__ uint4 s_misc[kWarpsPerCta];
+constexpr int kWarpsPerCta = 4;
+
+// K1: the simulator, one warp per env.  Results travel to K2 in the step's own output slots (no workspace):
+// final_weight (binary64) in next_state[i], tick count in reward[i], draws in obs[i].x.
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 32 / kWarpsPerCta) env_sim_warp_kernel(const StepArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_env = a.env.n_env;
     const int i = blockIdx.x * kWarpsPerCta + warp;
+    if (i >= a.env.n_env) return;                               // warp-uniform
     const uint32_t k0 = (uint32_t)a.env.seed, k1 = (uint32_t)(a.env.seed >> 32);
-    if (i < n_env) {                                            // warp-uniform
+    const uint32_t gid = a.env.env_id_base + (uint32_t)i;
+    const int cid = a.env.d_cond_id ? a.env.d_cond_id[i] : (int)(gid % (uint32_t)a.env.n_cond);
+    const erlfill_condition *c = a.env.d_cond + cid;
+    float v = 0.f;
+    if (lane < ERLFILL_ACTION_DIM) {
+        v = __ldg(a.d_actions + (size_t)i * ERLFILL_ACTION_DIM + lane);
+        const float lo = c->lo[lane], hi = c->hi[lane];
+        v = v < lo ? lo : v;
+        v = v > hi ? hi : v;
+    }
+    const int iv = (int)v;                                      // int() truncation (VirtualWeightController.py:71-83)
+    SimParams p;
+    p.fast_w = (double)__shfl_sync(kFullMask, iv, 0);
+    p.medium_w = (double)__shfl_sync(kFullMask, iv, 1);
+    p.slow_w = (double)__shfl_sync(kFullMask, iv, 2);
+    p.fast_pos = (double)__shfl_sync(kFullMask, iv, 3);
+    p.medium_pos = (double)__shfl_sync(kFullMask, iv, 4);
+    p.slow_pos = (double)__shfl_sync(kFullMask, iv, 5);
+    p.fast_delay = __shfl_sync(kFullMask, iv, 6);
+    p.medium_delay = __shfl_sync(kFullMask, iv, 7);
+    p.slow_delay = __shfl_sync(kFullMask, iv, 8);
+    p.sane = (p.fast_pos >= 0) & (p.medium_pos >= 0) & (p.slow_pos >= 0);
+    const uint4 misc = philox4x32_10(k0, k1, gid, a.step_idx, 0u, STREAM_MISC);
+    const double sysdelay = 15.0 + 35.0 * u32_to_unit(misc.x);             // uniform(15, 50): :137
+    WarpNoise nz;
+    nz.k0 = k0; nz.k1 = k1; nz.gid = gid; nz.step_idx = a.step_idx; nz.b0 = 0;
+    const SimResult sim = simulate_warp(p, sysdelay, nz, lane);
+    if (lane == 0) {
+        reinterpret_cast<double *>(a.out.d_next_state)[i] = sim.final_weight;
+        reinterpret_cast<int *>(a.out.d_reward)[i] = sim.tick;
+        reinterpret_cast<int *>(a.env.d_obs)[2 * i] = sim.draws;
+    }
+}
+
+// K2: reward / state / done / auto-reset / stores, one thread per env (E2/E3/E4)
+__global__ void __launch_bounds__(128) env_finish_kernel(const StepArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int draws = 0;
+    if (i < a.env.n_env) {
         const uint32_t gid = a.env.env_id_base + (uint32_t)i;
         const int cid = a.env.d_cond_id ? a.env.d_cond_id[i] : (int)(gid % (uint32_t)a.env.n_cond);
-        const erlfill_condition *c = a.env.d_cond + cid;
-        float v = 0.f;
-        if (lane < ERLFILL_ACTION_DIM) {
-            v = __ldg(a.d_actions + (size_t)i * ERLFILL_ACTION_DIM + lane);
-            const float lo = c->lo[lane], hi = c->hi[lane];
-            v = v < lo ? lo : v;
-            v = v > hi ? hi : v;
-            s_clip[warp][lane] = v;
+        const erlfill_condition c = a.env.d_cond[cid];
+        float clipped[ERLFILL_ACTION_DIM];
+#pragma unroll
+        for (int j = 0; j < ERLFILL_ACTION_DIM; ++j) {
+            float v = __ldg(a.d_actions + (size_t)i * ERLFILL_ACTION_DIM + j);
+            v = v < c.lo[j] ? c.lo[j] : v;
+            v = v > c.hi[j] ? c.hi[j] : v;
+            clipped[j] = v;
         }
-        const int iv = (int)v;                                  // int() truncation (VirtualWeightController.py:71-83)
-        SimParams p;
-        p.fast_w = (double)__shfl_sync(kFullMask, iv, 0);
-        p.medium_w = (double)__shfl_sync(kFullMask, iv, 1);
-        p.slow_w = (double)__shfl_sync(kFullMask, iv, 2);
-        p.fast_pos = (double)__shfl_sync(kFullMask, iv, 3);
-        p.medium_pos = (double)__shfl_sync(kFullMask, iv, 4);
-        p.slow_pos = (double)__shfl_sync(kFullMask, iv, 5);
-        p.fast_delay = __shfl_sync(kFullMask, iv, 6);
-        p.medium_delay = __shfl_sync(kFullMask, iv, 7);
-        p.slow_delay = __shfl_sync(kFullMask, iv, 8);
-        p.sane = (p.fast_pos >= 0) & (p.medium_pos >= 0) & (p.slow_pos >= 0);
-        const uint4 misc = philox4x32_10(k0, k1, gid, a.step_idx, 0u, STREAM_MISC);
-        const double sysdelay = 15.0 + 35.0 * u32_to_unit(misc.x);         // uniform(15, 50): :137
-        WarpNoise nz;
-        nz.k0 = k0; nz.k1 = k1; nz.gid = gid; nz.step_idx = a.step_idx; nz.b0 = 0;
-        const SimResult sim = simulate_warp(p, sysdelay, nz, lane);
-        if (lane == 0) {
-            s_fw[warp] = sim.final_weight;
-            s_tick[warp] = sim.tick;
-            s_draws[warp] = sim.draws;
-            s_misc[warp] = misc;
-        }
+        SimResult sim;
+        sim.final_weight = reinterpret_cast<const double *>(a.out.d_next_state)[i];
+        sim.tick = reinterpret_cast<const int *>(a.out.d_reward)[i];
+        sim.draws = reinterpret_cast<const int *>(a.env.d_obs)[2 * i];
+        draws = sim.draws;
+        const uint4 misc = philox4x32_10((uint32_t)a.env.seed, (uint32_t)(a.env.seed >> 32), gid, a.step_idx, 0u, STREAM_MISC);
+        finish_env<false>(a, i, c, clipped, sim, (int)clipped[9], misc);
     }
-    __syncthreads();
-    // reward / done / reset / stores: the first kWarpsPerCta threads take one env each
-    if (threadIdx.x < 32) {
-        const int e = threadIdx.x, ie = blockIdx.x * kWarpsPerCta + e;
-        int draws = 0;
-        if (e < kWarpsPerCta && ie < n_env) {
-            draws = s_draws[e];
-            finish_env_philox(a, ie, s_clip[e], s_fw[e], s_tick[e], draws, s_misc[e]);
-        }
-        if (a.out.d_tick_sum) {
-            const int sum = __reduce_add_sync(kFullMask, draws);
-            if (e == 0 && sum) atomicAdd(a.out.d_tick_sum, (unsigned long long)sum);
-        }
+    if (a.out.d_tick_sum) {
+        const int sum = __reduce_add_sync(kFullMask, draws);
+        if ((threadIdx.x & 31) == 0 && sum) atomicAdd(a.out.d_tick_sum, (unsigned long long)sum);
     }
 }
 
@@ -934,7 +1137,9 @@ int erlfill_env_step(const erlfill_env_batch *env, const float *d_actions, uint3
         env_step_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(a);
     } else {
         const int wgrid = (env->n_env + kWarpsPerCta - 1) / kWarpsPerCta;
-        env_step_warp_kernel<<<wgrid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(a);
+        env_sim_warp_kernel<<<wgrid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(a);
+        ERLFILL_CUDA_TRY(cudaGetLastError());
+        env_finish_kernel<<<(env->n_env + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     }
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
