@@ -750,21 +750,35 @@ __device__ __forceinline__ void hold_stretch(Lane &s, const SimParams &p, double
         if (acc + total < Dc) {
             // every remaining draw of the window stays below thr
             acc += total;
-            // stagnation counter: highest real draw whose increment is not small, whether any real draw is small
-            int tl = -1;
-            bool small_here = false;
+            // stagnation counter (VirtualWeightController.py:216-221): does any real draw have an increment < 0.01?
+            bool small_here;
+            if (skip == 0) {
+                uint32_t mn = 0xffffffffu;
 #pragma unroll
-            for (int h = 0; h < kNoiseBlocks; ++h) {
-                const uint32_t xv[4] = {nz.raw[h].x, nz.raw[h].y, nz.raw[h].z, nz.raw[h].w};
+                for (int h = 0; h < kNoiseBlocks; ++h)
+                    mn = min(mn, min(min(nz.raw[h].x, nz.raw[h].y), min(nz.raw[h].z, nz.raw[h].w)));
+                small_here = mn <= xs;
+            } else {
+                small_here = false;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int t = 128 * h + tb + k;
-                    const bool real = t >= skip, sm = xv[k] <= xs;
-                    small_here |= real & sm;
-                    tl = (real & !sm) ? t : tl;
+                for (int h = 0; h < kNoiseBlocks; ++h) {
+                    const uint32_t xv[4] = {nz.raw[h].x, nz.raw[h].y, nz.raw[h].z, nz.raw[h].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) small_here |= (128 * h + tb + k >= skip) & (xv[k] <= xs);
                 }
             }
             if (__any_sync(kFullMask, small_here)) {
+                // run of small increments at the end of the window: highest real draw that is NOT small
+                int tl = -1;
+#pragma unroll
+                for (int h = 0; h < kNoiseBlocks; ++h) {
+                    const uint32_t xv[4] = {nz.raw[h].x, nz.raw[h].y, nz.raw[h].z, nz.raw[h].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int t = 128 * h + tb + k;
+                        tl = ((t >= skip) & (xv[k] > xs)) ? t : tl;
+                    }
+                }
                 const int t_last = __reduce_max_sync(kFullMask, tl);
                 nochg = t_last < 0 ? nochg + (kWindow - skip) : kWindow - 1 - t_last;
             } else {
