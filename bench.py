@@ -1,14 +1,16 @@
 #!/usr/bin/env python
-"""bench.py — throughput of the ERL-Fill hot path on B200 (contract: see README / DESIGN.md section 6).
+"""bench.py — throughput of the ERL-Fill hot path on B200 (contract: DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sim] [--n-env 4096]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sim|rollout|update] [--n-env 4096]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the CPU port of the reference path on the host cores
 
-One JSON line on stdout (rank 0).  A "step" is one lock-step pass of the workload over the batch of
-envs of every rank.  `value` is device-timed with inputs resident in HBM; `e2e` goes through the
-public Python API with pinned HOST buffers (H2D of the step's actions, D2H of state/reward/done
-inside the timed region).
+One JSON line on stdout (rank 0).  A "step" is one lock-step pass of the workload over the batch of every rank:
+  sim      configs[1] of BASELINE.json: batched WeightEnv rollout, PID-effective constant action (default, 4096 envs/GPU)
+  rollout  configs[2]: MultiConditionWeightEnv, EmotionModule transformer -> ER-DDPG actor + OU -> env step -> emotion update
+  update   configs[3]: ER-DDPG update, minibatch 4096 from a 1M-transition replay (sample + gather + U1-U5)
+`value` is device-timed with inputs resident in HBM; `e2e` goes through the public Python API with pinned HOST
+buffers (H2D of the step's inputs, D2H of its results inside the timed region).
 """
 import argparse
 import json
@@ -22,8 +24,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-ENV_STEP_BYTES = 192          # algorithmic bytes per env-step
-L2_FLUSH_BYTES = 256 << 20    # > 126 MB L2
+ENV_STEP_BYTES = 192            # algorithmic bytes per env-step
+TRANSFORMER_FLOP = 21.83e6      # per env per call at S=20
+UPDATE_FLOP_PER_SAMPLE = 1.43e6
+L2_FLUSH_BYTES = 256 << 20      # > 126 MB L2
+# warp-instructions one env-step of the `sim` workload issues in env_sim_warp_kernel + env_finish_kernel
+# (ncu smsp__inst_executed.sum / n_env, profiles/r01_env_step_4096_pid.txt)
+SIM_WARP_INSTR_PER_ENV_STEP = {"pid": 3959.3 + 20.3}
 
 
 def _peaks():
@@ -65,7 +72,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()
@@ -75,10 +82,82 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# workloads
+# timing helpers
 # ------------------------------------------------------------------------------------------------
-def _sim_setup(args, rank, device):
-    """configs[1] of BASELINE.json: batched WeightEnv rollout, PID-effective constant action."""
+class Timer:
+    """K steps, each bracketed by its own CUDA-event pair on the launching stream with an L2 flush in between
+    (outside the pair); barrier + synchronize on both sides; max over ranks."""
+
+    def __init__(self, device, world):
+        import torch
+        self.torch, self.device, self.world = torch, device, world
+        self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
+        self.stream = torch.cuda.current_stream()
+
+    def sync(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _red(self, x, op):
+        if self.world == 1:
+            return float(x)
+        import torch.distributed as dist
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.device)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def maxr(self, x):
+        import torch.distributed as dist
+        return self._red(x, dist.ReduceOp.MAX)
+
+    def sumr(self, x):
+        import torch.distributed as dist
+        return self._red(x, dist.ReduceOp.SUM)
+
+    def run(self, fn, steps, flush=True):
+        torch = self.torch
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        self.sync()
+        w0 = time.perf_counter()
+        for k in range(steps):
+            if flush:
+                self.flush.zero_()
+            starts[k].record(self.stream)
+            fn()
+            ends[k].record(self.stream)
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        self.sync()
+        total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+        return self.maxr(total_ms), w1 - w0
+
+    def run_block(self, fn, steps):
+        """K back-to-back calls inside one event pair (host work of fn included): the e2e region."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.sync()
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+        e1.record(self.stream)
+        torch.cuda.synchronize()
+        self.sync()
+        return self.maxr(e0.elapsed_time(e1))
+
+
+def _kernel_ms(timer, fn, reps=5):
+    """Average device time of one call of fn (an L2 flush before every call, outside the event pair)."""
+    ms, _ = timer.run(fn, reps)
+    return ms / reps
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads (each returns the pieces of the JSON line)
+# ------------------------------------------------------------------------------------------------
+def wl_sim(args, rank, world, device, timer):
     import torch
     import erlfill_b200 as E
     K = E.conditions
@@ -87,7 +166,7 @@ def _sim_setup(args, rank, device):
                        env_id_base=rank * n, sim_mode=args.sim_mode)
     if args.actions == "pid":
         a_host = torch.tensor(K.PID_EFFECTIVE_ACTION, dtype=torch.float32).repeat(n, 1)
-    else:   # uniform in bounds (heavy divergence variant)
+    else:   # uniform in bounds (divergent episode lengths)
         g = torch.Generator().manual_seed(1234 + rank)
         lo = torch.tensor([K.SINGLE_25KG["bounds"][k][0] for k in E._lib.ACTION_ORDER], dtype=torch.float32)
         hi = torch.tensor([K.SINGLE_25KG["bounds"][k][1] for k in E._lib.ACTION_ORDER], dtype=torch.float32)
@@ -95,70 +174,13 @@ def _sim_setup(args, rank, device):
     a_host = a_host.contiguous().pin_memory()
     a_dev = a_host.to(device)
     env.reset()
-    return env, a_host, a_dev
-
-
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    import erlfill_b200 as E
-    E._lib.require_device()
-
-    env, a_host, a_dev = _sim_setup(args, rank, device)
-    n = args.n_env
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
-    stream = torch.cuda.current_stream()
-
-    def one_step():
-        env.step(a_dev)
-
     for _ in range(args.warmup):
-        one_step()
+        env.step(a_dev)
     torch.cuda.synchronize()
     env.tick_sum.zero_()
+    total_ms, wall = timer.run(lambda: env.step(a_dev), args.steps)
+    ticks_all = timer.sumr(int(env.tick_sum.item()))
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
-        starts[k].record(stream)
-        one_step()
-        ends[k].record(stream)
-    torch.cuda.synchronize()
-    wall1 = time.perf_counter()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop()
-    per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = sum(per_step_ms)
-    ticks = int(env.tick_sum.item())
-    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
-    tk = torch.tensor([ticks], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tk, op=dist.ReduceOp.SUM)
-    total_ms = float(t.item())
-    ticks_all = float(tk.item())
-    ms_per_step = total_ms / args.steps
-    value = n * world * args.steps / (total_ms * 1e-3)
-
-    # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region ------------
     ns_host = torch.empty(n, 2, dtype=torch.float32).pin_memory()
     r_host = torch.empty(n, dtype=torch.float32).pin_memory()
     d_host = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -170,65 +192,204 @@ def run_ours(args):
         ns_host.copy_(ns, non_blocking=True)
         r_host.copy_(r, non_blocking=True)
         d_host.copy_(d, non_blocking=True)
-        stream.synchronize()
+        timer.stream.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(3):
         e2e_step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n * world * args.steps / (float(te.item()) * 1e-3)
-    h2d = a_host.numel() * 4
-    d2h = ns_host.numel() * 4 + r_host.numel() * 4 + d_host.numel()
+    e2e_ms = timer.run_block(e2e_step, args.steps)
 
+    ms_per_step = total_ms / args.steps
+    units = n * world * args.steps
+    launches = 2 if args.sim_mode != "thread" else 1
+    peaks = _peaks()
+    achieved = ENV_STEP_BYTES * n / (ms_per_step * 1e-3) / 1e9
+    kname = "env_sim_warp_kernel + env_finish_kernel" if args.sim_mode != "thread" else "env_step_kernel<false>"
+    out = {
+        "metric": "env_steps_per_sec", "value": units / (total_ms * 1e-3), "unit": "env-steps/s", "dtype": "f64",
+        "ms_per_step": ms_per_step, "wall_s_timed_region": wall,
+        "config": {"workload": "configs[1]: batched WeightEnv rollout, %d envs/GPU, %s action (sim-kernel throughput), "
+                               "Philox noise" % (n, "PID-effective constant" if args.actions == "pid" else "uniform-random"),
+                   "n_env_per_gpu": n, "actions": args.actions, "sim_mode": args.sim_mode,
+                   "parallelism": "env-sharded x%d, no data-path collective" % world,
+                   "l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
+                   "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks"},
+        "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / units,
+        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": a_host.numel() * 4,
+                "d2h_bytes_per_step": ns_host.numel() * 4 + r_host.numel() * 4 + d_host.numel()},
+        "gpu_launches": launches * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"], "kernel": kname,
+                     "algorithmic_bytes_per_env_step": ENV_STEP_BYTES,
+                     "note": "the simulator is instruction-issue bound (about %d serial ticks of integer/Philox work per "
+                             "env-step against 192 B of HBM traffic), not HBM bound: see issue_roofline"
+                             % round(ticks_all / units)},
+    }
+    ipe = SIM_WARP_INSTR_PER_ENV_STEP.get(args.actions) if args.sim_mode != "thread" else None
+    if ipe:
+        out["_issue"] = (n * args.steps / (total_ms * 1e-3), ipe)
+    return out
+
+
+def _make_agent(args, rank, device, n, batch, memory):
+    import erlfill_b200 as E
+    K = E.conditions
+    conds = list(K.EXPERIMENT_3.values())
+    env = E.VecFillEnv(conds, n, kind="multi", max_steps=100, seed=0, device=device, env_id_base=rank * n,
+                       sim_mode=args.sim_mode)
+    agent = E.VecERDDPG(env, seed=0, batch_size=batch, memory_size=memory, rank=rank)
+    return env, agent
+
+
+def wl_rollout(args, rank, world, device, timer):
+    import torch
+    n = args.n_env
+    env, agent = _make_agent(args, rank, device, n, 128, 1024)
+    for _ in range(args.warmup):
+        agent.rollout_step(store=False, replay_reset=False)
+    torch.cuda.synchronize()
+    env.tick_sum.zero_()
+    total_ms, wall = timer.run(lambda: agent.rollout_step(store=False, replay_reset=False), args.steps)
+    ticks_all = timer.sumr(int(env.tick_sum.item()))
+    # e2e: the observations come from the host and the step's results go back to it
+    obs_host = env.obs.cpu().pin_memory()
+    res_host = [torch.empty(n, 2).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()]
+
+    def e2e_step():
+        env.obs.copy_(obs_host, non_blocking=True)
+        ns, r, d = agent.rollout_step(store=False, replay_reset=False)
+        res_host[0].copy_(ns, non_blocking=True)
+        res_host[1].copy_(r, non_blocking=True)
+        res_host[2].copy_(d, non_blocking=True)
+        timer.stream.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timer.run_block(e2e_step, args.steps)
+    # the dominant kernel (emotion transformer) timed alone
+    tf_ms = _kernel_ms(timer, agent._emotion_forward)
+    peaks = _peaks()
+    achieved = TRANSFORMER_FLOP * n / (tf_ms * 1e-3) / 1e12
+    units = n * world * args.steps
+    return {
+        "metric": "env_steps_per_sec", "value": units / (total_ms * 1e-3), "unit": "env-steps/s",
+        "dtype": "f64 simulator, %s transformer, f32 actor" % agent.emotion_precision,
+        "ms_per_step": total_ms / args.steps, "wall_s_timed_region": wall,
+        "config": {"workload": "configs[2]: MultiConditionWeightEnv (3 conditions round-robin), %d envs/GPU, EmotionModule "
+                               "transformer -> ER-DDPG actor + OU -> env step -> emotion update, dropout off" % n,
+                   "n_env_per_gpu": n, "sim_mode": args.sim_mode, "parallelism": "env-sharded x%d, no data-path collective" % world,
+                   "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+        "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / units,
+        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": obs_host.numel() * 4,
+                "d2h_bytes_per_step": n * 13},
+        "gpu_launches": 8 * args.steps,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                     "peak_source": peaks["source"] + " (sustained)", "kernel": "emotion_forward_kernel", "kernel_ms": tf_ms,
+                     "share_of_step": tf_ms / (total_ms / args.steps), "algorithmic_flop_per_env": TRANSFORMER_FLOP},
+    }
+
+
+def wl_update(args, rank, world, device, timer):
+    import torch
+    import torch.distributed as dist
+    B, C = args.batch, args.replay
+    env, agent = _make_agent(args, rank, device, 256, B, C)
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    # synthetic replay
+    chunk = 1 << 18
+    for o in range(0, C, chunk):
+        m = min(chunk, C - o)
+        rows = torch.zeros(m, 20)
+        rows[:, 0:2] = torch.rand(m, 2, generator=g) * 5
+        rows[:, 2:12] = torch.rand(m, 10, generator=g) * 2 - 1
+        rows[:, 12] = torch.rand(m, generator=g) * 9000 - 3000
+        rows[:, 13:15] = torch.rand(m, 2, generator=g) * 5
+        rows[:, 15] = (torch.rand(m, generator=g) < 0.01).float()
+        rows[:, 16:19] = torch.rand(m, 3, generator=g)
+        agent.memory.buf[o:o + m].copy_(rows.to(device))
+    agent.memory.size = agent.memory.inserted = C
+    allreduce = None
+    if world > 1:
+        def allreduce(t):
+            dist.all_reduce(t)
+            t.mul_(1.0 / world)
+
+    def step():
+        agent.learn(allreduce=allreduce)
+
+    for _ in range(args.warmup):
+        step()
+    total_ms, wall = timer.run(step, args.steps)
+    rep_host = torch.empty(4).pin_memory()
+    idx_host = torch.randint(0, C, (B,), generator=g)
+    batch_host = agent.memory.buf[idx_host.to(device)].cpu().pin_memory()
+
+    def e2e_step():   # minibatch supplied by the host (the reference's learn() assembles it on the host), losses read back
+        agent.batch.copy_(batch_host, non_blocking=True)
+        rep = agent.learner.update(agent.batch, agent.next_emotion, agent.train_step, allreduce=allreduce)
+        rep_host.copy_(rep, non_blocking=True)
+        timer.stream.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timer.run_block(e2e_step, args.steps)
+    peaks = _peaks()
+    ms = total_ms / args.steps
+    achieved = UPDATE_FLOP_PER_SAMPLE * B / (ms * 1e-3) / 1e12
+    return {
+        "metric": "er_ddpg_updates_per_sec", "value": args.steps / (total_ms * 1e-3), "unit": "updates/s", "dtype": "f32",
+        "ms_per_step": ms, "wall_s_timed_region": wall, "samples_per_sec": B * world * args.steps / (total_ms * 1e-3),
+        "config": {"workload": "configs[3]: ER-DDPG update, minibatch %d per GPU, %d-transition replay, data-parallel x%d "
+                               "(flat-bucket gradient all-reduce)" % (B, C, world),
+                   "minibatch_per_gpu": B, "replay": C, "parallelism": "dp%d" % world,
+                   "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+        "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": B * 80, "d2h_bytes_per_step": 16},
+        "gpu_launches": 70 * args.steps,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                     "peak_source": peaks["source"] + " (sustained)", "kernel": "whole update (sample + gather + U1-U5)",
+                     "algorithmic_flop_per_sample": UPDATE_FLOP_PER_SAMPLE,
+                     "note": "%.2f GFLOP per update: launch/latency bound at this size" % (UPDATE_FLOP_PER_SAMPLE * B / 1e9)},
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    import erlfill_b200 as E
+    E._lib.require_device()
+    timer = Timer(device, world)
+    sampler = ClockSampler(local)
+    sampler.start()
+    out = {"sim": wl_sim, "rollout": wl_rollout, "update": wl_update}[args.workload](args, rank, world, device, timer)
+    clocks = sampler.stop()
     if rank == 0:
-        peaks = _peaks()
-        kernel_s = ms_per_step * 1e-3
-        achieved = ENV_STEP_BYTES * n / kernel_s / 1e9
-        out = {
-            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: batched WeightEnv rollout, %d envs/GPU, %s action "
-                                   "(sim-kernel throughput), Philox noise" % (n, "PID-effective constant"
-                                                                              if args.actions == "pid" else "uniform-random"),
-                       "n_env_per_gpu": n, "actions": args.actions, "parallelism": "env-sharded x%d" % world,
-                       "l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
-                       "timing": "sum of per-step CUDA-event pairs, max over ranks"},
-            "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / (n * world * args.steps),
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps, "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                         "kernel": "env_step_kernel<false>", "algorithmic_bytes_per_env_step": ENV_STEP_BYTES,
-                         "note": "this kernel is FP64-issue/latency bound (about 14 DP instructions per 1 ms "
-                                 "tick, serial chain), not HBM bound: see fp64_issue"},
-            "fp64_issue": _issue_model(ticks_all / world / args.steps / kernel_s, clocks),
-            "wall_s_timed_region": wall1 - wall0,
-        }
-        out["cpu_baseline"] = cpu_baseline_sim(args, budget_s=args.cpu_budget)
-        print(json.dumps(out), flush=True)
+        issue = out.pop("_issue", None)
+        line = {"metric": out.pop("metric"), "value": out.pop("value"), "unit": out.pop("unit"), "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": out.pop("ms_per_step"), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": out.pop("dtype"), "data": "synthetic"}
+        line.update(out)
+        line["clocks"] = clocks
+        if issue:
+            mhz = clocks.get("sm_mhz") or 1965.0
+            ceiling = 148 * 4 * mhz * 1e6 / issue[1]
+            line["issue_roofline"] = {"achieved_env_steps_per_s_per_gpu": issue[0], "ceiling": ceiling, "frac": issue[0] / ceiling,
+                                      "warp_instr_per_env_step": issue[1], "sm_mhz_used": mhz,
+                                      "model": "148 SMs x 4 schedulers x 1 warp-instruction/clk / measured warp-instructions per env-step"}
+        if args.workload == "sim":
+            line["cpu_baseline"] = cpu_baseline_sim(args, budget_s=args.cpu_budget)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def _issue_model(ticks_per_s_per_gpu, clocks):
-    """Ticks/s against the FP64 issue ceiling: 148 SMs x 4 schedulers x 16 DP lanes/clk (B200 DP is half the
-    FP32 rate) / DP instructions per tick (14 counted in the SASS loop body)."""
-    mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    dp_per_tick = 14
-    ceiling = 148 * 4 * 16 * mhz * 1e6 / dp_per_tick
-    return {"achieved_ticks_per_s": ticks_per_s_per_gpu, "ceiling_ticks_per_s": ceiling,
-            "frac": ticks_per_s_per_gpu / ceiling, "dp_instr_per_tick": dp_per_tick, "sm_mhz_used": mhz}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -271,7 +432,7 @@ def cpu_baseline_sim(args, budget_s=12.0):
                  [25000, 18000, 0, 24900, 100, 100, 100, 35, 3, 3, 300]))
     rng = random.Random(0)
     t0, runs = time.perf_counter(), 0
-    while time.perf_counter() - t0 < 2.0:
+    while time.perf_counter() - t0 < min(2.0, budget_s):
         py_port.simulate_run(p, rng)
         runs += 1
     py_rate = runs / (time.perf_counter() - t0)
@@ -285,6 +446,10 @@ def cpu_baseline_sim(args, budget_s=12.0):
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
+        return
+    if args.workload != "sim":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU port is timed on the sim workload (configs[1]) only"}),
+              flush=True)
         return
     from oracle import oracle_lib as O
     cores = O.lib().orc_max_threads()
@@ -318,12 +483,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sim", choices=["sim"])
-    ap.add_argument("--n-env", type=int, default=4096)
+    ap.add_argument("--workload", default="sim", choices=["sim", "rollout", "update"])
+    ap.add_argument("--n-env", type=int, default=None)
     ap.add_argument("--actions", default="pid", choices=["pid", "random"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--replay", type=int, default=1000000)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--sim-mode", default="auto", choices=["auto", "warp", "thread"])
     args = ap.parse_args()
+    if args.n_env is None:
+        args.n_env = {"sim": 4096, "rollout": 65536, "update": 256}[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
