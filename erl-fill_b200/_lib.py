@@ -91,6 +91,7 @@ EXPORTS = [
     "erlfill_version", "erlfill_last_cuda_error", "erlfill_last_cuda_error_string", "erlfill_device_ok",
     "erlfill_env_reset", "erlfill_env_reset_from_replay", "erlfill_env_step", "erlfill_env_step_set_mode",
     "erlfill_actor_forward", "erlfill_emotion_update", "erlfill_episode_end", "erlfill_emotion_forward",
+    "erlfill_emotion_tc_image_bytes", "erlfill_emotion_tc_pack", "erlfill_emotion_forward_tc",
     "erlfill_replay_insert", "erlfill_replay_sample", "erlfill_replay_gather",
     "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_update",
 ]
@@ -108,6 +109,7 @@ def lib():
         L = C.CDLL(SO_PATH)
         L.erlfill_last_cuda_error_string.restype = C.c_char_p
         L.erlfill_ddpg_workspace_bytes.restype = C.c_size_t
+        L.erlfill_emotion_tc_image_bytes.restype = C.c_size_t
         for name in EXPORTS:
             getattr(L, name)
         _lib = L

@@ -1,0 +1,626 @@
+// emotion_tf_tc.cu — M2: EmotionTransformer.forward (EmotionModule.py:48-71) batched over envs on the sm_100a
+// tensor cores (tcgen05.mma, accumulators in tensor memory), dropout off (module.eval()).
+//
+// Same network as emotion_tf.cu (the exact fp32 twin): embedding Linear(3,32) + positions -> 4 x post-norm
+// TransformerEncoderLayer(d=32, 4 heads x 8, FFN 32->2048->32 ReLU, LayerNorm eps 1e-5) -> last token ->
+// Linear(32,3) -> 0.5*tanh+0.5.  Every dense contraction (in_proj, out_proj, linear1, linear2 = 99 % of the
+// 21.8 MFLOP per env) is a bf16 x bf16 -> fp32 tcgen05.mma; the 20x20 attention, the LayerNorms, the residual
+// stream and the embedding stay fp32 SIMT.
+//
+// Work decomposition (persistent kernel, one CTA per SM):
+//   token tile   = 128 accumulator rows (TMEM lanes) = 6 envs x 20 tokens (+8 idle rows); thread r of the
+//                  tile's warpgroup owns row r: its residual stream x[32] lives in that thread's registers, so
+//                  LayerNorm, softmax and the residual adds need no cross-thread traffic.
+//   CTA          = kTiles token tiles (one warpgroup each) + one MMA-issue warp + one weight-producer warp.
+//                  The tiles walk the layers in lock-step so every weight byte fetched from L2 feeds all of them.
+//   FFN pipeline = linear1/linear2 in 32 chunks of 64 hidden units.  Per chunk and tile:
+//                  MMA1  H[128x64] = [x|1|1] (smem, K=48) . [W1|b1_hi|b1_lo]^T (smem)         -> TMEM (double buffered)
+//                  epilogue: tcgen05.ld H -> relu -> bf16x2 -> tcgen05.st P in place (A operand of MMA2)
+//                  MMA2  Y[128x32] += P (TMEM, K=64) . W2chunk^T (smem)                        -> TMEM
+//                  The 2048-wide hidden activation never leaves tensor memory.  The linear1 bias rides in two
+//                  extra K columns (hi + lo bf16 halves against two columns of ones), which removes the bias
+//                  add from the epilogue: measured on B200 the epilogue then costs ~2.9k cycles per tile-layer
+//                  against ~5.1k cycles of MMA, with the bias add it costs 5.8-7.1k (tools/umma_epi.cu).
+//   weights      = pre-packed once (erlfill_emotion_tc_pack) into bf16 "images" in the canonical no-swizzle
+//                  K-major core-matrix layout, streamed per chunk with cp.async.bulk into a 6-stage ring.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace erlfill {
+namespace tc {
+using namespace umma;
+
+constexpr int D = 32, FF = 2048, NL = 4, SMAX = 20, NH = 4, HD = 8;
+constexpr int kTiles = 2;                  // token tiles per CTA
+constexpr int EPT = 6;                     // envs per tile
+constexpr int ROWS = EPT * SMAX;           // 120 live rows of 128
+constexpr int KX = 48;                     // K extent of the activation operand: 32 features | 1 | 1 | 14 x 0
+constexpr int CH = 64;                     // hidden units per FFN chunk
+constexpr int NCH = FF / CH;               // 32
+constexpr int NS = 6;                      // weight ring stages
+constexpr int W1_BYTES = CH * KX * 2;      // 6144
+constexpr int W2_BYTES = D * CH * 2;       // 4096
+constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES;
+constexpr int INP_BYTES = 96 * KX * 2;     // 9216
+constexpr int OUTP_BYTES = D * KX * 2;     // 3072
+constexpr int ATT_BYTES = INP_BYTES + OUTP_BYTES;
+// fp32 block: per layer [norm1_w norm1_b norm2_w norm2_b lin2_b] then emb_w[32][3] emb_b[32] pos[20][33] fc_w[3][32] fc_b[4]
+constexpr int MISC_LAYER = 5 * D;
+constexpr int MISC_EMBW = NL * MISC_LAYER, MISC_EMBB = MISC_EMBW + 96, MISC_POS = MISC_EMBB + 32;
+constexpr int POS_LD = 33;
+constexpr int MISC_FCW = MISC_POS + SMAX * POS_LD, MISC_FCB = MISC_FCW + 96;
+constexpr int MISC_FLOATS = ((MISC_FCB + 4 + 31) / 32) * 32;
+constexpr int IMG_FFN = 0;
+constexpr int IMG_ATT = IMG_FFN + NL * NCH * STAGE_BYTES;
+constexpr int IMG_MISC = IMG_ATT + NL * ATT_BYTES;
+constexpr int IMAGE_BYTES = IMG_MISC + MISC_FLOATS * 4;
+
+constexpr int XS_BYTES = 128 * KX * 2;     // 12288 per tile
+constexpr int KV_LD = 68;                  // floats per token row of k|v (64 + 4 pad: conflict-free 16-byte row stores)
+constexpr int KV_BYTES = ROWS * KV_LD * 4;
+// dynamic shared memory map
+constexpr int SM_RING = 0;
+constexpr int SM_ATT = SM_RING + NS * STAGE_BYTES;
+constexpr int SM_MISC = SM_ATT + NL * ATT_BYTES;
+constexpr int SM_XS = SM_MISC + MISC_FLOATS * 4;
+constexpr int SM_KV = SM_XS + kTiles * XS_BYTES;
+constexpr int SM_BAR = SM_KV + kTiles * KV_BYTES;
+constexpr int NHB = 3;                     // H buffers (TMEM) per tile: MMA1 runs two chunks ahead of the epilogue
+constexpr int kBarPerTile = 6 + 2 * NHB;   // x_full qkv_full o_full out_full x2_full y_full h_full[NHB] p_full[NHB]
+constexpr int kNumBars = kTiles * kBarPerTile + 2 * NS + 1;
+constexpr int SM_TMEM_SLOT = SM_BAR + kNumBars * 8;
+constexpr int SMEM_BYTES = SM_TMEM_SLOT + 16;
+static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KB");
+static_assert(SM_ATT % 128 == 0 && SM_XS % 128 == 0 && SM_KV % 16 == 0 && SM_BAR % 8 == 0, "alignment");
+
+constexpr int kThreads = kTiles * 128 + kTiles * 32 + 32;   // tile warpgroups | one MMA issuer warp per tile | weight producer
+constexpr int TM_TILE = 256;               // TMEM columns per tile: H ring [0,192) | Y [192,224); QKV aliases [0,96), OUT aliases Y
+constexpr int TM_Y = NHB * CH;
+static_assert(TM_Y + D <= TM_TILE && kTiles * TM_TILE <= 512, "tensor memory plan");
+constexpr float kQScale = 0.51006973f;     // log2(e) / sqrt(8): folded into the q rows of in_proj, softmax then uses exp2
+
+enum { B_XFULL = 0, B_QKV = 1, B_OFULL = 2, B_OUT = 3, B_X2 = 4, B_Y = 5, B_H = 6, B_P = 6 + NHB };
+
+struct TcArgs {
+    const uint8_t *img;
+    erlfill_emotion_state emo;
+    const float *d_seq;
+    float *d_out;
+    int n, S, n_groups;
+};
+
+// development profile: clock64 ticks of block 0 / thread 0 per phase (see erlfill_debug_tc_profile)
+__device__ unsigned long long g_tc_prof[16];
+#define TC_PROF_DECL long long tp = clock64(); unsigned int pacc[16] = {}
+#define TC_PROF(i)                                   \
+    do {                                             \
+        if (prof) {                                  \
+            const long long now_ = clock64();        \
+            pacc[i] += (unsigned int)(now_ - tp);    \
+            tp = now_;                               \
+        }                                            \
+    } while (0)
+#define TC_PROF_FLUSH                                \
+    do {                                             \
+        if (prof) {                                  \
+            _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_) if (pacc[i_]) g_tc_prof[i_] += pacc[i_]; \
+        }                                            \
+    } while (0)
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+// x <- LayerNorm(x) over the 32 features held by this thread; gamma/beta in shared memory (broadcast reads)
+__device__ __forceinline__ void layer_norm32(float (&x)[D], const float *g, const float *b) {
+    float mean = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) mean += x[d];
+    mean *= (1.0f / D);
+    float var = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { const float c = x[d] - mean; var = fmaf(c, c, var); }
+    const float rstd = rsqrtf(var * (1.0f / D) + 1e-5f);
+#pragma unroll
+    for (int d4 = 0; d4 < D; d4 += 4) {
+        const float4 gg = *reinterpret_cast<const float4 *>(g + d4), bb = *reinterpret_cast<const float4 *>(b + d4);
+        x[d4 + 0] = (x[d4 + 0] - mean) * rstd * gg.x + bb.x;
+        x[d4 + 1] = (x[d4 + 1] - mean) * rstd * gg.y + bb.y;
+        x[d4 + 2] = (x[d4 + 2] - mean) * rstd * gg.z + bb.z;
+        x[d4 + 3] = (x[d4 + 3] - mean) * rstd * gg.w + bb.w;
+    }
+}
+
+// this thread's 32 features, rounded to bf16, into row r of the tile's K-major activation image (columns 0..31)
+__device__ __forceinline__ void store_row_image(uint8_t *xs, int r, const float (&x)[D]) {
+    uint8_t *row = xs + (r >> 3) * (KX / 8) * 128 + (r & 7) * 16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 v;
+        v.x = pack_bf16x2(x[8 * j + 0], x[8 * j + 1]);
+        v.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
+        v.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
+        v.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
+        *reinterpret_cast<uint4 *>(row + j * 128) = v;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const TcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);
+    uint64_t *w_full = bars + kTiles * kBarPerTile, *w_empty = w_full + NS, *c_full = w_empty + NS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_TMEM_SLOT);
+    const float *misc = reinterpret_cast<const float *>(smem + SM_MISC);
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int n_it = (a.n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    // ---- one-time setup ----------------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int t = 0; t < kTiles; ++t) {
+            uint64_t *b = bars + t * kBarPerTile;
+            // the tile's 4 warps arrive once each (lane 0 after __syncwarp); MMA completions arrive through tcgen05.commit
+            mbar_init(b + B_XFULL, 4); mbar_init(b + B_QKV, 1); mbar_init(b + B_OFULL, 4); mbar_init(b + B_OUT, 1);
+            mbar_init(b + B_X2, 4); mbar_init(b + B_Y, 1);
+            for (int i = 0; i < NHB; ++i) { mbar_init(b + B_H + i, 1); mbar_init(b + B_P + i, 4); }
+        }
+        for (int s = 0; s < NS; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, kTiles); }
+        mbar_init(c_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == kTiles * 5) tmem_alloc(tmem_slot, 512);
+    // constant columns 32..47 of every activation image: [1, 1, 0 x 14] (bias hi/lo ride on the two ones)
+    for (int i = tid; i < kTiles * 128; i += kThreads) {
+        uint8_t *row = smem + SM_XS + (i >> 7) * XS_BYTES + ((i & 127) >> 3) * (KX / 8) * 128 + (i & 7) * 16;
+        *reinterpret_cast<uint4 *>(row + 4 * 128) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(row + 5 * 128) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_slot;
+
+    if (warp == kTiles * 5) {
+        // =============================== weight producer ===============================================
+        if (elect_one()) {
+            mbar_arrive_expect_tx(c_full, NL * ATT_BYTES + MISC_FLOATS * 4);
+            bulk_g2s(smem + SM_ATT, a.img + IMG_ATT, NL * ATT_BYTES, c_full);
+            bulk_g2s(smem + SM_MISC, a.img + IMG_MISC, MISC_FLOATS * 4, c_full);
+            uint32_t g = 0;
+            for (int it = 0; it < n_it; ++it)
+                for (int lc = 0; lc < NL * NCH; ++lc, ++g) {
+                    const uint32_t stage = g % NS, use = g / NS;
+                    mbar_wait(w_empty + stage, (use & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(w_full + stage, STAGE_BYTES);
+                    bulk_g2s(smem + SM_RING + stage * STAGE_BYTES, a.img + IMG_FFN + (size_t)lc * STAGE_BYTES, STAGE_BYTES,
+                             w_full + stage);
+                }
+        }
+        __syncwarp();
+    } else if (warp >= kTiles * 4) {
+        // =============================== MMA issuer of tile t ==========================================
+        const int t = warp - kTiles * 4;
+        constexpr uint32_t idesc_qkv = instr_desc_bf16(128, 96), idesc_32 = instr_desc_bf16(128, 32),
+                           idesc_h = instr_desc_bf16(128, CH);
+        constexpr uint32_t SBO_X = (KX / 8) * 128, SBO_W2 = (CH / 8) * 128;
+        const uint32_t xs = smem_u32(smem + SM_XS) + t * XS_BYTES, att0 = smem_u32(smem + SM_ATT), ring0 = smem_u32(smem + SM_RING);
+        const uint32_t tT = tbase + t * TM_TILE;
+        uint64_t *b = bars + t * kBarPerTile;
+        mbar_wait(c_full, 0);
+        const bool prof = blockIdx.x == 0 && t == 0 && (tid & 31) == 0;
+        TC_PROF_DECL;
+        uint32_t n = 0;                                    // (group iteration, layer) counter: phase of the per-layer barriers
+        for (int it = 0; it < n_it; ++it)
+            for (int l = 0; l < NL; ++l, ++n) {
+                const uint32_t par = n & 1u;
+                // ---- q|k|v = [x|1|1] . [W_in|b_hi|b_lo]^T ----
+                mbar_wait(b + B_XFULL, par);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int s = 0; s < KX / 16; ++s)
+                        mma_ss(tT, smem_desc(xs + s * 256, 128, SBO_X), smem_desc(att0 + l * ATT_BYTES + s * 256, 128, SBO_X), idesc_qkv, s > 0);
+                    mma_commit(b + B_QKV);
+                }
+                __syncwarp();
+                // ---- attention output projection ----
+                mbar_wait(b + B_OFULL, par);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int s = 0; s < KX / 16; ++s)
+                        mma_ss(tT + TM_Y, smem_desc(xs + s * 256, 128, SBO_X),
+                               smem_desc(att0 + l * ATT_BYTES + INP_BYTES + s * 256, 128, SBO_X), idesc_32, s > 0);
+                    mma_commit(b + B_OUT);
+                }
+                __syncwarp();
+                // ---- FFN: MMA1 runs NHB-1 chunks ahead of MMA2, so the epilogue always has a finished H chunk waiting ----
+                mbar_wait(b + B_X2, par);
+                tc_fence_after();
+                TC_PROF(8);
+                const uint32_t g0 = n * NCH;
+                for (int c = 0; c < NCH + NHB - 1; ++c) {
+                    if (c < NCH) {
+                        const uint32_t g = g0 + c, stage = g % NS, hb = g % NHB;
+                        mbar_wait(w_full + stage, (g / NS) & 1u);
+                        tc_fence_after();
+                        TC_PROF(9);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int s = 0; s < KX / 16; ++s)
+                                mma_ss(tT + hb * CH, smem_desc(xs + s * 256, 128, SBO_X),
+                                       smem_desc(ring0 + stage * STAGE_BYTES + s * 256, 128, SBO_X), idesc_h, s > 0);
+                            mma_commit(b + B_H + hb);
+                        }
+                        __syncwarp();
+                        TC_PROF(10);
+                    }
+                    if (c >= NHB - 1) {
+                        const int cc = c - (NHB - 1);
+                        const uint32_t g = g0 + cc, stage = g % NS, hb = g % NHB;
+                        mbar_wait(b + B_P + hb, (g / NHB) & 1u);
+                        tc_fence_after();
+                        TC_PROF(11);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int s = 0; s < CH / 16; ++s)
+                                mma_ts(tT + TM_Y, tT + hb * CH + s * 8,
+                                       smem_desc(ring0 + stage * STAGE_BYTES + W1_BYTES + s * 256, 128, SBO_W2), idesc_32,
+                                       (cc > 0 || s > 0) ? 1u : 0u);
+                            mma_commit(w_empty + stage);
+                            if (cc == NCH - 1) mma_commit(b + B_Y);
+                        }
+                        __syncwarp();
+                        TC_PROF(12);
+                    }
+                }
+            }
+        TC_PROF_FLUSH;
+    } else {
+        // =============================== token-tile warpgroups ==========================================
+        const int t = warp >> 2, r = tid & 127, lane = tid & 31;
+        const int e_loc = r / SMAX, s_pos = r % SMAX;
+        uint64_t *b = bars + t * kBarPerTile;
+        uint8_t *xs = smem + SM_XS + t * XS_BYTES;
+        float *kv = reinterpret_cast<float *>(smem + SM_KV + t * KV_BYTES);
+        const uint32_t tT = tbase + t * TM_TILE + ((uint32_t)((warp & 3) * 32) << 16);
+        mbar_wait(c_full, 0);
+        const bool prof = blockIdx.x == 0 && tid == 0;
+        TC_PROF_DECL;
+        uint32_t n = 0;
+        for (int it = 0; it < n_it; ++it) {
+            const int group = blockIdx.x + it * gridDim.x;
+            const int env = (group * kTiles + t) * EPT + e_loc;
+            const bool env_ok = r < ROWS && env < a.n;
+            // ---- sequence of this env (EmotionModule.get_state, :83-102) and this row's token ----
+            int S = 0;
+            float x[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) x[d] = 0.f;
+            if (env_ok) {
+                float in0, in1, in2;
+                if (a.d_seq) {
+                    S = a.S;
+                    if (s_pos < S) {
+                        const float *p = a.d_seq + ((size_t)env * a.S + s_pos) * 3;
+                        in0 = p[0]; in1 = p[1]; in2 = p[2];
+                    }
+                } else {
+                    const int len = a.emo.d_hist_len[env];
+                    if (len == 0) { S = 1; in0 = 0.5f; in1 = 0.5f; in2 = 0.0f; }
+                    else {
+                        S = SMAX;
+                        const int slot = (a.emo.d_hist_head[env] + max(0, s_pos - (SMAX - len))) % SMAX;
+                        in0 = a.emo.d_history[((size_t)slot * 3 + 0) * a.n + env];
+                        in1 = a.emo.d_history[((size_t)slot * 3 + 1) * a.n + env];
+                        in2 = a.emo.d_history[((size_t)slot * 3 + 2) * a.n + env];
+                    }
+                }
+                if (s_pos < S) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        float v = misc[MISC_EMBB + d];
+                        v = fmaf(in0, misc[MISC_EMBW + d * 3 + 0], v);
+                        v = fmaf(in1, misc[MISC_EMBW + d * 3 + 1], v);
+                        v = fmaf(in2, misc[MISC_EMBW + d * 3 + 2], v);
+                        x[d] = v + misc[MISC_POS + s_pos * POS_LD + d];
+                    }
+                }
+            }
+            const bool tok_ok = env_ok && s_pos < S;
+
+            for (int l = 0; l < NL; ++l, ++n) {
+                const uint32_t par = n & 1u;
+                const float *lw = misc + l * MISC_LAYER;
+                // ---- x -> bf16 image -> q|k|v on the tensor core ----
+                store_row_image(xs, r, x);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b + B_XFULL);
+                TC_PROF(0);
+                mbar_wait(b + B_QKV, par);
+                tc_fence_after();
+                TC_PROF(1);
+                float q[D];
+                {
+                    uint32_t rq[32], rk[32], rv[32];
+                    tmem_ld32(tT, rq);
+                    tmem_ld32(tT + 32, rk);
+                    tmem_ld32(tT + 64, rv);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int d = 0; d < D; ++d) q[d] = __uint_as_float(rq[d]);
+                    if (r < ROWS) {
+                        float4 *row = reinterpret_cast<float4 *>(kv + r * KV_LD);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            row[j] = make_float4(__uint_as_float(rk[4 * j]), __uint_as_float(rk[4 * j + 1]), __uint_as_float(rk[4 * j + 2]),
+                                                 __uint_as_float(rk[4 * j + 3]));
+                            row[8 + j] = make_float4(__uint_as_float(rv[4 * j]), __uint_as_float(rv[4 * j + 1]),
+                                                     __uint_as_float(rv[4 * j + 2]), __uint_as_float(rv[4 * j + 3]));
+                        }
+                    }
+                }
+                named_bar_sync(1 + t, 128);
+                TC_PROF(2);
+                // ---- attention: this thread = one query token, all 4 heads; scores are already in the log2 domain ----
+                float o[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) o[d] = 0.f;
+                if (tok_ok) {
+                    const float *kvb = kv + e_loc * SMAX * KV_LD;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) {
+                        float sc[SMAX];
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < SMAX; ++j) {
+                            if (j < S) {
+                                const float4 k0 = *reinterpret_cast<const float4 *>(kvb + j * KV_LD + h * HD);
+                                const float4 k1 = *reinterpret_cast<const float4 *>(kvb + j * KV_LD + h * HD + 4);
+                                float s = q[h * HD] * k0.x;
+                                s = fmaf(q[h * HD + 1], k0.y, s); s = fmaf(q[h * HD + 2], k0.z, s); s = fmaf(q[h * HD + 3], k0.w, s);
+                                s = fmaf(q[h * HD + 4], k1.x, s); s = fmaf(q[h * HD + 5], k1.y, s); s = fmaf(q[h * HD + 6], k1.z, s);
+                                s = fmaf(q[h * HD + 7], k1.w, s);
+                                sc[j] = s;
+                                mx = fmaxf(mx, s);
+                            } else sc[j] = -INFINITY;
+                        }
+                        float sum = 0.f;
+#pragma unroll
+                        for (int j = 0; j < SMAX; ++j) { sc[j] = exp2f(sc[j] - mx); sum += sc[j]; }
+                        float acc[HD];
+#pragma unroll
+                        for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+#pragma unroll
+                        for (int j = 0; j < SMAX; ++j) {
+                            if (j < S) {
+                                const float4 v0 = *reinterpret_cast<const float4 *>(kvb + j * KV_LD + D + h * HD);
+                                const float4 v1 = *reinterpret_cast<const float4 *>(kvb + j * KV_LD + D + h * HD + 4);
+                                acc[0] = fmaf(sc[j], v0.x, acc[0]); acc[1] = fmaf(sc[j], v0.y, acc[1]);
+                                acc[2] = fmaf(sc[j], v0.z, acc[2]); acc[3] = fmaf(sc[j], v0.w, acc[3]);
+                                acc[4] = fmaf(sc[j], v1.x, acc[4]); acc[5] = fmaf(sc[j], v1.y, acc[5]);
+                                acc[6] = fmaf(sc[j], v1.z, acc[6]); acc[7] = fmaf(sc[j], v1.w, acc[7]);
+                            }
+                        }
+                        const float inv = 1.0f / sum;
+#pragma unroll
+                        for (int d = 0; d < HD; ++d) o[h * HD + d] = acc[d] * inv;
+                    }
+                }
+                // ---- o -> bf16 image (the q|k|v MMA that read the image has completed) -> out_proj ----
+                store_row_image(xs, r, o);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b + B_OFULL);
+                TC_PROF(3);
+                mbar_wait(b + B_OUT, par);
+                tc_fence_after();
+                TC_PROF(4);
+                {
+                    uint32_t ro[32];
+                    tmem_ld32(tT + TM_Y, ro);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int d = 0; d < D; ++d) x[d] += __uint_as_float(ro[d]);
+                }
+                layer_norm32(x, lw, lw + D);
+                // ---- FFN ----
+                store_row_image(xs, r, x);
+                fence_proxy_async();
+                tc_fence_before();                        // orders the tcgen05.ld of OUT before MMA2 overwrites that region
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b + B_X2);
+                TC_PROF(5);
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    const uint32_t g = n * NCH + c, hb = g % NHB;
+                    mbar_wait(b + B_H + hb, (g / NHB) & 1u);
+                    tc_fence_after();
+                    uint32_t h0[32], h1[32], p[32];
+                    tmem_ld32(tT + hb * CH, h0);
+                    tmem_ld32(tT + hb * CH + 32, h1);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        p[j] = pack_relu_bf16x2(__uint_as_float(h0[2 * j]), __uint_as_float(h0[2 * j + 1]));
+                        p[16 + j] = pack_relu_bf16x2(__uint_as_float(h1[2 * j]), __uint_as_float(h1[2 * j + 1]));
+                    }
+                    tmem_st32(tT + hb * CH, p);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(b + B_P + hb);
+                }
+                TC_PROF(6);
+                mbar_wait(b + B_Y, par);
+                tc_fence_after();
+                {
+                    uint32_t ry[32];
+                    tmem_ld32(tT + TM_Y, ry);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int d4 = 0; d4 < D; d4 += 4) {
+                        const float4 b2 = *reinterpret_cast<const float4 *>(lw + 4 * D + d4);
+                        x[d4 + 0] += __uint_as_float(ry[d4 + 0]) + b2.x;
+                        x[d4 + 1] += __uint_as_float(ry[d4 + 1]) + b2.y;
+                        x[d4 + 2] += __uint_as_float(ry[d4 + 2]) + b2.z;
+                        x[d4 + 3] += __uint_as_float(ry[d4 + 3]) + b2.w;
+                    }
+                }
+                layer_norm32(x, lw + 2 * D, lw + 3 * D);
+                tc_fence_before();                        // tcgen05.ld of Y / H ordered before the next layer's MMAs
+                TC_PROF(7);
+            }
+            // ---- last token -> fc_out -> 0.5*tanh + 0.5 ----
+            if (tok_ok && s_pos == S - 1) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float acc = misc[MISC_FCB + c];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) acc = fmaf(x[d], misc[MISC_FCW + c * D + d], acc);
+                    a.d_out[(size_t)env * 3 + c] = tanhf(acc) * 0.5f + 0.5f;
+                }
+            }
+        }
+        TC_PROF_FLUSH;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kTiles * 5) tmem_dealloc(tbase, 512);
+}
+
+// ---- weight packing: fp32 state_dict tensors -> bf16 operand images + fp32 block -----------------------------
+__device__ __forceinline__ void put_bf16(uint8_t *img, uint32_t off, float v) {
+    *reinterpret_cast<__nv_bfloat16 *>(img + off) = __float2bfloat16_rn(v);
+}
+// value of column k (0..47) of an augmented weight row: 32 weights, bias hi, bias lo, zeros
+__device__ __forceinline__ float aug_col(const float *wrow, float bias, int k, float scale) {
+    if (k < D) return wrow[k] * scale;
+    const float bs = bias * scale;
+    const float hi = __bfloat162float(__float2bfloat16_rn(bs));
+    if (k == D) return hi;
+    if (k == D + 1) return bs - hi;
+    return 0.f;
+}
+
+__global__ void emotion_tc_pack_kernel(const erlfill_transformer_weights w, uint8_t *img) {
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    // FFN chunks
+    for (int i = i0; i < NL * NCH * (CH * KX + D * CH); i += stride) {
+        const int per = CH * KX + D * CH;
+        const int lc = i / per, j = i % per, l = lc / NCH, c = lc % NCH;
+        uint8_t *st = img + IMG_FFN + (size_t)lc * STAGE_BYTES;
+        if (j < CH * KX) {
+            const int nn = j / KX, k = j % KX, hid = c * CH + nn;
+            put_bf16(st, kmajor_off(nn, k, KX), aug_col(w.lin1_w + ((size_t)l * FF + hid) * D, w.lin1_b[l * FF + hid], k, 1.0f));
+        } else {
+            const int jj = j - CH * KX, o = jj / CH, k = jj % CH;
+            put_bf16(st + W1_BYTES, kmajor_off(o, k, CH), w.lin2_w[((size_t)l * D + o) * FF + c * CH + k]);
+        }
+    }
+    // attention projections (q rows pre-scaled by log2(e)/sqrt(8))
+    for (int i = i0; i < NL * (96 + D) * KX; i += stride) {
+        const int per = (96 + D) * KX;
+        const int l = i / per, j = i % per;
+        uint8_t *at = img + IMG_ATT + (size_t)l * ATT_BYTES;
+        if (j < 96 * KX) {
+            const int nn = j / KX, k = j % KX;
+            put_bf16(at, kmajor_off(nn, k, KX), aug_col(w.in_proj_w + ((size_t)l * 96 + nn) * D, w.in_proj_b[l * 96 + nn], k, nn < D ? kQScale : 1.0f));
+        } else {
+            const int jj = j - 96 * KX, nn = jj / KX, k = jj % KX;
+            put_bf16(at + INP_BYTES, kmajor_off(nn, k, KX), aug_col(w.out_proj_w + ((size_t)l * D + nn) * D, w.out_proj_b[l * D + nn], k, 1.0f));
+        }
+    }
+    float *misc = reinterpret_cast<float *>(img + IMG_MISC);
+    for (int i = i0; i < MISC_FLOATS; i += stride) {
+        float v = 0.f;
+        if (i < MISC_EMBW) {
+            const int l = i / MISC_LAYER, j = i % MISC_LAYER, f = j / D, d = j % D;
+            const float *src = f == 0 ? w.norm1_w : (f == 1 ? w.norm1_b : (f == 2 ? w.norm2_w : (f == 3 ? w.norm2_b : w.lin2_b)));
+            v = src[l * D + d];
+        } else if (i < MISC_EMBB) v = w.emb_w[i - MISC_EMBW];
+        else if (i < MISC_POS) v = w.emb_b[i - MISC_EMBB];
+        else if (i < MISC_FCW) {
+            const int j = i - MISC_POS, s = j / POS_LD, d = j % POS_LD;
+            v = d < D ? w.pos[s * D + d] : 0.f;
+        } else if (i < MISC_FCB) v = w.fc_w[i - MISC_FCW];
+        else if (i < MISC_FCB + 3) v = w.fc_b[i - MISC_FCB];
+        misc[i] = v;
+    }
+}
+
+}  // namespace tc
+}  // namespace erlfill
+
+using namespace erlfill;
+
+extern "C" {
+
+/* development aid (not in erlfill.h): clock64 ticks block 0 spent per phase since the last reset:
+ * 0 image store, 1 wait q|k|v, 2 q|k|v epilogue, 3 attention, 4 wait out_proj, 5 LN1 + image store, 6 FFN chunk loop,
+ * 7 wait Y + LN2; issuer warp of tile 0: 8 non-FFN part of the layer, 9 wait weights, 10 issue MMA1, 11 wait P, 12 issue MMA2 */
+int erlfill_debug_tc_profile(unsigned long long *out16, int reset) {
+    if (out16) ERLFILL_CUDA_TRY(cudaMemcpyFromSymbol(out16, tc::g_tc_prof, sizeof(tc::g_tc_prof)));
+    if (reset) {
+        unsigned long long z[16] = {};
+        ERLFILL_CUDA_TRY(cudaMemcpyToSymbol(tc::g_tc_prof, z, sizeof(z)));
+    }
+    return ERLFILL_OK;
+}
+
+size_t erlfill_emotion_tc_image_bytes(void) { return (size_t)tc::IMAGE_BYTES; }
+
+int erlfill_emotion_tc_pack(const erlfill_transformer_weights *w, void *d_image, void *stream) {
+    if (!w || !d_image) return ERLFILL_ERR_ARG;
+    if (((uintptr_t)d_image & 15) != 0) return ERLFILL_ERR_ARG;
+    const float *const *wp = reinterpret_cast<const float *const *>(w);
+    for (size_t i = 0; i < sizeof(*w) / sizeof(float *); ++i)
+        if (!wp[i]) return ERLFILL_ERR_ARG;
+    tc::emotion_tc_pack_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(*w, static_cast<uint8_t *>(d_image));
+    ERLFILL_CUDA_TRY(cudaGetLastError());
+    return ERLFILL_OK;
+}
+
+int erlfill_emotion_forward_tc(const void *d_image, int n_env, const float *d_seq, int seq_len,
+                               const erlfill_emotion_state *emo, float *d_out, void *stream) {
+    if (!d_image || n_env <= 0 || !d_out) return ERLFILL_ERR_ARG;
+    if (!d_seq && (!emo || !emo->d_history || !emo->d_hist_len || !emo->d_hist_head)) return ERLFILL_ERR_ARG;
+    if (d_seq && (seq_len < 1 || seq_len > tc::SMAX)) return ERLFILL_ERR_ARG;
+    tc::TcArgs a;
+    a.img = static_cast<const uint8_t *>(d_image);
+    if (emo) a.emo = *emo; else a.emo = erlfill_emotion_state{};
+    a.d_seq = d_seq; a.d_out = d_out; a.n = n_env; a.S = d_seq ? seq_len : tc::SMAX;
+    a.n_groups = (n_env + tc::kTiles * tc::EPT - 1) / (tc::kTiles * tc::EPT);
+    static int n_sm[64] = {};
+    int dev = 0;
+    ERLFILL_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return ERLFILL_ERR_UNSUPPORTED;
+    if (!n_sm[dev]) {
+        int v = 0;
+        ERLFILL_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+        ERLFILL_CUDA_TRY(cudaFuncSetAttribute(tc::emotion_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        n_sm[dev] = v;
+    }
+    const int grid = a.n_groups < n_sm[dev] ? a.n_groups : n_sm[dev];
+    tc::emotion_forward_tc_kernel<<<grid, tc::kThreads, tc::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    ERLFILL_CUDA_TRY(cudaGetLastError());
+    return ERLFILL_OK;
+}
+
+}  // extern "C"

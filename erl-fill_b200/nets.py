@@ -54,9 +54,23 @@ class TransformerParams:
             self.t[f] = torch.stack([_dev_f32(state_dict[f"transformer_encoder.layers.{l}.{k}"], self.device)
                                      for l in range(N_LAYERS)]).contiguous()
 
+        self._tc_image = None
+
     def struct(self):
         order = [n for n, _ in L.TransformerWeights._fields_]
         return L.TransformerWeights(*[L.ptr(self.t[n]) for n in order])
+
+    def tc_image(self, repack=False):
+        """bf16 operand images of the parameters for the tensor-core kernel (emotion_tf_tc.cu); packed on first use
+        (call with repack=True after changing self.t in place)."""
+        if self._tc_image is None or repack:
+            if self._tc_image is None:
+                self._tc_image = torch.empty(L.lib().erlfill_emotion_tc_image_bytes(), dtype=torch.uint8, device=self.device)
+            w = self.struct()
+            with torch.cuda.device(self.device):
+                L.check(L.lib().erlfill_emotion_tc_pack(C.byref(w), L.ptr(self._tc_image), L.stream_ptr()),
+                        "erlfill_emotion_tc_pack")
+        return self._tc_image
 
     def state_dict(self):
         sd = {k: self.t[f].clone() for f, k in _TF_GLOBAL}
@@ -125,10 +139,20 @@ def emotion_forward(params, seq=None, emo=None, dropout=L.DROPOUT_OFF, masks=Non
         n, S, dev = emo.n, L.HIST, emo.history.device
     if out is None:
         out = torch.empty(n, 3, dtype=torch.float32, device=dev)
-    if precision != "fp32":
-        raise L.ErlfillError("emotion_forward: only the fp32 path is built in this revision")
-    w = params.struct()
     es = emo.struct() if emo is not None else None
+    if precision == "bf16":
+        # tensor-core path (tcgen05, bf16 operands / fp32 accumulate): eval() semantics only
+        if dropout != L.DROPOUT_OFF or masks is not None:
+            raise L.ErlfillError("emotion_forward(precision='bf16') implements dropout off only; use the fp32 path")
+        img = params.tc_image()
+        with torch.cuda.device(dev):
+            L.check(L.lib().erlfill_emotion_forward_tc(L.ptr(img), C.c_int(n), L.ptr(seq), C.c_int(S),
+                                                       C.byref(es) if es is not None else None, L.ptr(out),
+                                                       L.stream_ptr()), "erlfill_emotion_forward_tc")
+        return out
+    if precision != "fp32":
+        raise L.ErlfillError(f"emotion_forward: unknown precision {precision!r}")
+    w = params.struct()
     ms = None
     if masks is not None:
         ms = L.TransformerMasks(L.ptr(masks["attn"]), L.ptr(masks["d1"]), L.ptr(masks["ff"]), L.ptr(masks["d2"]))
