@@ -4,17 +4,22 @@
 // Same network as emotion_tf.cu (the exact fp32 twin): embedding Linear(3,32) + positions -> 4 x post-norm
 // TransformerEncoderLayer(d=32, 4 heads x 8, FFN 32->2048->32 ReLU, LayerNorm eps 1e-5) -> last token ->
 // Linear(32,3) -> 0.5*tanh+0.5.  Every dense contraction (in_proj, out_proj, linear1, linear2 = 99 % of the
-// 21.8 MFLOP per env) is a bf16 x bf16 -> fp32 tcgen05.mma; the 20x20 attention, the LayerNorms, the residual
-// stream and the embedding stay fp32 SIMT.
+// 21.8 MFLOP per env) is a bf16 x bf16 -> fp32 tcgen05.mma; the per-(env, head) 20x20 attention runs on register
+// fragments with mma.sync.m16n8k8 (bf16 q/k/v/p, fp32 scores and softmax); the LayerNorms, the residual stream
+// and the embedding stay fp32 SIMT.
 //
 // Work decomposition (persistent kernel, one CTA per SM):
 //   token tile   = 128 accumulator rows (TMEM lanes) = 6 envs x 20 tokens (+8 idle rows); thread r of the
 //                  tile's warpgroup owns row r: its residual stream x[32] lives in that thread's registers, so
 //                  LayerNorm, softmax and the residual adds need no cross-thread traffic.
-//   CTA          = kTiles token tiles (one warpgroup each) + one MMA-issue warp + one weight-producer warp.
-//                  The tiles walk the layers in lock-step so every weight byte fetched from L2 feeds all of them.
+//   CTA          = kTiles token tiles (one warpgroup each) + one MMA-issue warp per tile + one weight-producer warp.
+//                  The tiles share the weight ring, so every weight byte fetched from L2 feeds all of them.
+//   activations  = the bf16 copy of x that the projections read lives in tensor memory too ([x|1|1|0..], 24 packed
+//                  columns written with tcgen05.st by the row owners), so in_proj and linear1 are TS-form MMAs whose
+//                  only shared-memory operand is the weight chunk (an SS-form N=64 MMA is bound by re-reading the
+//                  128x16 A tile from shared memory, ~48 instead of 32 cycles).
 //   FFN pipeline = linear1/linear2 in 32 chunks of 64 hidden units.  Per chunk and tile:
-//                  MMA1  H[128x64] = [x|1|1] (smem, K=48) . [W1|b1_hi|b1_lo]^T (smem)         -> TMEM (double buffered)
+//                  MMA1  H[128x64] = [x|1|1] (TMEM, K=48) . [W1|b1_hi|b1_lo]^T (smem)         -> TMEM (3-deep ring)
 //                  epilogue: tcgen05.ld H -> relu -> bf16x2 -> tcgen05.st P in place (A operand of MMA2)
 //                  MMA2  Y[128x32] += P (TMEM, K=64) . W2chunk^T (smem)                        -> TMEM
 //                  The 2048-wide hidden activation never leaves tensor memory.  The linear1 bias rides in two
@@ -22,7 +27,7 @@
 //                  add from the epilogue: measured on B200 the epilogue then costs ~2.9k cycles per tile-layer
 //                  against ~5.1k cycles of MMA, with the bias add it costs 5.8-7.1k (tools/umma_epi.cu).
 //   weights      = pre-packed once (erlfill_emotion_tc_pack) into bf16 "images" in the canonical no-swizzle
-//                  K-major core-matrix layout, streamed per chunk with cp.async.bulk into a 6-stage ring.
+//                  K-major core-matrix layout, streamed two chunks at a time with cp.async.bulk into a 3-stage ring.
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -33,17 +38,19 @@ namespace erlfill {
 namespace tc {
 using namespace umma;
 
-constexpr int D = 32, FF = 2048, NL = 4, SMAX = 20, NH = 4, HD = 8;
+constexpr int D = 32, FF = 2048, NL = 4, SMAX = 20, HD = 8;
 constexpr int kTiles = 2;                  // token tiles per CTA
 constexpr int EPT = 6;                     // envs per tile
 constexpr int ROWS = EPT * SMAX;           // 120 live rows of 128
 constexpr int KX = 48;                     // K extent of the activation operand: 32 features | 1 | 1 | 14 x 0
 constexpr int CH = 64;                     // hidden units per FFN chunk
 constexpr int NCH = FF / CH;               // 32
-constexpr int NS = 6;                      // weight ring stages
+constexpr int NS = 4;                      // weight ring stages
+constexpr int CPS = 2;                     // FFN chunks per ring stage
 constexpr int W1_BYTES = CH * KX * 2;      // 6144
 constexpr int W2_BYTES = D * CH * 2;       // 4096
-constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES;
+constexpr int CHUNK_BYTES = W1_BYTES + W2_BYTES;
+constexpr int STAGE_BYTES = CPS * CHUNK_BYTES;
 constexpr int INP_BYTES = 96 * KX * 2;     // 9216
 constexpr int OUTP_BYTES = D * KX * 2;     // 3072
 constexpr int ATT_BYTES = INP_BYTES + OUTP_BYTES;
@@ -54,13 +61,17 @@ constexpr int POS_LD = 33;
 constexpr int MISC_FCW = MISC_POS + SMAX * POS_LD, MISC_FCB = MISC_FCW + 96;
 constexpr int MISC_FLOATS = ((MISC_FCB + 4 + 31) / 32) * 32;
 constexpr int IMG_FFN = 0;
-constexpr int IMG_ATT = IMG_FFN + NL * NCH * STAGE_BYTES;
+constexpr int IMG_ATT = IMG_FFN + NL * NCH * CHUNK_BYTES;
 constexpr int IMG_MISC = IMG_ATT + NL * ATT_BYTES;
 constexpr int IMAGE_BYTES = IMG_MISC + MISC_FLOATS * 4;
 
 constexpr int XS_BYTES = 128 * KX * 2;     // 12288 per tile
-constexpr int KV_LD = 68;                  // floats per token row of k|v (64 + 4 pad: conflict-free 16-byte row stores)
-constexpr int KV_BYTES = ROWS * KV_LD * 4;
+// attention operands of one tile, bf16: q[136][40] k[136][40] (token rows, 32 features + 8 pad) and v transposed
+// vT[32][136] (feature rows, 128 tokens + 8 pad); the pads make every mma fragment load bank-conflict free
+constexpr int QK_LD = 40, QK_ROWS = 136, VT_LD = 136;
+constexpr int SQ_OFF = 0, SK_OFF = QK_ROWS * QK_LD * 2, SVT_OFF = 2 * QK_ROWS * QK_LD * 2;
+constexpr int KV_BYTES = SVT_OFF + D * VT_LD * 2 + 32;      // + per-env sequence lengths (6 ints)
+constexpr int SLEN_OFF = SVT_OFF + D * VT_LD * 2;
 // dynamic shared memory map
 constexpr int SM_RING = 0;
 constexpr int SM_ATT = SM_RING + NS * STAGE_BYTES;
@@ -77,9 +88,11 @@ static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KB");
 static_assert(SM_ATT % 128 == 0 && SM_XS % 128 == 0 && SM_KV % 16 == 0 && SM_BAR % 8 == 0, "alignment");
 
 constexpr int kThreads = kTiles * 128 + kTiles * 32 + 32;   // tile warpgroups | one MMA issuer warp per tile | weight producer
-constexpr int TM_TILE = 256;               // TMEM columns per tile: H ring [0,192) | Y [192,224); QKV aliases [0,96), OUT aliases Y
+// TMEM columns per tile: H ring [0,192) | Y [192,224) | X = bf16 [x|1|1|0..] [224,248); QKV aliases [0,96), OUT aliases Y
+constexpr int TM_TILE = 256;
 constexpr int TM_Y = NHB * CH;
-static_assert(TM_Y + D <= TM_TILE && kTiles * TM_TILE <= 512, "tensor memory plan");
+constexpr int TM_X = TM_Y + D;
+static_assert(TM_X + KX / 2 <= TM_TILE && kTiles * TM_TILE <= 512, "tensor memory plan");
 constexpr float kQScale = 0.51006973f;     // log2(e) / sqrt(8): folded into the q rows of in_proj, softmax then uses exp2
 
 enum { B_XFULL = 0, B_QKV = 1, B_OFULL = 2, B_OUT = 3, B_X2 = 4, B_Y = 5, B_H = 6, B_P = 6 + NHB };
@@ -125,6 +138,39 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// D(16x8, fp32) += A(16x8, bf16, row) . B(8x8, bf16, col) on register fragments (the legacy warp-level tensor path: the
+// per-(env, head) attention blocks are 20x20x8, far below a tcgen05 tile)
+__device__ __forceinline__ void mma_16x8x8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// this thread's 32 features, rounded to bf16, into its TMEM lane of the tile's X operand (16 packed columns)
+__device__ __forceinline__ void store_row_tmem(uint32_t tX, const float (&x)[D]) {
+    uint32_t p[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+    tmem_st16(tX, p);
+    tmem_wait_st();
+}
+
 // x <- LayerNorm(x) over the 32 features held by this thread; gamma/beta in shared memory (broadcast reads)
 __device__ __forceinline__ void layer_norm32(float (&x)[D], const float *g, const float *b) {
     float mean = 0.f;
@@ -142,20 +188,6 @@ __device__ __forceinline__ void layer_norm32(float (&x)[D], const float *g, cons
         x[d4 + 1] = (x[d4 + 1] - mean) * rstd * gg.y + bb.y;
         x[d4 + 2] = (x[d4 + 2] - mean) * rstd * gg.z + bb.z;
         x[d4 + 3] = (x[d4 + 3] - mean) * rstd * gg.w + bb.w;
-    }
-}
-
-// this thread's 32 features, rounded to bf16, into row r of the tile's K-major activation image (columns 0..31)
-__device__ __forceinline__ void store_row_image(uint8_t *xs, int r, const float (&x)[D]) {
-    uint8_t *row = xs + (r >> 3) * (KX / 8) * 128 + (r & 7) * 16;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint4 v;
-        v.x = pack_bf16x2(x[8 * j + 0], x[8 * j + 1]);
-        v.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
-        v.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
-        v.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
-        *reinterpret_cast<uint4 *>(row + j * 128) = v;
     }
 }
 
@@ -183,12 +215,16 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
         mbar_fence_init();
     }
     if (warp == kTiles * 5) tmem_alloc(tmem_slot, 512);
-    // constant columns 32..47 of every activation image: [1, 1, 0 x 14] (bias hi/lo ride on the two ones)
+    // attention-output images: zero (rows 120..127 are never written by the attention, and the out_proj reads them), then the
+    // constant columns 32..47 of every row: [1, 1, 0 x 14] (bias hi/lo ride on the two ones)
+    for (int i = tid; i < kTiles * XS_BYTES / 16; i += kThreads) reinterpret_cast<uint4 *>(smem + SM_XS)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
     for (int i = tid; i < kTiles * 128; i += kThreads) {
         uint8_t *row = smem + SM_XS + (i >> 7) * XS_BYTES + ((i & 127) >> 3) * (KX / 8) * 128 + (i & 7) * 16;
         *reinterpret_cast<uint4 *>(row + 4 * 128) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4 *>(row + 5 * 128) = make_uint4(0u, 0u, 0u, 0u);
     }
+    // attention operand buffers start finite (rows/columns past the 120 live tokens are read, never written)
+    for (int i = tid; i < kTiles * KV_BYTES / 16; i += kThreads) reinterpret_cast<uint4 *>(smem + SM_KV)[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -203,11 +239,11 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
             bulk_g2s(smem + SM_MISC, a.img + IMG_MISC, MISC_FLOATS * 4, c_full);
             uint32_t g = 0;
             for (int it = 0; it < n_it; ++it)
-                for (int lc = 0; lc < NL * NCH; ++lc, ++g) {
+                for (int ls = 0; ls < NL * NCH / CPS; ++ls, ++g) {
                     const uint32_t stage = g % NS, use = g / NS;
                     mbar_wait(w_empty + stage, (use & 1u) ^ 1u);
                     mbar_arrive_expect_tx(w_full + stage, STAGE_BYTES);
-                    bulk_g2s(smem + SM_RING + stage * STAGE_BYTES, a.img + IMG_FFN + (size_t)lc * STAGE_BYTES, STAGE_BYTES,
+                    bulk_g2s(smem + SM_RING + stage * STAGE_BYTES, a.img + IMG_FFN + (size_t)ls * STAGE_BYTES, STAGE_BYTES,
                              w_full + stage);
                 }
         }
@@ -228,17 +264,17 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
         for (int it = 0; it < n_it; ++it)
             for (int l = 0; l < NL; ++l, ++n) {
                 const uint32_t par = n & 1u;
-                // ---- q|k|v = [x|1|1] . [W_in|b_hi|b_lo]^T ----
+                // ---- q|k|v = [x|1|1] (TMEM) . [W_in|b_hi|b_lo]^T ----
                 mbar_wait(b + B_XFULL, par);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
                     for (int s = 0; s < KX / 16; ++s)
-                        mma_ss(tT, smem_desc(xs + s * 256, 128, SBO_X), smem_desc(att0 + l * ATT_BYTES + s * 256, 128, SBO_X), idesc_qkv, s > 0);
+                        mma_ts(tT, tT + TM_X + s * 8, smem_desc(att0 + l * ATT_BYTES + s * 256, 128, SBO_X), idesc_qkv, s > 0);
                     mma_commit(b + B_QKV);
                 }
                 __syncwarp();
-                // ---- attention output projection ----
+                // ---- attention output projection: [o|1|1] (smem image) . [W_out|b_hi|b_lo]^T ----
                 mbar_wait(b + B_OFULL, par);
                 tc_fence_after();
                 if (elect_one()) {
@@ -256,15 +292,17 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
                 const uint32_t g0 = n * NCH;
                 for (int c = 0; c < NCH + NHB - 1; ++c) {
                     if (c < NCH) {
-                        const uint32_t g = g0 + c, stage = g % NS, hb = g % NHB;
-                        mbar_wait(w_full + stage, (g / NS) & 1u);
-                        tc_fence_after();
+                        const uint32_t g = g0 + c, sg = g / CPS, stage = sg % NS, hb = g % NHB;
+                        if ((c & (CPS - 1)) == 0) {
+                            mbar_wait(w_full + stage, (sg / NS) & 1u);
+                            tc_fence_after();
+                        }
                         TC_PROF(9);
                         if (elect_one()) {
+                            const uint32_t w1 = ring0 + stage * STAGE_BYTES + (c & (CPS - 1)) * CHUNK_BYTES;
 #pragma unroll
                             for (int s = 0; s < KX / 16; ++s)
-                                mma_ss(tT + hb * CH, smem_desc(xs + s * 256, 128, SBO_X),
-                                       smem_desc(ring0 + stage * STAGE_BYTES + s * 256, 128, SBO_X), idesc_h, s > 0);
+                                mma_ts(tT + hb * CH, tT + TM_X + s * 8, smem_desc(w1 + s * 256, 128, SBO_X), idesc_h, s > 0);
                             mma_commit(b + B_H + hb);
                         }
                         __syncwarp();
@@ -272,17 +310,17 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
                     }
                     if (c >= NHB - 1) {
                         const int cc = c - (NHB - 1);
-                        const uint32_t g = g0 + cc, stage = g % NS, hb = g % NHB;
+                        const uint32_t g = g0 + cc, sg = g / CPS, stage = sg % NS, hb = g % NHB;
                         mbar_wait(b + B_P + hb, (g / NHB) & 1u);
                         tc_fence_after();
                         TC_PROF(11);
                         if (elect_one()) {
+                            const uint32_t w2 = ring0 + stage * STAGE_BYTES + (cc & (CPS - 1)) * CHUNK_BYTES + W1_BYTES;
 #pragma unroll
                             for (int s = 0; s < CH / 16; ++s)
-                                mma_ts(tT + TM_Y, tT + hb * CH + s * 8,
-                                       smem_desc(ring0 + stage * STAGE_BYTES + W1_BYTES + s * 256, 128, SBO_W2), idesc_32,
+                                mma_ts(tT + TM_Y, tT + hb * CH + s * 8, smem_desc(w2 + s * 256, 128, SBO_W2), idesc_32,
                                        (cc > 0 || s > 0) ? 1u : 0u);
-                            mma_commit(w_empty + stage);
+                            if ((cc & (CPS - 1)) == CPS - 1) mma_commit(w_empty + stage);
                             if (cc == NCH - 1) mma_commit(b + B_Y);
                         }
                         __syncwarp();
@@ -293,12 +331,21 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
         TC_PROF_FLUSH;
     } else {
         // =============================== token-tile warpgroups ==========================================
-        const int t = warp >> 2, r = tid & 127, lane = tid & 31;
+        const int t = warp >> 2, r = tid & 127, lane = tid & 31, wq = warp & 3;
         const int e_loc = r / SMAX, s_pos = r % SMAX;
         uint64_t *b = bars + t * kBarPerTile;
         uint8_t *xs = smem + SM_XS + t * XS_BYTES;
-        float *kv = reinterpret_cast<float *>(smem + SM_KV + t * KV_BYTES);
-        const uint32_t tT = tbase + t * TM_TILE + ((uint32_t)((warp & 3) * 32) << 16);
+        uint8_t *att = smem + SM_KV + t * KV_BYTES;
+        __nv_bfloat16 *sq = reinterpret_cast<__nv_bfloat16 *>(att + SQ_OFF), *sk = reinterpret_cast<__nv_bfloat16 *>(att + SK_OFF),
+                      *svt = reinterpret_cast<__nv_bfloat16 *>(att + SVT_OFF);
+        int *slen = reinterpret_cast<int *>(att + SLEN_OFF);
+        const uint32_t tT = tbase + t * TM_TILE + ((uint32_t)(wq * 32) << 16);
+        // constant K columns 32..47 of the X operand: [1, 1, 0 x 14]
+        {
+            const uint32_t ones[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            tmem_st8(tT + TM_X + 16, ones);
+            tmem_wait_st();
+        }
         mbar_wait(c_full, 0);
         const bool prof = blockIdx.x == 0 && tid == 0;
         TC_PROF_DECL;
@@ -343,88 +390,151 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
                 }
             }
             const bool tok_ok = env_ok && s_pos < S;
+            // the previous group's attention (last reader of slen) finished before its o_full arrivals, which every
+            // thread of the tile has since waited behind (out_full)
+            if (r < ROWS && s_pos == 0) slen[e_loc] = S;
 
             for (int l = 0; l < NL; ++l, ++n) {
                 const uint32_t par = n & 1u;
                 const float *lw = misc + l * MISC_LAYER;
-                // ---- x -> bf16 image -> q|k|v on the tensor core ----
-                store_row_image(xs, r, x);
-                fence_proxy_async();
+                // ---- x -> bf16 operand in tensor memory -> q|k|v on the tensor core ----
+                store_row_tmem(tT + TM_X, x);
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b + B_XFULL);
                 TC_PROF(0);
                 mbar_wait(b + B_QKV, par);
                 tc_fence_after();
                 TC_PROF(1);
-                float q[D];
                 {
-                    uint32_t rq[32], rk[32], rv[32];
+                    // q|k|v rows -> bf16 attention operands: q[r][:], k[r][:] row-major, v transposed vT[:][r]
+                    uint32_t rq[32];
                     tmem_ld32(tT, rq);
-                    tmem_ld32(tT + 32, rk);
-                    tmem_ld32(tT + 64, rv);
+                    tmem_wait_ld();
+                    uint4 *qrow = reinterpret_cast<uint4 *>(sq + r * QK_LD);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        qrow[j] = make_uint4(pack_bf16x2(__uint_as_float(rq[8 * j]), __uint_as_float(rq[8 * j + 1])),
+                                             pack_bf16x2(__uint_as_float(rq[8 * j + 2]), __uint_as_float(rq[8 * j + 3])),
+                                             pack_bf16x2(__uint_as_float(rq[8 * j + 4]), __uint_as_float(rq[8 * j + 5])),
+                                             pack_bf16x2(__uint_as_float(rq[8 * j + 6]), __uint_as_float(rq[8 * j + 7])));
+                    tmem_ld32(tT + 32, rq);
+                    tmem_wait_ld();
+                    uint4 *krow = reinterpret_cast<uint4 *>(sk + r * QK_LD);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        krow[j] = make_uint4(pack_bf16x2(__uint_as_float(rq[8 * j]), __uint_as_float(rq[8 * j + 1])),
+                                             pack_bf16x2(__uint_as_float(rq[8 * j + 2]), __uint_as_float(rq[8 * j + 3])),
+                                             pack_bf16x2(__uint_as_float(rq[8 * j + 4]), __uint_as_float(rq[8 * j + 5])),
+                                             pack_bf16x2(__uint_as_float(rq[8 * j + 6]), __uint_as_float(rq[8 * j + 7])));
+                    tmem_ld32(tT + 64, rq);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int d = 0; d < D; ++d) q[d] = __uint_as_float(rq[d]);
-                    if (r < ROWS) {
-                        float4 *row = reinterpret_cast<float4 *>(kv + r * KV_LD);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            row[j] = make_float4(__uint_as_float(rk[4 * j]), __uint_as_float(rk[4 * j + 1]), __uint_as_float(rk[4 * j + 2]),
-                                                 __uint_as_float(rk[4 * j + 3]));
-                            row[8 + j] = make_float4(__uint_as_float(rv[4 * j]), __uint_as_float(rv[4 * j + 1]),
-                                                     __uint_as_float(rv[4 * j + 2]), __uint_as_float(rv[4 * j + 3]));
-                        }
-                    }
+                    for (int d = 0; d < D; ++d) svt[d * VT_LD + r] = __float2bfloat16_rn(__uint_as_float(rq[d]));
                 }
                 named_bar_sync(1 + t, 128);
                 TC_PROF(2);
-                // ---- attention: this thread = one query token, all 4 heads; scores are already in the log2 domain ----
-                float o[D];
+                // ---- attention on register fragments: this warp owns 6 of the tile's 24 (env, head) blocks ----
+                {
+                    const int g8 = lane >> 2, tq = lane & 3;
+#pragma unroll 2
+                    for (int u = wq * 6; u < wq * 6 + 6; ++u) {
+                        const int e = u >> 2, h = u & 3, row0 = e * SMAX;
+                        const int Se = max(slen[e], 1);             // envs past the batch end: keep every value finite
+                        // scores S = Q_h K_h^T (already in the log2 domain): 2 query m-tiles x 3 key n-tiles
+                        uint32_t qa[2][2], kb[3];
 #pragma unroll
-                for (int d = 0; d < D; ++d) o[d] = 0.f;
-                if (tok_ok) {
-                    const float *kvb = kv + e_loc * SMAX * KV_LD;
-#pragma unroll
-                    for (int h = 0; h < NH; ++h) {
-                        float sc[SMAX];
-                        float mx = -INFINITY;
-#pragma unroll
-                        for (int j = 0; j < SMAX; ++j) {
-                            if (j < S) {
-                                const float4 k0 = *reinterpret_cast<const float4 *>(kvb + j * KV_LD + h * HD);
-                                const float4 k1 = *reinterpret_cast<const float4 *>(kvb + j * KV_LD + h * HD + 4);
-                                float s = q[h * HD] * k0.x;
-                                s = fmaf(q[h * HD + 1], k0.y, s); s = fmaf(q[h * HD + 2], k0.z, s); s = fmaf(q[h * HD + 3], k0.w, s);
-                                s = fmaf(q[h * HD + 4], k1.x, s); s = fmaf(q[h * HD + 5], k1.y, s); s = fmaf(q[h * HD + 6], k1.z, s);
-                                s = fmaf(q[h * HD + 7], k1.w, s);
-                                sc[j] = s;
-                                mx = fmaxf(mx, s);
-                            } else sc[j] = -INFINITY;
+                        for (int mt = 0; mt < 2; ++mt) {
+                            qa[mt][0] = *reinterpret_cast<const uint32_t *>(sq + (row0 + mt * 16 + g8) * QK_LD + h * HD + 2 * tq);
+                            qa[mt][1] = *reinterpret_cast<const uint32_t *>(sq + (row0 + mt * 16 + g8 + 8) * QK_LD + h * HD + 2 * tq);
                         }
-                        float sum = 0.f;
 #pragma unroll
-                        for (int j = 0; j < SMAX; ++j) { sc[j] = exp2f(sc[j] - mx); sum += sc[j]; }
-                        float acc[HD];
+                        for (int nt = 0; nt < 3; ++nt)
+                            kb[nt] = *reinterpret_cast<const uint32_t *>(sk + (row0 + nt * 8 + g8) * QK_LD + h * HD + 2 * tq);
+                        float sc[2][3][4];
 #pragma unroll
-                        for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+                        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                        for (int j = 0; j < SMAX; ++j) {
-                            if (j < S) {
-                                const float4 v0 = *reinterpret_cast<const float4 *>(kvb + j * KV_LD + D + h * HD);
-                                const float4 v1 = *reinterpret_cast<const float4 *>(kvb + j * KV_LD + D + h * HD + 4);
-                                acc[0] = fmaf(sc[j], v0.x, acc[0]); acc[1] = fmaf(sc[j], v0.y, acc[1]);
-                                acc[2] = fmaf(sc[j], v0.z, acc[2]); acc[3] = fmaf(sc[j], v0.w, acc[3]);
-                                acc[4] = fmaf(sc[j], v1.x, acc[4]); acc[5] = fmaf(sc[j], v1.y, acc[5]);
-                                acc[6] = fmaf(sc[j], v1.z, acc[6]); acc[7] = fmaf(sc[j], v1.w, acc[7]);
+                            for (int nt = 0; nt < 3; ++nt) {
+                                sc[mt][nt][0] = sc[mt][nt][1] = sc[mt][nt][2] = sc[mt][nt][3] = 0.f;
+                                mma_16x8x8(sc[mt][nt], qa[mt][0], qa[mt][1], kb[nt]);
+                            }
+                        // V fragments: vT[feature g8 of head h][key 8*ks + 2*tq, +1]
+                        uint32_t vb[3];
+#pragma unroll
+                        for (int ks = 0; ks < 3; ++ks)
+                            vb[ks] = *reinterpret_cast<const uint32_t *>(svt + (h * HD + g8) * VT_LD + row0 + ks * 8 + 2 * tq);
+                        // masked keys belong to another env (or to no token): their V is zeroed, not just weighted by p = 0, so a
+                        // non-finite value in one env can never reach its neighbours in the tile
+                        if (Se == SMAX) { if (tq >= 2) vb[2] = 0u; }
+                        else {
+#pragma unroll
+                            for (int ks = 0; ks < 3; ++ks) {
+                                const int k0 = ks * 8 + 2 * tq;
+                                if (k0 >= Se) vb[ks] = 0u; else if (k0 + 1 >= Se) vb[ks] &= 0x0000FFFFu;
                             }
                         }
-                        const float inv = 1.0f / sum;
 #pragma unroll
-                        for (int d = 0; d < HD; ++d) o[h * HD + d] = acc[d] * inv;
+                        for (int mt = 0; mt < 2; ++mt) {
+                            // rows g8 (elements 0,1) and g8+8 (elements 2,3) of this m-tile; key of element i: 8*nt + 2*tq + (i&1).
+                            // Rows 24..31 (second half of m-tile 1) never belong to this env: nothing is computed for them.
+                            const bool lo_rows_only = mt == 1;
+                            if (Se == SMAX) {                 // full history (the common case): only keys 20..23 are masked
+                                if (tq >= 2) sc[mt][2][0] = sc[mt][2][1] = sc[mt][2][2] = sc[mt][2][3] = -INFINITY;
+                            } else {
+#pragma unroll
+                                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i)
+                                        if (nt * 8 + 2 * tq + (i & 1) >= Se) sc[mt][nt][i] = -INFINITY;
+                            }
+                            float mx0 = fmaxf(fmaxf(fmaxf(sc[mt][0][0], sc[mt][0][1]), fmaxf(sc[mt][1][0], sc[mt][1][1])),
+                                              fmaxf(sc[mt][2][0], sc[mt][2][1]));
+                            float mx1 = lo_rows_only ? 0.f
+                                                     : fmaxf(fmaxf(fmaxf(sc[mt][0][2], sc[mt][0][3]), fmaxf(sc[mt][1][2], sc[mt][1][3])),
+                                                             fmaxf(sc[mt][2][2], sc[mt][2][3]));
+                            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+                            if (!lo_rows_only) {
+                                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+                            }
+                            float sum0 = 0.f, sum1 = 0.f;
+                            uint32_t pa[3][2];
+#pragma unroll
+                            for (int nt = 0; nt < 3; ++nt) {
+                                const float p0 = fast_exp2(sc[mt][nt][0] - mx0), p1 = fast_exp2(sc[mt][nt][1] - mx0);
+                                sum0 += p0 + p1;
+                                pa[nt][0] = pack_bf16x2(p0, p1);
+                                if (!lo_rows_only) {
+                                    const float p2 = fast_exp2(sc[mt][nt][2] - mx1), p3 = fast_exp2(sc[mt][nt][3] - mx1);
+                                    sum1 += p2 + p3;
+                                    pa[nt][1] = pack_bf16x2(p2, p3);
+                                } else pa[nt][1] = 0u;
+                            }
+                            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+                            if (!lo_rows_only) {
+                                sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+                            }
+                            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int ks = 0; ks < 3; ++ks) mma_16x8x8(o, pa[ks][0], pa[ks][1], vb[ks]);
+                            // rows past the env's 20 tokens belong to the next env: not stored
+                            const int q0 = mt * 16 + g8;
+                            if (q0 < SMAX) {
+                                const int rr = row0 + q0;
+                                const float i0 = fast_rcp(sum0);
+                                *reinterpret_cast<uint32_t *>(xs + (rr >> 3) * (KX / 8) * 128 + h * 128 + (rr & 7) * 16 + tq * 4) =
+                                    pack_bf16x2(o[0] * i0, o[1] * i0);
+                            }
+                            if (!lo_rows_only) {
+                                const int rr = row0 + q0 + 8;
+                                const float i1 = fast_rcp(sum1);
+                                *reinterpret_cast<uint32_t *>(xs + (rr >> 3) * (KX / 8) * 128 + h * 128 + (rr & 7) * 16 + tq * 4) =
+                                    pack_bf16x2(o[2] * i1, o[3] * i1);
+                            }
+                        }
                     }
                 }
-                // ---- o -> bf16 image (the q|k|v MMA that read the image has completed) -> out_proj ----
-                store_row_image(xs, r, o);
+                // ---- o (bf16 image in shared memory) -> out_proj ----
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b + B_OFULL);
@@ -441,9 +551,8 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
                 }
                 layer_norm32(x, lw, lw + D);
                 // ---- FFN ----
-                store_row_image(xs, r, x);
-                fence_proxy_async();
-                tc_fence_before();                        // orders the tcgen05.ld of OUT before MMA2 overwrites that region
+                store_row_tmem(tT + TM_X, x);
+                tc_fence_before();                        // also orders the tcgen05.ld of OUT before MMA2 overwrites that region
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b + B_X2);
                 TC_PROF(5);
@@ -484,7 +593,6 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
                     }
                 }
                 layer_norm32(x, lw + 2 * D, lw + 3 * D);
-                tc_fence_before();                        // tcgen05.ld of Y / H ordered before the next layer's MMAs
                 TC_PROF(7);
             }
             // ---- last token -> fc_out -> 0.5*tanh + 0.5 ----
@@ -525,7 +633,7 @@ __global__ void emotion_tc_pack_kernel(const erlfill_transformer_weights w, uint
     for (int i = i0; i < NL * NCH * (CH * KX + D * CH); i += stride) {
         const int per = CH * KX + D * CH;
         const int lc = i / per, j = i % per, l = lc / NCH, c = lc % NCH;
-        uint8_t *st = img + IMG_FFN + (size_t)lc * STAGE_BYTES;
+        uint8_t *st = img + IMG_FFN + (size_t)lc * CHUNK_BYTES;
         if (j < CH * KX) {
             const int nn = j / KX, k = j % KX, hid = c * CH + nn;
             put_bf16(st, kmajor_off(nn, k, KX), aug_col(w.lin1_w + ((size_t)l * FF + hid) * D, w.lin1_b[l * FF + hid], k, 1.0f));
