@@ -236,7 +236,8 @@ def _make_agent(args, rank, device, n, batch, memory):
     conds = list(K.EXPERIMENT_3.values())
     env = E.VecFillEnv(conds, n, kind="multi", max_steps=100, seed=0, device=device, env_id_base=rank * n,
                        sim_mode=args.sim_mode)
-    agent = E.VecERDDPG(env, seed=0, batch_size=batch, memory_size=memory, rank=rank)
+    agent = E.VecERDDPG(env, seed=0, batch_size=batch, memory_size=memory, rank=rank,
+                        emotion_precision=args.emotion_precision)
     return env, agent
 
 
@@ -284,7 +285,9 @@ def wl_rollout(args, rank, world, device, timer):
         "gpu_launches": 8 * args.steps,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
-                     "peak_source": peaks["source"] + " (sustained)", "kernel": "emotion_forward_kernel", "kernel_ms": tf_ms,
+                     "peak_source": peaks["source"] + " (sustained)",
+                     "kernel": "emotion_forward_tc_kernel" if agent.emotion_precision == "bf16" else "emotion_forward_kernel",
+                     "kernel_ms": tf_ms,
                      "share_of_step": tf_ms / (total_ms / args.steps), "algorithmic_flop_per_env": TRANSFORMER_FLOP},
     }
 
@@ -490,6 +493,8 @@ def main():
     ap.add_argument("--replay", type=int, default=1000000)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--sim-mode", default="auto", choices=["auto", "warp", "thread"])
+    ap.add_argument("--emotion-precision", default="bf16", choices=["bf16", "fp32"],
+                    help="EmotionTransformer kernel of the rollout: tcgen05 bf16 (default) or the exact fp32 SIMT twin")
     args = ap.parse_args()
     if args.n_env is None:
         args.n_env = {"sim": 4096, "rollout": 65536, "update": 256}[args.workload]
