@@ -9,6 +9,7 @@ One JSON line on stdout (rank 0).  A "step" is one lock-step pass of the workloa
   sim      configs[1] of BASELINE.json: batched WeightEnv rollout, PID-effective constant action (default, 4096 envs/GPU)
   rollout  configs[2]: MultiConditionWeightEnv, EmotionModule transformer -> ER-DDPG actor + OU -> env step -> emotion update
   update   configs[3]: ER-DDPG update, minibatch 4096 from a 1M-transition replay (sample + gather + U1-U5)
+  all      (default) the sim line, with the rollout and update results attached under "other_workloads"
 `value` is device-timed with inputs resident in HBM; `e2e` goes through the public Python API with pinned HOST
 buffers (H2D of the step's inputs, D2H of its results inside the timed region).
 """
@@ -373,8 +374,22 @@ def run_ours(args):
     timer = Timer(device, world)
     sampler = ClockSampler(local)
     sampler.start()
-    out = {"sim": wl_sim, "rollout": wl_rollout, "update": wl_update}[args.workload](args, rank, world, device, timer)
+    wl = {"sim": wl_sim, "rollout": wl_rollout, "update": wl_update}
+    head = "sim" if args.workload == "all" else args.workload
+    if args.workload == "all":
+        args.n_env = args.n_env or 4096
+    out = wl[head](args, rank, world, device, timer)
     clocks = sampler.stop()
+    others = []
+    if args.workload == "all":
+        # the two other metrics of BASELINE.json on their own configs, compact (same timing rules)
+        import copy
+        for name, n_env, steps in (("rollout", 65536, 10), ("update", 256, 20)):
+            a2 = copy.copy(args)
+            a2.n_env, a2.steps = n_env, steps
+            o = wl[name](a2, rank, world, device, timer)
+            others.append({k: o[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "e2e", "gpu_launches", "roofline")}
+                          | {"workload": o["config"]["workload"], "steps": steps})
     if rank == 0:
         issue = out.pop("_issue", None)
         line = {"metric": out.pop("metric"), "value": out.pop("value"), "unit": out.pop("unit"), "n_gpus": world,
@@ -388,8 +403,10 @@ def run_ours(args):
             line["issue_roofline"] = {"achieved_env_steps_per_s_per_gpu": issue[0], "ceiling": ceiling, "frac": issue[0] / ceiling,
                                       "warp_instr_per_env_step": issue[1], "sm_mhz_used": mhz,
                                       "model": "148 SMs x 4 schedulers x 1 warp-instruction/clk / measured warp-instructions per env-step"}
-        if args.workload == "sim":
+        if head == "sim":
             line["cpu_baseline"] = cpu_baseline_sim(args, budget_s=args.cpu_budget)
+        if others:
+            line["other_workloads"] = others
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -450,7 +467,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    if args.workload != "sim":
+    if args.workload not in ("sim", "all"):
         print(json.dumps({"impl": "reference", "unavailable": "the CPU port is timed on the sim workload (configs[1]) only"}),
               flush=True)
         return
@@ -486,7 +503,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sim", choices=["sim", "rollout", "update"])
+    ap.add_argument("--workload", default="all", choices=["all", "sim", "rollout", "update"],
+                    help="all = the sim headline line plus compact rollout and update results under other_workloads")
     ap.add_argument("--n-env", type=int, default=None)
     ap.add_argument("--actions", default="pid", choices=["pid", "random"])
     ap.add_argument("--batch", type=int, default=4096)
@@ -497,7 +515,7 @@ def main():
                     help="EmotionTransformer kernel of the rollout: tcgen05 bf16 (default) or the exact fp32 SIMT twin")
     args = ap.parse_args()
     if args.n_env is None:
-        args.n_env = {"sim": 4096, "rollout": 65536, "update": 256}[args.workload]
+        args.n_env = {"all": 4096, "sim": 4096, "rollout": 65536, "update": 256}[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -93,7 +93,7 @@ EXPORTS = [
     "erlfill_actor_forward", "erlfill_emotion_update", "erlfill_episode_end", "erlfill_emotion_forward",
     "erlfill_emotion_tc_image_bytes", "erlfill_emotion_tc_pack", "erlfill_emotion_forward_tc",
     "erlfill_replay_insert", "erlfill_replay_sample", "erlfill_replay_gather",
-    "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_update",
+    "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_set_step", "erlfill_ddpg_update",
 ]
 
 _lib = None

@@ -13,8 +13,8 @@
 //
 // Structure: parameters, gradients and Adam moments are flat fp32 buffers in the reference's
 // parameters() order, so clip / Adam / soft update / the data-parallel all-reduce are single passes.
-// The dense layers run through one strided, split-K capable SIMT fp32 GEMM (this file) — the update is
-// launch/latency bound at these sizes (5.9 GFLOP at B=4096), see DESIGN.md section 4.  Every reduction is
+// The dense layers run through one strided, split-K capable tensor-core GEMM (mma.sync TF32, 3xTF32 compensated,
+// this file); the update is dependent-launch/latency bound at these sizes (5.9 GFLOP at B=4096), see DESIGN.md section 4.  Every reduction is
 // tree-ordered without atomics, so an update is bit-reproducible.
 #include <math.h>
 
@@ -31,64 +31,103 @@ __constant__ int c_actor_seg[kActorTensors + 1] = {0, 30, 670, 798, 17182, 17310
 constexpr int kCriticGradPad = 103968;     // critic grads + 3 emotion means + padding (16 B multiple)
 constexpr int kActorGradPad = 26240;
 
-// ---- generic strided GEMM: C[M,N] = act(A(M,K) * B(K,N) + bias[N]) ----------------------------
-// A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].  gridDim.z > 1: split-K partials to C + z*M*ldc... (see below)
-constexpr int BM = 64, BN = 64, BK = 16;
+// ---- generic strided GEMM on the tensor cores: C[M,N] = act(A(M,K) * B(K,N) + bias[N]) ------------
+// A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].  gridDim.z > 1: split-K partials to C + z*split_stride.
+// mma.sync.m16n8k8 TF32 with fp32 accumulation, error-compensated (3xTF32: a = hi + lo, a*b ~ lo*hi + hi*lo + hi*hi), so
+// the result keeps fp32-level accuracy (the parity bar of the update is 1e-4 against torch fp32) while the
+// multiply-accumulates run on the tensor pipe.  These GEMMs are M = batch (128..4096) by N, K <= 256: the register-
+// fragment MMA fits them; a tcgen05/TMEM tile would be mostly padding.
+constexpr int BM = 64, BN = 64, BK = 16, LDS_T = 72;          // 72 % 32 == 8: conflict-free fragment loads
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
+
+__device__ __forceinline__ void split_tf32(float v, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+    const float r = v - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
 
 __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float *__restrict__ A, int sam, int sak,
                                                    const float *__restrict__ B, int sbk, int sbn, float *__restrict__ C,
                                                    int ldc, const float *__restrict__ bias, int act, int k_per_split,
                                                    size_t split_stride) {
-    __shared__ __align__(16) float As[BK][BM + 4];
-    __shared__ __align__(16) float Bs[BK][BN + 4];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    __shared__ __align__(16) float As[BK][LDS_T];
+    __shared__ __align__(16) float Bs[BK][LDS_T];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;      // 2 x 4 warps, each a 32 x 16 tile = 2 (m16) x 2 (n8) MMA tiles
+    const int g = lane >> 2, t = lane & 3;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
-    float acc[4][4] = {};
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
-        // load tiles; pick the fastest-varying index along the unit-stride dimension for coalescing
+    float acc[2][2][4] = {};
+    // per-thread tile coordinates (the fastest-varying index follows the unit-stride dimension for coalescing)
+    int am[4], ak[4], bn[4], bk[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int e = tid + it * 256;
+        if (sak == 1) { ak[it] = e & 15; am[it] = e >> 4; } else { am[it] = e & 63; ak[it] = e >> 6; }
+        if (sbn == 1) { bn[it] = e & 63; bk[it] = e >> 6; } else { bk[it] = e & 15; bn[it] = e >> 4; }
+    }
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-            const int e = tid + it * 256;
-            int m, k;
-            if (sak == 1) { k = e & 15; m = e >> 4; } else { m = e & 63; k = e >> 6; }
-            const int gm = m0 + m, gk = k0 + k;
-            As[k][m] = (gm < M && gk < kend) ? A[(size_t)gm * sam + (size_t)gk * sak] : 0.f;
-            int n, kb;
-            if (sbn == 1) { n = e & 63; kb = e >> 6; } else { kb = e & 15; n = e >> 4; }
-            const int gn = n0 + n, gkb = k0 + kb;
-            Bs[kb][n] = (gn < N && gkb < kend) ? B[(size_t)gkb * sbk + (size_t)gn * sbn] : 0.f;
+            const int gm = m0 + am[it], gk = k0 + ak[it];
+            ra[it] = (gm < M && gk < kend) ? A[(size_t)gm * sam + (size_t)gk * sak] : 0.f;
+            const int gn = n0 + bn[it], gkb = k0 + bk[it];
+            rb[it] = (gn < N && gkb < kend) ? B[(size_t)gkb * sbk + (size_t)gn * sbn] : 0.f;
         }
+    };
+    fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) { As[ak[it]][am[it]] = ra[it]; Bs[bk[it]][bn[it]] = rb[it]; }
         __syncthreads();
+        if (k0 + BK < kend) fetch(k0 + BK);           // next tile's global loads fly under this tile's MMAs
 #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            const float4 a = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        for (int ks = 0; ks < BK; ks += 8) {
+            uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i) {
+                split_tf32(As[ks + t][wm + i * 16 + g], ah[i][0], al[i][0]);
+                split_tf32(As[ks + t][wm + i * 16 + g + 8], ah[i][1], al[i][1]);
+                split_tf32(As[ks + t + 4][wm + i * 16 + g], ah[i][2], al[i][2]);
+                split_tf32(As[ks + t + 4][wm + i * 16 + g + 8], ah[i][3], al[i][3]);
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            for (int j = 0; j < 2; ++j) {
+                split_tf32(Bs[ks + t][wn + j * 8 + g], bh[j][0], bl[j][0]);
+                split_tf32(Bs[ks + t + 4][wn + j * 8 + g], bh[j][1], bl[j][1]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    mma_tf32(acc[i][j], al[i], bh[j]);
+                    mma_tf32(acc[i][j], ah[i], bl[j]);
+                    mma_tf32(acc[i][j], ah[i], bh[j]);
+                }
         }
         __syncthreads();
     }
     float *Cz = C + (size_t)blockIdx.z * split_stride;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + ty * 4 + i;
-        if (gm >= M) continue;
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gn = n0 + tx * 4 + j;
-            if (gn >= N) continue;
-            float v = acc[i][j];
-            if (bias) v += bias[gn];
-            if (act == ACT_RELU) v = fmaxf(v, 0.f);
-            else if (act == ACT_LEAKY) v = v > 0.f ? v : 0.1f * v;
-            Cz[(size_t)gm * ldc + gn] = v;
-        }
-    }
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int gm = m0 + wm + i * 16 + g + (e >> 1) * 8, gn = n0 + wn + j * 8 + 2 * t + (e & 1);
+                if (gm >= M || gn >= N) continue;
+                float v = acc[i][j][e];
+                if (bias) v += bias[gn];
+                if (act == ACT_RELU) v = fmaxf(v, 0.f);
+                else if (act == ACT_LEAKY) v = v > 0.f ? v : 0.1f * v;
+                Cz[(size_t)gm * ldc + gn] = v;
+            }
 }
 
 // sum split-K partials: out[i] = sum_z part[z*stride + i]
@@ -100,15 +139,20 @@ __global__ void splitk_reduce_kernel(int n, int splits, const float *part, size_
     out[i] = s;
 }
 
-// column sums: out[c] = sum_r X[r*ld + c] (* optional Y[r*ld+c]); one block per 32 columns, tree order fixed
-__global__ void __launch_bounds__(256) colsum_kernel(int rows, int cols, const float *X, const float *Y, int ld, float *out) {
+// column sums, two deterministic stages: part[s][c] = sum over the rows of slice s of X[r*ld + c] * y(r, c), where
+// y = 1 (Y == nullptr) or Y[r*ldy + c*ycs] (ycs = 0: one factor per row); then splitk_reduce_kernel adds the slices in
+// index order.  grid = (ceil(cols/32), kColSplits): a block is 32 columns x 8 row lanes over rows/kColSplits rows.
+constexpr int kColSplits = 32;
+__global__ void __launch_bounds__(256) colsum_part_kernel(int rows, int cols, const float *X, int ld, const float *Y, int ldy, int ycs,
+                                                          float *part) {
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+    const int per = (rows + kColSplits - 1) / kColSplits, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
     float s = 0.f;
     if (c < cols)
-        for (int r = rl; r < rows; r += 8) {
+        for (int r = r0 + rl; r < r1; r += 8) {
             const float x = X[(size_t)r * ld + c];
-            s += Y ? x * Y[(size_t)r * ld + c] : x;
+            s = Y ? fmaf(x, Y[(size_t)r * ldy + (size_t)c * ycs], s) : s + x;
         }
     red[rl][threadIdx.x & 31] = s;
     __syncthreads();
@@ -116,7 +160,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(int rows, int cols, const f
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
-        out[c] = t;
+        part[(size_t)blockIdx.y * cols + c] = t;
     }
 }
 
@@ -281,21 +325,6 @@ __global__ void critic_head_bwd_kernel(int B, const float *dq, const float *w10,
     const int r = g >> 7, c = g & 127;
     dh3[g] = h3[g] > 0.f ? dq[r] * w10[c] : 0.f;
 }
-__global__ void __launch_bounds__(256) head_wgrad_kernel(int B, const float *dq, const float *h3, float *dw10, float *db10) {
-    // dw10[c] = sum_r dq[r]*h3[r][c] (128 cols, 2 row-lanes each), db10 = sum_r dq[r]
-    __shared__ float red[2][128];
-    __shared__ float scratch[32];
-    const int c = threadIdx.x & 127, rl = threadIdx.x >> 7;
-    float s = 0.f;
-    for (int r = rl; r < B; r += 2) s = fmaf(dq[r], h3[(size_t)r * 128 + c], s);
-    red[rl][c] = s;
-    float b = 0.f;
-    for (int r = threadIdx.x; r < B; r += 256) b += dq[r];
-    const float bt = block_sum(b, scratch);
-    if (rl == 0) dw10[c] = red[0][c] + red[1][c];
-    if (threadIdx.x == 0) db10[0] = bt;
-}
-
 // ---- actor head: z4 -> physical action, and its backward ---------------------------------------
 __global__ void actor_head_fwd_kernel(int B, const float *z4, const float *xa, const float *ew, const float *scale,
                                       const float *offset, float *out, float *aux /*[B][10][3]: base, alpha*sflip*mod2.., see bwd*/) {
@@ -350,15 +379,21 @@ __global__ void actor_head_bwd_kernel(int B, const float *dout_critic, const flo
         draw_e[g] = gr * alpha * sf * (om * om) * (1.0f - raw * raw) * 1.5f;
     }
 }
-// dEW[k][c] = sum_r xa[r][2+k] * draw_e[r][c]   (30 outputs)
-__global__ void __launch_bounds__(256) ew_grad_kernel(int B, const float *xa, const float *draw_e, float *dew) {
-    __shared__ float scratch[32];
-    for (int o = 0; o < 30; ++o) {
-        const int k = o / 10, c = o % 10;
-        float s = 0.f;
-        for (int r = threadIdx.x; r < B; r += blockDim.x) s = fmaf(xa[r * 8 + 2 + k], draw_e[(size_t)r * 10 + c], s);
-        const float t = block_sum(s, scratch);
-        if (threadIdx.x == 0) dew[o] = t;
+// dEW[k][c] = sum_r xa[r][2+k] * draw_e[r][c]   (30 outputs): per-slice partials part[slice][30], summed by splitk_reduce_kernel
+__global__ void __launch_bounds__(256) ew_grad_part_kernel(int B, const float *xa, const float *draw_e, float *part) {
+    __shared__ float red[8][32];
+    const int o = threadIdx.x & 31, rl = threadIdx.x >> 5, k = o / 10, c = o % 10;
+    const int per = (B + kColSplits - 1) / kColSplits, r0 = blockIdx.x * per, r1 = min(B, r0 + per);
+    float s = 0.f;
+    if (o < 30)
+        for (int r = r0 + rl; r < r1; r += 8) s = fmaf(xa[r * 8 + 2 + k], draw_e[(size_t)r * 10 + c], s);
+    red[rl][o] = s;
+    __syncthreads();
+    if (rl == 0 && o < 30) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][o];
+        part[blockIdx.x * 30 + o] = t;
     }
 }
 
@@ -398,16 +433,25 @@ __global__ void actor_l2_grad_kernel(const float *actor, const float *tensor_nor
 }
 
 // ---- optimiser -------------------------------------------------------------------------------
-// sum of squares of a flat buffer -> out[0] (single block, fixed order)
-__global__ void __launch_bounds__(1024) sumsq_kernel(int n, const float *g, float *out) {
+// sum of squares of a flat buffer: kSumsqBlocks per-block partials (fixed order inside a block); the consumer adds them in index order
+constexpr int kSumsqBlocks = 64;
+__global__ void __launch_bounds__(256) sumsq_kernel(int n, const float *g, float *out /*[kSumsqBlocks]*/) {
     __shared__ float scratch[32];
+    const int per = (n + kSumsqBlocks - 1) / kSumsqBlocks, i0 = blockIdx.x * per, i1 = min(n, i0 + per);
     float s = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(g[i], g[i], s);
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) s = fmaf(g[i], g[i], s);
     const float t = block_sum(s, scratch);
-    if (threadIdx.x == 0) out[0] = t;
+    if (threadIdx.x == 0) out[blockIdx.x] = t;
 }
 // learning rates from the (all-reduced) emotion means: ddpg_agent.py:447-457
-__global__ void lr_kernel(const float *means, double decay, double critic_lr, double actor_lr, float *lrs /*[2]*/) {
+// per-update scalars in device memory so that a captured CUDA graph of the update can be replayed for every step:
+// step[0..1] = (double) lr_decay_rate ** train_step, step[2] = 1 - 0.9^t, step[3] = sqrt(1 - 0.999^t)
+__global__ void set_step_kernel(float *step, double decay, float bc1, float bc2_sqrt) {
+    *reinterpret_cast<double *>(step) = decay;
+    step[2] = bc1; step[3] = bc2_sqrt;
+}
+__global__ void lr_kernel(const float *means, const float *step, double critic_lr, double actor_lr, float *lrs /*[2]*/) {
+    const double decay = *reinterpret_cast<const double *>(step);
     const double cur = means[0], cons = means[1], anx = means[2];
     const double af = 1.0 + 0.8 * cur - 0.4 * cons + 0.2 * anx, cf = 1.0 - 0.3 * anx + 0.6 * cons;
     const double c = fmin(fmax(critic_lr * cf * decay, critic_lr * 0.1), critic_lr * 3);
@@ -416,10 +460,14 @@ __global__ void lr_kernel(const float *means, double decay, double critic_lr, do
 }
 // clip_grad_norm_(5.0) + Adam(0.9, 0.999, 1e-8) + soft target update, one pass over the flat buffers
 __global__ void adam_soft_kernel(int n, float *p, float *pt, float *m, float *v, const float *g, const float *sumsq,
-                                 const float *lr_ptr, float max_norm, float bc1, float bc2_sqrt, float tau) {
+                                 const float *lr_ptr, float max_norm, const float *step, float tau) {
+    const float bc1 = step[2], bc2_sqrt = step[3];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float total = sqrtf(sumsq[0]);
+    float ss = 0.f;
+#pragma unroll 8
+    for (int b = 0; b < kSumsqBlocks; ++b) ss += sumsq[b];
+    const float total = sqrtf(ss);
     const float coef = fminf(max_norm / (total + 1e-6f), 1.0f);
     const float gi = g[i] * coef;
     const float mi = m[i] + (gi - m[i]) * 0.1f;                             // exp_avg.lerp_(grad, 1-beta1)
@@ -451,7 +499,7 @@ __global__ void report_kernel(const float *scal, float *out) {
 // ---- workspace -------------------------------------------------------------------------------
 struct Ws {
     float *cgrad, *agrad;                       // flat gradient buckets (cgrad tail holds the 3 emotion means)
-    float *stats, *scal;                        // stats[6]; scal: [0] c_sumsq [1] a_sumsq [2..3] lrs [4] closs [5] aloss [6..14] norms
+    float *stats, *scal, *ssq, *step;                // stats[6]; scal: [2..3] lrs [4] closs [5] aloss [6..14] norms; ssq: [0:64] critic, [64:128] actor sum-of-squares partials
     float *x0, *xhat1, *h1, *xhat2, *h2, *h3, *rstd1, *rstd2, *q, *tq, *q2, *dq;
     float *xa, *a1, *a2, *a3, *z4, *aout, *aux, *atgt;
     float *g256a, *g256b, *g128, *g16, *ga128a, *ga128b, *ga64, *gz4, *drawe, *part;
@@ -463,7 +511,7 @@ static size_t carve(Ws *w, float *base, int B) {
     auto take = [&](float **p, size_t n) { if (w) *p = base + o; o += align16(n); };
     float *dummy;
     take(w ? &w->cgrad : &dummy, kCriticGradPad); take(w ? &w->agrad : &dummy, kActorGradPad);
-    take(w ? &w->stats : &dummy, 8); take(w ? &w->scal : &dummy, 32);
+    take(w ? &w->stats : &dummy, 8); take(w ? &w->scal : &dummy, 32); take(w ? &w->ssq : &dummy, 2 * kSumsqBlocks); take(w ? &w->step : &dummy, 4);
     const size_t b = (size_t)B;
     take(w ? &w->x0 : &dummy, b * 16); take(w ? &w->xhat1 : &dummy, b * 256); take(w ? &w->h1 : &dummy, b * 256);
     take(w ? &w->xhat2 : &dummy, b * 256); take(w ? &w->h2 : &dummy, b * 256); take(w ? &w->h3 : &dummy, b * 128);
@@ -500,8 +548,11 @@ static void gemm_wgrad(cudaStream_t st, const Ws &w, int Bt, int N, int K, const
         splitk_reduce_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(N * K, splits, w.part, (size_t)N * K, dW);
     }
 }
-static void colsum(cudaStream_t st, int rows, int cols, const float *X, const float *Y, int ld, float *out) {
-    colsum_kernel<<<(cols + 31) / 32, 256, 0, st>>>(rows, cols, X, Y, ld, out);
+// out[c] = sum_r X[r*ld + c] * (Y ? Y[r*ldy + c*ycs] : 1); uses w.part as the slice scratch (stream-ordered reuse)
+static void colsum(cudaStream_t st, const Ws &w, int rows, int cols, const float *X, int ld, const float *Y, int ldy, int ycs, float *out) {
+    dim3 grid((cols + 31) / 32, kColSplits);
+    colsum_part_kernel<<<grid, 256, 0, st>>>(rows, cols, X, ld, Y, ldy, ycs, w.part);
+    splitk_reduce_kernel<<<(cols + 255) / 256, 256, 0, st>>>(cols, kColSplits, w.part, (size_t)cols, out);
 }
 
 // Critic.forward on prepared x0; keeps the activations needed by the backward
@@ -515,21 +566,24 @@ static void critic_forward(cudaStream_t st, const Ws &w, int B, const float *P, 
 }
 // backward of critic_forward from dq; param grads into G (nullptr: input gradient only); dx0 -> w.g16
 static void critic_backward(cudaStream_t st, const Ws &w, int B, const float *P, const float *dq, float *G) {
-    if (G) head_wgrad_kernel<<<1, 256, 0, st>>>(B, dq, w.h3, G + CO::W10, G + CO::B10);
+    if (G) {   // dw10[c] = sum_r dq[r] h3[r][c], db10 = sum_r dq[r]
+        colsum(st, w, B, 128, w.h3, 128, dq, 1, 0, G + CO::W10);
+        colsum(st, w, B, 1, dq, 1, nullptr, 0, 0, G + CO::B10);
+    }
     critic_head_bwd_kernel<<<(B * 128 + 255) / 256, 256, 0, st>>>(B, dq, P + CO::W10, w.h3, w.g128);         // dz3
-    if (G) { gemm_wgrad(st, w, B, 128, 256, w.g128, 128, w.h2, 256, G + CO::W8); colsum(st, B, 128, w.g128, nullptr, 128, G + CO::B8); }
+    if (G) { gemm_wgrad(st, w, B, 128, 256, w.g128, 128, w.h2, 256, G + CO::W8); colsum(st, w, B, 128, w.g128, 128, nullptr, 0, 0, G + CO::B8); }
     gemm(st, B, 256, 128, w.g128, 128, 1, P + CO::W8, 256, 1, w.g256a, 256, nullptr, ACT_NONE);               // dh2 = dz3 W8
     ln_act_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, w.g256a, w.xhat2, w.rstd2, P + CO::G2, P + CO::BE2, ACT_RELU, w.g256b);
     if (G) {
-        colsum(st, B, 256, w.g256a, w.xhat2, 256, G + CO::G2); colsum(st, B, 256, w.g256a, nullptr, 256, G + CO::BE2);
-        gemm_wgrad(st, w, B, 256, 256, w.g256b, 256, w.h1, 256, G + CO::W4); colsum(st, B, 256, w.g256b, nullptr, 256, G + CO::B4);
+        colsum(st, w, B, 256, w.g256a, 256, w.xhat2, 256, 1, G + CO::G2); colsum(st, w, B, 256, w.g256a, 256, nullptr, 0, 0, G + CO::BE2);
+        gemm_wgrad(st, w, B, 256, 256, w.g256b, 256, w.h1, 256, G + CO::W4); colsum(st, w, B, 256, w.g256b, 256, nullptr, 0, 0, G + CO::B4);
     }
     gemm(st, B, 256, 256, w.g256b, 256, 1, P + CO::W4, 256, 1, w.g256a, 256, nullptr, ACT_NONE);              // dh1 = dz2 W4
     ln_act_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, w.g256a, w.xhat1, w.rstd1, P + CO::G1, P + CO::BE1, ACT_LEAKY, w.g256b);
     if (G) {
-        colsum(st, B, 256, w.g256a, w.xhat1, 256, G + CO::G1); colsum(st, B, 256, w.g256a, nullptr, 256, G + CO::BE1);
+        colsum(st, w, B, 256, w.g256a, 256, w.xhat1, 256, 1, G + CO::G1); colsum(st, w, B, 256, w.g256a, 256, nullptr, 0, 0, G + CO::BE1);
         // dW0[256][15] = dz1^T x0[:, :15]
-        gemm_wgrad(st, w, B, 256, 15, w.g256b, 256, w.x0, 16, G + CO::W0); colsum(st, B, 256, w.g256b, nullptr, 256, G + CO::B0);
+        gemm_wgrad(st, w, B, 256, 15, w.g256b, 256, w.x0, 16, G + CO::W0); colsum(st, w, B, 256, w.g256b, 256, nullptr, 0, 0, G + CO::B0);
     }
     gemm(st, B, 15, 256, w.g256b, 256, 1, P + CO::W0, 15, 1, w.g16, 16, nullptr, ACT_NONE);                   // dx0[:, :15]
 }
@@ -565,6 +619,16 @@ int erlfill_ddpg_grad_buckets(void *d_workspace, int batch, float **critic_grad,
     return ERLFILL_OK;
 }
 
+int erlfill_ddpg_set_step(void *d_workspace, int batch, int adam_step, double lr_decay, void *stream) {
+    if (!d_workspace || batch < 2 || adam_step < 1) return ERLFILL_ERR_ARG;
+    Ws w;
+    carve(&w, (float *)d_workspace, batch);
+    const double bc1d = 1.0 - pow(0.9, (double)adam_step), bc2d = sqrt(1.0 - pow(0.999, (double)adam_step));
+    set_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(w.step, lr_decay, (float)bc1d, (float)bc2d);
+    ERLFILL_CUDA_TRY(cudaGetLastError());
+    return ERLFILL_OK;
+}
+
 int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const float *d_batch,
                         const float *d_next_emotion, void *d_workspace, int phases, float *d_report, void *stream) {
     if (!n || !h || !d_batch || !d_next_emotion || !d_workspace) return ERLFILL_ERR_ARG;
@@ -572,11 +636,16 @@ int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h,
         !n->critic_v || !n->scale || !n->offset)
         return ERLFILL_ERR_ARG;
     const int B = h->batch;
-    if (B < 2 || h->adam_step < 1) return ERLFILL_ERR_ARG;
+    if (B < 2 || h->adam_step < 0) return ERLFILL_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     Ws w;
     carve(&w, (float *)d_workspace, B);
-    const double bc1d = 1.0 - pow(0.9, (double)h->adam_step), bc2d = sqrt(1.0 - pow(0.999, (double)h->adam_step));
+    // adam_step >= 1: upload this step's scalars first; adam_step == 0: the caller already did (erlfill_ddpg_set_step), which is
+    // how a CUDA graph captured once is replayed for every update
+    if (h->adam_step >= 1) {
+        const int rc = erlfill_ddpg_set_step(d_workspace, B, h->adam_step, h->lr_decay, stream);
+        if (rc != ERLFILL_OK) return rc;
+    }
 
     if (phases & ERLFILL_PHASE_CRITIC_GRAD) {
         emotion_stats_kernel<<<1, 1024, 0, st>>>(B, d_batch, w.stats, w.cgrad + CO::TOTAL);
@@ -592,10 +661,10 @@ int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h,
         critic_backward(st, w, B, n->critic, w.dq, w.cgrad);
     }
     if (phases & ERLFILL_PHASE_CRITIC_APPLY) {
-        lr_kernel<<<1, 1, 0, st>>>(w.cgrad + CO::TOTAL, h->lr_decay, h->critic_lr, h->actor_lr, w.scal + 2);
-        sumsq_kernel<<<1, 1024, 0, st>>>(CO::TOTAL, w.cgrad, w.scal + 0);
+        lr_kernel<<<1, 1, 0, st>>>(w.cgrad + CO::TOTAL, w.step, h->critic_lr, h->actor_lr, w.scal + 2);
+        sumsq_kernel<<<kSumsqBlocks, 256, 0, st>>>(CO::TOTAL, w.cgrad, w.ssq);
         adam_soft_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(CO::TOTAL, n->critic, nullptr, n->critic_m, n->critic_v, w.cgrad,
-                                                                  w.scal + 0, w.scal + 2, h->max_grad_norm, (float)bc1d, (float)bc2d, h->tau);
+                                                                  w.ssq, w.scal + 2, h->max_grad_norm, w.step, h->tau);
     }
     if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
         build_xa_kernel<<<(B * 8 + 255) / 256, 256, 0, st>>>(B, 0, d_batch, d_next_emotion, w.xa);
@@ -609,23 +678,24 @@ int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h,
         slice_action_grad_kernel<<<(B * 10 + 255) / 256, 256, 0, st>>>(B, w.g16, w.drawe);
         actor_head_bwd_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, w.drawe, w.aout, w.aux, w.xa, n->scale, w.z4, w.gz4, w.drawe);
         float *G = w.agrad;
-        ew_grad_kernel<<<1, 256, 0, st>>>(B, w.xa, w.drawe, G + AO::EW);
-        gemm_wgrad(st, w, B, 10, 64, w.gz4, 10, w.a3, 64, G + AO::W4); colsum(st, B, 10, w.gz4, nullptr, 10, G + AO::B4);
+        ew_grad_part_kernel<<<kColSplits, 256, 0, st>>>(B, w.xa, w.drawe, w.part);
+        splitk_reduce_kernel<<<1, 256, 0, st>>>(30, kColSplits, w.part, 30, G + AO::EW);
+        gemm_wgrad(st, w, B, 10, 64, w.gz4, 10, w.a3, 64, G + AO::W4); colsum(st, w, B, 10, w.gz4, 10, nullptr, 0, 0, G + AO::B4);
         gemm(st, B, 64, 10, w.gz4, 10, 1, n->actor + AO::W4, 64, 1, w.ga64, 64, nullptr, ACT_NONE);
         relu_bwd_kernel<<<(unsigned)(((size_t)B * 64 + 255) / 256), 256, 0, st>>>((size_t)B * 64, w.ga64, w.a3);
-        gemm_wgrad(st, w, B, 64, 128, w.ga64, 64, w.a2, 128, G + AO::W3); colsum(st, B, 64, w.ga64, nullptr, 64, G + AO::B3);
+        gemm_wgrad(st, w, B, 64, 128, w.ga64, 64, w.a2, 128, G + AO::W3); colsum(st, w, B, 64, w.ga64, 64, nullptr, 0, 0, G + AO::B3);
         gemm(st, B, 128, 64, w.ga64, 64, 1, n->actor + AO::W3, 128, 1, w.ga128a, 128, nullptr, ACT_NONE);
         relu_bwd_kernel<<<(unsigned)(((size_t)B * 128 + 255) / 256), 256, 0, st>>>((size_t)B * 128, w.ga128a, w.a2);
-        gemm_wgrad(st, w, B, 128, 128, w.ga128a, 128, w.a1, 128, G + AO::W2); colsum(st, B, 128, w.ga128a, nullptr, 128, G + AO::B2);
+        gemm_wgrad(st, w, B, 128, 128, w.ga128a, 128, w.a1, 128, G + AO::W2); colsum(st, w, B, 128, w.ga128a, 128, nullptr, 0, 0, G + AO::B2);
         gemm(st, B, 128, 128, w.ga128a, 128, 1, n->actor + AO::W2, 128, 1, w.ga128b, 128, nullptr, ACT_NONE);
         leaky_bwd_kernel<<<(unsigned)(((size_t)B * 128 + 255) / 256), 256, 0, st>>>((size_t)B * 128, w.ga128b, w.a1);
-        gemm_wgrad(st, w, B, 128, 5, w.ga128b, 128, w.xa, 8, G + AO::W1); colsum(st, B, 128, w.ga128b, nullptr, 128, G + AO::B1);
+        gemm_wgrad(st, w, B, 128, 5, w.ga128b, 128, w.xa, 8, G + AO::W1); colsum(st, w, B, 128, w.ga128b, 128, nullptr, 0, 0, G + AO::B1);
         actor_l2_grad_kernel<<<(AO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, w.scal + 6, G);
     }
     if (phases & ERLFILL_PHASE_ACTOR_APPLY) {
-        sumsq_kernel<<<1, 1024, 0, st>>>(AO::TOTAL, w.agrad, w.scal + 1);
+        sumsq_kernel<<<kSumsqBlocks, 256, 0, st>>>(AO::TOTAL, w.agrad, w.ssq + kSumsqBlocks);
         adam_soft_kernel<<<(AO::TOTAL + 255) / 256, 256, 0, st>>>(AO::TOTAL, n->actor, n->actor_target, n->actor_m, n->actor_v, w.agrad,
-                                                                  w.scal + 1, w.scal + 3, h->max_grad_norm, (float)bc1d, (float)bc2d, h->tau);
+                                                                  w.ssq + kSumsqBlocks, w.scal + 3, h->max_grad_norm, w.step, h->tau);
         // both soft updates happen after both optimiser steps (ddpg_agent.py:501-507)
         soft_update_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(CO::TOTAL, n->critic, n->critic_target, h->tau);
         if (d_report) report_kernel<<<1, 1, 0, st>>>(w.scal, d_report);   // [critic_loss, actor_loss, critic_lr, actor_lr]

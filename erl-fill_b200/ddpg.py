@@ -118,6 +118,9 @@ class DDPGLearner:
         self.report = torch.zeros(4, dtype=torch.float32, device=d)
         self._ws, self._ws_batch = None, 0
         self.batch_size = batch_size
+        self.use_graph = True
+        self._graphs = {}
+        self._warm = set()
 
     def _workspace(self, batch):
         if self._ws is None or self._ws_batch != batch:
@@ -145,27 +148,52 @@ class DDPGLearner:
                               L.ptr(v["hidden.7.weight"]), L.ptr(v["hidden.7.bias"]), L.ptr(v["emotion_weights"]),
                               L.ptr(self.scale), L.ptr(self.offset))
 
-    def update(self, batch, next_emotion, train_step, phases=L.PHASE_ALL, allreduce=None):
+    def update(self, batch, next_emotion, train_step, phases=L.PHASE_ALL, allreduce=None, graph=None):
         """One learn() on a gathered batch [B,20].  allreduce(tensor): optional in-place averaging callback
-        applied to the critic bucket and then the actor bucket (data-parallel)."""
+        applied to the critic bucket and then the actor bucket (data-parallel).
+
+        graph: replay the whole update (about 100 small launches, host-launch bound otherwise) as ONE captured CUDA
+        graph.  Default: on for the single-process full update, off with an all-reduce callback or partial phases.
+        The graph is keyed on the (batch, next_emotion) buffers; per-step scalars live in the workspace
+        (erlfill_ddpg_set_step), so the same graph serves every step."""
         B = batch.shape[0]
         ws = self._workspace(B)
         if phases & L.PHASE_CRITIC_GRAD:
             self.adam_step += 1
+        if graph is None:
+            graph = self.use_graph and allreduce is None and phases == L.PHASE_ALL
         nets = L.DDPGNets(L.ptr(self.actor.flat), L.ptr(self.actor_target.flat), L.ptr(self.critic.flat),
                           L.ptr(self.critic_target.flat), L.ptr(self.actor_m), L.ptr(self.actor_v), L.ptr(self.critic_m),
                           L.ptr(self.critic_v), L.ptr(self.scale), L.ptr(self.offset))
-        hyper = L.DDPGHyper(B, self.adam_step, self.gamma, self.tau, 5.0, 0.0, self.critic_lr, self.actor_lr,
-                            self.lr_decay_rate ** train_step)
+        decay = self.lr_decay_rate ** train_step
 
-        def run(ph):
+        def run(ph, adam_step):
+            hyper = L.DDPGHyper(B, adam_step, self.gamma, self.tau, 5.0, 0.0, self.critic_lr, self.actor_lr, decay)
             with torch.cuda.device(self.device):
                 L.check(L.lib().erlfill_ddpg_update(C.byref(nets), C.byref(hyper), L.ptr(batch), L.ptr(next_emotion), L.ptr(ws),
                                                     C.c_int(ph), L.ptr(self.report), L.stream_ptr()), "erlfill_ddpg_update")
-        if allreduce is None:
-            run(phases)
+
+        key = (B, batch.data_ptr(), next_emotion.data_ptr())
+        if graph and key not in self._graphs and key not in self._warm:
+            self._warm.add(key)          # first update on these buffers runs eagerly (module loading outside a capture)
+            graph = False
+        if graph:
+            with torch.cuda.device(self.device):
+                L.check(L.lib().erlfill_ddpg_set_step(L.ptr(ws), C.c_int(B), C.c_int(self.adam_step), C.c_double(decay),
+                                                      L.stream_ptr()), "erlfill_ddpg_set_step")
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) >= 4:
+                    self._graphs.clear()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    run(L.PHASE_ALL, 0)
+                self._graphs[key] = g
+            g.replay()
+        elif allreduce is None:
+            run(phases, self.adam_step)
         else:
             cb, ab = self.grad_buckets(B)
-            run(L.PHASE_CRITIC_GRAD); allreduce(cb); run(L.PHASE_CRITIC_APPLY)
-            run(L.PHASE_ACTOR_GRAD); allreduce(ab); run(L.PHASE_ACTOR_APPLY)
+            run(L.PHASE_CRITIC_GRAD, self.adam_step); allreduce(cb); run(L.PHASE_CRITIC_APPLY, 0)
+            run(L.PHASE_ACTOR_GRAD, 0); allreduce(ab); run(L.PHASE_ACTOR_APPLY, 0)
         return self.report

@@ -269,7 +269,7 @@ typedef struct {
 
 typedef struct {
     int32_t batch;
-    int32_t adam_step;        /* 1-based optimiser step of this update */
+    int32_t adam_step;        /* 1-based optimiser step of this update; 0 = scalars already uploaded by erlfill_ddpg_set_step */
     float gamma, tau, max_grad_norm, _pad;
     double critic_lr, actor_lr;   /* base rates (1e-3, 1e-4) */
     double lr_decay;              /* lr_decay_rate ** train_step (ddpg_agent.py:455) */
@@ -285,6 +285,10 @@ size_t erlfill_ddpg_workspace_bytes(int batch);
  * ACTOR_APPLY; the critic bucket carries the 3 batch emotion means that set the learning rates in its tail). */
 int erlfill_ddpg_grad_buckets(void *d_workspace, int batch, float **critic_grad, int *critic_len,
                               float **actor_grad, int *actor_len);
+/* Uploads the per-update scalars (Adam bias corrections of optimiser step `adam_step` >= 1, lr_decay) into the workspace.
+ * erlfill_ddpg_update does this itself when hyper->adam_step >= 1; call it separately and pass hyper->adam_step = 0 to
+ * replay one captured CUDA graph of the update for every step (the graph then contains no per-step constants). */
+int erlfill_ddpg_set_step(void *d_workspace, int batch, int adam_step, double lr_decay, void *stream);
 /* U1-U5 — DDPGAgent.learn (ddpg_agent.py:422-512), dropout off.  d_batch [B][ERLFILL_REC] gathered records,
  * d_next_emotion [3] the agent's fresh emotion (:466).  d_report (optional) [4] = critic_loss, actor_loss,
  * critic_lr, actor_lr. */
