@@ -17,4 +17,10 @@ def __getattr__(name):
     if name == "VecERDDPG":
         from . import agents
         return agents.VecERDDPG
+    if name in ("VecTD3", "VecSAC"):
+        from . import td3sac
+        return getattr(td3sac, name)
+    if name in ("init", "td3sac", "nets", "ddpg", "agents", "envs"):
+        import importlib
+        return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -80,6 +80,29 @@ class DDPGHyper(C.Structure):
                 ("actor_lr", C.c_double), ("lr_decay", C.c_double)]
 
 
+class TD3Nets(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("actor", "actor_target", "critic", "critic_target", "actor_m", "actor_v",
+                                           "critic_m", "critic_v")]
+
+
+class TD3Hyper(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("critic_step", C.c_int32), ("actor_step", C.c_int32), ("update_actor", C.c_int32),
+                ("gamma", C.c_float), ("tau", C.c_float), ("policy_noise", C.c_float), ("noise_clip", C.c_float),
+                ("critic_lr", C.c_double), ("actor_lr", C.c_double), ("seed", C.c_uint64), ("update_idx", C.c_uint32),
+                ("_pad", C.c_uint32)]
+
+
+class SACNets(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("policy", "q", "q_target", "policy_m", "policy_v", "q_m", "q_v")]
+
+
+class SACHyper(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("adam_step", C.c_int32), ("gamma", C.c_float), ("tau", C.c_float),
+                ("alpha", C.c_float), ("_pad", C.c_float), ("lr", C.c_double), ("seed", C.c_uint64),
+                ("update_idx", C.c_uint32), ("_pad2", C.c_uint32)]
+
+
+TD3_ACTOR_PARAMS, TD3_CRITIC_PARAMS, SAC_POLICY_PARAMS, SAC_Q_PARAMS = 69130, 138754, 71700, 138754
 PHASE_CRITIC_GRAD, PHASE_CRITIC_APPLY, PHASE_ACTOR_GRAD, PHASE_ACTOR_APPLY, PHASE_ALL = 1, 2, 4, 8, 15
 ACTOR_PARAMS, CRITIC_PARAMS = 26216, 103937
 
@@ -94,6 +117,8 @@ EXPORTS = [
     "erlfill_emotion_tc_image_bytes", "erlfill_emotion_tc_pack", "erlfill_emotion_forward_tc",
     "erlfill_replay_insert", "erlfill_replay_sample", "erlfill_replay_gather",
     "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_set_step", "erlfill_ddpg_update",
+    "erlfill_t1_workspace_bytes", "erlfill_t1_act_workspace_bytes", "erlfill_t1_grad_buckets", "erlfill_td3_act",
+    "erlfill_td3_update", "erlfill_sac_act", "erlfill_sac_update",
 ]
 
 _lib = None
@@ -110,6 +135,8 @@ def lib():
         L.erlfill_last_cuda_error_string.restype = C.c_char_p
         L.erlfill_ddpg_workspace_bytes.restype = C.c_size_t
         L.erlfill_emotion_tc_image_bytes.restype = C.c_size_t
+        L.erlfill_t1_workspace_bytes.restype = C.c_size_t
+        L.erlfill_t1_act_workspace_bytes.restype = C.c_size_t
         for name in EXPORTS:
             getattr(L, name)
         _lib = L

@@ -19,8 +19,10 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "mlp.cuh"
 
 namespace erlfill {
+using namespace mlp;
 
 // ---- flat layouts (parameters() order) -------------------------------------------------------
 namespace AO { constexpr int EW = 0, W1 = 30, B1 = 670, W2 = 798, B2 = 17182, W3 = 17310, B3 = 25502, W4 = 25566, B4 = 26206, TOTAL = 26216; }
@@ -30,157 +32,6 @@ __constant__ int c_actor_seg[kActorTensors + 1] = {0, 30, 670, 798, 17182, 17310
 
 constexpr int kCriticGradPad = 103968;     // critic grads + 3 emotion means + padding (16 B multiple)
 constexpr int kActorGradPad = 26240;
-
-// ---- generic strided GEMM on the tensor cores: C[M,N] = act(A(M,K) * B(K,N) + bias[N]) ------------
-// A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].  gridDim.z > 1: split-K partials to C + z*split_stride.
-// mma.sync.m16n8k8 TF32 with fp32 accumulation, error-compensated (3xTF32: a = hi + lo, a*b ~ lo*hi + hi*lo + hi*hi), so
-// the result keeps fp32-level accuracy (the parity bar of the update is 1e-4 against torch fp32) while the
-// multiply-accumulates run on the tensor pipe.  These GEMMs are M = batch (128..4096) by N, K <= 256: the register-
-// fragment MMA fits them; a tcgen05/TMEM tile would be mostly padding.
-constexpr int BM = 64, BN = 64, BK = 16, LDS_T = 72;          // 72 % 32 == 8: conflict-free fragment loads
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
-
-__device__ __forceinline__ void split_tf32(float v, uint32_t &hi, uint32_t &lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
-    const float r = v - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
-__global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float *__restrict__ A, int sam, int sak,
-                                                   const float *__restrict__ B, int sbk, int sbn, float *__restrict__ C,
-                                                   int ldc, const float *__restrict__ bias, int act, int k_per_split,
-                                                   size_t split_stride) {
-    __shared__ __align__(16) float As[BK][LDS_T];
-    __shared__ __align__(16) float Bs[BK][LDS_T];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;      // 2 x 4 warps, each a 32 x 16 tile = 2 (m16) x 2 (n8) MMA tiles
-    const int g = lane >> 2, t = lane & 3;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
-    float acc[2][2][4] = {};
-    // per-thread tile coordinates (the fastest-varying index follows the unit-stride dimension for coalescing)
-    int am[4], ak[4], bn[4], bk[4];
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int e = tid + it * 256;
-        if (sak == 1) { ak[it] = e & 15; am[it] = e >> 4; } else { am[it] = e & 63; ak[it] = e >> 6; }
-        if (sbn == 1) { bn[it] = e & 63; bk[it] = e >> 6; } else { bk[it] = e & 15; bn[it] = e >> 4; }
-    }
-    float ra[4], rb[4];
-    auto fetch = [&](int k0) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int gm = m0 + am[it], gk = k0 + ak[it];
-            ra[it] = (gm < M && gk < kend) ? A[(size_t)gm * sam + (size_t)gk * sak] : 0.f;
-            const int gn = n0 + bn[it], gkb = k0 + bk[it];
-            rb[it] = (gn < N && gkb < kend) ? B[(size_t)gkb * sbk + (size_t)gn * sbn] : 0.f;
-        }
-    };
-    fetch(kbeg);
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) { As[ak[it]][am[it]] = ra[it]; Bs[bk[it]][bn[it]] = rb[it]; }
-        __syncthreads();
-        if (k0 + BK < kend) fetch(k0 + BK);           // next tile's global loads fly under this tile's MMAs
-#pragma unroll
-        for (int ks = 0; ks < BK; ks += 8) {
-            uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                split_tf32(As[ks + t][wm + i * 16 + g], ah[i][0], al[i][0]);
-                split_tf32(As[ks + t][wm + i * 16 + g + 8], ah[i][1], al[i][1]);
-                split_tf32(As[ks + t + 4][wm + i * 16 + g], ah[i][2], al[i][2]);
-                split_tf32(As[ks + t + 4][wm + i * 16 + g + 8], ah[i][3], al[i][3]);
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                split_tf32(Bs[ks + t][wn + j * 8 + g], bh[j][0], bl[j][0]);
-                split_tf32(Bs[ks + t + 4][wn + j * 8 + g], bh[j][1], bl[j][1]);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    mma_tf32(acc[i][j], al[i], bh[j]);
-                    mma_tf32(acc[i][j], ah[i], bl[j]);
-                    mma_tf32(acc[i][j], ah[i], bh[j]);
-                }
-        }
-        __syncthreads();
-    }
-    float *Cz = C + (size_t)blockIdx.z * split_stride;
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int gm = m0 + wm + i * 16 + g + (e >> 1) * 8, gn = n0 + wn + j * 8 + 2 * t + (e & 1);
-                if (gm >= M || gn >= N) continue;
-                float v = acc[i][j][e];
-                if (bias) v += bias[gn];
-                if (act == ACT_RELU) v = fmaxf(v, 0.f);
-                else if (act == ACT_LEAKY) v = v > 0.f ? v : 0.1f * v;
-                Cz[(size_t)gm * ldc + gn] = v;
-            }
-}
-
-// sum split-K partials: out[i] = sum_z part[z*stride + i]
-__global__ void splitk_reduce_kernel(int n, int splits, const float *part, size_t stride, float *out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(size_t)z * stride + i];
-    out[i] = s;
-}
-
-// column sums, two deterministic stages: part[s][c] = sum over the rows of slice s of X[r*ld + c] * y(r, c), where
-// y = 1 (Y == nullptr) or Y[r*ldy + c*ycs] (ycs = 0: one factor per row); then splitk_reduce_kernel adds the slices in
-// index order.  grid = (ceil(cols/32), kColSplits): a block is 32 columns x 8 row lanes over rows/kColSplits rows.
-constexpr int kColSplits = 32;
-__global__ void __launch_bounds__(256) colsum_part_kernel(int rows, int cols, const float *X, int ld, const float *Y, int ldy, int ycs,
-                                                          float *part) {
-    __shared__ float red[8][33];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
-    const int per = (rows + kColSplits - 1) / kColSplits, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
-    float s = 0.f;
-    if (c < cols)
-        for (int r = r0 + rl; r < r1; r += 8) {
-            const float x = X[(size_t)r * ld + c];
-            s = Y ? fmaf(x, Y[(size_t)r * ldy + (size_t)c * ycs], s) : s + x;
-        }
-    red[rl][threadIdx.x & 31] = s;
-    __syncthreads();
-    if (rl == 0 && c < cols) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
-        part[(size_t)blockIdx.y * cols + c] = t;
-    }
-}
-
-// ---- block-wide deterministic reductions ------------------------------------------------------
-__device__ __forceinline__ float block_sum(float v, float *scratch /*[32]*/) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) scratch[w] = v;
-    __syncthreads();
-    float t = (threadIdx.x < (blockDim.x >> 5)) ? scratch[threadIdx.x] : 0.f;
-    if (w == 0) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (l == 0) scratch[0] = t;
-    }
-    __syncthreads();
-    return scratch[0];
-}
 
 // stats[0:3] mean, stats[3:6] unbiased std of the emotion columns of the batch (cols 16..18); also the
 // three means into mean_out (tail of the critic gradient bucket, so a DP all-reduce averages them too).
@@ -279,10 +130,6 @@ __global__ void __launch_bounds__(256) ln_act_bwd_kernel(int B, float *dh, const
 }
 
 // g *= (h > 0) for ReLU layers without LayerNorm
-__global__ void relu_bwd_kernel(size_t n, float *g, const float *h) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) g[i] = h[i] > 0.f ? g[i] : 0.f;
-}
 __global__ void leaky_bwd_kernel(size_t n, float *g, const float *h) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) g[i] = h[i] > 0.f ? g[i] : 0.1f * g[i];
@@ -433,17 +280,6 @@ __global__ void actor_l2_grad_kernel(const float *actor, const float *tensor_nor
 }
 
 // ---- optimiser -------------------------------------------------------------------------------
-// sum of squares of a flat buffer: kSumsqBlocks per-block partials (fixed order inside a block); the consumer adds them in index order
-constexpr int kSumsqBlocks = 64;
-__global__ void __launch_bounds__(256) sumsq_kernel(int n, const float *g, float *out /*[kSumsqBlocks]*/) {
-    __shared__ float scratch[32];
-    const int per = (n + kSumsqBlocks - 1) / kSumsqBlocks, i0 = blockIdx.x * per, i1 = min(n, i0 + per);
-    float s = 0.f;
-    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) s = fmaf(g[i], g[i], s);
-    const float t = block_sum(s, scratch);
-    if (threadIdx.x == 0) out[blockIdx.x] = t;
-}
-// learning rates from the (all-reduced) emotion means: ddpg_agent.py:447-457
 // per-update scalars in device memory so that a captured CUDA graph of the update can be replayed for every step:
 // step[0..1] = (double) lr_decay_rate ** train_step, step[2] = 1 - 0.9^t, step[3] = sqrt(1 - 0.999^t)
 __global__ void set_step_kernel(float *step, double decay, float bc1, float bc2_sqrt) {
@@ -479,10 +315,6 @@ __global__ void adam_soft_kernel(int n, float *p, float *pt, float *m, float *v,
     if (pt) pt[i] = tau * pi + (1.0f - tau) * pt[i];
 }
 
-__global__ void fill_kernel(int n, float v, float *p) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
 // d(out)[r][c] = dx0[r][2 + c]
 __global__ void slice_action_grad_kernel(int B, const float *g16, float *d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -530,30 +362,14 @@ static size_t carve(Ws *w, float *base, int B) {
 }
 
 // ---- launch helpers ---------------------------------------------------------------------------
-static void gemm(cudaStream_t st, int M, int N, int K, const float *A, int sam, int sak, const float *B, int sbk, int sbn,
-                 float *C, int ldc, const float *bias, int act) {
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
-    gemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, ldc, bias, act, K, 0);
-}
-// dW[N,K] = dZ^T[N,Bt] * X[Bt,K], reduction over the batch rows with split-K
+// update.cu's launch helpers bind the header's (mlp.cuh) to this workspace's split scratch
 static void gemm_wgrad(cudaStream_t st, const Ws &w, int Bt, int N, int K, const float *dZ, int ldz, const float *X, int ldx, float *dW) {
-    int splits = Bt >= 2048 ? 16 : (Bt >= 512 ? 8 : (Bt >= 128 ? 4 : 1));
-    const int kps = ((Bt + splits - 1) / splits + BK - 1) / BK * BK;
-    splits = (Bt + kps - 1) / kps;
-    dim3 grid((K + BN - 1) / BN, (N + BM - 1) / BM, splits);
-    if (splits == 1) {
-        gemm_kernel<<<grid, 256, 0, st>>>(N, K, Bt, dZ, 1, ldz, X, ldx, 1, dW, K, nullptr, ACT_NONE, kps, 0);
-    } else {
-        gemm_kernel<<<grid, 256, 0, st>>>(N, K, Bt, dZ, 1, ldz, X, ldx, 1, w.part, K, nullptr, ACT_NONE, kps, (size_t)N * K);
-        splitk_reduce_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(N * K, splits, w.part, (size_t)N * K, dW);
-    }
+    mlp::gemm_wgrad(st, w.part, Bt, N, K, dZ, ldz, X, ldx, dW);
 }
-// out[c] = sum_r X[r*ld + c] * (Y ? Y[r*ldy + c*ycs] : 1); uses w.part as the slice scratch (stream-ordered reuse)
 static void colsum(cudaStream_t st, const Ws &w, int rows, int cols, const float *X, int ld, const float *Y, int ldy, int ycs, float *out) {
-    dim3 grid((cols + 31) / 32, kColSplits);
-    colsum_part_kernel<<<grid, 256, 0, st>>>(rows, cols, X, ld, Y, ldy, ycs, w.part);
-    splitk_reduce_kernel<<<(cols + 255) / 256, 256, 0, st>>>(cols, kColSplits, w.part, (size_t)cols, out);
+    mlp::colsum(st, w.part, rows, cols, X, ld, Y, ldy, ycs, out);
 }
+using mlp::gemm;
 
 // Critic.forward on prepared x0; keeps the activations needed by the backward
 static void critic_forward(cudaStream_t st, const Ws &w, int B, const float *P, float *q_out) {

@@ -295,6 +295,69 @@ int erlfill_ddpg_set_step(void *d_workspace, int batch, int adam_step, double lr
 int erlfill_ddpg_update(const erlfill_ddpg_nets *nets, const erlfill_ddpg_hyper *hyper, const float *d_batch,
                         const float *d_next_emotion, void *d_workspace, int phases, float *d_report, void *stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* TD3 and SAC (BASELINE.json configs[4])                         */
+/* ------------------------------------------------------------------------------------------ */
+/* Flat fp32 parameter buffers in the reference's parameters() order; every MLP is  W0[256][in] b0 | W1[256][256] b1 | W2[out][256] b2.
+ *   TD3 actor  (69,130): TD3Actor.net.{0,2,4}            2-256-256-10               (td3_agent.py:51-85)
+ *   TD3 critic (138,754): TD3Critic.q1.{0,2,4} | q2.{0,2,4}   12-256-256-1 each     (td3_agent.py:88-133)
+ *   SAC policy (71,700): GaussianPolicy.net.{0,2} | mean | log_std                  (sac_agent.py:14-84)
+ *   SAC q      (138,754): q1.q.{0,2,4} | q2.q.{0,2,4}                               (sac_agent.py:87-112) */
+#define ERLFILL_TD3_ACTOR_PARAMS 69130
+#define ERLFILL_TD3_CRITIC_PARAMS 138754
+#define ERLFILL_SAC_POLICY_PARAMS 71700
+#define ERLFILL_SAC_Q_PARAMS 138754
+typedef struct {
+    float *actor, *actor_target, *critic, *critic_target;
+    float *actor_m, *actor_v, *critic_m, *critic_v;
+} erlfill_td3_nets;
+typedef struct {
+    int32_t batch;
+    int32_t critic_step, actor_step;   /* 1-based Adam steps of the two optimisers for this call */
+    int32_t update_actor;              /* total_it % policy_delay == 0 (td3_agent.py:287) */
+    float gamma, tau, policy_noise, noise_clip;
+    double critic_lr, actor_lr;
+    uint64_t seed;                     /* Philox key when d_noise == NULL */
+    uint32_t update_idx, _pad;
+} erlfill_td3_hyper;
+typedef struct {
+    float *policy, *q, *q_target;
+    float *policy_m, *policy_v, *q_m, *q_v;
+} erlfill_sac_nets;
+typedef struct {
+    int32_t batch, adam_step;
+    float gamma, tau, alpha, _pad;
+    double lr;
+    uint64_t seed;
+    uint32_t update_idx, _pad2;
+} erlfill_sac_hyper;
+
+/* bytes of the caller-provided device workspace of erlfill_td3_update / erlfill_sac_update, and of the *_act entries */
+size_t erlfill_t1_workspace_bytes(int batch);
+size_t erlfill_t1_act_workspace_bytes(void);
+/* flat gradient buckets inside the workspace for the data-parallel all-reduce between *_GRAD and *_APPLY
+ * (critic: 138,754 floats; actor: 69,130 (TD3) / 71,700 (SAC)) */
+int erlfill_t1_grad_buckets(void *d_workspace, int batch, float **critic_grad, float **actor_grad);
+
+/* TD3Agent.select_action (td3_agent.py:221-236): clip(actor(s) + noise_scale * N(0,1), -1, 1), denormalised with the bounds
+ * lo/hi (:198-219).  d_randn [n][10] injected draws or NULL (Philox).  d_norm_action (optional) receives the clipped
+ * normalised action, i.e. what remember() stores. */
+int erlfill_td3_act(const float *d_actor, int n, const float *d_state, const float *d_randn, float noise_scale, const float *d_lo,
+                    const float *d_hi, uint64_t seed, uint32_t row_id_base, uint32_t step_idx, float *d_action, float *d_norm_action,
+                    void *d_workspace, void *stream);
+/* TD3Agent.train_step (td3_agent.py:238-303) on gathered replay rows d_batch [B][ERLFILL_REC] (emotion columns unused).
+ * d_noise [B][10]: the N(0,1) draws of randn_like (:268) or NULL.  d_report (optional) [3] = critic_loss, mean q1, actor_loss. */
+int erlfill_td3_update(const erlfill_td3_nets *nets, const erlfill_td3_hyper *hyper, const float *d_batch, const float *d_noise,
+                       void *d_workspace, int phases, float *d_report, void *stream);
+/* SACAgent.act (sac_agent.py:186-205): tanh(mean + sigma * eps) (tanh(mean) when deterministic), denormalised (:163-184). */
+int erlfill_sac_act(const float *d_policy, int n, const float *d_state, const float *d_eps, int deterministic, const float *d_lo,
+                    const float *d_hi, uint64_t seed, uint32_t row_id_base, uint32_t step_idx, float *d_action, float *d_norm_action,
+                    void *d_workspace, void *stream);
+/* SACAgent.update (sac_agent.py:221-283).  d_eps_next / d_eps_new [B][10]: the two rsample() draws (:69) or NULL.
+ * d_report (optional) [3] = q1_loss, q2_loss, policy_loss. */
+int erlfill_sac_update(const erlfill_sac_nets *nets, const erlfill_sac_hyper *hyper, const float *d_batch, const float *d_eps_next,
+                       const float *d_eps_new, void *d_workspace, int phases, float *d_report, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

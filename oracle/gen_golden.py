@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (container only).
 
-Run from the repo root:   python oracle/gen_golden.py [sim] [env] [emotion] [nets] [learn]
+Run from the repo root:   python oracle/gen_golden.py [sim] [env] [emotion] [nets] [learn] [td3sac]
 
 The reference (/root/reference) is imported through oracle/ref_shim.py (pymodbus stub +
 frozen clock).  All randomness is CPython `random` seeded per case,
@@ -433,9 +433,120 @@ def gen_learn():
     print("learn: critic_loss", closs, "actor_loss", aloss, "lrs", lrs)
 
 
+# ----------------------------------------------------------------------------------------
+def gen_td3sac():
+    """T1 vectors: TD3Agent.train_step() x4 and SACAgent.update() x3 of the unmodified reference on an injected
+    replay buffer (B = 128).  The sampled indices are tapped from random.sample; the torch noise of each call
+    (randn_like, td3_agent.py:268; two rsample() draws, sac_agent.py:69) is re-drawn from the same seed."""
+    ref_shim.install()
+    import torch
+    import MutiConditionEnv as M
+    import td3_agent as T3
+    import sac_agent as SA
+    cfg = BOUNDS["variant_25kg"]
+    env = M.MultiConditionWeightEnv({**{k: cfg[k] for k in ("target_weight", "target_weight_err", "target_time")},
+                                     "bounds": dict(cfg["bounds"])})
+    g = np.random.RandomState(11)
+    B, n_buf = 128, 700
+    buf = dict(states=(g.rand(n_buf, 2) * 5).astype(np.float32), actions=(g.rand(n_buf, 10) * 2 - 1).astype(np.float32),
+               rewards=g.uniform(-3000, 6000, n_buf).astype(np.float32),
+               next_states=(g.rand(n_buf, 2) * 5).astype(np.float32), dones=(g.rand(n_buf) < 0.05))
+    out = {"buf_" + k: np.asarray(v) for k, v in buf.items()}
+
+    def fill(append):
+        for i in range(n_buf):
+            append((buf["states"][i], buf["actions"][i].astype(np.float64), float(buf["rewards"][i]),
+                    buf["next_states"][i], float(buf["dones"][i])))
+
+    def tap_sample(mod, store):
+        orig = mod.random.sample
+
+        def tapped(pop, k):
+            st = mod.random.getstate()
+            res = orig(pop, k)
+            mod.random.setstate(st)
+            store.append(np.array(orig(range(len(pop)), k)))
+            return res
+        return orig, tapped
+
+    # ---- TD3 ----
+    torch.manual_seed(3)
+    agent = T3.TD3Agent(env, device="cpu")
+    fill(lambda t: agent.memory.append(*t))
+    out.update(_sd(agent.actor, "td3.a0."))
+    out.update(_sd(agent.critic, "td3.c0."))
+    random.seed(77)
+    idx, noises, res = [], [], []
+    orig, tapped = tap_sample(T3, idx)
+    T3.random.sample = tapped
+    try:
+        for it in range(4):
+            torch.manual_seed(500 + it)
+            noises.append(torch.randn(B, 10).numpy())
+            torch.manual_seed(500 + it)
+            al, cl, qv = agent.train_step()
+            res.append((np.nan if al is None else al, cl, qv))
+        # weights after the last step only (fixture size); the per-step losses pin the steps in between
+        out.update(_sd(agent.actor, "td3.a4."))
+        out.update(_sd(agent.critic, "td3.c4."))
+        out.update(_sd(agent.actor_target, "td3.at4."))
+        out.update(_sd(agent.critic_target, "td3.ct4."))
+    finally:
+        T3.random.sample = orig
+    out["td3.idx"], out["td3.noise"], out["td3.res"] = np.array(idx), np.array(noises), np.array(res, np.float64)
+    # select_action (td3_agent.py:221-236) on a few states, injected numpy normals
+    st = (g.rand(6, 2) * 5).astype(np.float32)
+    acts, rn = [], []
+    for i in range(6):
+        np.random.seed(40 + i)
+        rn.append(np.random.randn(10))
+        np.random.seed(40 + i)
+        acts.append(agent.select_action(st[i], noise_scale=0.1))
+    out["td3.act_states"], out["td3.act_randn"], out["td3.act_out"] = st, np.array(rn), np.array(acts)
+
+    # ---- SAC ----
+    torch.manual_seed(4)
+    sac = SA.SACAgent(env, device="cpu")
+    fill(sac.memory.buffer.append)
+    out.update(_sd(sac.policy, "sac.p0."))
+    out.update(_sd(sac.q1, "sac.q1_0."))
+    out.update(_sd(sac.q2, "sac.q2_0."))
+    random.seed(78)
+    idx, e1, e2, res = [], [], [], []
+    orig, tapped = tap_sample(SA, idx)
+    SA.random.sample = tapped
+    try:
+        for it in range(3):
+            torch.manual_seed(600 + it)
+            e1.append(torch.randn(B, 10).numpy()); e2.append(torch.randn(B, 10).numpy())
+            torch.manual_seed(600 + it)
+            r = sac.update()
+            res.append((r["q1_loss"], r["q2_loss"], r["policy_loss"]))
+        out.update(_sd(sac.policy, "sac.p3."))
+        out.update(_sd(sac.q1, "sac.q1_3."))
+        out.update(_sd(sac.q2, "sac.q2_3."))
+        out.update(_sd(sac.q1_target, "sac.q1t_3."))
+        out.update(_sd(sac.q2_target, "sac.q2t_3."))
+    finally:
+        SA.random.sample = orig
+    out["sac.idx"], out["sac.eps_next"], out["sac.eps_new"] = np.array(idx), np.array(e1), np.array(e2)
+    out["sac.res"] = np.array(res, np.float64)
+    acts, eps = [], []
+    for i in range(6):
+        torch.manual_seed(50 + i)
+        eps.append(torch.randn(1, 10).numpy()[0])
+        torch.manual_seed(50 + i)
+        acts.append(sac.act(st[i], deterministic=False))
+    out["sac.act_states"], out["sac.act_eps"], out["sac.act_out"] = st, np.array(eps), np.array(acts)
+    out["sac.act_det"] = np.array([sac.act(st[i], deterministic=True) for i in range(6)])
+    out["meta"] = _meta("T1 TD3Agent.train_step x4 / SACAgent.update x3, B=128, injected buffer, tapped indices and noise")
+    np.savez_compressed(os.path.join(GOLD, "td3sac_golden.npz"), **out)
+    print("td3:", res if False else out["td3.res"].tolist(), "sac:", out["sac.res"].tolist())
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["sim", "env", "emotion"]
     os.chdir("/tmp")
     for w in which:
-        {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion, "nets": gen_nets, "learn": gen_learn}[w]()
+        {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion, "nets": gen_nets, "learn": gen_learn, "td3sac": gen_td3sac}[w]()

@@ -208,3 +208,113 @@ def ddpg_learn(actor, actor_t, critic, critic_t, opt, batch, next_emotion, train
     for k in CRITIC_PARAM_ORDER:
         critic_t[k] = tau * critic[k] + (1 - tau) * critic_t[k]
     return critic_loss.item(), actor_loss.item(), (c_lr, a_lr)
+
+
+# ---------------------------------------------------------------------------------------------
+# T1 — TD3 (DifferentModules/td3_agent.py:51-303) and fixed-alpha SAC (DifferentModules/sac_agent.py:14-283)
+# ---------------------------------------------------------------------------------------------
+TD3_ACTOR_ORDER = ["net.0.weight", "net.0.bias", "net.2.weight", "net.2.bias", "net.4.weight", "net.4.bias"]
+TD3_CRITIC_ORDER = [f"{q}.{i}.{w}" for q in ("q1", "q2") for i in (0, 2, 4) for w in ("weight", "bias")]
+SAC_POLICY_ORDER = ["net.0.weight", "net.0.bias", "net.2.weight", "net.2.bias", "mean.weight", "mean.bias",
+                    "log_std.weight", "log_std.bias"]
+SAC_Q_ORDER = ["q.0.weight", "q.0.bias", "q.2.weight", "q.2.bias", "q.4.weight", "q.4.bias"]
+
+
+def _mlp3(w, prefix, x, idx=(0, 2, 4)):
+    h = F.relu(F.linear(x, w[f"{prefix}{idx[0]}.weight"], w[f"{prefix}{idx[0]}.bias"]))
+    h = F.relu(F.linear(h, w[f"{prefix}{idx[1]}.weight"], w[f"{prefix}{idx[1]}.bias"]))
+    return F.linear(h, w[f"{prefix}{idx[2]}.weight"], w[f"{prefix}{idx[2]}.bias"])
+
+
+def td3_actor_forward(w, s):
+    """TD3Actor.forward (td3_agent.py:51-85): tanh(MLP 2-256-256-10)."""
+    return torch.tanh(_mlp3(w, "net.", s))
+
+
+def td3_critic_forward(w, s, a):
+    """TD3Critic.forward (td3_agent.py:88-133): twin Q on cat([s, a])."""
+    sa = torch.cat([s, a], dim=1)
+    return _mlp3(w, "q1.", sa), _mlp3(w, "q2.", sa)
+
+
+def td3_train_step(actor, actor_t, critic, critic_t, opt, batch, noise, total_it, gamma=0.99, tau=0.005,
+                   policy_noise=0.2, noise_clip=0.5, policy_delay=2, actor_lr=1e-4, critic_lr=1e-3):
+    """One TD3Agent.train_step() (td3_agent.py:238-303) on explicit tensors.  noise: the N(0,1) draws of
+    torch.randn_like(actions) (:268).  opt: {"am","av","cm","cv","cstep","astep"}.  total_it: value AFTER the
+    increment of :254.  Returns (actor_loss | None, critic_loss, q1.mean())."""
+    s, a, r = batch["states"], batch["actions"], batch["rewards"].unsqueeze(1)
+    s2, d = batch["next_states"], batch["dones"].unsqueeze(1)
+    with torch.no_grad():
+        n = (noise * policy_noise).clamp(-noise_clip, noise_clip)
+        a2 = (td3_actor_forward(actor_t, s2) + n).clamp(-1, 1)
+        q1t, q2t = td3_critic_forward(critic_t, s2, a2)
+        y = r + gamma * (1 - d) * torch.min(q1t, q2t)
+    cp = [critic[k].clone().requires_grad_(True) for k in TD3_CRITIC_ORDER]
+    cw = dict(zip(TD3_CRITIC_ORDER, cp))
+    q1, q2 = td3_critic_forward(cw, s, a)
+    critic_loss = F.mse_loss(q1, y) + F.mse_loss(q2, y)
+    cg = torch.autograd.grad(critic_loss, cp)
+    opt["cstep"] += 1
+    for k, p in zip(TD3_CRITIC_ORDER, adam_step([p.detach() for p in cp], list(cg), opt["cm"], opt["cv"], opt["cstep"], critic_lr)):
+        critic[k] = p
+    actor_loss = None
+    if total_it % policy_delay == 0:
+        ap = [actor[k].clone().requires_grad_(True) for k in TD3_ACTOR_ORDER]
+        aw = dict(zip(TD3_ACTOR_ORDER, ap))
+        al = -_mlp3(critic, "q1.", torch.cat([s, td3_actor_forward(aw, s)], dim=1)).mean()
+        ag = torch.autograd.grad(al, ap)
+        opt["astep"] += 1
+        for k, p in zip(TD3_ACTOR_ORDER, adam_step([p.detach() for p in ap], list(ag), opt["am"], opt["av"], opt["astep"], actor_lr)):
+            actor[k] = p
+        for k in TD3_CRITIC_ORDER:
+            critic_t[k] = tau * critic[k] + (1 - tau) * critic_t[k]
+        for k in TD3_ACTOR_ORDER:
+            actor_t[k] = tau * actor[k] + (1 - tau) * actor_t[k]
+        actor_loss = al.item()
+    return actor_loss, critic_loss.item(), q1.mean().item()
+
+
+def sac_policy_sample(w, s, eps):
+    """GaussianPolicy.sample (sac_agent.py:45-84) with the N(0,1) draw of rsample() given explicitly."""
+    h = F.relu(F.linear(s, w["net.0.weight"], w["net.0.bias"]))
+    h = F.relu(F.linear(h, w["net.2.weight"], w["net.2.bias"]))
+    mean = F.linear(h, w["mean.weight"], w["mean.bias"])
+    std = F.linear(h, w["log_std.weight"], w["log_std.bias"]).clamp(-20, 2).exp()
+    z = mean + std * eps
+    action = torch.tanh(z)
+    log_prob = (-((z - mean) ** 2) / (2 * std ** 2) - std.log() - math.log(math.sqrt(2 * math.pi))
+                - torch.log(1 - action.pow(2) + 1e-7)).sum(dim=-1, keepdim=True)
+    return action, log_prob
+
+
+def sac_q_forward(w, s, a):
+    return _mlp3(w, "q.", torch.cat([s, a], dim=1))
+
+
+def sac_update(policy, q1, q2, q1_t, q2_t, opt, batch, eps_next, eps_new, gamma=0.99, tau=0.005, alpha=0.3, lr=3e-4):
+    """One SACAgent.update() (sac_agent.py:221-283).  opt: {"pm","pv","q1m","q1v","q2m","q2v","step"}.
+    Returns (q1_loss, q2_loss, policy_loss)."""
+    s, a, r = batch["states"], batch["actions"], batch["rewards"].unsqueeze(1)
+    s2, d = batch["next_states"], batch["dones"].unsqueeze(1)
+    with torch.no_grad():
+        a2, lp2 = sac_policy_sample(policy, s2, eps_next)
+        y = r + (1 - d) * gamma * (torch.min(sac_q_forward(q1_t, s2, a2), sac_q_forward(q2_t, s2, a2)) - alpha * lp2)
+    opt["step"] += 1
+    losses = []
+    for net, m, v in ((q1, opt["q1m"], opt["q1v"]), (q2, opt["q2m"], opt["q2v"])):
+        ps = [net[k].clone().requires_grad_(True) for k in SAC_Q_ORDER]
+        loss = F.mse_loss(sac_q_forward(dict(zip(SAC_Q_ORDER, ps)), s, a), y)
+        gs = torch.autograd.grad(loss, ps)
+        for k, p in zip(SAC_Q_ORDER, adam_step([p.detach() for p in ps], list(gs), m, v, opt["step"], lr)):
+            net[k] = p
+        losses.append(loss.item())
+    pp = [policy[k].clone().requires_grad_(True) for k in SAC_POLICY_ORDER]
+    an, lp = sac_policy_sample(dict(zip(SAC_POLICY_ORDER, pp)), s, eps_new)
+    pl = (alpha * lp - sac_q_forward(q1, s, an)).mean()
+    pg = torch.autograd.grad(pl, pp)
+    for k, p in zip(SAC_POLICY_ORDER, adam_step([p.detach() for p in pp], list(pg), opt["pm"], opt["pv"], opt["step"], lr)):
+        policy[k] = p
+    for k in SAC_Q_ORDER:
+        q1_t[k] = tau * q1[k] + (1 - tau) * q1_t[k]
+        q2_t[k] = tau * q2[k] + (1 - tau) * q2_t[k]
+    return losses[0], losses[1], pl.item()

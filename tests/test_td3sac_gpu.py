@@ -1,0 +1,149 @@
+"""GPU parity of TD3 / SAC (csrc/td3_sac.cu) through the C ABI: against the torch restatement (oracle/nets_ref.py) step by
+step with the reference's own sampled indices and torch noise, and against the reference agents' fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import nets_ref as R  # noqa: E402
+
+
+def _w(g, prefix):
+    return {k[len(prefix):]: torch.from_numpy(np.array(g[k])) for k in g.files if k.startswith(prefix)}
+
+
+def T(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _env(n=8):
+    import erlfill_b200 as E
+    conds = list(E.conditions.EXPERIMENT_3.values())[:1]
+    return E.VecFillEnv(conds, n, kind="multi", max_steps=100, seed=0)
+
+
+def _fill(agent, g):
+    agent.memory.insert(T(g["buf_states"]), T(g["buf_actions"]), T(g["buf_rewards"].astype(np.float32)), T(g["buf_next_states"]),
+                        T(g["buf_dones"].astype(np.uint8)), torch.zeros(len(g["buf_states"]), 3, device="cuda"))
+
+
+def _batch(g, idx):
+    return {"states": torch.from_numpy(g["buf_states"][idx]), "actions": torch.from_numpy(g["buf_actions"][idx]),
+            "rewards": torch.from_numpy(g["buf_rewards"][idx]).float(), "next_states": torch.from_numpy(g["buf_next_states"][idx]),
+            "dones": torch.from_numpy(g["buf_dones"][idx].astype(np.float32))}
+
+
+def _close(dev, ref, lr, name):
+    a, b = dev.cpu().numpy(), ref.numpy() if hasattr(ref, "numpy") else ref
+    d = np.abs(a - b)
+    # Adam turns a 1e-7-relative gradient difference into a visible fraction of one lr step where the gradient is ~1e-8
+    assert (d > 2e-6 + 2e-4 * np.abs(b)).mean() <= 1e-3 and d.max() <= 0.2 * lr * 4, (name, d.max(), (d > 2e-6 + 2e-4 * np.abs(b)).mean())
+
+
+def test_td3_update_matches_oracle_and_reference(golden_dir):
+    import erlfill_b200 as E
+    g = np.load(os.path.join(golden_dir, "td3sac_golden.npz"))
+    actor, critic = _w(g, "td3.a0."), _w(g, "td3.c0.")
+    agent = E.VecTD3(_env(), batch_size=128, memory_size=1000, state_dicts=(actor, critic))
+    _fill(agent, g)
+    actor_t, critic_t = {k: v.clone() for k, v in actor.items()}, {k: v.clone() for k, v in critic.items()}
+    z = lambda net, order: [torch.zeros_like(net[k]) for k in order]
+    opt = {"am": z(actor, R.TD3_ACTOR_ORDER), "av": z(actor, R.TD3_ACTOR_ORDER), "cm": z(critic, R.TD3_CRITIC_ORDER),
+           "cv": z(critic, R.TD3_CRITIC_ORDER), "cstep": 0, "astep": 0}
+    for it in range(4):
+        idx = g["td3.idx"][it]
+        rep, upd = agent.train_step(idx=T(idx.astype(np.int64)), noise=T(g["td3.noise"][it]))
+        rep = rep.cpu().numpy()
+        al, cl, qv = R.td3_train_step(actor, actor_t, critic, critic_t, opt, _batch(g, idx), torch.from_numpy(g["td3.noise"][it]), it + 1)
+        assert upd == (al is not None)
+        assert abs(rep[0] - cl) <= 2e-5 * abs(cl) and abs(rep[1] - qv) <= 1e-4 * max(1.0, abs(qv)), (rep, cl, qv)
+        if upd:
+            assert abs(rep[2] - al) <= 1e-4 * max(1.0, abs(al))
+        # the reference's own numbers
+        assert abs(rep[0] - g["td3.res"][it][1]) <= 5e-5 * abs(g["td3.res"][it][1])
+        for net, ref, lr in ((agent.actor, actor, 1e-4), (agent.actor_target, actor_t, 1e-4), (agent.critic, critic, 1e-3),
+                             (agent.critic_target, critic_t, 1e-3)):
+            for k, v in net.views.items():
+                _close(v, ref[k], lr, f"{it} {k}")
+    for net, pre, lr in ((agent.actor, "td3.a4.", 1e-4), (agent.critic, "td3.c4.", 1e-3), (agent.actor_target, "td3.at4.", 1e-4),
+                         (agent.critic_target, "td3.ct4.", 1e-3)):
+        for k, v in net.views.items():
+            _close(v, g[pre + k], lr, pre + k)
+
+
+def test_sac_update_matches_oracle_and_reference(golden_dir):
+    import erlfill_b200 as E
+    g = np.load(os.path.join(golden_dir, "td3sac_golden.npz"))
+    pol, q1, q2 = _w(g, "sac.p0."), _w(g, "sac.q1_0."), _w(g, "sac.q2_0.")
+    q_sd = {"q1." + k: v for k, v in q1.items()}
+    q_sd.update({"q2." + k: v for k, v in q2.items()})
+    agent = E.VecSAC(_env(), batch_size=128, memory_size=1000, state_dicts=(pol, q_sd))
+    _fill(agent, g)
+    q1t, q2t = {k: v.clone() for k, v in q1.items()}, {k: v.clone() for k, v in q2.items()}
+    z = lambda net, order: [torch.zeros_like(net[k]) for k in order]
+    opt = {"pm": z(pol, R.SAC_POLICY_ORDER), "pv": z(pol, R.SAC_POLICY_ORDER), "q1m": z(q1, R.SAC_Q_ORDER), "q1v": z(q1, R.SAC_Q_ORDER),
+           "q2m": z(q2, R.SAC_Q_ORDER), "q2v": z(q2, R.SAC_Q_ORDER), "step": 0}
+    for it in range(3):
+        idx = g["sac.idx"][it]
+        rep = agent.update(idx=T(idx.astype(np.int64)), eps_next=T(g["sac.eps_next"][it]), eps_new=T(g["sac.eps_new"][it])).cpu().numpy()
+        l1, l2, pl = R.sac_update(pol, q1, q2, q1t, q2t, opt, _batch(g, idx), torch.from_numpy(g["sac.eps_next"][it]),
+                                  torch.from_numpy(g["sac.eps_new"][it]))
+        assert abs(rep[0] - l1) <= 2e-5 * abs(l1) and abs(rep[1] - l2) <= 2e-5 * abs(l2) and abs(rep[2] - pl) <= 1e-4 * max(1.0, abs(pl)), (rep, l1, l2, pl)
+        assert abs(rep[0] - g["sac.res"][it][0]) <= 5e-5 * abs(g["sac.res"][it][0])
+        for k, v in agent.policy.views.items():
+            _close(v, pol[k], 3e-4, f"{it} policy {k}")
+        for k, v in agent.q.views.items():
+            _close(v, (q1 if k.startswith("q1.") else q2)[k[3:]], 3e-4, f"{it} {k}")
+        for k, v in agent.q_target.views.items():
+            _close(v, (q1t if k.startswith("q1.") else q2t)[k[3:]], 3e-4, f"{it} target {k}")
+    for k, v in agent.policy.views.items():
+        _close(v, g["sac.p3." + k], 3e-4, "ref policy " + k)
+
+
+def test_action_selection_matches_reference(golden_dir):
+    import erlfill_b200 as E
+    g = np.load(os.path.join(golden_dir, "td3sac_golden.npz"))
+    env = _env(6)
+    td3 = E.VecTD3(env, batch_size=128, memory_size=256, state_dicts=(_w(g, "td3.a4."), _w(g, "td3.c4.")))
+    a = td3.select_action(T(g["td3.act_states"]), noise_scale=0.1, randn=T(g["td3.act_randn"].astype(np.float32))).cpu().numpy()
+    rng = (td3.hi - td3.lo).cpu().numpy()
+    assert np.all(np.abs(a - g["td3.act_out"]) <= 2e-6 * rng[None, :] + 1e-5 * np.abs(g["td3.act_out"]))
+    q_sd = {"q1." + k: v for k, v in _w(g, "sac.q1_3.").items()}
+    q_sd.update({"q2." + k: v for k, v in _w(g, "sac.q2_3.").items()})
+    sac = E.VecSAC(env, batch_size=128, memory_size=256, state_dicts=(_w(g, "sac.p3."), q_sd))
+    a = sac.act(T(g["sac.act_states"]), eps=T(g["sac.act_eps"])).cpu().numpy()
+    assert np.all(np.abs(a - g["sac.act_out"]) <= 2e-5 * rng[None, :] + 1e-5 * np.abs(g["sac.act_out"]))
+    a = sac.act(T(g["sac.act_states"]), deterministic=True).cpu().numpy()
+    assert np.all(np.abs(a - g["sac.act_det"]) <= 2e-6 * rng[None, :] + 1e-5 * np.abs(g["sac.act_det"]))
+
+
+def test_td3_sac_batched_loops_run_and_are_deterministic():
+    """train_td3 / train_sac loop bodies (act -> step -> remember -> update) for 512 envs: finite, reproducible, and the
+    phase-split data-parallel path with an identity all-reduce equals the fused call."""
+    import erlfill_b200 as E
+    conds = list(E.conditions.EXPERIMENT_3.values())
+
+    def run(kind, split):
+        env = E.VecFillEnv(conds[:1], 512, kind="multi", max_steps=8, seed=3)
+        agent = (E.VecTD3 if kind == "td3" else E.VecSAC)(env, seed=3, batch_size=256, memory_size=4096)
+        env.reset()
+        ar = (lambda t: None) if split else None
+        for _ in range(6):
+            agent.rollout_step()
+            rep = agent.train_step(allreduce=ar)[0] if kind == "td3" else agent.update(allreduce=ar)
+        torch.cuda.synchronize()
+        net = agent.actor if kind == "td3" else agent.policy
+        return rep.clone(), net.flat.clone(), agent.memory.buf[:3072].clone()
+
+    for kind in ("td3", "sac"):
+        r1, p1, b1 = run(kind, False)
+        r2, p2, b2 = run(kind, False)
+        r3, p3, _ = run(kind, True)
+        assert torch.isfinite(r1).all() and torch.isfinite(p1).all()
+        assert torch.equal(p1, p2) and torch.equal(b1, b2) and torch.equal(r1, r2)
+        assert torch.equal(p1, p3) and torch.equal(r1, r3)
+        # stored actions are the normalised ones, inside [-1, 1]
+        assert b1[:, 2:12].abs().max().item() <= 1.0
