@@ -9,6 +9,7 @@ One JSON line on stdout (rank 0).  A "step" is one lock-step pass of the workloa
   sim      configs[1] of BASELINE.json: batched WeightEnv rollout, PID-effective constant action (default, 4096 envs/GPU)
   rollout  configs[2]: MultiConditionWeightEnv, EmotionModule transformer -> ER-DDPG actor + OU -> env step -> emotion update
   update   configs[3]: ER-DDPG update, minibatch 4096 from a 1M-transition replay (sample + gather + U1-U5)
+  td3|sac  configs[4]: full TD3 / SAC loop (act -> env step -> remember -> update of B=4096), 131,072 envs/GPU
   all      (default) the sim line, with the rollout and update results attached under "other_workloads"
 `value` is device-timed with inputs resident in HBM; `e2e` goes through the public Python API with pinned HOST
 buffers (H2D of the step's inputs, D2H of its results inside the timed region).
@@ -312,11 +313,8 @@ def wl_update(args, rank, world, device, timer):
         rows[:, 16:19] = torch.rand(m, 3, generator=g)
         agent.memory.buf[o:o + m].copy_(rows.to(device))
     agent.memory.size = agent.memory.inserted = C
-    allreduce = None
-    if world > 1:
-        def allreduce(t):
-            dist.all_reduce(t)
-            t.mul_(1.0 / world)
+    from erlfill_b200 import parallel
+    allreduce = parallel.GradSync(world) if world > 1 else None
 
     def step():
         agent.learn(allreduce=allreduce)
@@ -357,6 +355,73 @@ def wl_update(args, rank, world, device, timer):
     }
 
 
+def wl_loop(args, rank, world, device, timer):
+    """configs[4]: TD3 / SAC on MultiConditionWeightEnv, full lock-step loop: act -> env step -> remember -> one update of
+    B = 4096 from the rank's replay shard (data-parallel gradient all-reduce when world > 1)."""
+    import torch
+    import erlfill_b200 as E
+    from erlfill_b200 import parallel
+    K = E.conditions
+    n, B = args.n_env, args.batch
+    kind = args.workload
+    env = E.VecFillEnv(list(K.EXPERIMENT_3.values())[:1], n, kind="multi", max_steps=100, seed=0, device=device, env_id_base=rank * n,
+                       sim_mode=args.sim_mode)
+    agent = (E.VecTD3 if kind == "td3" else E.VecSAC)(env, seed=0, batch_size=B, memory_size=max(4 * n, 1 << 20), rank=rank)
+    sync = parallel.GradSync(world) if world > 1 else None
+    env.reset()
+
+    def step():
+        agent.rollout_step()
+        if kind == "td3":
+            agent.train_step(allreduce=sync)
+        else:
+            agent.update(allreduce=sync)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    env.tick_sum.zero_()
+    total_ms, wall = timer.run(step, args.steps)
+    ticks_all = timer.sumr(int(env.tick_sum.item()))
+    obs_host = env.obs.cpu().pin_memory()
+    res_host = [torch.empty(n, 2).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory(),
+                torch.empty(3).pin_memory()]
+
+    def e2e_step():
+        env.obs.copy_(obs_host, non_blocking=True)
+        ns, r, d = agent.rollout_step()
+        rep = agent.train_step(allreduce=sync)[0] if kind == "td3" else agent.update(allreduce=sync)
+        res_host[0].copy_(ns, non_blocking=True); res_host[1].copy_(r, non_blocking=True); res_host[2].copy_(d, non_blocking=True)
+        res_host[3].copy_(rep, non_blocking=True)
+        timer.stream.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timer.run_block(e2e_step, args.steps)
+    sim_ms = _kernel_ms(timer, lambda: env.step(agent.action))
+    peaks = _peaks()
+    units = n * world * args.steps
+    achieved = ENV_STEP_BYTES * n / (sim_ms * 1e-3) / 1e9
+    return {
+        "metric": "env_steps_per_sec", "value": units / (total_ms * 1e-3), "unit": "env-steps/s",
+        "dtype": "f64 simulator, f32 (3xTF32 tensor-core GEMM) networks", "ms_per_step": total_ms / args.steps, "wall_s_timed_region": wall,
+        "updates_per_sec": args.steps / (total_ms * 1e-3),
+        "config": {"workload": "configs[4]: %s on MultiConditionWeightEnv, %d envs/GPU, full loop: act -> env step -> remember -> "
+                               "one update of minibatch %d" % (kind.upper(), n, B), "n_env_per_gpu": n, "minibatch_per_gpu": B,
+                   "parallelism": "env-sharded x%d, data-parallel update (flat-bucket gradient all-reduce)" % world,
+                   "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+        "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / units,
+        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": obs_host.numel() * 4,
+                "d2h_bytes_per_step": n * 13 + 12},
+        "gpu_launches": 130 * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": None, "peak_source": peaks["source"], "kernel": "env_sim_warp_kernel + env_finish_kernel",
+                     "kernel_ms": sim_ms, "share_of_step": sim_ms / (total_ms / args.steps),
+                     "algorithmic_bytes_per_env_step": ENV_STEP_BYTES,
+                     "note": "the simulator dominates this loop and is instruction-issue bound, not HBM bound (DESIGN.md section 4.1)"},
+    }
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -374,7 +439,7 @@ def run_ours(args):
     timer = Timer(device, world)
     sampler = ClockSampler(local)
     sampler.start()
-    wl = {"sim": wl_sim, "rollout": wl_rollout, "update": wl_update}
+    wl = {"sim": wl_sim, "rollout": wl_rollout, "update": wl_update, "td3": wl_loop, "sac": wl_loop}
     head = "sim" if args.workload == "all" else args.workload
     if args.workload == "all":
         args.n_env = args.n_env or 4096
@@ -503,7 +568,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "sim", "rollout", "update"],
+    ap.add_argument("--workload", default="all", choices=["all", "sim", "rollout", "update", "td3", "sac"],
                     help="all = the sim headline line plus compact rollout and update results under other_workloads")
     ap.add_argument("--n-env", type=int, default=None)
     ap.add_argument("--actions", default="pid", choices=["pid", "random"])
@@ -515,7 +580,7 @@ def main():
                     help="EmotionTransformer kernel of the rollout: tcgen05 bf16 (default) or the exact fp32 SIMT twin")
     args = ap.parse_args()
     if args.n_env is None:
-        args.n_env = {"all": 4096, "sim": 4096, "rollout": 65536, "update": 256}[args.workload]
+        args.n_env = {"all": 4096, "sim": 4096, "rollout": 65536, "update": 256, "td3": 131072, "sac": 131072}[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -161,7 +161,7 @@ class DDPGLearner:
         if phases & L.PHASE_CRITIC_GRAD:
             self.adam_step += 1
         if graph is None:
-            graph = self.use_graph and allreduce is None and phases == L.PHASE_ALL
+            graph = self.use_graph and phases == L.PHASE_ALL and (allreduce is None or getattr(allreduce, "graph_safe", False))
         nets = L.DDPGNets(L.ptr(self.actor.flat), L.ptr(self.actor_target.flat), L.ptr(self.critic.flat),
                           L.ptr(self.critic_target.flat), L.ptr(self.actor_m), L.ptr(self.actor_v), L.ptr(self.critic_m),
                           L.ptr(self.critic_v), L.ptr(self.scale), L.ptr(self.offset))
@@ -173,7 +173,7 @@ class DDPGLearner:
                 L.check(L.lib().erlfill_ddpg_update(C.byref(nets), C.byref(hyper), L.ptr(batch), L.ptr(next_emotion), L.ptr(ws),
                                                     C.c_int(ph), L.ptr(self.report), L.stream_ptr()), "erlfill_ddpg_update")
 
-        key = (B, batch.data_ptr(), next_emotion.data_ptr())
+        key = (B, batch.data_ptr(), next_emotion.data_ptr(), id(allreduce))
         if graph and key not in self._graphs and key not in self._warm:
             self._warm.add(key)          # first update on these buffers runs eagerly (module loading outside a capture)
             graph = False
@@ -187,7 +187,12 @@ class DDPGLearner:
                     self._graphs.clear()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    run(L.PHASE_ALL, 0)
+                    if allreduce is None:
+                        run(L.PHASE_ALL, 0)
+                    else:       # data-parallel: the two bucket all-reduces are captured between the phases
+                        cb, ab = self.grad_buckets(B)
+                        run(L.PHASE_CRITIC_GRAD, 0); allreduce(cb); run(L.PHASE_CRITIC_APPLY, 0)
+                        run(L.PHASE_ACTOR_GRAD, 0); allreduce(ab); run(L.PHASE_ACTOR_APPLY, 0)
                 self._graphs[key] = g
             g.replay()
         elif allreduce is None:
