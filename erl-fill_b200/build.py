@@ -24,6 +24,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "--std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
           "-I", CSRC, "--expt-relaxed-constexpr"]
 PER_FILE = {"env_step.cu": ["-fmad=false"]}
+if os.environ.get("ERLFILL_TC_DEFS"):       # development: e.g. ERLFILL_TC_DEFS="-DERLFILL_TC_TILES=2" (defaults live in the source)
+    PER_FILE["emotion_tf_tc.cu"] = os.environ["ERLFILL_TC_DEFS"].split()
 
 
 def _nvcc():

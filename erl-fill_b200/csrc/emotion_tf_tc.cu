@@ -39,14 +39,20 @@ namespace tc {
 using namespace umma;
 
 constexpr int D = 32, FF = 2048, NL = 4, SMAX = 20, HD = 8;
-constexpr int kTiles = 2;                  // token tiles per CTA
+#ifndef ERLFILL_TC_TILES
+#define ERLFILL_TC_TILES 2
+#endif
+constexpr int kTiles = ERLFILL_TC_TILES;   // token tiles per CTA: 2 (one CTA per SM, the tiles share the weight stream) or 1 (two CTAs per
+                                           // SM, each with its own stream: measured 3 % slower on B200 — every phase is bound by its own
+                                           // dependency chain, not by a shared unit, so desynchronising the two tiles buys nothing)
+constexpr int kCtasPerSm = kTiles == 1 ? 2 : 1;
 constexpr int EPT = 6;                     // envs per tile
 constexpr int ROWS = EPT * SMAX;           // 120 live rows of 128
 constexpr int KX = 48;                     // K extent of the activation operand: 32 features | 1 | 1 | 14 x 0
 constexpr int CH = 64;                     // hidden units per FFN chunk
 constexpr int NCH = FF / CH;               // 32
-constexpr int NS = 4;                      // weight ring stages
-constexpr int CPS = 2;                     // FFN chunks per ring stage
+constexpr int NS = 3;                      // weight ring stages
+constexpr int CPS = kTiles == 1 ? 2 : 4;   // FFN chunks per ring stage (the issuer checks the weight barrier once per stage: ~100 cycles)
 constexpr int W1_BYTES = CH * KX * 2;      // 6144
 constexpr int W2_BYTES = D * CH * 2;       // 4096
 constexpr int CHUNK_BYTES = W1_BYTES + W2_BYTES;
@@ -60,10 +66,13 @@ constexpr int MISC_EMBW = NL * MISC_LAYER, MISC_EMBB = MISC_EMBW + 96, MISC_POS 
 constexpr int POS_LD = 33;
 constexpr int MISC_FCW = MISC_POS + SMAX * POS_LD, MISC_FCB = MISC_FCW + 96;
 constexpr int MISC_FLOATS = ((MISC_FCB + 4 + 31) / 32) * 32;
-constexpr int IMG_FFN = 0;
-constexpr int IMG_ATT = IMG_FFN + NL * NCH * CHUNK_BYTES;
-constexpr int IMG_MISC = IMG_ATT + NL * ATT_BYTES;
+// weight stream: per layer one attention stage [in_proj | out_proj] (ATT_BYTES used of a STAGE_BYTES slot) followed by
+// NCH / CPS FFN stages; the producer walks it front to back once per token-tile group
+constexpr int SPL = 1 + NCH / CPS;         // stages per layer
+constexpr int IMG_STREAM = 0;
+constexpr int IMG_MISC = IMG_STREAM + NL * SPL * STAGE_BYTES;
 constexpr int IMAGE_BYTES = IMG_MISC + MISC_FLOATS * 4;
+static_assert(ATT_BYTES <= STAGE_BYTES, "attention weights must fit one ring stage");
 
 constexpr int XS_BYTES = 128 * KX * 2;     // 12288 per tile
 // attention operands of one tile, bf16: q[136][40] k[136][40] (token rows, 32 features + 8 pad) and v transposed
@@ -74,8 +83,7 @@ constexpr int KV_BYTES = SVT_OFF + D * VT_LD * 2 + 32;      // + per-env sequenc
 constexpr int SLEN_OFF = SVT_OFF + D * VT_LD * 2;
 // dynamic shared memory map
 constexpr int SM_RING = 0;
-constexpr int SM_ATT = SM_RING + NS * STAGE_BYTES;
-constexpr int SM_MISC = SM_ATT + NL * ATT_BYTES;
+constexpr int SM_MISC = SM_RING + NS * STAGE_BYTES;
 constexpr int SM_XS = SM_MISC + MISC_FLOATS * 4;
 constexpr int SM_KV = SM_XS + kTiles * XS_BYTES;
 constexpr int SM_BAR = SM_KV + kTiles * KV_BYTES;
@@ -84,15 +92,16 @@ constexpr int kBarPerTile = 6 + 2 * NHB;   // x_full qkv_full o_full out_full x2
 constexpr int kNumBars = kTiles * kBarPerTile + 2 * NS + 1;
 constexpr int SM_TMEM_SLOT = SM_BAR + kNumBars * 8;
 constexpr int SMEM_BYTES = SM_TMEM_SLOT + 16;
-static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds 227 KB");
-static_assert(SM_ATT % 128 == 0 && SM_XS % 128 == 0 && SM_KV % 16 == 0 && SM_BAR % 8 == 0, "alignment");
+static_assert(kCtasPerSm * (SMEM_BYTES + 1024) <= 233472, "shared memory plan exceeds the SM");
+static_assert(SM_MISC % 128 == 0 && SM_XS % 128 == 0 && SM_KV % 16 == 0 && SM_BAR % 8 == 0, "alignment");
 
 constexpr int kThreads = kTiles * 128 + kTiles * 32 + 32;   // tile warpgroups | one MMA issuer warp per tile | weight producer
 // TMEM columns per tile: H ring [0,192) | Y [192,224) | X = bf16 [x|1|1|0..] [224,248); QKV aliases [0,96), OUT aliases Y
 constexpr int TM_TILE = 256;
 constexpr int TM_Y = NHB * CH;
 constexpr int TM_X = TM_Y + D;
-static_assert(TM_X + KX / 2 <= TM_TILE && kTiles * TM_TILE <= 512, "tensor memory plan");
+constexpr int TM_COLS = kTiles * TM_TILE;    // 256 or 512: a power of two; two resident CTAs take 256 each
+static_assert(TM_X + KX / 2 <= TM_TILE && kCtasPerSm * TM_COLS <= 512, "tensor memory plan");
 constexpr float kQScale = 0.51006973f;     // log2(e) / sqrt(8): folded into the q rows of in_proj, softmax then uses exp2
 
 enum { B_XFULL = 0, B_QKV = 1, B_OFULL = 2, B_OUT = 3, B_X2 = 4, B_Y = 5, B_H = 6, B_P = 6 + NHB };
@@ -191,7 +200,7 @@ __device__ __forceinline__ void layer_norm32(float (&x)[D], const float *g, cons
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);
     uint64_t *w_full = bars + kTiles * kBarPerTile, *w_empty = w_full + NS, *c_full = w_empty + NS;
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
         mbar_init(c_full, 1);
         mbar_fence_init();
     }
-    if (warp == kTiles * 5) tmem_alloc(tmem_slot, 512);
+    if (warp == kTiles * 5) tmem_alloc(tmem_slot, TM_COLS);
     // attention-output images: zero (rows 120..127 are never written by the attention, and the out_proj reads them), then the
     // constant columns 32..47 of every row: [1, 1, 0 x 14] (bias hi/lo ride on the two ones)
     for (int i = tid; i < kTiles * XS_BYTES / 16; i += kThreads) reinterpret_cast<uint4 *>(smem + SM_XS)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -234,18 +243,22 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
     if (warp == kTiles * 5) {
         // =============================== weight producer ===============================================
         if (elect_one()) {
-            mbar_arrive_expect_tx(c_full, NL * ATT_BYTES + MISC_FLOATS * 4);
-            bulk_g2s(smem + SM_ATT, a.img + IMG_ATT, NL * ATT_BYTES, c_full);
+            mbar_arrive_expect_tx(c_full, MISC_FLOATS * 4);
             bulk_g2s(smem + SM_MISC, a.img + IMG_MISC, MISC_FLOATS * 4, c_full);
             uint32_t g = 0;
+            const bool prof = blockIdx.x == 0;
+            TC_PROF_DECL;
             for (int it = 0; it < n_it; ++it)
-                for (int ls = 0; ls < NL * NCH / CPS; ++ls, ++g) {
+                for (int ls = 0; ls < NL * SPL; ++ls, ++g) {
                     const uint32_t stage = g % NS, use = g / NS;
+                    const uint32_t bytes = (ls % SPL == 0) ? ATT_BYTES : STAGE_BYTES;
+                    TC_PROF(13);
                     mbar_wait(w_empty + stage, (use & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(w_full + stage, STAGE_BYTES);
-                    bulk_g2s(smem + SM_RING + stage * STAGE_BYTES, a.img + IMG_FFN + (size_t)ls * STAGE_BYTES, STAGE_BYTES,
-                             w_full + stage);
+                    TC_PROF(14);
+                    mbar_arrive_expect_tx(w_full + stage, bytes);
+                    bulk_g2s(smem + SM_RING + stage * STAGE_BYTES, a.img + IMG_STREAM + (size_t)ls * STAGE_BYTES, bytes, w_full + stage);
                 }
+            TC_PROF_FLUSH;
         }
         __syncwarp();
     } else if (warp >= kTiles * 4) {
@@ -254,9 +267,12 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
         constexpr uint32_t idesc_qkv = instr_desc_bf16(128, 96), idesc_32 = instr_desc_bf16(128, 32),
                            idesc_h = instr_desc_bf16(128, CH);
         constexpr uint32_t SBO_X = (KX / 8) * 128, SBO_W2 = (CH / 8) * 128;
-        const uint32_t xs = smem_u32(smem + SM_XS) + t * XS_BYTES, att0 = smem_u32(smem + SM_ATT), ring0 = smem_u32(smem + SM_RING);
+        const uint32_t xs = smem_u32(smem + SM_XS) + t * XS_BYTES, ring0 = smem_u32(smem + SM_RING);
         const uint32_t tT = tbase + t * TM_TILE;
         uint64_t *b = bars + t * kBarPerTile;
+        // descriptor of ring byte offset `off` = base descriptor + (off >> 4): the start-address field holds address/16 and never
+        // carries out of its 14 bits inside the ring, so the issue loop needs one add per MMA instead of rebuilding the descriptor
+        const uint64_t dX = smem_desc(ring0, 128, SBO_X), dW2 = smem_desc(ring0, 128, SBO_W2);
         mbar_wait(c_full, 0);
         const bool prof = blockIdx.x == 0 && t == 0 && (tid & 31) == 0;
         TC_PROF_DECL;
@@ -264,13 +280,16 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
         for (int it = 0; it < n_it; ++it)
             for (int l = 0; l < NL; ++l, ++n) {
                 const uint32_t par = n & 1u;
+                // this layer's attention weights: first stage of the layer in the weight stream
+                const uint32_t ga = n * SPL, att_stage = ga % NS, att = att_stage * (STAGE_BYTES >> 4);
+                mbar_wait(w_full + att_stage, (ga / NS) & 1u);
                 // ---- q|k|v = [x|1|1] (TMEM) . [W_in|b_hi|b_lo]^T ----
                 mbar_wait(b + B_XFULL, par);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
                     for (int s = 0; s < KX / 16; ++s)
-                        mma_ts(tT, tT + TM_X + s * 8, smem_desc(att0 + l * ATT_BYTES + s * 256, 128, SBO_X), idesc_qkv, s > 0);
+                        mma_ts(tT, tT + TM_X + s * 8, dX + (att + s * 16), idesc_qkv, s > 0);
                     mma_commit(b + B_QKV);
                 }
                 __syncwarp();
@@ -280,29 +299,29 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
                 if (elect_one()) {
 #pragma unroll
                     for (int s = 0; s < KX / 16; ++s)
-                        mma_ss(tT + TM_Y, smem_desc(xs + s * 256, 128, SBO_X),
-                               smem_desc(att0 + l * ATT_BYTES + INP_BYTES + s * 256, 128, SBO_X), idesc_32, s > 0);
+                        mma_ss(tT + TM_Y, smem_desc(xs + s * 256, 128, SBO_X), dX + (att + (INP_BYTES >> 4) + s * 16), idesc_32, s > 0);
                     mma_commit(b + B_OUT);
+                    mma_commit(w_empty + att_stage);
                 }
                 __syncwarp();
                 // ---- FFN: MMA1 runs NHB-1 chunks ahead of MMA2, so the epilogue always has a finished H chunk waiting ----
                 mbar_wait(b + B_X2, par);
                 tc_fence_after();
                 TC_PROF(8);
-                const uint32_t g0 = n * NCH;
+                const uint32_t g0 = n * NCH, gs0 = ga + 1;      // chunk counter (H ring / P phases) and first FFN stage of this layer
                 for (int c = 0; c < NCH + NHB - 1; ++c) {
                     if (c < NCH) {
-                        const uint32_t g = g0 + c, sg = g / CPS, stage = sg % NS, hb = g % NHB;
+                        const uint32_t g = g0 + c, sg = gs0 + c / CPS, stage = sg % NS, hb = g % NHB;
                         if ((c & (CPS - 1)) == 0) {
+                            if (prof && !mbar_try_wait(w_full + stage, (sg / NS) & 1u)) pacc[15] += 1;      // weights not there yet
                             mbar_wait(w_full + stage, (sg / NS) & 1u);
                             tc_fence_after();
                         }
                         TC_PROF(9);
                         if (elect_one()) {
-                            const uint32_t w1 = ring0 + stage * STAGE_BYTES + (c & (CPS - 1)) * CHUNK_BYTES;
+                            const uint64_t w1 = dX + (stage * (STAGE_BYTES >> 4) + (c & (CPS - 1)) * (CHUNK_BYTES >> 4));
 #pragma unroll
-                            for (int s = 0; s < KX / 16; ++s)
-                                mma_ts(tT + hb * CH, tT + TM_X + s * 8, smem_desc(w1 + s * 256, 128, SBO_X), idesc_h, s > 0);
+                            for (int s = 0; s < KX / 16; ++s) mma_ts(tT + hb * CH, tT + TM_X + s * 8, w1 + s * 16, idesc_h, s > 0);
                             mma_commit(b + B_H + hb);
                         }
                         __syncwarp();
@@ -310,16 +329,15 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
                     }
                     if (c >= NHB - 1) {
                         const int cc = c - (NHB - 1);
-                        const uint32_t g = g0 + cc, sg = g / CPS, stage = sg % NS, hb = g % NHB;
+                        const uint32_t g = g0 + cc, sg = gs0 + cc / CPS, stage = sg % NS, hb = g % NHB;
                         mbar_wait(b + B_P + hb, (g / NHB) & 1u);
                         tc_fence_after();
                         TC_PROF(11);
                         if (elect_one()) {
-                            const uint32_t w2 = ring0 + stage * STAGE_BYTES + (cc & (CPS - 1)) * CHUNK_BYTES + W1_BYTES;
+                            const uint64_t w2 = dW2 + (stage * (STAGE_BYTES >> 4) + (cc & (CPS - 1)) * (CHUNK_BYTES >> 4) + (W1_BYTES >> 4));
 #pragma unroll
                             for (int s = 0; s < CH / 16; ++s)
-                                mma_ts(tT + TM_Y, tT + hb * CH + s * 8, smem_desc(w2 + s * 256, 128, SBO_W2), idesc_32,
-                                       (cc > 0 || s > 0) ? 1u : 0u);
+                                mma_ts(tT + TM_Y, tT + hb * CH + s * 8, w2 + s * 16, idesc_32, (cc > 0 || s > 0) ? 1u : 0u);
                             if ((cc & (CPS - 1)) == CPS - 1) mma_commit(w_empty + stage);
                             if (cc == NCH - 1) mma_commit(b + B_Y);
                         }
@@ -437,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
                 // ---- attention on register fragments: this warp owns 6 of the tile's 24 (env, head) blocks ----
                 {
                     const int g8 = lane >> 2, tq = lane & 3;
-#pragma unroll 2
+#pragma unroll 3
                     for (int u = wq * 6; u < wq * 6 + 6; ++u) {
                         const int e = u >> 2, h = u & 3, row0 = e * SMAX;
                         const int Se = max(slen[e], 1);             // envs past the batch end: keep every value finite
@@ -610,7 +628,7 @@ __global__ void __launch_bounds__(kThreads, 1) emotion_forward_tc_kernel(const T
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kTiles * 5) tmem_dealloc(tbase, 512);
+    if (warp == kTiles * 5) tmem_dealloc(tbase, TM_COLS);
 }
 
 // ---- weight packing: fp32 state_dict tensors -> bf16 operand images + fp32 block -----------------------------
@@ -633,7 +651,7 @@ __global__ void emotion_tc_pack_kernel(const erlfill_transformer_weights w, uint
     for (int i = i0; i < NL * NCH * (CH * KX + D * CH); i += stride) {
         const int per = CH * KX + D * CH;
         const int lc = i / per, j = i % per, l = lc / NCH, c = lc % NCH;
-        uint8_t *st = img + IMG_FFN + (size_t)lc * CHUNK_BYTES;
+        uint8_t *st = img + IMG_STREAM + ((size_t)l * SPL + 1 + c / CPS) * STAGE_BYTES + (size_t)(c % CPS) * CHUNK_BYTES;
         if (j < CH * KX) {
             const int nn = j / KX, k = j % KX, hid = c * CH + nn;
             put_bf16(st, kmajor_off(nn, k, KX), aug_col(w.lin1_w + ((size_t)l * FF + hid) * D, w.lin1_b[l * FF + hid], k, 1.0f));
@@ -646,7 +664,7 @@ __global__ void emotion_tc_pack_kernel(const erlfill_transformer_weights w, uint
     for (int i = i0; i < NL * (96 + D) * KX; i += stride) {
         const int per = (96 + D) * KX;
         const int l = i / per, j = i % per;
-        uint8_t *at = img + IMG_ATT + (size_t)l * ATT_BYTES;
+        uint8_t *at = img + IMG_STREAM + (size_t)l * SPL * STAGE_BYTES;
         if (j < 96 * KX) {
             const int nn = j / KX, k = j % KX;
             put_bf16(at, kmajor_off(nn, k, KX), aug_col(w.in_proj_w + ((size_t)l * 96 + nn) * D, w.in_proj_b[l * 96 + nn], k, nn < D ? kQScale : 1.0f));
@@ -692,6 +710,13 @@ int erlfill_debug_tc_profile(unsigned long long *out16, int reset) {
     return ERLFILL_OK;
 }
 
+/* development aid: compile-time shape of the kernel (token tiles per CTA, resident CTAs per SM) */
+int erlfill_debug_tc_config(int *tiles, int *ctas_per_sm) {
+    if (tiles) *tiles = tc::kTiles;
+    if (ctas_per_sm) *ctas_per_sm = tc::kCtasPerSm;
+    return ERLFILL_OK;
+}
+
 size_t erlfill_emotion_tc_image_bytes(void) { return (size_t)tc::IMAGE_BYTES; }
 
 int erlfill_emotion_tc_pack(const erlfill_transformer_weights *w, void *d_image, void *stream) {
@@ -725,7 +750,8 @@ int erlfill_emotion_forward_tc(const void *d_image, int n_env, const float *d_se
         ERLFILL_CUDA_TRY(cudaFuncSetAttribute(tc::emotion_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         n_sm[dev] = v;
     }
-    const int grid = a.n_groups < n_sm[dev] ? a.n_groups : n_sm[dev];
+    const int max_ctas = n_sm[dev] * tc::kCtasPerSm;
+    const int grid = a.n_groups < max_ctas ? a.n_groups : max_ctas;
     tc::emotion_forward_tc_kernel<<<grid, tc::kThreads, tc::SMEM_BYTES, (cudaStream_t)stream>>>(a);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;

@@ -32,9 +32,12 @@ for prec, reps in (("bf16", 10),) + ((("fp32", 2),) if "--fp32" in sys.argv else
     if prec == "bf16":
         L.lib().erlfill_debug_tc_profile(prof, 0)
         names = ["image store", "wait qkv", "qkv epilogue", "attention", "wait out_proj", "LN1+store", "FFN loop", "wait Y+LN2"]
-        names += ["I:non-FFN", "I:wait W", "I:issue MMA1", "I:wait P", "I:issue MMA2"]
+        names += ["I:non-FFN", "I:wait W", "I:issue MMA1", "I:wait P", "I:issue MMA2", "P:issue", "P:wait empty", "I:W-not-ready count"]
         tot = sum(prof[:8])
-        groups = -(-n // 12)
-        n_it = -(-groups // min(groups, 148))
+        tiles, cps = C.c_int(), C.c_int()
+        L.lib().erlfill_debug_tc_config(C.byref(tiles), C.byref(cps))
+        groups = -(-n // (6 * tiles.value))
+        n_it = -(-groups // min(groups, 148 * cps.value))
+        print("kernel shape: %d tile(s)/CTA, %d CTA(s)/SM" % (tiles.value, cps.value))
         print("block 0 phase cycles per layer-step (%d layer-steps/launch):" % (n_it * 4), ", ".join(
             "%s %.0f" % (nm, v / (reps * n_it * 4)) for nm, v in zip(names, prof)), "| total %.0f" % (tot / (reps * n_it * 4)))
