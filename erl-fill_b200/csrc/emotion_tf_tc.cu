@@ -52,7 +52,7 @@ constexpr int KX = 48;                     // K extent of the activation operand
 constexpr int CH = 64;                     // hidden units per FFN chunk
 constexpr int NCH = FF / CH;               // 32
 constexpr int NS = 3;                      // weight ring stages
-constexpr int CPS = kTiles == 1 ? 2 : 4;   // FFN chunks per ring stage (the issuer checks the weight barrier once per stage: ~100 cycles)
+constexpr int CPS = 2;                     // FFN chunks per ring stage
 constexpr int W1_BYTES = CH * KX * 2;      // 6144
 constexpr int W2_BYTES = D * CH * 2;       // 4096
 constexpr int CHUNK_BYTES = W1_BYTES + W2_BYTES;
@@ -86,14 +86,22 @@ constexpr int SM_RING = 0;
 constexpr int SM_MISC = SM_RING + NS * STAGE_BYTES;
 constexpr int SM_XS = SM_MISC + MISC_FLOATS * 4;
 constexpr int SM_KV = SM_XS + kTiles * XS_BYTES;
-constexpr int SM_BAR = SM_KV + kTiles * KV_BYTES;
+// deferred last layer: only the LAST token of an env feeds fc_out, so in layer 4 everything after the attention (out_proj,
+// LayerNorm1, FFN, LayerNorm2) is needed for one row in 20.  Those rows are parked here — the attention output row in a second
+// operand image, the residual stream and the env index beside it — and processed kTiles*128 at a time ("tail pass").
+constexpr int TAIL_ROWS = kTiles * 128;
+constexpr int XT_LD = 36;                  // floats per parked residual row (32 + 4 pad: conflict-free 16-byte row access)
+constexpr int SM_XSTAIL = SM_KV + kTiles * KV_BYTES;
+constexpr int SM_XTAIL = SM_XSTAIL + kTiles * XS_BYTES;
+constexpr int SM_ENVTAIL = SM_XTAIL + TAIL_ROWS * XT_LD * 4;
+constexpr int SM_BAR = SM_ENVTAIL + TAIL_ROWS * 4;
 constexpr int NHB = 3;                     // H buffers (TMEM) per tile: MMA1 runs two chunks ahead of the epilogue
 constexpr int kBarPerTile = 6 + 2 * NHB;   // x_full qkv_full o_full out_full x2_full y_full h_full[NHB] p_full[NHB]
 constexpr int kNumBars = kTiles * kBarPerTile + 2 * NS + 1;
 constexpr int SM_TMEM_SLOT = SM_BAR + kNumBars * 8;
 constexpr int SMEM_BYTES = SM_TMEM_SLOT + 16;
 static_assert(kCtasPerSm * (SMEM_BYTES + 1024) <= 233472, "shared memory plan exceeds the SM");
-static_assert(SM_MISC % 128 == 0 && SM_XS % 128 == 0 && SM_KV % 16 == 0 && SM_BAR % 8 == 0, "alignment");
+static_assert(SM_MISC % 128 == 0 && SM_XS % 128 == 0 && SM_KV % 16 == 0 && SM_XSTAIL % 16 == 0 && SM_XTAIL % 16 == 0 && SM_BAR % 8 == 0, "alignment");
 
 constexpr int kThreads = kTiles * 128 + kTiles * 32 + 32;   // tile warpgroups | one MMA issuer warp per tile | weight producer
 // TMEM columns per tile: H ring [0,192) | Y [192,224) | X = bf16 [x|1|1|0..] [224,248); QKV aliases [0,96), OUT aliases Y
@@ -200,6 +208,16 @@ __device__ __forceinline__ void layer_norm32(float (&x)[D], const float *g, cons
     }
 }
 
+// One schedule, walked identically by every warp role of the CTA (the roles only meet through barriers):
+//   for each group of kTiles*6 envs:  layers 0..2 in full, layer 3 up to the attention (its last-token rows are parked);
+//   a tail pass (second half of layer 3 on the parked rows) whenever the next group would not fit, and after the last group.
+struct Sched {
+    int pending = 0;            // parked rows
+    uint32_t nA = 0, nB = 0;    // first halves / second halves done so far: phases of their barriers
+    uint32_t gs = 0;            // weight stages consumed so far
+    __device__ bool flush_after_group(int it, int n_it) const { return pending + kTiles * EPT > TAIL_ROWS || it == n_it - 1; }
+};
+
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);
@@ -224,13 +242,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
         mbar_fence_init();
     }
     if (warp == kTiles * 5) tmem_alloc(tmem_slot, TM_COLS);
-    // attention-output images: zero (rows 120..127 are never written by the attention, and the out_proj reads them), then the
-    // constant columns 32..47 of every row: [1, 1, 0 x 14] (bias hi/lo ride on the two ones)
-    for (int i = tid; i < kTiles * XS_BYTES / 16; i += kThreads) reinterpret_cast<uint4 *>(smem + SM_XS)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // attention-output images (per-layer and tail): zero (rows the attention never writes are still read by the out_proj), then
+    // the constant columns 32..47 of every row: [1, 1, 0 x 14] (bias hi/lo ride on the two ones)
+    for (int i = tid; i < kTiles * XS_BYTES / 16; i += kThreads) {
+        reinterpret_cast<uint4 *>(smem + SM_XS)[i] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4 *>(smem + SM_XSTAIL)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int i = tid; i < TAIL_ROWS * XT_LD / 4; i += kThreads) reinterpret_cast<uint4 *>(smem + SM_XTAIL)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < TAIL_ROWS; i += kThreads) reinterpret_cast<int *>(smem + SM_ENVTAIL)[i] = -1;
     __syncthreads();
     for (int i = tid; i < kTiles * 128; i += kThreads) {
-        uint8_t *row = smem + SM_XS + (i >> 7) * XS_BYTES + ((i & 127) >> 3) * (KX / 8) * 128 + (i & 7) * 16;
-        *reinterpret_cast<uint4 *>(row + 4 * 128) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+        const int off = (i >> 7) * XS_BYTES + ((i & 127) >> 3) * (KX / 8) * 128 + (i & 7) * 16 + 4 * 128;
+        *reinterpret_cast<uint4 *>(smem + SM_XS + off) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(smem + SM_XSTAIL + off) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
     }
     // attention operand buffers start finite (rows/columns past the 120 live tokens are read, never written)
     for (int i = tid; i < kTiles * KV_BYTES / 16; i += kThreads) reinterpret_cast<uint4 *>(smem + SM_KV)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -248,16 +272,24 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
             uint32_t g = 0;
             const bool prof = blockIdx.x == 0;
             TC_PROF_DECL;
-            for (int it = 0; it < n_it; ++it)
-                for (int ls = 0; ls < NL * SPL; ++ls, ++g) {
+            // stages [first, first + count) of layer l's block of the stream
+            auto load = [&](int l, int first, int count) {
+                for (int sidx = first; sidx < first + count; ++sidx, ++g) {
                     const uint32_t stage = g % NS, use = g / NS;
-                    const uint32_t bytes = (ls % SPL == 0) ? ATT_BYTES : STAGE_BYTES;
+                    const uint32_t bytes = sidx == 0 ? ATT_BYTES : STAGE_BYTES;
                     TC_PROF(13);
                     mbar_wait(w_empty + stage, (use & 1u) ^ 1u);
                     TC_PROF(14);
                     mbar_arrive_expect_tx(w_full + stage, bytes);
-                    bulk_g2s(smem + SM_RING + stage * STAGE_BYTES, a.img + IMG_STREAM + (size_t)ls * STAGE_BYTES, bytes, w_full + stage);
+                    bulk_g2s(smem + SM_RING + stage * STAGE_BYTES, a.img + IMG_STREAM + ((size_t)l * SPL + sidx) * STAGE_BYTES, bytes, w_full + stage);
                 }
+            };
+            Sched sc;
+            for (int it = 0; it < n_it; ++it) {
+                for (int l = 0; l < NL; ++l) load(l, 0, l < NL - 1 ? SPL : 1);
+                sc.pending += kTiles * EPT;
+                if (sc.flush_after_group(it, n_it)) { load(NL - 1, 0, SPL); sc.pending = 0; }
+            }
             TC_PROF_FLUSH;
         }
         __syncwarp();
@@ -267,7 +299,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
         constexpr uint32_t idesc_qkv = instr_desc_bf16(128, 96), idesc_32 = instr_desc_bf16(128, 32),
                            idesc_h = instr_desc_bf16(128, CH);
         constexpr uint32_t SBO_X = (KX / 8) * 128, SBO_W2 = (CH / 8) * 128;
-        const uint32_t xs = smem_u32(smem + SM_XS) + t * XS_BYTES, ring0 = smem_u32(smem + SM_RING);
+        const uint32_t xs = smem_u32(smem + SM_XS) + t * XS_BYTES, xs_tail = smem_u32(smem + SM_XSTAIL) + t * XS_BYTES;
+        const uint32_t ring0 = smem_u32(smem + SM_RING);
         const uint32_t tT = tbase + t * TM_TILE;
         uint64_t *b = bars + t * kBarPerTile;
         // descriptor of ring byte offset `off` = base descriptor + (off >> 4): the start-address field holds address/16 and never
@@ -276,76 +309,89 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
         mbar_wait(c_full, 0);
         const bool prof = blockIdx.x == 0 && t == 0 && (tid & 31) == 0;
         TC_PROF_DECL;
-        uint32_t n = 0;                                    // (group iteration, layer) counter: phase of the per-layer barriers
-        for (int it = 0; it < n_it; ++it)
-            for (int l = 0; l < NL; ++l, ++n) {
-                const uint32_t par = n & 1u;
-                // this layer's attention weights: first stage of the layer in the weight stream
-                const uint32_t ga = n * SPL, att_stage = ga % NS, att = att_stage * (STAGE_BYTES >> 4);
-                mbar_wait(w_full + att_stage, (ga / NS) & 1u);
-                // ---- q|k|v = [x|1|1] (TMEM) . [W_in|b_hi|b_lo]^T ----
-                mbar_wait(b + B_XFULL, par);
-                tc_fence_after();
-                if (elect_one()) {
+        Sched sc;
+        // first half of a layer: q|k|v = [x|1|1] (TMEM) . [W_in|b_hi|b_lo]^T from the layer's attention stage (stage sc.gs)
+        auto first_half = [&](bool release_stage) {
+            const uint32_t att_stage = sc.gs % NS, att = att_stage * (STAGE_BYTES >> 4);
+            mbar_wait(w_full + att_stage, (sc.gs / NS) & 1u);
+            mbar_wait(b + B_XFULL, sc.nA & 1u);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-                    for (int s = 0; s < KX / 16; ++s)
-                        mma_ts(tT, tT + TM_X + s * 8, dX + (att + s * 16), idesc_qkv, s > 0);
-                    mma_commit(b + B_QKV);
-                }
-                __syncwarp();
-                // ---- attention output projection: [o|1|1] (smem image) . [W_out|b_hi|b_lo]^T ----
-                mbar_wait(b + B_OFULL, par);
-                tc_fence_after();
-                if (elect_one()) {
+                for (int s = 0; s < KX / 16; ++s) mma_ts(tT, tT + TM_X + s * 8, dX + (att + s * 16), idesc_qkv, s > 0);
+                mma_commit(b + B_QKV);
+                if (release_stage) mma_commit(w_empty + att_stage);
+            }
+            __syncwarp();
+            ++sc.nA;
+        };
+        // second half: out_proj from the image at `img` and the attention stage sc.gs, then the FFN from stages sc.gs+1 ..
+        auto second_half = [&](uint32_t img) {
+            const uint32_t par = sc.nB & 1u;
+            const uint32_t att_stage = sc.gs % NS, att = att_stage * (STAGE_BYTES >> 4);
+            mbar_wait(w_full + att_stage, (sc.gs / NS) & 1u);
+            mbar_wait(b + B_OFULL, par);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-                    for (int s = 0; s < KX / 16; ++s)
-                        mma_ss(tT + TM_Y, smem_desc(xs + s * 256, 128, SBO_X), dX + (att + (INP_BYTES >> 4) + s * 16), idesc_32, s > 0);
-                    mma_commit(b + B_OUT);
-                    mma_commit(w_empty + att_stage);
-                }
-                __syncwarp();
-                // ---- FFN: MMA1 runs NHB-1 chunks ahead of MMA2, so the epilogue always has a finished H chunk waiting ----
-                mbar_wait(b + B_X2, par);
-                tc_fence_after();
-                TC_PROF(8);
-                const uint32_t g0 = n * NCH, gs0 = ga + 1;      // chunk counter (H ring / P phases) and first FFN stage of this layer
-                for (int c = 0; c < NCH + NHB - 1; ++c) {
-                    if (c < NCH) {
-                        const uint32_t g = g0 + c, sg = gs0 + c / CPS, stage = sg % NS, hb = g % NHB;
-                        if ((c & (CPS - 1)) == 0) {
-                            if (prof && !mbar_try_wait(w_full + stage, (sg / NS) & 1u)) pacc[15] += 1;      // weights not there yet
-                            mbar_wait(w_full + stage, (sg / NS) & 1u);
-                            tc_fence_after();
-                        }
-                        TC_PROF(9);
-                        if (elect_one()) {
-                            const uint64_t w1 = dX + (stage * (STAGE_BYTES >> 4) + (c & (CPS - 1)) * (CHUNK_BYTES >> 4));
-#pragma unroll
-                            for (int s = 0; s < KX / 16; ++s) mma_ts(tT + hb * CH, tT + TM_X + s * 8, w1 + s * 16, idesc_h, s > 0);
-                            mma_commit(b + B_H + hb);
-                        }
-                        __syncwarp();
-                        TC_PROF(10);
-                    }
-                    if (c >= NHB - 1) {
-                        const int cc = c - (NHB - 1);
-                        const uint32_t g = g0 + cc, sg = gs0 + cc / CPS, stage = sg % NS, hb = g % NHB;
-                        mbar_wait(b + B_P + hb, (g / NHB) & 1u);
+                for (int s = 0; s < KX / 16; ++s)
+                    mma_ss(tT + TM_Y, smem_desc(img + s * 256, 128, SBO_X), dX + (att + (INP_BYTES >> 4) + s * 16), idesc_32, s > 0);
+                mma_commit(b + B_OUT);
+                mma_commit(w_empty + att_stage);
+            }
+            __syncwarp();
+            // ---- FFN: MMA1 runs NHB-1 chunks ahead of MMA2, so the epilogue always has a finished H chunk waiting ----
+            mbar_wait(b + B_X2, par);
+            tc_fence_after();
+            TC_PROF(8);
+            const uint32_t g0 = sc.nB * NCH, gs0 = sc.gs + 1;   // chunk counter (H ring / P phases) and first FFN stage
+            for (int c = 0; c < NCH + NHB - 1; ++c) {
+                if (c < NCH) {
+                    const uint32_t g = g0 + c, sg = gs0 + c / CPS, stage = sg % NS, hb = g % NHB;
+                    if ((c & (CPS - 1)) == 0) {
+                        mbar_wait(w_full + stage, (sg / NS) & 1u);
                         tc_fence_after();
-                        TC_PROF(11);
-                        if (elect_one()) {
-                            const uint64_t w2 = dW2 + (stage * (STAGE_BYTES >> 4) + (cc & (CPS - 1)) * (CHUNK_BYTES >> 4) + (W1_BYTES >> 4));
-#pragma unroll
-                            for (int s = 0; s < CH / 16; ++s)
-                                mma_ts(tT + TM_Y, tT + hb * CH + s * 8, w2 + s * 16, idesc_32, (cc > 0 || s > 0) ? 1u : 0u);
-                            if ((cc & (CPS - 1)) == CPS - 1) mma_commit(w_empty + stage);
-                            if (cc == NCH - 1) mma_commit(b + B_Y);
-                        }
-                        __syncwarp();
-                        TC_PROF(12);
                     }
+                    TC_PROF(9);
+                    if (elect_one()) {
+                        const uint64_t w1 = dX + (stage * (STAGE_BYTES >> 4) + (c & (CPS - 1)) * (CHUNK_BYTES >> 4));
+#pragma unroll
+                        for (int s = 0; s < KX / 16; ++s) mma_ts(tT + hb * CH, tT + TM_X + s * 8, w1 + s * 16, idesc_h, s > 0);
+                        mma_commit(b + B_H + hb);
+                    }
+                    __syncwarp();
+                    TC_PROF(10);
+                }
+                if (c >= NHB - 1) {
+                    const int cc = c - (NHB - 1);
+                    const uint32_t g = g0 + cc, sg = gs0 + cc / CPS, stage = sg % NS, hb = g % NHB;
+                    mbar_wait(b + B_P + hb, (g / NHB) & 1u);
+                    tc_fence_after();
+                    TC_PROF(11);
+                    if (elect_one()) {
+                        const uint64_t w2 = dW2 + (stage * (STAGE_BYTES >> 4) + (cc & (CPS - 1)) * (CHUNK_BYTES >> 4) + (W1_BYTES >> 4));
+#pragma unroll
+                        for (int s = 0; s < CH / 16; ++s)
+                            mma_ts(tT + TM_Y, tT + hb * CH + s * 8, w2 + s * 16, idesc_32, (cc > 0 || s > 0) ? 1u : 0u);
+                        if ((cc & (CPS - 1)) == CPS - 1) mma_commit(w_empty + stage);
+                        if (cc == NCH - 1) mma_commit(b + B_Y);
+                    }
+                    __syncwarp();
+                    TC_PROF(12);
                 }
             }
+            ++sc.nB;
+            sc.gs += SPL;
+        };
+        for (int it = 0; it < n_it; ++it) {
+            for (int l = 0; l < NL; ++l) {
+                first_half(l == NL - 1);
+                if (l < NL - 1) second_half(xs);
+                else sc.gs += 1;
+            }
+            sc.pending += kTiles * EPT;
+            if (sc.flush_after_group(it, n_it)) { second_half(xs_tail); sc.pending = 0; }
+        }
         TC_PROF_FLUSH;
     } else {
         // =============================== token-tile warpgroups ==========================================
@@ -357,6 +403,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
         __nv_bfloat16 *sq = reinterpret_cast<__nv_bfloat16 *>(att + SQ_OFF), *sk = reinterpret_cast<__nv_bfloat16 *>(att + SK_OFF),
                       *svt = reinterpret_cast<__nv_bfloat16 *>(att + SVT_OFF);
         int *slen = reinterpret_cast<int *>(att + SLEN_OFF);
+        float *xtail = reinterpret_cast<float *>(smem + SM_XTAIL);
+        int *envtail = reinterpret_cast<int *>(smem + SM_ENVTAIL);
         const uint32_t tT = tbase + t * TM_TILE + ((uint32_t)(wq * 32) << 16);
         // constant K columns 32..47 of the X operand: [1, 1, 0 x 14]
         {
@@ -367,14 +415,233 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
         mbar_wait(c_full, 0);
         const bool prof = blockIdx.x == 0 && tid == 0;
         TC_PROF_DECL;
-        uint32_t n = 0;
+        Sched sc;
+        float x[D];
+
+        // ---- first half of a layer: x -> q|k|v (tensor core) -> attention on register fragments -> bf16 rows of o.
+        //      park == false: o goes to the tile's operand image for the out_proj that follows;
+        //      park == true (last layer): only each env's last-token row is kept, in the tail image at row sc.pending + t*6 + env ----
+        auto first_half = [&](bool park) {
+            store_row_tmem(tT + TM_X, x);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b + B_XFULL);
+            TC_PROF(0);
+            mbar_wait(b + B_QKV, sc.nA & 1u);
+            tc_fence_after();
+            TC_PROF(1);
+            {
+                // q|k|v rows -> bf16 attention operands: q[r][:], k[r][:] row-major, v transposed vT[:][r]
+                uint32_t rq[32];
+                tmem_ld32(tT, rq);
+                tmem_wait_ld();
+                uint4 *qrow = reinterpret_cast<uint4 *>(sq + r * QK_LD);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    qrow[j] = make_uint4(pack_bf16x2(__uint_as_float(rq[8 * j]), __uint_as_float(rq[8 * j + 1])),
+                                         pack_bf16x2(__uint_as_float(rq[8 * j + 2]), __uint_as_float(rq[8 * j + 3])),
+                                         pack_bf16x2(__uint_as_float(rq[8 * j + 4]), __uint_as_float(rq[8 * j + 5])),
+                                         pack_bf16x2(__uint_as_float(rq[8 * j + 6]), __uint_as_float(rq[8 * j + 7])));
+                tmem_ld32(tT + 32, rq);
+                tmem_wait_ld();
+                uint4 *krow = reinterpret_cast<uint4 *>(sk + r * QK_LD);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    krow[j] = make_uint4(pack_bf16x2(__uint_as_float(rq[8 * j]), __uint_as_float(rq[8 * j + 1])),
+                                         pack_bf16x2(__uint_as_float(rq[8 * j + 2]), __uint_as_float(rq[8 * j + 3])),
+                                         pack_bf16x2(__uint_as_float(rq[8 * j + 4]), __uint_as_float(rq[8 * j + 5])),
+                                         pack_bf16x2(__uint_as_float(rq[8 * j + 6]), __uint_as_float(rq[8 * j + 7])));
+                tmem_ld32(tT + 64, rq);
+                tmem_wait_ld();
+#pragma unroll
+                for (int d = 0; d < D; ++d) svt[d * VT_LD + r] = __float2bfloat16_rn(__uint_as_float(rq[d]));
+            }
+            tc_fence_before();                                // q|k|v loads ordered before the MMAs that reuse those columns
+            named_bar_sync(1 + t, 128);
+            TC_PROF(2);
+            // ---- attention on register fragments: this warp owns 6 of the tile's 24 (env, head) blocks ----
+            {
+                const int g8 = lane >> 2, tq = lane & 3;
+#pragma unroll 3
+                for (int u = wq * 6; u < wq * 6 + 6; ++u) {
+                    const int e = u >> 2, h = u & 3, row0 = e * SMAX;
+                    const int Se = max(slen[e], 1);             // envs past the batch end: keep every value finite
+                    // scores S = Q_h K_h^T (already in the log2 domain): 2 query m-tiles x 3 key n-tiles
+                    uint32_t qa[2][2], kb[3];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        qa[mt][0] = *reinterpret_cast<const uint32_t *>(sq + (row0 + mt * 16 + g8) * QK_LD + h * HD + 2 * tq);
+                        qa[mt][1] = *reinterpret_cast<const uint32_t *>(sq + (row0 + mt * 16 + g8 + 8) * QK_LD + h * HD + 2 * tq);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < 3; ++nt)
+                        kb[nt] = *reinterpret_cast<const uint32_t *>(sk + (row0 + nt * 8 + g8) * QK_LD + h * HD + 2 * tq);
+                    float scr[2][3][4];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 3; ++nt) {
+                            scr[mt][nt][0] = scr[mt][nt][1] = scr[mt][nt][2] = scr[mt][nt][3] = 0.f;
+                            mma_16x8x8(scr[mt][nt], qa[mt][0], qa[mt][1], kb[nt]);
+                        }
+                    // V fragments: vT[feature g8 of head h][key 8*ks + 2*tq, +1]
+                    uint32_t vb[3];
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks)
+                        vb[ks] = *reinterpret_cast<const uint32_t *>(svt + (h * HD + g8) * VT_LD + row0 + ks * 8 + 2 * tq);
+                    // masked keys belong to another env (or to no token): their V is zeroed, not just weighted by p = 0, so a
+                    // non-finite value in one env can never reach its neighbours in the tile
+                    if (Se == SMAX) { if (tq >= 2) vb[2] = 0u; }
+                    else {
+#pragma unroll
+                        for (int ks = 0; ks < 3; ++ks) {
+                            const int k0 = ks * 8 + 2 * tq;
+                            if (k0 >= Se) vb[ks] = 0u; else if (k0 + 1 >= Se) vb[ks] &= 0x0000FFFFu;
+                        }
+                    }
+                    // destination of a query row: the tile image, or (parked) the tail image row of this env if it is the last token
+                    const int park_row = sc.pending + t * EPT + e;
+                    uint8_t *park_img = smem + SM_XSTAIL + (park_row >> 7) * XS_BYTES;
+                    auto store_o = [&](int qrow, float o0, float o1) {
+                        if (!park) {
+                            const int rr = row0 + qrow;
+                            *reinterpret_cast<uint32_t *>(xs + (rr >> 3) * (KX / 8) * 128 + h * 128 + (rr & 7) * 16 + tq * 4) = pack_bf16x2(o0, o1);
+                        } else if (qrow == Se - 1) {
+                            const int rr = park_row & 127;
+                            *reinterpret_cast<uint32_t *>(park_img + (rr >> 3) * (KX / 8) * 128 + h * 128 + (rr & 7) * 16 + tq * 4) = pack_bf16x2(o0, o1);
+                        }
+                    };
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        // rows g8 (elements 0,1) and g8+8 (elements 2,3) of this m-tile; key of element i: 8*nt + 2*tq + (i&1).
+                        // Rows 24..31 (second half of m-tile 1) never belong to this env: nothing is computed for them.
+                        const bool lo_rows_only = mt == 1;
+                        if (Se == SMAX) {                 // full history (the common case): only keys 20..23 are masked
+                            if (tq >= 2) scr[mt][2][0] = scr[mt][2][1] = scr[mt][2][2] = scr[mt][2][3] = -INFINITY;
+                        } else {
+#pragma unroll
+                            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    if (nt * 8 + 2 * tq + (i & 1) >= Se) scr[mt][nt][i] = -INFINITY;
+                        }
+                        float mx0 = fmaxf(fmaxf(fmaxf(scr[mt][0][0], scr[mt][0][1]), fmaxf(scr[mt][1][0], scr[mt][1][1])),
+                                          fmaxf(scr[mt][2][0], scr[mt][2][1]));
+                        float mx1 = lo_rows_only ? 0.f
+                                                 : fmaxf(fmaxf(fmaxf(scr[mt][0][2], scr[mt][0][3]), fmaxf(scr[mt][1][2], scr[mt][1][3])),
+                                                         fmaxf(scr[mt][2][2], scr[mt][2][3]));
+                        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+                        if (!lo_rows_only) {
+                            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+                        }
+                        float sum0 = 0.f, sum1 = 0.f;
+                        uint32_t pa[3][2];
+#pragma unroll
+                        for (int nt = 0; nt < 3; ++nt) {
+                            const float p0 = fast_exp2(scr[mt][nt][0] - mx0), p1 = fast_exp2(scr[mt][nt][1] - mx0);
+                            sum0 += p0 + p1;
+                            pa[nt][0] = pack_bf16x2(p0, p1);
+                            if (!lo_rows_only) {
+                                const float p2 = fast_exp2(scr[mt][nt][2] - mx1), p3 = fast_exp2(scr[mt][nt][3] - mx1);
+                                sum1 += p2 + p3;
+                                pa[nt][1] = pack_bf16x2(p2, p3);
+                            } else pa[nt][1] = 0u;
+                        }
+                        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+                        if (!lo_rows_only) {
+                            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+                        }
+                        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int ks = 0; ks < 3; ++ks) mma_16x8x8(o, pa[ks][0], pa[ks][1], vb[ks]);
+                        // rows past the env's 20 tokens belong to the next env: not stored
+                        const int q0 = mt * 16 + g8;
+                        if (q0 < SMAX) {
+                            const float i0 = fast_rcp(sum0);
+                            store_o(q0, o[0] * i0, o[1] * i0);
+                        }
+                        if (!lo_rows_only) {
+                            const float i1 = fast_rcp(sum1);
+                            store_o(q0 + 8, o[2] * i1, o[3] * i1);
+                        }
+                    }
+                }
+            }
+            fence_proxy_async();                              // o rows (generic-proxy stores) -> visible to the out_proj MMA
+            TC_PROF(3);
+            ++sc.nA;
+        };
+
+        // ---- second half of a layer on this thread's row: out_proj + residual + LayerNorm1, FFN, + residual + LayerNorm2 ----
+        auto second_half = [&](int l) {
+            const uint32_t par = sc.nB & 1u;
+            const float *lw = misc + l * MISC_LAYER;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b + B_OFULL);
+            mbar_wait(b + B_OUT, par);
+            tc_fence_after();
+            TC_PROF(4);
+            {
+                uint32_t ro[32];
+                tmem_ld32(tT + TM_Y, ro);
+                tmem_wait_ld();
+#pragma unroll
+                for (int d = 0; d < D; ++d) x[d] += __uint_as_float(ro[d]);
+            }
+            layer_norm32(x, lw, lw + D);
+            store_row_tmem(tT + TM_X, x);
+            tc_fence_before();                                // also orders the tcgen05.ld of OUT before MMA2 overwrites that region
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b + B_X2);
+            TC_PROF(5);
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+                const uint32_t g = sc.nB * NCH + c, hb = g % NHB;
+                mbar_wait(b + B_H + hb, (g / NHB) & 1u);
+                tc_fence_after();
+                uint32_t h0[32], h1[32], p[32];
+                tmem_ld32(tT + hb * CH, h0);
+                tmem_ld32(tT + hb * CH + 32, h1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    p[j] = pack_relu_bf16x2(__uint_as_float(h0[2 * j]), __uint_as_float(h0[2 * j + 1]));
+                    p[16 + j] = pack_relu_bf16x2(__uint_as_float(h1[2 * j]), __uint_as_float(h1[2 * j + 1]));
+                }
+                tmem_st32(tT + hb * CH, p);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b + B_P + hb);
+            }
+            TC_PROF(6);
+            mbar_wait(b + B_Y, par);
+            tc_fence_after();
+            {
+                uint32_t ry[32];
+                tmem_ld32(tT + TM_Y, ry);
+                tmem_wait_ld();
+#pragma unroll
+                for (int d4 = 0; d4 < D; d4 += 4) {
+                    const float4 b2 = *reinterpret_cast<const float4 *>(lw + 4 * D + d4);
+                    x[d4 + 0] += __uint_as_float(ry[d4 + 0]) + b2.x;
+                    x[d4 + 1] += __uint_as_float(ry[d4 + 1]) + b2.y;
+                    x[d4 + 2] += __uint_as_float(ry[d4 + 2]) + b2.z;
+                    x[d4 + 3] += __uint_as_float(ry[d4 + 3]) + b2.w;
+                }
+            }
+            layer_norm32(x, lw + 2 * D, lw + 3 * D);
+            tc_fence_before();                                // tcgen05.ld of Y / H ordered before the next MMAs into those columns
+            TC_PROF(7);
+            ++sc.nB;
+        };
+
         for (int it = 0; it < n_it; ++it) {
             const int group = blockIdx.x + it * gridDim.x;
             const int env = (group * kTiles + t) * EPT + e_loc;
             const bool env_ok = r < ROWS && env < a.n;
             // ---- sequence of this env (EmotionModule.get_state, :83-102) and this row's token ----
             int S = 0;
-            float x[D];
 #pragma unroll
             for (int d = 0; d < D; ++d) x[d] = 0.f;
             if (env_ok) {
@@ -407,221 +674,48 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
                     }
                 }
             }
-            const bool tok_ok = env_ok && s_pos < S;
-            // the previous group's attention (last reader of slen) finished before its o_full arrivals, which every
-            // thread of the tile has since waited behind (out_full)
+            // the previous group's attention (last reader of slen) finished before this point: every warp of the tile has since
+            // passed a barrier that all four warps arrive on after their attention
             if (r < ROWS && s_pos == 0) slen[e_loc] = S;
 
-            for (int l = 0; l < NL; ++l, ++n) {
-                const uint32_t par = n & 1u;
-                const float *lw = misc + l * MISC_LAYER;
-                // ---- x -> bf16 operand in tensor memory -> q|k|v on the tensor core ----
-                store_row_tmem(tT + TM_X, x);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(b + B_XFULL);
-                TC_PROF(0);
-                mbar_wait(b + B_QKV, par);
-                tc_fence_after();
-                TC_PROF(1);
-                {
-                    // q|k|v rows -> bf16 attention operands: q[r][:], k[r][:] row-major, v transposed vT[:][r]
-                    uint32_t rq[32];
-                    tmem_ld32(tT, rq);
-                    tmem_wait_ld();
-                    uint4 *qrow = reinterpret_cast<uint4 *>(sq + r * QK_LD);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        qrow[j] = make_uint4(pack_bf16x2(__uint_as_float(rq[8 * j]), __uint_as_float(rq[8 * j + 1])),
-                                             pack_bf16x2(__uint_as_float(rq[8 * j + 2]), __uint_as_float(rq[8 * j + 3])),
-                                             pack_bf16x2(__uint_as_float(rq[8 * j + 4]), __uint_as_float(rq[8 * j + 5])),
-                                             pack_bf16x2(__uint_as_float(rq[8 * j + 6]), __uint_as_float(rq[8 * j + 7])));
-                    tmem_ld32(tT + 32, rq);
-                    tmem_wait_ld();
-                    uint4 *krow = reinterpret_cast<uint4 *>(sk + r * QK_LD);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        krow[j] = make_uint4(pack_bf16x2(__uint_as_float(rq[8 * j]), __uint_as_float(rq[8 * j + 1])),
-                                             pack_bf16x2(__uint_as_float(rq[8 * j + 2]), __uint_as_float(rq[8 * j + 3])),
-                                             pack_bf16x2(__uint_as_float(rq[8 * j + 4]), __uint_as_float(rq[8 * j + 5])),
-                                             pack_bf16x2(__uint_as_float(rq[8 * j + 6]), __uint_as_float(rq[8 * j + 7])));
-                    tmem_ld32(tT + 64, rq);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int d = 0; d < D; ++d) svt[d * VT_LD + r] = __float2bfloat16_rn(__uint_as_float(rq[d]));
-                }
-                named_bar_sync(1 + t, 128);
-                TC_PROF(2);
-                // ---- attention on register fragments: this warp owns 6 of the tile's 24 (env, head) blocks ----
-                {
-                    const int g8 = lane >> 2, tq = lane & 3;
-#pragma unroll 3
-                    for (int u = wq * 6; u < wq * 6 + 6; ++u) {
-                        const int e = u >> 2, h = u & 3, row0 = e * SMAX;
-                        const int Se = max(slen[e], 1);             // envs past the batch end: keep every value finite
-                        // scores S = Q_h K_h^T (already in the log2 domain): 2 query m-tiles x 3 key n-tiles
-                        uint32_t qa[2][2], kb[3];
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-                            qa[mt][0] = *reinterpret_cast<const uint32_t *>(sq + (row0 + mt * 16 + g8) * QK_LD + h * HD + 2 * tq);
-                            qa[mt][1] = *reinterpret_cast<const uint32_t *>(sq + (row0 + mt * 16 + g8 + 8) * QK_LD + h * HD + 2 * tq);
-                        }
-#pragma unroll
-                        for (int nt = 0; nt < 3; ++nt)
-                            kb[nt] = *reinterpret_cast<const uint32_t *>(sk + (row0 + nt * 8 + g8) * QK_LD + h * HD + 2 * tq);
-                        float sc[2][3][4];
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                            for (int nt = 0; nt < 3; ++nt) {
-                                sc[mt][nt][0] = sc[mt][nt][1] = sc[mt][nt][2] = sc[mt][nt][3] = 0.f;
-                                mma_16x8x8(sc[mt][nt], qa[mt][0], qa[mt][1], kb[nt]);
-                            }
-                        // V fragments: vT[feature g8 of head h][key 8*ks + 2*tq, +1]
-                        uint32_t vb[3];
-#pragma unroll
-                        for (int ks = 0; ks < 3; ++ks)
-                            vb[ks] = *reinterpret_cast<const uint32_t *>(svt + (h * HD + g8) * VT_LD + row0 + ks * 8 + 2 * tq);
-                        // masked keys belong to another env (or to no token): their V is zeroed, not just weighted by p = 0, so a
-                        // non-finite value in one env can never reach its neighbours in the tile
-                        if (Se == SMAX) { if (tq >= 2) vb[2] = 0u; }
-                        else {
-#pragma unroll
-                            for (int ks = 0; ks < 3; ++ks) {
-                                const int k0 = ks * 8 + 2 * tq;
-                                if (k0 >= Se) vb[ks] = 0u; else if (k0 + 1 >= Se) vb[ks] &= 0x0000FFFFu;
-                            }
-                        }
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-                            // rows g8 (elements 0,1) and g8+8 (elements 2,3) of this m-tile; key of element i: 8*nt + 2*tq + (i&1).
-                            // Rows 24..31 (second half of m-tile 1) never belong to this env: nothing is computed for them.
-                            const bool lo_rows_only = mt == 1;
-                            if (Se == SMAX) {                 // full history (the common case): only keys 20..23 are masked
-                                if (tq >= 2) sc[mt][2][0] = sc[mt][2][1] = sc[mt][2][2] = sc[mt][2][3] = -INFINITY;
-                            } else {
-#pragma unroll
-                                for (int nt = 0; nt < 3; ++nt)
-#pragma unroll
-                                    for (int i = 0; i < 4; ++i)
-                                        if (nt * 8 + 2 * tq + (i & 1) >= Se) sc[mt][nt][i] = -INFINITY;
-                            }
-                            float mx0 = fmaxf(fmaxf(fmaxf(sc[mt][0][0], sc[mt][0][1]), fmaxf(sc[mt][1][0], sc[mt][1][1])),
-                                              fmaxf(sc[mt][2][0], sc[mt][2][1]));
-                            float mx1 = lo_rows_only ? 0.f
-                                                     : fmaxf(fmaxf(fmaxf(sc[mt][0][2], sc[mt][0][3]), fmaxf(sc[mt][1][2], sc[mt][1][3])),
-                                                             fmaxf(sc[mt][2][2], sc[mt][2][3]));
-                            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-                            if (!lo_rows_only) {
-                                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-                            }
-                            float sum0 = 0.f, sum1 = 0.f;
-                            uint32_t pa[3][2];
-#pragma unroll
-                            for (int nt = 0; nt < 3; ++nt) {
-                                const float p0 = fast_exp2(sc[mt][nt][0] - mx0), p1 = fast_exp2(sc[mt][nt][1] - mx0);
-                                sum0 += p0 + p1;
-                                pa[nt][0] = pack_bf16x2(p0, p1);
-                                if (!lo_rows_only) {
-                                    const float p2 = fast_exp2(sc[mt][nt][2] - mx1), p3 = fast_exp2(sc[mt][nt][3] - mx1);
-                                    sum1 += p2 + p3;
-                                    pa[nt][1] = pack_bf16x2(p2, p3);
-                                } else pa[nt][1] = 0u;
-                            }
-                            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-                            if (!lo_rows_only) {
-                                sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-                            }
-                            float o[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                            for (int ks = 0; ks < 3; ++ks) mma_16x8x8(o, pa[ks][0], pa[ks][1], vb[ks]);
-                            // rows past the env's 20 tokens belong to the next env: not stored
-                            const int q0 = mt * 16 + g8;
-                            if (q0 < SMAX) {
-                                const int rr = row0 + q0;
-                                const float i0 = fast_rcp(sum0);
-                                *reinterpret_cast<uint32_t *>(xs + (rr >> 3) * (KX / 8) * 128 + h * 128 + (rr & 7) * 16 + tq * 4) =
-                                    pack_bf16x2(o[0] * i0, o[1] * i0);
-                            }
-                            if (!lo_rows_only) {
-                                const int rr = row0 + q0 + 8;
-                                const float i1 = fast_rcp(sum1);
-                                *reinterpret_cast<uint32_t *>(xs + (rr >> 3) * (KX / 8) * 128 + h * 128 + (rr & 7) * 16 + tq * 4) =
-                                    pack_bf16x2(o[2] * i1, o[3] * i1);
-                            }
-                        }
-                    }
-                }
-                // ---- o (bf16 image in shared memory) -> out_proj ----
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(b + B_OFULL);
-                TC_PROF(3);
-                mbar_wait(b + B_OUT, par);
-                tc_fence_after();
-                TC_PROF(4);
-                {
-                    uint32_t ro[32];
-                    tmem_ld32(tT + TM_Y, ro);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int d = 0; d < D; ++d) x[d] += __uint_as_float(ro[d]);
-                }
-                layer_norm32(x, lw, lw + D);
-                // ---- FFN ----
-                store_row_tmem(tT + TM_X, x);
-                tc_fence_before();                        // also orders the tcgen05.ld of OUT before MMA2 overwrites that region
-                __syncwarp();
-                if (lane == 0) mbar_arrive(b + B_X2);
-                TC_PROF(5);
-#pragma unroll 1
-                for (int c = 0; c < NCH; ++c) {
-                    const uint32_t g = n * NCH + c, hb = g % NHB;
-                    mbar_wait(b + B_H + hb, (g / NHB) & 1u);
-                    tc_fence_after();
-                    uint32_t h0[32], h1[32], p[32];
-                    tmem_ld32(tT + hb * CH, h0);
-                    tmem_ld32(tT + hb * CH + 32, h1);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        p[j] = pack_relu_bf16x2(__uint_as_float(h0[2 * j]), __uint_as_float(h0[2 * j + 1]));
-                        p[16 + j] = pack_relu_bf16x2(__uint_as_float(h1[2 * j]), __uint_as_float(h1[2 * j + 1]));
-                    }
-                    tmem_st32(tT + hb * CH, p);
-                    tmem_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(b + B_P + hb);
-                }
-                TC_PROF(6);
-                mbar_wait(b + B_Y, par);
-                tc_fence_after();
-                {
-                    uint32_t ry[32];
-                    tmem_ld32(tT + TM_Y, ry);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int d4 = 0; d4 < D; d4 += 4) {
-                        const float4 b2 = *reinterpret_cast<const float4 *>(lw + 4 * D + d4);
-                        x[d4 + 0] += __uint_as_float(ry[d4 + 0]) + b2.x;
-                        x[d4 + 1] += __uint_as_float(ry[d4 + 1]) + b2.y;
-                        x[d4 + 2] += __uint_as_float(ry[d4 + 2]) + b2.z;
-                        x[d4 + 3] += __uint_as_float(ry[d4 + 3]) + b2.w;
-                    }
-                }
-                layer_norm32(x, lw + 2 * D, lw + 3 * D);
-                TC_PROF(7);
+            for (int l = 0; l < NL - 1; ++l) {
+                first_half(false);
+                second_half(l);
             }
-            // ---- last token -> fc_out -> 0.5*tanh + 0.5 ----
-            if (tok_ok && s_pos == S - 1) {
+            // last layer: park the residual stream of each env's last token (and which env it is); the attention parks its o row
+            if (r < ROWS && s_pos == max(S, 1) - 1) {
+                const int pr = sc.pending + t * EPT + e_loc;
+                float4 *dst = reinterpret_cast<float4 *>(xtail + pr * XT_LD);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    float acc = misc[MISC_FCB + c];
+                for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+                envtail[pr] = (env_ok && S > 0) ? env : -1;
+            }
+            first_half(true);
+            sc.pending += kTiles * EPT;
+            if (sc.flush_after_group(it, n_it)) {
+                // ---- tail pass: second half of the last layer on the parked rows; thread r of tile t takes parked row t*128 + r ----
+                asm volatile("bar.sync %0, %1;" ::"r"(kTiles + 1), "r"(kTiles * 128) : "memory");     // all parked rows written
+                const int pr = t * 128 + r;
+                const int penv = pr < sc.pending ? envtail[pr] : -1;
+                {
+                    const float4 *src = reinterpret_cast<const float4 *>(xtail + pr * XT_LD);
 #pragma unroll
-                    for (int d = 0; d < D; ++d) acc = fmaf(x[d], misc[MISC_FCW + c * D + d], acc);
-                    a.d_out[(size_t)env * 3 + c] = tanhf(acc) * 0.5f + 0.5f;
+                    for (int j = 0; j < 8; ++j) { const float4 v = src[j]; x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
                 }
+                second_half(NL - 1);
+                // ---- fc_out -> 0.5*tanh + 0.5 ----
+                if (penv >= 0) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float acc = misc[MISC_FCB + c];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) acc = fmaf(x[d], misc[MISC_FCW + c * D + d], acc);
+                        a.d_out[(size_t)penv * 3 + c] = tanhf(acc) * 0.5f + 0.5f;
+                    }
+                }
+                // the parked rows may be overwritten only after every thread has read its own
+                asm volatile("bar.sync %0, %1;" ::"r"(kTiles + 1), "r"(kTiles * 128) : "memory");
+                sc.pending = 0;
             }
         }
         TC_PROF_FLUSH;
