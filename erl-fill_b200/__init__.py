@@ -20,7 +20,10 @@ def __getattr__(name):
     if name in ("VecTD3", "VecSAC"):
         from . import td3sac
         return getattr(td3sac, name)
-    if name in ("init", "td3sac", "nets", "ddpg", "agents", "envs"):
+    if name in ("DDPGAgent", "EmotionModule", "EmotionModuleNone", "TD3Agent", "SACAgent", "reset_actor_scaling"):
+        from . import dropin
+        return getattr(dropin, name)
+    if name in ("init", "td3sac", "nets", "ddpg", "agents", "envs", "dropin", "loops"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -100,6 +100,11 @@ class VecERDDPG:
         self.episodes += done.sum()
         return next_state, reward, done
 
+    def rollout_eval_step(self):
+        """One evaluation step (experiment_runner.py:545-556: `act(state, add_noise=False)` -> `env.step`).  The test
+        loop never calls `emotion.update`, so every env keeps the emotion its history gave at the end of training."""
+        return self.env.step(self.act(add_noise=False))
+
     def learn(self, allreduce=None):
         """R2 + U1-U5 on a fresh minibatch; returns the device report [critic_loss, actor_loss, critic_lr, actor_lr]."""
         if len(self.memory) < self.batch_size:

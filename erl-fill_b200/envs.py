@@ -78,6 +78,18 @@ class VecFillEnv:
                           L.ptr(self.episode_counter), L.ptr(self.ring_len), L.ptr(self.ring_head),
                           L.ptr(self.ring), L.ptr(self.obs))
 
+    @property
+    def cond_id(self):
+        """int32[N]: the condition each env runs (explicit table, or round-robin on the global env id)."""
+        if self._d_cond_id is not None:
+            return self._d_cond_id
+        return ((torch.arange(self.n_env, device=self.device, dtype=torch.int64) + self.env_id_base) % len(self.conditions)).to(torch.int32)
+
+    @property
+    def target_weight_per_env(self):
+        tw = torch.tensor([float(c["target_weight"]) for c in self.conditions], dtype=torch.float64, device=self.device)
+        return tw[self.cond_id.long()]
+
     @staticmethod
     def _noise(u=None, reset_u=None):
         if u is None and reset_u is None:

@@ -58,3 +58,13 @@ def er_ddpg_state_dicts(bounds, seed=None, with_transformer=True):
     _critic_sd()
     trans = _transformer_sd() if with_transformer else None
     return actor, critic, trans
+
+
+def transformer_keys():
+    """EmotionTransformer.state_dict() keys in torch's order (own parameter, then children in registration order)."""
+    per_layer = ["self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight", "self_attn.out_proj.bias",
+                 "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias", "norm1.weight", "norm1.bias",
+                 "norm2.weight", "norm2.bias"]
+    keys = ["positional_encoding", "embedding.weight", "embedding.bias"]
+    keys += [f"transformer_encoder.layers.{l}.{k}" for l in range(4) for k in per_layer]
+    return keys + ["fc_out.weight", "fc_out.bias"]

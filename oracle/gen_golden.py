@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (container only).
 
-Run from the repo root:   python oracle/gen_golden.py [sim] [env] [emotion] [nets] [learn] [td3sac]
+Run from the repo root:   python oracle/gen_golden.py [sim] [env] [emotion] [nets] [learn] [td3sac] [loop]
 
 The reference (/root/reference) is imported through oracle/ref_shim.py (pymodbus stub +
 frozen clock).  All randomness is CPython `random` seeded per case,
@@ -8,6 +8,7 @@ so a test can regenerate the identical Mersenne-Twister stream with `random.Rand
 and does not need the reference at run time; the fixtures hold only inputs, seeds and the
 reference's outputs.  Fixture provenance is recorded inside each file (`meta`).
 """
+import collections
 import contextlib
 import io
 import json
@@ -543,10 +544,112 @@ def gen_td3sac():
     np.savez_compressed(os.path.join(GOLD, "td3sac_golden.npz"), **out)
     print("td3:", res if False else out["td3.res"].tolist(), "sac:", out["sac.res"].tolist())
 
+# ----------------------------------------------------------------------------------------
+def gen_loop():
+    """Config-1 anchor: the reference's OWN train_ddpg (ddpg_agent.py:579-732) driving its own env and agent for
+    3 short episodes, eval-mode networks, with every call across the env/agent boundary tapped: what the caller
+    passed and what came back.  tests/test_dropin_gpu.py replays the same call sequence through the drop-ins."""
+    import tempfile
+    import logging
+    import torch
+    random.seed(0); np.random.seed(0)
+    env, agent = _build_agent(0)
+    import ddpg_agent as D
+    for m in (agent.actor, agent.actor_target, agent.critic, agent.critic_target, agent.emotion.transformer):
+        m.eval()
+    torch.backends.mha.set_fastpath_enabled(False)
+    agent.batch_size = 16
+    agent.memory.capacity = 30          # small, so PrioritizedReplayBuffer.add's overwrite branch (:222-226) runs too
+    out = {}                            # initial weights = nets_golden.npz's actor./critic./trans. (same _build_agent(0))
+    calls = []                          # (kind, payload) in call order
+    rec = collections.defaultdict(list)
+
+    def tap(obj, name, kind, pack):
+        orig = getattr(obj, name)
+
+        def wrapped(*a, **k):
+            r = orig(*a, **k)
+            calls.append(kind)
+            for key, val in pack(a, k, r).items():
+                rec[kind + "." + key].append(np.asarray(val))
+            return r
+        setattr(obj, name, wrapped)
+
+    idx_log = []
+    orig_choice = np.random.choice
+
+    def tap_choice(n, size, p=None):
+        r = orig_choice(n, size, p=p)
+        idx_log.append(np.array(r))
+        return r
+
+    tap(env, "reset", "reset", lambda a, k, r: {"state": r})
+    tap(agent, "act", "act", lambda a, k, r: {"state": a[0], "action": r})
+    tap(env, "step", "step", lambda a, k, r: {"action": a[0], "next_state": r[0], "reward": np.float64(r[1]), "done": r[2],
+                                               "final_weight": np.float64(r[3]["final_weight"]), "total_time": np.float64(r[3]["total_time"])})
+    tap(agent.emotion, "update", "update", lambda a, k, r: {"reward": np.float64(a[0]), "movement": a[1], "emotion": r})
+    def _slot(a):                       # the slot add() just wrote (the tuple holding this call's state object)
+        return [j for j, tr in enumerate(agent.memory.buffer) if tr[0] is a[0]][-1]
+
+    # reward_f32: under numpy 2 some reward branches of MutiConditionEnv.step return np.float32 (weak scalar promotion); the
+    # type flows into the NaN td_error and its priority, and float32(1e-4) < float64(1e-4) decides np.argmin when full
+    tap(agent, "remember", "remember", lambda a, k, r: {"state": a[0], "action": a[1], "reward": np.float64(a[2]), "next_state": a[3],
+                                                        "reward_f32": isinstance(a[2], np.float32),
+                                                        "done": a[4], "slot": _slot(a), "stored_emotion": agent.memory.buffer[_slot(a)][5],
+                                                        "stored_norm_action": agent.memory.buffer[_slot(a)][1],
+                                                        "len": len(agent.memory)})
+    tap(agent, "learn", "learn", lambda a, k, r: {"ran": r is not None,
+                                                  "critic_loss": np.float64(r["critic_loss"]) if r else np.nan,
+                                                  "actor_loss": np.float64(r["actor_loss"]) if r else np.nan,
+                                                  "critic_lr": agent.critic_optim.param_groups[0]["lr"],
+                                                  "actor_lr": agent.actor_optim.param_groups[0]["lr"]})
+    np.random.choice = tap_choice
+    cwd = os.getcwd()
+    try:
+        with tempfile.TemporaryDirectory() as td, _quiet():
+            os.chdir(td)
+            lg = logging.getLogger("gen_loop"); lg.addHandler(logging.NullHandler()); lg.propagate = False
+            import tqdm as _tq
+            D.tqdm = lambda it, **k: it
+            rewards = D.train_ddpg(env, agent, episodes=3, max_steps=12, log_prefix="gen_loop", logger=lg)
+    finally:
+        os.chdir(cwd)
+        np.random.choice = orig_choice
+    out["calls"] = np.array(calls)
+    for k, v in rec.items():
+        out[k] = np.stack(v)
+    out["learn.idx"] = np.stack(idx_log)
+    out["episode_rewards"] = np.array(rewards, np.float64)
+    out.update(_sd(agent.actor, "actor_end."))
+    out.update(_sd(agent.critic, "critic_end."))
+    out.update(_sd(agent.actor_target, "actor_target_end."))
+    out.update(_sd(agent.critic_target, "critic_target_end."))
+    out["train_step_end"] = agent.train_step
+    # the checkpoint the reference writes for this agent (N2): keys and tensors, flattened
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "ref.pth")
+        agent.save(path)
+        ck = torch.load(path, weights_only=False)
+    out["ckpt_keys"] = np.array(sorted(ck.keys()))
+    for name in ("actor", "critic", "actor_target", "critic_target", "emotion_transformer"):
+        out["ckpt_order." + name] = np.array(list(ck[name].keys()))
+    for name in ("actor_optim", "critic_optim"):
+        st = ck[name]["state"]
+        out[f"ckpt.{name}.n"] = len(st)
+        out[f"ckpt.{name}.step"] = np.array([float(st[i]["step"]) for i in sorted(st)])
+        for i in sorted(st):
+            out[f"ckpt.{name}.exp_avg.{i}"] = st[i]["exp_avg"].numpy()
+            out[f"ckpt.{name}.exp_avg_sq.{i}"] = st[i]["exp_avg_sq"].numpy()
+        out[f"ckpt.{name}.lr"] = ck[name]["param_groups"][0]["lr"]
+    out["meta"] = _meta("config-1 anchor: reference train_ddpg x3 episodes x12 steps, eval-mode nets, B=16, capacity 30, "
+                        "seeds random/np/torch = 0; plus the reference's save() checkpoint layout")
+    np.savez_compressed(os.path.join(GOLD, "loop_golden.npz"), **out)
+    print("loop: calls", len(calls), "learns", int(np.sum(out["learn.ran"])), "rewards", rewards)
+
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["sim", "env", "emotion"]
     os.chdir("/tmp")
     for w in which:
-        {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion, "nets": gen_nets, "learn": gen_learn, "td3sac": gen_td3sac}[w]()
+        {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion, "nets": gen_nets, "learn": gen_learn, "td3sac": gen_td3sac, "loop": gen_loop}[w]()
