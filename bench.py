@@ -28,11 +28,23 @@ if ROOT not in sys.path:
 
 ENV_STEP_BYTES = 192            # algorithmic bytes per env-step
 TRANSFORMER_FLOP = 21.83e6      # per env per call at S=20
+# what emotion_forward_tc_kernel executes: layers 0-2 in full (3 x 5,457,920), layer 3 q|k|v + attention for 20 tokens
+# (174,080) and out_proj + FFN for the last token only (264,192)
+TRANSFORMER_FLOP_EXECUTED = 3 * 5457920 + 174080 + 264192
 UPDATE_FLOP_PER_SAMPLE = 1.43e6
 L2_FLUSH_BYTES = 256 << 20      # > 126 MB L2
 # warp-instructions one env-step of the `sim` workload issues in env_sim_warp_kernel + env_finish_kernel
 # (ncu smsp__inst_executed.sum / n_env, profiles/r01_env_step_4096_pid.txt)
 SIM_WARP_INSTR_PER_ENV_STEP = {"pid": 3959.3 + 20.3}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of exactly these configurations
+# (cold L2, one launch): {(workload, envs per GPU): (bytes, summary file)}; any other configuration reports traffic null
+NCU_TRAFFIC = {("sim", 4096): (208640 + 326656, "profiles/r01b_env_sim_warp.txt + profiles/r01_env_step_4096_pid.txt (finish kernel)"),
+               ("rollout", 65536): (17171968, "profiles/r01b_emotion_tc.txt")}
+
+
+def _traffic(workload, n):
+    t = NCU_TRAFFIC.get((workload, n))
+    return (t[0], t[1]) if t else (None, None)
 
 
 def _peaks():
@@ -220,7 +232,10 @@ def wl_sim(args, rank, world, device, timer):
                 "d2h_bytes_per_step": ns_host.numel() * 4 + r_host.numel() * 4 + d_host.numel()},
         "gpu_launches": launches * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"], "kernel": kname,
+                     "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": _traffic("sim", n)[0] if (args.actions == "pid" and args.sim_mode != "thread") else None,
+                     "traffic_source": _traffic("sim", n)[1] if (args.actions == "pid" and args.sim_mode != "thread") else None,
+                     "peak_source": peaks["source"], "kernel": kname,
                      "algorithmic_bytes_per_env_step": ENV_STEP_BYTES,
                      "note": "the simulator is instruction-issue bound (about %d serial ticks of integer/Philox work per "
                              "env-step against 192 B of HBM traffic), not HBM bound: see issue_roofline"
@@ -286,11 +301,17 @@ def wl_rollout(args, rank, world, device, timer):
                 "d2h_bytes_per_step": n * 13},
         "gpu_launches": 8 * args.steps,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                     "frac": achieved / peaks["bf16_tflops_sustained"],
+                     "traffic": _traffic("rollout", n)[0] if agent.emotion_precision == "bf16" else None,
+                     "traffic_source": _traffic("rollout", n)[1] if agent.emotion_precision == "bf16" else None,
                      "peak_source": peaks["source"] + " (sustained)",
                      "kernel": "emotion_forward_tc_kernel" if agent.emotion_precision == "bf16" else "emotion_forward_kernel",
                      "kernel_ms": tf_ms,
-                     "share_of_step": tf_ms / (total_ms / args.steps), "algorithmic_flop_per_env": TRANSFORMER_FLOP},
+                     "share_of_step": tf_ms / (total_ms / args.steps), "algorithmic_flop_per_env": TRANSFORMER_FLOP,
+                     "executed_flop_per_env": TRANSFORMER_FLOP_EXECUTED,
+                     "note": "achieved = the reference's algorithmic FLOPs / time; the kernel executes 16.81 of the 21.83 MFLOP "
+                             "(in the last layer only the last token's out_proj/FFN feed fc_out; the other 19 rows are skipped), "
+                             "so the tensor pipe itself runs at achieved x %.2f" % (TRANSFORMER_FLOP_EXECUTED / TRANSFORMER_FLOP)},
     }
 
 
