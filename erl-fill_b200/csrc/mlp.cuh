@@ -28,17 +28,15 @@ static __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-static __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float *__restrict__ A, int sam, int sak,
-                                                   const float *__restrict__ B, int sbk, int sbn, float *__restrict__ C,
-                                                   int ldc, const float *__restrict__ bias, int act, int k_per_split,
-                                                   size_t split_stride) {
+// one 64 x 64 output tile at (m0, n0) over k in [kbeg, kend), written to Cz
+static __device__ __forceinline__ void gemm_tile(int M, int N, const float *__restrict__ A, int sam, int sak,
+                                                 const float *__restrict__ B, int sbk, int sbn, float *__restrict__ Cz, int ldc,
+                                                 const float *__restrict__ bias, int act, int kbeg, int kend, int m0, int n0) {
     __shared__ __align__(16) float As[BK][LDS_T];
     __shared__ __align__(16) float Bs[BK][LDS_T];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;      // 2 x 4 warps, each a 32 x 16 tile = 2 (m16) x 2 (n8) MMA tiles
     const int g = lane >> 2, t = lane & 3;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
     float acc[2][2][4] = {};
     // per-thread tile coordinates (the fastest-varying index follows the unit-stride dimension for coalescing)
     int am[4], ak[4], bn[4], bk[4];
@@ -90,7 +88,6 @@ static __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, c
         }
         __syncthreads();
     }
-    float *Cz = C + (size_t)blockIdx.z * split_stride;
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -105,6 +102,47 @@ static __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, c
                 else if (act == ACT_LEAKY) v = v > 0.f ? v : 0.1f * v;
                 Cz[(size_t)gm * ldc + gn] = v;
             }
+}
+
+static __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float *__restrict__ A, int sam, int sak,
+                                                   const float *__restrict__ B, int sbk, int sbn, float *__restrict__ C,
+                                                   int ldc, const float *__restrict__ bias, int act, int k_per_split,
+                                                   size_t split_stride) {
+    const int kbeg = blockIdx.z * k_per_split;
+    gemm_tile(M, N, A, sam, sak, B, sbk, sbn, C + (size_t)blockIdx.z * split_stride, ldc, bias, act, kbeg, min(K, kbeg + k_per_split),
+              blockIdx.y * BM, blockIdx.x * BN);
+}
+
+// ---- grouped weight gradients: up to 4 GEMMs dW_i[N_i][K_i] = dZ_i^T[N_i][Bt] X_i[Bt][K_i] in ONE launch ------------
+// Every task is cut into 64 x 64 tiles x `splits` slices of the batch rows; slice s of task i goes to part_i + s*N_i*K_i
+// and group_reduce_kernel adds the slices in index order (deterministic).
+struct WgTask { const float *dZ, *X; float *part; int ldz, ldx, N, K, tiles_k, tiles, first_block; };
+struct WgArgs { WgTask t[4]; int ntask, Bt, splits, kps; };
+static __global__ void __launch_bounds__(256) wgrad_group_kernel(const WgArgs a) {
+    int ti = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (i < a.ntask && (int)blockIdx.x >= a.t[i].first_block) ti = i;
+    const WgTask &k = a.t[ti];
+    const int local = blockIdx.x - k.first_block, tile = local % k.tiles, split = local / k.tiles;
+    const int kbeg = split * a.kps;
+    gemm_tile(k.N, k.K, k.dZ, 1, k.ldz, k.X, k.ldx, 1, k.part + (size_t)split * k.N * k.K, k.K, nullptr, ACT_NONE, kbeg,
+              min(a.Bt, kbeg + a.kps), (tile / k.tiles_k) * BM, (tile % k.tiles_k) * BN);
+}
+// out_i[j] = sum_s part_i[s*stride_i + j] for up to 12 segments in one launch (256 elements per block)
+struct RedSeg { const float *part; float *out; int n, splits, stride, first_block; };
+struct RedArgs { RedSeg s[12]; int nseg; };
+static __global__ void __launch_bounds__(256) group_reduce_kernel(const RedArgs a) {
+    int si = 0;
+#pragma unroll
+    for (int i = 1; i < 12; ++i)
+        if (i < a.nseg && (int)blockIdx.x >= a.s[i].first_block) si = i;
+    const RedSeg &g = a.s[si];
+    const int j = (blockIdx.x - g.first_block) * 256 + threadIdx.x;
+    if (j >= g.n) return;
+    float acc = 0.f;
+    for (int z = 0; z < g.splits; ++z) acc += g.part[(size_t)z * g.stride + j];
+    g.out[j] = acc;
 }
 
 // sum split-K partials: out[i] = sum_z part[z*stride + i]

@@ -20,9 +20,11 @@
 
 #include "common.cuh"
 #include "mlp.cuh"
+#include "fused_mlp.cuh"
 
 namespace erlfill {
 using namespace mlp;
+using namespace fused;
 
 // ---- flat layouts (parameters() order) -------------------------------------------------------
 namespace AO { constexpr int EW = 0, W1 = 30, B1 = 670, W2 = 798, B2 = 17182, W3 = 17310, B3 = 25502, W4 = 25566, B4 = 26206, TOTAL = 26216; }
@@ -48,105 +50,6 @@ __global__ void __launch_bounds__(1024) emotion_stats_kernel(int B, const float 
     }
 }
 
-// critic input rows [B][16] = [state(2) | action(10) | emotion standardised(3) | 0]
-//   mode 0: (s, batch action, e)   mode 1: (s', actions_ext, 0)  [target]   mode 2: (s, actions_ext, e)
-__global__ void build_x0_kernel(int B, int mode, const float *batch, const float *actions_ext, const float *stats, float *x0) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= B * 16) return;
-    const int r = g >> 4, c = g & 15;
-    const float *row = batch + (size_t)r * ERLFILL_REC;
-    float v = 0.f;
-    if (c < 2) v = mode == 1 ? row[13 + c] : row[c];
-    else if (c < 12) v = mode == 0 ? row[c] : actions_ext[(size_t)r * 10 + (c - 2)];
-    else if (c < 15) v = mode == 1 ? 0.f : (row[16 + (c - 12)] - stats[c - 12]) / (stats[3 + (c - 12)] + 1e-6f);
-    x0[g] = v;
-}
-// actor input rows [B][8] = [state | emotion | 0]; mode 1: (s', next_emotion broadcast)
-__global__ void build_xa_kernel(int B, int mode, const float *batch, const float *next_emotion, float *xa) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= B * 8) return;
-    const int r = g >> 3, c = g & 7;
-    const float *row = batch + (size_t)r * ERLFILL_REC;
-    float v = 0.f;
-    if (c < 2) v = mode == 1 ? row[13 + c] : row[c];
-    else if (c < 5) v = mode == 1 ? next_emotion[c - 2] : row[16 + (c - 2)];
-    xa[g] = v;
-}
-
-// LayerNorm(256) + activation, one warp per row.  z (in: x W^T + b) is overwritten with xhat.
-__global__ void __launch_bounds__(256) ln_act_fwd_kernel(int B, float *z, const float *gamma, const float *beta, int act,
-                                                         float *h, float *rstd_out) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), l = threadIdx.x & 31;
-    if (row >= B) return;
-    float v[8];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { v[i] = z[(size_t)row * 256 + l + 32 * i]; s += v[i]; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * (1.0f / 256.0f);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q * (1.0f / 256.0f) + 1e-5f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = l + 32 * i;
-        const float xh = (v[i] - mean) * rstd;
-        float y = xh * gamma[c] + beta[c];
-        y = act == ACT_LEAKY ? (y > 0.f ? y : 0.1f * y) : fmaxf(y, 0.f);
-        z[(size_t)row * 256 + c] = xh;
-        h[(size_t)row * 256 + c] = y;
-    }
-    if (l == 0) rstd_out[row] = rstd;
-}
-
-// backward of (LayerNorm + activation): dh -> dy (in place, for the gamma/beta column sums) and dz.
-__global__ void __launch_bounds__(256) ln_act_bwd_kernel(int B, float *dh, const float *xhat, const float *rstd,
-                                                         const float *gamma, const float *beta, int act, float *dz) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), l = threadIdx.x & 31;
-    if (row >= B) return;
-    float dxh[8], xh[8];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = l + 32 * i;
-        xh[i] = xhat[(size_t)row * 256 + c];
-        const float y = xh[i] * gamma[c] + beta[c];
-        float g = dh[(size_t)row * 256 + c];
-        g *= act == ACT_LEAKY ? (y > 0.f ? 1.f : 0.1f) : (y > 0.f ? 1.f : 0.f);
-        dh[(size_t)row * 256 + c] = g;                         // dy
-        dxh[i] = g * gamma[c];
-        s1 += dxh[i];
-        s2 = fmaf(dxh[i], xh[i], s2);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-    const float r = rstd[row], m1 = s1 * (1.0f / 256.0f), m2 = s2 * (1.0f / 256.0f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dz[(size_t)row * 256 + l + 32 * i] = r * (dxh[i] - m1 - xh[i] * m2);
-}
-
-// g *= (h > 0) for ReLU layers without LayerNorm
-__global__ void leaky_bwd_kernel(size_t n, float *g, const float *h) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) g[i] = h[i] > 0.f ? g[i] : 0.1f * g[i];
-}
-
-// critic head: q = clamp(h3 . w10 + b10, +-1e6), one warp per row
-__global__ void __launch_bounds__(256) critic_head_kernel(int B, const float *h3, const float *w10, const float *b10, float *q) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), l = threadIdx.x & 31;
-    if (row >= B) return;
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) s = fmaf(h3[(size_t)row * 128 + l + 32 * i], w10[l + 32 * i], s);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (l == 0) q[row] = fminf(fmaxf(s + b10[0], -1e6f), 1e6f);
-}
-
 // y = 0.01 r + (1-d) gamma Q'; SmoothL1(beta=1) mean loss and dq = dL/dq; loss via deterministic block reduce
 __global__ void __launch_bounds__(1024) critic_loss_kernel(int B, const float *batch, const float *q, const float *tq, float gamma,
                                                            float *dq, float *loss_out) {
@@ -163,85 +66,6 @@ __global__ void __launch_bounds__(1024) critic_loss_kernel(int B, const float *b
     }
     const float t = block_sum(ls, scratch);
     if (threadIdx.x == 0) loss_out[0] = t / (float)B;
-}
-
-// dh3[r][c] = dq[r] * w10[c] * (h3 > 0)    and  dW10 / db10 come from colsum(dq*h3) / sum(dq)
-__global__ void critic_head_bwd_kernel(int B, const float *dq, const float *w10, const float *h3, float *dh3) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= B * 128) return;
-    const int r = g >> 7, c = g & 127;
-    dh3[g] = h3[g] > 0.f ? dq[r] * w10[c] : 0.f;
-}
-// ---- actor head: z4 -> physical action, and its backward ---------------------------------------
-__global__ void actor_head_fwd_kernel(int B, const float *z4, const float *xa, const float *ew, const float *scale,
-                                      const float *offset, float *out, float *aux /*[B][10][3]: base, alpha*sflip*mod2.., see bwd*/) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= B * 10) return;
-    const int r = g / 10, c = g % 10;
-    const float z = z4[g];
-    const float base = z / (1.0f + fabsf(z));
-    const float cur = xa[r * 8 + 2], cons = xa[r * 8 + 3], anx = xa[r * 8 + 4];
-    float e = cur * ew[c];
-    e = fmaf(cons, ew[10 + c], e);
-    e = fmaf(anx, ew[20 + c], e);
-    const float raw = tanhf(e * 1.5f);
-    float alpha = 0.1f + 0.9f * anx;
-    alpha *= (1.0f - 0.5f * cons);
-    alpha *= (1.0f + 0.5f * cur);
-    alpha = fminf(fmaxf(alpha, 0.01f), 1.0f);
-    const float om = 1.0f - fabsf(base);
-    const float sf = base > 0.f ? -1.0f : (base < 0.f ? 1.0f : 0.0f);
-    out[g] = (base + alpha * raw * sf * (om * om)) * scale[c] + offset[c];
-    if (aux) { aux[(size_t)g * 3 + 0] = base; aux[(size_t)g * 3 + 1] = raw; aux[(size_t)g * 3 + 2] = alpha; }
-}
-
-// d(out) -> dz4, and the per-row contribution to d(emotion_weights): dew_part[r][k][c] folded by colsum later.
-// dout already contains the critic path; the diversity term -0.03*mean_rows(std_unbiased(out,dim=1)) is added here.
-__global__ void actor_head_bwd_kernel(int B, const float *dout_critic, const float *out, const float *aux, const float *xa,
-                                      const float *scale, const float *z4, float *dz4, float *draw_e /*[B][10]*/) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= B) return;
-    float o[10], mean = 0.f;
-#pragma unroll
-    for (int c = 0; c < 10; ++c) { o[c] = out[(size_t)r * 10 + c]; mean += o[c]; }
-    mean *= 0.1f;
-    float var = 0.f;
-#pragma unroll
-    for (int c = 0; c < 10; ++c) { const float d = o[c] - mean; var = fmaf(d, d, var); }
-    const float sd = sqrtf(var / 9.0f);
-#pragma unroll
-    for (int c = 0; c < 10; ++c) {
-        const size_t g = (size_t)r * 10 + c;
-        float go = dout_critic[g];
-        go += (-0.03f / (float)B) * (o[c] - mean) / (9.0f * sd);                      // d std / d o_c
-        const float gr = go * scale[c];                                                   // d raw_action
-        const float base = aux[g * 3 + 0], raw = aux[g * 3 + 1], alpha = aux[g * 3 + 2];
-        const float om = 1.0f - fabsf(base);
-        const float sf = base > 0.f ? -1.0f : (base < 0.f ? 1.0f : 0.0f);
-        // d raw_action / d base = 1 + alpha*raw*sf * 2*om*(-sign(base)) = 1 + 2*alpha*raw*om*sf*sf (sign has zero grad)
-        const float dbase = gr * (1.0f + 2.0f * alpha * raw * om * (sf * sf));
-        const float z = z4[g], den = 1.0f + fabsf(z);
-        dz4[g] = dbase / (den * den);                                                     // softsign'
-        // d raw_action / d (e @ W_e)[c] = alpha*sf*om^2 * (1 - raw^2) * 1.5
-        draw_e[g] = gr * alpha * sf * (om * om) * (1.0f - raw * raw) * 1.5f;
-    }
-}
-// dEW[k][c] = sum_r xa[r][2+k] * draw_e[r][c]   (30 outputs): per-slice partials part[slice][30], summed by splitk_reduce_kernel
-__global__ void __launch_bounds__(256) ew_grad_part_kernel(int B, const float *xa, const float *draw_e, float *part) {
-    __shared__ float red[8][32];
-    const int o = threadIdx.x & 31, rl = threadIdx.x >> 5, k = o / 10, c = o % 10;
-    const int per = (B + kColSplits - 1) / kColSplits, r0 = blockIdx.x * per, r1 = min(B, r0 + per);
-    float s = 0.f;
-    if (o < 30)
-        for (int r = r0 + rl; r < r1; r += 8) s = fmaf(xa[r * 8 + 2 + k], draw_e[(size_t)r * 10 + c], s);
-    red[rl][o] = s;
-    __syncthreads();
-    if (rl == 0 && o < 30) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][o];
-        part[blockIdx.x * 30 + o] = t;
-    }
 }
 
 // actor loss value (reported): -mean(q2) - 0.03*mean_rows(std) + 1e-4 * sum_t ||theta_t||
@@ -315,11 +139,6 @@ __global__ void adam_soft_kernel(int n, float *p, float *pt, float *m, float *v,
     if (pt) pt[i] = tau * pi + (1.0f - tau) * pt[i];
 }
 
-// d(out)[r][c] = dx0[r][2 + c]
-__global__ void slice_action_grad_kernel(int B, const float *g16, float *d) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B * 10) d[i] = g16[(i / 10) * 16 + 2 + (i % 10)];
-}
 __global__ void soft_update_kernel(int n, const float *p, float *pt, float tau) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) pt[i] = tau * p[i] + (1.0f - tau) * pt[i];
@@ -328,16 +147,437 @@ __global__ void report_kernel(const float *scal, float *out) {
     out[0] = scal[4]; out[1] = scal[5]; out[2] = scal[2]; out[3] = scal[3];
 }
 
+// ---- fused row-tile kernels (fused_mlp.cuh): one CTA = 32 minibatch rows through a whole layer chain ------------------
+// shared memory: bufA | bufB (activation tiles) | two weight stages | misc (actor input tile, row statistics)
+constexpr int kMisc = 512;
+constexpr int kFusedSmem = (2 * TILE + 2 * WST + kMisc) * 4;
+// per-CTA column partial sums of the critic backward: [db0 | dgamma1 | dbeta1] [db4 | dgamma2 | dbeta2] [db8 | dW10 | db10]
+constexpr int kCPartA = 0, kCPartB = 768, kCPartC = 1536, kCPart = 1800;
+// per-CTA partials of the actor backward: dEW(30, padded 32) | db4(10, padded 16) | db3(64) | db2(128) | db1(128)
+constexpr int kAPartEW = 0, kAPartB4 = 32, kAPartB3 = 48, kAPartB2 = 112, kAPartB1 = 240, kAPart = 368;
+
+// LayerNorm(256) + activation on the tile: z_s (pre-LN rows) becomes h in place; xhat / rstd / h also go to global
+// memory (what the backward needs) when the pointers are set.  Warp w owns rows 4w .. 4w+3.
+__device__ __forceinline__ void ln_act_tile(float *z_s, const float *gamma, const float *beta, int act, int row0, int B,
+                                            float *xhat_g, float *rstd_g, float *h_g) {
+    const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll 1
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = warp * 4 + rr, gr = row0 + r;
+        float v[8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i] = z_s[r * LDA + l + 32 * i]; s += v[i]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / 256.0f);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.0f / 256.0f) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = l + 32 * i;
+            const float xh = (v[i] - mean) * rstd;
+            float y = xh * gamma[c] + beta[c];
+            y = act == ACT_LEAKY ? (y > 0.f ? y : 0.1f * y) : fmaxf(y, 0.f);
+            z_s[r * LDA + c] = y;
+            if (gr < B) {
+                if (xhat_g) xhat_g[(size_t)gr * 256 + c] = xh;
+                if (h_g) h_g[(size_t)gr * 256 + c] = y;
+            }
+        }
+        if (l == 0 && rstd_g && gr < B) rstd_g[gr] = rstd;
+    }
+}
+
+// Critic.forward for the CTA's rows (ddpg_agent.py:163-183).  The input row [state(2) | action(10) | emotion standardised(3) | 0]
+// is assembled here:  mode 0: (s, stored normalised action, e)   mode 1: (s', actions_ext, 0) [target]   mode 2: (s, actions_ext, e)
+struct CriticFwdArgs {
+    int B, mode, save;
+    const float *batch, *actions_ext, *stats, *P;
+    float *x0, *xhat1, *h1, *rstd1, *xhat2, *h2, *rstd2, *h3, *q;
+};
+__global__ void __launch_bounds__(NTHR) critic_fwd_kernel(const CriticFwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float *bufA = sm, *bufB = sm + TILE, *wst = sm + 2 * TILE;
+    const int tid = threadIdx.x, row0 = blockIdx.x * TM, B = a.B;
+    for (int e = tid; e < TM * 16; e += NTHR) {
+        const int r = e >> 4, c = e & 15, gr = row0 + r;
+        float v = 0.f;
+        if (gr < B) {
+            const float *row = a.batch + (size_t)gr * ERLFILL_REC;
+            if (c < 2) v = a.mode == 1 ? row[13 + c] : row[c];
+            else if (c < 12) v = a.mode == 0 ? row[c] : a.actions_ext[(size_t)gr * 10 + (c - 2)];
+            else if (c < 15) v = a.mode == 1 ? 0.f : (row[16 + (c - 12)] - a.stats[c - 12]) / (a.stats[3 + (c - 12)] + 1e-6f);
+            if (a.save) a.x0[(size_t)gr * 16 + c] = v;
+        }
+        bufA[r * LDA + c] = v;
+    }
+    const float *P = a.P;
+    {   // Linear(15, 256) -> LayerNorm -> LeakyReLU(0.1)
+        float acc[2][4][4];
+        dense<16, 256, false>(acc, bufA, P + CO::W0, 15, 256, 15, wst, 0);
+        for_each_out<256>(acc, 256, [&](int r, int c, float v) { bufB[r * LDA + c] = v + P[CO::B0 + c]; });
+    }
+    __syncthreads();
+    ln_act_tile(bufB, P + CO::G1, P + CO::BE1, ACT_LEAKY, row0, B, a.save ? a.xhat1 : nullptr, a.save ? a.rstd1 : nullptr, a.save ? a.h1 : nullptr);
+    {   // Linear(256, 256) -> LayerNorm -> ReLU
+        float acc[2][4][4];
+        dense<256, 256, false>(acc, bufB, P + CO::W4, 256, 256, 256, wst, 4);
+        for_each_out<256>(acc, 256, [&](int r, int c, float v) { bufA[r * LDA + c] = v + P[CO::B4 + c]; });
+    }
+    __syncthreads();
+    ln_act_tile(bufA, P + CO::G2, P + CO::BE2, ACT_RELU, row0, B, a.save ? a.xhat2 : nullptr, a.save ? a.rstd2 : nullptr, a.save ? a.h2 : nullptr);
+    {   // Linear(256, 128) -> ReLU
+        float acc[2][2][4];
+        dense<256, 128, false>(acc, bufA, P + CO::W8, 256, 128, 256, wst, 4);
+        for_each_out<128>(acc, 128, [&](int r, int c, float v) {
+            v = fmaxf(v + P[CO::B8 + c], 0.f);
+            bufB[r * LDA + c] = v;
+            if (a.save && row0 + r < B) a.h3[(size_t)(row0 + r) * 128 + c] = v;
+        });
+    }
+    __syncthreads();
+    // Linear(128, 1), clamp +-1e6: warp w owns rows 4w .. 4w+3
+    const int warp = tid >> 5, l = tid & 31;
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = warp * 4 + rr;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s = fmaf(bufB[r * LDA + l + 32 * i], P[CO::W10 + l + 32 * i], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (l == 0 && row0 + r < B) a.q[row0 + r] = fminf(fmaxf(s + P[CO::B10], -1e6f), 1e6f);
+    }
+}
+
+// Actor.forward for the CTA's rows (ddpg_agent.py:73-122) -> physical-unit actions.  Input row [state | emotion | 0]; mode 1:
+// (s', next_emotion broadcast) for the target.  keep: store what the backward needs.
+struct ActorFwdArgs {
+    int B, mode, keep;
+    const float *batch, *next_emotion, *P, *scale, *offset;
+    float *out, *xa, *a1, *a2, *a3, *z4, *aux;
+};
+__global__ void __launch_bounds__(NTHR) actor_fwd_kernel(const ActorFwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float *bufA = sm, *bufB = sm + TILE, *wst = sm + 2 * TILE, *xa_s = sm + 2 * TILE + 2 * WST;
+    const int tid = threadIdx.x, row0 = blockIdx.x * TM, B = a.B;
+    for (int e = tid; e < TM * 8; e += NTHR) {
+        const int r = e >> 3, c = e & 7, gr = row0 + r;
+        float v = 0.f;
+        if (gr < B) {
+            const float *row = a.batch + (size_t)gr * ERLFILL_REC;
+            if (c < 2) v = a.mode == 1 ? row[13 + c] : row[c];
+            else if (c < 5) v = a.mode == 1 ? a.next_emotion[c - 2] : row[16 + (c - 2)];
+            if (a.keep) a.xa[(size_t)gr * 8 + c] = v;
+        }
+        bufA[r * LDA + c] = v;
+        xa_s[e] = v;
+    }
+    const float *P = a.P;
+    {   // Linear(5, 128) -> LeakyReLU(0.1)
+        float acc[2][2][4];
+        dense<8, 128, false>(acc, bufA, P + AO::W1, 5, 128, 5, wst, 0);
+        for_each_out<128>(acc, 128, [&](int r, int c, float v) {
+            v += P[AO::B1 + c];
+            v = v > 0.f ? v : 0.1f * v;
+            bufB[r * LDA + c] = v;
+            if (a.keep && row0 + r < B) a.a1[(size_t)(row0 + r) * 128 + c] = v;
+        });
+    }
+    {   // Linear(128, 128) -> ReLU
+        float acc[2][2][4];
+        dense<128, 128, false>(acc, bufB, P + AO::W2, 128, 128, 128, wst, 2);
+        for_each_out<128>(acc, 128, [&](int r, int c, float v) {
+            v = fmaxf(v + P[AO::B2 + c], 0.f);
+            bufA[r * LDA + c] = v;
+            if (a.keep && row0 + r < B) a.a2[(size_t)(row0 + r) * 128 + c] = v;
+        });
+    }
+    {   // Linear(128, 64) -> ReLU
+        float acc[2][1][4];
+        dense<128, 64, false>(acc, bufA, P + AO::W3, 128, 64, 128, wst, 2);
+        for_each_out<64>(acc, 64, [&](int r, int c, float v) {
+            v = fmaxf(v + P[AO::B3 + c], 0.f);
+            bufB[r * LDA + c] = v;
+            if (a.keep && row0 + r < B) a.a3[(size_t)(row0 + r) * 64 + c] = v;
+        });
+    }
+    {   // Linear(64, 10)
+        float acc[2][1][4];
+        dense<64, 16, false>(acc, bufB, P + AO::W4, 64, 10, 64, wst, 2);
+        for_each_out<16>(acc, 10, [&](int r, int c, float v) { bufA[r * LDA + c] = v + P[AO::B4 + c]; });
+    }
+    __syncthreads();
+    // Softsign, emotion modulation, scaling (ddpg_agent.py:104-122)
+    for (int e = tid; e < TM * 10; e += NTHR) {
+        const int r = e / 10, c = e % 10, gr = row0 + r;
+        if (gr >= B) continue;
+        const float z = bufA[r * LDA + c];
+        const float base = z / (1.0f + fabsf(z));
+        const float cur = xa_s[r * 8 + 2], cons = xa_s[r * 8 + 3], anx = xa_s[r * 8 + 4];
+        float em = cur * P[AO::EW + c];
+        em = fmaf(cons, P[AO::EW + 10 + c], em);
+        em = fmaf(anx, P[AO::EW + 20 + c], em);
+        const float raw = tanhf(em * 1.5f);
+        float alpha = 0.1f + 0.9f * anx;
+        alpha *= (1.0f - 0.5f * cons);
+        alpha *= (1.0f + 0.5f * cur);
+        alpha = fminf(fmaxf(alpha, 0.01f), 1.0f);
+        const float om = 1.0f - fabsf(base);
+        const float sf = base > 0.f ? -1.0f : (base < 0.f ? 1.0f : 0.0f);
+        const size_t g = (size_t)gr * 10 + c;
+        a.out[g] = (base + alpha * raw * sf * (om * om)) * a.scale[c] + a.offset[c];
+        if (a.keep) { a.z4[g] = z; a.aux[g * 3 + 0] = base; a.aux[g * 3 + 1] = raw; a.aux[g * 3 + 2] = alpha; }
+    }
+}
+
+// backward of (LayerNorm + activation) on the tile.  In: dh in d_s, xhat in x_s.  Out: dz in x_s (and global when dz_g),
+// per-CTA column sums [sum dz | sum dy*xhat | sum dy] to part[0:256 | 256:512 | 512:768] when part is set.
+__device__ __forceinline__ void ln_act_bwd_tile(float *d_s, float *x_s, float *stat_s, const float *gamma, const float *beta, int act,
+                                                const float *rstd_g, int row0, int B, float *dz_g, float *part) {
+    const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+#pragma unroll 1
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = warp * 4 + rr;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = l + 32 * i;
+            const float xh = x_s[r * LDA + c];
+            const float y = xh * gamma[c] + beta[c];
+            float g = d_s[r * LDA + c];
+            g *= act == ACT_LEAKY ? (y > 0.f ? 1.f : 0.1f) : (y > 0.f ? 1.f : 0.f);
+            d_s[r * LDA + c] = g;                                  // dy
+            const float dxh = g * gamma[c];
+            s1 += dxh;
+            s2 = fmaf(dxh, xh, s2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        if (l == 0) { stat_s[r] = s1 * (1.0f / 256.0f); stat_s[TM + r] = s2 * (1.0f / 256.0f); stat_s[2 * TM + r] = row0 + r < B ? rstd_g[row0 + r] : 0.f; }
+    }
+    __syncthreads();
+    {   // thread c owns column c: dz and the three column sums in one pass over the 32 rows
+        const int c = tid;
+        const float gm = gamma[c];
+        float sdz = 0.f, sg = 0.f, sb = 0.f;
+#pragma unroll 4
+        for (int r = 0; r < TM; ++r) {
+            const float dy = d_s[r * LDA + c], xh = x_s[r * LDA + c];
+            sb += dy;
+            sg = fmaf(dy, xh, sg);
+            const float dz = stat_s[2 * TM + r] * (dy * gm - stat_s[r] - xh * stat_s[TM + r]);
+            x_s[r * LDA + c] = dz;
+            sdz += dz;
+            if (dz_g && row0 + r < B) dz_g[(size_t)(row0 + r) * 256 + c] = dz;
+        }
+        if (part) { part[c] = sdz; part[256 + c] = sg; part[512 + c] = sb; }
+    }
+    __syncthreads();
+}
+
+// backward of critic_fwd_kernel from dq (dq == nullptr: the constant dq_const for every row): the input-gradient chain for
+// the CTA's rows.  grads != 0: also dz1/dz2/dz3 to global (operands of the weight-gradient GEMMs) and the per-CTA column
+// partial sums (bias, LayerNorm and head gradients) to cpart[cta].  dx0 -> g16 [B][16].
+struct CriticBwdArgs {
+    int B, grads;
+    float dq_const;
+    const float *P, *dq, *h3, *xhat2, *rstd2, *xhat1, *rstd1;
+    float *dz3, *dz2, *dz1, *g16, *cpart;
+};
+__global__ void __launch_bounds__(NTHR) critic_bwd_kernel(const CriticBwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float *bufA = sm, *bufB = sm + TILE, *wst = sm + 2 * TILE, *stat_s = sm + 2 * TILE + 2 * WST;
+    const int tid = threadIdx.x, row0 = blockIdx.x * TM, B = a.B;
+    const float *P = a.P;
+    float *part = a.grads ? a.cpart + (size_t)blockIdx.x * kCPart : nullptr;
+    // dz3 = dq * w10 * (h3 > 0)
+    for (int e = tid; e < TM * 128; e += NTHR) {
+        const int r = e >> 7, c = e & 127, gr = row0 + r;
+        float v = 0.f;
+        if (gr < B) {
+            const float dq = a.dq ? a.dq[gr] : a.dq_const;
+            v = a.h3[(size_t)gr * 128 + c] > 0.f ? dq * P[CO::W10 + c] : 0.f;
+            if (a.grads) a.dz3[(size_t)gr * 128 + c] = v;
+        }
+        bufA[r * LDA + c] = v;
+    }
+    __syncthreads();
+    if (a.grads) {
+        if (tid < 128) {          // db8[c] = sum_r dz3[r][c]
+            float s = 0.f;
+            for (int r = 0; r < TM; ++r) s += bufA[r * LDA + tid];
+            part[kCPartC + tid] = s;
+        } else {                  // dW10[c] = sum_r dq[r] h3[r][c]; db10 = sum_r dq[r]
+            const int c = tid - 128;
+            float s = 0.f, sq = 0.f;
+            for (int r = 0; r < TM && row0 + r < B; ++r) {
+                const float dq = a.dq ? a.dq[row0 + r] : a.dq_const;
+                s = fmaf(dq, a.h3[(size_t)(row0 + r) * 128 + c], s);
+                sq += dq;
+            }
+            part[kCPartC + 128 + c] = s;
+            if (c == 0) part[kCPartC + 256] = sq;
+        }
+    }
+    {   // dh2 = dz3 W8
+        float acc[2][4][4];
+        dense<128, 256, true>(acc, bufA, P + CO::W8, 256, 256, 128, wst, 4);
+        for_each_out<256>(acc, 256, [&](int r, int c, float v) { bufB[r * LDA + c] = v; });
+    }
+    for (int e = tid; e < TM * 256; e += NTHR) {
+        const int r = e >> 8, c = e & 255;
+        bufA[r * LDA + c] = row0 + r < B ? a.xhat2[(size_t)(row0 + r) * 256 + c] : 0.f;
+    }
+    __syncthreads();
+    ln_act_bwd_tile(bufB, bufA, stat_s, P + CO::G2, P + CO::BE2, ACT_RELU, a.rstd2, row0, B, a.grads ? a.dz2 : nullptr,
+                    part ? part + kCPartB : nullptr);
+    {   // dh1 = dz2 W4
+        float acc[2][4][4];
+        dense<256, 256, true>(acc, bufA, P + CO::W4, 256, 256, 256, wst, 4);
+        for_each_out<256>(acc, 256, [&](int r, int c, float v) { bufB[r * LDA + c] = v; });
+    }
+    for (int e = tid; e < TM * 256; e += NTHR) {
+        const int r = e >> 8, c = e & 255;
+        bufA[r * LDA + c] = row0 + r < B ? a.xhat1[(size_t)(row0 + r) * 256 + c] : 0.f;
+    }
+    __syncthreads();
+    ln_act_bwd_tile(bufB, bufA, stat_s, P + CO::G1, P + CO::BE1, ACT_LEAKY, a.rstd1, row0, B, a.grads ? a.dz1 : nullptr,
+                    part ? part + kCPartA : nullptr);
+    {   // dx0[:, :15] = dz1 W0
+        float acc[2][1][4];
+        dense<256, 16, true>(acc, bufA, P + CO::W0, 15, 15, 256, wst, 0);
+        for_each_out<16>(acc, 16, [&](int r, int c, float v) {
+            if (row0 + r < B) a.g16[(size_t)(row0 + r) * 16 + c] = c < 15 ? v : 0.f;
+        });
+    }
+}
+
+// backward of actor_fwd_kernel for the CTA's rows: d(out) from the critic path (g16 columns 2..11) plus the diversity term
+// -0.03 * mean_rows(std_unbiased(out, dim=1)) -> dz4 .. dz1 to global (operands of the weight-gradient GEMMs) and the per-CTA
+// partial sums of d(emotion_weights) and the bias gradients to apart[cta].
+struct ActorBwdArgs {
+    int B;
+    const float *P, *g16, *out, *aux, *xa, *scale, *z4, *a3, *a2, *a1;
+    float *gz4, *ga64, *ga128a, *ga128b, *apart;
+};
+__global__ void __launch_bounds__(NTHR) actor_bwd_kernel(const ActorBwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float *bufA = sm, *bufB = sm + TILE, *wst = sm + 2 * TILE, *de_s = sm + 2 * TILE + 2 * WST;   // de_s[TM][10]
+    const int tid = threadIdx.x, row0 = blockIdx.x * TM, B = a.B;
+    const float *P = a.P;
+    float *part = a.apart + (size_t)blockIdx.x * kAPart;
+    if (tid < TM) {
+        const int r = tid, gr = row0 + r;
+        if (gr < B) {
+            float o[10], mean = 0.f;
+#pragma unroll
+            for (int c = 0; c < 10; ++c) { o[c] = a.out[(size_t)gr * 10 + c]; mean += o[c]; }
+            mean *= 0.1f;
+            float var = 0.f;
+#pragma unroll
+            for (int c = 0; c < 10; ++c) { const float d = o[c] - mean; var = fmaf(d, d, var); }
+            const float sd = sqrtf(var / 9.0f);
+#pragma unroll
+            for (int c = 0; c < 10; ++c) {
+                const size_t g = (size_t)gr * 10 + c;
+                float go = a.g16[(size_t)gr * 16 + 2 + c];
+                go += (-0.03f / (float)B) * (o[c] - mean) / (9.0f * sd);                      // d std / d o_c
+                const float gr_ = go * a.scale[c];                                                // d raw_action
+                const float base = a.aux[g * 3 + 0], raw = a.aux[g * 3 + 1], alpha = a.aux[g * 3 + 2];
+                const float om = 1.0f - fabsf(base);
+                const float sf = base > 0.f ? -1.0f : (base < 0.f ? 1.0f : 0.0f);
+                // d raw_action / d base = 1 + alpha*raw*sf * 2*om*(-sign(base)) = 1 + 2*alpha*raw*om*sf*sf (sign has zero grad)
+                const float dbase = gr_ * (1.0f + 2.0f * alpha * raw * om * (sf * sf));
+                const float z = a.z4[g], den = 1.0f + fabsf(z);
+                const float dz = dbase / (den * den);                                             // softsign'
+                bufA[r * LDA + c] = dz;
+                a.gz4[g] = dz;
+                // d raw_action / d (e @ W_e)[c] = alpha*sf*om^2 * (1 - raw^2) * 1.5
+                de_s[r * 10 + c] = gr_ * alpha * sf * (om * om) * (1.0f - raw * raw) * 1.5f;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 10; ++c) { bufA[r * LDA + c] = 0.f; de_s[r * 10 + c] = 0.f; }
+        }
+#pragma unroll
+        for (int c = 10; c < 16; ++c) bufA[r * LDA + c] = 0.f;
+    }
+    __syncthreads();
+    if (tid < 30) {               // dEW[k][c] = sum_r emotion[r][k] * de[r][c]
+        const int k = tid / 10, c = tid % 10;
+        float s = 0.f;
+        for (int r = 0; r < TM && row0 + r < B; ++r) s = fmaf(a.xa[(size_t)(row0 + r) * 8 + 2 + k], de_s[r * 10 + c], s);
+        part[kAPartEW + tid] = s;
+    } else if (tid >= 32 && tid < 42) {
+        float s = 0.f;
+        for (int r = 0; r < TM; ++r) s += bufA[r * LDA + tid - 32];
+        part[kAPartB4 + tid - 32] = s;
+    }
+    {   // da3 = dz4 W4, relu'
+        float acc[2][1][4];
+        dense<16, 64, true>(acc, bufA, P + AO::W4, 64, 64, 10, wst, 2);
+        for_each_out<64>(acc, 64, [&](int r, int c, float v) {
+            const int gr = row0 + r;
+            v = (gr < B && a.a3[(size_t)gr * 64 + c] > 0.f) ? v : 0.f;
+            bufB[r * LDA + c] = v;
+            if (gr < B) a.ga64[(size_t)gr * 64 + c] = v;
+        });
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float s = 0.f;
+        for (int r = 0; r < TM; ++r) s += bufB[r * LDA + tid];
+        part[kAPartB3 + tid] = s;
+    }
+    {   // da2 = dz3 W3, relu'
+        float acc[2][2][4];
+        dense<64, 128, true>(acc, bufB, P + AO::W3, 128, 128, 64, wst, 2);
+        for_each_out<128>(acc, 128, [&](int r, int c, float v) {
+            const int gr = row0 + r;
+            v = (gr < B && a.a2[(size_t)gr * 128 + c] > 0.f) ? v : 0.f;
+            bufA[r * LDA + c] = v;
+            if (gr < B) a.ga128a[(size_t)gr * 128 + c] = v;
+        });
+    }
+    __syncthreads();
+    if (tid < 128) {
+        float s = 0.f;
+        for (int r = 0; r < TM; ++r) s += bufA[r * LDA + tid];
+        part[kAPartB2 + tid] = s;
+    }
+    {   // da1 = dz2 W2, leaky'
+        float acc[2][2][4];
+        dense<128, 128, true>(acc, bufA, P + AO::W2, 128, 128, 128, wst, 2);
+        for_each_out<128>(acc, 128, [&](int r, int c, float v) {
+            const int gr = row0 + r;
+            v = gr < B ? (a.a1[(size_t)gr * 128 + c] > 0.f ? v : 0.1f * v) : 0.f;
+            bufB[r * LDA + c] = v;
+            if (gr < B) a.ga128b[(size_t)gr * 128 + c] = v;
+        });
+    }
+    __syncthreads();
+    if (tid < 128) {
+        float s = 0.f;
+        for (int r = 0; r < TM; ++r) s += bufB[r * LDA + tid];
+        part[kAPartB1 + tid] = s;
+    }
+}
+
 // ---- workspace -------------------------------------------------------------------------------
 struct Ws {
     float *cgrad, *agrad;                       // flat gradient buckets (cgrad tail holds the 3 emotion means)
     float *stats, *scal, *ssq, *step;                // stats[6]; scal: [2..3] lrs [4] closs [5] aloss [6..14] norms; ssq: [0:64] critic, [64:128] actor sum-of-squares partials
     float *x0, *xhat1, *h1, *xhat2, *h2, *h3, *rstd1, *rstd2, *q, *tq, *q2, *dq;
     float *xa, *a1, *a2, *a3, *z4, *aout, *aux, *atgt;
-    float *g256a, *g256b, *g128, *g16, *ga128a, *ga128b, *ga64, *gz4, *drawe, *part;
-    size_t part_floats;
+    float *dz1, *dz2, *dz3, *g16, *ga128a, *ga128b, *ga64, *gz4, *part, *cpart, *apart;
 };
 static size_t align16(size_t n) { return (n + 3) & ~(size_t)3; }
+static int n_tiles(int B) { return (B + TM - 1) / TM; }
 static size_t carve(Ws *w, float *base, int B) {
     size_t o = 0;
     auto take = [&](float **p, size_t n) { if (w) *p = base + o; o += align16(n); };
@@ -352,66 +592,66 @@ static size_t carve(Ws *w, float *base, int B) {
     take(w ? &w->xa : &dummy, b * 8); take(w ? &w->a1 : &dummy, b * 128); take(w ? &w->a2 : &dummy, b * 128);
     take(w ? &w->a3 : &dummy, b * 64); take(w ? &w->z4 : &dummy, b * 10); take(w ? &w->aout : &dummy, b * 10);
     take(w ? &w->aux : &dummy, b * 30); take(w ? &w->atgt : &dummy, b * 10);
-    take(w ? &w->g256a : &dummy, b * 256); take(w ? &w->g256b : &dummy, b * 256); take(w ? &w->g128 : &dummy, b * 128);
+    take(w ? &w->dz1 : &dummy, b * 256); take(w ? &w->dz2 : &dummy, b * 256); take(w ? &w->dz3 : &dummy, b * 128);
     take(w ? &w->g16 : &dummy, b * 16); take(w ? &w->ga128a : &dummy, b * 128); take(w ? &w->ga128b : &dummy, b * 128);
-    take(w ? &w->ga64 : &dummy, b * 64); take(w ? &w->gz4 : &dummy, b * 10); take(w ? &w->drawe : &dummy, b * 10);
-    const size_t part = (size_t)32 * 256 * 256;              // split-K partials (up to 32 splits of a 256x256 dW)
-    take(w ? &w->part : &dummy, part);
-    if (w) w->part_floats = part;
+    take(w ? &w->ga64 : &dummy, b * 64); take(w ? &w->gz4 : &dummy, b * 10);
+    take(w ? &w->part : &dummy, mlp::kPartFloats);            // split partials of the grouped weight-gradient GEMMs
+    take(w ? &w->cpart : &dummy, (size_t)n_tiles(B) * kCPart); take(w ? &w->apart : &dummy, (size_t)n_tiles(B) * kAPart);
     return o;
 }
 
 // ---- launch helpers ---------------------------------------------------------------------------
-// update.cu's launch helpers bind the header's (mlp.cuh) to this workspace's split scratch
-static void gemm_wgrad(cudaStream_t st, const Ws &w, int Bt, int N, int K, const float *dZ, int ldz, const float *X, int ldx, float *dW) {
-    mlp::gemm_wgrad(st, w.part, Bt, N, K, dZ, ldz, X, ldx, dW);
+static cudaError_t fused_smem_optin() {
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(critic_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(actor_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(critic_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(actor_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return e;
+    done = true;
+    return cudaSuccess;
 }
-static void colsum(cudaStream_t st, const Ws &w, int rows, int cols, const float *X, int ld, const float *Y, int ldy, int ycs, float *out) {
-    mlp::colsum(st, w.part, rows, cols, X, ld, Y, ldy, ycs, out);
+static void critic_forward(cudaStream_t st, const Ws &w, int B, int mode, const float *batch, const float *actions_ext, const float *P,
+                           float *q_out, bool save) {
+    const CriticFwdArgs a{B, mode, save ? 1 : 0, batch, actions_ext, w.stats, P, w.x0, w.xhat1, w.h1, w.rstd1, w.xhat2, w.h2, w.rstd2, w.h3, q_out};
+    critic_fwd_kernel<<<n_tiles(B), NTHR, kFusedSmem, st>>>(a);
 }
-using mlp::gemm;
-
-// Critic.forward on prepared x0; keeps the activations needed by the backward
-static void critic_forward(cudaStream_t st, const Ws &w, int B, const float *P, float *q_out) {
-    gemm(st, B, 256, 15, w.x0, 16, 1, P + CO::W0, 1, 15, w.xhat1, 256, P + CO::B0, ACT_NONE);
-    ln_act_fwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, w.xhat1, P + CO::G1, P + CO::BE1, ACT_LEAKY, w.h1, w.rstd1);
-    gemm(st, B, 256, 256, w.h1, 256, 1, P + CO::W4, 1, 256, w.xhat2, 256, P + CO::B4, ACT_NONE);
-    ln_act_fwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, w.xhat2, P + CO::G2, P + CO::BE2, ACT_RELU, w.h2, w.rstd2);
-    gemm(st, B, 128, 256, w.h2, 256, 1, P + CO::W8, 1, 256, w.h3, 128, P + CO::B8, ACT_RELU);
-    critic_head_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, w.h3, P + CO::W10, P + CO::B10, q_out);
+static void actor_forward(cudaStream_t st, const Ws &w, int B, int mode, const float *batch, const float *next_emotion, const float *P,
+                          const float *scale, const float *offset, float *out, bool keep) {
+    const ActorFwdArgs a{B, mode, keep ? 1 : 0, batch, next_emotion, P, scale, offset, out, w.xa, w.a1, w.a2, w.a3, w.z4, w.aux};
+    actor_fwd_kernel<<<n_tiles(B), NTHR, kFusedSmem, st>>>(a);
 }
-// backward of critic_forward from dq; param grads into G (nullptr: input gradient only); dx0 -> w.g16
-static void critic_backward(cudaStream_t st, const Ws &w, int B, const float *P, const float *dq, float *G) {
-    if (G) {   // dw10[c] = sum_r dq[r] h3[r][c], db10 = sum_r dq[r]
-        colsum(st, w, B, 128, w.h3, 128, dq, 1, 0, G + CO::W10);
-        colsum(st, w, B, 1, dq, 1, nullptr, 0, 0, G + CO::B10);
+// the grouped weight-gradient GEMMs and the one reduction launch that finishes every parameter gradient of a network
+struct GradPlan {
+    mlp::WgArgs wg;
+    mlp::RedArgs red;
+    int wg_blocks = 0, red_blocks = 0;
+    size_t part_used = 0;
+    void init(int Bt) {
+        wg.ntask = 0; red.nseg = 0; wg.Bt = Bt;
+        int splits = Bt >= 2048 ? 16 : (Bt >= 512 ? 8 : (Bt >= 128 ? 4 : 1));
+        wg.kps = ((Bt + splits - 1) / splits + BK - 1) / BK * BK;
+        wg.splits = (Bt + wg.kps - 1) / wg.kps;
     }
-    critic_head_bwd_kernel<<<(B * 128 + 255) / 256, 256, 0, st>>>(B, dq, P + CO::W10, w.h3, w.g128);         // dz3
-    if (G) { gemm_wgrad(st, w, B, 128, 256, w.g128, 128, w.h2, 256, G + CO::W8); colsum(st, w, B, 128, w.g128, 128, nullptr, 0, 0, G + CO::B8); }
-    gemm(st, B, 256, 128, w.g128, 128, 1, P + CO::W8, 256, 1, w.g256a, 256, nullptr, ACT_NONE);               // dh2 = dz3 W8
-    ln_act_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, w.g256a, w.xhat2, w.rstd2, P + CO::G2, P + CO::BE2, ACT_RELU, w.g256b);
-    if (G) {
-        colsum(st, w, B, 256, w.g256a, 256, w.xhat2, 256, 1, G + CO::G2); colsum(st, w, B, 256, w.g256a, 256, nullptr, 0, 0, G + CO::BE2);
-        gemm_wgrad(st, w, B, 256, 256, w.g256b, 256, w.h1, 256, G + CO::W4); colsum(st, w, B, 256, w.g256b, 256, nullptr, 0, 0, G + CO::B4);
+    void seg(const float *part, float *out, int n, int splits, int stride) {
+        red.s[red.nseg++] = mlp::RedSeg{part, out, n, splits, stride, red_blocks};
+        red_blocks += (n + 255) / 256;
     }
-    gemm(st, B, 256, 256, w.g256b, 256, 1, P + CO::W4, 256, 1, w.g256a, 256, nullptr, ACT_NONE);              // dh1 = dz2 W4
-    ln_act_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, w.g256a, w.xhat1, w.rstd1, P + CO::G1, P + CO::BE1, ACT_LEAKY, w.g256b);
-    if (G) {
-        colsum(st, w, B, 256, w.g256a, 256, w.xhat1, 256, 1, G + CO::G1); colsum(st, w, B, 256, w.g256a, 256, nullptr, 0, 0, G + CO::BE1);
-        // dW0[256][15] = dz1^T x0[:, :15]
-        gemm_wgrad(st, w, B, 256, 15, w.g256b, 256, w.x0, 16, G + CO::W0); colsum(st, w, B, 256, w.g256b, 256, nullptr, 0, 0, G + CO::B0);
+    // dW[N][K] = dZ^T X
+    void wgrad(float *part_base, const float *dZ, int ldz, const float *X, int ldx, int N, int K, float *dW) {
+        float *part = part_base + part_used;
+        const int tiles_k = (K + BN - 1) / BN, tiles = tiles_k * ((N + BM - 1) / BM);
+        wg.t[wg.ntask++] = mlp::WgTask{dZ, X, part, ldz, ldx, N, K, tiles_k, tiles, wg_blocks};
+        wg_blocks += tiles * wg.splits;
+        seg(part, dW, N * K, wg.splits, N * K);
+        part_used += (size_t)wg.splits * N * K;
     }
-    gemm(st, B, 15, 256, w.g256b, 256, 1, P + CO::W0, 15, 1, w.g16, 16, nullptr, ACT_NONE);                   // dx0[:, :15]
-}
-// Actor.forward on prepared xa -> physical actions `out`; keep_act: store activations for the backward
-static void actor_forward_train(cudaStream_t st, const Ws &w, int B, const float *P, const float *scale, const float *offset,
-                                float *out, bool keep) {
-    gemm(st, B, 128, 5, w.xa, 8, 1, P + AO::W1, 1, 5, w.a1, 128, P + AO::B1, ACT_LEAKY);
-    gemm(st, B, 128, 128, w.a1, 128, 1, P + AO::W2, 1, 128, w.a2, 128, P + AO::B2, ACT_RELU);
-    gemm(st, B, 64, 128, w.a2, 128, 1, P + AO::W3, 1, 128, w.a3, 64, P + AO::B3, ACT_RELU);
-    gemm(st, B, 10, 64, w.a3, 64, 1, P + AO::W4, 1, 64, w.z4, 10, P + AO::B4, ACT_NONE);
-    actor_head_fwd_kernel<<<(B * 10 + 255) / 256, 256, 0, st>>>(B, w.z4, w.xa, P + AO::EW, scale, offset, out, keep ? w.aux : nullptr);
-}
+    void launch(cudaStream_t st) const {
+        mlp::wgrad_group_kernel<<<wg_blocks, 256, 0, st>>>(wg);
+        mlp::group_reduce_kernel<<<red_blocks, 256, 0, st>>>(red);
+    }
+};
 
 }  // namespace erlfill
 
@@ -463,18 +703,29 @@ int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h,
         if (rc != ERLFILL_OK) return rc;
     }
 
+    ERLFILL_CUDA_TRY(fused_smem_optin());
+    const int nt = n_tiles(B);
+
     if (phases & ERLFILL_PHASE_CRITIC_GRAD) {
         emotion_stats_kernel<<<1, 1024, 0, st>>>(B, d_batch, w.stats, w.cgrad + CO::TOTAL);
         // target: a' = actor_target(s', e'), Q' = critic_target(s', a', 0)
-        build_xa_kernel<<<(B * 8 + 255) / 256, 256, 0, st>>>(B, 1, d_batch, d_next_emotion, w.xa);
-        actor_forward_train(st, w, B, n->actor_target, n->scale, n->offset, w.atgt, false);
-        build_x0_kernel<<<(B * 16 + 255) / 256, 256, 0, st>>>(B, 1, d_batch, w.atgt, w.stats, w.x0);
-        critic_forward(st, w, B, n->critic_target, w.tq);
+        actor_forward(st, w, B, 1, d_batch, d_next_emotion, n->actor_target, n->scale, n->offset, w.atgt, false);
+        critic_forward(st, w, B, 1, d_batch, w.atgt, n->critic_target, w.tq, false);
         // Q(s, a_norm, e) and its gradient
-        build_x0_kernel<<<(B * 16 + 255) / 256, 256, 0, st>>>(B, 0, d_batch, nullptr, w.stats, w.x0);
-        critic_forward(st, w, B, n->critic, w.q);
+        critic_forward(st, w, B, 0, d_batch, nullptr, n->critic, w.q, true);
         critic_loss_kernel<<<1, 1024, 0, st>>>(B, d_batch, w.q, w.tq, h->gamma, w.dq, w.scal + 4);
-        critic_backward(st, w, B, n->critic, w.dq, w.cgrad);
+        const CriticBwdArgs ba{B, 1, 0.f, n->critic, w.dq, w.h3, w.xhat2, w.rstd2, w.xhat1, w.rstd1, w.dz3, w.dz2, w.dz1, w.g16, w.cpart};
+        critic_bwd_kernel<<<nt, NTHR, kFusedSmem, st>>>(ba);
+        float *G = w.cgrad;
+        GradPlan gp;
+        gp.init(B);
+        gp.wgrad(w.part, w.dz3, 128, w.h2, 256, 128, 256, G + CO::W8);
+        gp.wgrad(w.part, w.dz2, 256, w.h1, 256, 256, 256, G + CO::W4);
+        gp.wgrad(w.part, w.dz1, 256, w.x0, 16, 256, 15, G + CO::W0);
+        gp.seg(w.cpart + kCPartA, G + CO::B0, 768, nt, kCPart);       // db0 | dgamma1 | dbeta1
+        gp.seg(w.cpart + kCPartB, G + CO::B4, 768, nt, kCPart);       // db4 | dgamma2 | dbeta2
+        gp.seg(w.cpart + kCPartC, G + CO::B8, 257, nt, kCPart);       // db8 | dW10 | db10
+        gp.launch(st);
     }
     if (phases & ERLFILL_PHASE_CRITIC_APPLY) {
         lr_kernel<<<1, 1, 0, st>>>(w.cgrad + CO::TOTAL, w.step, h->critic_lr, h->actor_lr, w.scal + 2);
@@ -483,29 +734,28 @@ int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h,
                                                                   w.ssq, w.scal + 2, h->max_grad_norm, w.step, h->tau);
     }
     if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
-        build_xa_kernel<<<(B * 8 + 255) / 256, 256, 0, st>>>(B, 0, d_batch, d_next_emotion, w.xa);
-        actor_forward_train(st, w, B, n->actor, n->scale, n->offset, w.aout, true);
-        build_x0_kernel<<<(B * 16 + 255) / 256, 256, 0, st>>>(B, 2, d_batch, w.aout, w.stats, w.x0);
-        critic_forward(st, w, B, n->critic, w.q2);
+        actor_forward(st, w, B, 0, d_batch, d_next_emotion, n->actor, n->scale, n->offset, w.aout, true);
+        critic_forward(st, w, B, 2, d_batch, w.aout, n->critic, w.q2, true);
         actor_loss_kernel<<<1, 1024, 0, st>>>(B, w.q2, w.aout, n->actor, w.scal + 5, w.scal + 6);
         // d(-mean q2)/dq2 = -1/B (the +-1e6 clamp is inactive): input gradient of the critic only -> w.g16
-        fill_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, -1.0f / (float)B, w.dq);
-        critic_backward(st, w, B, n->critic, w.dq, nullptr);
-        slice_action_grad_kernel<<<(B * 10 + 255) / 256, 256, 0, st>>>(B, w.g16, w.drawe);
-        actor_head_bwd_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, w.drawe, w.aout, w.aux, w.xa, n->scale, w.z4, w.gz4, w.drawe);
+        const CriticBwdArgs ba{B, 0, -1.0f / (float)B, n->critic, nullptr, w.h3, w.xhat2, w.rstd2, w.xhat1, w.rstd1, nullptr, nullptr, nullptr,
+                               w.g16, nullptr};
+        critic_bwd_kernel<<<nt, NTHR, kFusedSmem, st>>>(ba);
+        const ActorBwdArgs ab{B, n->actor, w.g16, w.aout, w.aux, w.xa, n->scale, w.z4, w.a3, w.a2, w.a1, w.gz4, w.ga64, w.ga128a, w.ga128b, w.apart};
+        actor_bwd_kernel<<<nt, NTHR, kFusedSmem, st>>>(ab);
         float *G = w.agrad;
-        ew_grad_part_kernel<<<kColSplits, 256, 0, st>>>(B, w.xa, w.drawe, w.part);
-        splitk_reduce_kernel<<<1, 256, 0, st>>>(30, kColSplits, w.part, 30, G + AO::EW);
-        gemm_wgrad(st, w, B, 10, 64, w.gz4, 10, w.a3, 64, G + AO::W4); colsum(st, w, B, 10, w.gz4, 10, nullptr, 0, 0, G + AO::B4);
-        gemm(st, B, 64, 10, w.gz4, 10, 1, n->actor + AO::W4, 64, 1, w.ga64, 64, nullptr, ACT_NONE);
-        relu_bwd_kernel<<<(unsigned)(((size_t)B * 64 + 255) / 256), 256, 0, st>>>((size_t)B * 64, w.ga64, w.a3);
-        gemm_wgrad(st, w, B, 64, 128, w.ga64, 64, w.a2, 128, G + AO::W3); colsum(st, w, B, 64, w.ga64, 64, nullptr, 0, 0, G + AO::B3);
-        gemm(st, B, 128, 64, w.ga64, 64, 1, n->actor + AO::W3, 128, 1, w.ga128a, 128, nullptr, ACT_NONE);
-        relu_bwd_kernel<<<(unsigned)(((size_t)B * 128 + 255) / 256), 256, 0, st>>>((size_t)B * 128, w.ga128a, w.a2);
-        gemm_wgrad(st, w, B, 128, 128, w.ga128a, 128, w.a1, 128, G + AO::W2); colsum(st, w, B, 128, w.ga128a, 128, nullptr, 0, 0, G + AO::B2);
-        gemm(st, B, 128, 128, w.ga128a, 128, 1, n->actor + AO::W2, 128, 1, w.ga128b, 128, nullptr, ACT_NONE);
-        leaky_bwd_kernel<<<(unsigned)(((size_t)B * 128 + 255) / 256), 256, 0, st>>>((size_t)B * 128, w.ga128b, w.a1);
-        gemm_wgrad(st, w, B, 128, 5, w.ga128b, 128, w.xa, 8, G + AO::W1); colsum(st, w, B, 128, w.ga128b, 128, nullptr, 0, 0, G + AO::B1);
+        GradPlan gp;
+        gp.init(B);
+        gp.wgrad(w.part, w.gz4, 10, w.a3, 64, 10, 64, G + AO::W4);
+        gp.wgrad(w.part, w.ga64, 64, w.a2, 128, 64, 128, G + AO::W3);
+        gp.wgrad(w.part, w.ga128a, 128, w.a1, 128, 128, 128, G + AO::W2);
+        gp.wgrad(w.part, w.ga128b, 128, w.xa, 8, 128, 5, G + AO::W1);
+        gp.seg(w.apart + kAPartEW, G + AO::EW, 30, nt, kAPart);
+        gp.seg(w.apart + kAPartB4, G + AO::B4, 10, nt, kAPart);
+        gp.seg(w.apart + kAPartB3, G + AO::B3, 64, nt, kAPart);
+        gp.seg(w.apart + kAPartB2, G + AO::B2, 128, nt, kAPart);
+        gp.seg(w.apart + kAPartB1, G + AO::B1, 128, nt, kAPart);
+        gp.launch(st);
         actor_l2_grad_kernel<<<(AO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, w.scal + 6, G);
     }
     if (phases & ERLFILL_PHASE_ACTOR_APPLY) {
