@@ -23,7 +23,7 @@ static __device__ __forceinline__ void split_tf32(float v, uint32_t &hi, uint32_
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
 static __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
@@ -77,14 +77,20 @@ static __device__ __forceinline__ void gemm_tile(int M, int N, const float *__re
                 split_tf32(Bs[ks + t][wn + j * 8 + g], bh[j][0], bl[j][0]);
                 split_tf32(Bs[ks + t + 4][wn + j * 8 + g], bh[j][1], bl[j][1]);
             }
+            // term-major order: the MMAs on one accumulator are dependent (in-order issue), so the four accumulators are
+            // interleaved between the three correction terms (small terms first)
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    mma_tf32(acc[i][j], al[i], bh[j]);
-                    mma_tf32(acc[i][j], ah[i], bl[j]);
-                    mma_tf32(acc[i][j], ah[i], bh[j]);
-                }
+                for (int j = 0; j < 2; ++j) mma_tf32(acc[i][j], al[i], bh[j]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) mma_tf32(acc[i][j], ah[i], bl[j]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) mma_tf32(acc[i][j], ah[i], bh[j]);
         }
         __syncthreads();
     }

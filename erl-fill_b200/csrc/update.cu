@@ -39,14 +39,19 @@ constexpr int kActorGradPad = 26240;
 // three means into mean_out (tail of the critic gradient bucket, so a DP all-reduce averages them too).
 __global__ void __launch_bounds__(1024) emotion_stats_kernel(int B, const float *batch, float *stats, float *mean_out) {
     __shared__ float scratch[32];
+    float s[3] = {0.f, 0.f, 0.f}, mean[3], q[3] = {0.f, 0.f, 0.f};
+    for (int r = threadIdx.x; r < B; r += blockDim.x)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s[c] += batch[(size_t)r * ERLFILL_REC + 16 + c];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) mean[c] = block_sum(s[c], scratch) / (float)B;
+    for (int r = threadIdx.x; r < B; r += blockDim.x)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { const float d = batch[(size_t)r * ERLFILL_REC + 16 + c] - mean[c]; q[c] = fmaf(d, d, q[c]); }
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
-        float s = 0.f;
-        for (int r = threadIdx.x; r < B; r += blockDim.x) s += batch[(size_t)r * ERLFILL_REC + 16 + c];
-        const float mean = block_sum(s, scratch) / (float)B;
-        float q = 0.f;
-        for (int r = threadIdx.x; r < B; r += blockDim.x) { const float d = batch[(size_t)r * ERLFILL_REC + 16 + c] - mean; q = fmaf(d, d, q); }
-        const float var = block_sum(q, scratch) / (float)(B - 1);
-        if (threadIdx.x == 0) { stats[c] = mean; stats[3 + c] = sqrtf(var); mean_out[c] = mean; }
+        const float var = block_sum(q[c], scratch) / (float)(B - 1);
+        if (threadIdx.x == 0) { stats[c] = mean[c]; stats[3 + c] = sqrtf(var); mean_out[c] = mean[c]; }
     }
 }
 
@@ -68,31 +73,32 @@ __global__ void __launch_bounds__(1024) critic_loss_kernel(int B, const float *b
     if (threadIdx.x == 0) loss_out[0] = t / (float)B;
 }
 
-// actor loss value (reported): -mean(q2) - 0.03*mean_rows(std) + 1e-4 * sum_t ||theta_t||
+// actor loss value (reported): -mean(q2) - 0.03*mean_rows(std) + 1e-4 * sum_t ||theta_t||.  Block 0: the two batch means
+// into loss_out[0]; block 1 + t: ||theta_t|| into tensor_norms[t] (needed by the L2 gradient); report_kernel adds them up.
 __global__ void __launch_bounds__(1024) actor_loss_kernel(int B, const float *q2, const float *out, const float *actor, float *loss_out,
                                                           float *tensor_norms /*[9]*/) {
     __shared__ float scratch[32];
-    float s = 0.f, d = 0.f;
-    for (int r = threadIdx.x; r < B; r += blockDim.x) {
-        s += q2[r];
-        float mean = 0.f;
-        for (int c = 0; c < 10; ++c) mean += out[(size_t)r * 10 + c];
-        mean *= 0.1f;
-        float var = 0.f;
-        for (int c = 0; c < 10; ++c) { const float x = out[(size_t)r * 10 + c] - mean; var = fmaf(x, x, var); }
-        d += sqrtf(var / 9.0f);
-    }
-    const float qs = block_sum(s, scratch);
-    const float ds = block_sum(d, scratch);
-    float l2 = 0.f;
-    for (int t = 0; t < kActorTensors; ++t) {
+    if (blockIdx.x == 0) {
+        float s = 0.f, d = 0.f;
+        for (int r = threadIdx.x; r < B; r += blockDim.x) {
+            s += q2[r];
+            float mean = 0.f;
+            for (int c = 0; c < 10; ++c) mean += out[(size_t)r * 10 + c];
+            mean *= 0.1f;
+            float var = 0.f;
+            for (int c = 0; c < 10; ++c) { const float x = out[(size_t)r * 10 + c] - mean; var = fmaf(x, x, var); }
+            d += sqrtf(var / 9.0f);
+        }
+        const float qs = block_sum(s, scratch);
+        const float ds = block_sum(d, scratch);
+        if (threadIdx.x == 0) loss_out[0] = -qs / (float)B - 0.03f * ds / (float)B;
+    } else {
+        const int t = blockIdx.x - 1;
         float q = 0.f;
         for (int i = c_actor_seg[t] + threadIdx.x; i < c_actor_seg[t + 1]; i += blockDim.x) q = fmaf(actor[i], actor[i], q);
         const float nrm = sqrtf(block_sum(q, scratch));
         if (threadIdx.x == 0) tensor_norms[t] = nrm;
-        l2 += nrm;
     }
-    if (threadIdx.x == 0) loss_out[0] = -qs / (float)B - 0.03f * ds / (float)B + 1e-4f * l2;
 }
 // grad += 1e-4 * theta / ||theta_tensor||
 __global__ void actor_l2_grad_kernel(const float *actor, const float *tensor_norms, float *grad) {
@@ -144,26 +150,33 @@ __global__ void soft_update_kernel(int n, const float *p, float *pt, float tau) 
     if (i < n) pt[i] = tau * p[i] + (1.0f - tau) * pt[i];
 }
 __global__ void report_kernel(const float *scal, float *out) {
-    out[0] = scal[4]; out[1] = scal[5]; out[2] = scal[2]; out[3] = scal[3];
+    float l2 = 0.f;
+    for (int t = 0; t < kActorTensors; ++t) l2 += scal[6 + t];
+    out[0] = scal[4]; out[1] = scal[5] + 1e-4f * l2; out[2] = scal[2]; out[3] = scal[3];
 }
 
 // ---- fused row-tile kernels (fused_mlp.cuh): one CTA = 32 minibatch rows through a whole layer chain ------------------
-// shared memory: bufA | bufB (activation tiles) | two weight stages | misc (actor input tile, row statistics)
-constexpr int kMisc = 512;
-constexpr int kFusedSmem = (2 * TILE + 2 * WST + kMisc) * 4;
+// shared memory: bufA | bufB | bufC (activation tiles) | three weight stages | misc (actor input tile, row statistics)
+constexpr int kMisc = 1280;
+constexpr int kFusedSmem = (3 * TILE + NSTAGE * WST + kMisc) * 4;
+static_assert(kFusedSmem <= 232448, "shared memory plan exceeds the 227 KB opt-in limit");
 // per-CTA column partial sums of the critic backward: [db0 | dgamma1 | dbeta1] [db4 | dgamma2 | dbeta2] [db8 | dW10 | db10]
 constexpr int kCPartA = 0, kCPartB = 768, kCPartC = 1536, kCPart = 1800;
 // per-CTA partials of the actor backward: dEW(30, padded 32) | db4(10, padded 16) | db3(64) | db2(128) | db1(128)
 constexpr int kAPartEW = 0, kAPartB4 = 32, kAPartB3 = 48, kAPartB2 = 112, kAPartB1 = 240, kAPart = 368;
 
 // LayerNorm(256) + activation on the tile: z_s (pre-LN rows) becomes h in place; xhat / rstd / h also go to global
-// memory (what the backward needs) when the pointers are set.  Warp w owns rows 4w .. 4w+3.
+// memory (what the backward needs) when the pointers are set.  Warp w owns rows kRowsPerWarp*w ...
+constexpr int kRowsPerWarp = TM / (NTHR / 32);
 __device__ __forceinline__ void ln_act_tile(float *z_s, const float *gamma, const float *beta, int act, int row0, int B,
                                             float *xhat_g, float *rstd_g, float *h_g) {
     const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+    float gm[8], bt[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { gm[i] = gamma[l + 32 * i]; bt[i] = beta[l + 32 * i]; }
 #pragma unroll 1
-    for (int rr = 0; rr < 4; ++rr) {
-        const int r = warp * 4 + rr, gr = row0 + r;
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int r = warp * kRowsPerWarp + rr, gr = row0 + r;
         float v[8];
         float s = 0.f;
 #pragma unroll
@@ -181,7 +194,7 @@ __device__ __forceinline__ void ln_act_tile(float *z_s, const float *gamma, cons
         for (int i = 0; i < 8; ++i) {
             const int c = l + 32 * i;
             const float xh = (v[i] - mean) * rstd;
-            float y = xh * gamma[c] + beta[c];
+            float y = xh * gm[i] + bt[i];
             y = act == ACT_LEAKY ? (y > 0.f ? y : 0.1f * y) : fmaxf(y, 0.f);
             z_s[r * LDA + c] = y;
             if (gr < B) {
@@ -202,7 +215,7 @@ struct CriticFwdArgs {
 };
 __global__ void __launch_bounds__(NTHR) critic_fwd_kernel(const CriticFwdArgs a) {
     extern __shared__ __align__(16) float sm[];
-    float *bufA = sm, *bufB = sm + TILE, *wst = sm + 2 * TILE;
+    float *bufA = sm, *bufB = sm + TILE, *wst = sm + 3 * TILE;
     const int tid = threadIdx.x, row0 = blockIdx.x * TM, B = a.B;
     for (int e = tid; e < TM * 16; e += NTHR) {
         const int r = e >> 4, c = e & 15, gr = row0 + r;
@@ -218,21 +231,21 @@ __global__ void __launch_bounds__(NTHR) critic_fwd_kernel(const CriticFwdArgs a)
     }
     const float *P = a.P;
     {   // Linear(15, 256) -> LayerNorm -> LeakyReLU(0.1)
-        float acc[2][4][4];
+        float acc[2][Cols<256>::NTW][4];
         dense<16, 256, false>(acc, bufA, P + CO::W0, 15, 256, 15, wst, 0);
         for_each_out<256>(acc, 256, [&](int r, int c, float v) { bufB[r * LDA + c] = v + P[CO::B0 + c]; });
     }
     __syncthreads();
     ln_act_tile(bufB, P + CO::G1, P + CO::BE1, ACT_LEAKY, row0, B, a.save ? a.xhat1 : nullptr, a.save ? a.rstd1 : nullptr, a.save ? a.h1 : nullptr);
     {   // Linear(256, 256) -> LayerNorm -> ReLU
-        float acc[2][4][4];
+        float acc[2][Cols<256>::NTW][4];
         dense<256, 256, false>(acc, bufB, P + CO::W4, 256, 256, 256, wst, 4);
         for_each_out<256>(acc, 256, [&](int r, int c, float v) { bufA[r * LDA + c] = v + P[CO::B4 + c]; });
     }
     __syncthreads();
     ln_act_tile(bufA, P + CO::G2, P + CO::BE2, ACT_RELU, row0, B, a.save ? a.xhat2 : nullptr, a.save ? a.rstd2 : nullptr, a.save ? a.h2 : nullptr);
     {   // Linear(256, 128) -> ReLU
-        float acc[2][2][4];
+        float acc[2][Cols<128>::NTW][4];
         dense<256, 128, false>(acc, bufA, P + CO::W8, 256, 128, 256, wst, 4);
         for_each_out<128>(acc, 128, [&](int r, int c, float v) {
             v = fmaxf(v + P[CO::B8 + c], 0.f);
@@ -241,10 +254,10 @@ __global__ void __launch_bounds__(NTHR) critic_fwd_kernel(const CriticFwdArgs a)
         });
     }
     __syncthreads();
-    // Linear(128, 1), clamp +-1e6: warp w owns rows 4w .. 4w+3
+    // Linear(128, 1), clamp +-1e6
     const int warp = tid >> 5, l = tid & 31;
-    for (int rr = 0; rr < 4; ++rr) {
-        const int r = warp * 4 + rr;
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int r = warp * kRowsPerWarp + rr;
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) s = fmaf(bufB[r * LDA + l + 32 * i], P[CO::W10 + l + 32 * i], s);
@@ -263,7 +276,7 @@ struct ActorFwdArgs {
 };
 __global__ void __launch_bounds__(NTHR) actor_fwd_kernel(const ActorFwdArgs a) {
     extern __shared__ __align__(16) float sm[];
-    float *bufA = sm, *bufB = sm + TILE, *wst = sm + 2 * TILE, *xa_s = sm + 2 * TILE + 2 * WST;
+    float *bufA = sm, *bufB = sm + TILE, *wst = sm + 3 * TILE, *xa_s = sm + 3 * TILE + NSTAGE * WST;
     const int tid = threadIdx.x, row0 = blockIdx.x * TM, B = a.B;
     for (int e = tid; e < TM * 8; e += NTHR) {
         const int r = e >> 3, c = e & 7, gr = row0 + r;
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(NTHR) actor_fwd_kernel(const ActorFwdArgs a) {
     }
     const float *P = a.P;
     {   // Linear(5, 128) -> LeakyReLU(0.1)
-        float acc[2][2][4];
+        float acc[2][Cols<128>::NTW][4];
         dense<8, 128, false>(acc, bufA, P + AO::W1, 5, 128, 5, wst, 0);
         for_each_out<128>(acc, 128, [&](int r, int c, float v) {
             v += P[AO::B1 + c];
@@ -289,7 +302,7 @@ __global__ void __launch_bounds__(NTHR) actor_fwd_kernel(const ActorFwdArgs a) {
         });
     }
     {   // Linear(128, 128) -> ReLU
-        float acc[2][2][4];
+        float acc[2][Cols<128>::NTW][4];
         dense<128, 128, false>(acc, bufB, P + AO::W2, 128, 128, 128, wst, 2);
         for_each_out<128>(acc, 128, [&](int r, int c, float v) {
             v = fmaxf(v + P[AO::B2 + c], 0.f);
@@ -340,33 +353,39 @@ __global__ void __launch_bounds__(NTHR) actor_fwd_kernel(const ActorFwdArgs a) {
 __device__ __forceinline__ void ln_act_bwd_tile(float *d_s, float *x_s, float *stat_s, const float *gamma, const float *beta, int act,
                                                 const float *rstd_g, int row0, int B, float *dz_g, float *part) {
     const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+    float gmr[8], btr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { gmr[i] = gamma[l + 32 * i]; btr[i] = beta[l + 32 * i]; }
+    const float rs_mine = (l < kRowsPerWarp && row0 + warp * kRowsPerWarp + l < B) ? rstd_g[row0 + warp * kRowsPerWarp + l] : 0.f;
 #pragma unroll 1
-    for (int rr = 0; rr < 4; ++rr) {
-        const int r = warp * 4 + rr;
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int r = warp * kRowsPerWarp + rr;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int c = l + 32 * i;
             const float xh = x_s[r * LDA + c];
-            const float y = xh * gamma[c] + beta[c];
+            const float y = xh * gmr[i] + btr[i];
             float g = d_s[r * LDA + c];
             g *= act == ACT_LEAKY ? (y > 0.f ? 1.f : 0.1f) : (y > 0.f ? 1.f : 0.f);
             d_s[r * LDA + c] = g;                                  // dy
-            const float dxh = g * gamma[c];
+            const float dxh = g * gmr[i];
             s1 += dxh;
             s2 = fmaf(dxh, xh, s2);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-        if (l == 0) { stat_s[r] = s1 * (1.0f / 256.0f); stat_s[TM + r] = s2 * (1.0f / 256.0f); stat_s[2 * TM + r] = row0 + r < B ? rstd_g[row0 + r] : 0.f; }
+        if (l == 0) { stat_s[r] = s1 * (1.0f / 256.0f); stat_s[TM + r] = s2 * (1.0f / 256.0f); }
+        if (l == rr) stat_s[2 * TM + r] = rs_mine;
     }
     __syncthreads();
-    {   // thread c owns column c: dz and the three column sums in one pass over the 32 rows
-        const int c = tid;
+    {   // two threads per column (16 rows each): dz and the three column sums in one pass; the upper half's sums go through
+        // shared memory and are added by the lower half (fixed order)
+        const int c = tid & 255, half = tid >> 8;
         const float gm = gamma[c];
         float sdz = 0.f, sg = 0.f, sb = 0.f;
 #pragma unroll 4
-        for (int r = 0; r < TM; ++r) {
+        for (int r = half * (TM / 2); r < (half + 1) * (TM / 2); ++r) {
             const float dy = d_s[r * LDA + c], xh = x_s[r * LDA + c];
             sb += dy;
             sg = fmaf(dy, xh, sg);
@@ -375,7 +394,10 @@ __device__ __forceinline__ void ln_act_bwd_tile(float *d_s, float *x_s, float *s
             sdz += dz;
             if (dz_g && row0 + r < B) dz_g[(size_t)(row0 + r) * 256 + c] = dz;
         }
-        if (part) { part[c] = sdz; part[256 + c] = sg; part[512 + c] = sb; }
+        float *hs = stat_s + 3 * TM;                               // [3][256]
+        if (half == 1) { hs[c] = sdz; hs[256 + c] = sg; hs[512 + c] = sb; }
+        __syncthreads();
+        if (half == 0 && part) { part[c] = sdz + hs[c]; part[256 + c] = sg + hs[256 + c]; part[512 + c] = sb + hs[512 + c]; }
     }
     __syncthreads();
 }
@@ -391,20 +413,28 @@ struct CriticBwdArgs {
 };
 __global__ void __launch_bounds__(NTHR) critic_bwd_kernel(const CriticBwdArgs a) {
     extern __shared__ __align__(16) float sm[];
-    float *bufA = sm, *bufB = sm + TILE, *wst = sm + 2 * TILE, *stat_s = sm + 2 * TILE + 2 * WST;
+    float *bufA = sm, *bufB = sm + TILE, *bufC = sm + 2 * TILE, *wst = sm + 3 * TILE, *stat_s = sm + 3 * TILE + NSTAGE * WST;
     const int tid = threadIdx.x, row0 = blockIdx.x * TM, B = a.B;
     const float *P = a.P;
     float *part = a.grads ? a.cpart + (size_t)blockIdx.x * kCPart : nullptr;
+    prefetch_tile256(bufC, a.xhat2, row0, B);        // lands while dz3 and dh2 are computed
     // dz3 = dq * w10 * (h3 > 0)
-    for (int e = tid; e < TM * 128; e += NTHR) {
-        const int r = e >> 7, c = e & 127, gr = row0 + r;
-        float v = 0.f;
-        if (gr < B) {
-            const float dq = a.dq ? a.dq[gr] : a.dq_const;
-            v = a.h3[(size_t)gr * 128 + c] > 0.f ? dq * P[CO::W10 + c] : 0.f;
-            if (a.grads) a.dz3[(size_t)gr * 128 + c] = v;
+    {
+        constexpr int IT = TM * 128 / NTHR;
+        float hv[IT], dqv[IT];
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int e = tid + it * NTHR, r = e >> 7, c = e & 127, gr = row0 + r;
+            hv[it] = gr < B ? a.h3[(size_t)gr * 128 + c] : 0.f;
+            dqv[it] = gr < B ? (a.dq ? a.dq[gr] : a.dq_const) : 0.f;
         }
-        bufA[r * LDA + c] = v;
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int e = tid + it * NTHR, r = e >> 7, c = e & 127, gr = row0 + r;
+            const float v = hv[it] > 0.f ? dqv[it] * P[CO::W10 + c] : 0.f;
+            if (a.grads && gr < B) a.dz3[(size_t)gr * 128 + c] = v;
+            bufA[r * LDA + c] = v;
+        }
     }
     __syncthreads();
     if (a.grads) {
@@ -412,7 +442,7 @@ __global__ void __launch_bounds__(NTHR) critic_bwd_kernel(const CriticBwdArgs a)
             float s = 0.f;
             for (int r = 0; r < TM; ++r) s += bufA[r * LDA + tid];
             part[kCPartC + tid] = s;
-        } else {                  // dW10[c] = sum_r dq[r] h3[r][c]; db10 = sum_r dq[r]
+        } else if (tid < 256) {   // dW10[c] = sum_r dq[r] h3[r][c]; db10 = sum_r dq[r]
             const int c = tid - 128;
             float s = 0.f, sq = 0.f;
             for (int r = 0; r < TM && row0 + r < B; ++r) {
@@ -425,27 +455,21 @@ __global__ void __launch_bounds__(NTHR) critic_bwd_kernel(const CriticBwdArgs a)
         }
     }
     {   // dh2 = dz3 W8
-        float acc[2][4][4];
+        float acc[2][Cols<256>::NTW][4];
         dense<128, 256, true>(acc, bufA, P + CO::W8, 256, 256, 128, wst, 4);
         for_each_out<256>(acc, 256, [&](int r, int c, float v) { bufB[r * LDA + c] = v; });
     }
-    for (int e = tid; e < TM * 256; e += NTHR) {
-        const int r = e >> 8, c = e & 255;
-        bufA[r * LDA + c] = row0 + r < B ? a.xhat2[(size_t)(row0 + r) * 256 + c] : 0.f;
-    }
+    prefetch_tile256(bufA, a.xhat1, row0, B);        // bufA (dz3) is free: lands under the LayerNorm backward and dh1
+    cp_async_wait<1>();                              // xhat2 tile (the older group)
     __syncthreads();
-    ln_act_bwd_tile(bufB, bufA, stat_s, P + CO::G2, P + CO::BE2, ACT_RELU, a.rstd2, row0, B, a.grads ? a.dz2 : nullptr,
+    ln_act_bwd_tile(bufB, bufC, stat_s, P + CO::G2, P + CO::BE2, ACT_RELU, a.rstd2, row0, B, a.grads ? a.dz2 : nullptr,
                     part ? part + kCPartB : nullptr);
     {   // dh1 = dz2 W4
-        float acc[2][4][4];
-        dense<256, 256, true>(acc, bufA, P + CO::W4, 256, 256, 256, wst, 4);
+        float acc[2][Cols<256>::NTW][4];
+        dense<256, 256, true>(acc, bufC, P + CO::W4, 256, 256, 256, wst, 4);
         for_each_out<256>(acc, 256, [&](int r, int c, float v) { bufB[r * LDA + c] = v; });
     }
-    for (int e = tid; e < TM * 256; e += NTHR) {
-        const int r = e >> 8, c = e & 255;
-        bufA[r * LDA + c] = row0 + r < B ? a.xhat1[(size_t)(row0 + r) * 256 + c] : 0.f;
-    }
-    __syncthreads();
+    __syncthreads();                                 // (dense drained every cp.async group, the xhat1 tile included)
     ln_act_bwd_tile(bufB, bufA, stat_s, P + CO::G1, P + CO::BE1, ACT_LEAKY, a.rstd1, row0, B, a.grads ? a.dz1 : nullptr,
                     part ? part + kCPartA : nullptr);
     {   // dx0[:, :15] = dz1 W0
@@ -467,7 +491,7 @@ struct ActorBwdArgs {
 };
 __global__ void __launch_bounds__(NTHR) actor_bwd_kernel(const ActorBwdArgs a) {
     extern __shared__ __align__(16) float sm[];
-    float *bufA = sm, *bufB = sm + TILE, *wst = sm + 2 * TILE, *de_s = sm + 2 * TILE + 2 * WST;   // de_s[TM][10]
+    float *bufA = sm, *bufB = sm + TILE, *wst = sm + 3 * TILE, *de_s = sm + 3 * TILE + NSTAGE * WST;   // de_s[TM][10]
     const int tid = threadIdx.x, row0 = blockIdx.x * TM, B = a.B;
     const float *P = a.P;
     float *part = a.apart + (size_t)blockIdx.x * kAPart;
@@ -535,7 +559,7 @@ __global__ void __launch_bounds__(NTHR) actor_bwd_kernel(const ActorBwdArgs a) {
         part[kAPartB3 + tid] = s;
     }
     {   // da2 = dz3 W3, relu'
-        float acc[2][2][4];
+        float acc[2][Cols<128>::NTW][4];
         dense<64, 128, true>(acc, bufB, P + AO::W3, 128, 128, 64, wst, 2);
         for_each_out<128>(acc, 128, [&](int r, int c, float v) {
             const int gr = row0 + r;
@@ -551,7 +575,7 @@ __global__ void __launch_bounds__(NTHR) actor_bwd_kernel(const ActorBwdArgs a) {
         part[kAPartB2 + tid] = s;
     }
     {   // da1 = dz2 W2, leaky'
-        float acc[2][2][4];
+        float acc[2][Cols<128>::NTW][4];
         dense<128, 128, true>(acc, bufA, P + AO::W2, 128, 128, 128, wst, 2);
         for_each_out<128>(acc, 128, [&](int r, int c, float v) {
             const int gr = row0 + r;
@@ -736,7 +760,7 @@ int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h,
     if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
         actor_forward(st, w, B, 0, d_batch, d_next_emotion, n->actor, n->scale, n->offset, w.aout, true);
         critic_forward(st, w, B, 2, d_batch, w.aout, n->critic, w.q2, true);
-        actor_loss_kernel<<<1, 1024, 0, st>>>(B, w.q2, w.aout, n->actor, w.scal + 5, w.scal + 6);
+        actor_loss_kernel<<<1 + kActorTensors, 1024, 0, st>>>(B, w.q2, w.aout, n->actor, w.scal + 5, w.scal + 6);
         // d(-mean q2)/dq2 = -1/B (the +-1e6 clamp is inactive): input gradient of the critic only -> w.g16
         const CriticBwdArgs ba{B, 0, -1.0f / (float)B, n->critic, nullptr, w.h3, w.xhat2, w.rstd2, w.xhat1, w.rstd1, nullptr, nullptr, nullptr,
                                w.g16, nullptr};
