@@ -367,7 +367,7 @@ def wl_update(args, rank, world, device, timer):
                    "minibatch_per_gpu": B, "replay": C, "parallelism": "dp%d" % world,
                    "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
         "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": B * 80, "d2h_bytes_per_step": 16},
-        "gpu_launches": 70 * args.steps,
+        "gpu_launches": 26 * args.steps,       # sample + gather + 24 launches of erlfill_ddpg_update
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
                      "peak_source": peaks["source"] + " (sustained)", "kernel": "whole update (sample + gather + U1-U5)",

@@ -17,10 +17,12 @@ namespace mlp {
 constexpr int BM = 64, BN = 64, BK = 16, LDS_T = 72;          // 72 % 32 == 8: conflict-free fragment loads
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
 
+// v = hi + lo with hi = v truncated to TF32 (one LOP) and lo = v - hi (exact in fp32; the tensor core reads the top 19 bits of
+// the register, i.e. truncates lo to TF32 itself: |error| <= 2^-21 |v|).  No cvt.rna: the conversion pipe is quarter rate
+// and throttled the MMA loop (ncu: math_pipe_throttle was the top stall with it).
 static __device__ __forceinline__ void split_tf32(float v, uint32_t &hi, uint32_t &lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
-    const float r = v - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
 }
 static __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"

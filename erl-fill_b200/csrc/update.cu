@@ -11,11 +11,13 @@
 // fresh emotion broadcast over the batch, whose batch standardisation is (e-mean)/(0+1e-6) of identical
 // rows: pure summation noise in torch (measured +-0.36), defined here as exactly 0.
 //
-// Structure: parameters, gradients and Adam moments are flat fp32 buffers in the reference's
-// parameters() order, so clip / Adam / soft update / the data-parallel all-reduce are single passes.
-// The dense layers run through one strided, split-K capable tensor-core GEMM (mma.sync TF32, 3xTF32 compensated,
-// this file); the update is dependent-launch/latency bound at these sizes (5.9 GFLOP at B=4096), see DESIGN.md section 4.  Every reduction is
-// tree-ordered without atomics, so an update is bit-reproducible.
+// Structure: parameters, gradients and Adam moments are flat fp32 buffers in the reference's parameters() order, so
+// clip / Adam / soft update / the data-parallel all-reduce are single passes.  Each forward and each input-gradient chain
+// is ONE launch (fused_mlp.cuh: a CTA owns 32 minibatch rows, activations in shared memory, weights streamed from L2
+// through a cp.async ring, mma.sync TF32 with 3xTF32 compensation); the weight gradients of a network are one grouped
+// split-K GEMM launch plus one grouped reduction that also folds the per-CTA bias / LayerNorm / head partial sums.
+// 24 launches per update (70 before the fusion); every reduction is ordered and atomics-free, so an update is
+// bit-reproducible.  The update stays latency bound at B = 4096 (5.9 GFLOP): see DESIGN.md section 4.5.
 #include <math.h>
 
 #include "common.cuh"
