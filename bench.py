@@ -335,7 +335,12 @@ def wl_update(args, rank, world, device, timer):
         agent.memory.buf[o:o + m].copy_(rows.to(device))
     agent.memory.size = agent.memory.inserted = C
     from erlfill_b200 import parallel
-    allreduce = parallel.GradSync(world) if world > 1 else None
+    allreduce = None
+    if world > 1:      # gradient exchange: one-shot NVLink peer-memory kernel (default) or the NCCL all-reduce
+        if args.exchange == "peer":
+            allreduce = parallel.PeerExchange(agent.learner, B)
+        else:
+            allreduce = parallel.GradSync(world)
 
     def step():
         agent.learn(allreduce=allreduce)
@@ -360,14 +365,21 @@ def wl_update(args, rank, world, device, timer):
     ms = total_ms / args.steps
     achieved = UPDATE_FLOP_PER_SAMPLE * B / (ms * 1e-3) / 1e12
     return {
-        "metric": "er_ddpg_updates_per_sec", "value": args.steps / (total_ms * 1e-3), "unit": "updates/s", "dtype": "f32",
+        # weak scaling: every rank pushes its own minibatch of B through the update each step, so the units processed per step
+        # are `world` minibatch updates (one synchronous optimiser step on the global batch of world x B)
+        "metric": "er_ddpg_updates_per_sec", "value": world * args.steps / (total_ms * 1e-3), "unit": "updates/s", "dtype": "f32",
         "ms_per_step": ms, "wall_s_timed_region": wall, "samples_per_sec": B * world * args.steps / (total_ms * 1e-3),
+        "sync_steps_per_sec": args.steps / (total_ms * 1e-3),
         "config": {"workload": "configs[3]: ER-DDPG update, minibatch %d per GPU, %d-transition replay, data-parallel x%d "
-                               "(flat-bucket gradient all-reduce)" % (B, C, world),
+                               "(%s); value counts per-GPU minibatch updates, sync_steps_per_sec the optimiser steps on the "
+                               "global batch" % (B, C, world, "no exchange" if world == 1 else
+                                                 ("one-shot NVLink peer-memory gradient exchange fused with the clip-norm partials"
+                                                  if args.exchange == "peer" else "NCCL flat-bucket all-reduce")),
                    "minibatch_per_gpu": B, "replay": C, "parallelism": "dp%d" % world,
                    "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
-        "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": B * 80, "d2h_bytes_per_step": 16},
-        "gpu_launches": 26 * args.steps,       # sample + gather + 24 launches of erlfill_ddpg_update
+        "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": B * 80, "d2h_bytes_per_step": 16},
+        # sample + gather + 24 launches of erlfill_ddpg_update (+ 2 x (signal, reduce) - 2 sumsq with the peer exchange)
+        "gpu_launches": (26 if world == 1 else 28) * args.steps,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
                      "peak_source": peaks["source"] + " (sustained)", "kernel": "whole update (sample + gather + U1-U5)",
@@ -495,7 +507,10 @@ def run_ours(args):
             line["other_workloads"] = others
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # no NCCL / interpreter teardown: captured graphs that hold collectives and peer mappings are still alive
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -597,6 +612,8 @@ def main():
     ap.add_argument("--replay", type=int, default=1000000)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--sim-mode", default="auto", choices=["auto", "warp", "thread"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="gradient exchange of the data-parallel update at N > 1 (csrc/peer.cu or ncclAllReduce)")
     ap.add_argument("--emotion-precision", default="bf16", choices=["bf16", "fp32"],
                     help="EmotionTransformer kernel of the rollout: tcgen05 bf16 (default) or the exact fp32 SIMT twin")
     args = ap.parse_args()

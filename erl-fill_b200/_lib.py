@@ -103,7 +103,13 @@ class SACHyper(C.Structure):
 
 
 TD3_ACTOR_PARAMS, TD3_CRITIC_PARAMS, SAC_POLICY_PARAMS, SAC_Q_PARAMS = 69130, 138754, 71700, 138754
-PHASE_CRITIC_GRAD, PHASE_CRITIC_APPLY, PHASE_ACTOR_GRAD, PHASE_ACTOR_APPLY, PHASE_ALL = 1, 2, 4, 8, 15
+PHASE_CRITIC_GRAD, PHASE_CRITIC_APPLY, PHASE_ACTOR_GRAD, PHASE_ACTOR_APPLY, PHASE_ALL, PHASE_REDUCED = 1, 2, 4, 8, 15, 16
+MAX_PEERS = 8
+
+
+class PeerGroup(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("ws", C.c_void_p * MAX_PEERS), ("ctrl", C.c_void_p * MAX_PEERS)]
+
 ACTOR_PARAMS, CRITIC_PARAMS = 26216, 103937
 
 DROPOUT_OFF, DROPOUT_PHILOX, DROPOUT_MASK = 0, 1, 2
@@ -117,6 +123,8 @@ EXPORTS = [
     "erlfill_emotion_tc_image_bytes", "erlfill_emotion_tc_pack", "erlfill_emotion_forward_tc",
     "erlfill_replay_insert", "erlfill_replay_sample", "erlfill_replay_gather",
     "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_set_step", "erlfill_ddpg_update",
+    "erlfill_ddpg_exchange_buffers", "erlfill_peer_ctrl_bytes", "erlfill_peer_alloc", "erlfill_peer_open", "erlfill_peer_close",
+    "erlfill_peer_free", "erlfill_ddpg_peer_allreduce", "erlfill_peer_error",
     "erlfill_t1_workspace_bytes", "erlfill_t1_act_workspace_bytes", "erlfill_t1_grad_buckets", "erlfill_td3_act",
     "erlfill_td3_update", "erlfill_sac_act", "erlfill_sac_update",
 ]
@@ -137,6 +145,7 @@ def lib():
         L.erlfill_emotion_tc_image_bytes.restype = C.c_size_t
         L.erlfill_t1_workspace_bytes.restype = C.c_size_t
         L.erlfill_t1_act_workspace_bytes.restype = C.c_size_t
+        L.erlfill_peer_ctrl_bytes.restype = C.c_size_t
         for name in EXPORTS:
             getattr(L, name)
         _lib = L

@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(NTHR) actor_bwd_kernel(const ActorBwdArgs a) {
 
 // ---- workspace -------------------------------------------------------------------------------
 struct Ws {
-    float *cgrad, *agrad;                       // flat gradient buckets (cgrad tail holds the 3 emotion means)
+    float *cgrad, *agrad, *cred, *ared;         // flat gradient buckets (cgrad tail holds the 3 emotion means) and their peer-reduced twins
     float *stats, *scal, *ssq, *step;                // stats[6]; scal: [2..3] lrs [4] closs [5] aloss [6..14] norms; ssq: [0:64] critic, [64:128] actor sum-of-squares partials
     float *x0, *xhat1, *h1, *xhat2, *h2, *h3, *rstd1, *rstd2, *q, *tq, *q2, *dq;
     float *xa, *a1, *a2, *a3, *z4, *aout, *aux, *atgt;
@@ -609,6 +609,7 @@ static size_t carve(Ws *w, float *base, int B) {
     auto take = [&](float **p, size_t n) { if (w) *p = base + o; o += align16(n); };
     float *dummy;
     take(w ? &w->cgrad : &dummy, kCriticGradPad); take(w ? &w->agrad : &dummy, kActorGradPad);
+    take(w ? &w->cred : &dummy, kCriticGradPad); take(w ? &w->ared : &dummy, kActorGradPad);
     take(w ? &w->stats : &dummy, 8); take(w ? &w->scal : &dummy, 32); take(w ? &w->ssq : &dummy, 2 * kSumsqBlocks); take(w ? &w->step : &dummy, 4);
     const size_t b = (size_t)B;
     take(w ? &w->x0 : &dummy, b * 16); take(w ? &w->xhat1 : &dummy, b * 256); take(w ? &w->h1 : &dummy, b * 256);
@@ -701,6 +702,21 @@ int erlfill_ddpg_grad_buckets(void *d_workspace, int batch, float **critic_grad,
     return ERLFILL_OK;
 }
 
+int erlfill_ddpg_exchange_buffers(void *d_workspace, int batch, float **critic_grad, int *critic_len, float **actor_grad, int *actor_len,
+                                  float **critic_reduced, float **actor_reduced, float **sumsq) {
+    if (!d_workspace || batch < 2) return ERLFILL_ERR_ARG;
+    Ws w;
+    carve(&w, (float *)d_workspace, batch);
+    if (critic_grad) *critic_grad = w.cgrad;
+    if (critic_len) *critic_len = CO::TOTAL + 3;
+    if (actor_grad) *actor_grad = w.agrad;
+    if (actor_len) *actor_len = AO::TOTAL;
+    if (critic_reduced) *critic_reduced = w.cred;
+    if (actor_reduced) *actor_reduced = w.ared;
+    if (sumsq) *sumsq = w.ssq;
+    return ERLFILL_OK;
+}
+
 int erlfill_ddpg_set_step(void *d_workspace, int batch, int adam_step, double lr_decay, void *stream) {
     if (!d_workspace || batch < 2 || adam_step < 1) return ERLFILL_ERR_ARG;
     Ws w;
@@ -753,10 +769,12 @@ int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h,
         gp.seg(w.cpart + kCPartC, G + CO::B8, 257, nt, kCPart);       // db8 | dW10 | db10
         gp.launch(st);
     }
+    const bool reduced = (phases & ERLFILL_PHASE_REDUCED) != 0;      // gradient + norm partials come from the peer exchange
     if (phases & ERLFILL_PHASE_CRITIC_APPLY) {
-        lr_kernel<<<1, 1, 0, st>>>(w.cgrad + CO::TOTAL, w.step, h->critic_lr, h->actor_lr, w.scal + 2);
-        sumsq_kernel<<<kSumsqBlocks, 256, 0, st>>>(CO::TOTAL, w.cgrad, w.ssq);
-        adam_soft_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(CO::TOTAL, n->critic, nullptr, n->critic_m, n->critic_v, w.cgrad,
+        const float *G = reduced ? w.cred : w.cgrad;
+        lr_kernel<<<1, 1, 0, st>>>(G + CO::TOTAL, w.step, h->critic_lr, h->actor_lr, w.scal + 2);
+        if (!reduced) sumsq_kernel<<<kSumsqBlocks, 256, 0, st>>>(CO::TOTAL, G, w.ssq);
+        adam_soft_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(CO::TOTAL, n->critic, nullptr, n->critic_m, n->critic_v, G,
                                                                   w.ssq, w.scal + 2, h->max_grad_norm, w.step, h->tau);
     }
     if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
@@ -785,8 +803,9 @@ int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h,
         actor_l2_grad_kernel<<<(AO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, w.scal + 6, G);
     }
     if (phases & ERLFILL_PHASE_ACTOR_APPLY) {
-        sumsq_kernel<<<kSumsqBlocks, 256, 0, st>>>(AO::TOTAL, w.agrad, w.ssq + kSumsqBlocks);
-        adam_soft_kernel<<<(AO::TOTAL + 255) / 256, 256, 0, st>>>(AO::TOTAL, n->actor, n->actor_target, n->actor_m, n->actor_v, w.agrad,
+        const float *G = reduced ? w.ared : w.agrad;
+        if (!reduced) sumsq_kernel<<<kSumsqBlocks, 256, 0, st>>>(AO::TOTAL, G, w.ssq + kSumsqBlocks);
+        adam_soft_kernel<<<(AO::TOTAL + 255) / 256, 256, 0, st>>>(AO::TOTAL, n->actor, n->actor_target, n->actor_m, n->actor_v, G,
                                                                   w.ssq + kSumsqBlocks, w.scal + 3, h->max_grad_norm, w.step, h->tau);
         // both soft updates happen after both optimiser steps (ddpg_agent.py:501-507)
         soft_update_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(CO::TOTAL, n->critic, n->critic_target, h->tau);

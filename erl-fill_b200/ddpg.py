@@ -189,16 +189,23 @@ class DDPGLearner:
                 with torch.cuda.graph(g):
                     if allreduce is None:
                         run(L.PHASE_ALL, 0)
-                    else:       # data-parallel: the two bucket all-reduces are captured between the phases
-                        cb, ab = self.grad_buckets(B)
-                        run(L.PHASE_CRITIC_GRAD, 0); allreduce(cb); run(L.PHASE_CRITIC_APPLY, 0)
-                        run(L.PHASE_ACTOR_GRAD, 0); allreduce(ab); run(L.PHASE_ACTOR_APPLY, 0)
+                    else:       # data-parallel: the two bucket exchanges are captured between the phases
+                        self._run_dp(run, allreduce, B, 0)
                 self._graphs[key] = g
             g.replay()
         elif allreduce is None:
             run(phases, self.adam_step)
         else:
-            cb, ab = self.grad_buckets(B)
-            run(L.PHASE_CRITIC_GRAD, self.adam_step); allreduce(cb); run(L.PHASE_CRITIC_APPLY, 0)
-            run(L.PHASE_ACTOR_GRAD, 0); allreduce(ab); run(L.PHASE_ACTOR_APPLY, 0)
+            self._run_dp(run, allreduce, B, self.adam_step)
         return self.report
+
+    def _run_dp(self, run, allreduce, B, adam_step):
+        """GRAD | average the bucket over the ranks | APPLY, for the critic and then the actor."""
+        if getattr(allreduce, "peer", False):      # parallel.PeerExchange: one-shot NVLink exchange fused with the norm partials
+            red = L.PHASE_REDUCED
+            run(L.PHASE_CRITIC_GRAD, adam_step); allreduce.exchange(0); run(L.PHASE_CRITIC_APPLY | red, 0)
+            run(L.PHASE_ACTOR_GRAD, 0); allreduce.exchange(1); run(L.PHASE_ACTOR_APPLY | red, 0)
+        else:                                      # any in-place averaging callback (parallel.GradSync: NCCL / gloo)
+            cb, ab = self.grad_buckets(B)
+            run(L.PHASE_CRITIC_GRAD, adam_step); allreduce(cb); run(L.PHASE_CRITIC_APPLY, 0)
+            run(L.PHASE_ACTOR_GRAD, 0); allreduce(ab); run(L.PHASE_ACTOR_APPLY, 0)

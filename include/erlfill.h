@@ -276,7 +276,10 @@ typedef struct {
 } erlfill_ddpg_hyper;
 
 typedef enum { ERLFILL_PHASE_CRITIC_GRAD = 1, ERLFILL_PHASE_CRITIC_APPLY = 2, ERLFILL_PHASE_ACTOR_GRAD = 4,
-               ERLFILL_PHASE_ACTOR_APPLY = 8, ERLFILL_PHASE_ALL = 15 } erlfill_ddpg_phase;
+               ERLFILL_PHASE_ACTOR_APPLY = 8, ERLFILL_PHASE_ALL = 15,
+               /* with *_APPLY: take the gradient (and its sum-of-squares partials) that erlfill_ddpg_peer_allreduce left in
+                * the reduced buffers instead of the local bucket */
+               ERLFILL_PHASE_REDUCED = 16 } erlfill_ddpg_phase;
 
 /* bytes of the caller-provided device workspace for a given minibatch size */
 size_t erlfill_ddpg_workspace_bytes(int batch);
@@ -294,6 +297,37 @@ int erlfill_ddpg_set_step(void *d_workspace, int batch, int adam_step, double lr
  * critic_lr, actor_lr. */
 int erlfill_ddpg_update(const erlfill_ddpg_nets *nets, const erlfill_ddpg_hyper *hyper, const float *d_batch,
                         const float *d_next_emotion, void *d_workspace, int phases, float *d_report, void *stream);
+
+/* Exchange buffers inside the workspace: the two gradient buckets (as erlfill_ddpg_grad_buckets), the two reduced
+ * buffers of the same lengths and the [2][64] sum-of-squares partials. */
+int erlfill_ddpg_exchange_buffers(void *d_workspace, int batch, float **critic_grad, int *critic_len, float **actor_grad,
+                                  int *actor_len, float **critic_reduced, float **actor_reduced, float **sumsq);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Data-parallel gradient exchange over NVLink peer memory            */
+/* ------------------------------------------------------------------------------------------ */
+/* The reference has no multi-GPU path (nothing to mirror).  One process per GPU; each rank puts its update workspace
+ * (+ erlfill_peer_ctrl_bytes() of control block behind it) in a block from erlfill_peer_alloc, ships the 64-byte IPC handle
+ * to the other ranks of the node (any transport: torch.distributed.all_gather_object), and maps theirs with
+ * erlfill_peer_open.  These four are the only entry points that allocate or map memory. */
+#define ERLFILL_MAX_PEERS 8
+typedef struct {
+    int32_t world, rank;
+    void *ws[ERLFILL_MAX_PEERS];     /* update workspace of every rank as mapped in THIS process (own entry: the local block) */
+    void *ctrl[ERLFILL_MAX_PEERS];   /* control block of every rank (= ws + workspace bytes rounded up to 256) */
+} erlfill_peer_group;
+size_t erlfill_peer_ctrl_bytes(void);
+int erlfill_peer_alloc(size_t bytes, void **dptr, unsigned char handle[64]);          /* cudaMalloc + zero + IPC handle */
+int erlfill_peer_open(int peer_device, const unsigned char handle[64], void **mapped); /* peer access + cudaIpcOpenMemHandle */
+int erlfill_peer_close(void *mapped);
+int erlfill_peer_free(void *dptr);
+/* Averages bucket `which` (0 critic incl. the 3 emotion means, 1 actor) over the ranks in ONE pass over peer memory, in rank
+ * order (bit-identical on every rank), into the reduced buffer, and writes the sum-of-squares partials of the reduced
+ * gradient.  Call between X_GRAD and (X_APPLY | ERLFILL_PHASE_REDUCED); stream-ordered, graph-capturable, no host sync.
+ * Every rank must make the same sequence of calls. */
+int erlfill_ddpg_peer_allreduce(const erlfill_peer_group *g, int batch, int which, void *stream);
+/* 1 in *error_out if a wait for a peer timed out (about 2 s) since the allocation; synchronises the device. */
+int erlfill_peer_error(const erlfill_peer_group *g, int *error_out);
 
 /* ------------------------------------------------------------------------------------------ */
 /* TD3 and SAC (BASELINE.json configs[4])                         */

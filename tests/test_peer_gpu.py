@@ -1,0 +1,32 @@
+"""GPU (needs >= 2 GPUs on the box, skipped otherwise): the peer-memory gradient exchange of the data-parallel update
+(csrc/peer.cu) against the NCCL all-reduce path, through tools/dp_check.py under torchrun.
+
+Bars: replicas bit-identical across ranks after the updates; parameters equal to the NCCL path's within fp32 summation
+order (world 2: a + b is commutative, so bit-exact; larger worlds 1e-6); no peer wait timed out."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+def test_peer_exchange_matches_nccl_allreduce():
+    world = min(torch.cuda.device_count(), 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tools", "dp_check.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=180, cwd=ROOT)
+    line = [l for l in p.stdout.splitlines() if l.startswith("DP_CHECK ")]
+    assert p.returncode == 0 and line, p.stdout[-2000:] + p.stderr[-4000:]
+    res = json.loads(line[-1][len("DP_CHECK "):])
+    assert len(res) == world
+    for r in res:
+        assert r["peer_error"] == 0 and r["same_across_ranks"], r
+        tol = 0.0 if world == 2 else 1e-6
+        assert r["max_abs_diff_critic_vs_nccl"] <= tol and r["max_abs_diff_actor_vs_nccl"] <= tol, r
+        assert r["max_abs_diff_report_vs_nccl"] <= 1e-6, r

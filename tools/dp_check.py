@@ -1,0 +1,82 @@
+"""Two-or-more-rank check of the data-parallel ER-DDPG update (run under torchrun, one rank per GPU):
+the peer-memory exchange (parallel.PeerExchange, csrc/peer.cu) against the NCCL all-reduce path (parallel.GradSync) on
+identical replicas and per-rank minibatches, plus timing of both.  Used by tests/test_peer_gpu.py.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/dp_check.py
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import erlfill_b200 as E  # noqa: E402
+from erlfill_b200 import _lib as L, ddpg, init, parallel  # noqa: E402
+
+
+def main():
+    rank, world, local = parallel.env_info()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    parallel.init("nccl", dev)
+    B = int(os.environ.get("DP_CHECK_BATCH", 512))
+    bounds = E.conditions.EXPERIMENT_3["variant_25kg"]["bounds"]
+    a_sd, c_sd, _ = init.er_ddpg_state_dicts(bounds, seed=3, with_transformer=False)     # identical replicas
+    g = torch.Generator().manual_seed(100 + rank)                                          # different minibatch per rank
+    batch = torch.zeros(B, 20)
+    batch[:, 0:2] = torch.rand(B, 2, generator=g) * 5
+    batch[:, 2:12] = torch.rand(B, 10, generator=g) * 2 - 1
+    batch[:, 12] = torch.rand(B, generator=g) * 9000 - 3000
+    batch[:, 13:15] = torch.rand(B, 2, generator=g) * 5
+    batch[:, 15] = (torch.rand(B, generator=g) < 0.05).float()
+    batch[:, 16:19] = torch.rand(B, 3, generator=g)
+    batch = batch.to(dev)
+    ne = torch.tensor([0.4, 0.6, 0.2], device=dev)
+    out = {}
+    learners = {}
+    for mode in ("nccl", "peer"):
+        lr = ddpg.DDPGLearner(a_sd, c_sd, device=dev, batch_size=B)
+        ex = parallel.GradSync(world) if mode == "nccl" else parallel.PeerExchange(lr, B)
+        reps = []
+        for it in range(4):                       # the first runs eagerly, the rest replay the captured graph
+            reps.append(lr.update(batch, ne, 3, allreduce=ex).clone())
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        ev0.record()
+        n_t = 50
+        for it in range(n_t):
+            lr.update(batch, ne, 3, allreduce=ex)
+        ev1.record()
+        torch.cuda.synchronize()
+        out[mode + "_ms"] = ev0.elapsed_time(ev1) / n_t
+        learners[mode] = (lr, ex, torch.stack(reps).cpu())
+    (ln, _, rn), (lp, ex, rp) = learners["nccl"], learners["peer"]
+    err = ex.error()
+    # replicas identical across ranks (bit-exact): compare with rank 0's parameters
+    ref = lp.critic.flat.clone()
+    dist.broadcast(ref, src=0)
+    same_across_ranks = bool(torch.equal(ref, lp.critic.flat))
+    refa = lp.actor.flat.clone()
+    dist.broadcast(refa, src=0)
+    same_across_ranks &= bool(torch.equal(refa, lp.actor.flat))
+    d_c = float((ln.critic.flat - lp.critic.flat).abs().max())
+    d_a = float((ln.actor.flat - lp.actor.flat).abs().max())
+    d_rep = float((rn - rp).abs().max())
+    ex.close()
+    res = {"rank": rank, "world": world, "batch": B, "peer_error": err, "same_across_ranks": same_across_ranks,
+           "max_abs_diff_critic_vs_nccl": d_c, "max_abs_diff_actor_vs_nccl": d_a, "max_abs_diff_report_vs_nccl": d_rep,
+           "nccl_ms_per_update": out["nccl_ms"], "peer_ms_per_update": out["peer_ms"]}
+    allres = [None] * world
+    dist.all_gather_object(allres, res)
+    if rank == 0:
+        print("DP_CHECK " + json.dumps(allres), flush=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)       # skip NCCL / interpreter teardown (graphs that captured collectives are still alive)
+
+
+if __name__ == "__main__":
+    main()
