@@ -930,7 +930,7 @@ __device__ __forceinline__ SimResult simulate_warp(const SimParams &p, double sy
     return res;
 }
 
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = 1;
 
 // K1: the simulator, one warp per env.  Results travel to K2 in the step's own output slots (no workspace):
 // final_weight (binary64) in next_state[i], tick count in reward[i], draws in obs[i].x.

@@ -58,10 +58,13 @@ class VecFillEnv:
         self.ring_head = torch.zeros(n, dtype=torch.int32, device=dev)
         self.ring = torch.zeros(L.RING, n, dtype=torch.float64, device=dev)
         self.obs = torch.zeros(n, 2, dtype=torch.float32, device=dev)
-        # step outputs (reused every step)
-        self.next_state = torch.zeros(n, 2, dtype=torch.float32, device=dev)
-        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        # step outputs (reused every step).  next_state | reward | done are views into ONE allocation so that a host
+        # consumer fetches them with a single device-to-host copy (step_host)
+        self._out_pack = torch.zeros(13 * n, dtype=torch.uint8, device=dev)
+        self.next_state = self._out_pack[:8 * n].view(torch.float32).view(n, 2)
+        self.reward = self._out_pack[8 * n:12 * n].view(torch.float32)
+        self.done = self._out_pack[12 * n:]
+        self._host = None
         self.final_weight = torch.zeros(n, dtype=torch.float64, device=dev)
         self.total_time = torch.zeros(n, dtype=torch.float64, device=dev)
         self.ticks = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -135,6 +138,21 @@ class VecFillEnv:
         self.step_idx += 1
         info = {"final_weight": self.final_weight, "total_time": self.total_time, "ticks": self.ticks}
         return self.next_state, self.reward, self.done, info
+
+    def step_host(self, actions_host):
+        """Host-facing step: float32[N,10] actions in (pinned) host memory in, (next_state, reward, done) as numpy-viewable
+        pinned host tensors out — one H2D copy, the step kernels, one D2H copy of the packed outputs, one stream sync."""
+        n = self.n_env
+        if self._host is None:
+            pack = torch.empty(13 * n, dtype=torch.uint8).pin_memory()
+            self._host = (torch.empty(n, 10, dtype=torch.float32, device=self.device), pack,
+                          pack[:8 * n].view(torch.float32).view(n, 2), pack[8 * n:12 * n].view(torch.float32), pack[12 * n:])
+        a_dev, pack, ns_h, r_h, d_h = self._host
+        a_dev.copy_(actions_host, non_blocking=True)
+        self.step(a_dev)
+        pack.copy_(self._out_pack, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return ns_h, r_h, d_h
 
 
 # ----------------------------------------------------------------------------------------------
