@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (container only).
 
-Run from the repo root:   python oracle/gen_golden.py [sim] [env] [emotion] [nets] [learn] [td3sac] [loop]
+Run from the repo root:   python oracle/gen_golden.py [sim] [env] [emotion] [nets] [learn] [td3sac] [loop] [esac]
 
 The reference (/root/reference) is imported through oracle/ref_shim.py (pymodbus stub +
 frozen clock).  All randomness is CPython `random` seeded per case,
@@ -646,10 +646,88 @@ def gen_loop():
     np.savez_compressed(os.path.join(GOLD, "loop_golden.npz"), **out)
     print("loop: calls", len(calls), "learns", int(np.sum(out["learn.ran"])), "rewards", rewards)
 
+# ----------------------------------------------------------------------------------------
+def gen_esac():
+    """N3 vectors: EmotionSACAgent.update() x3 and act() of the reference (ERL_Fill_agent.py) on an injected replay buffer
+    (B = 128), eval-mode EmotionTransformer; sampled indices tapped from random.sample, the two rsample() draws per update
+    re-drawn from the same torch seed."""
+    ref_shim.install()
+    import torch
+    import MutiConditionEnv as M
+    import ERL_Fill_agent as EF
+    cfg = BOUNDS["variant_25kg"]
+    env = M.MultiConditionWeightEnv({**{k: cfg[k] for k in ("target_weight", "target_weight_err", "target_time")},
+                                     "bounds": dict(cfg["bounds"])})
+    g = np.random.RandomState(21)
+    B, n_buf = 128, 600
+    buf = dict(states=(g.rand(n_buf, 2) * 5).astype(np.float32), actions=(g.rand(n_buf, 10) * 2 - 1).astype(np.float32),
+               rewards=g.uniform(-3000, 6000, n_buf).astype(np.float32), next_states=(g.rand(n_buf, 2) * 5).astype(np.float32),
+               dones=(g.rand(n_buf) < 0.05), emotions=g.rand(n_buf, 3).astype(np.float32))
+    out = {"buf_" + k: np.asarray(v) for k, v in buf.items()}
+    torch.manual_seed(5)
+    with _quiet():
+        agent = EF.EmotionSACAgent(env, device="cpu")
+    agent.emotion.transformer.eval()
+    torch.backends.mha.set_fastpath_enabled(False)
+    for i in range(n_buf):
+        agent.memory.add((buf["states"][i], buf["actions"][i].astype(np.float64), float(buf["rewards"][i]), buf["next_states"][i],
+                          float(buf["dones"][i]), buf["emotions"][i]))
+    out.update(_sd(agent.policy, "p0."))
+    out.update(_sd(agent.q1, "q1_0."))
+    out.update(_sd(agent.q2, "q2_0."))
+    for t in range(6):      # an emotion history, so get_emotion() is a real S = 20 call and e_now != e_prev between updates
+        agent.emotion.update(float(g.uniform(-2000, 4000)), (g.rand(10) * 100).astype(np.float32))
+    random.seed(79)
+    idx, e1, e2, res, enow = [], [], [], [], []
+    orig = EF.random.sample
+
+    def tapped(pop, k):
+        st = EF.random.getstate()
+        r = orig(pop, k)
+        EF.random.setstate(st)
+        idx.append(np.array(orig(range(len(pop)), k)))
+        return r
+    EF.random.sample = tapped
+    upd_rewards, upd_moves = [], []
+    try:
+        with _quiet():
+            for it in range(3):
+                torch.manual_seed(700 + it)
+                e1.append(torch.randn(B, 10).numpy()); e2.append(torch.randn(B, 10).numpy())
+                torch.manual_seed(700 + it)
+                enow.append(np.array(agent.emotion.get_emotion()))
+                r = agent.update()
+                res.append((r["q1_loss"], r["q2_loss"], r["policy_loss"], r["emo_reg"]))
+                rw, mv = float(g.uniform(-2000, 4000)), (g.rand(10) * 100).astype(np.float32)
+                upd_rewards.append(rw); upd_moves.append(mv)
+                agent.emotion.update(rw, mv)                       # the emotion moves between updates (train_erl_fill :538)
+    finally:
+        EF.random.sample = orig
+    # end-of-run weights: every 9th element of every tensor (fixture size); the per-update losses pin the steps in between
+    for name, mod in (("p3.", agent.policy), ("q1_3.", agent.q1), ("q2_3.", agent.q2), ("q1t_3.", agent.q1_target), ("q2t_3.", agent.q2_target)):
+        out.update({k: v.reshape(-1)[::9].copy() for k, v in _sd(mod, name).items()})
+    out["idx"], out["eps_next"], out["eps_new"] = np.array(idx), np.array(e1), np.array(e2)
+    out["res"], out["e_now"] = np.array(res, np.float64), np.array(enow)
+    out["upd_rewards"], out["upd_moves"] = np.array(upd_rewards), np.array(upd_moves)
+    # act (:322-348): stochastic (injected eps), deterministic
+    st = (g.rand(6, 2) * 5).astype(np.float32)
+    acts, eps = [], []
+    out["act_emotion"] = np.array(agent.emotion.get_emotion())
+    for i in range(6):
+        torch.manual_seed(60 + i)
+        eps.append(torch.randn(1, 10).numpy()[0])
+        torch.manual_seed(60 + i)
+        acts.append(agent.act(st[i]))
+    out["act_states"], out["act_eps"], out["act_out"] = st, np.array(eps), np.array(acts)
+    out["act_det"] = np.array([agent.act(st[i], deterministic=True) for i in range(6)])
+    out["meta"] = _meta("N3 EmotionSACAgent.update x3 + act, B=128, injected buffer, tapped indices and noise, eval-mode transformer")
+    np.savez_compressed(os.path.join(GOLD, "esac_golden.npz"), **out)
+    print("esac:", out["res"].tolist())
+
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["sim", "env", "emotion"]
     os.chdir("/tmp")
     for w in which:
-        {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion, "nets": gen_nets, "learn": gen_learn, "td3sac": gen_td3sac, "loop": gen_loop}[w]()
+        {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion, "nets": gen_nets, "learn": gen_learn, "td3sac": gen_td3sac, "loop": gen_loop, "esac": gen_esac}[w]()

@@ -318,3 +318,86 @@ def sac_update(policy, q1, q2, q1_t, q2_t, opt, batch, eps_next, eps_new, gamma=
         q1_t[k] = tau * q1[k] + (1 - tau) * q1_t[k]
         q2_t[k] = tau * q2[k] + (1 - tau) * q2_t[k]
     return losses[0], losses[1], pl.item()
+
+
+# ---------------------------------------------------------------------------------------------
+# EmotionSAC: DifferentModules/ERL_Fill_agent.py
+# ---------------------------------------------------------------------------------------------
+ESAC_POLICY_ORDER = ["state_encoder.0.weight", "state_encoder.0.bias", "state_encoder.1.weight", "state_encoder.1.bias",
+                     "emotion_encoder.0.weight", "emotion_encoder.0.bias", "emotion_encoder.1.weight", "emotion_encoder.1.bias",
+                     "policy_net.0.weight", "policy_net.0.bias", "policy_net.2.weight", "policy_net.2.bias",
+                     "mean_layer.weight", "mean_layer.bias", "log_std_layer.weight", "log_std_layer.bias",
+                     "emotion_adapter_mean.0.weight", "emotion_adapter_mean.0.bias",
+                     "emotion_adapter_std.0.weight", "emotion_adapter_std.0.bias"]
+ESAC_Q_ORDER = ["state_encoder.0.weight", "state_encoder.0.bias", "state_encoder.1.weight", "state_encoder.1.bias",
+                "action_encoder.0.weight", "action_encoder.0.bias", "action_encoder.1.weight", "action_encoder.1.bias",
+                "emotion_encoder.0.weight", "emotion_encoder.0.bias", "emotion_encoder.1.weight", "emotion_encoder.1.bias",
+                "q_net.0.weight", "q_net.0.bias", "q_net.2.weight", "q_net.2.bias", "q_net.4.weight", "q_net.4.bias"]
+
+
+def _enc(w, name, x):
+    """Linear -> LayerNorm -> ReLU encoder (ERL_Fill_agent.py:78-89, 196-213)."""
+    z = F.linear(x, w[name + ".0.weight"], w[name + ".0.bias"])
+    return F.relu(F.layer_norm(z, (z.shape[-1],), w[name + ".1.weight"], w[name + ".1.bias"], 1e-5))
+
+
+def esac_policy_forward(w, s, e):
+    """EmotionGaussianPolicy.forward (ERL_Fill_agent.py:117-144): (mean, log_std clamped to [-20, 2])."""
+    x = torch.cat([_enc(w, "state_encoder", s), _enc(w, "emotion_encoder", e)], dim=-1)
+    x = F.relu(F.linear(x, w["policy_net.0.weight"], w["policy_net.0.bias"]))
+    x = F.relu(F.linear(x, w["policy_net.2.weight"], w["policy_net.2.bias"]))
+    mean = F.linear(x, w["mean_layer.weight"], w["mean_layer.bias"]) + \
+        torch.tanh(F.linear(e, w["emotion_adapter_mean.0.weight"], w["emotion_adapter_mean.0.bias"]))
+    log_std = F.linear(x, w["log_std_layer.weight"], w["log_std_layer.bias"]) + \
+        torch.tanh(F.linear(e, w["emotion_adapter_std.0.weight"], w["emotion_adapter_std.0.bias"]))
+    return mean, torch.clamp(log_std, -20, 2)
+
+
+def esac_policy_sample(w, s, e, eps):
+    """EmotionGaussianPolicy.sample (:146-167) with the rsample() draw injected: z = mean + std * eps."""
+    mean, log_std = esac_policy_forward(w, s, e)
+    std = torch.exp(log_std)
+    z = mean + std * eps
+    a = torch.tanh(z)
+    log_prob = -((z - mean) ** 2) / (2 * std ** 2) - log_std - math.log(math.sqrt(2 * math.pi)) - torch.log(1 - a.pow(2) + 1e-6)
+    return a, log_prob.sum(dim=-1, keepdim=True)
+
+
+def esac_q_forward(w, s, a, e):
+    """EmotionAwareQNetwork.forward (:222-239)."""
+    x = torch.cat([_enc(w, "state_encoder", s), _enc(w, "action_encoder", a), _enc(w, "emotion_encoder", e)], dim=-1)
+    x = F.relu(F.linear(x, w["q_net.0.weight"], w["q_net.0.bias"]))
+    x = F.relu(F.linear(x, w["q_net.2.weight"], w["q_net.2.bias"]))
+    return F.linear(x, w["q_net.4.weight"], w["q_net.4.bias"])
+
+
+def esac_update(policy, q1, q2, q1_t, q2_t, opt, batch, eps_next, eps_new, e_now, e_prev, gamma=0.99, tau=0.005, alpha=0.3,
+                lr=3e-4):
+    """One EmotionSACAgent.update() (ERL_Fill_agent.py:365-448).  opt as in sac_update; batch additionally holds "emotions".
+    The emotion regulariser ||e_now - e_prev||_2 (:417-430) is a constant of the parameters: reported, no gradient.
+    Returns (q1_loss, q2_loss, policy_loss, emo_reg)."""
+    s, a, r = batch["states"], batch["actions"], batch["rewards"].unsqueeze(1)
+    s2, d, e = batch["next_states"], batch["dones"].unsqueeze(1), batch["emotions"]
+    with torch.no_grad():
+        a2, lp2 = esac_policy_sample(policy, s2, e, eps_next)
+        y = r + (1 - d) * gamma * (torch.min(esac_q_forward(q1_t, s2, a2, e), esac_q_forward(q2_t, s2, a2, e)) - alpha * lp2)
+    opt["step"] += 1
+    losses = []
+    for net, m, v in ((q1, opt["q1m"], opt["q1v"]), (q2, opt["q2m"], opt["q2v"])):
+        ps = [net[k].clone().requires_grad_(True) for k in ESAC_Q_ORDER]
+        loss = F.mse_loss(esac_q_forward(dict(zip(ESAC_Q_ORDER, ps)), s, a, e), y)
+        gs = torch.autograd.grad(loss, ps)
+        for k, p in zip(ESAC_Q_ORDER, adam_step([p.detach() for p in ps], list(gs), m, v, opt["step"], lr)):
+            net[k] = p
+        losses.append(loss.item())
+    pp = [policy[k].clone().requires_grad_(True) for k in ESAC_POLICY_ORDER]
+    an, lp = esac_policy_sample(dict(zip(ESAC_POLICY_ORDER, pp)), s, e, eps_new)
+    pl = (alpha * lp - esac_q_forward(q1, s, an, e)).mean()
+    pg = torch.autograd.grad(pl, pp)
+    for k, p in zip(ESAC_POLICY_ORDER, adam_step([p.detach() for p in pp], list(pg), opt["pm"], opt["pv"], opt["step"], lr)):
+        policy[k] = p
+    for k in ESAC_Q_ORDER:
+        q1_t[k] = tau * q1[k] + (1 - tau) * q1_t[k]
+        q2_t[k] = tau * q2[k] + (1 - tau) * q2_t[k]
+    emo_reg = float(torch.norm(torch.as_tensor(e_now, dtype=torch.float32) - torch.as_tensor(e_prev, dtype=torch.float32), p=2))
+    return losses[0], losses[1], pl.item(), emo_reg
