@@ -17,13 +17,16 @@ def __getattr__(name):
     if name == "VecERDDPG":
         from . import agents
         return agents.VecERDDPG
+    if name == "VecEmotionSAC":
+        from . import esac
+        return esac.VecEmotionSAC
     if name in ("VecTD3", "VecSAC"):
         from . import td3sac
         return getattr(td3sac, name)
-    if name in ("DDPGAgent", "EmotionModule", "EmotionModuleNone", "TD3Agent", "SACAgent", "reset_actor_scaling"):
+    if name in ("DDPGAgent", "EmotionModule", "EmotionModuleNone", "TD3Agent", "SACAgent", "EmotionSACAgent", "reset_actor_scaling"):
         from . import dropin
         return getattr(dropin, name)
-    if name in ("init", "td3sac", "nets", "ddpg", "agents", "envs", "dropin", "loops"):
+    if name in ("init", "td3sac", "nets", "ddpg", "agents", "envs", "dropin", "loops", "esac", "parallel"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

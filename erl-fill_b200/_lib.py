@@ -103,6 +103,7 @@ class SACHyper(C.Structure):
 
 
 TD3_ACTOR_PARAMS, TD3_CRITIC_PARAMS, SAC_POLICY_PARAMS, SAC_Q_PARAMS = 69130, 138754, 71700, 138754
+ESAC_POLICY_PARAMS, ESAC_Q_PARAMS = 146468, 210369
 PHASE_CRITIC_GRAD, PHASE_CRITIC_APPLY, PHASE_ACTOR_GRAD, PHASE_ACTOR_APPLY, PHASE_ALL, PHASE_REDUCED = 1, 2, 4, 8, 15, 16
 MAX_PEERS = 8
 
@@ -127,6 +128,8 @@ EXPORTS = [
     "erlfill_peer_free", "erlfill_ddpg_peer_allreduce", "erlfill_peer_error",
     "erlfill_t1_workspace_bytes", "erlfill_t1_act_workspace_bytes", "erlfill_t1_grad_buckets", "erlfill_td3_act",
     "erlfill_td3_update", "erlfill_sac_act", "erlfill_sac_update",
+    "erlfill_esac_workspace_bytes", "erlfill_esac_act_workspace_bytes", "erlfill_esac_grad_buckets", "erlfill_esac_act",
+    "erlfill_esac_update",
 ]
 
 _lib = None
@@ -146,6 +149,8 @@ def lib():
         L.erlfill_t1_workspace_bytes.restype = C.c_size_t
         L.erlfill_t1_act_workspace_bytes.restype = C.c_size_t
         L.erlfill_peer_ctrl_bytes.restype = C.c_size_t
+        L.erlfill_esac_workspace_bytes.restype = C.c_size_t
+        L.erlfill_esac_act_workspace_bytes.restype = C.c_size_t
         for name in EXPORTS:
             getattr(L, name)
         _lib = L

@@ -392,6 +392,36 @@ int erlfill_sac_act(const float *d_policy, int n, const float *d_state, const fl
 int erlfill_sac_update(const erlfill_sac_nets *nets, const erlfill_sac_hyper *hyper, const float *d_batch, const float *d_eps_next,
                        const float *d_eps_new, void *d_workspace, int phases, float *d_report, void *stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* EmotionSAC: DifferentModules/ERL_Fill_agent.py                */
+/* ------------------------------------------------------------------------------------------ */
+/* Flat fp32 parameter buffers in the reference's parameters() order.
+ *   policy (146,468): EmotionGaussianPolicy — state_encoder.0 [256][2] .bias | state_encoder.1 (LayerNorm) weight, bias |
+ *       emotion_encoder.0 [32][3] .bias | emotion_encoder.1 weight, bias | policy_net.0 [256][288] .bias | policy_net.2 [256][256] .bias |
+ *       mean_layer [10][256] .bias | log_std_layer [10][256] .bias | emotion_adapter_mean.0 [10][3] .bias | emotion_adapter_std.0 [10][3] .bias
+ *   q (2 x 210,369): EmotionAwareQNetwork q1 then q2 — state_encoder.0 [256][2] .bias | .1 | action_encoder.0 [256][10] .bias | .1 |
+ *       emotion_encoder.0 [32][3] .bias | .1 | q_net.0 [256][544] .bias | q_net.2 [256][256] .bias | q_net.4 [1][256] .bias      (:63-239) */
+#define ERLFILL_ESAC_POLICY_PARAMS 146468
+#define ERLFILL_ESAC_Q_PARAMS 210369
+typedef erlfill_sac_nets erlfill_esac_nets;      /* policy | q = [q1 | q2] | q_target | Adam moments */
+typedef erlfill_sac_hyper erlfill_esac_hyper;    /* gamma 0.99, tau 0.005, alpha 0.3, lr 3e-4 (:262-290) */
+size_t erlfill_esac_workspace_bytes(int batch);
+size_t erlfill_esac_act_workspace_bytes(void);
+/* the two gradient buckets inside the workspace ([q1 | q2] and the policy) for a data-parallel all-reduce between the phases */
+int erlfill_esac_grad_buckets(void *d_workspace, int batch, float **q_grad, float **policy_grad);
+/* EmotionSACAgent.act (:322-348) for n rows: d_state [n][2], d_emotion [n][3] (or [3] with emotion_broadcast), d_eps [n][10] the
+ * rsample() normals (NULL: Philox (row_id_base + row, step_idx)); deterministic: tanh(mean).  Physical action and the
+ * normalised action (what remember() stores, :350-363). */
+int erlfill_esac_act(const float *d_policy, int n, const float *d_state, const float *d_emotion, int emotion_broadcast, const float *d_eps,
+                     int deterministic, const float *d_lo, const float *d_hi, uint64_t seed, uint32_t row_id_base, uint32_t step_idx,
+                     float *d_action, float *d_norm_action, void *d_workspace, void *stream);
+/* EmotionSACAgent.update (:365-448) on gathered records d_batch [B][ERLFILL_REC] (the emotion columns are the stored emotions).
+ * d_eps_next / d_eps_new [B][10]: the two rsample() draws (NULL: Philox); d_emotion_now / d_emotion_prev [3]: the operands of the
+ * emotion regulariser (reported; it has no gradient).  d_report [4] = q1_loss, q2_loss, policy_loss, emo_reg. */
+int erlfill_esac_update(const erlfill_esac_nets *nets, const erlfill_esac_hyper *hyper, const float *d_batch, const float *d_eps_next,
+                        const float *d_eps_new, const float *d_emotion_now, const float *d_emotion_prev, void *d_workspace, int phases,
+                        float *d_report, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
