@@ -10,6 +10,7 @@ One JSON line on stdout (rank 0).  A "step" is one lock-step pass of the workloa
   rollout  configs[2]: MultiConditionWeightEnv, EmotionModule transformer -> ER-DDPG actor + OU -> env step -> emotion update
   update   configs[3]: ER-DDPG update, minibatch 4096 from a 1M-transition replay (sample + gather + U1-U5)
   td3|sac  configs[4]: full TD3 / SAC loop (act -> env step -> remember -> update of B=4096), 131,072 envs/GPU
+  esac     EmotionSAC (ERL_Fill_agent.py) full loop incl. the emotion transformer, 65,536 envs/GPU
   all      (default) the sim line, with the rollout and update results attached under "other_workloads"
 `value` is device-timed with inputs resident in HBM; `e2e` goes through the public Python API with pinned HOST
 buffers (H2D of the step's inputs, D2H of its results inside the timed region).
@@ -389,9 +390,13 @@ def wl_loop(args, rank, world, device, timer):
     kind = args.workload
     env = E.VecFillEnv(list(K.EXPERIMENT_3.values())[:1], n, kind="multi", max_steps=100, seed=0, device=device, env_id_base=rank * n,
                        sim_mode=args.sim_mode)
-    agent = (E.VecTD3 if kind == "td3" else E.VecSAC)(env, seed=0, batch_size=B, memory_size=max(4 * n, 1 << 20), rank=rank)
+    if kind == "esac":      # EmotionSAC (row N3): the emotion transformer runs every step on the tensor-core kernel
+        agent = E.VecEmotionSAC(env, seed=0, batch_size=B, memory_size=max(4 * n, 1 << 20), rank=rank, emotion_precision="bf16")
+        agent.reset()
+    else:
+        agent = (E.VecTD3 if kind == "td3" else E.VecSAC)(env, seed=0, batch_size=B, memory_size=max(4 * n, 1 << 20), rank=rank)
+        env.reset()
     sync = parallel.GradSync(world) if world > 1 else None
-    env.reset()
 
     def step():
         agent.rollout_step()
@@ -408,7 +413,7 @@ def wl_loop(args, rank, world, device, timer):
     ticks_all = timer.sumr(int(env.tick_sum.item()))
     obs_host = env.obs.cpu().pin_memory()
     res_host = [torch.empty(n, 2).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory(),
-                torch.empty(3).pin_memory()]
+                torch.empty(4 if kind == "esac" else 3).pin_memory()]
 
     def e2e_step():
         env.obs.copy_(obs_host, non_blocking=True)
@@ -429,8 +434,10 @@ def wl_loop(args, rank, world, device, timer):
         "metric": "env_steps_per_sec", "value": units / (total_ms * 1e-3), "unit": "env-steps/s",
         "dtype": "f64 simulator, f32 (3xTF32 tensor-core GEMM) networks", "ms_per_step": total_ms / args.steps, "wall_s_timed_region": wall,
         "updates_per_sec": args.steps / (total_ms * 1e-3),
-        "config": {"workload": "configs[4]: %s on MultiConditionWeightEnv, %d envs/GPU, full loop: act -> env step -> remember -> "
-                               "one update of minibatch %d" % (kind.upper(), n, B), "n_env_per_gpu": n, "minibatch_per_gpu": B,
+        "config": {"workload": "configs[4]: %s on MultiConditionWeightEnv, %d envs/GPU, full loop: %sact -> env step -> remember -> "
+                               "one update of minibatch %d" % ("EmotionSAC" if kind == "esac" else kind.upper(), n,
+                                                               "emotion transformer -> " if kind == "esac" else "", B),
+                   "n_env_per_gpu": n, "minibatch_per_gpu": B,
                    "parallelism": "env-sharded x%d, data-parallel update (flat-bucket gradient all-reduce)" % world,
                    "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
         "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / units,
@@ -462,7 +469,7 @@ def run_ours(args):
     timer = Timer(device, world)
     sampler = ClockSampler(local)
     sampler.start()
-    wl = {"sim": wl_sim, "rollout": wl_rollout, "update": wl_update, "td3": wl_loop, "sac": wl_loop}
+    wl = {"sim": wl_sim, "rollout": wl_rollout, "update": wl_update, "td3": wl_loop, "sac": wl_loop, "esac": wl_loop}
     head = "sim" if args.workload == "all" else args.workload
     if args.workload == "all":
         args.n_env = args.n_env or 4096
@@ -594,7 +601,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "sim", "rollout", "update", "td3", "sac"],
+    ap.add_argument("--workload", default="all", choices=["all", "sim", "rollout", "update", "td3", "sac", "esac"],
                     help="all = the sim headline line plus compact rollout and update results under other_workloads")
     ap.add_argument("--n-env", type=int, default=None)
     ap.add_argument("--actions", default="pid", choices=["pid", "random"])
@@ -608,7 +615,7 @@ def main():
                     help="EmotionTransformer kernel of the rollout: tcgen05 bf16 (default) or the exact fp32 SIMT twin")
     args = ap.parse_args()
     if args.n_env is None:
-        args.n_env = {"all": 4096, "sim": 4096, "rollout": 65536, "update": 256, "td3": 131072, "sac": 131072}[args.workload]
+        args.n_env = {"all": 4096, "sim": 4096, "rollout": 65536, "update": 256, "td3": 131072, "sac": 131072, "esac": 65536}[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

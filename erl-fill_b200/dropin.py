@@ -27,7 +27,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from . import ddpg, init, nets, td3sac
+from . import ddpg, esac, init, nets, td3sac
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -208,7 +208,9 @@ class EmotionModule:
         self._r.fill_(float(reward))
         mv = np.asarray(movement, dtype=np.float32).reshape(-1)
         if mv.shape[0] != 2:
-            raise ValueError("EmotionModule.update: movement must be the 2-dimensional state difference")
+            # only ||movement|| enters (EmotionModule.py:139): a k-vector (train_erl_fill passes the 10-vector action, :538) goes
+            # to the kernel as the 2-vector (||movement||, 0), capped at 2 where the clip to [0, 1] has long saturated
+            mv = np.array([min(float(np.linalg.norm(np.asarray(movement, dtype=np.float64))), 2.0), 0.0], dtype=np.float32)
         self._mv.copy_(torch.from_numpy(mv).view(1, 2))
         nets.emotion_update(self.emo, self._r, self._zero2, self._mv)              # (0 + movement) - 0: exact
         self._cache = None
@@ -683,3 +685,106 @@ class SACAgent(_T1Scalar):
 
     def load(self, path):
         self.policy.load_state_dict(torch.load(path, map_location=self.device, weights_only=False)["policy"])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# EmotionSAC
+# ---------------------------------------------------------------------------------------------------------
+class _EmotionReplay:
+    """EmotionReplayBuffer surface (ERL_Fill_agent.py:17-60): deque(maxlen) of (s, a_norm, r, s', d, e) + add / sample / len."""
+
+    def __init__(self, capacity=100000):
+        self.buffer = collections.deque(maxlen=capacity)
+
+    def add(self, transition):
+        self.buffer.append(transition)
+
+    def sample(self, batch_size):
+        return random.sample(self.buffer, batch_size)
+
+    def __len__(self):
+        return len(self.buffer)
+
+
+class EmotionSACAgent(_T1Scalar):
+    """EmotionSACAgent (ERL_Fill_agent.py:242-489) at N = 1.  Construct after `torch.manual_seed(s)` for the reference's initial
+    weights (EmotionModule, policy, q1, q2 and the two targets consume the global RNG in that order, :270-281)."""
+
+    def __init__(self, env, lambda_emo=0.05, device="cuda", state_dicts=None):
+        self._setup(env, device)
+        self.lambda_emo = lambda_emo
+        self.train_step = 1
+        if state_dicts is None:
+            self.emotion = EmotionModule(device=self.device)
+            _, pol, q = esac.esac_state_dicts(None, with_transformer=False)
+        else:
+            trans, pol, q = state_dicts
+            self.emotion = EmotionModule(device=self.device, state_dict=trans)
+        self._vec = esac.VecEmotionSAC(self._view, batch_size=self.batch_size, state_dicts=(None, pol, q), lambda_emo=lambda_emo)
+        v = self._vec
+        self.policy = NetFacade("EmotionGaussianPolicy", v.policy, [k for k, _ in esac.POLICY_LAYOUT])
+        self.q1, self.q2 = _SACQFacade(v.q, "q1."), _SACQFacade(v.q, "q2.")
+        self.q1_target, self.q2_target = _SACQFacade(v.q_target, "q1."), _SACQFacade(v.q_target, "q2.")
+        self.gamma, self.tau, self.alpha = v.gamma, v.tau, v.alpha
+        self.offsets = np.array([(hi + lo) / 2 for lo, hi in env.bounds.values()])
+        self.scales = np.array([(hi - lo) / 2 for lo, hi in env.bounds.values()])
+        self.memory = _EmotionReplay()
+
+    def normalize_action(self, action):
+        return (action - self.offsets) / self.scales
+
+    def denormalize_action(self, norm_action):
+        return norm_action * self.scales + self.offsets
+
+    def act(self, state, deterministic=False, add_noise=True, eps=None):
+        """:322-348.  The reparameterisation draw is torch.randn(1, 10) (Normal.rsample on a CPU agent) unless given."""
+        det = deterministic or not add_noise
+        if eps is None and not det:
+            eps = torch.randn(1, self.action_dim)
+        d_eps = None if det else torch.as_tensor(eps, dtype=torch.float32).reshape(1, -1).to(self.device).contiguous()
+        self._vec.act(self._dev(state, 2), emotion=self.emotion.get_emotion_device(), deterministic=det, eps=d_eps)
+        return self.denormalize_action(self._vec.norm_action[0].cpu().numpy())
+
+    def remember(self, s, a, r, s_, d):
+        """:350-363: the stored emotion is get_emotion() at remember time."""
+        norm_a = self.normalize_action(np.asarray(a))
+        e = self.emotion.get_emotion()
+        self.memory.add((s, norm_a, r, s_, d, e))
+        v = self._vec
+        v.memory.insert(self._dev(s, 2), self._dev(norm_a, 10), torch.tensor([float(r)], dtype=torch.float32, device=self.device),
+                        self._dev(s_, 2), torch.tensor([1 if d else 0], dtype=torch.uint8, device=self.device), self._dev(e, 3))
+
+    def update(self, eps_next=None, eps_new=None):
+        """:365-448 -> {"q1_loss", "q2_loss", "policy_loss", "emo_reg"} or None."""
+        if len(self.memory) < self.batch_size:
+            return None
+        v = self._vec
+        v.gamma, v.tau, v.alpha = self.gamma, self.tau, self.alpha
+        if v.batch_size != self.batch_size:
+            import ctypes as C
+            v.batch_size = int(self.batch_size)
+            v.batch = torch.zeros(v.batch_size, L.REC, dtype=torch.float32, device=self.device)
+            v._ws = torch.zeros((L.lib().erlfill_esac_workspace_bytes(C.c_int(v.batch_size)) + 3) // 4, dtype=torch.float32, device=self.device)
+        idx = self._sample()
+        B, A = self.batch_size, self.action_dim
+        e1 = torch.randn(B, A) if eps_next is None else torch.as_tensor(eps_next, dtype=torch.float32)
+        e2 = torch.randn(B, A) if eps_new is None else torch.as_tensor(eps_new, dtype=torch.float32)
+        e_now = self.emotion.get_emotion_device()[0].contiguous().clone()
+        r = v.update(idx=idx, eps_next=e1.to(self.device).contiguous(), eps_new=e2.to(self.device).contiguous(), e_now=e_now).cpu().numpy()
+        return {"q1_loss": float(r[0]), "q2_loss": float(r[1]), "policy_loss": float(r[2]), "emo_reg": float(r[3])}
+
+    def save(self, path):
+        """:450-465: the policy, and the emotion transformer next to it as *_emo.pth."""
+        import os
+        if os.path.dirname(path):
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+        torch.save({"policy": self.policy.state_dict()}, path)
+        if hasattr(self.emotion, "transformer"):
+            self.emotion.save(path.replace(".pth", "_emo.pth"))
+
+    def load(self, path):
+        import os
+        self.policy.load_state_dict(torch.load(path, map_location=self.device, weights_only=False)["policy"])
+        emo_path = path.replace(".pth", "_emo.pth")
+        if hasattr(self.emotion, "transformer") and os.path.exists(emo_path):
+            self.emotion.load(emo_path)

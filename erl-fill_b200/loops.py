@@ -4,6 +4,7 @@ and the evaluation loops of `experiment_runner.py`, without the TensorBoard / lo
   train_ddpg(env, agent, ...)       ddpg_agent.py:628-729 — the exact call order across the env/agent boundary
                                     (reset, ou reset+anneal, act, step, emotion.update, remember, learn, get_emotion),
                                     for the N = 1 drop-ins of dropin.py / envs.py
+  train_erl_fill(env, agent, ...)   ERL_Fill_agent.py:526-541 — EmotionSAC's loop body
   test_agent(env, agent, ...)       experiment_runner.py:541-556 (and :160-180) — deterministic test episodes and the
                                     per-episode record the reference writes to its CSV (`results_detail`, :566-577)
   evaluate_batched(agent, ...)      the same evaluation for N envs in lock-step on the device: one episode per env,
@@ -40,6 +41,31 @@ def train_ddpg(env, agent, episodes=1000, max_steps=500, on_step=None):
             if done:
                 break
         rewards.append(episode_reward)
+        agent.train_step += 1
+    return rewards
+
+
+def train_erl_fill(env, agent, episodes=1000, max_steps=500, on_step=None):
+    """Loop body of train_erl_fill (ERL_Fill_agent.py:526-541, 619): note `emotion.update(reward, action)` — the action is
+    the "movement" — and `float(done)` in the stored tuple."""
+    rewards = []
+    env.max_steps = max_steps
+    for ep in range(episodes):
+        state = env.reset()
+        ep_reward = 0
+        for step in range(max_steps):
+            action = agent.act(state)
+            next_state, reward, done, info = env.step(action)
+            agent.emotion.update(reward, action)
+            agent.remember(state, action, reward, next_state, float(done))
+            update_info = agent.update()
+            state = next_state
+            ep_reward += reward
+            if on_step is not None:
+                on_step(ep, step, reward, update_info, np.array(agent.emotion.get_emotion()).flatten(), info)
+            if done:
+                break
+        rewards.append(ep_reward)
         agent.train_step += 1
     return rewards
 

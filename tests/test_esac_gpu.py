@@ -111,3 +111,44 @@ def test_esac_batched_loop_runs_and_learns():
     assert float(e.min()) >= 0.0 and float(e.max()) <= 1.0
     na = agent.memory.buf[:len(agent.memory), 2:12]
     assert float(na.abs().max()) <= 1.0
+
+
+def test_esac_scalar_dropin_matches_reference_update():
+    """EmotionSACAgent (N = 1 drop-in): the reference's recorded update inputs through the scalar API (random.sample indices from
+    the same seed, injected rsample() normals) reproduce the reference's losses; act / remember / save / load surface."""
+    import random
+    import erlfill_b200 as E
+    G = np.load(GOLD)
+    cfg = E.conditions.EXPERIMENT_3["variant_25kg"]
+    env = E.MultiConditionWeightEnv({k: cfg[k] for k in ("target_weight", "target_weight_err", "target_time", "bounds")})
+    q = {"q1." + k: v for k, v in _sd(G, "q1_0.").items()}
+    q.update({"q2." + k: v for k, v in _sd(G, "q2_0.").items()})
+    torch.manual_seed(0)
+    agent = E.EmotionSACAgent(env, state_dicts=(E.init._transformer_sd(), _sd(G, "p0."), q))
+    n = G["buf_states"].shape[0]
+    for i in range(n):       # remember() takes physical actions and normalises them (:350-363)
+        a_phys = agent.denormalize_action(G["buf_actions"][i].astype(np.float64))
+        # the stored emotion comes from the agent's EmotionModule; parity needs the fixture's, so write the tuple as the reference had it
+        agent.memory.add((G["buf_states"][i], G["buf_actions"][i].astype(np.float64), float(G["buf_rewards"][i]), G["buf_next_states"][i],
+                          float(G["buf_dones"][i]), G["buf_emotions"][i]))
+        assert np.allclose(agent.normalize_action(a_phys), G["buf_actions"][i], atol=1e-12)
+    dev = agent.device
+    t = lambda k: torch.from_numpy(np.asarray(G["buf_" + k]).astype(np.float32)).to(dev)
+    agent._vec.memory.insert(t("states"), t("actions"), t("rewards"), t("next_states"), torch.from_numpy(G["buf_dones"].astype(np.uint8)).to(dev),
+                             t("emotions"))
+    random.seed(79)
+    out = agent.update(eps_next=G["eps_next"][0], eps_new=G["eps_new"][0])
+    assert np.array_equal(agent.last_indices, G["idx"][0])                                 # random.sample indices: bit-exact
+    for k, ref in zip(("q1_loss", "q2_loss", "policy_loss"), G["res"][0][:3]):
+        assert abs(out[k] - ref) <= 1e-4 * abs(ref), (k, out[k], ref)
+    assert out["emo_reg"] == 0.0                                                           # first update: prev_emotion = e_now
+    s = np.array([0.5, 1.0], np.float32)
+    a = agent.act(s)
+    lo = np.array([b[0] for b in env.bounds.values()]); hi = np.array([b[1] for b in env.bounds.values()])
+    assert a.shape == (10,) and a.dtype == np.float64 and np.all(a >= lo) and np.all(a <= hi)
+    assert np.array_equal(agent.act(s, deterministic=True), agent.act(s, add_noise=False))
+    e = agent.emotion.update(123.0, a)                                                     # 10-vector movement (train_erl_fill :538)
+    assert e.shape == (3,)
+    agent.remember(s, a, 1.0, s, 0.0)
+    assert len(agent.memory) == n + 1 and np.allclose(agent.memory.buffer[-1][5], agent.emotion.get_emotion())
+    assert list(agent.policy.state_dict().keys()) == R.ESAC_POLICY_ORDER and list(agent.q1.state_dict().keys()) == R.ESAC_Q_ORDER
