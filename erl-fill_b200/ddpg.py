@@ -140,6 +140,17 @@ class DDPGLearner:
         ao = (ag.value - ws.data_ptr()) // 4
         return ws[co:co + cl.value], ws[ao:ao + al.value]
 
+    def exchange_buffers(self, batch):
+        """Views of the workspace's exchange buffers: gradient buckets, peer-reduced buckets, [2][64] sum-of-squares partials."""
+        ws = self._workspace(batch)
+        p = [C.c_void_p() for _ in range(5)]
+        cl, al = C.c_int(), C.c_int()
+        L.check(L.lib().erlfill_ddpg_exchange_buffers(L.ptr(ws), C.c_int(batch), C.byref(p[0]), C.byref(cl), C.byref(p[1]), C.byref(al),
+                                                      C.byref(p[2]), C.byref(p[3]), C.byref(p[4])), "erlfill_ddpg_exchange_buffers")
+        o = [(x.value - ws.data_ptr()) // 4 for x in p]
+        return {"critic_grad": ws[o[0]:o[0] + cl.value], "actor_grad": ws[o[1]:o[1] + al.value], "critic_reduced": ws[o[2]:o[2] + cl.value],
+                "actor_reduced": ws[o[3]:o[3] + al.value], "sumsq": ws[o[4]:o[4] + 128]}
+
     def actor_struct(self, target=False):
         """erlfill_actor_weights pointing into the flat buffer (rollout kernel reads the live parameters)."""
         v = (self.actor_target if target else self.actor).views

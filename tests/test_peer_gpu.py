@@ -1,8 +1,9 @@
 """GPU (needs >= 2 GPUs on the box, skipped otherwise): the peer-memory gradient exchange of the data-parallel update
 (csrc/peer.cu) against the NCCL all-reduce path, through tools/dp_check.py under torchrun.
 
-Bars: replicas bit-identical across ranks after the updates; parameters equal to the NCCL path's within fp32 summation
-order (world 2: a + b is commutative, so bit-exact; larger worlds 1e-6); no peer wait timed out."""
+Bars: the reduced bucket equals ncclAllReduce / world (world 2: bit-exact; larger worlds 1e-6 of the bucket's scale, fp32
+summation order) and is bit-identical on every rank; replicas bit-identical across ranks after 54 updates; at world 2 the whole
+trajectory equals the NCCL path's bit for bit; no peer wait timed out."""
 import json
 import os
 import subprocess
@@ -26,7 +27,11 @@ def test_peer_exchange_matches_nccl_allreduce():
     res = json.loads(line[-1][len("DP_CHECK "):])
     assert len(res) == world
     for r in res:
-        assert r["peer_error"] == 0 and r["same_across_ranks"], r
-        tol = 0.0 if world == 2 else 1e-6
-        assert r["max_abs_diff_critic_vs_nccl"] <= tol and r["max_abs_diff_actor_vs_nccl"] <= tol, r
-        assert r["max_abs_diff_report_vs_nccl"] <= 1e-6, r
+        assert r["peer_error"] == 0 and r["same_across_ranks"] and r["exchange_same_across_ranks"], r
+        # the exchange itself: the averaged bucket equals ncclAllReduce / world up to fp32 summation order (world 2: a + b is
+        # commutative, so bit-exact), and the fused sum-of-squares partials add up to the norm of the reduced gradient
+        assert r["exchange_max_abs_diff"] <= (0.0 if world == 2 else 1e-6 * r["exchange_scale"]), r
+        assert r["sumsq_rel_diff"] <= 1e-5, r
+        if world == 2:      # identical gradients -> identical trajectories; beyond 2 ranks Adam amplifies the summation-order noise
+            assert r["max_abs_diff_critic_vs_nccl"] == 0.0 and r["max_abs_diff_actor_vs_nccl"] == 0.0, r
+            assert r["max_abs_diff_report_vs_nccl"] <= 1e-6, r

@@ -36,6 +36,25 @@ def main():
     ne = torch.tensor([0.4, 0.6, 0.2], device=dev)
     out = {}
     learners = {}
+    # (1) the exchange itself: one CRITIC_GRAD phase, then the peer all-reduce against ncclAllReduce of the same buckets
+    lr0 = ddpg.DDPGLearner(a_sd, c_sd, device=dev, batch_size=B)
+    ex0 = parallel.PeerExchange(lr0, B)
+    lr0.update(batch, ne, 3, phases=L.PHASE_CRITIC_GRAD, graph=False)
+    ex0.exchange(0)
+    torch.cuda.synchronize()
+    xb = lr0.exchange_buffers(B)
+    ref = xb["critic_grad"].clone()
+    dist.all_reduce(ref)
+    ref /= world
+    red = xb["critic_reduced"]
+    out["exchange_max_abs_diff"] = float((red - ref).abs().max())
+    out["exchange_scale"] = float(ref.abs().max())
+    ssq_ref = float((ref[:L.CRITIC_PARAMS].double() ** 2).sum())
+    out["sumsq_rel_diff"] = abs(float(xb["sumsq"][:64].double().sum()) - ssq_ref) / ssq_ref
+    gathered = [torch.empty_like(red) for _ in range(world)]
+    dist.all_gather(gathered, red.contiguous())
+    out["exchange_same_across_ranks"] = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+    # (2) whole updates: replicas stay bit-identical; the NCCL path for comparison and timing
     for mode in ("nccl", "peer"):
         lr = ddpg.DDPGLearner(a_sd, c_sd, device=dev, batch_size=B)
         ex = parallel.GradSync(world) if mode == "nccl" else parallel.PeerExchange(lr, B)
@@ -68,7 +87,9 @@ def main():
     ex.close()
     res = {"rank": rank, "world": world, "batch": B, "peer_error": err, "same_across_ranks": same_across_ranks,
            "max_abs_diff_critic_vs_nccl": d_c, "max_abs_diff_actor_vs_nccl": d_a, "max_abs_diff_report_vs_nccl": d_rep,
-           "nccl_ms_per_update": out["nccl_ms"], "peer_ms_per_update": out["peer_ms"]}
+           "nccl_ms_per_update": out["nccl_ms"], "peer_ms_per_update": out["peer_ms"],
+           "exchange_max_abs_diff": out["exchange_max_abs_diff"], "exchange_scale": out["exchange_scale"],
+           "sumsq_rel_diff": out["sumsq_rel_diff"], "exchange_same_across_ranks": out["exchange_same_across_ranks"]}
     allres = [None] * world
     dist.all_gather_object(allres, res)
     if rank == 0:
