@@ -113,8 +113,10 @@ struct StepArgs {
     const double *d_reset_u;   // [2][n_env] or nullptr
     int noise_rows;
     uint32_t step_idx;
+    const uint32_t *d_step_idx;  // != nullptr: the lock-step index lives in device memory (graph replay), step_idx is ignored
     int auto_reset;
     int actions_aligned16;
+    __device__ __forceinline__ uint32_t step() const { return d_step_idx ? __ldg(d_step_idx) : step_idx; }
 };
 
 struct SimResult {
@@ -583,7 +585,7 @@ __global__ void __launch_bounds__(kMaxBlock) env_step_kernel(const StepArgs a) {
     const int unload_delay = (int)clipped[9];
 
     // noise for this (env, step): misc lanes = {system_delay, reset u0, reset u1, -}
-    const uint4 misc = philox4x32_10(k0, k1, gid, a.step_idx, 0u, STREAM_MISC);
+    const uint4 misc = philox4x32_10(k0, k1, gid, a.step(), 0u, STREAM_MISC);
     double sysdelay;
     SimResult sim;
     if (kInjected) {
@@ -594,7 +596,7 @@ __global__ void __launch_bounds__(kMaxBlock) env_step_kernel(const StepArgs a) {
     } else {
         sysdelay = 15.0 + 35.0 * u32_to_unit(misc.x);                 // uniform(15, 50): :137
         PhiloxNoise nz;
-        nz.k0 = k0; nz.k1 = k1; nz.gid = gid; nz.step_idx = a.step_idx;
+        nz.k0 = k0; nz.k1 = k1; nz.gid = gid; nz.step_idx = a.step();
         sim = simulate(p, s_tab, sysdelay, nz, valid);
     }
     const int draws = valid ? sim.draws : 0;
@@ -961,10 +963,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 32 / kWarpsPerCta) env_sim_
     p.medium_delay = __shfl_sync(kFullMask, iv, 7);
     p.slow_delay = __shfl_sync(kFullMask, iv, 8);
     p.sane = (p.fast_pos >= 0) & (p.medium_pos >= 0) & (p.slow_pos >= 0);
-    const uint4 misc = philox4x32_10(k0, k1, gid, a.step_idx, 0u, STREAM_MISC);
+    const uint4 misc = philox4x32_10(k0, k1, gid, a.step(), 0u, STREAM_MISC);
     const double sysdelay = 15.0 + 35.0 * u32_to_unit(misc.x);             // uniform(15, 50): :137
     WarpNoise nz;
-    nz.k0 = k0; nz.k1 = k1; nz.gid = gid; nz.step_idx = a.step_idx; nz.b0 = 0;
+    nz.k0 = k0; nz.k1 = k1; nz.gid = gid; nz.step_idx = a.step(); nz.b0 = 0;
     const SimResult sim = simulate_warp(p, sysdelay, nz, lane);
     if (lane == 0) {
         reinterpret_cast<double *>(a.out.d_next_state)[i] = sim.final_weight;
@@ -994,7 +996,7 @@ __global__ void __launch_bounds__(128) env_finish_kernel(const StepArgs a) {
         sim.tick = reinterpret_cast<const int *>(a.out.d_reward)[i];
         sim.draws = reinterpret_cast<const int *>(a.env.d_obs)[2 * i];
         draws = sim.draws;
-        const uint4 misc = philox4x32_10((uint32_t)a.env.seed, (uint32_t)(a.env.seed >> 32), gid, a.step_idx, 0u, STREAM_MISC);
+        const uint4 misc = philox4x32_10((uint32_t)a.env.seed, (uint32_t)(a.env.seed >> 32), gid, a.step(), 0u, STREAM_MISC);
         finish_env<false>(a, i, c, clipped, sim, (int)clipped[9], misc);
     }
     if (a.out.d_tick_sum) {
@@ -1125,8 +1127,10 @@ int erlfill_env_reset_from_replay(const erlfill_env_batch *env, const uint8_t *d
     return ERLFILL_OK;
 }
 
-int erlfill_env_step(const erlfill_env_batch *env, const float *d_actions, uint32_t step_idx, int auto_reset,
-                     const erlfill_noise *noise, const erlfill_step_out *out, void *stream) {
+__global__ void step_idx_increment_kernel(uint32_t *p) { *p += 1u; }
+
+static int env_step_impl(const erlfill_env_batch *env, const float *d_actions, uint32_t step_idx, uint32_t *d_step_idx, int auto_reset,
+                         const erlfill_noise *noise, const erlfill_step_out *out, void *stream) {
     if (!env_ok(env) || !d_actions || !out || !out->d_next_state || !out->d_reward || !out->d_done)
         return ERLFILL_ERR_ARG;
     if (env->kind != ERLFILL_ENV_MULTI && env->kind != ERLFILL_ENV_SINGLE) return ERLFILL_ERR_ARG;
@@ -1140,6 +1144,7 @@ int erlfill_env_step(const erlfill_env_batch *env, const float *d_actions, uint3
     a.d_reset_u = noise ? noise->d_reset_u : nullptr;
     a.noise_rows = noise ? noise->rows : 0;
     a.step_idx = step_idx;
+    a.d_step_idx = d_step_idx;
     a.auto_reset = auto_reset;
     a.actions_aligned16 = ((uintptr_t)d_actions & 15u) == 0;
     const int block = pick_block(env->n_env);
@@ -1155,8 +1160,20 @@ int erlfill_env_step(const erlfill_env_batch *env, const float *d_actions, uint3
         ERLFILL_CUDA_TRY(cudaGetLastError());
         env_finish_kernel<<<(env->n_env + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     }
+    if (d_step_idx) step_idx_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_step_idx);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
+}
+
+int erlfill_env_step(const erlfill_env_batch *env, const float *d_actions, uint32_t step_idx, int auto_reset,
+                     const erlfill_noise *noise, const erlfill_step_out *out, void *stream) {
+    return env_step_impl(env, d_actions, step_idx, nullptr, auto_reset, noise, out, stream);
+}
+
+int erlfill_env_step_counted(const erlfill_env_batch *env, const float *d_actions, uint32_t *d_step_idx, int auto_reset,
+                             const erlfill_noise *noise, const erlfill_step_out *out, void *stream) {
+    if (!d_step_idx) return ERLFILL_ERR_ARG;
+    return env_step_impl(env, d_actions, 0u, d_step_idx, auto_reset, noise, out, stream);
 }
 
 }  // extern "C"

@@ -141,16 +141,50 @@ class VecFillEnv:
 
     def step_host(self, actions_host):
         """Host-facing step: float32[N,10] actions in (pinned) host memory in, (next_state, reward, done) as numpy-viewable
-        pinned host tensors out — one H2D copy, the step kernels, one D2H copy of the packed outputs, one stream sync."""
+        pinned host tensors out.  One H2D copy, the step kernels, one D2H copy of the packed outputs — captured ONCE in a CUDA
+        graph (the lock-step index lives in device memory: erlfill_env_step_counted) and replayed per call, then one stream
+        sync.  `actions_host` must be the same pinned tensor on every call (the graph holds its address); max_steps, the
+        simulator kernel choice and auto_reset are frozen at the first call."""
         n = self.n_env
         if self._host is None:
+            if not actions_host.is_pinned():
+                raise ValueError("step_host: actions_host must be a pinned host tensor")
             pack = torch.empty(13 * n, dtype=torch.uint8).pin_memory()
-            self._host = (torch.empty(n, 10, dtype=torch.float32, device=self.device), pack,
-                          pack[:8 * n].view(torch.float32).view(n, 2), pack[8 * n:12 * n].view(torch.float32), pack[12 * n:])
-        a_dev, pack, ns_h, r_h, d_h = self._host
-        a_dev.copy_(actions_host, non_blocking=True)
-        self.step(a_dev)
-        pack.copy_(self._out_pack, non_blocking=True)
+            a_dev = torch.empty(n, 10, dtype=torch.float32, device=self.device)
+            v = self.step_idx & 0xFFFFFFFF
+            d_idx = torch.tensor([v - (1 << 32) if v >= (1 << 31) else v], dtype=torch.int32, device=self.device)   # uint32 bits
+            with torch.cuda.device(self.device):
+                L.check(L.lib().erlfill_env_step_set_mode(C.c_int(self.sim_mode)), "erlfill_env_step_set_mode")
+            b = self._batch()
+
+            def body():
+                a_dev.copy_(actions_host, non_blocking=True)
+                L.check(L.lib().erlfill_env_step_counted(C.byref(b), L.ptr(a_dev), L.ptr(d_idx), C.c_int(int(self.auto_reset)), None,
+                                                         C.byref(self._out), L.stream_ptr()), "erlfill_env_step_counted")
+                pack.copy_(self._out_pack, non_blocking=True)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):          # one eager pass first (module load, motor tables) outside the capture
+                body()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self.step_idx += 1
+            self._host_counter = self.step_idx
+            self._host = (g, actions_host, pack, pack[:8 * n].view(torch.float32).view(n, 2), pack[8 * n:12 * n].view(torch.float32),
+                          pack[12 * n:], d_idx, b)
+            return self._host[3], self._host[4], self._host[5]
+        g, a_bound, pack, ns_h, r_h, d_h, d_idx = self._host[:7]
+        if actions_host.data_ptr() != a_bound.data_ptr():
+            raise ValueError("step_host: pass the same pinned actions tensor on every call (its address is captured)")
+        if self._host_counter != self.step_idx:      # step() was called in between: bring the device counter up to date
+            v = self.step_idx & 0xFFFFFFFF
+            d_idx.fill_(v - (1 << 32) if v >= (1 << 31) else v)
+        g.replay()
+        self.step_idx += 1
+        self._host_counter = self.step_idx
         torch.cuda.current_stream(self.device).synchronize()
         return ns_h, r_h, d_h
 

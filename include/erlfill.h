@@ -129,6 +129,13 @@ int erlfill_env_step(const erlfill_env_batch *env, const float *d_actions, uint3
                      int auto_reset, const erlfill_noise *noise, const erlfill_step_out *out,
                      void *stream);
 
+/* The same step with the lock-step index read from device memory (*d_step_idx, incremented by one after the step): the call
+ * sequence then holds no per-step constant, so [H2D actions, step, D2H results] can be captured once in a CUDA graph and
+ * replayed for every step. */
+int erlfill_env_step_counted(const erlfill_env_batch *env, const float *d_actions, uint32_t *d_step_idx,
+                             int auto_reset, const erlfill_noise *noise, const erlfill_step_out *out,
+                             void *stream);
+
 /* Which simulator kernel erlfill_env_step launches for Philox noise (injected noise always uses the
  * thread-per-env binary64 kernel).  Both produce bit-identical results; AUTO = warp per env. */
 typedef enum { ERLFILL_SIM_AUTO = 0, ERLFILL_SIM_THREAD_PER_ENV = 1, ERLFILL_SIM_WARP_PER_ENV = 2 } erlfill_sim_mode;

@@ -213,3 +213,28 @@ def test_simulator_edge_cases_philox(sim_mode):
             rn, rtt, rfw, _ = O.simulate_run_philox(c, seed, base + i, step)
             assert (int(ticks[i]), float(tt[i])) == (rn, rtt), (i, c, step)
             assert float(fw[i]).hex() == rfw.hex(), (i, c, step)
+
+
+def test_step_host_graph_replay_equals_step():
+    """VecFillEnv.step_host (H2D + step + D2H captured once in a CUDA graph, lock-step index in device memory) returns what
+    step() returns, step after step, also when the two are interleaved."""
+    import erlfill_b200 as E
+    K = E.conditions
+    n = 512
+    g = torch.Generator().manual_seed(3)
+    lo = torch.tensor([K.SINGLE_25KG["bounds"][k][0] for k in E._lib.ACTION_ORDER], dtype=torch.float32)
+    hi = torch.tensor([K.SINGLE_25KG["bounds"][k][1] for k in E._lib.ACTION_ORDER], dtype=torch.float32)
+    a_host = (lo + torch.rand(n, 10, generator=g) * (hi - lo)).contiguous().pin_memory()
+    e1 = E.VecFillEnv([K.SINGLE_25KG], n, kind="single", max_steps=5, seed=9)
+    e2 = E.VecFillEnv([K.SINGLE_25KG], n, kind="single", max_steps=5, seed=9)
+    e1.reset(); e2.reset()
+    a_dev = a_host.cuda()
+    for t in range(7):
+        ns, r, d, _ = e1.step(a_dev)
+        if t == 4:                      # interleave a plain step() on the graph-driven env
+            ns2, r2, d2, _ = e2.step(a_dev)
+            ns2, r2, d2 = ns2.cpu(), r2.cpu(), d2.cpu()
+        else:
+            ns2, r2, d2 = e2.step_host(a_host)
+        assert torch.equal(ns.cpu(), ns2) and torch.equal(r.cpu(), r2) and torch.equal(d.cpu(), d2), t
+        assert torch.equal(e1.obs, e2.obs)
