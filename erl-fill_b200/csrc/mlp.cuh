@@ -15,6 +15,7 @@ namespace mlp {
 // multiply-accumulates run on the tensor pipe.  These GEMMs are M = batch (128..4096) by N, K <= 256: the register-
 // fragment MMA fits them; a tcgen05/TMEM tile would be mostly padding.
 constexpr int BM = 64, BN = 64, BK = 16, LDS_T = 72;          // 72 % 32 == 8: conflict-free fragment loads
+constexpr int kFetch = BM * BK / 256;                         // tile elements per thread
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
 
 // v = hi + lo with hi = v truncated to TF32 (one LOP) and lo = v - hi (exact in fp32; the tensor core reads the top 19 bits of
@@ -41,17 +42,17 @@ static __device__ __forceinline__ void gemm_tile(int M, int N, const float *__re
     const int g = lane >> 2, t = lane & 3;
     float acc[2][2][4] = {};
     // per-thread tile coordinates (the fastest-varying index follows the unit-stride dimension for coalescing)
-    int am[4], ak[4], bn[4], bk[4];
+    int am[kFetch], ak[kFetch], bn[kFetch], bk[kFetch];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < kFetch; ++it) {
         const int e = tid + it * 256;
-        if (sak == 1) { ak[it] = e & 15; am[it] = e >> 4; } else { am[it] = e & 63; ak[it] = e >> 6; }
-        if (sbn == 1) { bn[it] = e & 63; bk[it] = e >> 6; } else { bk[it] = e & 15; bn[it] = e >> 4; }
+        if (sak == 1) { ak[it] = e % BK; am[it] = e / BK; } else { am[it] = e & 63; ak[it] = e >> 6; }
+        if (sbn == 1) { bn[it] = e & 63; bk[it] = e >> 6; } else { bk[it] = e % BK; bn[it] = e / BK; }
     }
-    float ra[4], rb[4];
+    float ra[kFetch], rb[kFetch];
     auto fetch = [&](int k0) {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
+        for (int it = 0; it < kFetch; ++it) {
             const int gm = m0 + am[it], gk = k0 + ak[it];
             ra[it] = (gm < M && gk < kend) ? A[(size_t)gm * sam + (size_t)gk * sak] : 0.f;
             const int gn = n0 + bn[it], gkb = k0 + bk[it];
@@ -61,7 +62,7 @@ static __device__ __forceinline__ void gemm_tile(int M, int N, const float *__re
     fetch(kbeg);
     for (int k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) { As[ak[it]][am[it]] = ra[it]; Bs[bk[it]][bn[it]] = rb[it]; }
+        for (int it = 0; it < kFetch; ++it) { As[ak[it]][am[it]] = ra[it]; Bs[bk[it]][bn[it]] = rb[it]; }
         __syncthreads();
         if (k0 + BK < kend) fetch(k0 + BK);           // next tile's global loads fly under this tile's MMAs
 #pragma unroll
