@@ -113,7 +113,7 @@ static __device__ __forceinline__ void gemm_tile(int M, int N, const float *__re
             }
 }
 
-static __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float *__restrict__ A, int sam, int sak,
+static __global__ void __launch_bounds__(256, 3) gemm_kernel(int M, int N, int K, const float *__restrict__ A, int sam, int sak,
                                                    const float *__restrict__ B, int sbk, int sbn, float *__restrict__ C,
                                                    int ldc, const float *__restrict__ bias, int act, int k_per_split,
                                                    size_t split_stride) {
@@ -127,7 +127,7 @@ static __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, c
 // and group_reduce_kernel adds the slices in index order (deterministic).
 struct WgTask { const float *dZ, *X; float *part; int ldz, ldx, N, K, tiles_k, tiles, first_block; };
 struct WgArgs { WgTask t[4]; int ntask, Bt, splits, kps; };
-static __global__ void __launch_bounds__(256) wgrad_group_kernel(const WgArgs a) {
+static __global__ void __launch_bounds__(256, 3) wgrad_group_kernel(const WgArgs a) {
     int ti = 0;
 #pragma unroll
     for (int i = 1; i < 4; ++i)
