@@ -114,7 +114,7 @@ class PeerGroup(C.Structure):
 ACTOR_PARAMS, CRITIC_PARAMS = 26216, 103937
 
 DROPOUT_OFF, DROPOUT_PHILOX, DROPOUT_MASK = 0, 1, 2
-SIM_AUTO, SIM_THREAD_PER_ENV, SIM_WARP_PER_ENV = 0, 1, 2
+SIM_AUTO, SIM_THREAD_PER_ENV, SIM_WARP_PER_ENV, SIM_WARP_WINDOWS, SIM_WARP_REJECT_RUNS = 0, 1, 2, 3, 4
 
 # every symbol include/erlfill.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTS = [

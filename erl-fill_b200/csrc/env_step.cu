@@ -95,7 +95,12 @@ static int ensure_motor_table() {
                 tr[m++] = open;
                 if (!far) { snapped = true; break; }
             }
-            if (ok && snapped) len = (uint8_t)m;
+            if (ok && snapped && m < kTrajLen) {
+                len = (uint8_t)m;
+                tr[kTrajLen - 1] = (double)m;      // the row carries its own length (the prefetched copy needs no second load)
+            } else {
+                tr[kTrajLen - 1] = 0.0;
+            }
         }
     }
     ERLFILL_CUDA_TRY(cudaMemcpyToSymbol(g_traj, host_traj, sizeof(host_traj)));
@@ -116,6 +121,7 @@ struct StepArgs {
     const uint32_t *d_step_idx;  // != nullptr: the lock-step index lives in device memory (graph replay), step_idx is ignored
     int auto_reset;
     int actions_aligned16;
+    int warp_fast_mode;        // SimParams::fast_mode of the warp-per-env kernel
     __device__ __forceinline__ uint32_t step() const { return d_step_idx ? __ldg(d_step_idx) : step_idx; }
 };
 
@@ -264,6 +270,7 @@ struct SimParams {
     double fast_pos, medium_pos, slow_pos;
     int fast_delay, medium_delay, slow_delay;
     bool sane;      // all three opening targets >= 0: the hold phase can be used
+    int fast_mode;  // warp kernel only: 0 = multi-window fast runs on, 1 = off, 2 = computed but rejected (tests the redo path)
 };
 
 struct Lane {
@@ -638,6 +645,10 @@ struct WarpNoise {
     uint32_t k0, k1, gid, step_idx;
     int b0;         // the warp holds the draw window [4*b0, 4*b0 + kWindow): lane L has noise blocks b0 + 32*h + L
     uint4 raw[kNoiseBlocks];
+#ifdef ERLFILL_SIM_PROF
+    long long pf_fast = 0, pf_hold = 0, pf_cross = 0, pf_move = 0, pf_gen = 0;
+    int pf_fastwin = 0, pf_win = 0, pf_nhold = 0, pf_nmove = 0, pf_ngen = 0, pf_movefail = 0;
+#endif
     __device__ __forceinline__ void fill(int block0, int lane) {
         b0 = block0;
 #pragma unroll
@@ -662,6 +673,13 @@ struct WarpNoise {
 __device__ __forceinline__ unsigned long long warp_sum_u44(unsigned long long v) {   // v < 2^44 per lane
     return (unsigned long long)__reduce_add_sync(kFullMask, (unsigned)v & 0x3FFFFFu) +
            ((unsigned long long)__reduce_add_sync(kFullMask, (unsigned)(v >> 22)) << 22);
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u59(unsigned long long v) {   // v < 2^59 per lane
+    const unsigned long long lo = (unsigned long long)__reduce_add_sync(kFullMask, (unsigned)v & 0x3FFFFFu);
+    const unsigned long long mid = (unsigned long long)__reduce_add_sync(kFullMask, (unsigned)(v >> 22) & 0x3FFFFFu);
+    const unsigned long long hi = (unsigned long long)__reduce_add_sync(kFullMask, (unsigned)(v >> 44));
+    return lo + (mid << 22) + (hi << 44);
 }
 
 // sum of this lane's increments P = ti * x over the 4 draws of one noise block; draws with window index < skip
@@ -735,20 +753,101 @@ __device__ __forceinline__ void hold_stretch(Lane &s, const SimParams &p, double
     const int tb = 4 * lane;
     unsigned long long acc = 0;
     int nochg = s.nochg;
+    bool try_fast = (p.fast_mode != 1) & (ti != 0u);
     for (;;) {
+        // ---- fast run (at most once per stretch): what is left of the window the warp holds plus Kr fresh rows of
+        // 128 draws (one noise block per lane) that stay below thr with overwhelming probability.  The draws left
+        // until thr are R = (Dc - acc) / (ti * 2^31) on average, with a standard deviation of 0.577 * sqrt(R) draws
+        // (x uniform on 32 bits); the run is sized to end 5 sigma short of that.  Every lane sums its raw noise
+        // words (the increments are ti * x, so one multiply at the end gives their exact sum), consecutive rows'
+        // Philox chains overlap, and ONE warp sum checks acc + total < Dc: all increments are >= 0, so every prefix
+        // is then below thr too.  The stagnation rule (VirtualWeightController.py:216-221) needs (i) no run of more
+        // than 500 small increments inside: guaranteed when no complete noise block is all-small (every run is then
+        // at most 6 + 3 draws long; nochg + kWindow <= LIMIT covers the run that continues the previous count), and
+        // (ii) the count at the end: the run that ends the last row.  If the check or (i) fails nothing is committed
+        // and the draws are redone window by window below (fast_mode 2 forces that in the tests).
+        if (try_fast) {
+            try_fast = false;
+            const int wend = 4 * nz.b0 + kWindow;
+            const int L = n < wend ? wend - n : 0;                   // unused draws of the current window
+            const int nstart = n < wend ? wend : n;                  // first draw of the fresh rows
+            if (((nstart & 3) == 0) & (nochg + kWindow <= ERLFILL_NOCHANGE_LIMIT)) {
+                const float R = __fdividef((float)(long long)(Dc - acc), (float)ti * 2147483648.0f);
+                int Kr = (int)((R - 3.0f * sqrtf(R) - (float)L) * (1.0f / 128.0f));
+                Kr = min(Kr, (ERLFILL_MAX_ITER - nstart) >> 7);
+                if (Kr >= 1) {
+#ifdef ERLFILL_SIM_PROF
+                    const long long pf_f0 = clock64();
+#endif
+                    unsigned long long lx = 0;              // sum of this lane's raw words
+                    uint32_t worst = 0xffffffffu;           // min over complete blocks of max(x): <= xs <=> one is all-small
+                    if (L > 0) {
+                        const int skip = kWindow - L;
+#pragma unroll
+                        for (int h = 0; h < kNoiseBlocks; ++h) {
+                            const int t0 = 128 * h + tb;
+                            const uint4 r = nz.raw[h];
+                            lx += (unsigned long long)(t0 + 0 >= skip ? r.x : 0u) + (t0 + 1 >= skip ? r.y : 0u);
+                            lx += (unsigned long long)(t0 + 2 >= skip ? r.z : 0u) + (t0 + 3 >= skip ? r.w : 0u);
+                            worst = min(worst, t0 >= skip ? max(max(r.x, r.y), max(r.z, r.w)) : 0xffffffffu);
+                        }
+                    }
+                    const uint32_t blk0 = (uint32_t)(nstart >> 2) + (uint32_t)lane;
+                    uint4 rl = make_uint4(0u, 0u, 0u, 0u);
+                    int row = 0;
+#pragma unroll 1
+                    for (; row + 4 <= Kr; row += 4) {
+                        uint4 r[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            r[q] = philox4x32_10(nz.k0, nz.k1, nz.gid, nz.step_idx, blk0 + (uint32_t)(32 * (row + q)), STREAM_TICK);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            lx += ((unsigned long long)r[q].x + r[q].y) + ((unsigned long long)r[q].z + r[q].w);
+                            worst = min(worst, max(max(r[q].x, r[q].y), max(r[q].z, r[q].w)));
+                        }
+                        rl = r[3];
+                    }
+#pragma unroll 1
+                    for (; row < Kr; ++row) {
+                        rl = philox4x32_10(nz.k0, nz.k1, nz.gid, nz.step_idx, blk0 + (uint32_t)(32 * row), STREAM_TICK);
+                        lx += ((unsigned long long)rl.x + rl.y) + ((unsigned long long)rl.z + rl.w);
+                        worst = min(worst, max(max(rl.x, rl.y), max(rl.z, rl.w)));
+                    }
+                    const unsigned long long total = (unsigned long long)ti * warp_sum_u44(lx);   // lx < 2^40
+                    const bool ok = !__any_sync(kFullMask, worst <= xs) & (acc + total < Dc) & (p.fast_mode != 2);
+                    if (ok) {
+                        int tl = -1;                        // last draw of the last row that is not small
+                        tl = rl.x > xs ? tb : tl; tl = rl.y > xs ? tb + 1 : tl;
+                        tl = rl.z > xs ? tb + 2 : tl; tl = rl.w > xs ? tb + 3 : tl;
+                        nochg = 127 - __reduce_max_sync(kFullMask, tl);
+                        acc += total;
+                        n = nstart + 128 * Kr;
+#ifdef ERLFILL_SIM_PROF
+                        nz.pf_fastwin += Kr; nz.pf_fast += clock64() - pf_f0;
+#endif
+                    }
+                }
+            }
+        }
         if (n >= 4 * nz.b0 + kWindow) nz.fill(n >> 2, lane);
         const int base = 4 * nz.b0;
         if ((base + kWindow > ERLFILL_MAX_ITER) | (nochg + kWindow > ERLFILL_NOCHANGE_LIMIT)) break;
         const int skip = n - base;
-        unsigned long long bs[kNoiseBlocks], lane_total = 0;
-        if (skip == 0) {
+        unsigned long long bx[kNoiseBlocks], lane_x = 0;      // raw-word sums per noise block (increment sums / ti)
 #pragma unroll
-            for (int h = 0; h < kNoiseBlocks; ++h) { bs[h] = block_sum<false>(ti, nz.raw[h], 0, 0); lane_total += bs[h]; }
-        } else {
-#pragma unroll
-            for (int h = 0; h < kNoiseBlocks; ++h) { bs[h] = block_sum<true>(ti, nz.raw[h], 128 * h + tb, skip); lane_total += bs[h]; }
+        for (int h = 0; h < kNoiseBlocks; ++h) {
+            const uint4 r = nz.raw[h];
+            if (skip == 0) {
+                bx[h] = ((unsigned long long)r.x + r.y) + ((unsigned long long)r.z + r.w);
+            } else {
+                const int t0 = 128 * h + tb;
+                bx[h] = ((unsigned long long)(t0 + 0 >= skip ? r.x : 0u) + (t0 + 1 >= skip ? r.y : 0u)) +
+                        ((unsigned long long)(t0 + 2 >= skip ? r.z : 0u) + (t0 + 3 >= skip ? r.w : 0u));
+            }
+            lane_x += bx[h];
         }
-        const unsigned long long total = warp_sum_u44(lane_total);
+        const unsigned long long total = (unsigned long long)ti * warp_sum_u44(lane_x);
         if (acc + total < Dc) {
             // every remaining draw of the window stays below thr
             acc += total;
@@ -787,14 +886,20 @@ __device__ __forceinline__ void hold_stretch(Lane &s, const SimParams &p, double
                 nochg = 0;
             }
             n = base + kWindow;
+#ifdef ERLFILL_SIM_PROF
+            nz.pf_win++;
+#endif
             continue;
         }
         // some draw of this window reaches thr: find the noise block row, then the draw
+#ifdef ERLFILL_SIM_PROF
+        const long long pf_c0 = clock64();
+#endif
         int hx = 0;
         unsigned long long row_before = acc;
 #pragma unroll
         for (int h = 0; h < kNoiseBlocks - 1; ++h) {
-            const unsigned long long th = warp_sum_u44(bs[h]);
+            const unsigned long long th = (unsigned long long)ti * warp_sum_u44(bx[h]);
             if (hx == h && row_before + th < Dc) { row_before += th; hx = h + 1; }
         }
         uint4 r = nz.raw[0];
@@ -846,6 +951,9 @@ __device__ __forceinline__ void hold_stretch(Lane &s, const SimParams &p, double
         s.nochg = (fabs(w_new - w_prev) < 0.01) ? run_before + 1 : 0;
         s.prev = w_new;
         fin = (n > ERLFILL_MAX_ITER) | (s.nochg > ERLFILL_NOCHANGE_LIMIT);
+#ifdef ERLFILL_SIM_PROF
+        nz.pf_cross += clock64() - pf_c0;
+#endif
         return;
     }
     // a safety stop is within reach: hand the exact state to the generic ticks
@@ -856,49 +964,87 @@ __device__ __forceinline__ void hold_stretch(Lane &s, const SimParams &p, double
 
 // MOVING phase from a hold state (open == A, speed 0) to a new target B, A != B integers in 0..100: the motor
 // trajectory open_1..open_m (m <= 55, the last entry is the snap to B) does not depend on the noise, so it is
-// read from the host-built table g_traj.  Lane j forms the tick's increment open_j * (1 + u_j); the weight is
-// then accumulated by m dependent binary64 adds in the reference's order.  All increments are >= 0, so w is
-// non-decreasing and "same stage flags at both ends" means no stage change happened inside the phase; with
-// every increment >= 0.011 the stagnation counter is 0 afterwards.  Returns false (nothing committed) when a
-// precondition fails; the caller then runs generic ticks.
+// read from the host-built table g_traj.  Lane j forms the tick's increment open_j * (1 + u_j) and parks it in
+// shared memory; the weight is then accumulated by m dependent binary64 adds in the reference's order (every
+// lane redundantly, broadcast 128-bit loads, no shuffle on the chain; entries past m are +0.0 and w >= 0, so
+// adding them changes nothing).  All increments are >= 0, so w is non-decreasing and "same stage flags at both
+// ends" means no stage change happened inside the phase.  Stagnation counter (VirtualWeightController.py:216-221):
+// with every increment >= 0.011 each |dw| >= 0.01 and the counter is 0 afterwards; otherwise the chain is redone
+// with the reference's own test on every tick.  Returns false (nothing committed) when a precondition fails; the
+// caller then runs generic ticks.
 __device__ __forceinline__ bool moving_phase(Lane &s, const SimParams &p, WarpNoise &nz, int lane, int &n, int &delay,
-                                             bool first, double sysdelay) {
+                                             bool first, double sysdelay, double *sh_p, const double *sh_traj, int pre0,
+                                             int pre1) {
     const int A = (int)s.open, B = (int)s.target;
     if (!((s.k == 0) & ((double)A == s.open) & ((double)B == s.target) & ((unsigned)A < (unsigned)kTrajDim) &
           ((unsigned)B < (unsigned)kTrajDim)))
         return false;
     const int pair = A * kTrajDim + B;
-    const int m = g_traj_len[pair];
+    int m;
+    double o_lo, o_hi;
+    if ((pair == pre0) | (pair == pre1)) {                     // the row was copied to shared memory by the prologue
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        const double *row = sh_traj + (pair == pre0 ? 0 : kTrajLen);
+        o_lo = row[lane]; o_hi = row[lane + 32];
+        m = (int)row[kTrajLen - 1];
+    } else {
+        const double *tr = g_traj + (size_t)pair * kTrajLen;
+        m = __ldg(g_traj_len + pair);                          // the three loads are independent of each other
+        o_lo = __ldg(tr + lane); o_hi = __ldg(tr + lane + 32);
+    }
     if (m == 0 || n + m > ERLFILL_MAX_ITER) return false;
     const double w0 = s.w;
     const bool lf = w0 < p.fast_w, lm = w0 < p.medium_w, ls = w0 < p.slow_w;
     const double stage_target = lf ? p.fast_pos : (lm ? p.medium_pos : p.slow_pos);
     if (!(lf | lm | ls) || dbits(stage_target) != dbits(s.target)) return false;
     if (n + m > 4 * nz.b0 + kWindow) nz.fill(n >> 2, lane);
-    const double *tr = g_traj + (size_t)pair * kTrajLen;
     const bool v_lo = lane < m, v_hi = lane + 32 < m;
-    const double o_lo = v_lo ? tr[lane] : 1.0;
-    const double p_lo = __dmul_rn(o_lo, opu_from_u32(nz.word(n + lane)));
-    double p_hi = 1.0;
+    const double q_lo = __dmul_rn(o_lo, opu_from_u32(nz.word(n + lane)));
+    const double p_lo = v_lo ? q_lo : 0.0;
+    double p_hi = 0.0;
     if (m > 32) {
-        const double o_hi = v_hi ? tr[lane + 32] : 1.0;
-        p_hi = __dmul_rn(o_hi, opu_from_u32(nz.word(n + 32 + lane)));
+        const double q_hi = __dmul_rn(o_hi, opu_from_u32(nz.word(n + 32 + lane)));
+        p_hi = v_hi ? q_hi : 0.0;
     }
-    if (__any_sync(kFullMask, (v_lo & (p_lo < 0.011)) | (v_hi & (p_hi < 0.011)))) return false;
-    double w = __dadd_rn(w0, __shfl_sync(kFullMask, p_lo, 0));
+    const bool small = __any_sync(kFullMask, (v_lo & (p_lo < 0.011)) | (v_hi & (p_hi < 0.011)));
+    if (small && s.nochg + m > ERLFILL_NOCHANGE_LIMIT) return false;
+    __syncwarp();
+    sh_p[lane] = p_lo;
+    sh_p[lane + 32] = p_hi;
+    __syncwarp();
+    const double2 *sh2 = reinterpret_cast<const double2 *>(sh_p);
+    double2 v = sh2[0];
+    double w = __dadd_rn(w0, v.x);
     if (first) w = __dadd_rn(w, __dmul_rn(s.target, sysdelay));            // one-time stage delay: :192-212
-    const int m_lo = m < 32 ? m : 32;
-    for (int j = 1; j < m_lo; ++j) w = __dadd_rn(w, __shfl_sync(kFullMask, p_lo, j));
-    for (int j = 32; j < m; ++j) w = __dadd_rn(w, __shfl_sync(kFullMask, p_hi, j - 32));
+    int nc = 0;
+    if (!small) {
+        w = __dadd_rn(w, v.y);
+#pragma unroll
+        for (int j = 1; j < 16; ++j) { v = sh2[j]; w = __dadd_rn(w, v.x); w = __dadd_rn(w, v.y); }
+        if (m > 32) {
+#pragma unroll
+            for (int j = 16; j < 32; ++j) { v = sh2[j]; w = __dadd_rn(w, v.x); w = __dadd_rn(w, v.y); }
+        }
+    } else {
+        nc = (fabs(w - s.prev) < 0.01) ? s.nochg + 1 : 0;
+#pragma unroll 1
+        for (int j = 1; j < m; ++j) {
+            const double w2 = __dadd_rn(w, sh_p[j]);
+            nc = (fabs(w2 - w) < 0.01) ? nc + 1 : 0;
+            w = w2;
+        }
+    }
     if (((w < p.fast_w) != lf) | ((w < p.medium_w) != lm) | ((w < p.slow_w) != ls)) return false;
     if (first) delay = lf ? p.fast_delay : (lm ? p.medium_delay : p.slow_delay);
-    s.w = w; s.prev = w; s.nochg = 0;
+    s.w = w; s.prev = w; s.nochg = nc;
     s.open = s.target; s.k = 0; s.dd = 0.0;
     n += m;
     return true;
 }
 
-__device__ __forceinline__ SimResult simulate_warp(const SimParams &p, double sysdelay, WarpNoise &nz, int lane) {
+__device__ __forceinline__ SimResult simulate_warp(const SimParams &p, double sysdelay, WarpNoise &nz, int lane,
+                                                  double *sh_p, const double *sh_traj, int pre0, int pre1) {
     Lane s;
     s.w = 0.0; s.open = 0.0; s.prev = 0.0; s.target = p.fast_pos; s.dd = 0.0; s.k = 0; s.nochg = 0;
     int n = 0, delay = 0;
@@ -910,13 +1056,31 @@ __device__ __forceinline__ SimResult simulate_warp(const SimParams &p, double sy
             const double bin_start = __longlong_as_double(dbits(s.w) & 0x7ff0000000000000LL);
             if (!first & (s.target <= 255.0) & (s.w >= 1.0) & (thr <= 1048576.0) & (2.0 * s.target <= bin_start) &
                 hold_caps_ok(nz, n, s.nochg)) {
+#ifdef ERLFILL_SIM_PROF
+                const long long pf_t = clock64();
+#endif
                 hold_stretch(s, p, thr, nz, lane, n, fin);
+#ifdef ERLFILL_SIM_PROF
+                nz.pf_hold += clock64() - pf_t; nz.pf_nhold++;
+#endif
                 continue;
             }
-        } else if (moving_phase(s, p, nz, lane, n, delay, first, sysdelay)) {
-            first = false;
-            continue;
+        } else {
+#ifdef ERLFILL_SIM_PROF
+            const long long pf_t = clock64();
+#endif
+            const bool moved = moving_phase(s, p, nz, lane, n, delay, first, sysdelay, sh_p, sh_traj, pre0, pre1);
+#ifdef ERLFILL_SIM_PROF
+            nz.pf_move += clock64() - pf_t; nz.pf_nmove++; nz.pf_movefail += !moved;
+#endif
+            if (moved) {
+                first = false;
+                continue;
+            }
         }
+#ifdef ERLFILL_SIM_PROF
+        const long long pf_g = clock64();
+#endif
         // generic tick (first tick without a table entry, openings outside 0..100, stage change while moving, ...)
         if (n >= 4 * nz.b0 + kWindow) nz.fill(n >> 2, lane);
         const double o = opu_from_u32(nz.word(n));
@@ -924,6 +1088,9 @@ __device__ __forceinline__ SimResult simulate_warp(const SimParams &p, double sy
         if (first) fin = generic_tick<true, kTabGlobal>(s, p, g_motor_tab, o, sysdelay, n, delay);
         else fin = generic_tick<false, kTabGlobal>(s, p, g_motor_tab, o, sysdelay, n, delay);
         first = false;
+#ifdef ERLFILL_SIM_PROF
+        nz.pf_gen += clock64() - pf_g; nz.pf_ngen++;
+#endif
     }
     SimResult res;
     res.final_weight = s.w;
@@ -936,7 +1103,24 @@ constexpr int kWarpsPerCta = 1;
 
 // K1: the simulator, one warp per env.  Results travel to K2 in the step's own output slots (no workspace):
 // final_weight (binary64) in next_state[i], tick count in reward[i], draws in obs[i].x.
+#ifdef ERLFILL_SIM_PROF
+__device__ unsigned long long *g_sim_prof = nullptr;    // [n_env][16], development only (tools/sim_prof.cu)
+__device__ __forceinline__ unsigned long long pf_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
+// kFused: lane 0 also runs K2's per-env epilogue right here.  That costs a warp-instruction per scalar instruction
+// (about +15 % issue slots per env) but saves the second launch and its cold loads: the host takes it when the
+// whole batch is resident at once (one warp slot per env), where issue slots are free and latency is everything.
+template <bool kFused>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 32 / kWarpsPerCta) env_sim_warp_kernel(const StepArgs a) {
+#ifdef ERLFILL_SIM_PROF
+    const unsigned long long pf_g0 = pf_globaltimer();
+    const long long pf_c0 = clock64();
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * kWarpsPerCta + warp;
     if (i >= a.env.n_env) return;                               // warp-uniform
@@ -963,16 +1147,60 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 32 / kWarpsPerCta) env_sim_
     p.medium_delay = __shfl_sync(kFullMask, iv, 7);
     p.slow_delay = __shfl_sync(kFullMask, iv, 8);
     p.sane = (p.fast_pos >= 0) & (p.medium_pos >= 0) & (p.slow_pos >= 0);
+    p.fast_mode = a.warp_fast_mode;
+    // the two motor trajectories this env will almost surely need (0 -> fast opening -> slow opening): copy their
+    // table rows into shared memory (cp.async, L1-allocating: the envs of an SM mostly share rows) while the first
+    // noise window is generated
+    __shared__ __align__(16) double sh_p[kWarpsPerCta][64];
+    __shared__ __align__(16) double sh_traj[kWarpsPerCta][2 * kTrajLen];
+    int pre0 = -1, pre1 = -1;
+    {
+        const int fo = __shfl_sync(kFullMask, iv, 3), so = __shfl_sync(kFullMask, iv, 5);
+        if (((unsigned)fo < (unsigned)kTrajDim) & ((unsigned)so < (unsigned)kTrajDim)) {
+            pre0 = fo; pre1 = fo * kTrajDim + so;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sh_traj[warp][lane]);
+            const double *s0 = g_traj + (size_t)pre0 * kTrajLen + lane, *s1 = g_traj + (size_t)pre1 * kTrajLen + lane;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(s0) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 256u), "l"(s0 + 32) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 512u), "l"(s1) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 768u), "l"(s1 + 32) : "memory");
+        }
+    }
     const uint4 misc = philox4x32_10(k0, k1, gid, a.step(), 0u, STREAM_MISC);
     const double sysdelay = 15.0 + 35.0 * u32_to_unit(misc.x);             // uniform(15, 50): :137
     WarpNoise nz;
     nz.k0 = k0; nz.k1 = k1; nz.gid = gid; nz.step_idx = a.step(); nz.b0 = 0;
-    const SimResult sim = simulate_warp(p, sysdelay, nz, lane);
-    if (lane == 0) {
+#ifdef ERLFILL_SIM_PROF
+    const long long pf_c1 = clock64();
+#endif
+    const SimResult sim = simulate_warp(p, sysdelay, nz, lane, sh_p[warp], sh_traj[warp], pre0, pre1);
+    if (kFused) {
+        float clipped[ERLFILL_ACTION_DIM];
+#pragma unroll
+        for (int j = 0; j < ERLFILL_ACTION_DIM; ++j) clipped[j] = __shfl_sync(kFullMask, v, j);
+        if (lane == 0) {
+            const erlfill_condition cc = *c;
+            finish_env<false>(a, i, cc, clipped, sim, (int)clipped[9], misc);
+            if (a.out.d_tick_sum && sim.draws) atomicAdd(a.out.d_tick_sum, (unsigned long long)sim.draws);
+        }
+    } else if (lane == 0) {
         reinterpret_cast<double *>(a.out.d_next_state)[i] = sim.final_weight;
         reinterpret_cast<int *>(a.out.d_reward)[i] = sim.tick;
         reinterpret_cast<int *>(a.env.d_obs)[2 * i] = sim.draws;
     }
+#ifdef ERLFILL_SIM_PROF
+    if (lane == 0 && g_sim_prof) {
+        unsigned long long *o = g_sim_prof + (size_t)i * 16;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        o[0] = pf_g0; o[1] = pf_globaltimer(); o[2] = smid;
+        o[3] = (unsigned long long)(pf_c1 - pf_c0);              // prologue
+        o[4] = (unsigned long long)(clock64() - pf_c1);          // simulate_warp + stores
+        o[5] = nz.pf_hold; o[6] = nz.pf_cross; o[7] = nz.pf_move; o[8] = nz.pf_gen;
+        o[9] = nz.pf_win; o[10] = nz.pf_nhold; o[11] = nz.pf_nmove; o[12] = nz.pf_ngen; o[13] = nz.pf_movefail;
+        o[14] = ((unsigned long long)nz.pf_fast << 24) | (unsigned)sim.draws; o[15] = nz.pf_fastwin;
+    }
+#endif
 }
 
 // K2: reward / state / done / auto-reset / stores, one thread per env (E2/E3/E4)
@@ -1072,7 +1300,15 @@ static int pick_block(int n_env) {
     return 128;
 }
 
+// envs (= warps) the device holds at once with one warp per CTA: 32 CTAs per SM
+static int resident_warp_slots() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * (32 / kWarpsPerCta) * kWarpsPerCta;
+}
+
 static int g_env_step_mode = ERLFILL_SIM_AUTO;
+static int g_warp_fast_mode = 0;
 
 static bool env_ok(const erlfill_env_batch *e) {
     return e && e->n_env > 0 && e->n_cond > 0 && e->d_cond && e->d_step_counter && e->d_episode_counter &&
@@ -1099,9 +1335,9 @@ int erlfill_device_ok(void) {
 }
 
 int erlfill_env_step_set_mode(int mode) {
-    if (mode != ERLFILL_SIM_AUTO && mode != ERLFILL_SIM_THREAD_PER_ENV && mode != ERLFILL_SIM_WARP_PER_ENV)
-        return ERLFILL_ERR_ARG;
-    g_env_step_mode = mode;
+    if (mode < ERLFILL_SIM_AUTO || mode > ERLFILL_SIM_WARP_REJECT_RUNS) return ERLFILL_ERR_ARG;
+    g_warp_fast_mode = mode == ERLFILL_SIM_WARP_WINDOWS ? 1 : (mode == ERLFILL_SIM_WARP_REJECT_RUNS ? 2 : 0);
+    g_env_step_mode = mode >= ERLFILL_SIM_WARP_WINDOWS ? ERLFILL_SIM_WARP_PER_ENV : mode;
     return ERLFILL_OK;
 }
 
@@ -1147,6 +1383,7 @@ static int env_step_impl(const erlfill_env_batch *env, const float *d_actions, u
     a.d_step_idx = d_step_idx;
     a.auto_reset = auto_reset;
     a.actions_aligned16 = ((uintptr_t)d_actions & 15u) == 0;
+    a.warp_fast_mode = g_warp_fast_mode;
     const int block = pick_block(env->n_env);
     const int grid = (env->n_env + block - 1) / block;
     if (a.d_u) {
@@ -1156,9 +1393,13 @@ static int env_step_impl(const erlfill_env_batch *env, const float *d_actions, u
         env_step_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(a);
     } else {
         const int wgrid = (env->n_env + kWarpsPerCta - 1) / kWarpsPerCta;
-        env_sim_warp_kernel<<<wgrid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(a);
-        ERLFILL_CUDA_TRY(cudaGetLastError());
-        env_finish_kernel<<<(env->n_env + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+        if (env->n_env <= resident_warp_slots()) {
+            env_sim_warp_kernel<true><<<wgrid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(a);
+        } else {
+            env_sim_warp_kernel<false><<<wgrid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(a);
+            ERLFILL_CUDA_TRY(cudaGetLastError());
+            env_finish_kernel<<<(env->n_env + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+        }
     }
     if (d_step_idx) step_idx_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_step_idx);
     ERLFILL_CUDA_TRY(cudaGetLastError());

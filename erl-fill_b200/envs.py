@@ -30,7 +30,8 @@ class VecFillEnv:
     sim_mode   : "auto" | "warp" (one warp per env, integer hold phase) | "thread" (one thread per env)
     """
 
-    SIM_MODES = {"auto": L.SIM_AUTO, "thread": L.SIM_THREAD_PER_ENV, "warp": L.SIM_WARP_PER_ENV}
+    SIM_MODES = {"auto": L.SIM_AUTO, "thread": L.SIM_THREAD_PER_ENV, "warp": L.SIM_WARP_PER_ENV,
+                 "warp_windows": L.SIM_WARP_WINDOWS, "warp_reject_runs": L.SIM_WARP_REJECT_RUNS}   # last two: test hooks
 
     def __init__(self, conditions, n_env, kind="multi", max_steps=100, seed=0, device="cuda",
                  env_id_base=0, cond_id=None, auto_reset=True, sim_mode="auto"):

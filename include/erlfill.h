@@ -137,8 +137,11 @@ int erlfill_env_step_counted(const erlfill_env_batch *env, const float *d_action
                              void *stream);
 
 /* Which simulator kernel erlfill_env_step launches for Philox noise (injected noise always uses the
- * thread-per-env binary64 kernel).  Both produce bit-identical results; AUTO = warp per env. */
-typedef enum { ERLFILL_SIM_AUTO = 0, ERLFILL_SIM_THREAD_PER_ENV = 1, ERLFILL_SIM_WARP_PER_ENV = 2 } erlfill_sim_mode;
+ * thread-per-env binary64 kernel).  All produce bit-identical results; AUTO = warp per env.  The last two are
+ * the warp kernel with its multi-window hold runs switched off / computed and then rejected: they exist so the
+ * tests can pin the window-by-window path and the redo path of a rejected run against the oracle. */
+typedef enum { ERLFILL_SIM_AUTO = 0, ERLFILL_SIM_THREAD_PER_ENV = 1, ERLFILL_SIM_WARP_PER_ENV = 2,
+               ERLFILL_SIM_WARP_WINDOWS = 3, ERLFILL_SIM_WARP_REJECT_RUNS = 4 } erlfill_sim_mode;
 int erlfill_env_step_set_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------ */

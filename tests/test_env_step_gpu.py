@@ -87,10 +87,11 @@ def test_dropin_env_episodes_match_reference(golden_dir):
     assert n_f32 >= 50 and n_done >= 15
 
 
-@pytest.mark.parametrize("sim_mode", ["warp", "thread"])
-@pytest.mark.parametrize("kind,n_env,max_steps", [("multi", 3000, 7), ("single", 1111, 5)])
+@pytest.mark.parametrize("sim_mode", ["warp", "thread", "warp_windows", "warp_reject_runs"])
+@pytest.mark.parametrize("kind,n_env,max_steps", [("multi", 5000, 7), ("single", 1111, 5)])
 def test_philox_batch_matches_oracle(kind, n_env, max_steps, sim_mode):
-    """Philox mode, ragged N (not a multiple of the CTA size), three conditions round-robin, random
+    """Philox mode, ragged N (not a multiple of the CTA size; 5000 envs take the two-kernel path of the warp simulator,
+    1111 the fused one), three conditions round-robin, random
     actions 10 % outside the bounds, auto-reset: every output equals the C oracle's."""
     import erlfill_b200 as E
     K = E.conditions
@@ -171,7 +172,7 @@ def test_full_size_properties():
         assert o.ticks == int(full.ticks[i].item())
 
 
-@pytest.mark.parametrize("sim_mode", ["warp", "thread"])
+@pytest.mark.parametrize("sim_mode", ["warp", "thread", "warp_windows", "warp_reject_runs"])
 def test_simulator_edge_cases_philox(sim_mode):
     """Philox noise, parameters the exactness argument of the integer hold phase singles out (thresholds on a
     power of two, reachable medium stage, openings 0/1/2 with stagnation counting and the stagnation stop, the
@@ -213,6 +214,32 @@ def test_simulator_edge_cases_philox(sim_mode):
             rn, rtt, rfw, _ = O.simulate_run_philox(c, seed, base + i, step)
             assert (int(ticks[i]), float(tt[i])) == (rn, rtt), (i, c, step)
             assert float(fw[i]).hex() == rfw.hex(), (i, c, step)
+
+
+@pytest.mark.parametrize("sim_mode", ["warp", "warp_windows", "warp_reject_runs"])
+def test_pid_constant_action_long_holds(sim_mode):
+    """configs[1]'s workload (every action at its lower bound: 2,300-tick hold at opening 3, the longest multi-window
+    runs of the warp kernel; about 1 % of the envs see an increment below 0.011 inside a motor move, the exact
+    stagnation-count path of moving_phase): ticks, total_time, final_weight, state, done equal the oracle's."""
+    import erlfill_b200 as E
+    K = E.conditions
+    n, seed, base = 4096, 0, 0
+    env = E.VecFillEnv([K.SINGLE_25KG], n, kind="single", max_steps=100, seed=seed, env_id_base=base, sim_mode=sim_mode)
+    c = K.SINGLE_25KG
+    ref = O.BatchEnv(O.ENV_SINGLE, [O.make_condition(c["target_weight"], c["target_weight_err"], c["target_time"], c["bounds"])],
+                     n, max_steps=100, seed=seed, env_id_base=base)
+    a = np.tile(np.array(K.PID_EFFECTIVE_ACTION, np.float32), (n, 1))
+    a_dev = torch.tensor(a, device="cuda")
+    for step in range(3):
+        ns, r, d, info = env.step(a_dev)
+        ref.step(a, step)
+        torch.cuda.synchronize()
+        assert np.array_equal(info["ticks"].cpu().numpy(), ref.ticks), step
+        assert np.array_equal(info["final_weight"].cpu().numpy(), ref.final_weight), step
+        assert np.array_equal(info["total_time"].cpu().numpy(), ref.total_time), step
+        assert np.array_equal(ns.cpu().numpy(), ref.next_state), step
+        assert np.array_equal(d.cpu().numpy(), ref.done), step
+        assert np.all(np.abs(r.cpu().numpy() - ref.reward) <= np.spacing(np.abs(ref.reward))), step
 
 
 def test_step_host_graph_replay_equals_step():
