@@ -34,12 +34,15 @@ TRANSFORMER_FLOP = 21.83e6      # per env per call at S=20 (SURVEY.md section 8d
 TRANSFORMER_FLOP_EXECUTED = 3 * 5457920 + 174080 + 264192
 UPDATE_FLOP_PER_SAMPLE = 1.43e6
 L2_FLUSH_BYTES = 256 << 20      # > 126 MB L2
-# warp-instructions one env-step of the `sim` workload issues in env_sim_warp_kernel + env_finish_kernel
-# (ncu smsp__inst_executed.sum / n_env, profiles/r01_env_step_4096_pid.txt)
-SIM_WARP_INSTR_PER_ENV_STEP = {"pid": 3959.3 + 20.3}
+# warp-instructions one env-step of the `sim` workload issues (ncu smsp__inst_executed.sum / n_env): the fused
+# env_sim_warp_kernel<true> when the batch is resident at once (profiles/r01d_env_sim_warp_4096.txt), else
+# env_sim_warp_kernel<false> + env_finish_kernel (profiles/r01d_env_sim_warp_65536.txt)
+SIM_WARP_INSTR_PER_ENV_STEP = {("pid", True): 3683.9, ("pid", False): 3118.3 + 20.4}
+SIM_FUSED_MAX_ENVS = 148 * 32   # csrc/env_step.cu: resident_warp_slots()
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of exactly these configurations
 # (cold L2, one launch): {(workload, envs per GPU): (bytes, summary file)}; any other configuration reports traffic null
-NCU_TRAFFIC = {("sim", 4096): (208640 + 326656, "profiles/r01b_env_sim_warp.txt + profiles/r01_env_step_4096_pid.txt (finish kernel)"),
+NCU_TRAFFIC = {("sim", 4096): (280576, "profiles/r01d_env_sim_warp_4096.txt"),
+               ("sim", 65536): (2663168 + 4750336, "profiles/r01d_env_sim_warp_65536.txt (simulator + finish kernel)"),
                ("rollout", 65536): (17171968, "profiles/r01b_emotion_tc.txt")}
 
 
@@ -205,10 +208,12 @@ def wl_sim(args, rank, world, device, timer):
 
     ms_per_step = total_ms / args.steps
     units = n * world * args.steps
-    launches = 2 if args.sim_mode != "thread" else 1
+    fused = args.sim_mode != "thread" and n <= SIM_FUSED_MAX_ENVS
+    launches = 1 if (fused or args.sim_mode == "thread") else 2
     peaks = _peaks()
     achieved = ENV_STEP_BYTES * n / (ms_per_step * 1e-3) / 1e9
-    kname = "env_sim_warp_kernel + env_finish_kernel" if args.sim_mode != "thread" else "env_step_kernel<false>"
+    kname = ("env_sim_warp_kernel<fused epilogue>" if fused else "env_sim_warp_kernel + env_finish_kernel") \
+        if args.sim_mode != "thread" else "env_step_kernel<false>"
     out = {
         "metric": "env_steps_per_sec", "value": units / (total_ms * 1e-3), "unit": "env-steps/s", "dtype": "f64",
         "ms_per_step": ms_per_step, "wall_s_timed_region": wall,
@@ -220,7 +225,12 @@ def wl_sim(args, rank, world, device, timer):
                    "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks"},
         "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / units,
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": a_host.numel() * 4,
-                "d2h_bytes_per_step": 13 * n},
+                "d2h_bytes_per_step": 13 * n,
+                "path": "VecFillEnv.step_host (CUDA graph replay + stream sync per step): " +
+                        ("the fused simulator kernel reads the pinned host actions and writes next_state/reward/done to pinned "
+                         "host memory directly (zero-copy over PCIe, no copy nodes)" if fused and
+                         os.environ.get("ERLFILL_STEP_HOST_MODE", "2") == "2" else
+                         "H2D copy of the actions, step kernels, D2H copy of the packed outputs")},
         "gpu_launches": launches * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"],
@@ -232,7 +242,7 @@ def wl_sim(args, rank, world, device, timer):
                              "env-step against 192 B of HBM traffic), not HBM bound: see issue_roofline"
                              % round(ticks_all / units)},
     }
-    ipe = SIM_WARP_INSTR_PER_ENV_STEP.get(args.actions) if args.sim_mode != "thread" else None
+    ipe = SIM_WARP_INSTR_PER_ENV_STEP.get((args.actions, fused)) if args.sim_mode != "thread" else None
     if ipe:
         out["_issue"] = (n * args.steps / (total_ms * 1e-3), ipe)
     return out

@@ -120,6 +120,7 @@ SIM_AUTO, SIM_THREAD_PER_ENV, SIM_WARP_PER_ENV, SIM_WARP_WINDOWS, SIM_WARP_REJEC
 EXPORTS = [
     "erlfill_version", "erlfill_last_cuda_error", "erlfill_last_cuda_error_string", "erlfill_device_ok",
     "erlfill_env_reset", "erlfill_env_reset_from_replay", "erlfill_env_step", "erlfill_env_step_counted", "erlfill_env_step_set_mode",
+    "erlfill_env_step_fused_max_envs",
     "erlfill_actor_forward", "erlfill_emotion_update", "erlfill_episode_end", "erlfill_emotion_forward",
     "erlfill_emotion_tc_image_bytes", "erlfill_emotion_tc_pack", "erlfill_emotion_forward_tc",
     "erlfill_replay_insert", "erlfill_replay_sample", "erlfill_replay_gather",

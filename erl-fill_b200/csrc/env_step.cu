@@ -1182,6 +1182,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 32 / kWarpsPerCta) env_sim_
             const erlfill_condition cc = *c;
             finish_env<false>(a, i, cc, clipped, sim, (int)clipped[9], misc);
             if (a.out.d_tick_sum && sim.draws) atomicAdd(a.out.d_tick_sum, (unsigned long long)sim.draws);
+            if (a.d_step_idx) {
+                // graph-replay mode: the last env to finish advances the lock-step index (every warp read it in its
+                // prologue, so nobody still needs the old value) and re-arms the ticket word next to it
+                uint32_t *cnt = const_cast<uint32_t *>(a.d_step_idx);
+                if (atomicAdd(cnt + 1, 1u) == (uint32_t)a.env.n_env - 1u) {
+                    cnt[1] = 0u;
+                    cnt[0] += 1u;
+                }
+            }
         }
     } else if (lane == 0) {
         reinterpret_cast<double *>(a.out.d_next_state)[i] = sim.final_weight;
@@ -1341,6 +1350,8 @@ int erlfill_env_step_set_mode(int mode) {
     return ERLFILL_OK;
 }
 
+int erlfill_env_step_fused_max_envs(void) { return resident_warp_slots(); }
+
 int erlfill_env_reset(const erlfill_env_batch *env, const uint8_t *d_mask, uint32_t step_idx,
                       const erlfill_noise *noise, void *stream) {
     if (!env_ok(env)) return ERLFILL_ERR_ARG;
@@ -1401,7 +1412,8 @@ static int env_step_impl(const erlfill_env_batch *env, const float *d_actions, u
             env_finish_kernel<<<(env->n_env + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
         }
     }
-    if (d_step_idx) step_idx_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_step_idx);
+    const bool fused_warp = !a.d_u && g_env_step_mode != ERLFILL_SIM_THREAD_PER_ENV && env->n_env <= resident_warp_slots();
+    if (d_step_idx && !fused_warp) step_idx_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_step_idx);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
 }

@@ -10,6 +10,7 @@ The drop-ins keep the reference's duck-typed surface: `bo
 `step(action) -> (np.float32[2], float, bool, info)`, `normalize_action`.
 """
 import ctypes as C
+import os
 import random
 
 import numpy as np
@@ -142,7 +143,9 @@ class VecFillEnv:
 
     def step_host(self, actions_host):
         """Host-facing step: float32[N,10] actions in (pinned) host memory in, (next_state, reward, done) as numpy-viewable
-        pinned host tensors out.  One H2D copy, the step kernels, one D2H copy of the packed outputs — captured ONCE in a CUDA
+        pinned host tensors out.  Batches that run as one fused kernel (<= erlfill_env_step_fused_max_envs() envs) read the
+        actions from and write the results to the pinned host buffers directly; larger ones use one H2D copy, the step
+        kernels and one D2H copy of the packed outputs.  Either way the sequence is captured ONCE in a CUDA
         graph (the lock-step index lives in device memory: erlfill_env_step_counted) and replayed per call, then one stream
         sync.  `actions_host` must be the same pinned tensor on every call (the graph holds its address); max_steps, the
         simulator kernel choice and auto_reset are frozen at the first call."""
@@ -153,16 +156,35 @@ class VecFillEnv:
             pack = torch.empty(13 * n, dtype=torch.uint8).pin_memory()
             a_dev = torch.empty(n, 10, dtype=torch.float32, device=self.device)
             v = self.step_idx & 0xFFFFFFFF
-            d_idx = torch.tensor([v - (1 << 32) if v >= (1 << 31) else v], dtype=torch.int32, device=self.device)   # uint32 bits
+            d_idx = torch.tensor([v - (1 << 32) if v >= (1 << 31) else v, 0], dtype=torch.int32, device=self.device)   # uint32 {index, ticket}
             with torch.cuda.device(self.device):
                 L.check(L.lib().erlfill_env_step_set_mode(C.c_int(self.sim_mode)), "erlfill_env_step_set_mode")
             b = self._batch()
 
+            # How the bytes cross PCIe.  0: copy nodes (H2D actions, D2H packed outputs).  2: the simulator kernel reads the
+            # pinned host actions in place and writes next_state/reward/done straight into the pinned pack (zero-copy; only
+            # when the batch runs as ONE fused kernel, whose outputs are written exactly once: include/erlfill.h).  1: reads
+            # in place, outputs by copy.  Default: 2 when eligible, else 0; ERLFILL_STEP_HOST_MODE overrides (measurements).
+            with torch.cuda.device(self.device):
+                fused = self.sim_mode != L.SIM_THREAD_PER_ENV and n <= L.lib().erlfill_env_step_fused_max_envs()
+            zc = int(os.environ.get("ERLFILL_STEP_HOST_MODE", "2" if fused else "0"))
+            if not fused:
+                zc = 0
+            out = self._out
+            if zc == 2:
+                hp = pack.data_ptr()
+                out = L.StepOut(hp, hp + 8 * n, hp + 12 * n, L.ptr(self.final_weight), L.ptr(self.total_time), L.ptr(self.ticks),
+                                L.ptr(self.tick_sum))
+            self._host_out = out
+
             def body():
-                a_dev.copy_(actions_host, non_blocking=True)
-                L.check(L.lib().erlfill_env_step_counted(C.byref(b), L.ptr(a_dev), L.ptr(d_idx), C.c_int(int(self.auto_reset)), None,
-                                                         C.byref(self._out), L.stream_ptr()), "erlfill_env_step_counted")
-                pack.copy_(self._out_pack, non_blocking=True)
+                if zc == 0:
+                    a_dev.copy_(actions_host, non_blocking=True)
+                L.check(L.lib().erlfill_env_step_counted(C.byref(b), L.ptr(a_dev) if zc == 0 else C.c_void_p(actions_host.data_ptr()), L.ptr(d_idx),
+                                                         C.c_int(int(self.auto_reset)), None, C.byref(out), L.stream_ptr()),
+                        "erlfill_env_step_counted")
+                if zc != 2:
+                    pack.copy_(self._out_pack, non_blocking=True)
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):          # one eager pass first (module load, motor tables) outside the capture
@@ -182,7 +204,7 @@ class VecFillEnv:
             raise ValueError("step_host: pass the same pinned actions tensor on every call (its address is captured)")
         if self._host_counter != self.step_idx:      # step() was called in between: bring the device counter up to date
             v = self.step_idx & 0xFFFFFFFF
-            d_idx.fill_(v - (1 << 32) if v >= (1 << 31) else v)
+            d_idx[0] = v - (1 << 32) if v >= (1 << 31) else v
         g.replay()
         self.step_idx += 1
         self._host_counter = self.step_idx

@@ -129,9 +129,10 @@ int erlfill_env_step(const erlfill_env_batch *env, const float *d_actions, uint3
                      int auto_reset, const erlfill_noise *noise, const erlfill_step_out *out,
                      void *stream);
 
-/* The same step with the lock-step index read from device memory (*d_step_idx, incremented by one after the step): the call
+/* The same step with the lock-step index read from device memory (d_step_idx[0], incremented by one after the step): the call
  * sequence then holds no per-step constant, so [H2D actions, step, D2H results] can be captured once in a CUDA graph and
- * replayed for every step. */
+ * replayed for every step.  d_step_idx points at TWO words: {index, ticket}; the ticket word must be zero before the first
+ * call and belongs to the library (the fused simulator kernel lets its last env advance the index, no extra launch). */
 int erlfill_env_step_counted(const erlfill_env_batch *env, const float *d_actions, uint32_t *d_step_idx,
                              int auto_reset, const erlfill_noise *noise, const erlfill_step_out *out,
                              void *stream);
@@ -143,6 +144,12 @@ int erlfill_env_step_counted(const erlfill_env_batch *env, const float *d_action
 typedef enum { ERLFILL_SIM_AUTO = 0, ERLFILL_SIM_THREAD_PER_ENV = 1, ERLFILL_SIM_WARP_PER_ENV = 2,
                ERLFILL_SIM_WARP_WINDOWS = 3, ERLFILL_SIM_WARP_REJECT_RUNS = 4 } erlfill_sim_mode;
 int erlfill_env_step_set_mode(int mode);
+
+/* Largest batch the warp-per-env simulator runs as ONE kernel (every env resident at once, the per-env epilogue fused
+ * into it): its outputs are then written exactly once, so a host caller may point d_actions / d_next_state / d_reward /
+ * d_done at pinned, device-mapped host memory and skip the copies (VecFillEnv.step_host does).  Larger batches use two
+ * kernels that pass intermediate values through the output slots: keep those in device memory. */
+int erlfill_env_step_fused_max_envs(void);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Policy side of the rollout                                                                  */

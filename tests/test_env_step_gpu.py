@@ -242,12 +242,15 @@ def test_pid_constant_action_long_holds(sim_mode):
         assert np.all(np.abs(r.cpu().numpy() - ref.reward) <= np.spacing(np.abs(ref.reward))), step
 
 
-def test_step_host_graph_replay_equals_step():
-    """VecFillEnv.step_host (H2D + step + D2H captured once in a CUDA graph, lock-step index in device memory) returns what
-    step() returns, step after step, also when the two are interleaved."""
+@pytest.mark.parametrize("n,host_mode", [(512, "2"), (512, "0"), (6000, None)])
+def test_step_host_graph_replay_equals_step(n, host_mode, monkeypatch):
+    """VecFillEnv.step_host (captured once in a CUDA graph, lock-step index in device memory; zero-copy host buffers for a
+    fused batch ("2"), H2D + step + D2H copies otherwise ("0", and always above the fused-batch limit)) returns what step()
+    returns, step after step, also when the two are interleaved."""
     import erlfill_b200 as E
     K = E.conditions
-    n = 512
+    if host_mode is not None:
+        monkeypatch.setenv("ERLFILL_STEP_HOST_MODE", host_mode)
     g = torch.Generator().manual_seed(3)
     lo = torch.tensor([K.SINGLE_25KG["bounds"][k][0] for k in E._lib.ACTION_ORDER], dtype=torch.float32)
     hi = torch.tensor([K.SINGLE_25KG["bounds"][k][1] for k in E._lib.ACTION_ORDER], dtype=torch.float32)
