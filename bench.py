@@ -389,6 +389,91 @@ def wl_update(args, rank, world, device, timer):
     }
 
 
+def wl_replay(args, rank, world, device, timer):
+    """Rows R1/R2 on their own: replay insert of one lock-step batch of transitions (configs[4] size: 131,072 envs per GPU)
+    into a 1M-row ring, and the minibatch path sample + gather.  HBM-bound kernels: achieved GB/s on the algorithmic bytes
+    (insert: 76 B read + 80 B written per transition; gather: 8 B index + 80 B read + 80 B written per sample)."""
+    import torch
+    from erlfill_b200.ddpg import ReplayBuffer
+    n, C, B = args.n_env, args.replay, args.batch
+    g = torch.Generator(device="cpu").manual_seed(7 + rank)
+    mem = ReplayBuffer(C, device=device)
+    state = torch.rand(n, 2, generator=g).to(device)
+    action = (torch.rand(n, 10, generator=g) * 100).to(device)
+    reward = torch.rand(n, generator=g).to(device)
+    next_state = torch.rand(n, 2, generator=g).to(device)
+    done = (torch.rand(n, generator=g) < 0.01).to(torch.uint8).to(device)
+    emotion = torch.rand(n, 3, generator=g).to(device)
+    scale = (torch.rand(10, generator=g) + 1).to(device)
+    offset = torch.rand(10, generator=g).to(device)
+
+    def insert():
+        mem.insert(state, action, reward, next_state, done, emotion, scale=scale, offset=offset)
+
+    for _ in range(max(args.warmup, C // n + 1)):     # fill the ring once so sampling covers all of it
+        insert()
+    total_ms, wall = timer.run(insert, args.steps)
+    ms = total_ms / args.steps
+    idx = torch.empty(B, dtype=torch.int64, device=device)
+    out = torch.empty(B, 20, dtype=torch.float32, device=device)
+    cnt = [0]
+
+    def sample_gather():
+        cnt[0] += 1
+        mem.sample_indices(B, 1234, cnt[0], out=idx)
+        mem.gather(idx, out=out)
+
+    sg_ms = _kernel_ms(timer, sample_gather, reps=10)
+    big = 1 << 20
+    idx_big = torch.randint(0, C, (big,), generator=g).to(device)
+    out_big = torch.empty(big, 20, dtype=torch.float32, device=device)
+    gb_ms = _kernel_ms(timer, lambda: mem.gather(idx_big, out=out_big), reps=10)
+    nb = min(C, 1 << 20)
+    bigin = [torch.rand(nb, 2, generator=g).to(device), (torch.rand(nb, 10, generator=g) * 100).to(device), torch.rand(nb, generator=g).to(device),
+             torch.rand(nb, 2, generator=g).to(device), (torch.rand(nb, generator=g) < 0.01).to(torch.uint8).to(device),
+             torch.rand(nb, 3, generator=g).to(device)]
+    ib_ms = _kernel_ms(timer, lambda: mem.insert(*bigin, scale=scale, offset=offset), reps=10)
+    host = [t.cpu().pin_memory() for t in (state, action, reward, next_state, done, emotion)]
+    dev = [state, action, reward, next_state, done, emotion]
+    out_host = torch.empty(B, 20).pin_memory()
+
+    def e2e_step():    # transitions handed over by a host producer, one minibatch read back
+        for d, h in zip(dev, host):
+            d.copy_(h, non_blocking=True)
+        insert()
+        sample_gather()
+        out_host.copy_(out, non_blocking=True)
+        timer.stream.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timer.run_block(e2e_step, args.steps)
+    peaks = _peaks()
+    ins_bytes = (76 + 80) * n
+    achieved = ins_bytes / (ms * 1e-3) / 1e9
+    return {
+        "metric": "replay_insert_transitions_per_sec", "value": n * world * args.steps / (total_ms * 1e-3), "unit": "transitions/s",
+        "dtype": "f32", "ms_per_step": ms, "wall_s_timed_region": wall,
+        "config": {"workload": "rows R1/R2: replay insert of %d transitions per GPU per step into a %d-row ring (FIFO); "
+                               "sample + gather of B = %d timed beside it" % (n, C, B),
+                   "n_env_per_gpu": n, "replay": C, "minibatch_per_gpu": B, "parallelism": "per-rank replay shard x%d" % world,
+                   "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+        "e2e": {"value": n * world * args.steps / (e2e_ms * 1e-3), "unit": "transitions/s",
+                "h2d_bytes_per_step": sum(h.numel() * h.element_size() for h in host), "d2h_bytes_per_step": B * 80},
+        "gpu_launches": 1 * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": None, "peak_source": peaks["source"], "kernel": "replay_insert_kernel",
+                     "algorithmic_bytes_per_transition": 156},
+        "sample_gather": {"batch": B, "ms": sg_ms, "note": "two launches, latency bound at this size"},
+        "insert_1M": {"transitions": nb, "ms": ib_ms, "achieved_gbs": 156 * nb / (ib_ms * 1e-3) / 1e9,
+                      "frac": 156 * nb / (ib_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                      "note": "the same kernel on a batch large enough to amortise launch and ramp"},
+        "gather_1M": {"samples": big, "ms": gb_ms, "achieved_gbs": (8 + 160) * big / (gb_ms * 1e-3) / 1e9,
+                      "frac": (8 + 160) * big / (gb_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                      "note": "random 80 B rows: 96 of every 3 x 32 B sectors fetched are 80 useful bytes"},
+    }
+
+
 def wl_loop(args, rank, world, device, timer):
     """configs[4]: TD3 / SAC on MultiConditionWeightEnv, full lock-step loop: act -> env step -> remember -> one update of
     B = 4096 from the rank's replay shard (data-parallel gradient all-reduce when world > 1)."""
@@ -479,7 +564,8 @@ def run_ours(args):
     timer = Timer(device, world)
     sampler = ClockSampler(local)
     sampler.start()
-    wl = {"sim": wl_sim, "rollout": wl_rollout, "update": wl_update, "td3": wl_loop, "sac": wl_loop, "esac": wl_loop}
+    wl = {"sim": wl_sim, "rollout": wl_rollout, "update": wl_update, "td3": wl_loop, "sac": wl_loop, "esac": wl_loop,
+          "replay": wl_replay}
     head = "sim" if args.workload == "all" else args.workload
     if args.workload == "all":
         args.n_env = args.n_env or 4096
@@ -611,7 +697,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "sim", "rollout", "update", "td3", "sac", "esac"],
+    ap.add_argument("--workload", default="all", choices=["all", "sim", "rollout", "update", "td3", "sac", "esac", "replay"],
                     help="all = the sim headline line plus compact rollout and update results under other_workloads")
     ap.add_argument("--n-env", type=int, default=None)
     ap.add_argument("--actions", default="pid", choices=["pid", "random"])
@@ -625,7 +711,8 @@ def main():
                     help="EmotionTransformer kernel of the rollout: tcgen05 bf16 (default) or the exact fp32 SIMT twin")
     args = ap.parse_args()
     if args.n_env is None:
-        args.n_env = {"all": 4096, "sim": 4096, "rollout": 65536, "update": 256, "td3": 131072, "sac": 131072, "esac": 65536}[args.workload]
+        args.n_env = {"all": 4096, "sim": 4096, "rollout": 65536, "update": 256, "td3": 131072, "sac": 131072, "esac": 65536,
+                      "replay": 131072}[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -11,36 +11,112 @@
 //   [0:2] state  [2:12] normalised action  [12] reward  [13:15] next_state  [15] done  [16:19] emotion  [19] pad
 // The buffer is [capacity][20] row-major, so an insert of N consecutive env transitions is one contiguous
 // 80*N-byte write and a gathered sample is five 128-bit loads.  Both kernels are HBM-bandwidth bound:
-// insert moves 80 B/transition (+ the 76 B it reads from the step outputs), gather 4 + 80 + 80 B/sample.
+// insert moves 80 B/transition (+ the 76 B it reads from the step outputs), gather 8 + 80 + 80 B/sample.
 #include "common.cuh"
 
 namespace erlfill {
 
-__global__ void replay_insert_kernel(int n, float *d_buf, int64_t capacity, int64_t start, const int64_t *d_pos,
-                                     const float *d_state, const float *d_action, const float *d_reward,
-                                     const float *d_next_state, const uint8_t *d_done, const float *d_emotion,
-                                     const float *d_scale, const float *d_offset, int normalize) {
-    // one thread per float of the record: consecutive threads write consecutive addresses
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (int64_t)n * ERLFILL_REC) return;
-    const int i = (int)(g / ERLFILL_REC), f = (int)(g % ERLFILL_REC);
-    float v;
-    if (f < 2) v = d_state[(size_t)i * 2 + f];
-    else if (f < 12) {
-        const int c = f - 2;
-        v = d_action[(size_t)i * 10 + c];
-        if (normalize) {
-            v = __fdiv_rn(__fsub_rn(v, d_offset[c]), d_scale[c]);
+__global__ void __launch_bounds__(128) replay_insert_kernel(int n, float *d_buf, int64_t capacity, int64_t start, const int64_t *d_pos,
+                                                            const float *d_state, const float *d_action, const float *d_reward,
+                                                            const float *d_next_state, const uint8_t *d_done, const float *d_emotion,
+                                                            const float *d_scale, const float *d_offset, int normalize) {
+    // One thread per transition: every input byte is fetched exactly once (8-byte loads, rows of a warp are adjacent, so
+    // the sectors a load instruction touches are shared by neighbouring lanes and by the next instruction through L1),
+    // all 15 loads of a thread are independent and in flight together, and the 80-byte record leaves as five 128-bit
+    // stores (L2 merges the five partial-sector writes of a record before anything reaches DRAM).
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 st = __ldg(reinterpret_cast<const float2 *>(d_state) + i);
+    const float2 *ap = reinterpret_cast<const float2 *>(d_action) + (size_t)i * 5;
+    float a[10];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float2 t = __ldg(ap + j);
+        a[2 * j] = t.x; a[2 * j + 1] = t.y;
+    }
+    const float rw = __ldg(d_reward + i);
+    const float2 ns = __ldg(reinterpret_cast<const float2 *>(d_next_state) + i);
+    const float dn = __ldg(d_done + i) ? 1.f : 0.f;
+    const float e0 = __ldg(d_emotion + (size_t)i * 3), e1 = __ldg(d_emotion + (size_t)i * 3 + 1), e2 = __ldg(d_emotion + (size_t)i * 3 + 2);
+    int64_t row;
+    if (d_pos) {
+        row = d_pos[i];
+    } else {
+        row = start + i;                       // start < capacity and n <= capacity (checked by the host)
+        row = row >= capacity ? row - capacity : row;
+    }
+    if (normalize) {
+#pragma unroll
+        for (int c = 0; c < 10; ++c) {
+            float v = __fdiv_rn(__fsub_rn(a[c], __ldg(d_offset + c)), __ldg(d_scale + c));
             v = v < -1.f ? -1.f : v;
-            v = v > 1.f ? 1.f : v;
+            a[c] = v > 1.f ? 1.f : v;
         }
-    } else if (f == 12) v = d_reward[i];
-    else if (f < 15) v = d_next_state[(size_t)i * 2 + (f - 13)];
-    else if (f == 15) v = d_done[i] ? 1.f : 0.f;
-    else if (f < 19) v = d_emotion[(size_t)i * 3 + (f - 16)];
-    else v = 0.f;
-    const int64_t row = d_pos ? d_pos[i] : (start + i) % capacity;
-    d_buf[row * ERLFILL_REC + f] = v;
+    }
+    float4 *dst = reinterpret_cast<float4 *>(d_buf + row * ERLFILL_REC);
+    dst[0] = make_float4(st.x, st.y, a[0], a[1]);
+    dst[1] = make_float4(a[2], a[3], a[4], a[5]);
+    dst[2] = make_float4(a[6], a[7], a[8], a[9]);
+    dst[3] = make_float4(rw, ns.x, ns.y, dn);
+    dst[4] = make_float4(e0, e1, e2, 0.f);
+}
+
+// The ring-order insert (no position table): the records of a CTA are consecutive rows, so they are assembled in shared
+// memory (80-byte stride: the five 128-bit stores of a quarter-warp fall on distinct banks) and leave as fully coalesced
+// 128-bit stores, 512 contiguous bytes per warp instruction.  A CTA whose rows wrap around the ring end writes directly.
+constexpr int kInsertBlock = 128;
+__global__ void __launch_bounds__(kInsertBlock) replay_insert_ring_kernel(int n, float *d_buf, int64_t capacity, int64_t start,
+                                                                        const float *d_state, const float *d_action,
+                                                                        const float *d_reward, const float *d_next_state,
+                                                                        const uint8_t *d_done, const float *d_emotion,
+                                                                        const float *d_scale, const float *d_offset, int normalize) {
+    __shared__ __align__(16) float4 sh[kInsertBlock * 5];
+    const int i0 = blockIdx.x * kInsertBlock, i = i0 + threadIdx.x;
+    const int cnt = min(kInsertBlock, n - i0);
+    int64_t row0 = start + i0;
+    row0 = row0 >= capacity ? row0 - capacity : row0;
+    const bool contiguous = row0 + cnt <= capacity;
+    if (i < n) {
+        const float2 st = __ldg(reinterpret_cast<const float2 *>(d_state) + i);
+        const float2 *ap = reinterpret_cast<const float2 *>(d_action) + (size_t)i * 5;
+        float a[10];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float2 t = __ldg(ap + j);
+            a[2 * j] = t.x; a[2 * j + 1] = t.y;
+        }
+        const float rw = __ldg(d_reward + i);
+        const float2 ns = __ldg(reinterpret_cast<const float2 *>(d_next_state) + i);
+        const float dn = __ldg(d_done + i) ? 1.f : 0.f;
+        const float e0 = __ldg(d_emotion + (size_t)i * 3), e1 = __ldg(d_emotion + (size_t)i * 3 + 1), e2 = __ldg(d_emotion + (size_t)i * 3 + 2);
+        if (normalize) {
+#pragma unroll
+            for (int c = 0; c < 10; ++c) {
+                float v = __fdiv_rn(__fsub_rn(a[c], __ldg(d_offset + c)), __ldg(d_scale + c));
+                v = v < -1.f ? -1.f : v;
+                a[c] = v > 1.f ? 1.f : v;
+            }
+        }
+        float4 *dst = sh + threadIdx.x * 5;
+        if (!contiguous) {
+            int64_t row = start + i;
+            row = row >= capacity ? row - capacity : row;
+            dst = reinterpret_cast<float4 *>(d_buf + row * ERLFILL_REC);
+        }
+        dst[0] = make_float4(st.x, st.y, a[0], a[1]);
+        dst[1] = make_float4(a[2], a[3], a[4], a[5]);
+        dst[2] = make_float4(a[6], a[7], a[8], a[9]);
+        dst[3] = make_float4(rw, ns.x, ns.y, dn);
+        dst[4] = make_float4(e0, e1, e2, 0.f);
+    }
+    if (!contiguous) return;                      // block-uniform
+    __syncthreads();
+    float4 *out = reinterpret_cast<float4 *>(d_buf + row0 * ERLFILL_REC);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int q = threadIdx.x + kInsertBlock * k;
+        if (q < cnt * 5) out[q] = sh[q];
+    }
 }
 
 __global__ void replay_sample_kernel(int batch, int64_t n_valid, uint32_t k0, uint32_t k1, uint32_t update_idx,
@@ -76,12 +152,18 @@ int erlfill_replay_insert(int n, float *d_buf, int64_t capacity, int64_t start, 
         return ERLFILL_ERR_ARG;
     if ((d_scale == nullptr) != (d_offset == nullptr)) return ERLFILL_ERR_ARG;
     if (!d_pos && (start < 0 || n > capacity)) return ERLFILL_ERR_ARG;
-    const int64_t total = (int64_t)n * ERLFILL_REC;
-    const int block = 256;
-    const int64_t grid = (total + block - 1) / block;
-    replay_insert_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(n, d_buf, capacity, start, d_pos, d_state, d_action,
-                                                                             d_reward, d_next_state, d_done, d_emotion, d_scale,
-                                                                             d_offset, d_scale ? 1 : 0);
+    if (((uintptr_t)d_buf & 15u) || ((uintptr_t)d_state & 7u) || ((uintptr_t)d_action & 7u) || ((uintptr_t)d_next_state & 7u))
+        return ERLFILL_ERR_ARG;
+    const int block = kInsertBlock;
+    const int grid = (n + block - 1) / block;
+    if (d_pos)
+        replay_insert_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(n, d_buf, capacity, start, d_pos, d_state, d_action,
+                                                                                 d_reward, d_next_state, d_done, d_emotion, d_scale,
+                                                                                 d_offset, d_scale ? 1 : 0);
+    else
+        replay_insert_ring_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(n, d_buf, capacity, start % capacity, d_state, d_action,
+                                                                                      d_reward, d_next_state, d_done, d_emotion,
+                                                                                      d_scale, d_offset, d_scale ? 1 : 0);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
 }

@@ -22,7 +22,7 @@ def T(x, dev="cuda"):
 def test_replay_insert_sample_gather_bit_exact():
     from erlfill_b200 import ddpg
     rng = np.random.RandomState(0)
-    cap, n = 1000, 384
+    cap, n = 1000, 389          # ragged last CTA; the third and fourth inserts wrap around the ring end inside a CTA
     rb = ddpg.ReplayBuffer(cap)
     scale = np.array([5500, .5, 50, 20, 1, 7.5, 100, 50, 50, 100], np.float32)
     offset = np.array([12500, .5, 24950, 55, 4, 12.5, 200, 150, 150, 400], np.float32)
