@@ -96,8 +96,7 @@ class VecERDDPG:
         self._emotion_forward()
         if store:
             self.memory.insert(self.state, a, reward, next_state, done, self.emotion, self.learner.scale, self.learner.offset)
-        nets.episode_end(done, self.ou_state, self.sigma, self.sigma64)
-        self.episodes += done.sum()
+        nets.episode_end(done, self.ou_state, self.sigma, self.sigma64, episode_count=self.episodes)
         return next_state, reward, done
 
     def rollout_eval_step(self):

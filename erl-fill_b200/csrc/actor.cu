@@ -289,9 +289,15 @@ __global__ void emotion_update_kernel(int n, const float *d_reward, const float 
 }
 
 // per-episode OU bookkeeping of train_ddpg (ddpg_agent.py:633-634): reset(); anneal()
-__global__ void episode_end_kernel(int n, const uint8_t *d_done, float *d_ou_state, float *d_sigma, double *d_sigma64) {
+__global__ void episode_end_kernel(int n, const uint8_t *d_done, float *d_ou_state, float *d_sigma, double *d_sigma64,
+                                   long long *d_episode_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !d_done[i]) return;
+    const bool fin = i < n && d_done[i];
+    if (d_episode_count) {                              // finished episodes of the batch, one atomic per warp
+        const unsigned m = __ballot_sync(0xffffffffu, fin);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(reinterpret_cast<unsigned long long *>(d_episode_count), (unsigned long long)__popc(m));
+    }
+    if (!fin) return;
 #pragma unroll
     for (int c = 0; c < 10; ++c) d_ou_state[(size_t)i * 10 + c] = 0.f;
     const double s = fmax(0.1, d_sigma64[i] * 0.9995);         // sigma is a Python float in the reference
@@ -361,10 +367,11 @@ int erlfill_emotion_update(int n_env, const float *d_reward, const float *d_stat
     return ERLFILL_OK;
 }
 
-int erlfill_episode_end(int n_env, const uint8_t *d_done, float *d_ou_state, float *d_sigma, double *d_sigma64, void *stream) {
+int erlfill_episode_end(int n_env, const uint8_t *d_done, float *d_ou_state, float *d_sigma, double *d_sigma64,
+                        long long *d_episode_count, void *stream) {
     if (n_env <= 0 || !d_done || !d_ou_state || !d_sigma || !d_sigma64) return ERLFILL_ERR_ARG;
     const int block = 128, grid = (n_env + block - 1) / block;
-    episode_end_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_env, d_done, d_ou_state, d_sigma, d_sigma64);
+    episode_end_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_env, d_done, d_ou_state, d_sigma, d_sigma64, d_episode_count);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
 }

@@ -165,7 +165,7 @@ def emotion_forward(params, seq=None, emo=None, dropout=L.DROPOUT_OFF, masks=Non
     return out
 
 
-def episode_end(done, ou_state, sigma32, sigma64):
+def episode_end(done, ou_state, sigma32, sigma64, episode_count=None):
     with torch.cuda.device(done.device):
         L.check(L.lib().erlfill_episode_end(C.c_int(done.shape[0]), L.ptr(done), L.ptr(ou_state), L.ptr(sigma32),
-                                            L.ptr(sigma64), L.stream_ptr()), "erlfill_episode_end")
+                                            L.ptr(sigma64), L.ptr(episode_count), L.stream_ptr()), "erlfill_episode_end")

@@ -201,9 +201,11 @@ int erlfill_actor_forward(const erlfill_actor_weights *w, int n_rows, const floa
 int erlfill_emotion_update(int n_env, const float *d_reward, const float *d_state, const float *d_next_state,
                            const erlfill_emotion_state *emo, void *stream);
 
-/* train_ddpg's per-episode `ou_noise.reset(); ou_noise.anneal()` (ddpg_agent.py:633-634) for envs with done. */
+/* train_ddpg's per-episode `ou_noise.reset(); ou_noise.anneal()` (ddpg_agent.py:633-634) for envs with done.
+ * d_episode_count (int64[1], may be NULL) += number of envs with done: the batched stand-in for the trainer's
+ * `agent.train_step += 1` per episode (ddpg_agent.py:729). */
 int erlfill_episode_end(int n_env, const uint8_t *d_done, float *d_ou_state, float *d_sigma, double *d_sigma64,
-                        void *stream);
+                        long long *d_episode_count, void *stream);
 
 /* EmotionTransformer parameters (EmotionModule.py:27-40), device pointers, per-layer tensors stacked on a
  * leading [4] axis, each slice in the reference state_dict layout. */
