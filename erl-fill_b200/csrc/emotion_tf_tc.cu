@@ -43,8 +43,9 @@ constexpr int D = 32, FF = 2048, NL = 4, SMAX = 20, HD = 8;
 #define ERLFILL_TC_TILES 2
 #endif
 constexpr int kTiles = ERLFILL_TC_TILES;   // token tiles per CTA: 2 (one CTA per SM, the tiles share the weight stream) or 1 (two CTAs per
-                                           // SM, each with its own stream: measured 3 % slower on B200 — every phase is bound by its own
-                                           // dependency chain, not by a shared unit, so desynchronising the two tiles buys nothing)
+                                           // SM, each with its own stream: measured 3 % slower on B200 with both CTAs starting together, i.e.
+                                           // in lock-step — a forced phase offset between them is untested; the variant no longer fits the
+                                           // shared memory since the parked-row buffers were added: DESIGN.md section 4.2)
 constexpr int kCtasPerSm = kTiles == 1 ? 2 : 1;
 constexpr int EPT = 6;                     // envs per tile
 constexpr int ROWS = EPT * SMAX;           // 120 live rows of 128
