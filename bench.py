@@ -474,6 +474,51 @@ def wl_replay(args, rank, world, device, timer):
     }
 
 
+def wl_n1(args, rank, world, device, timer):
+    """configs[0]: the reference's own case — ONE env, ER-DDPG (`DDPGAgent(use_td_error=True)` + `EmotionModule`), B = 128, replay
+    100,000 — through the N = 1 drop-ins and the loop body of train_ddpg (`loops.train_ddpg`: reset, act, step, emotion.update,
+    remember, learn, get_emotion per step, numpy in / numpy out like the reference).  Host-driven by nature: value == e2e.
+    The reference's own figure for this loop is 27 env-steps/s on 8 vCPU (survey-measured)."""
+    import random
+    import numpy as np
+    import torch
+    import erlfill_b200 as E
+    from erlfill_b200 import loops
+    K = E.conditions
+    cfg = K.EXPERIMENT_3["variant_25kg"]
+    torch.manual_seed(0); random.seed(0); np.random.seed(0)
+    env = E.MultiConditionWeightEnv({k: cfg[k] for k in ("target_weight", "target_weight_err", "target_time", "bounds")})
+    agent = E.DDPGAgent(env, device=device, use_td_error=True)
+    agent.emotion = E.EmotionModule(device=device)
+    env.attach_agent(agent)
+    steps_per_ep = 50
+    n_steps = [0]
+    loops.train_ddpg(env, agent, episodes=4, max_steps=steps_per_ep)        # warm-up: past the first learn() (128 transitions)
+    timer.sync()
+    t0 = time.perf_counter()
+    loops.train_ddpg(env, agent, episodes=max(2, args.steps // 2), max_steps=steps_per_ep,
+                     on_step=lambda *a: n_steps.__setitem__(0, n_steps[0] + 1))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    v = n_steps[0] / dt
+    peaks = _peaks()
+    return {
+        "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "dtype": "f64 simulator, f32 networks",
+        "ms_per_step": dt / n_steps[0] * 1e3, "wall_s_timed_region": dt,
+        "config": {"workload": "configs[0]: ER-DDPG on one MultiConditionWeightEnv (25 kg), N = 1 drop-ins, train_ddpg loop body "
+                               "(act -> step -> emotion.update -> remember -> learn B=128 -> get_emotion), %d env-steps timed by "
+                               "wall clock (host-driven loop: every call returns numpy like the reference)" % n_steps[0],
+                   "n_env_per_gpu": 1, "minibatch": 128, "parallelism": "single env", "l2": "not flushed (host-paced launches)",
+                   "timing": "wall clock around the loop, device synchronised on both sides"},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * (2 + 10 + 19), "d2h_bytes_per_step": 4 * (10 + 2 + 3 + 3 + 2)},
+        "gpu_launches": None,
+        "roofline": {"bound": "hbm", "achieved": ENV_STEP_BYTES * v / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": ENV_STEP_BYTES * v / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                     "kernel": "whole N = 1 step", "note": "latency bound: about 40 dependent launches and 8 host syncs per step"},
+        "reference_cpu": {"value": 27.0, "unit": "env-steps/s", "source": "SURVEY.md section 6: the reference's train_ddpg body, 8 vCPU, survey-measured"},
+    }
+
+
 def wl_loop(args, rank, world, device, timer):
     """configs[4]: TD3 / SAC on MultiConditionWeightEnv, full lock-step loop: act -> env step -> remember -> one update of
     B = 4096 from the rank's replay shard (data-parallel gradient all-reduce when world > 1)."""
@@ -565,7 +610,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     wl = {"sim": wl_sim, "rollout": wl_rollout, "update": wl_update, "td3": wl_loop, "sac": wl_loop, "esac": wl_loop,
-          "replay": wl_replay}
+          "replay": wl_replay, "n1": wl_n1}
     head = "sim" if args.workload == "all" else args.workload
     if args.workload == "all":
         args.n_env = args.n_env or 4096
@@ -697,7 +742,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "sim", "rollout", "update", "td3", "sac", "esac", "replay"],
+    ap.add_argument("--workload", default="all", choices=["all", "sim", "rollout", "update", "td3", "sac", "esac", "replay", "n1"],
                     help="all = the sim headline line plus compact rollout and update results under other_workloads")
     ap.add_argument("--n-env", type=int, default=None)
     ap.add_argument("--actions", default="pid", choices=["pid", "random"])
@@ -712,7 +757,7 @@ def main():
     args = ap.parse_args()
     if args.n_env is None:
         args.n_env = {"all": 4096, "sim": 4096, "rollout": 65536, "update": 256, "td3": 131072, "sac": 131072, "esac": 65536,
-                      "replay": 131072}[args.workload]
+                      "replay": 131072, "n1": 1}[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

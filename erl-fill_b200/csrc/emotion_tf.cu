@@ -9,6 +9,11 @@
 // This is the fp32 SIMT implementation: it is the N=1 drop-in's get_emotion() (1e-5 parity with the
 // reference) and the checker-side twin of the bf16 tensor-core kernel (emotion_tf_tc.cu) that the batched
 // rollout uses.  One CTA handles kG envs (kG*20 tokens) so every weight read from L2 is used kG*20 times.
+// Small batches (the N = 1 drop-in: one launch is a 1.3 M-cycle serial walk of 64 FFN chunks on one SM) run as
+// thread-block clusters of kSplit CTAs per env group: every CTA repeats the cheap parts (embedding, q|k|v, attention,
+// LayerNorms) and owns FF / kSplit of the hidden units; the partial linear2 sums are exchanged through distributed
+// shared memory and added in rank order on every CTA, so the result does not depend on the launch shape of the cluster.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -74,12 +79,17 @@ __device__ __forceinline__ void layer_norm_rows(float *sm, int n_tok, const floa
     }
 }
 
+constexpr int kSplitSmall = 8;            // CTAs per cluster in the small-batch variant
+
+template <int kSplit>
 __global__ void __launch_bounds__(kTfThreads) emotion_forward_kernel(const TfArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x;
-    const int env0 = blockIdx.x * kG;
+    const int rank = kSplit > 1 ? (int)(blockIdx.x % kSplit) : 0;      // == cluster rank (1-D clusters of kSplit CTAs)
+    const int env0 = (int)(blockIdx.x / kSplit) * kG;
     const int n_env = min(kG, a.n - env0);
     int *s_len = reinterpret_cast<int *>(&sm[sLen]);
+    const int nT = n_env * SMAX;          // token rows of the envs this CTA really has (a ragged last CTA, or N = 1: 20 of 80)
 
     // ---- sequence lengths ----
     if (tid < kG) {
@@ -132,11 +142,15 @@ __global__ void __launch_bounds__(kTfThreads) emotion_forward_kernel(const TfArg
 #pragma unroll
             for (int d = 0; d < D; ++d) wr[d] = __ldg(in_w + tid * D + d);
             const float bb = __ldg(in_b + tid);
-            for (int t = 0; t < kT; ++t) {
-                float acc = bb;
+            // four tokens at a time: four independent fma chains (each keeps its d = 0..31 order), nT is a multiple of 20
+            for (int t = 0; t < nT; t += 4) {
+                float acc[4] = {bb, bb, bb, bb};
 #pragma unroll
-                for (int d = 0; d < D; ++d) acc = fmaf(sm[sX + t * ldX + d], wr[d], acc);
-                sm[sQ + t * ldQ + tid] = acc;
+                for (int d = 0; d < D; ++d)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc[u] = fmaf(sm[sX + (t + u) * ldX + d], wr[d], acc[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) sm[sQ + (t + u) * ldQ + tid] = acc[u];
             }
         }
         __syncthreads();
@@ -178,7 +192,7 @@ __global__ void __launch_bounds__(kTfThreads) emotion_forward_kernel(const TfArg
         }
         __syncthreads();
         // ---- out_proj + dropout1 -> sA ; then x = LN1(x + sA) ----
-        for (int i = tid; i < kT * D; i += kTfThreads) {
+        for (int i = tid; i < nT * D; i += kTfThreads) {
             const int t = i / D, c = i % D, e = t / SMAX, s = t % SMAX;
             float acc = __ldg(out_b + c);
 #pragma unroll
@@ -189,32 +203,38 @@ __global__ void __launch_bounds__(kTfThreads) emotion_forward_kernel(const TfArg
             sm[sA + t * ldX + c] = acc;
         }
         __syncthreads();
-        layer_norm_rows(sm, kT, a.w.norm1_w + l * D, a.w.norm1_b + l * D, tid);
+        layer_norm_rows(sm, nT, a.w.norm1_w + l * D, a.w.norm1_b + l * D, tid);
         __syncthreads();
         // ---- FFN in chunks of 128 hidden units; accumulators for out[t][o]: thread = (o, token group) ----
         const int o_col = tid & 31, tg = tid >> 5;               // 4 groups x 20 tokens
         float acc[SMAX];
 #pragma unroll
-        for (int i = 0; i < SMAX; ++i) acc[i] = __ldg(b2 + o_col);
-        for (int c0 = 0; c0 < FF; c0 += kChunk) {
+        for (int i = 0; i < SMAX; ++i) acc[i] = rank == 0 ? __ldg(b2 + o_col) : 0.f;
+        for (int c0 = rank * (FF / kSplit); c0 < (rank + 1) * (FF / kSplit); c0 += kChunk) {
             // hidden: thread j owns hidden unit c0 + j for every token
             {
                 float wr[D];
 #pragma unroll
                 for (int d = 0; d < D; ++d) wr[d] = __ldg(w1 + (size_t)(c0 + tid) * D + d);
                 const float bb = __ldg(b1 + c0 + tid);
-                for (int t = 0; t < kT; ++t) {
-                    float h = bb;
+                for (int t4 = 0; t4 < nT; t4 += 4) {
+                    float hh[4] = {bb, bb, bb, bb};
 #pragma unroll
-                    for (int d = 0; d < D; ++d) h = fmaf(sm[sX + t * ldX + d], wr[d], h);
-                    h = fmaxf(h, 0.f);
-                    if (a.dropout_mode != ERLFILL_DROPOUT_OFF) {
-                        const int e = t / SMAX, s = t % SMAX;
-                        if (e < n_env && s < s_len[e])
-                            h *= keep_scale(a, a.row_id_base + env0 + e, 4u * l + 2u, (uint32_t)(s * FF + c0 + tid),
-                                            a.masks.ff, (((size_t)l * a.n + env0 + e) * a.S + s) * FF + c0 + tid);
+                    for (int d = 0; d < D; ++d)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) hh[u] = fmaf(sm[sX + (t4 + u) * ldX + d], wr[d], hh[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = t4 + u;
+                        float h = fmaxf(hh[u], 0.f);
+                        if (a.dropout_mode != ERLFILL_DROPOUT_OFF) {
+                            const int e = t / SMAX, s = t % SMAX;
+                            if (e < n_env && s < s_len[e])
+                                h *= keep_scale(a, a.row_id_base + env0 + e, 4u * l + 2u, (uint32_t)(s * FF + c0 + tid),
+                                                a.masks.ff, (((size_t)l * a.n + env0 + e) * a.S + s) * FF + c0 + tid);
+                        }
+                        sm[sHd + t * ldH + tid] = h;
                     }
-                    sm[sHd + t * ldH + tid] = h;
                 }
             }
             // linear2 chunk, transposed into smem: w2s[j][o] = W2[o][c0 + j]
@@ -223,6 +243,7 @@ __global__ void __launch_bounds__(kTfThreads) emotion_forward_kernel(const TfArg
                 sm[sW2 + j * D + o] = __ldg(w2 + (size_t)o * FF + c0 + j);
             }
             __syncthreads();
+            if (tg < n_env)
             for (int j = 0; j < kChunk; j += 4) {
                 const float w0 = sm[sW2 + (j + 0) * D + o_col], w1v = sm[sW2 + (j + 1) * D + o_col];
                 const float w2v = sm[sW2 + (j + 2) * D + o_col], w3 = sm[sW2 + (j + 3) * D + o_col];
@@ -235,6 +256,27 @@ __global__ void __launch_bounds__(kTfThreads) emotion_forward_kernel(const TfArg
             }
             __syncthreads();
         }
+        if (kSplit > 1) {
+            // partial sums of this CTA's hidden units -> its own smem (the hidden-chunk buffer is free now), then every CTA adds
+            // the kSplit partials in rank order
+            namespace cg = cooperative_groups;
+            cg::cluster_group cluster = cg::this_cluster();
+            if (tg < n_env)
+#pragma unroll
+                for (int i = 0; i < SMAX; ++i) sm[sHd + (tg * SMAX + i) * ldH + o_col] = acc[i];
+            cluster.sync();
+            if (tg < n_env) {
+#pragma unroll
+                for (int i = 0; i < SMAX; ++i) acc[i] = 0.f;
+                for (int rr = 0; rr < kSplit; ++rr) {
+                    const float *remote = cluster.map_shared_rank(sm, rr);
+#pragma unroll
+                    for (int i = 0; i < SMAX; ++i) acc[i] += remote[sHd + (tg * SMAX + i) * ldH + o_col];
+                }
+            }
+            cluster.sync();                                   // nobody overwrites its partials while a peer still reads them
+        }
+        if (tg < n_env)
 #pragma unroll
         for (int i = 0; i < SMAX; ++i) {
             const int t = tg * SMAX + i, e = tg, s = i;
@@ -245,11 +287,11 @@ __global__ void __launch_bounds__(kTfThreads) emotion_forward_kernel(const TfArg
             sm[sA + t * ldX + o_col] = v;
         }
         __syncthreads();
-        layer_norm_rows(sm, kT, a.w.norm2_w + l * D, a.w.norm2_b + l * D, tid);
+        layer_norm_rows(sm, nT, a.w.norm2_w + l * D, a.w.norm2_b + l * D, tid);
         __syncthreads();
     }
     // ---- last token -> fc_out -> 0.5*tanh + 0.5 ----
-    if (tid < kG * 3) {
+    if (rank == 0 && tid < kG * 3) {
         const int e = tid / 3, c = tid % 3;
         if (e < n_env) {
             const int t = e * SMAX + (s_len[e] - 1);
@@ -290,11 +332,26 @@ int erlfill_emotion_forward(const erlfill_transformer_weights *w, int n_env, con
     int dev = 0;
     ERLFILL_CUDA_TRY(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        ERLFILL_CUDA_TRY(cudaFuncSetAttribute(emotion_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ERLFILL_CUDA_TRY(cudaFuncSetAttribute(emotion_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ERLFILL_CUDA_TRY(cudaFuncSetAttribute(emotion_forward_kernel<kSplitSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dev] = true;
     }
-    const int grid = (n_env + kG - 1) / kG;
-    emotion_forward_kernel<<<grid, kTfThreads, smem, (cudaStream_t)stream>>>(a);
+    const int groups = (n_env + kG - 1) / kG;
+    if (groups * kSplitSmall <= 160) {
+        // small batch (<= 80 envs): kSplitSmall CTAs per env group as one thread-block cluster
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(groups * kSplitSmall), 1, 1);
+        cfg.blockDim = dim3(kTfThreads, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kSplitSmall; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        ERLFILL_CUDA_TRY(cudaLaunchKernelEx(&cfg, emotion_forward_kernel<kSplitSmall>, a));
+    } else {
+        emotion_forward_kernel<1><<<groups, kTfThreads, smem, (cudaStream_t)stream>>>(a);
+    }
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
 }

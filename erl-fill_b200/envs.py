@@ -76,6 +76,26 @@ class VecFillEnv:
                               L.ptr(self.final_weight), L.ptr(self.total_time), L.ptr(self.ticks),
                               L.ptr(self.tick_sum))
 
+    def use_host_outputs(self):
+        """Point every step output at pinned, device-mapped HOST memory (zero-copy): after a stream synchronise the caller
+        reads next_state / reward / done / final_weight / total_time / ticks as numpy views, with no device-to-host copies.
+        Only for batches that run as one kernel (include/erlfill.h: erlfill_env_step_fused_max_envs) — the scalar drop-ins."""
+        n = self.n_env
+        with torch.cuda.device(self.device):
+            if n > L.lib().erlfill_env_step_fused_max_envs():
+                raise ValueError("use_host_outputs: batch too large for the single-kernel step")
+        buf = torch.zeros(40 * n, dtype=torch.uint8).pin_memory()
+        self._host_buf = buf
+        self.final_weight = buf[:8 * n].view(torch.float64)
+        self.total_time = buf[8 * n:16 * n].view(torch.float64)
+        self.next_state = buf[16 * n:24 * n].view(torch.float32).view(n, 2)
+        self.reward = buf[24 * n:28 * n].view(torch.float32)
+        self.ticks = buf[28 * n:32 * n].view(torch.int32)
+        self.done = buf[32 * n:33 * n]
+        self._out = L.StepOut(L.ptr(self.next_state), L.ptr(self.reward), L.ptr(self.done),
+                              L.ptr(self.final_weight), L.ptr(self.total_time), L.ptr(self.ticks),
+                              L.ptr(self.tick_sum))
+
     # -- C-ABI descriptor (rebuilt per call: max_steps is assigned by trainers at any time) ----
     def _batch(self):
         return L.EnvBatch(self.n_env, self.kind, int(self.max_steps), len(self.conditions), self.env_id_base, 0,
@@ -256,6 +276,9 @@ class _ScalarEnvBase:
                    "target_time": self.target_time, "bounds": self.bounds}
             self._vec = VecFillEnv([cfg], 1, kind=self._kind, max_steps=self.max_steps, seed=self._seed,
                                    device=self._device, auto_reset=False)
+            self._vec.use_host_outputs()
+            self._a_host = torch.zeros(1, 10, dtype=torch.float32).pin_memory()
+            self._a_dev = torch.zeros(1, 10, dtype=torch.float32, device=self._vec.device)
             self._u = torch.zeros(MAX_DRAWS, 1, dtype=torch.float64, device=self._vec.device)
             self._u_host = torch.zeros(MAX_DRAWS, 1, dtype=torch.float64).pin_memory()
             self._ru = torch.zeros(2, 1, dtype=torch.float64, device=self._vec.device)
@@ -289,30 +312,41 @@ class _ScalarEnvBase:
         v.max_steps = int(self.max_steps)
         if isinstance(action, dict):
             action = np.array([action[k] for k in L.ACTION_ORDER])
-        a = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, 10)).to(v.device)
+        self._a_host.numpy()[0, :] = np.asarray(action, dtype=np.float32).reshape(10)
+        a = self._a_dev
+        a.copy_(self._a_host, non_blocking=True)
         if self._noise_mode == "reference":
+            # The reference draws uniform(15, 50) once and uniform(-1, 1) per tick from CPython's global Mersenne Twister
+            # (VirtualWeightController.py:122,137).  numpy's RandomState is the same generator with the same 53-bit double
+            # construction, so the draws are produced vectorised from a copy of `random`'s state (a + (b - a) * random(),
+            # the same two roundings as random.uniform), and `random` is then advanced by exactly the draws the run consumed.
             st = random.getstate()
+            key, pos = np.array(st[1][:-1], dtype=np.uint32), st[1][-1]
+            rs = np.random.RandomState()
+            rs.set_state(("MT19937", key, pos))
+            u = rs.random_sample(MAX_DRAWS)
             host = self._u_host.numpy()
-            host[0, 0] = random.uniform(15, 50)
-            for t in range(1, MAX_DRAWS):
-                host[t, 0] = random.uniform(-1, 1)
+            host[0, 0] = 15.0 + 35.0 * u[0]
+            host[1:, 0] = -1.0 + 2.0 * u[1:]
             self._u.copy_(self._u_host, non_blocking=True)
             ns, r, d, info = v.step(a, noise_u=self._u)
-            n_draws = int(info["ticks"][0].item())
-            random.setstate(st)
-            random.uniform(15, 50)
-            for _ in range(n_draws):
-                random.random()
+            torch.cuda.current_stream(v.device).synchronize()      # outputs live in pinned host memory (use_host_outputs)
+            n_draws = int(info["ticks"][0])
+            rs.set_state(("MT19937", key, pos))
+            rs.random_sample(1 + n_draws)
+            k2 = rs.get_state()
+            random.setstate((st[0], tuple(k2[1].tolist()) + (int(k2[2]),), st[2]))
         else:
             ns, r, d, info = v.step(a)
+            torch.cuda.current_stream(v.device).synchronize()
         clipped = np.clip(np.asarray(action, dtype=np.float32), [self.bounds[k][0] for k in L.ACTION_ORDER],
                           [self.bounds[k][1] for k in L.ACTION_ORDER]).astype(np.float32)
         act = {k: clipped[i] for i, k in enumerate(L.ACTION_ORDER)}
         act["target_weight"] = self.target_weight
-        fw = float(info["final_weight"][0].item())
-        tt = float(info["total_time"][0].item())
+        fw = float(info["final_weight"][0])
+        tt = float(info["total_time"][0])
         self.step_counter += 1
-        return (ns[0].cpu().numpy(), float(r[0].item()), bool(d[0].item()),
+        return (ns[0].numpy().copy(), float(r[0]), bool(d[0]),
                 {"final_weight": fw, "weight_error": abs(fw - self.target_weight), "total_time": tt, "action": act})
 
 
