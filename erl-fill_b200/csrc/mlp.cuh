@@ -122,6 +122,166 @@ static __global__ void __launch_bounds__(256, 3) gemm_kernel(int M, int N, int K
               blockIdx.y * BM, blockIdx.x * BN);
 }
 
+// ---- large-M forward GEMM: C[M,N] = act(A[M,K] W[N,K]^T + bias[N]), A and W row-major with unit K stride -------------------
+// The act paths of the batched agents push 16,384 .. 131,072 rows through 256-wide layers; there the 64 x 64 kernel above is
+// bound by its fragment traffic (4 instructions per MMA: ncu tensor pipe 34 %, profiles/r01d_td3_gemm.txt).  Here a CTA owns a
+// 128 x 128 tile and a warp 64 x 32 of it (4 x 4 MMA tiles): 24 fragment loads + 24 hi/lo splits feed 48 MMAs per k-step
+// (2.5 instructions per MMA), tiles arrive through a 3-stage cp.async ring of 32-wide K chunks with one barrier per chunk.
+// Per output element the accumulation order (k ascending, lo*hi, hi*lo, hi*hi per k-step) is the one of gemm_kernel: same bits.
+constexpr int GB_M = 128, GB_N = 128, GB_K = 32, GB_LD = 36, GB_STAGES = 3;      // 36 % 32 == 4: conflict-free fragment loads
+constexpr int kGemmBigSmem = GB_STAGES * (GB_M + GB_N) * GB_LD * 4;               // 110,592 B
+static __device__ __forceinline__ void gb_cp_async16(float *s, const float *g) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(s);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g));
+}
+static __global__ void __launch_bounds__(256, 1) gemm_big_kernel(int M, int N, int K, const float *__restrict__ A, int lda,
+                                                                 const float *__restrict__ W, int ldw, float *__restrict__ C, int ldc,
+                                                                 const float *__restrict__ bias, int act) {
+    extern __shared__ __align__(16) float gsm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;      // 2 x 4 warps, each 64 x 32 = 4 (m16) x 4 (n8) MMA tiles
+    const int g = lane >> 2, t = lane & 3;
+    const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N;
+    float acc[4][4][4] = {};
+    const int nk = K / GB_K;
+    auto load = [&](int c) {
+        float *As = gsm + (c % GB_STAGES) * (GB_M + GB_N) * GB_LD, *Ws = As + GB_M * GB_LD;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int v = tid + it * 256, r = v >> 3, c4 = (v & 7) * 4;
+            float *da = As + r * GB_LD + c4, *dw = Ws + r * GB_LD + c4;
+            if (m0 + r < M) gb_cp_async16(da, A + (size_t)(m0 + r) * lda + c * GB_K + c4);
+            else *reinterpret_cast<float4 *>(da) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + r < N) gb_cp_async16(dw, W + (size_t)(n0 + r) * ldw + c * GB_K + c4);
+            else *reinterpret_cast<float4 *>(dw) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    load(0);
+    if (nk > 1) load(1);
+#pragma unroll 1
+    for (int c = 0; c < nk; ++c) {
+        if (c + 1 < nk) asm volatile("cp.async.wait_group 1;"); else asm volatile("cp.async.wait_group 0;");
+        __syncthreads();
+        if (c + 2 < nk) load(c + 2);           // into the stage chunk c - 1 was read from: every warp is past its MMAs
+        const float *As = gsm + (c % GB_STAGES) * (GB_M + GB_N) * GB_LD, *Ws = As + GB_M * GB_LD;
+#pragma unroll
+        for (int ks = 0; ks < GB_K; ks += 8) {
+            uint32_t ah[4][4], al[4][4], bh[4][2], bl[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float *ap = As + (wm + i * 16 + g) * GB_LD + ks + t;
+                split_tf32(ap[0], ah[i][0], al[i][0]);
+                split_tf32(ap[8 * GB_LD], ah[i][1], al[i][1]);
+                split_tf32(ap[4], ah[i][2], al[i][2]);
+                split_tf32(ap[8 * GB_LD + 4], ah[i][3], al[i][3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float *bp = Ws + (wn + j * 8 + g) * GB_LD + ks + t;
+                split_tf32(bp[0], bh[j][0], bl[j][0]);
+                split_tf32(bp[4], bh[j][1], bl[j][1]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_tf32(acc[i][j], al[i], bh[j]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_tf32(acc[i][j], ah[i], bl[j]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_tf32(acc[i][j], ah[i], bh[j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int gm = m0 + wm + i * 16 + g + (e >> 1) * 8, gn = n0 + wn + j * 8 + 2 * t + (e & 1);
+                if (gm >= M || gn >= N) continue;
+                float v = acc[i][j][e];
+                if (bias) v += bias[gn];
+                if (act == ACT_RELU) v = fmaxf(v, 0.f);
+                else if (act == ACT_LEAKY) v = v > 0.f ? v : 0.1f * v;
+                C[(size_t)gm * ldc + gn] = v;
+            }
+}
+
+// ---- the two thin layers of the act MLPs at large M (exact fp32 FMA; the MMA tile kernels are mostly padding there) ------------
+// K <= 4 (state -> first hidden layer): C[m][n] = act(bias[n] + sum_k A[m][k] W[n][k]); one thread per (row, 4 columns): the
+// kernel is the 4 N bytes per row it writes.
+static __global__ void __launch_bounds__(256) linear_smallk_kernel(int M, int N, int K, const float *__restrict__ A, int lda,
+                                                                   const float *__restrict__ W, int ldw, float *__restrict__ C, int ldc,
+                                                                   const float *__restrict__ bias, int act) {
+    const int n4 = N >> 2;
+    const size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gidx >= (size_t)M * n4) return;
+    const int m = (int)(gidx / n4), n = (int)(gidx % n4) * 4;
+    float a[4], v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = k < K ? __ldg(A + (size_t)m * lda + k) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float s = bias ? __ldg(bias + n + j) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (k < K) s = fmaf(a[k], __ldg(W + (size_t)(n + j) * ldw + k), s);
+        if (act == ACT_RELU) s = fmaxf(s, 0.f);
+        else if (act == ACT_LEAKY) s = s > 0.f ? s : 0.1f * s;
+        v[j] = s;
+    }
+    *reinterpret_cast<float4 *>(C + (size_t)m * ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+}
+// N <= 16 (last hidden layer -> action heads), K a multiple of 128: one warp per row, lane l owns k = l + 32 q (coalesced loads
+// of the row), W transposed in shared memory as [k][20] (20-word stride: the 128-bit loads of a quarter-warp hit distinct
+// banks), the N partial sums reduced by butterfly shuffles (fixed order).
+constexpr int kThinNMax = 16, kThinLd = 20;
+static __global__ void __launch_bounds__(256) linear_smalln_kernel(int M, int N, int K, const float *__restrict__ A, int lda,
+                                                                   const float *__restrict__ W, int ldw, float *__restrict__ C, int ldc,
+                                                                   const float *__restrict__ bias, int act) {
+    extern __shared__ __align__(16) float wsm[];        // [K][kThinLd]
+    for (int i = threadIdx.x; i < K * kThinNMax; i += blockDim.x) {
+        const int n = i / K, k = i % K;                 // consecutive threads read consecutive k of one W row
+        wsm[k * kThinLd + n] = n < N ? __ldg(W + (size_t)n * ldw + k) : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (int m = blockIdx.x * wpb + warp; m < M; m += gridDim.x * wpb) {
+        float s[kThinNMax];
+#pragma unroll
+        for (int n = 0; n < kThinNMax; ++n) s[n] = 0.f;
+        const float *arow = A + (size_t)m * lda;
+        for (int k = lane; k < K; k += 32) {
+            const float av = __ldg(arow + k);
+            const float4 *wr = reinterpret_cast<const float4 *>(wsm + (size_t)k * kThinLd);
+#pragma unroll
+            for (int n4 = 0; n4 < kThinNMax / 4; ++n4) {
+                const float4 w = wr[n4];
+                s[4 * n4 + 0] = fmaf(av, w.x, s[4 * n4 + 0]); s[4 * n4 + 1] = fmaf(av, w.y, s[4 * n4 + 1]);
+                s[4 * n4 + 2] = fmaf(av, w.z, s[4 * n4 + 2]); s[4 * n4 + 3] = fmaf(av, w.w, s[4 * n4 + 3]);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < kThinNMax; ++n) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) s[n] += __shfl_xor_sync(0xffffffffu, s[n], d);
+        }
+        if (lane < N) {
+            float v = 0.f;
+#pragma unroll
+            for (int n = 0; n < kThinNMax; ++n) v = lane == n ? s[n] : v;
+            if (bias) v += __ldg(bias + lane);
+            if (act == ACT_RELU) v = fmaxf(v, 0.f);
+            else if (act == ACT_LEAKY) v = v > 0.f ? v : 0.1f * v;
+            C[(size_t)m * ldc + lane] = v;
+        }
+    }
+}
+
 // ---- grouped weight gradients: up to 4 GEMMs dW_i[N_i][K_i] = dZ_i^T[N_i][Bt] X_i[Bt][K_i] in ONE launch ------------
 // Every task is cut into 64 x 64 tiles x `splits` slices of the batch rows; slice s of task i goes to part_i + s*N_i*K_i
 // and group_reduce_kernel adds the slices in index order (deterministic).
@@ -232,6 +392,31 @@ static __global__ void fill_kernel(int n, float v, float *p) {
 // ---- launch helpers ---------------------------------------------------------------------------
 static inline void gemm(cudaStream_t st, int M, int N, int K, const float *A, int sam, int sak, const float *B, int sbk, int sbn,
                         float *C, int ldc, const float *bias, int act) {
+    // large row-major forward GEMMs (the act paths): thin first / last layers in exact fp32, the 128 x 128 tile kernel for the
+    // hidden layers; everything else: the 64 x 64 strided kernel
+    if (M >= 8192 && sak == 1 && sbk == 1) {
+        if (K <= 4 && (N & 3) == 0 && (ldc & 3) == 0 && ((uintptr_t)C & 15u) == 0) {
+            const size_t total = (size_t)M * (N >> 2);
+            linear_smallk_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(M, N, K, A, sam, B, sbn, C, ldc, bias, act);
+            return;
+        }
+        if (N <= kThinNMax && K % 32 == 0 && K <= 512) {
+            linear_smalln_kernel<<<148 * 8, 256, (size_t)K * kThinLd * sizeof(float), st>>>(M, N, K, A, sam, B, sbn, C, ldc, bias, act);
+            return;
+        }
+    }
+    if (M >= 8192 && N >= 64 && sak == 1 && sbk == 1 && K % GB_K == 0 && (sam & 3) == 0 && (sbn & 3) == 0 &&
+        (((uintptr_t)A | (uintptr_t)B) & 15u) == 0) {
+        static bool attr_set[64] = {};
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !attr_set[dev]) {
+            cudaFuncSetAttribute(gemm_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmBigSmem);
+            attr_set[dev] = true;
+        }
+        dim3 gridb((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M, 1);
+        gemm_big_kernel<<<gridb, 256, kGemmBigSmem, st>>>(M, N, K, A, sam, B, sbn, C, ldc, bias, act);
+        return;
+    }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
     gemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, ldc, bias, act, K, 0);
 }
