@@ -213,71 +213,105 @@ static __global__ void __launch_bounds__(256, 1) gemm_big_kernel(int M, int N, i
 }
 
 // ---- the two thin layers of the act MLPs at large M (exact fp32 FMA; the MMA tile kernels are mostly padding there) ------------
-// K <= 4 (state -> first hidden layer): C[m][n] = act(bias[n] + sum_k A[m][k] W[n][k]); one thread per (row, 4 columns): the
-// kernel is the 4 N bytes per row it writes.
-static __global__ void __launch_bounds__(256) linear_smallk_kernel(int M, int N, int K, const float *__restrict__ A, int lda,
+// K <= 4 (state -> first hidden layer), N == 256: C[m][n] = act(bias[n] + sum_k A[m][k] W[n][k]).  A warp walks rows; lane l owns
+// columns 4 l .. 4 l + 3 and 128 + 4 l .. : its 8 weight rows and biases stay in registers, a row costs two broadcast loads and two
+// fully coalesced 512-byte stores: the kernel is the bytes it writes.
+constexpr int kThinKN = 256;
+static __global__ void __launch_bounds__(256) linear_smallk_kernel(int M, int K, const float *__restrict__ A, int lda,
                                                                    const float *__restrict__ W, int ldw, float *__restrict__ C, int ldc,
                                                                    const float *__restrict__ bias, int act) {
-    const int n4 = N >> 2;
-    const size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gidx >= (size_t)M * n4) return;
-    const int m = (int)(gidx / n4), n = (int)(gidx % n4) * 4;
-    float a[4], v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) a[k] = k < K ? __ldg(A + (size_t)m * lda + k) : 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float s = bias ? __ldg(bias + n + j) : 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (k < K) s = fmaf(a[k], __ldg(W + (size_t)(n + j) * ldw + k), s);
-        if (act == ACT_RELU) s = fmaxf(s, 0.f);
-        else if (act == ACT_LEAKY) s = s > 0.f ? s : 0.1f * s;
-        v[j] = s;
-    }
-    *reinterpret_cast<float4 *>(C + (size_t)m * ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
-}
-// N <= 16 (last hidden layer -> action heads), K a multiple of 128: one warp per row, lane l owns k = l + 32 q (coalesced loads
-// of the row), W transposed in shared memory as [k][20] (20-word stride: the 128-bit loads of a quarter-warp hit distinct
-// banks), the N partial sums reduced by butterfly shuffles (fixed order).
-constexpr int kThinNMax = 16, kThinLd = 20;
-static __global__ void __launch_bounds__(256) linear_smalln_kernel(int M, int N, int K, const float *__restrict__ A, int lda,
-                                                                   const float *__restrict__ W, int ldw, float *__restrict__ C, int ldc,
-                                                                   const float *__restrict__ bias, int act) {
-    extern __shared__ __align__(16) float wsm[];        // [K][kThinLd]
-    for (int i = threadIdx.x; i < K * kThinNMax; i += blockDim.x) {
-        const int n = i / K, k = i % K;                 // consecutive threads read consecutive k of one W row
-        wsm[k * kThinLd + n] = n < N ? __ldg(W + (size_t)n * ldw + k) : 0.f;
-    }
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float w[8][4], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int n = (j >> 2) * 128 + 4 * lane + (j & 3);
+        b[j] = bias ? __ldg(bias + n) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[j][k] = k < K ? __ldg(W + (size_t)n * ldw + k) : 0.f;
+    }
     for (int m = blockIdx.x * wpb + warp; m < M; m += gridDim.x * wpb) {
+        float a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = k < K ? __ldg(A + (size_t)m * lda + k) : 0.f;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float s = b[j];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (k < K) s = fmaf(a[k], w[j][k], s);
+            if (act == ACT_RELU) s = fmaxf(s, 0.f);
+            else if (act == ACT_LEAKY) s = s > 0.f ? s : 0.1f * s;
+            v[j] = s;
+        }
+        float4 *dst = reinterpret_cast<float4 *>(C + (size_t)m * ldc) + lane;
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[32] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+// N <= 16 (last hidden layer -> action heads), K == 256: one warp per row, lane l owns k = l + 32 q; its 8 x 16 weights stay in
+// registers, a row costs 8 coalesced loads, 128 FMAs and a 16-shuffle transposing reduction (each step halves the values a lane
+// holds and the lanes that share them; fixed order), after which lane 2 n (bit-reversed over lane bits 4..1) holds output n.
+constexpr int kThinNMax = 16, kThinNK = 256;
+template <int NW>      // columns of W held in registers: N <= NW <= 16 (10 for the action heads: 80 weight registers, two CTAs per SM)
+static __global__ void __launch_bounds__(256, NW <= 10 ? 2 : 1) linear_smalln_kernel(int M, int N, const float *__restrict__ A, int lda,
+                                                                      const float *__restrict__ W, int ldw, float *__restrict__ C, int ldc,
+                                                                      const float *__restrict__ bias, int act) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float w[8][NW];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int n = 0; n < NW; ++n) w[q][n] = n < N ? __ldg(W + (size_t)n * ldw + lane + 32 * q) : 0.f;
+    // output this lane ends up with: bit 4 of the lane picks the upper 8, bit 3 the upper 4 of those, ...
+    const int n_mine = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const float b_mine = (bias && n_mine < N) ? __ldg(bias + n_mine) : 0.f;
+    const int stride = gridDim.x * wpb;
+    float an[8];                                        // the next row's values are in flight while this row is reduced
+    {
+        const int m = blockIdx.x * wpb + warp;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) an[q] = m < M ? __ldg(A + (size_t)m * lda + lane + 32 * q) : 0.f;
+    }
+    for (int m = blockIdx.x * wpb + warp; m < M; m += stride) {
+        float a[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] = an[q];
+        if (m + stride < M) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) an[q] = __ldg(A + (size_t)(m + stride) * lda + lane + 32 * q);
+        }
         float s[kThinNMax];
 #pragma unroll
         for (int n = 0; n < kThinNMax; ++n) s[n] = 0.f;
-        const float *arow = A + (size_t)m * lda;
-        for (int k = lane; k < K; k += 32) {
-            const float av = __ldg(arow + k);
-            const float4 *wr = reinterpret_cast<const float4 *>(wsm + (size_t)k * kThinLd);
 #pragma unroll
-            for (int n4 = 0; n4 < kThinNMax / 4; ++n4) {
-                const float4 w = wr[n4];
-                s[4 * n4 + 0] = fmaf(av, w.x, s[4 * n4 + 0]); s[4 * n4 + 1] = fmaf(av, w.y, s[4 * n4 + 1]);
-                s[4 * n4 + 2] = fmaf(av, w.z, s[4 * n4 + 2]); s[4 * n4 + 3] = fmaf(av, w.w, s[4 * n4 + 3]);
-            }
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int n = 0; n < NW; ++n) s[n] = fmaf(a[q], w[q][n], s[n]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float send = (lane & 16) ? s[i] : s[i + 8], keep = (lane & 16) ? s[i + 8] : s[i];
+            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
 #pragma unroll
-        for (int n = 0; n < kThinNMax; ++n) {
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) s[n] += __shfl_xor_sync(0xffffffffu, s[n], d);
+        for (int i = 0; i < 4; ++i) {
+            const float send = (lane & 8) ? s[i] : s[i + 4], keep = (lane & 8) ? s[i + 4] : s[i];
+            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
         }
-        if (lane < N) {
-            float v = 0.f;
 #pragma unroll
-            for (int n = 0; n < kThinNMax; ++n) v = lane == n ? s[n] : v;
-            if (bias) v += __ldg(bias + lane);
+        for (int i = 0; i < 2; ++i) {
+            const float send = (lane & 4) ? s[i] : s[i + 2], keep = (lane & 4) ? s[i + 2] : s[i];
+            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        {
+            const float send = (lane & 2) ? s[0] : s[1], keep = (lane & 2) ? s[1] : s[0];
+            s[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+        if ((lane & 1) == 0 && n_mine < N) {
+            float v = s[0] + b_mine;
             if (act == ACT_RELU) v = fmaxf(v, 0.f);
             else if (act == ACT_LEAKY) v = v > 0.f ? v : 0.1f * v;
-            C[(size_t)m * ldc + lane] = v;
+            C[(size_t)m * ldc + n_mine] = v;
         }
     }
 }
@@ -395,13 +429,13 @@ static inline void gemm(cudaStream_t st, int M, int N, int K, const float *A, in
     // large row-major forward GEMMs (the act paths): thin first / last layers in exact fp32, the 128 x 128 tile kernel for the
     // hidden layers; everything else: the 64 x 64 strided kernel
     if (M >= 8192 && sak == 1 && sbk == 1) {
-        if (K <= 4 && (N & 3) == 0 && (ldc & 3) == 0 && ((uintptr_t)C & 15u) == 0) {
-            const size_t total = (size_t)M * (N >> 2);
-            linear_smallk_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(M, N, K, A, sam, B, sbn, C, ldc, bias, act);
+        if (K <= 4 && N == kThinKN && (ldc & 3) == 0 && ((uintptr_t)C & 15u) == 0) {
+            linear_smallk_kernel<<<148 * 8, 256, 0, st>>>(M, K, A, sam, B, sbn, C, ldc, bias, act);
             return;
         }
-        if (N <= kThinNMax && K % 32 == 0 && K <= 512) {
-            linear_smalln_kernel<<<148 * 8, 256, (size_t)K * kThinLd * sizeof(float), st>>>(M, N, K, A, sam, B, sbn, C, ldc, bias, act);
+        if (N <= kThinNMax && K == kThinNK) {
+            if (N <= 10) linear_smalln_kernel<10><<<148 * 2, 256, 0, st>>>(M, N, A, sam, B, sbn, C, ldc, bias, act);
+            else linear_smalln_kernel<kThinNMax><<<148, 256, 0, st>>>(M, N, A, sam, B, sbn, C, ldc, bias, act);
             return;
         }
     }
