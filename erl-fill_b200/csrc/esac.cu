@@ -306,7 +306,7 @@ static void policy_forward(cudaStream_t st, int B, const float *P, const float *
     gemm(st, B, AD, H, b.h2, H, 1, P + PO::LS_W, 1, H, b.ml + AD, 20, P + PO::LS_B, ACT_NONE);
 }
 
-constexpr int kActChunk = 16384;
+constexpr int kActChunk = 65536;     // rows per pass of the policy MLP (as in td3_sac.cu: whole waves of 128 x 128 GEMM tiles)
 
 }  // namespace esac
 }  // namespace erlfill
