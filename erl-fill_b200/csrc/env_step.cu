@@ -645,6 +645,7 @@ struct WarpNoise {
     uint32_t k0, k1, gid, step_idx;
     int b0;         // the warp holds the draw window [4*b0, 4*b0 + kWindow): lane L has noise blocks b0 + 32*h + L
     uint4 raw[kNoiseBlocks];
+    uint32_t *sh;   // the same window in shared memory, word i = draw 4*b0 + i (random access for the motor moves and generic ticks)
 #ifdef ERLFILL_SIM_PROF
     long long pf_fast = 0, pf_hold = 0, pf_cross = 0, pf_move = 0, pf_gen = 0;
     int pf_fastwin = 0, pf_win = 0, pf_nhold = 0, pf_nmove = 0, pf_ngen = 0, pf_movefail = 0;
@@ -654,19 +655,15 @@ struct WarpNoise {
 #pragma unroll
         for (int h = 0; h < kNoiseBlocks; ++h)
             raw[h] = philox4x32_10(k0, k1, gid, step_idx, (uint32_t)(block0 + 32 * h + lane), STREAM_TICK);
+        __syncwarp();                                   // every lane is done reading the previous window
+#pragma unroll
+        for (int h = 0; h < kNoiseBlocks; ++h) reinterpret_cast<uint4 *>(sh)[32 * h + lane] = raw[h];
+        __syncwarp();
     }
     // Philox word of draw t (0-based, inside the window); t may differ per lane
     __device__ __forceinline__ uint32_t word(int t) const {
-        const int rel = t - 4 * b0, src = (rel >> 2) & 31, k = rel & 3, hh = rel >> 7;
-        uint32_t r = 0;
-#pragma unroll
-        for (int h = 0; h < kNoiseBlocks; ++h) {
-            const uint32_t xa = __shfl_sync(kFullMask, raw[h].x, src), xb = __shfl_sync(kFullMask, raw[h].y, src);
-            const uint32_t xc = __shfl_sync(kFullMask, raw[h].z, src), xd = __shfl_sync(kFullMask, raw[h].w, src);
-            const uint32_t v = k == 0 ? xa : (k == 1 ? xb : (k == 2 ? xc : xd));
-            r = hh == h ? v : r;
-        }
-        return r;
+        const int rel = t - 4 * b0;
+        return (unsigned)rel < (unsigned)kWindow ? sh[rel] : 0u;
     }
 };
 
@@ -1153,6 +1150,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 32 / kWarpsPerCta) env_sim_
     // noise window is generated
     __shared__ __align__(16) double sh_p[kWarpsPerCta][64];
     __shared__ __align__(16) double sh_traj[kWarpsPerCta][2 * kTrajLen];
+    __shared__ __align__(16) uint32_t sh_noise[kWarpsPerCta][kWindow];
     int pre0 = -1, pre1 = -1;
     {
         const int fo = __shfl_sync(kFullMask, iv, 3), so = __shfl_sync(kFullMask, iv, 5);
@@ -1169,7 +1167,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 32 / kWarpsPerCta) env_sim_
     const uint4 misc = philox4x32_10(k0, k1, gid, a.step(), 0u, STREAM_MISC);
     const double sysdelay = 15.0 + 35.0 * u32_to_unit(misc.x);             // uniform(15, 50): :137
     WarpNoise nz;
-    nz.k0 = k0; nz.k1 = k1; nz.gid = gid; nz.step_idx = a.step(); nz.b0 = 0;
+    nz.k0 = k0; nz.k1 = k1; nz.gid = gid; nz.step_idx = a.step(); nz.b0 = 0; nz.sh = sh_noise[warp];
 #ifdef ERLFILL_SIM_PROF
     const long long pf_c1 = clock64();
 #endif
