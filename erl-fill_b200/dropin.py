@@ -190,6 +190,7 @@ class EmotionModule:
         self.transformer = TransformerFacade(self)
         self._calls = 0
         self._cache = None
+        self._cache_host = None
         self._out = torch.zeros(1, 3, dtype=torch.float32, device=self.device)
         self._r = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._zero2 = torch.zeros(1, 2, dtype=torch.float32, device=self.device)
@@ -214,6 +215,7 @@ class EmotionModule:
         self._mv.copy_(torch.from_numpy(mv).view(1, 2))
         nets.emotion_update(self.emo, self._r, self._zero2, self._mv)              # (0 + movement) - 0: exact
         self._cache = None
+        self._cache_host = None
         return self.current_emotion.copy()
 
     def get_emotion_device(self):
@@ -226,10 +228,14 @@ class EmotionModule:
                                  out=self._out, precision=self.precision)
             self._calls += 1
             self._cache = self._out
+            self._cache_host = None
         return self._cache
 
     def get_emotion(self):
-        return self.get_emotion_device()[0].cpu().numpy()
+        dev = self.get_emotion_device()
+        if self._cache_host is None or self.dropout != L.DROPOUT_OFF:
+            self._cache_host = dev[0].cpu().numpy()          # one D2H per transformer call; repeated calls return copies
+        return self._cache_host.copy()
 
     def save(self, path):
         torch.save(self.transformer.state_dict(), path)
@@ -290,6 +296,7 @@ class PrioritizedReplay:
         self.buffer, self.priorities = [], []
         self.device_ring = ddpg.ReplayBuffer(capacity, device=device)
         self._scale, self._offset, self._dev = scale, offset, device
+        self._stage = None
 
     def __len__(self):
         return len(self.buffer)
@@ -310,19 +317,35 @@ class PrioritizedReplay:
             self.buffer[slot] = transition; self.priorities[slot] = p
         s, a, r, s2, d, e = transition[:6]
         dev = self._dev
-        t = lambda x, n: torch.as_tensor(np.asarray(x, dtype=np.float32).reshape(1, n)).to(dev)
         ring = self.device_ring
-        pos = torch.tensor([slot], dtype=torch.int64, device=dev)
-        # the kernel normalises a raw action with (a - offset) / scale, clip +-1 (ddpg_agent.py:374-376); an already
-        # normalised one is written as is.  (Locals keep every staging tensor alive until the launch is queued.)
+        # One pinned staging record (96 B: state | action | reward | next_state | emotion | done | ring position), ONE H2D
+        # copy, the insert kernel reads the device copy field by field.  The kernel normalises a raw action with
+        # (a - offset) / scale, clip +-1 (ddpg_agent.py:374-376); an already normalised one is written as is.
+        if self._stage is None:
+            self._stage_h = torch.zeros(96, dtype=torch.uint8).pin_memory()
+            self._stage = torch.zeros(96, dtype=torch.uint8, device=dev)
+            self._stage_ev = torch.cuda.Event()
+            self._stage_busy = False
+        if self._stage_busy:
+            self._stage_ev.synchronize()            # the previous record's copy has left the pinned buffer (normally long ago)
+        hf = self._stage_h[:80].view(torch.float32).numpy()
+        hf[0:2] = np.asarray(s, dtype=np.float32).reshape(2)
+        hf[2:12] = np.asarray(raw_action if raw_action is not None else a, dtype=np.float32).reshape(10)
+        hf[12] = float(r)
+        hf[14:16] = np.asarray(s2, dtype=np.float32).reshape(2)
+        hf[16:19] = np.asarray(e, dtype=np.float32).reshape(3)
+        self._stage_h[80] = 1 if d else 0
+        self._stage_h[88:96].view(torch.int64)[0] = slot
         import ctypes as C
-        act, sc, of = (t(raw_action, 10), self._scale, self._offset) if raw_action is not None else (t(a, 10), None, None)
-        d_s, d_s2, d_e = t(s, 2), t(s2, 2), t(e, 3)
-        d_r = torch.tensor([float(r)], dtype=torch.float32, device=dev)
-        d_d = torch.tensor([1 if d else 0], dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            L.check(L.lib().erlfill_replay_insert(C.c_int(1), L.ptr(ring.buf), C.c_int64(ring.capacity), C.c_int64(0), L.ptr(pos),
-                                                  L.ptr(d_s), L.ptr(act), L.ptr(d_r), L.ptr(d_s2), L.ptr(d_d), L.ptr(d_e),
+            self._stage.copy_(self._stage_h, non_blocking=True)
+            self._stage_ev.record()
+            self._stage_busy = True
+            base = self._stage.data_ptr()
+            P = lambda off: C.c_void_p(base + off)
+            sc, of = (self._scale, self._offset) if raw_action is not None else (None, None)
+            L.check(L.lib().erlfill_replay_insert(C.c_int(1), L.ptr(ring.buf), C.c_int64(ring.capacity), C.c_int64(0), P(88),
+                                                  P(0), P(8), P(48), P(56), P(80), P(64),
                                                   L.ptr(sc), L.ptr(of), L.stream_ptr()), "erlfill_replay_insert")
         ring.size = len(self.buffer)
         ring.inserted += 1
@@ -407,7 +430,11 @@ class DDPGAgent:
         """ddpg_agent.py:359-395."""
         emotion_state = self.emotion.get_emotion()
         a32 = np.asarray(action, dtype=np.float32)
-        scale, offset = self.learner.scale.cpu().numpy(), self.learner.offset.cpu().numpy()
+        ver = (self.learner.scale._version, self.learner.offset._version)
+        if getattr(self, "_so_ver", None) != ver:                 # host copies of the scaling buffers, refreshed when they change
+            self._so_host = (self.learner.scale.cpu().numpy(), self.learner.offset.cpu().numpy())
+            self._so_ver = ver
+        scale, offset = self._so_host
         norm_action = np.clip((np.array(action) - offset) / scale, -1.0, 1.0)      # what the tuple list shows; the device row is
         td_error = 0                                                              # normalised by the insert kernel from a32
         if self.use_td_error:

@@ -277,6 +277,7 @@ class _ScalarEnvBase:
             self._vec = VecFillEnv([cfg], 1, kind=self._kind, max_steps=self.max_steps, seed=self._seed,
                                    device=self._device, auto_reset=False)
             self._vec.use_host_outputs()
+            self._rs = np.random.RandomState(0)            # scratch generator: its state is overwritten from `random` every step
             self._a_host = torch.zeros(1, 10, dtype=torch.float32).pin_memory()
             self._a_dev = torch.zeros(1, 10, dtype=torch.float32, device=self._vec.device)
             self._u = torch.zeros(MAX_DRAWS, 1, dtype=torch.float64, device=self._vec.device)
@@ -319,12 +320,12 @@ class _ScalarEnvBase:
             # The reference draws uniform(15, 50) once and uniform(-1, 1) per tick from CPython's global Mersenne Twister
             # (VirtualWeightController.py:122,137).  numpy's RandomState is the same generator with the same 53-bit double
             # construction, so the draws are produced vectorised from a copy of `random`'s state (a + (b - a) * random(),
-            # the same two roundings as random.uniform), and `random` is then advanced by exactly the draws the run consumed.
+            # the same two roundings as random.uniform), and `random` is then advanced by exactly the draws the run consumed
+            # (getrandbits(64 k) takes 2 k outputs of the generator, like k calls of random.random()).
             st = random.getstate()
-            key, pos = np.array(st[1][:-1], dtype=np.uint32), st[1][-1]
-            rs = np.random.RandomState()
-            rs.set_state(("MT19937", key, pos))
-            u = rs.random_sample(MAX_DRAWS)
+            key = np.fromiter(st[1], dtype=np.uint32, count=625)          # 624 state words + the position
+            self._rs.set_state(("MT19937", key[:624], int(st[1][-1])))
+            u = self._rs.random_sample(MAX_DRAWS)
             host = self._u_host.numpy()
             host[0, 0] = 15.0 + 35.0 * u[0]
             host[1:, 0] = -1.0 + 2.0 * u[1:]
@@ -332,10 +333,7 @@ class _ScalarEnvBase:
             ns, r, d, info = v.step(a, noise_u=self._u)
             torch.cuda.current_stream(v.device).synchronize()      # outputs live in pinned host memory (use_host_outputs)
             n_draws = int(info["ticks"][0])
-            rs.set_state(("MT19937", key, pos))
-            rs.random_sample(1 + n_draws)
-            k2 = rs.get_state()
-            random.setstate((st[0], tuple(k2[1].tolist()) + (int(k2[2]),), st[2]))
+            random.getrandbits(64 * (1 + n_draws))     # == 1 + n_draws calls of random.random(): two 32-bit outputs each
         else:
             ns, r, d, info = v.step(a)
             torch.cuda.current_stream(v.device).synchronize()

@@ -74,26 +74,23 @@ def test_reference_noise_stream_is_cpythons_mersenne_twister():
     """envs._ScalarEnvBase.step (noise="reference") draws the run's uniforms vectorised from numpy's RandomState loaded with
     CPython `random`'s state, then advances `random` by exactly the draws consumed.  Both claims, on the CPU: the values equal
     random.uniform(15, 50) / random.uniform(-1, 1) bit for bit (VirtualWeightController.py:137,122), and the state written back
-    equals the state after that many random.random() calls."""
+    equals the state after that many random.random() calls (getrandbits(64 k) == k calls)."""
     import random
 
     import numpy as np
     random.seed(20240607)
     for trial in range(4):
         st = random.getstate()
-        key, pos = np.array(st[1][:-1], dtype=np.uint32), st[1][-1]
-        rs = np.random.RandomState()
-        rs.set_state(("MT19937", key, pos))
+        key = np.fromiter(st[1], dtype=np.uint32, count=625)
+        rs = np.random.RandomState(0)
+        rs.set_state(("MT19937", key[:624], int(st[1][-1])))
         u = rs.random_sample(5001)
         ours = np.concatenate([[15.0 + 35.0 * u[0]], -1.0 + 2.0 * u[1:]])
         ref = np.array([random.uniform(15, 50)] + [random.uniform(-1, 1) for _ in range(5000)])
         assert np.array_equal(ours, ref)
         random.setstate(st)
         n_draws = 700 + 611 * trial
-        rs.set_state(("MT19937", key, pos))
-        rs.random_sample(1 + n_draws)
-        k2 = rs.get_state()
-        random.setstate((st[0], tuple(k2[1].tolist()) + (int(k2[2]),), st[2]))
+        random.getrandbits(64 * (1 + n_draws))
         ours_state = random.getstate()
         random.setstate(st)
         for _ in range(1 + n_draws):
