@@ -428,9 +428,9 @@ static inline void gemm(cudaStream_t st, int M, int N, int K, const float *A, in
                         float *C, int ldc, const float *bias, int act) {
     // large row-major forward GEMMs (the act paths): thin first / last layers in exact fp32, the 128 x 128 tile kernel for the
     // hidden layers; everything else: the 64 x 64 strided kernel
-    if (M >= 8192 && sak == 1 && sbk == 1) {
+    if (M >= 1024 && sak == 1 && sbk == 1) {      // thin layers: already at minibatch size (the B = 4096 updates), not only on the act path
         if (K <= 4 && N == kThinKN && (ldc & 3) == 0 && ((uintptr_t)C & 15u) == 0) {
-            linear_smallk_kernel<<<148 * 8, 256, 0, st>>>(M, K, A, sam, B, sbn, C, ldc, bias, act);
+            linear_smallk_kernel<<<M >= 65536 ? 148 * 8 : 148 * 2, 256, 0, st>>>(M, K, A, sam, B, sbn, C, ldc, bias, act);
             return;
         }
         if (N <= kThinNMax && K == kThinNK) {
