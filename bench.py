@@ -37,12 +37,12 @@ L2_FLUSH_BYTES = 256 << 20      # > 126 MB L2
 # warp-instructions one env-step of the `sim` workload issues (ncu smsp__inst_executed.sum / n_env): the fused
 # env_sim_warp_kernel<true> when the batch is resident at once (profiles/r01d_env_sim_warp_4096.txt), else
 # env_sim_warp_kernel<false> + env_finish_kernel (profiles/r01d_env_sim_warp_65536.txt)
-SIM_WARP_INSTR_PER_ENV_STEP = {("pid", True): 3683.9, ("pid", False): 3118.3 + 20.4}
+SIM_WARP_INSTR_PER_ENV_STEP = {("pid", True): 3620.3, ("pid", False): 3074.6 + 20.4}
 SIM_FUSED_MAX_ENVS = 148 * 32   # csrc/env_step.cu: resident_warp_slots()
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of exactly these configurations
 # (cold L2, one launch): {(workload, envs per GPU): (bytes, summary file)}; any other configuration reports traffic null
-NCU_TRAFFIC = {("sim", 4096): (280576, "profiles/r01d_env_sim_warp_4096.txt"),
-               ("sim", 65536): (2663168 + 4750336, "profiles/r01d_env_sim_warp_65536.txt (simulator + finish kernel)"),
+NCU_TRAFFIC = {("sim", 4096): (280064, "profiles/r01d_env_sim_warp_4096.txt"),
+               ("sim", 65536): (2662400 + 4749824, "profiles/r01d_env_sim_warp_65536.txt (simulator + finish kernel)"),
                ("rollout", 65536): (17171968, "profiles/r01b_emotion_tc.txt")}
 
 

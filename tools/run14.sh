@@ -1,0 +1,4 @@
+ncu --set full --clock-control none --import-source on -k regex:env_sim_warp -s 3 -c 1 -o gpurun_out/r01d_env_sim_warp_4096 -f python bench.py --workload sim --steps 2 --warmup 3 --cpu-budget 1 > gpurun_out/ncu_f9a.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"env_sim_warp|env_finish" -s 6 -c 2 -o gpurun_out/r01d_env_sim_warp_65536 -f python bench.py --workload sim --n-env 65536 --steps 2 --warmup 3 --cpu-budget 1 > gpurun_out/ncu_f9b.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_big -s 2 -c 1 -o gpurun_out/r01d_td3_gemm_big -f python bench.py --workload td3 --steps 2 --warmup 3 > gpurun_out/ncu_f9c.log 2>&1
+ls -la gpurun_out/*.ncu-rep | tail -4
