@@ -11,6 +11,8 @@ One JSON line on stdout (rank 0).  A "step" is one lock-step pass of the workloa
   update   configs[3]: ER-DDPG update, minibatch 4096 from a 1M-transition replay (sample + gather + U1-U5)
   td3|sac  configs[4]: full TD3 / SAC loop (act -> env step -> remember -> update of B=4096), 131,072 envs/GPU
   esac     EmotionSAC (ERL_Fill_agent.py) full loop incl. the emotion transformer, 65,536 envs/GPU
+  erddpg   the whole ER-DDPG loop: rollout (with replay insert / replay-branch resets) + one update of B=4096 per lock-step step
+  replay   rows R1/R2 alone against the HBM roofline; n1: configs[0], the N = 1 drop-in loop
   all      (default) the sim line, with the rollout and update results attached under "other_workloads"
 `value` is device-timed with inputs resident in HBM; `e2e` goes through the public Python API with pinned HOST
 buffers (H2D of the step's inputs, D2H of its results inside the timed region).
@@ -519,6 +521,68 @@ def wl_n1(args, rank, world, device, timer):
     }
 
 
+def wl_erddpg(args, rank, world, device, timer):
+    """The whole north-star loop for ER-DDPG: per lock-step step, transformer -> actor + OU -> env step -> replay-branch reset ->
+    emotion update -> replay insert of every env's transition -> ONE minibatch update (B = 4096, data-parallel at N > 1)."""
+    import torch
+    from erlfill_b200 import parallel
+    n, B = args.n_env, args.batch
+    env, agent = _make_agent(args, rank, device, n, B, max(4 * n, 1 << 20))
+    allreduce = None
+    if world > 1:
+        allreduce = parallel.PeerExchange(agent.learner, B) if args.exchange == "peer" else parallel.GradSync(world)
+
+    def step():
+        agent.rollout_step()
+        agent.learn(allreduce=allreduce)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    env.tick_sum.zero_()
+    total_ms, wall = timer.run(step, args.steps)
+    ticks_all = timer.sumr(int(env.tick_sum.item()))
+    obs_host = env.obs.cpu().pin_memory()
+    res_host = [torch.empty(n, 2).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory(),
+                torch.empty(4).pin_memory()]
+
+    def e2e_step():
+        env.obs.copy_(obs_host, non_blocking=True)
+        ns, r, d = agent.rollout_step()
+        rep = agent.learn(allreduce=allreduce)
+        res_host[0].copy_(ns, non_blocking=True); res_host[1].copy_(r, non_blocking=True); res_host[2].copy_(d, non_blocking=True)
+        res_host[3].copy_(rep, non_blocking=True)
+        timer.stream.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timer.run_block(e2e_step, args.steps)
+    tf_ms = _kernel_ms(timer, agent._emotion_forward)
+    peaks = _peaks()
+    achieved = TRANSFORMER_FLOP * n / (tf_ms * 1e-3) / 1e12
+    units = n * world * args.steps
+    return {
+        "metric": "env_steps_per_sec", "value": units / (total_ms * 1e-3), "unit": "env-steps/s",
+        "dtype": "f64 simulator, %s transformer, f32 actor, f32 (3xTF32) update" % agent.emotion_precision,
+        "ms_per_step": total_ms / args.steps, "wall_s_timed_region": wall, "updates_per_sec": world * args.steps / (total_ms * 1e-3),
+        "config": {"workload": "ER-DDPG full loop on MultiConditionWeightEnv (3 conditions round-robin), %d envs/GPU: transformer -> actor "
+                               "+ OU -> env step -> replay-branch reset -> emotion update -> replay insert -> one update of minibatch %d, "
+                               "dropout off" % (n, B),
+                   "n_env_per_gpu": n, "minibatch_per_gpu": B,
+                   "parallelism": "env-sharded x%d, data-parallel update (%s)" % (world, "none" if world == 1 else args.exchange),
+                   "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+        "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / units,
+        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": obs_host.numel() * 4,
+                "d2h_bytes_per_step": n * 13 + 16},
+        "gpu_launches": (10 + 26) * args.steps,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": _traffic("rollout", n)[0],
+                     "traffic_source": _traffic("rollout", n)[1], "peak_source": peaks["source"] + " (sustained)",
+                     "kernel": "emotion_forward_tc_kernel", "kernel_ms": tf_ms, "share_of_step": tf_ms / (total_ms / args.steps),
+                     "algorithmic_flop_per_env": TRANSFORMER_FLOP, "executed_flop_per_env": TRANSFORMER_FLOP_EXECUTED},
+    }
+
+
 def wl_loop(args, rank, world, device, timer):
     """configs[4]: TD3 / SAC on MultiConditionWeightEnv, full lock-step loop: act -> env step -> remember -> one update of
     B = 4096 from the rank's replay shard (data-parallel gradient all-reduce when world > 1)."""
@@ -610,7 +674,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     wl = {"sim": wl_sim, "rollout": wl_rollout, "update": wl_update, "td3": wl_loop, "sac": wl_loop, "esac": wl_loop,
-          "replay": wl_replay, "n1": wl_n1}
+          "replay": wl_replay, "n1": wl_n1, "erddpg": wl_erddpg}
     head = "sim" if args.workload == "all" else args.workload
     if args.workload == "all":
         args.n_env = args.n_env or 4096
@@ -742,7 +806,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "sim", "rollout", "update", "td3", "sac", "esac", "replay", "n1"],
+    ap.add_argument("--workload", default="all", choices=["all", "sim", "rollout", "update", "td3", "sac", "esac", "replay", "n1", "erddpg"],
                     help="all = the sim headline line plus compact rollout and update results under other_workloads")
     ap.add_argument("--n-env", type=int, default=None)
     ap.add_argument("--actions", default="pid", choices=["pid", "random"])
@@ -757,7 +821,7 @@ def main():
     args = ap.parse_args()
     if args.n_env is None:
         args.n_env = {"all": 4096, "sim": 4096, "rollout": 65536, "update": 256, "td3": 131072, "sac": 131072, "esac": 65536,
-                      "replay": 131072, "n1": 1}[args.workload]
+                      "replay": 131072, "n1": 1, "erddpg": 65536}[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
