@@ -134,7 +134,7 @@ static __device__ __forceinline__ void gb_cp_async16(float *s, const float *g) {
     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(s);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g));
 }
-static __global__ void __launch_bounds__(256, 1) gemm_big_kernel(int M, int N, int K, const float *__restrict__ A, int lda,
+static __global__ void __launch_bounds__(256, 2) gemm_big_kernel(int M, int N, int K, const float *__restrict__ A, int lda,
                                                                  const float *__restrict__ W, int ldw, float *__restrict__ C, int ldc,
                                                                  const float *__restrict__ bias, int act) {
     extern __shared__ __align__(16) float gsm[];

@@ -240,7 +240,7 @@ __global__ void act_finish_kernel(int n, int sac, int deterministic, const float
 }
 
 // ---- workspaces -----------------------------------------------------------------------------------------------------
-constexpr int kActChunk = 65536;     // rows per pass of the action-selection MLP (1024 tiles of the 128 x 128 GEMM: 6.9 waves of 148 SMs)
+constexpr int kActChunk = 131072;    // rows per pass of the action-selection MLP (2048 tiles of the 128 x 128 GEMM: 6.9 waves of 2 x 148 resident CTAs)
 struct Ws {
     float *cgrad, *agrad, *scal;
     float *x0, *h1a, *h2a, *h1b, *h2b, *ah1, *ah2, *z, *ml, *a, *se, *logp, *logp2;
