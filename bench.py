@@ -6,16 +6,22 @@
     python bench.py --impl reference ...      # the CPU port of the reference path on the host cores
 
 One JSON line on stdout (rank 0).  A "step" is one lock-step pass of the workload over the batch of every rank:
-  sim      configs[1] of BASELINE.json: batched WeightEnv rollout, PID-effective constant action (default, 4096 envs/GPU)
-  rollout  configs[2]: MultiConditionWeightEnv, EmotionModule transformer -> ER-DDPG actor + OU -> env step -> emotion update
+  rollout  configs[2] of BASELINE.json (the configuration the north-star target is quoted on): MultiConditionWeightEnv,
+           65,536 envs/GPU, EmotionModule transformer -> ER-DDPG actor + OU -> env step -> emotion update
+  sim      configs[1]: batched WeightEnv rollout, PID-effective constant action (4096 envs/GPU)
   update   configs[3]: ER-DDPG update, minibatch 4096 from a 1M-transition replay (sample + gather + U1-U5)
   td3|sac  configs[4]: full TD3 / SAC loop (act -> env step -> remember -> update of B=4096), 131,072 envs/GPU
   esac     EmotionSAC (ERL_Fill_agent.py) full loop incl. the emotion transformer, 65,536 envs/GPU
   erddpg   the whole ER-DDPG loop: rollout (with replay insert / replay-branch resets) + one update of B=4096 per lock-step step
   replay   rows R1/R2 alone against the HBM roofline; n1: configs[0], the N = 1 drop-in loop
-  all      (default) the sim line, with the rollout and update results attached under "other_workloads"
+  all      (default) the rollout line, with the sim and update results attached under "other_workloads"
 `value` is device-timed with inputs resident in HBM; `e2e` goes through the public Python API with pinned HOST
 buffers (H2D of the step's inputs, D2H of its results inside the timed region).
+
+`--impl reference` times the UNMODIFIED reference (vendored byte for byte into the git-ignored baseline/_ref/ by
+oracle/vendor_ref.py, imported through oracle/ref_shim.py) on the host cores for the SAME workload and prints the same line
+with an identical `config` (oracle/ref_bench.py).  At N = 1 our arm runs that leg itself
+on a bounded sample first (before CUDA is touched) and reports it as `cpu_baseline` (kind "reference").
 """
 import argparse
 import json
@@ -36,21 +42,35 @@ TRANSFORMER_FLOP = 21.83e6      # per env per call at S=20 (SURVEY.md section 8d
 TRANSFORMER_FLOP_EXECUTED = 3 * 5457920 + 174080 + 264192
 UPDATE_FLOP_PER_SAMPLE = 1.43e6
 L2_FLUSH_BYTES = 256 << 20      # > 126 MB L2
-# warp-instructions one env-step of the `sim` workload issues (ncu smsp__inst_executed.sum / n_env): the fused
-# env_sim_warp_kernel<true> when the batch is resident at once (profiles/r01d_env_sim_warp_4096.txt), else
-# env_sim_warp_kernel<false> + env_finish_kernel (profiles/r01d_env_sim_warp_65536.txt)
-SIM_WARP_INSTR_PER_ENV_STEP = {("pid", True): 3620.3, ("pid", False): 3074.6 + 20.4}
 SIM_FUSED_MAX_ENVS = 148 * 32   # csrc/env_step.cu: resident_warp_slots()
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of exactly these configurations
-# (cold L2, one launch): {(workload, envs per GPU): (bytes, summary file)}; any other configuration reports traffic null
-NCU_TRAFFIC = {("sim", 4096): (280064, "profiles/r01d_env_sim_warp_4096.txt"),
-               ("sim", 65536): (2662400 + 4749824, "profiles/r01d_env_sim_warp_65536.txt (simulator + finish kernel)"),
-               ("rollout", 65536): (17171968, "profiles/r01b_emotion_tc.txt")}
 
 
-def _traffic(workload, n):
-    t = NCU_TRAFFIC.get((workload, n))
-    return (t[0], t[1]) if t else (None, None)
+def _ncu_constants():
+    """Numbers that only an ncu capture can give (warp-instructions per env-step, DRAM bytes per launch) live in
+    profiles/ncu_constants.json next to the sha256 of the kernel source they were captured from; when the source has
+    changed since, the entry is reported with "stale": true instead of silently going out of date."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "ncu_constants.json")
+    if not os.path.exists(path):
+        return {}
+    d = json.load(open(path))
+    for e in d.values():
+        src = os.path.join(ROOT, "erl-fill_b200", "csrc", e.get("source", ""))
+        sha = hashlib.sha256(open(src, "rb").read()).hexdigest()[:16] if os.path.isfile(src) else None
+        e["stale"] = sha != e.get("source_sha16")
+    return d
+
+
+def _traffic(key):
+    e = _ncu_constants().get(key)
+    if not e or "dram_bytes_per_launch" not in e:
+        return None, None
+    return e["dram_bytes_per_launch"], e["file"] + (" (STALE: kernel source changed since the capture)" if e["stale"] else "")
+
+
+def _sim_instr(actions, fused):
+    e = _ncu_constants().get("sim_%s_%s" % (actions, "fused" if fused else "two_kernel"))
+    return (e["warp_instr_per_env_step"], e["stale"], e["file"]) if e and "warp_instr_per_env_step" in e else None
 
 
 def _peaks():
@@ -60,6 +80,50 @@ def _peaks():
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
                 "bf16_tflops_sustained": d["bf16_tflops_sustained"], "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+DEFAULT_N_ENV = {"all": 65536, "sim": 4096, "rollout": 65536, "update": 256, "td3": 131072, "sac": 131072, "esac": 65536,
+                 "replay": 131072, "n1": 1, "erddpg": 65536}
+DEFAULT_REPLAY = {"replay": 4 << 20}        # rows R1/R2 are measured on a ring larger than the 126 MB L2 (4 Mi rows x 80 B = 336 MB)
+
+
+def workload_config(name, args, world):
+    """The `config` object of the JSON line.  BOTH arms (ours and `--impl reference`) print exactly this dict for a given
+    command line: it names the workload, nothing about how an arm runs it (that goes under `timing` / `cpu_baseline`)."""
+    n, B, C = args.n_env, args.batch, args.replay
+    act = "PID-effective constant" if args.actions == "pid" else "uniform-random"
+    if name == "sim":
+        return {"workload": "configs[1]: batched WeightEnv rollout, %d envs/GPU, %s action (sim-kernel throughput)" % (n, act),
+                "n_env_per_gpu": n, "actions": args.actions, "parallelism": "env-sharded x%d, no data-path collective" % world}
+    if name == "rollout":
+        return {"workload": "configs[2]: MultiConditionWeightEnv (3 conditions round-robin), %d envs/GPU, per env-step: EmotionModule "
+                            "transformer -> ER-DDPG actor + OU -> env step -> emotion update" % n,
+                "n_env_per_gpu": n, "parallelism": "env-sharded x%d, no data-path collective" % world}
+    if name == "update":
+        return {"workload": "configs[3]: ER-DDPG update (DDPGAgent.learn), minibatch %d per GPU, %d-transition replay" % (B, C),
+                "minibatch_per_gpu": B, "replay": C, "parallelism": "dp%d" % world}
+    if name == "erddpg":
+        return {"workload": "ER-DDPG full loop on MultiConditionWeightEnv (3 conditions round-robin), %d envs/GPU: transformer -> "
+                            "actor + OU -> env step -> reset -> emotion update -> remember -> one update of minibatch %d" % (n, B),
+                "n_env_per_gpu": n, "minibatch_per_gpu": B, "parallelism": "env-sharded x%d, data-parallel update" % world}
+    if name in ("td3", "sac", "esac"):
+        return {"workload": "configs[4]: %s on MultiConditionWeightEnv, %d envs/GPU, full loop: %sact -> env step -> remember -> one "
+                            "update of minibatch %d" % ("EmotionSAC" if name == "esac" else name.upper(), n,
+                                                        "emotion transformer -> " if name == "esac" else "", B),
+                "n_env_per_gpu": n, "minibatch_per_gpu": B, "parallelism": "env-sharded x%d, data-parallel update" % world}
+    if name == "replay":
+        return {"workload": "rows R1/R2: replay insert of %d transitions per GPU per step into a %d-row ring (FIFO); sample + gather "
+                            "of B = %d timed beside it" % (n, C, B),
+                "n_env_per_gpu": n, "replay": C, "minibatch_per_gpu": B, "parallelism": "per-rank replay shard x%d" % world}
+    if name == "n1":
+        return {"workload": "configs[0]: ER-DDPG on one MultiConditionWeightEnv (25 kg), train_ddpg loop body (act -> step -> "
+                            "emotion.update -> remember -> learn B=128 -> get_emotion)",
+                "n_env_per_gpu": 1, "minibatch": 128, "parallelism": "single env"}
+    raise KeyError(name)
+
+
+TIMING = {"l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
+          "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks"}
 
 
 class ClockSampler(threading.Thread):
@@ -214,17 +278,15 @@ def wl_sim(args, rank, world, device, timer):
     launches = 1 if (fused or args.sim_mode == "thread") else 2
     peaks = _peaks()
     achieved = ENV_STEP_BYTES * n / (ms_per_step * 1e-3) / 1e9
+    tkey = None
+    if args.actions == "pid" and args.sim_mode != "thread":
+        tkey = "sim_pid_fused" if (fused and n == 4096) else ("sim_pid_two_kernel" if (not fused and n == 65536) else None)
     kname = ("env_sim_warp_kernel<fused epilogue>" if fused else "env_sim_warp_kernel + env_finish_kernel") \
         if args.sim_mode != "thread" else "env_step_kernel<false>"
     out = {
         "metric": "env_steps_per_sec", "value": units / (total_ms * 1e-3), "unit": "env-steps/s", "dtype": "f64",
         "ms_per_step": ms_per_step, "wall_s_timed_region": wall,
-        "config": {"workload": "configs[1]: batched WeightEnv rollout, %d envs/GPU, %s action (sim-kernel throughput), "
-                               "Philox noise" % (n, "PID-effective constant" if args.actions == "pid" else "uniform-random"),
-                   "n_env_per_gpu": n, "actions": args.actions, "sim_mode": args.sim_mode,
-                   "parallelism": "env-sharded x%d, no data-path collective" % world,
-                   "l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
-                   "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks"},
+        "config": workload_config("sim", args, world), "timing": dict(TIMING, sim_mode=args.sim_mode, noise="Philox-4x32-10"),
         "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / units,
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": a_host.numel() * 4,
                 "d2h_bytes_per_step": 13 * n,
@@ -236,18 +298,38 @@ def wl_sim(args, rank, world, device, timer):
         "gpu_launches": launches * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": _traffic("sim", n)[0] if (args.actions == "pid" and args.sim_mode != "thread") else None,
-                     "traffic_source": _traffic("sim", n)[1] if (args.actions == "pid" and args.sim_mode != "thread") else None,
+                     "traffic": _traffic(tkey)[0], "traffic_source": _traffic(tkey)[1],
                      "peak_source": peaks["source"], "kernel": kname,
                      "algorithmic_bytes_per_env_step": ENV_STEP_BYTES,
                      "note": "the simulator is instruction-issue bound (about %d serial ticks of integer/Philox work per "
                              "env-step against 192 B of HBM traffic), not HBM bound: see issue_roofline"
                              % round(ticks_all / units)},
     }
-    ipe = SIM_WARP_INSTR_PER_ENV_STEP.get((args.actions, fused)) if args.sim_mode != "thread" else None
+    ipe = _sim_instr(args.actions, fused) if args.sim_mode != "thread" else None
     if ipe:
         out["_issue"] = (n * args.steps / (total_ms * 1e-3), ipe)
     return out
+
+
+def _dp_check(agent, allreduce, world, device):
+    """After a data-parallel timed region: (1) the peer exchange never timed out waiting for a rank (a timeout would have
+    summed stale buckets), (2) every rank holds bit-identical actor / critic parameters (integer checksums of the raw bits)."""
+    if world == 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    err = allreduce.error() if hasattr(allreduce, "error") else 0
+    L = agent.learner
+    bits = torch.cat([L.actor.flat, L.critic.flat, L.actor_target.flat, L.critic_target.flat]).view(torch.int32).to(torch.int64)
+    chk = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=device)).sum(),
+                       torch.tensor(err, dtype=torch.int64, device=device)])
+    allc = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    errs = [int(c[2]) for c in allc]
+    same = all(bool((c[:2] == allc[0][:2]).all()) for c in allc)
+    if any(errs) or not same:
+        raise SystemExit("data-parallel check FAILED: peer-exchange errors per rank %s, replicas bit-identical: %s" % (errs, same))
+    return {"peer_exchange_errors": errs, "replicas_bit_identical": same, "checksum": int(allc[0][0])}
 
 
 def _make_agent(args, rank, device, n, batch, memory):
@@ -257,7 +339,7 @@ def _make_agent(args, rank, device, n, batch, memory):
     env = E.VecFillEnv(conds, n, kind="multi", max_steps=100, seed=0, device=device, env_id_base=rank * n,
                        sim_mode=args.sim_mode)
     agent = E.VecERDDPG(env, seed=0, batch_size=batch, memory_size=memory, rank=rank,
-                        emotion_precision=args.emotion_precision)
+                        emotion_precision=args.emotion_precision, dropout=args.dropout, update_precision=args.update_precision)
     return env, agent
 
 
@@ -288,34 +370,39 @@ def wl_rollout(args, rank, world, device, timer):
     e2e_ms = timer.run_block(e2e_step, args.steps)
     # the dominant kernel (emotion transformer) timed alone
     tf_ms = _kernel_ms(timer, agent._emotion_forward)
-    peaks = _peaks()
-    achieved = TRANSFORMER_FLOP * n / (tf_ms * 1e-3) / 1e12
     units = n * world * args.steps
     return {
         "metric": "env_steps_per_sec", "value": units / (total_ms * 1e-3), "unit": "env-steps/s",
         "dtype": "f64 simulator, %s transformer, f32 actor" % agent.emotion_precision,
         "ms_per_step": total_ms / args.steps, "wall_s_timed_region": wall,
-        "config": {"workload": "configs[2]: MultiConditionWeightEnv (3 conditions round-robin), %d envs/GPU, EmotionModule "
-                               "transformer -> ER-DDPG actor + OU -> env step -> emotion update, dropout off" % n,
-                   "n_env_per_gpu": n, "sim_mode": args.sim_mode, "parallelism": "env-sharded x%d, no data-path collective" % world,
-                   "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+        "config": workload_config("rollout", args, world),
+        "timing": dict(TIMING, sim_mode=args.sim_mode, dropout=args.dropout,
+                       dropout_note="off = module.eval(); philox = train() mode as the reference ships it (it never calls .eval() on "
+                                    "this path), keep-masks from counter-based generators"),
         "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / units,
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": obs_host.numel() * 4,
                 "d2h_bytes_per_step": n * 13},
-        "gpu_launches": 8 * args.steps,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_tflops_sustained"],
-                     "traffic": _traffic("rollout", n)[0] if agent.emotion_precision == "bf16" else None,
-                     "traffic_source": _traffic("rollout", n)[1] if agent.emotion_precision == "bf16" else None,
-                     "peak_source": peaks["source"] + " (sustained)",
-                     "kernel": "emotion_forward_tc_kernel" if agent.emotion_precision == "bf16" else "emotion_forward_kernel",
-                     "kernel_ms": tf_ms,
-                     "share_of_step": tf_ms / (total_ms / args.steps), "algorithmic_flop_per_env": TRANSFORMER_FLOP,
-                     "executed_flop_per_env": TRANSFORMER_FLOP_EXECUTED,
-                     "note": "achieved = the reference's algorithmic FLOPs / time; the kernel executes 16.81 of the 21.83 MFLOP "
-                             "(in the last layer only the last token's out_proj/FFN feed fc_out; the other 19 rows are skipped), "
-                             "so the tensor pipe itself runs at achieved x %.2f" % (TRANSFORMER_FLOP_EXECUTED / TRANSFORMER_FLOP)},
+        "gpu_launches": agent.launches_per_rollout_step(store=False, replay_reset=False) * args.steps,
+        "roofline": _transformer_roofline(agent, n, tf_ms, total_ms / args.steps),
     }
+
+
+def _transformer_roofline(agent, n, tf_ms, step_ms):
+    """Tensor roofline of the emotion-transformer kernel, timed ALONE (an L2 flush before each of its launches): the peak that
+    applies is the burst bf16 figure of MEASURED_PEAKS.json.  `frac` counts the reference's algorithmic FLOPs; `frac_executed`
+    the FLOPs the kernel really issues (it skips the 19 dead rows of the last layer), i.e. what the tensor pipe does."""
+    peaks = _peaks()
+    achieved = TRANSFORMER_FLOP * n / (tf_ms * 1e-3) / 1e12
+    executed = TRANSFORMER_FLOP_EXECUTED * n / (tf_ms * 1e-3) / 1e12
+    tc = agent.emotion_precision == "bf16"
+    tr, trs = _traffic("emotion_tc_65536") if (tc and n == 65536) else (None, None)
+    return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["bf16_tflops"], "traffic": tr, "traffic_source": trs,
+            "peak_source": peaks["source"] + " (burst: the kernel is timed alone)",
+            "kernel": "emotion_forward_tc_kernel" if tc else "emotion_forward_kernel", "kernel_ms": tf_ms,
+            "share_of_step": tf_ms / step_ms, "algorithmic_flop_per_env": TRANSFORMER_FLOP,
+            "executed_flop_per_env": TRANSFORMER_FLOP_EXECUTED, "achieved_executed": executed,
+            "frac_executed": executed / peaks["bf16_tflops"], "frac_vs_sustained_peak": achieved / peaks["bf16_tflops_sustained"]}
 
 
 def wl_update(args, rank, world, device, timer):
@@ -364,30 +451,31 @@ def wl_update(args, rank, world, device, timer):
     for _ in range(2):
         e2e_step()
     e2e_ms = timer.run_block(e2e_step, args.steps)
+    dp = _dp_check(agent, allreduce, world, device)
     peaks = _peaks()
     ms = total_ms / args.steps
     achieved = UPDATE_FLOP_PER_SAMPLE * B / (ms * 1e-3) / 1e12
     return {
         # weak scaling: every rank pushes its own minibatch of B through the update each step, so the units processed per step
         # are `world` minibatch updates (one synchronous optimiser step on the global batch of world x B)
-        "metric": "er_ddpg_updates_per_sec", "value": world * args.steps / (total_ms * 1e-3), "unit": "updates/s", "dtype": "f32",
+        "metric": "er_ddpg_updates_per_sec", "value": world * args.steps / (total_ms * 1e-3), "unit": "updates/s",
+        "dtype": agent.learner.precision_name(),
         "ms_per_step": ms, "wall_s_timed_region": wall, "samples_per_sec": B * world * args.steps / (total_ms * 1e-3),
         "sync_steps_per_sec": args.steps / (total_ms * 1e-3),
-        "config": {"workload": "configs[3]: ER-DDPG update, minibatch %d per GPU, %d-transition replay, data-parallel x%d "
-                               "(%s); value counts per-GPU minibatch updates, sync_steps_per_sec the optimiser steps on the "
-                               "global batch" % (B, C, world, "no exchange" if world == 1 else
-                                                 ("one-shot NVLink peer-memory gradient exchange fused with the clip-norm partials"
-                                                  if args.exchange == "peer" else "NCCL flat-bucket all-reduce")),
-                   "minibatch_per_gpu": B, "replay": C, "parallelism": "dp%d" % world,
-                   "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+        "config": workload_config("update", args, world),
+        "timing": dict(TIMING, exchange="none" if world == 1 else args.exchange, dropout=args.dropout, precision=args.update_precision,
+                       note="value counts per-GPU minibatch updates; sync_steps_per_sec the optimiser steps on the global batch"),
         "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": B * 80, "d2h_bytes_per_step": 16},
-        # sample + gather + 24 launches of erlfill_ddpg_update (+ 2 x (signal, reduce) - 2 sumsq with the peer exchange)
-        "gpu_launches": (26 if world == 1 else 28) * args.steps,
+        "gpu_launches": (2 + agent.learner.launches_per_update(world > 1)) * args.steps,      # sample + gather + the update
+        "dp_check": dp,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
-                     "peak_source": peaks["source"] + " (sustained)", "kernel": "whole update (sample + gather + U1-U5)",
+                     "peak_source": peaks["source"] + " (sustained: timed inside the whole step)",
+                     "kernel": "whole update (sample + gather + U1-U5)",
                      "algorithmic_flop_per_sample": UPDATE_FLOP_PER_SAMPLE,
-                     "note": "%.2f GFLOP per update: launch/latency bound at this size" % (UPDATE_FLOP_PER_SAMPLE * B / 1e9)},
+                     "floor_note": "%.2f GFLOP and about 5.5 MB per update: 4.3 us at the tensor peak, 0.8 us at the HBM peak; a chain of "
+                                   "about 30 dependent layer passes bounds it by latency (DESIGN.md section 4.5)"
+                                   % (UPDATE_FLOP_PER_SAMPLE * B / 1e9)},
     }
 
 
@@ -426,11 +514,11 @@ def wl_replay(args, rank, world, device, timer):
         mem.gather(idx, out=out)
 
     sg_ms = _kernel_ms(timer, sample_gather, reps=10)
-    big = 1 << 20
+    big = min(C, 4 << 20)      # 4 Mi random rows: 336 MB read + 336 MB written, far beyond the 126 MB L2
     idx_big = torch.randint(0, C, (big,), generator=g).to(device)
     out_big = torch.empty(big, 20, dtype=torch.float32, device=device)
     gb_ms = _kernel_ms(timer, lambda: mem.gather(idx_big, out=out_big), reps=10)
-    nb = min(C, 1 << 20)
+    nb = min(C, 4 << 20)
     bigin = [torch.rand(nb, 2, generator=g).to(device), (torch.rand(nb, 10, generator=g) * 100).to(device), torch.rand(nb, generator=g).to(device),
              torch.rand(nb, 2, generator=g).to(device), (torch.rand(nb, generator=g) < 0.01).to(torch.uint8).to(device),
              torch.rand(nb, 3, generator=g).to(device)]
@@ -456,10 +544,7 @@ def wl_replay(args, rank, world, device, timer):
     return {
         "metric": "replay_insert_transitions_per_sec", "value": n * world * args.steps / (total_ms * 1e-3), "unit": "transitions/s",
         "dtype": "f32", "ms_per_step": ms, "wall_s_timed_region": wall,
-        "config": {"workload": "rows R1/R2: replay insert of %d transitions per GPU per step into a %d-row ring (FIFO); "
-                               "sample + gather of B = %d timed beside it" % (n, C, B),
-                   "n_env_per_gpu": n, "replay": C, "minibatch_per_gpu": B, "parallelism": "per-rank replay shard x%d" % world,
-                   "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+        "config": workload_config("replay", args, world), "timing": dict(TIMING),
         "e2e": {"value": n * world * args.steps / (e2e_ms * 1e-3), "unit": "transitions/s",
                 "h2d_bytes_per_step": sum(h.numel() * h.element_size() for h in host), "d2h_bytes_per_step": B * 80},
         "gpu_launches": 1 * args.steps,
@@ -467,12 +552,13 @@ def wl_replay(args, rank, world, device, timer):
                      "traffic": None, "peak_source": peaks["source"], "kernel": "replay_insert_kernel",
                      "algorithmic_bytes_per_transition": 156},
         "sample_gather": {"batch": B, "ms": sg_ms, "note": "two launches, latency bound at this size"},
-        "insert_1M": {"transitions": nb, "ms": ib_ms, "achieved_gbs": 156 * nb / (ib_ms * 1e-3) / 1e9,
-                      "frac": 156 * nb / (ib_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                      "note": "the same kernel on a batch large enough to amortise launch and ramp"},
-        "gather_1M": {"samples": big, "ms": gb_ms, "achieved_gbs": (8 + 160) * big / (gb_ms * 1e-3) / 1e9,
-                      "frac": (8 + 160) * big / (gb_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                      "note": "random 80 B rows: 96 of every 3 x 32 B sectors fetched are 80 useful bytes"},
+        "insert_big": {"transitions": nb, "ms": ib_ms, "achieved_gbs": 156 * nb / (ib_ms * 1e-3) / 1e9,
+                       "frac": 156 * nb / (ib_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                       "note": "the same kernel on %d transitions: %.0f MB read + %.0f MB written, beyond what the 126 MB L2 can hold "
+                               "back, so the device time is DRAM time" % (nb, 76e-6 * nb, 80e-6 * nb)},
+        "gather_big": {"samples": big, "ms": gb_ms, "achieved_gbs": (8 + 160) * big / (gb_ms * 1e-3) / 1e9,
+                       "frac": (8 + 160) * big / (gb_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                       "note": "random 80 B rows out of a %.0f MB ring" % (80e-6 * C)},
     }
 
 
@@ -507,17 +593,14 @@ def wl_n1(args, rank, world, device, timer):
     return {
         "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "dtype": "f64 simulator, f32 networks",
         "ms_per_step": dt / n_steps[0] * 1e3, "wall_s_timed_region": dt,
-        "config": {"workload": "configs[0]: ER-DDPG on one MultiConditionWeightEnv (25 kg), N = 1 drop-ins, train_ddpg loop body "
-                               "(act -> step -> emotion.update -> remember -> learn B=128 -> get_emotion), %d env-steps timed by "
-                               "wall clock (host-driven loop: every call returns numpy like the reference)" % n_steps[0],
-                   "n_env_per_gpu": 1, "minibatch": 128, "parallelism": "single env", "l2": "not flushed (host-paced launches)",
-                   "timing": "wall clock around the loop, device synchronised on both sides"},
+        "config": workload_config("n1", args, world),
+        "timing": {"l2": "not flushed (host-paced launches)", "timing": "wall clock around the loop, device synchronised on both sides; "
+                   "%d env-steps timed (host-driven loop: every call returns numpy like the reference)" % n_steps[0]},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * (2 + 10 + 19), "d2h_bytes_per_step": 4 * (10 + 2 + 3 + 3 + 2)},
         "gpu_launches": None,
         "roofline": {"bound": "hbm", "achieved": ENV_STEP_BYTES * v / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": ENV_STEP_BYTES * v / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
                      "kernel": "whole N = 1 step", "note": "latency bound: about 40 dependent launches and 8 host syncs per step"},
-        "reference_cpu": {"value": 27.0, "unit": "env-steps/s", "source": "SURVEY.md section 6: the reference's train_ddpg body, 8 vCPU, survey-measured"},
     }
 
 
@@ -558,28 +641,20 @@ def wl_erddpg(args, rank, world, device, timer):
         e2e_step()
     e2e_ms = timer.run_block(e2e_step, args.steps)
     tf_ms = _kernel_ms(timer, agent._emotion_forward)
-    peaks = _peaks()
-    achieved = TRANSFORMER_FLOP * n / (tf_ms * 1e-3) / 1e12
+    dp = _dp_check(agent, allreduce, world, device)
     units = n * world * args.steps
     return {
         "metric": "env_steps_per_sec", "value": units / (total_ms * 1e-3), "unit": "env-steps/s",
-        "dtype": "f64 simulator, %s transformer, f32 actor, f32 (3xTF32) update" % agent.emotion_precision,
+        "dtype": "f64 simulator, %s transformer, f32 actor, %s update" % (agent.emotion_precision, agent.learner.precision_name()),
         "ms_per_step": total_ms / args.steps, "wall_s_timed_region": wall, "updates_per_sec": world * args.steps / (total_ms * 1e-3),
-        "config": {"workload": "ER-DDPG full loop on MultiConditionWeightEnv (3 conditions round-robin), %d envs/GPU: transformer -> actor "
-                               "+ OU -> env step -> replay-branch reset -> emotion update -> replay insert -> one update of minibatch %d, "
-                               "dropout off" % (n, B),
-                   "n_env_per_gpu": n, "minibatch_per_gpu": B,
-                   "parallelism": "env-sharded x%d, data-parallel update (%s)" % (world, "none" if world == 1 else args.exchange),
-                   "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+        "config": workload_config("erddpg", args, world),
+        "timing": dict(TIMING, exchange="none" if world == 1 else args.exchange, dropout=args.dropout, precision=args.update_precision),
+        "dp_check": dp,
         "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / units,
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": obs_host.numel() * 4,
                 "d2h_bytes_per_step": n * 13 + 16},
-        "gpu_launches": (10 + 26) * args.steps,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": _traffic("rollout", n)[0],
-                     "traffic_source": _traffic("rollout", n)[1], "peak_source": peaks["source"] + " (sustained)",
-                     "kernel": "emotion_forward_tc_kernel", "kernel_ms": tf_ms, "share_of_step": tf_ms / (total_ms / args.steps),
-                     "algorithmic_flop_per_env": TRANSFORMER_FLOP, "executed_flop_per_env": TRANSFORMER_FLOP_EXECUTED},
+        "gpu_launches": (agent.launches_per_rollout_step() + 2 + agent.learner.launches_per_update(world > 1)) * args.steps,
+        "roofline": _transformer_roofline(agent, n, tf_ms, total_ms / args.steps),
     }
 
 
@@ -638,12 +713,7 @@ def wl_loop(args, rank, world, device, timer):
         "metric": "env_steps_per_sec", "value": units / (total_ms * 1e-3), "unit": "env-steps/s",
         "dtype": "f64 simulator, f32 (3xTF32 tensor-core GEMM) networks", "ms_per_step": total_ms / args.steps, "wall_s_timed_region": wall,
         "updates_per_sec": args.steps / (total_ms * 1e-3),
-        "config": {"workload": "configs[4]: %s on MultiConditionWeightEnv, %d envs/GPU, full loop: %sact -> env step -> remember -> "
-                               "one update of minibatch %d" % ("EmotionSAC" if kind == "esac" else kind.upper(), n,
-                                                               "emotion transformer -> " if kind == "esac" else "", B),
-                   "n_env_per_gpu": n, "minibatch_per_gpu": B,
-                   "parallelism": "env-sharded x%d, data-parallel update (flat-bucket gradient all-reduce)" % world,
-                   "l2": "flushed between timed steps", "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+        "config": workload_config(kind, args, world), "timing": dict(TIMING, exchange="flat-bucket gradient all-reduce (NCCL)"),
         "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / units,
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": obs_host.numel() * 4,
                 "d2h_bytes_per_step": n * 13 + 12},
@@ -657,13 +727,18 @@ def wl_loop(args, rank, world, device, timer):
 
 
 def run_ours(args):
-    import torch
-    import torch.distributed as dist
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
+    head = "rollout" if args.workload == "all" else args.workload
+    # CPU leg first (N = 1 only), in a child process, BEFORE this process touches CUDA or joins a process group: no GPU waits on it
+    cpu = None
+    if world == 1 and args.cpu_budget > 0:
+        cpu = cpu_baseline(args, head)
+    import torch
+    import torch.distributed as dist
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
@@ -675,21 +750,19 @@ def run_ours(args):
     sampler.start()
     wl = {"sim": wl_sim, "rollout": wl_rollout, "update": wl_update, "td3": wl_loop, "sac": wl_loop, "esac": wl_loop,
           "replay": wl_replay, "n1": wl_n1, "erddpg": wl_erddpg}
-    head = "sim" if args.workload == "all" else args.workload
-    if args.workload == "all":
-        args.n_env = args.n_env or 4096
     out = wl[head](args, rank, world, device, timer)
     clocks = sampler.stop()
     others = []
     if args.workload == "all":
-        # the two other metrics of BASELINE.json on their own configs, compact (same timing rules)
+        # the other metrics of BASELINE.json on their own configs, compact (same timing rules)
         import copy
-        for name, n_env, steps in (("rollout", 65536, 10), ("update", 256, 20)):
+        for name, n_env, steps in (("sim", 4096, 20), ("update", 256, 20)):
             a2 = copy.copy(args)
             a2.n_env, a2.steps = n_env, steps
             o = wl[name](a2, rank, world, device, timer)
-            others.append({k: o[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "e2e", "gpu_launches", "roofline")}
-                          | {"workload": o["config"]["workload"], "steps": steps})
+            o.pop("_issue", None)
+            others.append({k: o[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "e2e", "gpu_launches", "roofline", "config")
+                           if k in o} | {"steps": steps})
     if rank == 0:
         issue = out.pop("_issue", None)
         line = {"metric": out.pop("metric"), "value": out.pop("value"), "unit": out.pop("unit"), "n_gpus": world,
@@ -699,12 +772,13 @@ def run_ours(args):
         line["clocks"] = clocks
         if issue:
             mhz = clocks.get("sm_mhz") or 1965.0
-            ceiling = 148 * 4 * mhz * 1e6 / issue[1]
+            ceiling = 148 * 4 * mhz * 1e6 / issue[1][0]
             line["issue_roofline"] = {"achieved_env_steps_per_s_per_gpu": issue[0], "ceiling": ceiling, "frac": issue[0] / ceiling,
-                                      "warp_instr_per_env_step": issue[1], "sm_mhz_used": mhz,
+                                      "warp_instr_per_env_step": issue[1][0], "warp_instr_source": issue[1][2],
+                                      "warp_instr_stale": issue[1][1], "sm_mhz_used": mhz,
                                       "model": "148 SMs x 4 schedulers x 1 warp-instruction/clk / measured warp-instructions per env-step"}
-        if head == "sim":
-            line["cpu_baseline"] = cpu_baseline_sim(args, budget_s=args.cpu_budget)
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
         if others:
             line["other_workloads"] = others
         print(json.dumps(line), flush=True)
@@ -718,6 +792,33 @@ def run_ours(args):
 # ------------------------------------------------------------------------------------------------
 # CPU legs (the only places bench.py may execute oracle/)
 # ------------------------------------------------------------------------------------------------
+def cpu_baseline(args, head):
+    """The reference arm of this very file on a bounded sample (about 10-30 s), run as a child process so that the forked
+    per-core workers never see a CUDA context; returns the `cpu_baseline` object of the JSON line."""
+    import subprocess
+    steps, warm = 4, 1
+    slice_s = max(0.5, min(4.0, args.cpu_budget / (steps + warm)))
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", head, "--steps", str(steps), "--warmup", str(warm),
+           "--ref-slice", "%.3f" % slice_s, "--n-env", str(args.n_env), "--batch", str(args.batch), "--replay", str(args.replay),
+           "--actions", args.actions]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        d = json.loads(lines[-1])
+    except Exception as e:      # the line still prints; the failure is visible
+        return {"value": None, "unit": None, "cores": None, "kind": "reference", "sample": "FAILED: %r" % (e,)}
+    if "unavailable" in d:
+        return {"value": None, "unit": None, "cores": None, "kind": "reference", "sample": "unavailable: " + d["unavailable"]}
+    cb = d["cpu_baseline"]
+    for k in ("ticks_per_sec", "c_port"):
+        if k in d:
+            cb[k] = d[k]
+    return cb
+
+
 def _cpu_sim_once(args, n_env, n_threads, steps):
     import numpy as np
     from oracle import oracle_lib as O
@@ -741,62 +842,84 @@ def _cpu_sim_once(args, n_env, n_threads, steps):
     return n_env * steps / dt, ticks / dt, dt
 
 
-def cpu_baseline_sim(args, budget_s=12.0):
-    """C port of the reference path (oracle/erlfill_oracle.c), all host cores, bounded sample."""
-    import random
-    from oracle import oracle_lib as O, py_port
+def c_port_sim(args, budget_s=4.0):
+    """Extra, beside the reference figure: the C port of the simulator path (oracle/erlfill_oracle.c), all host cores."""
+    from oracle import oracle_lib as O
     cores = O.lib().orc_max_threads()
     rate, _, _ = _cpu_sim_once(args, 64 * cores, cores, 1)          # calibrate
     n_env = max(64 * cores, int(rate * budget_s / 4) // 64 * 64)
     v, tps, dt = _cpu_sim_once(args, n_env, cores, 4)
-    # the reference's own language: pure-Python restatement, one core, ~2 s
-    p = dict(zip(["target_weight", "fast_weight", "medium_weight", "slow_weight", "fast_delay", "medium_delay",
-                  "slow_delay", "fast_opening", "medium_opening", "slow_opening", "unload_delay"],
-                 [25000, 18000, 0, 24900, 100, 100, 100, 35, 3, 3, 300]))
-    rng = random.Random(0)
-    t0, runs = time.perf_counter(), 0
-    while time.perf_counter() - t0 < min(2.0, budget_s):
-        py_port.simulate_run(p, rng)
-        runs += 1
-    py_rate = runs / (time.perf_counter() - t0)
-    return {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": "%d envs x 4 steps of the same workload, C oracle (pthreads over envs), %.1f s" % (n_env, dt),
-            "ticks_per_sec": tps,
-            "python_port_one_core": {"value": py_rate, "unit": "env-steps/s", "cores": 1,
-                                     "note": "pure-Python restatement of simulate_run (the reference is a CPython loop)"}}
+    return {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "ticks_per_sec": tps,
+            "sample": "%d envs x 4 steps, C restatement of the simulator (pthreads over envs), %.1f s" % (n_env, dt)}
+
+
+REF_ROWS = {"sim": "C1", "rollout": "C2", "update": "C3", "n1": "C4", "erddpg": "C4", "td3": "C4", "sac": "C4", "esac": "C4"}
+
+
+def _ref_measure(args, name):
+    """One reference measurement -> (value, unit, cores, sample text, extras).  BASELINE.md section 3."""
+    from oracle import ref_bench as R
+    T = args.ref_slice
+    if name in ("sim", "rollout"):
+        r = R.run_per_core(name, args.steps, args.warmup, T, actions=args.actions)
+        what = ("controller.reset(); load_params(action); simulate_run()" if name == "sim" else
+                "agent.act(state) -> env.step(action) -> agent.emotion.update(reward, next_state - state), networks in train() mode as shipped")
+        sample = ("row %s: the unmodified reference's `%s` on %d single-env worker processes (one per host core, torch single-threaded); "
+                  "a step = a %.2f s slice on every worker, %d env-steps in %d timed slices"
+                  % (REF_ROWS[name], what, r["cores"], T, r["units"], args.steps))
+        extras = {"ticks_per_sec": r["ticks_per_sec"], "mean_ticks_per_env_step": r["mean_ticks"]} if "ticks_per_sec" in r else {}
+        return r["value"], "env-steps/s", r["cores"], sample, extras, T * 1e3
+    if name == "update":
+        r = R.run_update(args.batch, args.replay, args.steps, args.warmup)
+        sample = ("row C3: the unmodified reference's DDPGAgent.learn() with batch_size = %d on a %d-transition PrioritizedReplayBuffer, one "
+                  "process, %d torch threads; a step = one learn() call, %d timed" % (args.batch, args.replay, r["cores"], args.steps))
+        return r["value"], "updates/s", r["cores"], sample, {}, r["seconds"] / args.steps * 1e3
+    r = R.run_loop(name, max(args.steps, 20), args.warmup)
+    sample = ("row C4: per-step body of the unmodified reference's train loop (%s) on ONE env with its own minibatch of 128, one process, "
+              "%d torch threads; a step = one env-step + one update, %d timed (the batched loop has no single-process analogue "
+              "in the reference)" % ({"n1": "train_ddpg", "erddpg": "train_ddpg", "td3": "train_td3", "sac": "train_sac",
+                                      "esac": "train_erl_fill"}[name], r["cores"], r["units"]))
+    return r["value"], "env-steps/s", r["cores"], sample, {}, r["seconds"] / r["units"] * 1e3
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
-    if args.workload not in ("sim", "all"):
-        print(json.dumps({"impl": "reference", "unavailable": "the CPU port is timed on the sim workload (configs[1]) only"}),
-              flush=True)
+    head = "rollout" if args.workload == "all" else args.workload
+    if head == "replay":
+        print(json.dumps({"impl": "reference", "unavailable": "rows R1/R2 have no separate reference entry point (list append / np.random.choice "
+                                                              "inside remember() and learn()): timed as part of --workload update / n1"}), flush=True)
         return
-    from oracle import oracle_lib as O
-    cores = O.lib().orc_max_threads()
-    n = args.n_env
-    # bounded sample: every "step" is one pass of the C port over n_ref envs of the same workload
-    rate, _, _ = _cpu_sim_once(args, 64 * cores, cores, 1)
-    per_step_budget = max(0.5, min(10.0, 120.0 / max(1, args.steps + args.warmup)))
-    n_ref = int(min(n, max(64 * cores, rate * per_step_budget)))
-    for _ in range(args.warmup):
-        _cpu_sim_once(args, n_ref, cores, 1)
-    t0 = time.perf_counter()
-    v, tps, dt = _cpu_sim_once(args, n_ref, cores, args.steps)
-    total = time.perf_counter() - t0
-    sample = "%d of %d envs per step (bounded sample), C port of the reference path, %d threads" % (n_ref, n, cores)
-    out = {"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "configs[1]: batched WeightEnv rollout, %d envs/GPU, %s action (sim-kernel "
-                                  "throughput)" % (n, "PID-effective constant" if args.actions == "pid" else "uniform-random"),
-                      "n_env_per_gpu": n, "actions": args.actions},
-           "ticks_per_sec": tps,
-           "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
-           "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0}
+    from oracle import ref_bench as R
+    if not R.available():
+        print(json.dumps({"impl": "reference", "unavailable": "no reference tree: neither /root/reference nor baseline/_ref/erlfill_reference "
+                                                              "(run `python oracle/vendor_ref.py` where /root/reference exists)"}), flush=True)
+        return
+    v, unit, cores, sample, extras, ms = _ref_measure(args, head)
+    metric = "er_ddpg_updates_per_sec" if head == "update" else "env_steps_per_sec"
+    out = {"impl": "reference", "metric": metric, "value": v, "unit": unit,
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 simulator, f32 networks (torch CPU)",
+           "data": "synthetic", "config": workload_config(head, args, max(world, args.gpus)),
+           "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
+           "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "host_cpu_count": os.cpu_count()}
+    out.update(extras)
+    if head == "sim":
+        out["c_port"] = c_port_sim(args)
+    if args.workload == "all":
+        import copy
+        others = []
+        for name, n_env, steps in (("sim", 4096, 4), ("update", 256, 5)):
+            a2 = copy.copy(args)
+            a2.n_env, a2.steps, a2.warmup = n_env, steps, 1
+            v2, u2, c2, s2, e2, ms2 = _ref_measure(a2, name)
+            others.append({"metric": "er_ddpg_updates_per_sec" if name == "update" else "env_steps_per_sec", "value": v2, "unit": u2,
+                           "ms_per_step": ms2, "config": workload_config(name, a2, max(world, args.gpus)),
+                           "cpu_baseline": {"value": v2, "unit": u2, "cores": c2, "kind": "reference", "sample": s2}, "steps": steps} | e2)
+        out["other_workloads"] = others
     print(json.dumps(out), flush=True)
 
 
@@ -807,21 +930,29 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="all", choices=["all", "sim", "rollout", "update", "td3", "sac", "esac", "replay", "n1", "erddpg"],
-                    help="all = the sim headline line plus compact rollout and update results under other_workloads")
+                    help="all = the rollout headline line (configs[2]) plus compact sim and update results under other_workloads")
     ap.add_argument("--n-env", type=int, default=None)
     ap.add_argument("--actions", default="pid", choices=["pid", "random"])
     ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--replay", type=int, default=1000000)
-    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--replay", type=int, default=None)
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of reference CPU work for the cpu_baseline leg (0: skip)")
+    ap.add_argument("--ref-slice", type=float, default=None, help="reference arm: seconds per step slice of the per-core workloads")
     ap.add_argument("--sim-mode", default="auto", choices=["auto", "warp", "thread"])
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="gradient exchange of the data-parallel update at N > 1 (csrc/peer.cu or ncclAllReduce)")
     ap.add_argument("--emotion-precision", default="bf16", choices=["bf16", "fp32"],
                     help="EmotionTransformer kernel of the rollout: tcgen05 bf16 (default) or the exact fp32 SIMT twin")
+    ap.add_argument("--dropout", default="off", choices=["off", "philox"],
+                    help="off = module.eval(); philox = train() mode like the reference, counter-based keep-masks")
+    ap.add_argument("--update-precision", default="fast", choices=["fast", "exact"],
+                    help="ER-DDPG update GEMMs: fast = tcgen05 bf16 operands / fp32 accumulate (stated tolerance); exact = 3xTF32 (1e-4 parity)")
     args = ap.parse_args()
     if args.n_env is None:
-        args.n_env = {"all": 4096, "sim": 4096, "rollout": 65536, "update": 256, "td3": 131072, "sac": 131072, "esac": 65536,
-                      "replay": 131072, "n1": 1, "erddpg": 65536}[args.workload]
+        args.n_env = DEFAULT_N_ENV[args.workload]
+    if args.replay is None:
+        args.replay = DEFAULT_REPLAY.get(args.workload, 1000000)
+    if args.ref_slice is None:      # the whole reference run stays within about two minutes
+        args.ref_slice = max(0.5, min(3.0, 100.0 / max(1, args.steps + args.warmup)))
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

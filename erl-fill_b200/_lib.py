@@ -54,6 +54,11 @@ class OU(C.Structure):
                 ("step_idx", C.c_uint32)]
 
 
+class CondScaling(C.Structure):
+    _fields_ = [("d_scale", C.c_void_p), ("d_offset", C.c_void_p), ("d_cond_id", C.c_void_p), ("n_cond", C.c_int32),
+                ("row_id_base", C.c_uint32)]
+
+
 class EmotionState(C.Structure):
     _fields_ = [("d_current", C.c_void_p), ("d_history", C.c_void_p), ("d_hist_len", C.c_void_p),
                 ("d_hist_head", C.c_void_p)]
@@ -76,7 +81,7 @@ class DDPGNets(C.Structure):
 
 class DDPGHyper(C.Structure):
     _fields_ = [("batch", C.c_int32), ("adam_step", C.c_int32), ("gamma", C.c_float), ("tau", C.c_float),
-                ("max_grad_norm", C.c_float), ("_pad", C.c_float), ("critic_lr", C.c_double),
+                ("max_grad_norm", C.c_float), ("n_cond", C.c_int32), ("critic_lr", C.c_double),
                 ("actor_lr", C.c_double), ("lr_decay", C.c_double)]
 
 
@@ -89,7 +94,7 @@ class TD3Hyper(C.Structure):
     _fields_ = [("batch", C.c_int32), ("critic_step", C.c_int32), ("actor_step", C.c_int32), ("update_actor", C.c_int32),
                 ("gamma", C.c_float), ("tau", C.c_float), ("policy_noise", C.c_float), ("noise_clip", C.c_float),
                 ("critic_lr", C.c_double), ("actor_lr", C.c_double), ("seed", C.c_uint64), ("update_idx", C.c_uint32),
-                ("_pad", C.c_uint32)]
+                ("rank", C.c_uint32)]
 
 
 class SACNets(C.Structure):
@@ -99,7 +104,7 @@ class SACNets(C.Structure):
 class SACHyper(C.Structure):
     _fields_ = [("batch", C.c_int32), ("adam_step", C.c_int32), ("gamma", C.c_float), ("tau", C.c_float),
                 ("alpha", C.c_float), ("_pad", C.c_float), ("lr", C.c_double), ("seed", C.c_uint64),
-                ("update_idx", C.c_uint32), ("_pad2", C.c_uint32)]
+                ("update_idx", C.c_uint32), ("rank", C.c_uint32)]
 
 
 TD3_ACTOR_PARAMS, TD3_CRITIC_PARAMS, SAC_POLICY_PARAMS, SAC_Q_PARAMS = 69130, 138754, 71700, 138754
@@ -121,11 +126,11 @@ EXPORTS = [
     "erlfill_version", "erlfill_last_cuda_error", "erlfill_last_cuda_error_string", "erlfill_device_ok",
     "erlfill_env_reset", "erlfill_env_reset_from_replay", "erlfill_env_step", "erlfill_env_step_counted", "erlfill_env_step_set_mode",
     "erlfill_env_step_fused_max_envs",
-    "erlfill_actor_forward", "erlfill_emotion_update", "erlfill_episode_end", "erlfill_emotion_forward",
+    "erlfill_actor_forward", "erlfill_actor_forward_cond", "erlfill_replay_insert_cond", "erlfill_emotion_update", "erlfill_episode_end", "erlfill_emotion_forward",
     "erlfill_emotion_tc_image_bytes", "erlfill_emotion_tc_pack", "erlfill_emotion_forward_tc",
     "erlfill_replay_insert", "erlfill_replay_sample", "erlfill_replay_gather",
     "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_set_step", "erlfill_ddpg_update",
-    "erlfill_ddpg_exchange_buffers", "erlfill_peer_ctrl_bytes", "erlfill_peer_alloc", "erlfill_peer_open", "erlfill_peer_close",
+    "erlfill_ddpg_exchange_buffers", "erlfill_ddpg_update_launches", "erlfill_ddpg_peer_launches", "erlfill_peer_ctrl_bytes", "erlfill_peer_alloc", "erlfill_peer_open", "erlfill_peer_close",
     "erlfill_peer_free", "erlfill_ddpg_peer_allreduce", "erlfill_peer_error",
     "erlfill_t1_workspace_bytes", "erlfill_t1_act_workspace_bytes", "erlfill_t1_grad_buckets", "erlfill_td3_act",
     "erlfill_td3_update", "erlfill_sac_act", "erlfill_sac_update",

@@ -22,7 +22,7 @@ from . import ddpg, init, nets
 
 class VecERDDPG:
     def __init__(self, env, seed=0, batch_size=128, memory_size=100000, dropout="off", state_dicts=None,
-                 emotion_precision="fp32", rank=0, world_size=1):
+                 emotion_precision="fp32", rank=0, world_size=1, update_precision="exact"):
         self.env = env
         self.device = env.device
         self.n = env.n_env
@@ -32,7 +32,7 @@ class VecERDDPG:
         if state_dicts is None:
             state_dicts = init.er_ddpg_state_dicts(bounds, seed=seed)
         actor_sd, critic_sd, trans_sd = state_dicts
-        self.learner = ddpg.DDPGLearner(actor_sd, critic_sd, device=self.device, batch_size=batch_size)
+        self.learner = ddpg.DDPGLearner(actor_sd, critic_sd, device=self.device, batch_size=batch_size, precision=update_precision)
         self.transformer = nets.TransformerParams(trans_sd, device=self.device)
         self.emotion_precision = emotion_precision
         self.memory = ddpg.ReplayBuffer(memory_size, device=self.device)
@@ -55,6 +55,16 @@ class VecERDDPG:
         self.t = 0
         self.updates = 0
         self._actor_struct = self.learner.actor_struct()
+        # one agent per condition in the reference (experiment_runner.py:504-510): each env's action is scaled with the
+        # scale_params / offset_params of ITS condition's bounds (ddpg_agent.py:56-71)
+        self._cond = None
+        if len(env.conditions) > 1:
+            sc = [[(c["bounds"][k][1] - c["bounds"][k][0]) / 2.0 for k in L.ACTION_ORDER] for c in env.conditions]
+            of = [[(c["bounds"][k][1] + c["bounds"][k][0]) / 2.0 for k in L.ACTION_ORDER] for c in env.conditions]
+            self.learner.set_condition_scaling(torch.tensor(sc, dtype=torch.float32), torch.tensor(of, dtype=torch.float32))
+            self._cond_id = env._d_cond_id          # explicit table or None (round-robin on the global env id, like the env)
+            self._cond = L.CondScaling(L.ptr(self.learner.scale_tab), L.ptr(self.learner.offset_tab), L.ptr(self._cond_id),
+                                       len(env.conditions), env.env_id_base)
         self.reset()
 
     # -- pieces -------------------------------------------------------------------------------
@@ -75,11 +85,12 @@ class VecERDDPG:
         ou = L.OU(L.ptr(self.ou_state), L.ptr(self.sigma), None, L.ptr(self.action), self.seed, self.env.env_id_base,
                   self.t & 0xFFFFFFFF)
         with torch.cuda.device(self.device):
-            L.check(L.lib().erlfill_actor_forward(C.byref(w), C.c_int(self.n), L.ptr(self.env.obs), L.ptr(self.emotion),
-                                                  C.c_int(0), C.c_int(self.dropout), C.c_uint64(self.seed),
-                                                  C.c_uint32(self.t & 0xFFFFFFFF), C.c_uint32(self.env.env_id_base), None, None,
-                                                  L.ptr(self.scaled), None, C.byref(ou) if add_noise else None, L.stream_ptr()),
-                    "erlfill_actor_forward")
+            L.check(L.lib().erlfill_actor_forward_cond(C.byref(w), C.c_int(self.n), L.ptr(self.env.obs), L.ptr(self.emotion),
+                                                       C.c_int(0), C.c_int(self.dropout), C.c_uint64(self.seed),
+                                                       C.c_uint32(self.t & 0xFFFFFFFF), C.c_uint32(self.env.env_id_base), None, None,
+                                                       L.ptr(self.scaled), None, C.byref(ou) if add_noise else None,
+                                                       C.byref(self._cond) if self._cond is not None else None, L.stream_ptr()),
+                    "erlfill_actor_forward_cond")
         return self.action if add_noise else self.scaled
 
     def rollout_step(self, store=True, replay_reset=True):
@@ -95,9 +106,20 @@ class VecERDDPG:
         self.t += 1
         self._emotion_forward()
         if store:
-            self.memory.insert(self.state, a, reward, next_state, done, self.emotion, self.learner.scale, self.learner.offset)
+            if self._cond is not None:
+                self.memory.insert(self.state, a, reward, next_state, done, self.emotion, cond=self._cond)
+            else:
+                self.memory.insert(self.state, a, reward, next_state, done, self.emotion, self.learner.scale, self.learner.offset)
         nets.episode_end(done, self.ou_state, self.sigma, self.sigma64, episode_count=self.episodes)
         return next_state, reward, done
+
+    def launches_per_rollout_step(self, store=True, replay_reset=True):
+        """Kernels of liberlfill.so one rollout_step launches: actor(+OU), simulator (one fused kernel for a resident batch, else
+        simulator + finish), [replay-branch reset], emotion update, transformer, [replay insert], episode end."""
+        with torch.cuda.device(self.device):
+            fused = self.env.sim_mode != L.SIM_THREAD_PER_ENV and self.n <= L.lib().erlfill_env_step_fused_max_envs()
+        sim = 1 if (fused or self.env.sim_mode == L.SIM_THREAD_PER_ENV) else 2
+        return 1 + sim + (1 if (replay_reset and len(self.memory) >= 10) else 0) + 1 + 1 + (1 if store else 0) + 1
 
     def rollout_eval_step(self):
         """One evaluation step (experiment_runner.py:545-556: `act(state, add_noise=False)` -> `env.step`).  The test
@@ -116,6 +138,14 @@ class VecERDDPG:
         return rep
 
     def sync_counters(self):
-        """Host copy of the episode count (one D2H sync): train_step = 1 + episodes // N (:455, :729)."""
-        self.train_step = 1 + int(self.episodes.item()) // self.n
+        """Host copy of the episode count (one D2H sync): train_step = 1 + episodes // N (:455, :729).  Data-parallel: episodes
+        and env counts are summed over the ranks first, so every replica decays its learning rate identically (ranks finish
+        episodes at different times; a rank-local count would let the replicas drift apart)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            t = torch.stack([self.episodes.reshape(()).to(torch.int64), torch.tensor(self.n, dtype=torch.int64, device=self.device)])
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            self.train_step = 1 + int(t[0].item()) // int(t[1].item())
+        else:
+            self.train_step = 1 + int(self.episodes.item()) // self.n
         return self.train_step

@@ -31,6 +31,7 @@ struct ActorArgs {
     int n_rows, emotion_broadcast, dropout_mode, has_ou;
     uint32_t call_idx, row_id_base;
     uint64_t seed;
+    erlfill_cond_scaling cs;       // n_cond > 0: per-condition scale / offset rows instead of w.scale / w.offset
 };
 
 // shared-memory plan (floats)
@@ -222,7 +223,12 @@ __global__ void __launch_bounds__(kThreads, 1) actor_forward_kernel(const ActorA
             const float om = 1.0f - fabsf(base);
             const float sign_flip = base > 0.f ? -1.0f : (base < 0.f ? 1.0f : 0.0f);
             const float raw_action = base + alpha * raw_effect * sign_flip * (om * om);
-            const float scale = sm[oSC + c], offset = sm[oSC + 16 + c];
+            float scale = sm[oSC + c], offset = sm[oSC + 16 + c];
+            if (a.cs.n_cond > 0) {     // the env's own condition scales its action (one agent per condition in the reference)
+                const int cid = a.cs.d_cond_id ? a.cs.d_cond_id[row] : (int)((a.cs.row_id_base + (uint32_t)row) % (uint32_t)a.cs.n_cond);
+                scale = __ldg(a.cs.d_scale + cid * 10 + c);
+                offset = __ldg(a.cs.d_offset + cid * 10 + c);
+            }
             const float scaled = raw_action * scale + offset;
             a.d_scaled[(size_t)row * 10 + c] = scaled;
             if (a.d_base) a.d_base[(size_t)row * 10 + c] = base;
@@ -326,7 +332,16 @@ int erlfill_actor_forward(const erlfill_actor_weights *w, int n_rows, const floa
                           int emotion_broadcast, int dropout_mode, uint64_t seed, uint32_t call_idx,
                           uint32_t row_id_base, const uint8_t *d_mask1, const uint8_t *d_mask2, float *d_scaled_action,
                           float *d_base_action, const erlfill_ou *ou, void *stream) {
+    return erlfill_actor_forward_cond(w, n_rows, d_state, d_emotion, emotion_broadcast, dropout_mode, seed, call_idx, row_id_base,
+                                      d_mask1, d_mask2, d_scaled_action, d_base_action, ou, nullptr, stream);
+}
+
+int erlfill_actor_forward_cond(const erlfill_actor_weights *w, int n_rows, const float *d_state, const float *d_emotion,
+                               int emotion_broadcast, int dropout_mode, uint64_t seed, uint32_t call_idx,
+                               uint32_t row_id_base, const uint8_t *d_mask1, const uint8_t *d_mask2, float *d_scaled_action,
+                               float *d_base_action, const erlfill_ou *ou, const erlfill_cond_scaling *cs, void *stream) {
     if (!w || n_rows <= 0 || !d_state || !d_emotion || !d_scaled_action) return ERLFILL_ERR_ARG;
+    if (cs && (cs->n_cond <= 0 || !cs->d_scale || !cs->d_offset)) return ERLFILL_ERR_ARG;
     if (!w->w_in || !w->b_in || !w->w_h2 || !w->b_h2 || !w->w_h5 || !w->b_h5 || !w->w_h7 || !w->b_h7 ||
         !w->emotion_weights || !w->scale || !w->offset)
         return ERLFILL_ERR_ARG;
@@ -340,6 +355,7 @@ int erlfill_actor_forward(const erlfill_actor_weights *w, int n_rows, const floa
     a.d_scaled = d_scaled_action; a.d_base = d_base_action;
     a.n_rows = n_rows; a.emotion_broadcast = emotion_broadcast; a.dropout_mode = dropout_mode;
     a.call_idx = call_idx; a.row_id_base = row_id_base; a.seed = seed;
+    if (cs) a.cs = *cs; else a.cs = erlfill_cond_scaling{};
     const size_t smem = kSmemFloats * sizeof(float);
     static bool attr_set[64] = {};
     int dev = 0;

@@ -364,7 +364,7 @@ int erlfill_esac_update(const erlfill_esac_nets *n, const erlfill_esac_hyper *h,
     if (phases & ERLFILL_PHASE_CRITIC_GRAD) {
         // target: a' ~ pi(s', e), y from the twin target critics (the reference conditions s' on the STORED emotion e, :385-387)
         policy_forward(st, B, n->policy, s2, ld, e, ld, w.pb, false);
-        sample_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, n->policy, e, ld, w.pb.ml, d_eps_next, h->seed, 0u, h->update_idx, 0u, 0, w.a16, w.logp2, nullptr,
+        sample_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, n->policy, e, ld, w.pb.ml, d_eps_next, h->seed, h->rank << 20, h->update_idx, 4u, 0, w.a16, w.logp2, nullptr,
                                                       nullptr, nullptr, nullptr, nullptr, 0);
         q_forward(st, B, n->q_target, s2, ld, w.a16, 16, e, ld, w.qa, w.q1t, false);
         q_forward(st, B, n->q_target + NQ, s2, ld, w.a16, 16, e, ld, w.qb, w.q2t, false);
@@ -379,7 +379,7 @@ int erlfill_esac_update(const erlfill_esac_nets *n, const erlfill_esac_hyper *h,
     if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
         const float *P = n->policy;
         policy_forward(st, B, P, s, ld, e, ld, w.pb, true);
-        sample_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, P, e, ld, w.pb.ml, d_eps_new, h->seed, 0u, h->update_idx, 1u, 0, w.a16, w.logp, w.sv, nullptr,
+        sample_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, P, e, ld, w.pb.ml, d_eps_new, h->seed, h->rank << 20, h->update_idx, 5u, 0, w.a16, w.logp, w.sv, nullptr,
                                                       nullptr, nullptr, nullptr, 0);
         q_forward(st, B, n->q, s, ld, w.a16, 16, e, ld, w.qa, w.q1, true);
         policy_loss_kernel<<<1, 1024, 0, st>>>(B, w.logp, w.q1, h->alpha, d_emotion_now, d_emotion_prev, w.scal);

@@ -9,7 +9,11 @@
 // so the exchange replaces ncclAllReduce + scale + sumsq (3 launches, 2 of them collective-latency bound) and every rank
 // adds the same values in the same order: replicas stay bit-identical.  Buckets are only rewritten by the next update's
 // *_GRAD phase, which a rank reaches after the OTHER bucket's exchange — i.e. after every peer has finished reading this one
-// (DESIGN.md section 7).  A peer that never arrives trips a bounded spin (about 2 s): the error flag is set, no hang.
+// (DESIGN.md section 7).  A peer that never arrives trips a bounded spin (ERLFILL_PEER_TIMEOUT_S seconds, default 30): never a
+// hang, and never a silent divergence either — the sticky error flag is set and the reduced bucket and its norm partials are
+// written as NaN, so the APPLY phase poisons the parameters and the update report of THIS rank; callers poll
+// erlfill_peer_error (bench.py and the training loops do after every timed region).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -25,6 +29,7 @@ struct PeerCtrl {                  // one per rank, at the tail of its peer allo
 
 struct PeerArgs {
     int world, rank, which, n, n_norm;
+    long long timeout_cycles;
     const float *bucket[ERLFILL_MAX_PEERS];
     PeerCtrl *ctrl[ERLFILL_MAX_PEERS];
     float *out, *ssq;
@@ -52,11 +57,19 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerArgs a) {
         const uint32_t e = *reinterpret_cast<volatile uint32_t *>(&mine->epoch[a.which]);
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(&mine->flag[a.which][threadIdx.x]) - e) < 0) {
-            if (clock64() - t0 > 4000000000LL) { mine->error = 1u; break; }
+            if (clock64() - t0 > a.timeout_cycles) { atomicExch(&mine->error, 1u); break; }
             __nanosleep(100);
         }
     }
     __syncthreads();
+    // sticky: once a wait timed out the peers' buckets may be stale or half written; nothing computed from them may look valid
+    const bool poisoned = *reinterpret_cast<volatile uint32_t *>(&mine->error) != 0u;
+    if (poisoned) {
+        const float nan = __int_as_float(0x7fc00000);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) a.out[i] = nan;
+        if (threadIdx.x == 0) a.ssq[blockIdx.x] = nan;
+        return;
+    }
     const int per = (a.n_norm + mlp::kSumsqBlocks - 1) / mlp::kSumsqBlocks;      // the slices of mlp::sumsq_kernel
     const int i0 = blockIdx.x * per, i1 = blockIdx.x == mlp::kSumsqBlocks - 1 ? a.n : min(a.n_norm, i0 + per);
     const float inv = 1.0f / (float)a.world;
@@ -129,6 +142,8 @@ int erlfill_peer_error(const erlfill_peer_group *g, int *error_out) {
     return ERLFILL_OK;
 }
 
+int erlfill_ddpg_peer_launches(void) { return 4; }       // 2 x (signal, reduce) per update, minus nothing: the APPLY phases skip their sumsq kernels
+
 int erlfill_ddpg_peer_allreduce(const erlfill_peer_group *g, int batch, int which, void *stream) {
     if (!g || g->world < 1 || g->world > ERLFILL_MAX_PEERS || g->rank < 0 || g->rank >= g->world || (which != 0 && which != 1) ||
         batch < 2)
@@ -150,6 +165,14 @@ int erlfill_ddpg_peer_allreduce(const erlfill_peer_group *g, int batch, int whic
             a.ssq = ssq + which * mlp::kSumsqBlocks;
         }
     }
+    static long long timeout_cycles = 0;
+    if (timeout_cycles == 0) {
+        const char *e = getenv("ERLFILL_PEER_TIMEOUT_S");
+        double sec = e ? atof(e) : 30.0;
+        if (!(sec > 0.0)) sec = 30.0;
+        timeout_cycles = (long long)(sec * 1.9e9);          // clock64 ticks at about the SM clock
+    }
+    a.timeout_cycles = timeout_cycles;
     cudaStream_t st = (cudaStream_t)stream;
     peer_signal_kernel<<<1, 1, 0, st>>>(a);
     peer_reduce_kernel<<<mlp::kSumsqBlocks, 256, 0, st>>>(a);

@@ -16,10 +16,26 @@
 
 namespace erlfill {
 
+// condition of transition i (0 without a table): column 19 of the record, read back by the update for the actor's scaling
+__device__ __forceinline__ int cond_of(const erlfill_cond_scaling &cs, int i) {
+    if (cs.n_cond <= 0) return 0;
+    return cs.d_cond_id ? cs.d_cond_id[i] : (int)((cs.row_id_base + (uint32_t)i) % (uint32_t)cs.n_cond);
+}
+// clip((a - offset) / scale, -1, 1): ddpg_agent.py:373-375
+__device__ __forceinline__ void normalise_action(float (&a)[10], const float *scale, const float *offset) {
+#pragma unroll
+    for (int c = 0; c < 10; ++c) {
+        float v = __fdiv_rn(__fsub_rn(a[c], __ldg(offset + c)), __ldg(scale + c));
+        v = v < -1.f ? -1.f : v;
+        a[c] = v > 1.f ? 1.f : v;
+    }
+}
+
 __global__ void __launch_bounds__(128) replay_insert_kernel(int n, float *d_buf, int64_t capacity, int64_t start, const int64_t *d_pos,
                                                             const float *d_state, const float *d_action, const float *d_reward,
                                                             const float *d_next_state, const uint8_t *d_done, const float *d_emotion,
-                                                            const float *d_scale, const float *d_offset, int normalize) {
+                                                            const float *d_scale, const float *d_offset, int normalize,
+                                                            const erlfill_cond_scaling cs) {
     // One thread per transition: every input byte is fetched exactly once (8-byte loads, rows of a warp are adjacent, so
     // the sectors a load instruction touches are shared by neighbouring lanes and by the next instruction through L1),
     // all 15 loads of a thread are independent and in flight together, and the 80-byte record leaves as five 128-bit
@@ -45,20 +61,14 @@ __global__ void __launch_bounds__(128) replay_insert_kernel(int n, float *d_buf,
         row = start + i;                       // start < capacity and n <= capacity (checked by the host)
         row = row >= capacity ? row - capacity : row;
     }
-    if (normalize) {
-#pragma unroll
-        for (int c = 0; c < 10; ++c) {
-            float v = __fdiv_rn(__fsub_rn(a[c], __ldg(d_offset + c)), __ldg(d_scale + c));
-            v = v < -1.f ? -1.f : v;
-            a[c] = v > 1.f ? 1.f : v;
-        }
-    }
+    const int cid = cond_of(cs, i);
+    if (normalize) normalise_action(a, cs.n_cond > 0 ? cs.d_scale + cid * 10 : d_scale, cs.n_cond > 0 ? cs.d_offset + cid * 10 : d_offset);
     float4 *dst = reinterpret_cast<float4 *>(d_buf + row * ERLFILL_REC);
     dst[0] = make_float4(st.x, st.y, a[0], a[1]);
     dst[1] = make_float4(a[2], a[3], a[4], a[5]);
     dst[2] = make_float4(a[6], a[7], a[8], a[9]);
     dst[3] = make_float4(rw, ns.x, ns.y, dn);
-    dst[4] = make_float4(e0, e1, e2, 0.f);
+    dst[4] = make_float4(e0, e1, e2, (float)cid);
 }
 
 // The ring-order insert (no position table): the records of a CTA are consecutive rows, so they are assembled in shared
@@ -69,7 +79,8 @@ __global__ void __launch_bounds__(kInsertBlock) replay_insert_ring_kernel(int n,
                                                                         const float *d_state, const float *d_action,
                                                                         const float *d_reward, const float *d_next_state,
                                                                         const uint8_t *d_done, const float *d_emotion,
-                                                                        const float *d_scale, const float *d_offset, int normalize) {
+                                                                        const float *d_scale, const float *d_offset, int normalize,
+                                                                        const erlfill_cond_scaling cs) {
     __shared__ __align__(16) float4 sh[kInsertBlock * 5];
     const int i0 = blockIdx.x * kInsertBlock, i = i0 + threadIdx.x;
     const int cnt = min(kInsertBlock, n - i0);
@@ -89,14 +100,8 @@ __global__ void __launch_bounds__(kInsertBlock) replay_insert_ring_kernel(int n,
         const float2 ns = __ldg(reinterpret_cast<const float2 *>(d_next_state) + i);
         const float dn = __ldg(d_done + i) ? 1.f : 0.f;
         const float e0 = __ldg(d_emotion + (size_t)i * 3), e1 = __ldg(d_emotion + (size_t)i * 3 + 1), e2 = __ldg(d_emotion + (size_t)i * 3 + 2);
-        if (normalize) {
-#pragma unroll
-            for (int c = 0; c < 10; ++c) {
-                float v = __fdiv_rn(__fsub_rn(a[c], __ldg(d_offset + c)), __ldg(d_scale + c));
-                v = v < -1.f ? -1.f : v;
-                a[c] = v > 1.f ? 1.f : v;
-            }
-        }
+        const int cid = cond_of(cs, i);
+        if (normalize) normalise_action(a, cs.n_cond > 0 ? cs.d_scale + cid * 10 : d_scale, cs.n_cond > 0 ? cs.d_offset + cid * 10 : d_offset);
         float4 *dst = sh + threadIdx.x * 5;
         if (!contiguous) {
             int64_t row = start + i;
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(kInsertBlock) replay_insert_ring_kernel(int n,
         dst[1] = make_float4(a[2], a[3], a[4], a[5]);
         dst[2] = make_float4(a[6], a[7], a[8], a[9]);
         dst[3] = make_float4(rw, ns.x, ns.y, dn);
-        dst[4] = make_float4(e0, e1, e2, 0.f);
+        dst[4] = make_float4(e0, e1, e2, (float)cid);
     }
     if (!contiguous) return;                      // block-uniform
     __syncthreads();
@@ -144,13 +149,19 @@ using namespace erlfill;
 
 extern "C" {
 
-int erlfill_replay_insert(int n, float *d_buf, int64_t capacity, int64_t start, const int64_t *d_pos,
-                          const float *d_state, const float *d_action, const float *d_reward,
-                          const float *d_next_state, const uint8_t *d_done, const float *d_emotion,
-                          const float *d_scale, const float *d_offset, void *stream) {
+static int replay_insert_impl(int n, float *d_buf, int64_t capacity, int64_t start, const int64_t *d_pos,
+                              const float *d_state, const float *d_action, const float *d_reward,
+                              const float *d_next_state, const uint8_t *d_done, const float *d_emotion,
+                              const float *d_scale, const float *d_offset, const erlfill_cond_scaling *csp, void *stream) {
     if (n <= 0 || !d_buf || capacity <= 0 || !d_state || !d_action || !d_reward || !d_next_state || !d_done || !d_emotion)
         return ERLFILL_ERR_ARG;
     if ((d_scale == nullptr) != (d_offset == nullptr)) return ERLFILL_ERR_ARG;
+    erlfill_cond_scaling cs{};
+    if (csp) {
+        if (csp->n_cond <= 0 || !csp->d_scale || !csp->d_offset) return ERLFILL_ERR_ARG;
+        cs = *csp;
+    }
+    const int normalize = (d_scale || csp) ? 1 : 0;
     if (!d_pos && (start < 0 || n > capacity)) return ERLFILL_ERR_ARG;
     if (((uintptr_t)d_buf & 15u) || ((uintptr_t)d_state & 7u) || ((uintptr_t)d_action & 7u) || ((uintptr_t)d_next_state & 7u))
         return ERLFILL_ERR_ARG;
@@ -159,13 +170,30 @@ int erlfill_replay_insert(int n, float *d_buf, int64_t capacity, int64_t start, 
     if (d_pos)
         replay_insert_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(n, d_buf, capacity, start, d_pos, d_state, d_action,
                                                                                  d_reward, d_next_state, d_done, d_emotion, d_scale,
-                                                                                 d_offset, d_scale ? 1 : 0);
+                                                                                 d_offset, normalize, cs);
     else
         replay_insert_ring_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(n, d_buf, capacity, start % capacity, d_state, d_action,
                                                                                       d_reward, d_next_state, d_done, d_emotion,
-                                                                                      d_scale, d_offset, d_scale ? 1 : 0);
+                                                                                      d_scale, d_offset, normalize, cs);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
+}
+
+int erlfill_replay_insert(int n, float *d_buf, int64_t capacity, int64_t start, const int64_t *d_pos,
+                          const float *d_state, const float *d_action, const float *d_reward,
+                          const float *d_next_state, const uint8_t *d_done, const float *d_emotion,
+                          const float *d_scale, const float *d_offset, void *stream) {
+    return replay_insert_impl(n, d_buf, capacity, start, d_pos, d_state, d_action, d_reward, d_next_state, d_done, d_emotion, d_scale,
+                              d_offset, nullptr, stream);
+}
+
+int erlfill_replay_insert_cond(int n, float *d_buf, int64_t capacity, int64_t start, const int64_t *d_pos,
+                               const float *d_state, const float *d_action, const float *d_reward,
+                               const float *d_next_state, const uint8_t *d_done, const float *d_emotion,
+                               const erlfill_cond_scaling *cs, void *stream) {
+    if (!cs) return ERLFILL_ERR_ARG;
+    return replay_insert_impl(n, d_buf, capacity, start, d_pos, d_state, d_action, d_reward, d_next_state, d_done, d_emotion, nullptr,
+                              nullptr, cs, stream);
 }
 
 int erlfill_replay_sample(int batch, int64_t n_valid, uint64_t seed, uint32_t update_idx, uint32_t stream_id,

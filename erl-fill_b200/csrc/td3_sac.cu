@@ -60,7 +60,9 @@ static void mlp_backward(cudaStream_t st, float *part, int B, const float *P, fl
 }
 
 // ---- noise ------------------------------------------------------------------------------------------------------
-// standard normal draw j (0..9) of row `row`: injected, or Philox Box-Muller keyed (row, idx, j/4 [+ salt], STREAM_OU)
+// standard normal draw j (0..9) of row `row`: injected, or Philox Box-Muller keyed (row id, idx, j/2 + 8 salt, STREAM_OU).  Salts keep the
+// streams apart: 1 = exploration noise at act time (row id = global env id, idx = lock-step index); 4 / 5 = the update's draws (row id =
+// rank << 20 | minibatch row, idx = update index), so ranks draw different noise for their different minibatches
 __device__ __forceinline__ float normal_draw(const float *inj, size_t row, int j, uint64_t seed, uint32_t row_id, uint32_t idx, uint32_t salt) {
     if (inj) return inj[row * AD + j];
     const uint4 r = philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), row_id, idx, (uint32_t)(j >> 1) + 8u * salt, STREAM_OU);
@@ -72,7 +74,7 @@ __device__ __forceinline__ float normal_draw(const float *inj, size_t row, int j
 // ---- TD3 row kernels ----------------------------------------------------------------------------------------------
 // x0n[r] = [s'(2) | clamp(tanh(z') + clamp(0.2 n, +-0.5), -1, 1)(10) | 0 x 4]          (td3_agent.py:268-269)
 __global__ void td3_target_action_kernel(int B, const float *batch, const float *z, const float *noise, float policy_noise, float noise_clip,
-                                         uint64_t seed, uint32_t update_idx, float *x0n) {
+                                         uint64_t seed, uint32_t update_idx, uint32_t row_id_base, float *x0n) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= B * 16) return;
     const int r = g >> 4, c = g & 15;
@@ -80,7 +82,7 @@ __global__ void td3_target_action_kernel(int B, const float *batch, const float 
     if (c < SD) v = batch[(size_t)r * ERLFILL_REC + 13 + c];
     else if (c < QIN) {
         const int j = c - SD;
-        const float n = fminf(fmaxf(normal_draw(noise, r, j, seed, r, update_idx, 0) * policy_noise, -noise_clip), noise_clip);
+        const float n = fminf(fmaxf(normal_draw(noise, r, j, seed, row_id_base + (uint32_t)r, update_idx, 4) * policy_noise, -noise_clip), noise_clip);
         v = fminf(fmaxf(tanhf(z[(size_t)r * AD + j]) + n, -1.0f), 1.0f);
     }
     x0n[g] = v;
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(1024) neg_mean_kernel(int B, const float *q, f
 // GaussianPolicy.sample (sac_agent.py:45-84) from ml[r] = [mean(10) | log_std(10)]: a = tanh(mean + exp(clamp(ls,-20,2)) eps),
 // log_prob = sum(-eps^2/2 - ls_c - log sqrt(2 pi) - log(1 - a^2 + 1e-7)).  x0[r] = [state | a | 0]; a, sigma*eps kept for the backward.
 __global__ void sac_sample_kernel(int B, const float *batch, int state_col, const float *ml, const float *eps, uint64_t seed, uint32_t update_idx,
-                                  uint32_t salt, float *x0, float *a_out, float *se_out, float *logp) {
+                                  uint32_t salt, uint32_t row_id_base, float *x0, float *a_out, float *se_out, float *logp) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= B) return;
     float lp = 0.f;
@@ -140,7 +142,7 @@ __global__ void sac_sample_kernel(int B, const float *batch, int state_col, cons
 #pragma unroll
     for (int j = 0; j < AD; ++j) {
         const float mean = ml[(size_t)r * 20 + j], ls = fminf(fmaxf(ml[(size_t)r * 20 + AD + j], -20.0f), 2.0f);
-        const float e = normal_draw(eps, r, j, seed, r, update_idx, salt);
+        const float e = normal_draw(eps, r, j, seed, row_id_base + (uint32_t)r, update_idx, salt);
         const float se = expf(ls) * e;
         const float a = tanhf(mean + se);
         lp += -0.5f * e * e - ls - 0.9189385332046727f - logf(1.0f - a * a + 1e-7f);
@@ -339,7 +341,7 @@ int erlfill_td3_update(const erlfill_td3_nets *n, const erlfill_td3_hyper *h, co
         // target: a' = clamp(actor_target(s') + clipped noise), y from the twin target critics
         mlp_forward(st, B, n->actor_target, kTd3Actor, d_batch + 13, ERLFILL_REC, w.ah1, w.ah2, w.z, AD);
         td3_target_action_kernel<<<(B * 16 + 255) / 256, 256, 0, st>>>(B, d_batch, w.z, d_noise, h->policy_noise, h->noise_clip, h->seed,
-                                                                        h->update_idx, w.x0);
+                                                                        h->update_idx, h->rank << 20, w.x0);
         q_forward(st, B, n->critic_target, kQ1, w.x0, 16, w.h1a, w.h2a, w.q1t);
         q_forward(st, B, n->critic_target, kQ2, w.x0, 16, w.h1b, w.h2b, w.q2t);
         // current estimates on (s, a) read in place from the replay rows
@@ -392,7 +394,7 @@ int erlfill_sac_update(const erlfill_sac_nets *n, const erlfill_sac_hyper *h, co
     };
     if (phases & ERLFILL_PHASE_CRITIC_GRAD) {
         policy_forward(d_batch + 13, ERLFILL_REC);
-        sac_sample_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, d_batch, 13, w.ml, d_eps_next, h->seed, h->update_idx, 0, w.x0, nullptr, nullptr, w.logp2);
+        sac_sample_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, d_batch, 13, w.ml, d_eps_next, h->seed, h->update_idx, 4, h->rank << 20, w.x0, nullptr, nullptr, w.logp2);
         q_forward(st, B, n->q_target, kQ1, w.x0, 16, w.h1a, w.h2a, w.q1t);
         q_forward(st, B, n->q_target, kQ2, w.x0, 16, w.h1b, w.h2b, w.q2t);
         q_forward(st, B, n->q, kQ1, d_batch, ERLFILL_REC, w.h1a, w.h2a, w.q1);
@@ -405,7 +407,7 @@ int erlfill_sac_update(const erlfill_sac_nets *n, const erlfill_sac_hyper *h, co
     if (phases & ERLFILL_PHASE_CRITIC_APPLY) adam(st, NQ, n->q, n->q_m, n->q_v, w.cgrad, h->lr, h->adam_step);
     if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
         policy_forward(d_batch, ERLFILL_REC);
-        sac_sample_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, d_batch, 0, w.ml, d_eps_new, h->seed, h->update_idx, 1, w.x0, w.a, w.se, w.logp);
+        sac_sample_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, d_batch, 0, w.ml, d_eps_new, h->seed, h->update_idx, 5, h->rank << 20, w.x0, w.a, w.se, w.logp);
         q_forward(st, B, n->q, kQ1, w.x0, 16, w.h1a, w.h2a, w.q1);
         sac_policy_loss_kernel<<<1, 1024, 0, st>>>(B, w.logp, w.q1, h->alpha, w.scal + 2);
         fill_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, -1.0f / (float)B, w.dq1);

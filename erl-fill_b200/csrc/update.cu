@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(NTHR) critic_fwd_kernel(const CriticFwdArgs a)
 // Actor.forward for the CTA's rows (ddpg_agent.py:73-122) -> physical-unit actions.  Input row [state | emotion | 0]; mode 1:
 // (s', next_emotion broadcast) for the target.  keep: store what the backward needs.
 struct ActorFwdArgs {
-    int B, mode, keep;
+    int B, mode, keep, n_cond;
     const float *batch, *next_emotion, *P, *scale, *offset;
     float *out, *xa, *a1, *a2, *a3, *z4, *aux;
 };
@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(NTHR) actor_fwd_kernel(const ActorFwdArgs a) {
             const float *row = a.batch + (size_t)gr * ERLFILL_REC;
             if (c < 2) v = a.mode == 1 ? row[13 + c] : row[c];
             else if (c < 5) v = a.mode == 1 ? a.next_emotion[c - 2] : row[16 + (c - 2)];
+            else if (c == 5) v = a.n_cond > 1 ? row[19] : 0.f;      // the record's condition index (multiplied by zero weights below)
             if (a.keep) a.xa[(size_t)gr * 8 + c] = v;
         }
         bufA[r * LDA + c] = v;
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(NTHR) actor_fwd_kernel(const ActorFwdArgs a) {
         const float om = 1.0f - fabsf(base);
         const float sf = base > 0.f ? -1.0f : (base < 0.f ? 1.0f : 0.0f);
         const size_t g = (size_t)gr * 10 + c;
-        a.out[g] = (base + alpha * raw * sf * (om * om)) * a.scale[c] + a.offset[c];
+        const int so = (int)xa_s[r * 8 + 5] * 10 + c;          // per-condition scaling row (0 for a single condition)
+        a.out[g] = (base + alpha * raw * sf * (om * om)) * a.scale[so] + a.offset[so];
         if (a.keep) { a.z4[g] = z; a.aux[g * 3 + 0] = base; a.aux[g * 3 + 1] = raw; a.aux[g * 3 + 2] = alpha; }
     }
 }
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(NTHR) actor_bwd_kernel(const ActorBwdArgs a) {
                 const size_t g = (size_t)gr * 10 + c;
                 float go = a.g16[(size_t)gr * 16 + 2 + c];
                 go += (-0.03f / (float)B) * (o[c] - mean) / (9.0f * sd);                      // d std / d o_c
-                const float gr_ = go * a.scale[c];                                                // d raw_action
+                const float gr_ = go * a.scale[(int)a.xa[(size_t)gr * 8 + 5] * 10 + c];           // d raw_action
                 const float base = a.aux[g * 3 + 0], raw = a.aux[g * 3 + 1], alpha = a.aux[g * 3 + 2];
                 const float om = 1.0f - fabsf(base);
                 const float sf = base > 0.f ? -1.0f : (base < 0.f ? 1.0f : 0.0f);
@@ -645,8 +647,8 @@ static void critic_forward(cudaStream_t st, const Ws &w, int B, int mode, const 
     critic_fwd_kernel<<<n_tiles(B), NTHR, kFusedSmem, st>>>(a);
 }
 static void actor_forward(cudaStream_t st, const Ws &w, int B, int mode, const float *batch, const float *next_emotion, const float *P,
-                          const float *scale, const float *offset, float *out, bool keep) {
-    const ActorFwdArgs a{B, mode, keep ? 1 : 0, batch, next_emotion, P, scale, offset, out, w.xa, w.a1, w.a2, w.a3, w.z4, w.aux};
+                          const float *scale, const float *offset, float *out, bool keep, int n_cond) {
+    const ActorFwdArgs a{B, mode, keep ? 1 : 0, n_cond, batch, next_emotion, P, scale, offset, out, w.xa, w.a1, w.a2, w.a3, w.z4, w.aux};
     actor_fwd_kernel<<<n_tiles(B), NTHR, kFusedSmem, st>>>(a);
 }
 // the grouped weight-gradient GEMMs and the one reduction launch that finishes every parameter gradient of a network
@@ -690,6 +692,8 @@ size_t erlfill_ddpg_workspace_bytes(int batch) {
     if (batch < 2) return 0;
     return carve(nullptr, nullptr, batch) * sizeof(float);
 }
+
+int erlfill_ddpg_update_launches(int fast) { return fast ? 0 : 24; }
 
 int erlfill_ddpg_grad_buckets(void *d_workspace, int batch, float **critic_grad, int *critic_len, float **actor_grad, int *actor_len) {
     if (!d_workspace || batch < 2) return ERLFILL_ERR_ARG;
@@ -751,7 +755,7 @@ int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h,
     if (phases & ERLFILL_PHASE_CRITIC_GRAD) {
         emotion_stats_kernel<<<1, 1024, 0, st>>>(B, d_batch, w.stats, w.cgrad + CO::TOTAL);
         // target: a' = actor_target(s', e'), Q' = critic_target(s', a', 0)
-        actor_forward(st, w, B, 1, d_batch, d_next_emotion, n->actor_target, n->scale, n->offset, w.atgt, false);
+        actor_forward(st, w, B, 1, d_batch, d_next_emotion, n->actor_target, n->scale, n->offset, w.atgt, false, h->n_cond);
         critic_forward(st, w, B, 1, d_batch, w.atgt, n->critic_target, w.tq, false);
         // Q(s, a_norm, e) and its gradient
         critic_forward(st, w, B, 0, d_batch, nullptr, n->critic, w.q, true);
@@ -778,7 +782,7 @@ int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h,
                                                                   w.ssq, w.scal + 2, h->max_grad_norm, w.step, h->tau);
     }
     if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
-        actor_forward(st, w, B, 0, d_batch, d_next_emotion, n->actor, n->scale, n->offset, w.aout, true);
+        actor_forward(st, w, B, 0, d_batch, d_next_emotion, n->actor, n->scale, n->offset, w.aout, true, h->n_cond);
         critic_forward(st, w, B, 2, d_batch, w.aout, n->critic, w.q2, true);
         actor_loss_kernel<<<1 + kActorTensors, 1024, 0, st>>>(B, w.q2, w.aout, n->actor, w.scal + 5, w.scal + 6);
         // d(-mean q2)/dq2 = -1/B (the +-1e6 clamp is inactive): input gradient of the critic only -> w.g16

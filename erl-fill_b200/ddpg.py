@@ -56,10 +56,11 @@ class ReplayBuffer:
     def __len__(self):
         return self.size
 
-    def insert(self, state, action, reward, next_state, done, emotion, scale=None, offset=None, policy="ring"):
+    def insert(self, state, action, reward, next_state, done, emotion, scale=None, offset=None, policy="ring", cond=None):
         """R1.  policy "ring": FIFO ring (TD3/SAC deque semantics and the batched ER-DDPG loop);
         "per_argmin": the reference's PrioritizedReplayBuffer.add with its all-equal priorities — append until
-        full, then always overwrite slot 0 (np.argmin of equal values)."""
+        full, then always overwrite slot 0 (np.argmin of equal values).
+        cond: an _lib.CondScaling for a mixed-condition batch (per-env scale / offset rows, condition id into column 19)."""
         n = state.shape[0]
         pos = None
         if policy == "per_argmin":
@@ -70,10 +71,16 @@ class ReplayBuffer:
         else:
             start = self.inserted % self.capacity
         with torch.cuda.device(self.device):
-            L.check(L.lib().erlfill_replay_insert(C.c_int(n), L.ptr(self.buf), C.c_int64(self.capacity), C.c_int64(start),
-                                                  L.ptr(pos), L.ptr(state), L.ptr(action), L.ptr(reward), L.ptr(next_state),
-                                                  L.ptr(done), L.ptr(emotion), L.ptr(scale), L.ptr(offset), L.stream_ptr()),
-                    "erlfill_replay_insert")
+            if cond is not None:
+                L.check(L.lib().erlfill_replay_insert_cond(C.c_int(n), L.ptr(self.buf), C.c_int64(self.capacity), C.c_int64(start),
+                                                           L.ptr(pos), L.ptr(state), L.ptr(action), L.ptr(reward), L.ptr(next_state),
+                                                           L.ptr(done), L.ptr(emotion), C.byref(cond), L.stream_ptr()),
+                        "erlfill_replay_insert_cond")
+            else:
+                L.check(L.lib().erlfill_replay_insert(C.c_int(n), L.ptr(self.buf), C.c_int64(self.capacity), C.c_int64(start),
+                                                      L.ptr(pos), L.ptr(state), L.ptr(action), L.ptr(reward), L.ptr(next_state),
+                                                      L.ptr(done), L.ptr(emotion), L.ptr(scale), L.ptr(offset), L.stream_ptr()),
+                        "erlfill_replay_insert")
         self.inserted += n
         self.size = min(self.capacity, self.size + n)
 
@@ -100,7 +107,7 @@ class DDPGLearner:
     """Flat-buffer ER-DDPG networks + optimiser state and the fused update (DDPGAgent.learn)."""
 
     def __init__(self, actor_sd, critic_sd, device="cuda", batch_size=128, gamma=0.99, tau=0.01, actor_lr=1e-4,
-                 critic_lr=1e-3, lr_decay_rate=0.999):
+                 critic_lr=1e-3, lr_decay_rate=0.999, precision="exact"):
         self.device = torch.device(device)
         d = self.device
         self.actor = FlatNet(ACTOR_LAYOUT, L.ACTOR_PARAMS, d)
@@ -114,20 +121,48 @@ class DDPGLearner:
         self.actor_m = torch.zeros(L.ACTOR_PARAMS, device=d); self.actor_v = torch.zeros(L.ACTOR_PARAMS, device=d)
         self.critic_m = torch.zeros(L.CRITIC_PARAMS, device=d); self.critic_v = torch.zeros(L.CRITIC_PARAMS, device=d)
         self.gamma, self.tau, self.actor_lr, self.critic_lr, self.lr_decay_rate = gamma, tau, actor_lr, critic_lr, lr_decay_rate
+        self.n_cond, self.scale_tab, self.offset_tab = 1, None, None      # set_condition_scaling: mixed-condition batches
         self.adam_step = 0
         self.report = torch.zeros(4, dtype=torch.float32, device=d)
         self._ws, self._ws_batch = None, 0
+        self._ws_shared = False          # True while a parallel.PeerExchange owns the workspace (peers read its buckets in place)
+        if precision not in ("exact", "fast"):
+            raise L.ErlfillError("DDPGLearner: precision must be 'exact' (3xTF32, 1e-4 parity) or 'fast' (tcgen05 bf16 operands)")
+        self.precision = precision
         self.batch_size = batch_size
         self.use_graph = True
         self._graphs = {}
         self._warm = set()
 
+    def set_condition_scaling(self, scale_tab, offset_tab):
+        """Per-condition scale / offset rows [n_cond, 10] for a batch that mixes operating conditions: the update maps the actor
+        output of a sampled record with the row of the record's own condition (column 19, written by ReplayBuffer.insert(cond=...))."""
+        self.scale_tab = torch.as_tensor(scale_tab).to(self.device, torch.float32).contiguous()
+        self.offset_tab = torch.as_tensor(offset_tab).to(self.device, torch.float32).contiguous()
+        self.n_cond = int(self.scale_tab.shape[0])
+        self._graphs.clear(); self._warm.clear()
+
     def _workspace(self, batch):
         if self._ws is None or self._ws_batch != batch:
+            if self._ws_shared:
+                raise L.ErlfillError("DDPGLearner: the workspace is shared with the other ranks (parallel.PeerExchange was built for "
+                                     "minibatch %d); a minibatch of %d needs a new PeerExchange" % (self._ws_batch, batch))
             nbytes = L.lib().erlfill_ddpg_workspace_bytes(C.c_int(batch))
             self._ws = torch.zeros((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
             self._ws_batch = batch
+            # captured graphs hold the old workspace's address (and the old allocation may be reused by anything)
+            self._graphs.clear()
+            self._warm.clear()
         return self._ws
+
+    def precision_name(self):
+        return {"exact": "f32 (3xTF32 tensor-core GEMMs, fp32 accumulate)",
+                "fast": "bf16 operands / f32 accumulate (tcgen05), f32 master weights and optimiser"}[self.precision]
+
+    def launches_per_update(self, data_parallel=False):
+        """Kernels of liberlfill.so per erlfill_ddpg_update(PHASE_ALL) (+ the two peer exchanges when data-parallel)."""
+        n = int(L.lib().erlfill_ddpg_update_launches(C.c_int(1 if self.precision == "fast" else 0)))
+        return n + (int(L.lib().erlfill_ddpg_peer_launches()) if data_parallel else 0)
 
     def grad_buckets(self, batch):
         """(critic_bucket, actor_bucket) tensors aliasing the gradient buckets in the workspace."""
@@ -173,18 +208,22 @@ class DDPGLearner:
             self.adam_step += 1
         if graph is None:
             graph = self.use_graph and phases == L.PHASE_ALL and (allreduce is None or getattr(allreduce, "graph_safe", False))
+        multi = self.n_cond > 1
         nets = L.DDPGNets(L.ptr(self.actor.flat), L.ptr(self.actor_target.flat), L.ptr(self.critic.flat),
                           L.ptr(self.critic_target.flat), L.ptr(self.actor_m), L.ptr(self.actor_v), L.ptr(self.critic_m),
-                          L.ptr(self.critic_v), L.ptr(self.scale), L.ptr(self.offset))
+                          L.ptr(self.critic_v), L.ptr(self.scale_tab if multi else self.scale),
+                          L.ptr(self.offset_tab if multi else self.offset))
         decay = self.lr_decay_rate ** train_step
 
         def run(ph, adam_step):
-            hyper = L.DDPGHyper(B, adam_step, self.gamma, self.tau, 5.0, 0.0, self.critic_lr, self.actor_lr, decay)
+            hyper = L.DDPGHyper(B, adam_step, self.gamma, self.tau, 5.0, self.n_cond, self.critic_lr, self.actor_lr, decay)
             with torch.cuda.device(self.device):
                 L.check(L.lib().erlfill_ddpg_update(C.byref(nets), C.byref(hyper), L.ptr(batch), L.ptr(next_emotion), L.ptr(ws),
                                                     C.c_int(ph), L.ptr(self.report), L.stream_ptr()), "erlfill_ddpg_update")
 
-        key = (B, batch.data_ptr(), next_emotion.data_ptr(), id(allreduce))
+        # everything a captured graph bakes in: buffer addresses (the workspace included) and the by-value hyper-parameters
+        key = (B, batch.data_ptr(), next_emotion.data_ptr(), ws.data_ptr(), id(allreduce), self.gamma, self.tau, self.critic_lr,
+               self.actor_lr, self.n_cond, self.precision)
         if graph and key not in self._graphs and key not in self._warm:
             self._warm.add(key)          # first update on these buffers runs eagerly (module loading outside a capture)
             graph = False

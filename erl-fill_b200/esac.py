@@ -162,6 +162,8 @@ class VecEmotionSAC:
         if idx is None:
             self.memory.sample_indices(self.batch_size, self.seed, self.updates, stream_id=self.rank, out=self.idx)
             idx = self.idx
+        if idx.shape[0] > self.batch_size:      # the update workspace is sized for batch_size rows
+            raise L.ErlfillError("minibatch of %d indices exceeds batch_size %d" % (idx.shape[0], self.batch_size))
         batch = self.memory.gather(idx, out=self.batch if idx.shape[0] == self.batch_size else None)
         if e_now is None:
             torch.mean(self.emotion, dim=0, out=self.e_now)
@@ -171,7 +173,7 @@ class VecEmotionSAC:
         nets_ = L.SACNets(L.ptr(self.policy.flat), L.ptr(self.q.flat), L.ptr(self.q_target.flat), L.ptr(self.policy_m), L.ptr(self.policy_v),
                           L.ptr(self.q_m), L.ptr(self.q_v))
         hyper = L.SACHyper(batch.shape[0], self.adam_step, self.gamma, self.tau, self.alpha, 0.0, self.lr, self.seed,
-                           self.updates & 0xFFFFFFFF, 0)
+                           self.updates & 0xFFFFFFFF, self.rank)
 
         def run(ph):
             with torch.cuda.device(self.device):

@@ -133,7 +133,10 @@ class PeerExchange:
         self._holder = _DevMem(self._base, ws_bytes)
         learner._ws = torch.as_tensor(self._holder, device=dev)
         learner._ws_batch = self.batch
+        learner._ws_shared = True
+        self._learner = learner
         learner._graphs.clear()
+        learner._warm.clear()
         dist.barrier(group=group)        # every rank has mapped every block before the first exchange
 
     def exchange(self, which):
@@ -154,5 +157,9 @@ class PeerExchange:
         self._mapped = []
         dist.barrier(group=self.group)
         if self._base:
+            ln = getattr(self, "_learner", None)
+            if ln is not None:          # the learner must not keep pointing at the freed block
+                ln._ws, ln._ws_batch, ln._ws_shared = None, 0, False
+                ln._graphs.clear(); ln._warm.clear()
             self.L.lib().erlfill_peer_free(C.c_void_p(self._base))
             self._base = None

@@ -106,6 +106,8 @@ class _T1Base:
         if idx is None:
             self.memory.sample_indices(self.batch_size, self.seed, self.updates, stream_id=self.rank, out=self.idx)
             idx = self.idx
+        if idx.shape[0] > self.batch_size:      # the update workspace is sized for batch_size rows
+            raise L.ErlfillError("minibatch of %d indices exceeds batch_size %d" % (idx.shape[0], self.batch_size))
         return self.memory.gather(idx, out=self.batch if idx.shape[0] == self.batch_size else None)
 
     def rollout_step(self, store=True, **act_kw):
@@ -167,7 +169,7 @@ class VecTD3(_T1Base):
         nets = L.TD3Nets(L.ptr(self.actor.flat), L.ptr(self.actor_target.flat), L.ptr(self.critic.flat), L.ptr(self.critic_target.flat),
                          L.ptr(self.actor_m), L.ptr(self.actor_v), L.ptr(self.critic_m), L.ptr(self.critic_v))
         hyper = L.TD3Hyper(batch.shape[0], self.total_it, max(self.actor_steps, 1), int(upd), self.gamma, self.tau, self.policy_noise,
-                           self.noise_clip, self.critic_lr, self.actor_lr, self.seed, self.updates & 0xFFFFFFFF, 0)
+                           self.noise_clip, self.critic_lr, self.actor_lr, self.seed, self.updates & 0xFFFFFFFF, self.rank)
 
         def run(ph):
             with torch.cuda.device(self.device):
@@ -224,7 +226,7 @@ class VecSAC(_T1Base):
         nets = L.SACNets(L.ptr(self.policy.flat), L.ptr(self.q.flat), L.ptr(self.q_target.flat), L.ptr(self.policy_m), L.ptr(self.policy_v),
                          L.ptr(self.q_m), L.ptr(self.q_v))
         hyper = L.SACHyper(batch.shape[0], self.adam_step, self.gamma, self.tau, self.alpha, 0.0, self.lr, self.seed,
-                           self.updates & 0xFFFFFFFF, 0)
+                           self.updates & 0xFFFFFFFF, self.rank)
 
         def run(ph):
             with torch.cuda.device(self.device):

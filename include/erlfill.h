@@ -190,12 +190,32 @@ typedef struct {
     int32_t *d_hist_head;          /* [n] slot of the oldest entry */
 } erlfill_emotion_state;
 
+/* Per-condition action scaling for a batch that mixes operating conditions.  The reference builds ONE AGENT PER CONDITION
+ * (experiment_runner.py:504-510), each with scale_params / offset_params from its own env.bounds (ddpg_agent.py:56-71), so the
+ * network output of an env under condition c is mapped with row c of these tables; a batch of one condition equals the
+ * plain entry points.  A replay record written through the _cond insert carries its condition in column 19, which
+ * erlfill_ddpg_update reads back when hyper->n_cond > 1 (nets->scale / nets->offset are then the [n_cond][10] tables). */
+typedef struct {
+    const float *d_scale;      /* [n_cond][10] */
+    const float *d_offset;     /* [n_cond][10] */
+    const int32_t *d_cond_id;  /* [n_rows], or NULL => (row_id_base + row) % n_cond (erlfill_env_batch's round-robin rule) */
+    int32_t n_cond;
+    uint32_t row_id_base;
+} erlfill_cond_scaling;
+
 /* A1 (+A2 when ou != NULL) — Actor.forward (ddpg_agent.py:73-122); with ou also OUNoise.sample and
  * DDPGAgent.act's clip (:348-356, :768-778).  d_emotion is [n][3], or [3] when emotion_broadcast. */
 int erlfill_actor_forward(const erlfill_actor_weights *w, int n_rows, const float *d_state, const float *d_emotion,
                           int emotion_broadcast, int dropout_mode, uint64_t seed, uint32_t call_idx,
                           uint32_t row_id_base, const uint8_t *d_mask1, const uint8_t *d_mask2,
                           float *d_scaled_action, float *d_base_action, const erlfill_ou *ou, void *stream);
+
+/* The same with per-condition scaling (cs == NULL: identical to erlfill_actor_forward). */
+int erlfill_actor_forward_cond(const erlfill_actor_weights *w, int n_rows, const float *d_state, const float *d_emotion,
+                               int emotion_broadcast, int dropout_mode, uint64_t seed, uint32_t call_idx,
+                               uint32_t row_id_base, const uint8_t *d_mask1, const uint8_t *d_mask2,
+                               float *d_scaled_action, float *d_base_action, const erlfill_ou *ou,
+                               const erlfill_cond_scaling *cs, void *stream);
 
 /* M1 — EmotionModule.update(reward, next_state - state) (EmotionModule.py:121-162) for every env. */
 int erlfill_emotion_update(int n_env, const float *d_reward, const float *d_state, const float *d_next_state,
@@ -249,7 +269,8 @@ int erlfill_emotion_forward_tc(const void *d_image, int n_env, const float *d_se
 
 /* ------------------------------------------------------------------------------------------ */
 /* Replay buffer: [capacity][ERLFILL_REC] binary32 rows                                        */
-/*   [0:2] state [2:12] normalised action [12] reward [13:15] next_state [15] done [16:19] emotion [19] pad */
+/*   [0:2] state [2:12] normalised action [12] reward [13:15] next_state [15] done [16:19] emotion [19] condition index (0.0f unless
+ *   written by erlfill_replay_insert_cond) */
 /* ------------------------------------------------------------------------------------------ */
 
 /* R1 — DDPGAgent.remember + PrioritizedReplayBuffer.add (ddpg_agent.py:359-395, 206-226) for n transitions.
@@ -261,6 +282,13 @@ int erlfill_replay_insert(int n, float *d_buf, int64_t capacity, int64_t start, 
                           const float *d_state, const float *d_action, const float *d_reward,
                           const float *d_next_state, const uint8_t *d_done, const float *d_emotion,
                           const float *d_scale, const float *d_offset, void *stream);
+
+/* R1 for a mixed-condition batch: transition i is normalised with the scale / offset row of its own condition, and the
+ * condition index is stored (as a float) in column 19 of the record. */
+int erlfill_replay_insert_cond(int n, float *d_buf, int64_t capacity, int64_t start, const int64_t *d_pos,
+                               const float *d_state, const float *d_action, const float *d_reward,
+                               const float *d_next_state, const uint8_t *d_done, const float *d_emotion,
+                               const erlfill_cond_scaling *cs, void *stream);
 
 /* R2 — PrioritizedReplayBuffer.sample's index draw (ddpg_agent.py:228-254) with equal priorities:
  * idx[i] = floor(U_i * n_valid), U from Philox (i/4, update_idx, stream_id, SAMPLE)[i%4]. */
@@ -289,7 +317,8 @@ typedef struct {
 typedef struct {
     int32_t batch;
     int32_t adam_step;        /* 1-based optimiser step of this update; 0 = scalars already uploaded by erlfill_ddpg_set_step */
-    float gamma, tau, max_grad_norm, _pad;
+    float gamma, tau, max_grad_norm;
+    int32_t n_cond;           /* <= 1: nets->scale / offset are [10]; > 1: [n_cond][10] tables indexed by column 19 of each record */
     double critic_lr, actor_lr;   /* base rates (1e-3, 1e-4) */
     double lr_decay;              /* lr_decay_rate ** train_step (ddpg_agent.py:455) */
 } erlfill_ddpg_hyper;
@@ -316,6 +345,9 @@ int erlfill_ddpg_set_step(void *d_workspace, int batch, int adam_step, double lr
  * critic_lr, actor_lr. */
 int erlfill_ddpg_update(const erlfill_ddpg_nets *nets, const erlfill_ddpg_hyper *hyper, const float *d_batch,
                         const float *d_next_emotion, void *d_workspace, int phases, float *d_report, void *stream);
+
+/* kernels one erlfill_ddpg_update(ERLFILL_PHASE_ALL) launches (fast: the tcgen05 bf16 path; else the 3xTF32 path) */
+int erlfill_ddpg_update_launches(int fast);
 
 /* Exchange buffers inside the workspace: the two gradient buckets (as erlfill_ddpg_grad_buckets), the two reduced
  * buffers of the same lengths and the [2][64] sum-of-squares partials. */
@@ -345,7 +377,11 @@ int erlfill_peer_free(void *dptr);
  * gradient.  Call between X_GRAD and (X_APPLY | ERLFILL_PHASE_REDUCED); stream-ordered, graph-capturable, no host sync.
  * Every rank must make the same sequence of calls. */
 int erlfill_ddpg_peer_allreduce(const erlfill_peer_group *g, int batch, int which, void *stream);
-/* 1 in *error_out if a wait for a peer timed out (about 2 s) since the allocation; synchronises the device. */
+/* kernels the two exchanges of one update add (bench.py's gpu_launches claim) */
+int erlfill_ddpg_peer_launches(void);
+/* 1 in *error_out if a wait for a peer timed out (ERLFILL_PEER_TIMEOUT_S seconds, default 30) since the allocation; synchronises
+ * the device.  A timed-out exchange also writes NaN into the reduced bucket and its norm partials, so the following APPLY phase
+ * poisons this rank's parameters and update report instead of applying a stale sum. */
 int erlfill_peer_error(const erlfill_peer_group *g, int *error_out);
 
 /* ------------------------------------------------------------------------------------------ */
@@ -371,7 +407,7 @@ typedef struct {
     float gamma, tau, policy_noise, noise_clip;
     double critic_lr, actor_lr;
     uint64_t seed;                     /* Philox key when d_noise == NULL */
-    uint32_t update_idx, _pad;
+    uint32_t update_idx, rank;         /* data-parallel rank: mixed into the Philox counter so ranks draw different update noise */
 } erlfill_td3_hyper;
 typedef struct {
     float *policy, *q, *q_target;
@@ -382,7 +418,7 @@ typedef struct {
     float gamma, tau, alpha, _pad;
     double lr;
     uint64_t seed;
-    uint32_t update_idx, _pad2;
+    uint32_t update_idx, rank;
 } erlfill_sac_hyper;
 
 /* bytes of the caller-provided device workspace of erlfill_td3_update / erlfill_sac_update, and of the *_act entries */

@@ -1,9 +1,11 @@
 """Import shim for the UNMODIFIED reference (test infrastructure only, never the product path).
 
-Only usable where /root/reference exists (the build container). It is used by
-oracle/gen_golden.py to manufacture the fixtures under tests/golden/ and by the
-container-only cross-checks of the oracle restatements. Nothing in bench.py,
-smoke() or the -m gpu tests imports this file.
+Usable where /root/reference exists (the build container) or where oracle/vendor_ref.py left its
+byte-for-byte copy under baseline/_ref/ (git-ignored; it travels to the GPU box).  Used by
+oracle/gen_golden.py to manufacture the fixtures under tests/golden/, by the container-only
+cross-checks of the oracle restatements, by bench.py's CPU legs (`--impl reference`, `cpu_baseline`:
+oracle/ref_bench.py) and by the one GPU test that runs the reference's own train_ddpg against the
+drop-ins.  Nothing in the product package, smoke() or the timed GPU region of bench.py imports it.
 
 What it does:
   * stubs `pymodbus` (reference imports it at WeightEnv.py:7-8, MutiConditionEnv.py:5,
@@ -16,7 +18,23 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("ERLFILL_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+VENDORED_ROOT = os.path.join(os.path.dirname(_HERE), "baseline", "_ref", "erlfill_reference")   # oracle/vendor_ref.py
+
+
+def _resolve_root():
+    """ERLFILL_REFERENCE_ROOT, else /root/reference (build container), else the vendored byte-for-byte copy
+    (baseline/_ref/, git-ignored, travels to the GPU box: bench.py's CPU legs and tests/test_ref_train_ddpg_gpu.py)."""
+    env = os.environ.get("ERLFILL_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", VENDORED_ROOT):
+        if os.path.isfile(os.path.join(cand, "VirtualWeightController.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def available() -> bool:
