@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "lib", "liberlfill.so")
 
 ACTION_DIM, STATE_DIM, EMOTION_DIM, RING, HIST, REC = 10, 2, 3, 20, 20, 20
-ENV_MULTI, ENV_SINGLE = 0, 1
+ENV_MULTI, ENV_SINGLE, ENV_ONBOARD = 0, 1, 2
 ACTION_ORDER = ("fast_weight", "medium_weight", "slow_weight", "fast_opening", "medium_opening",
                 "slow_opening", "fast_delay", "medium_delay", "slow_delay", "unload_delay")
 

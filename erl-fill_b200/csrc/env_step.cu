@@ -472,6 +472,63 @@ __device__ __forceinline__ SimResult simulate(const SimParams &p, const double2 
     return res;
 }
 
+// Row N1 — the "on-board" per-tick models of the env classes (WeightEnv.py:176-229, MutiConditionEnv.py:184-226) under the stage
+// logic of simulate_run (in the reference that logic runs in an external PLC polled over Modbus, WeightEnv.py:245-331; the offline
+// controller's loop is the scripted stand-in, exactly what oracle/gen_golden.py onboard runs).  Differences from generic_tick:
+//   motor:  decelerate_time = speed / 100000 with no `speed > 0` guard; np.power(dt, 2) == dt * dt for every reachable speed
+//           (tests/test_oracle_golden.py); the speed CAP `if current_speed < 10000: current_speed += 5000`
+//   weight: current_weight = int(current_weight + opening * (1.0 + u)) — truncation toward zero every tick, no clamp at zero
+// int() truncation breaks the exact-integer hold phase of the warp kernel, so this variant is one thread per env, one tick at a time.
+template <class NoiseT>
+__device__ __forceinline__ SimResult simulate_onboard(const SimParams &p, double sysdelay, const NoiseT &nz, bool valid) {
+    double w = 0.0, open = 0.0, speed = 0.0, dir = 0.0, prev = 0.0, target = p.fast_pos;
+    int n = 0, delay = 0, nochg = 0;
+    bool first = true, fin = !valid;
+    double o[4] = {0.0, 0.0, 0.0, 0.0};
+    while (!fin) {
+        if ((n & 3) == 0) nz.fetch(o, n >> 2);
+        const int j = n & 3;
+        const double opu = j == 0 ? o[0] : (j == 1 ? o[1] : (j == 2 ? o[2] : o[3]));     // 1.0 + u
+        n += 1;
+        // motor_simulation(target): WeightEnv.py:188-218
+        const double dt = __ddiv_rn(speed, 100000.0);
+        const double dd = __dmul_rn(50000.0, __dmul_rn(dt, dt));
+        if (fabs(__dsub_rn(open, target)) > 1.0) {
+            if (open < target) {
+                dir = 1.0;
+                if (open < __dsub_rn(target, dd)) { if (speed < 10000.0) speed = __dadd_rn(speed, 5000.0); }
+                else speed = __dsub_rn(speed, 100.0);
+            } else if (open > target) {
+                dir = -1.0;
+                if (open > dd) { if (speed < 10000.0) speed = __dadd_rn(speed, 5000.0); }
+                else speed = __dsub_rn(speed, 100.0);
+            }
+        } else {
+            speed = 0.0; open = target;
+        }
+        open = __dadd_rn(open, __ddiv_rn(__dmul_rn(speed, dir), 1000.0));
+        // weight_simulation(open, 1.0): :228-229
+        w = trunc(__dadd_rn(w, __dmul_rn(open, opu)));
+        // stage selection, first-tick delay, safety stops: VirtualWeightController.py:191-229
+        const bool lf = w < p.fast_w, lm = w < p.medium_w, ls = w < p.slow_w;
+        if (!(lf | lm | ls)) break;
+        target = lf ? p.fast_pos : (lm ? p.medium_pos : p.slow_pos);
+        if (first) {
+            delay = lf ? p.fast_delay : (lm ? p.medium_delay : p.slow_delay);
+            w = __dadd_rn(w, __dmul_rn(target, sysdelay));
+            first = false;
+        }
+        nochg = (fabs(__dsub_rn(w, prev)) < 0.01) ? nochg + 1 : 0;
+        prev = w;
+        fin = (n > ERLFILL_MAX_ITER) | (nochg > ERLFILL_NOCHANGE_LIMIT);
+    }
+    SimResult res;
+    res.final_weight = w;
+    res.tick = n + delay;
+    res.draws = n;
+    return res;
+}
+
 // Reward, state, done rule, auto-reset and all stores of one env (E2/E3/E4 after the simulator run).
 template <bool kInjected>
 __device__ __forceinline__ void finish_env(const StepArgs &a, int i, const erlfill_condition &c, const float *clipped,
@@ -481,7 +538,7 @@ __device__ __forceinline__ void finish_env(const StepArgs &a, int i, const erlfi
     const double fw = sim.final_weight;
 
     double we, te;
-    const float reward = a.env.kind == ERLFILL_ENV_MULTI ? reward_multi(c, clipped, fw, total_time, we, te)
+    const float reward = (a.env.kind & 1) == ERLFILL_ENV_MULTI ? reward_multi(c, clipped, fw, total_time, we, te)
                                                         : reward_single(c, clipped, fw, total_time, we, te);
     const float2 ns = make_float2((float)(we / c.target_weight_err), (float)(te / c.target_time));
 
@@ -534,7 +591,7 @@ __device__ __forceinline__ void finish_env(const StepArgs &a, int i, const erlfi
 
 constexpr int kMaxBlock = 256;
 
-template <bool kInjected>
+template <bool kInjected, bool kOnboard = false>
 __global__ void __launch_bounds__(kMaxBlock) env_step_kernel(const StepArgs a) {
     __shared__ __align__(16) double2 s_tab[kTabShared];
     __shared__ __align__(16) float s_act[kMaxBlock * ERLFILL_ACTION_DIM];
@@ -599,12 +656,12 @@ __global__ void __launch_bounds__(kMaxBlock) env_step_kernel(const StepArgs a) {
         sysdelay = a.noise_rows > 0 ? __ldg(a.d_u + ic) : 0.0;
         InjectedNoise nz;
         nz.u_col = a.d_u + ic; nz.n_env = n_env; nz.rows = a.noise_rows;
-        sim = simulate(p, s_tab, sysdelay, nz, valid);
+        sim = kOnboard ? simulate_onboard(p, sysdelay, nz, valid) : simulate(p, s_tab, sysdelay, nz, valid);
     } else {
         sysdelay = 15.0 + 35.0 * u32_to_unit(misc.x);                 // uniform(15, 50): :137
         PhiloxNoise nz;
         nz.k0 = k0; nz.k1 = k1; nz.gid = gid; nz.step_idx = a.step();
-        sim = simulate(p, s_tab, sysdelay, nz, valid);
+        sim = kOnboard ? simulate_onboard(p, sysdelay, nz, valid) : simulate(p, s_tab, sysdelay, nz, valid);
     }
     const int draws = valid ? sim.draws : 0;
     if (valid) finish_env<kInjected>(a, i, c, clipped, sim, unload_delay, misc);
@@ -1378,7 +1435,8 @@ static int env_step_impl(const erlfill_env_batch *env, const float *d_actions, u
                          const erlfill_noise *noise, const erlfill_step_out *out, void *stream) {
     if (!env_ok(env) || !d_actions || !out || !out->d_next_state || !out->d_reward || !out->d_done)
         return ERLFILL_ERR_ARG;
-    if (env->kind != ERLFILL_ENV_MULTI && env->kind != ERLFILL_ENV_SINGLE) return ERLFILL_ERR_ARG;
+    if (env->kind < 0 || env->kind > (ERLFILL_ENV_SINGLE | ERLFILL_ENV_ONBOARD)) return ERLFILL_ERR_ARG;
+    const bool onboard = (env->kind & ERLFILL_ENV_ONBOARD) != 0;
     const int rc = ensure_motor_table();
     if (rc != ERLFILL_OK) return rc;
     StepArgs a;
@@ -1395,7 +1453,11 @@ static int env_step_impl(const erlfill_env_batch *env, const float *d_actions, u
     a.warp_fast_mode = g_warp_fast_mode;
     const int block = pick_block(env->n_env);
     const int grid = (env->n_env + block - 1) / block;
-    if (a.d_u) {
+    if (onboard) {
+        // row N1: int()-truncated weight per tick -> thread-per-env tick loop (Philox or injected noise)
+        if (a.d_u) env_step_kernel<true, true><<<grid, block, 0, (cudaStream_t)stream>>>(a);
+        else env_step_kernel<false, true><<<grid, block, 0, (cudaStream_t)stream>>>(a);
+    } else if (a.d_u) {
         // injected binary64 noise is not on the 2^-31 grid: thread-per-env kernel, binary64 throughout
         env_step_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(a);
     } else if (g_env_step_mode == ERLFILL_SIM_THREAD_PER_ENV) {
@@ -1410,7 +1472,7 @@ static int env_step_impl(const erlfill_env_batch *env, const float *d_actions, u
             env_finish_kernel<<<(env->n_env + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
         }
     }
-    const bool fused_warp = !a.d_u && g_env_step_mode != ERLFILL_SIM_THREAD_PER_ENV && env->n_env <= resident_warp_slots();
+    const bool fused_warp = !onboard && !a.d_u && g_env_step_mode != ERLFILL_SIM_THREAD_PER_ENV && env->n_env <= resident_warp_slots();
     if (d_step_idx && !fused_warp) step_idx_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_step_idx);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;

@@ -29,17 +29,20 @@ class VecFillEnv:
     cond_id    : optional int32[N]; default env (env_id_base + i) uses condition (env_id_base + i) % len(conditions)
     kind       : "multi" (MutiConditionEnv reward) or "single" (WeightEnv reward v2)
     sim_mode   : "auto" | "warp" (one warp per env, integer hold phase) | "thread" (one thread per env)
+    onboard    : per tick the env classes' "on-board" motor / weight models (WeightEnv.py:176-229) instead of the offline controller's
     """
 
     SIM_MODES = {"auto": L.SIM_AUTO, "thread": L.SIM_THREAD_PER_ENV, "warp": L.SIM_WARP_PER_ENV,
                  "warp_windows": L.SIM_WARP_WINDOWS, "warp_reject_runs": L.SIM_WARP_REJECT_RUNS}   # last two: test hooks
 
     def __init__(self, conditions, n_env, kind="multi", max_steps=100, seed=0, device="cuda",
-                 env_id_base=0, cond_id=None, auto_reset=True, sim_mode="auto"):
+                 env_id_base=0, cond_id=None, auto_reset=True, sim_mode="auto", onboard=False):
         L.require_device()
         self.device = torch.device(device)
         self.n_env = int(n_env)
-        self.kind = {"multi": L.ENV_MULTI, "single": L.ENV_SINGLE}[kind]
+        # onboard: the env classes' own per-tick motor / weight models (speed cap, int()-truncated weight; SURVEY row N1)
+        self.onboard = bool(onboard)
+        self.kind = {"multi": L.ENV_MULTI, "single": L.ENV_SINGLE}[kind] | (L.ENV_ONBOARD if onboard else 0)
         self.max_steps = int(max_steps)
         self.seed = int(seed)
         self.env_id_base = int(env_id_base)
@@ -84,6 +87,8 @@ class VecFillEnv:
         with torch.cuda.device(self.device):
             if n > L.lib().erlfill_env_step_fused_max_envs():
                 raise ValueError("use_host_outputs: batch too large for the single-kernel step")
+        if self.onboard and n > 256:
+            raise ValueError("use_host_outputs: the on-board variant runs one kernel of one CTA per 32..128 envs; keep host outputs to small batches")
         buf = torch.zeros(40 * n, dtype=torch.uint8).pin_memory()
         self._host_buf = buf
         self.final_weight = buf[:8 * n].view(torch.float64)
@@ -186,7 +191,7 @@ class VecFillEnv:
             # when the batch runs as ONE fused kernel, whose outputs are written exactly once: include/erlfill.h).  1: reads
             # in place, outputs by copy.  Default: 2 when eligible, else 0; ERLFILL_STEP_HOST_MODE overrides (measurements).
             with torch.cuda.device(self.device):
-                fused = self.sim_mode != L.SIM_THREAD_PER_ENV and n <= L.lib().erlfill_env_step_fused_max_envs()
+                fused = (not self.onboard) and self.sim_mode != L.SIM_THREAD_PER_ENV and n <= L.lib().erlfill_env_step_fused_max_envs()
             zc = int(os.environ.get("ERLFILL_STEP_HOST_MODE", "2" if fused else "0"))
             if not fused:
                 zc = 0
@@ -245,7 +250,8 @@ class _ScalarEnvBase:
     """
     _kind = "multi"
 
-    def __init__(self, cfg, noise="reference", device="cuda", seed=0):
+    def __init__(self, cfg, noise="reference", device="cuda", seed=0, onboard=False):
+        self._onboard = bool(onboard)
         self.target_weight = cfg["target_weight"]
         self.target_weight_err = cfg["target_weight_err"]
         self.target_time = cfg["target_time"]
@@ -275,7 +281,7 @@ class _ScalarEnvBase:
             cfg = {"target_weight": self.target_weight, "target_weight_err": self.target_weight_err,
                    "target_time": self.target_time, "bounds": self.bounds}
             self._vec = VecFillEnv([cfg], 1, kind=self._kind, max_steps=self.max_steps, seed=self._seed,
-                                   device=self._device, auto_reset=False)
+                                   device=self._device, auto_reset=False, onboard=self._onboard)
             self._vec.use_host_outputs()
             self._rs = np.random.RandomState(0)            # scratch generator: its state is overwritten from `random` every step
             self._a_host = torch.zeros(1, 10, dtype=torch.float32).pin_memory()
@@ -352,19 +358,19 @@ class WeightEnv(_ScalarEnvBase):
     """Drop-in for WeightEnv.WeightEnv (WeightEnv.py:21-588), offline-simulator branch."""
     _kind = "single"
 
-    def __init__(self, noise="reference", device="cuda", seed=0):
-        super().__init__(K.SINGLE_25KG, noise=noise, device=device, seed=seed)
+    def __init__(self, noise="reference", device="cuda", seed=0, onboard=False):
+        super().__init__(K.SINGLE_25KG, noise=noise, device=device, seed=seed, onboard=onboard)
 
 
 class MultiConditionWeightEnv(_ScalarEnvBase):
     """Drop-in for MutiConditionEnv.MultiConditionWeightEnv (MutiConditionEnv.py:470-486)."""
     _kind = "multi"
 
-    def __init__(self, config=None, noise="reference", device="cuda", seed=0):
+    def __init__(self, config=None, noise="reference", device="cuda", seed=0, onboard=False):
         cfg = dict(K.MULTI_CLASS_DEFAULT)
         if config is not None:
             for k in ("target_weight", "target_weight_err", "target_time"):
                 cfg[k] = config.get(k, cfg[k])
             if "bounds" in config:
                 cfg["bounds"] = config["bounds"]
-        super().__init__(cfg, noise=noise, device=device, seed=seed)
+        super().__init__(cfg, noise=noise, device=device, seed=seed, onboard=onboard)

@@ -45,7 +45,13 @@ typedef enum {
 } erlfill_status;
 
 typedef enum { ERLFILL_ENV_MULTI = 0,   /* MutiConditionEnv.WeightEnv.step reward (MutiConditionEnv.py:376-436) */
-               ERLFILL_ENV_SINGLE = 1   /* WeightEnv.step reward v2 (WeightEnv.py:480-556) */
+               ERLFILL_ENV_SINGLE = 1,  /* WeightEnv.step reward v2 (WeightEnv.py:480-556) */
+               /* OR into the kind: per tick the env classes' "on-board" models instead of the offline
+                * controller's — motor_simulation with the speed cap `if current_speed < 10000` and weight_simulation with
+                * `int(current_weight + opening * (1 + u))` (WeightEnv.py:176-229, MutiConditionEnv.py:184-226) — under the same
+                * 3-stage threshold logic, first-tick delay and stop rules as E1.  One thread per env (no integer hold phase:
+                * the weight is truncated every tick); the fused host-buffer path does not apply. */
+               ERLFILL_ENV_ONBOARD = 2
 } erlfill_env_kind;
 
 /* One operating condition (experiment_runner.py:417-478).  bounds are in ACTION order:

@@ -20,6 +20,8 @@
  *   M1  EmotionModule.update (EmotionModule.py:121-162)
  *   A2  OUNoise.sample/anneal (ddpg_agent.py:762-785) and act()'s clip (:352-356)
  *   R1  action normalisation in remember (ddpg_agent.py:373-375)
+ *   N1  the on-board per-tick motor / weight models (WeightEnv.py:176-229, MutiConditionEnv.py:184-226)
+ *       under the same stage logic (kind | 2 in the env-step entry points)
  *   R2  uniform-priority index draw: searchsorted(cumsum(p)/last, u, 'right') == floor(u*n)
  *       for equal priorities (ddpg_agent.py:228-254)
  *
@@ -155,6 +157,91 @@ static int simulate_core(const int p[11], double sysdelay, orc_noise *nz, double
     *final_weight = w;
     if (tick_out) *tick_out = tick;
     return n;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* N1: the "on-board" per-tick models of the env classes (WeightEnv.py:176-229,            */
+/* MutiConditionEnv.py:184-226), driven by the stage logic of simulate_run above (in the     */
+/* reference the stage logic of this variant lives in an external PLC polled over Modbus,   */
+/* WeightEnv.py:245-331; the offline controller's own loop is the scripted stand-in).        */
+/*   motor_simulation: decelerate_time = speed / 100000 with NO `speed > 0` guard,          */
+/*     np.power(dt, 2) (== dt*dt for every reachable speed, tests/test_oracle_golden.py),    */
+/*     and the speed CAP: `if current_speed < motor_speed (10000): current_speed += 5000`.   */
+/*   weight_simulation: current_weight = int(current_weight + opening * (1.0 + u)):         */
+/*     truncation toward zero on every tick, no clamp at zero.                               */
+/* ------------------------------------------------------------------------------------ */
+static int simulate_core_onboard(const int p[11], double sysdelay, orc_noise *nz, double *total_time,
+                                 double *final_weight, int *tick_out) {
+    const double fast_pos = p[7], medium_pos = p[8], slow_pos = p[9];
+    const double fast_w = p[1], medium_w = p[2], slow_w = p[3];
+    double w = 0.0, open = 0.0, speed = 0.0, dir = 0.0;  /* WeightEnv.py:66-68,78 */
+    double target = fast_pos;
+    int delay_done = 0, tick = 0, iteration = 0, nochg = 0, n = 0;
+    double prev = 0.0;
+    for (;;) {
+        tick += 1;
+        /* motor_simulation(target): WeightEnv.py:188-218 */
+        double dt = speed / 100000;
+        double dd = 0.5 * 100000 * (dt * dt);
+        if (fabs(open - target) > 1) {
+            if (open < target) {
+                dir = 1.0;
+                if (open < target - dd) { if (speed < 10000) speed += 5000000 / 1000; }
+                else speed -= 100000 / 1000;
+            } else if (open > target) {
+                dir = -1.0;
+                if (open > dd) { if (speed < 10000) speed += 5000000 / 1000; }
+                else speed -= 100000 / 1000;
+            }
+        } else {
+            speed = 0.0; open = target;
+        }
+        open += (speed * dir) / 1000;
+        /* weight_simulation(open, 1.0): WeightEnv.py:228-229, int() truncates toward zero */
+        double u = noise_tick(nz, n);
+        n += 1;
+        w = trunc(w + open * (1.0 + u));
+        /* stage selection / first-tick delay / safety stops: VirtualWeightController.py:191-229 */
+        if (w < fast_w) {
+            target = fast_pos;
+            if (!delay_done) { tick += p[4]; delay_done = 1; w += target * sysdelay; }
+        } else if (w < medium_w) {
+            target = medium_pos;
+            if (!delay_done) { tick += p[5]; delay_done = 1; w += target * sysdelay; }
+        } else if (w < slow_w) {
+            target = slow_pos;
+            if (!delay_done) { tick += p[6]; delay_done = 1; w += target * sysdelay; }
+        } else {
+            break;
+        }
+        iteration += 1;
+        if (fabs(w - prev) < 0.01) nochg += 1; else nochg = 0;
+        prev = w;
+        if (iteration > 5000) break;
+        if (nochg > 500) break;
+    }
+    *total_time = (tick + p[10]) / 1000.0;
+    *final_weight = w;
+    if (tick_out) *tick_out = tick;
+    return n;
+}
+
+int orc_simulate_onboard_noise(const int p[11], double sysdelay, const double *u, int n_u,
+                               double *total_time, double *final_weight, int *tick_out) {
+    orc_noise nz; memset(&nz, 0, sizeof nz);
+    nz.u = u; nz.n_u = n_u; nz.cache_block = -1;
+    return simulate_core_onboard(p, sysdelay, &nz, total_time, final_weight, tick_out);
+}
+
+int orc_simulate_onboard_philox(const int p[11], uint32_t seed_lo, uint32_t seed_hi, uint32_t env_id,
+                                uint32_t step_idx, double *total_time, double *final_weight, int *tick_out) {
+    orc_noise nz; memset(&nz, 0, sizeof nz);
+    nz.seed_lo = seed_lo; nz.seed_hi = seed_hi; nz.env_id = env_id; nz.step_idx = step_idx;
+    nz.cache_block = -1;
+    uint32_t r[4];
+    orc_philox4x32(seed_lo, seed_hi, env_id, step_idx, 0u, ORC_STREAM_MISC, r);
+    const double sysdelay = 15.0 + 35.0 * u32_to_unit(r[0]);      /* uniform(15,50) */
+    return simulate_core_onboard(p, sysdelay, &nz, total_time, final_weight, tick_out);
 }
 
 int orc_simulate_run_noise(const int p[11], double sysdelay, const double *u, int n_u,
@@ -386,8 +473,9 @@ void orc_env_step_noise(int kind, const orc_condition *c, orc_env_state *st, int
                         orc_step_out *o) {
     clip_and_truncate(c, action, o->clipped, o->iparams);
     double tt, fw;
-    o->ticks = orc_simulate_run_noise(o->iparams, sysdelay, u, n_u, &tt, &fw, NULL);
-    finish_step(kind, c, st, max_steps, fw, tt, o);
+    o->ticks = (kind & 2) ? orc_simulate_onboard_noise(o->iparams, sysdelay, u, n_u, &tt, &fw, NULL)
+                          : orc_simulate_run_noise(o->iparams, sysdelay, u, n_u, &tt, &fw, NULL);
+    finish_step(kind & 1, c, st, max_steps, fw, tt, o);
 }
 
 void orc_env_step_philox(int kind, const orc_condition *c, orc_env_state *st, int max_steps,
@@ -395,8 +483,9 @@ void orc_env_step_philox(int kind, const orc_condition *c, orc_env_state *st, in
                          uint32_t env_id, uint32_t step_idx, orc_step_out *o) {
     clip_and_truncate(c, action, o->clipped, o->iparams);
     double tt, fw;
-    o->ticks = orc_simulate_run_philox(o->iparams, seed_lo, seed_hi, env_id, step_idx, &tt, &fw, NULL);
-    finish_step(kind, c, st, max_steps, fw, tt, o);
+    o->ticks = (kind & 2) ? orc_simulate_onboard_philox(o->iparams, seed_lo, seed_hi, env_id, step_idx, &tt, &fw, NULL)
+                          : orc_simulate_run_philox(o->iparams, seed_lo, seed_hi, env_id, step_idx, &tt, &fw, NULL);
+    finish_step(kind & 1, c, st, max_steps, fw, tt, o);
 }
 
 /* E4 reset, cold-start branch: raw = f32([U(0,err), U(0,T)]); state = f32 divisions [f32]. */

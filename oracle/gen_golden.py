@@ -155,6 +155,82 @@ def gen_sim():
           "peak speed", peak_speed.max())
 
 
+def gen_onboard():
+    """Row N1 known-answer vectors.  The on-board per-tick models are methods of the env classes (WeightEnv.py:176-229,
+    MutiConditionEnv.py:184-226); in the reference their stage logic runs in an external PLC polled over Modbus, so the
+    scripted stand-in is the reference's OWN offline loop: VirtualWeightController.simulate_run is run unmodified on a
+    subclass whose two per-tick methods and three state attributes forward to a real env instance."""
+    V = ref_shim.install()
+    import WeightEnv as W
+    import MutiConditionEnv as M
+
+    def controller_on(env):
+        class Onboard(V.VirtualWeightController):
+            curr_weight = property(lambda self: env.current_weight, lambda self, v: setattr(env, "current_weight", v))
+            current_opening = property(lambda self: env.current_opening, lambda self, v: setattr(env, "current_opening", v))
+            current_speed = property(lambda self: env.current_speed, lambda self, v: setattr(env, "current_speed", v))
+
+            def motor_simulation(self, target_pos):
+                env.motor_simulation(target_pos)
+
+            def weight_simulation(self, opening):
+                env.weight_simulation(opening, env.material_coefficient)
+        return Onboard()
+
+    rng = np.random.RandomState(4321)
+    cases = []
+    with _quiet():
+        envs = {"single": W.WeightEnv(), "multi": M.MultiConditionWeightEnv(None)}
+    for name, cfg in BOUNDS.items():
+        which = "single" if name == "single_25kg" else "multi"
+        for _ in range(40):
+            p = {"target_weight": cfg["target_weight"]}
+            for k, (lo, hi) in cfg["bounds"].items():
+                p[k] = int(rng.randint(lo, hi + 1))
+            cases.append((which, p, int(rng.randint(0, 2**31 - 1))))
+    # outside the shipped bounds: long moves where the 10000 speed cap binds, a reversing motor, tiny / zero openings
+    # (stagnation stop), an unreachable threshold (iteration cap), a reachable medium stage
+    edge = [
+        dict(target_weight=90000, fast_weight=60000, medium_weight=0, slow_weight=89000, fast_delay=0, medium_delay=0, slow_delay=0,
+             fast_opening=100, medium_opening=4, slow_opening=3, unload_delay=0),
+        dict(target_weight=25000, fast_weight=8000, medium_weight=16000, slow_weight=24900, fast_delay=120, medium_delay=130,
+             slow_delay=140, fast_opening=250, medium_opening=30, slow_opening=6, unload_delay=333),
+        dict(target_weight=25000, fast_weight=8000, medium_weight=16000, slow_weight=24900, fast_delay=120, medium_delay=130,
+             slow_delay=140, fast_opening=20, medium_opening=60, slow_opening=90, unload_delay=333),
+        dict(target_weight=25000, fast_weight=12000, medium_weight=0, slow_weight=24950, fast_delay=200, medium_delay=150,
+             slow_delay=150, fast_opening=0, medium_opening=4, slow_opening=12, unload_delay=400),
+        dict(target_weight=25000, fast_weight=12000, medium_weight=0, slow_weight=24950, fast_delay=200, medium_delay=150,
+             slow_delay=150, fast_opening=1, medium_opening=4, slow_opening=1, unload_delay=400),
+        dict(target_weight=25000, fast_weight=2000, medium_weight=0, slow_weight=24950, fast_delay=200, medium_delay=150,
+             slow_delay=150, fast_opening=50, medium_opening=4, slow_opening=2, unload_delay=400),
+        dict(target_weight=500, fast_weight=0, medium_weight=0, slow_weight=0, fast_delay=1, medium_delay=2, slow_delay=3,
+             fast_opening=50, medium_opening=4, slow_opening=3, unload_delay=7),
+    ]
+    for i, p in enumerate(edge):
+        for s in (7, 8):
+            cases.append(("single" if i % 2 else "multi", dict(p), 2000 + 10 * i + s))
+    n = len(cases)
+    out = dict(params=np.zeros((n, 11), np.int32), seeds=np.zeros(n, np.int64), iters=np.zeros(n, np.int32),
+               total_time=np.zeros(n), final_weight=np.zeros(n), peak_speed=np.zeros(n), min_speed=np.zeros(n),
+               env=np.array([c[0] for c in cases]))
+    for i, (which, p, s) in enumerate(cases):
+        env = envs[which]
+        env.current_weight = 0; env.current_speed = 0; env.current_opening = 0       # WeightEnv.reset (:141-143)
+        c = controller_on(env)
+        random.seed(s)
+        c.reset()
+        c.load_params(p)
+        with _quiet():
+            speeds, openings, weights, tt, fw = c.simulate_run()
+        out["params"][i] = [p[k] for k in PARAM_ORDER]
+        out["seeds"][i], out["iters"][i], out["total_time"][i], out["final_weight"][i] = s, len(weights), tt, fw
+        out["peak_speed"][i], out["min_speed"][i] = max(speeds), min(speeds)
+    out["meta"] = _meta("N1 on-board motor_simulation / weight_simulation of the env classes under simulate_run's stage logic")
+    np.savez_compressed(os.path.join(GOLD, "onboard_golden.npz"), **out)
+    print("onboard:", n, "cases; iters min/mean/max", out["iters"].min(), out["iters"].mean(), out["iters"].max(),
+          "speed range", out["min_speed"].min(), out["peak_speed"].max())
+
+
 # ----------------------------------------------------------------------------------------
 def _make_env(kind, name):
     ref_shim.install()
@@ -730,4 +806,5 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["sim", "env", "emotion"]
     os.chdir("/tmp")
     for w in which:
-        {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion, "nets": gen_nets, "learn": gen_learn, "td3sac": gen_td3sac, "loop": gen_loop, "esac": gen_esac}[w]()
+        {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion, "nets": gen_nets, "learn": gen_learn, "td3sac": gen_td3sac, "loop": gen_loop, "esac": gen_esac,
+         "onboard": gen_onboard}[w]()

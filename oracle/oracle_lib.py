@@ -14,6 +14,7 @@ _SO = os.path.join(_HERE, "_build", "liberlfill_oracle.so")
 
 RING = 20
 ENV_MULTI, ENV_SINGLE = 0, 1
+ENV_ONBOARD = 2      # OR into the kind: the on-board per-tick motor / weight models (row N1) instead of the offline controller's
 ACTION_ORDER = ["fast_weight", "medium_weight", "slow_weight", "fast_opening", "medium_opening",
                 "slow_opening", "fast_delay", "medium_delay", "slow_delay", "unload_delay"]
 
@@ -82,6 +83,16 @@ def simulate_run_noise(params, sysdelay, u):
     tt, fw, tick = C.c_double(), C.c_double(), C.c_int()
     n = lib().orc_simulate_run_noise(p, C.c_double(sysdelay), u.ctypes.data_as(C.POINTER(C.c_double)),
                                      C.c_int(len(u)), C.byref(tt), C.byref(fw), C.byref(tick))
+    return n, tt.value, fw.value, tick.value
+
+
+def simulate_onboard_noise(params, sysdelay, u):
+    """Row N1: the env classes' on-board motor_simulation / weight_simulation under simulate_run's stage logic."""
+    p = (C.c_int * 11)(*[int(x) for x in params])
+    u = np.ascontiguousarray(u, np.float64)
+    tt, fw, tick = C.c_double(), C.c_double(), C.c_int()
+    n = lib().orc_simulate_onboard_noise(p, C.c_double(sysdelay), u.ctypes.data_as(C.POINTER(C.c_double)),
+                                         C.c_int(len(u)), C.byref(tt), C.byref(fw), C.byref(tick))
     return n, tt.value, fw.value, tick.value
 
 

@@ -184,3 +184,33 @@ def test_python_port_matches_golden(golden_dir):
         p = {k: int(v) for k, v in zip(names, g["params"][i])}
         n, tt, fw = py_port.simulate_run(p, random.Random(int(g["seeds"][i])))
         assert (n, tt, fw) == (int(g["iters"][i]), g["total_time"][i], g["final_weight"][i])
+
+
+def test_np_power_equals_mul_for_onboard_speeds():
+    # WeightEnv.py:189 / MutiConditionEnv.py:192 use np.power(decelerate_time, 2); the oracle and the CUDA kernel use dt*dt.
+    # With the speed cap the on-board motor never exceeds 10000 + 4900; checked far beyond, both signs.
+    for k in range(-400, 401):
+        dt = float(k * 100) / 100000
+        assert float(0.5 * 100000 * np.power(dt, 2)) == 50000.0 * (dt * dt)
+
+
+def test_onboard_golden_bit_exact(golden_dir):
+    """Row N1: the reference's own simulate_run driving the env classes' on-board motor_simulation / weight_simulation
+    (oracle/gen_golden.py onboard) against oracle/erlfill_oracle.c:simulate_core_onboard."""
+    g = np.load(os.path.join(golden_dir, "onboard_golden.npz"))
+    assert g["peak_speed"].max() == 10000.0                # the speed cap binds in the fixtures
+    stops = {"cap": 0, "stagnant": 0, "normal": 0}
+    differs = 0
+    for i in range(len(g["seeds"])):
+        rng = random.Random(int(g["seeds"][i]))
+        sysdelay = 15 + (50 - 15) * rng.random()
+        u = _stream(rng, int(g["iters"][i]) + 8)
+        n, tt, fw, tick = O.simulate_onboard_noise(g["params"][i], sysdelay, u)
+        assert n == int(g["iters"][i]), (i, n, g["iters"][i])
+        assert tt == g["total_time"][i], i
+        assert fw == g["final_weight"][i], i
+        stops["cap" if n == 5001 else "stagnant" if n <= 502 and fw < 1 else "normal"] += 1
+        n0, tt0, fw0, _ = O.simulate_run_noise(g["params"][i], sysdelay, u)          # the offline controller on the same noise
+        differs += (n0, fw0) != (n, fw)
+    assert stops["cap"] > 0 and stops["stagnant"] > 0 and stops["normal"] > 150
+    assert differs > 150                                   # int() truncation makes it a different trajectory, not a relabelling
