@@ -79,10 +79,18 @@ class DDPGNets(C.Structure):
                                            "critic_m", "critic_v", "scale", "offset")]
 
 
+class DDPGMasks(C.Structure):
+    _fields_ = [("keep", C.c_void_p * 10)]
+
+
+PRECISION_EXACT, PRECISION_FAST = 0, 1
+
+
 class DDPGHyper(C.Structure):
     _fields_ = [("batch", C.c_int32), ("adam_step", C.c_int32), ("gamma", C.c_float), ("tau", C.c_float),
                 ("max_grad_norm", C.c_float), ("n_cond", C.c_int32), ("critic_lr", C.c_double),
-                ("actor_lr", C.c_double), ("lr_decay", C.c_double)]
+                ("actor_lr", C.c_double), ("lr_decay", C.c_double), ("precision", C.c_int32), ("dropout_mode", C.c_int32),
+                ("seed", C.c_uint64), ("update_idx", C.c_uint32), ("rank", C.c_uint32), ("masks", C.c_void_p)]
 
 
 class TD3Nets(C.Structure):
@@ -129,7 +137,7 @@ EXPORTS = [
     "erlfill_actor_forward", "erlfill_actor_forward_cond", "erlfill_replay_insert_cond", "erlfill_emotion_update", "erlfill_episode_end", "erlfill_emotion_forward",
     "erlfill_emotion_tc_image_bytes", "erlfill_emotion_tc_pack", "erlfill_emotion_forward_tc",
     "erlfill_replay_insert", "erlfill_replay_sample", "erlfill_replay_gather",
-    "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_set_step", "erlfill_ddpg_update",
+    "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_set_step", "erlfill_ddpg_update", "erlfill_ddpg_pack_images",
     "erlfill_ddpg_exchange_buffers", "erlfill_ddpg_update_launches", "erlfill_ddpg_peer_launches", "erlfill_peer_ctrl_bytes", "erlfill_peer_alloc", "erlfill_peer_open", "erlfill_peer_close",
     "erlfill_peer_free", "erlfill_ddpg_peer_allreduce", "erlfill_peer_error",
     "erlfill_t1_workspace_bytes", "erlfill_t1_act_workspace_bytes", "erlfill_t1_grad_buckets", "erlfill_td3_act",

@@ -32,7 +32,8 @@ class VecERDDPG:
         if state_dicts is None:
             state_dicts = init.er_ddpg_state_dicts(bounds, seed=seed)
         actor_sd, critic_sd, trans_sd = state_dicts
-        self.learner = ddpg.DDPGLearner(actor_sd, critic_sd, device=self.device, batch_size=batch_size, precision=update_precision)
+        self.learner = ddpg.DDPGLearner(actor_sd, critic_sd, device=self.device, batch_size=batch_size, precision=update_precision,
+                                        dropout=dropout, seed=seed, rank=rank)
         self.transformer = nets.TransformerParams(trans_sd, device=self.device)
         self.emotion_precision = emotion_precision
         self.memory = ddpg.ReplayBuffer(memory_size, device=self.device)

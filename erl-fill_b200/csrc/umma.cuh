@@ -103,6 +103,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
 // ---- descriptors ------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, no swizzle, K-major.  Element (row r, k) of the operand lives at
 //   base + (r/8)*sbo + (k/8)*lbo + (r%8)*16 + (k%8)*2      (bf16; 8x8 core matrices of 128 contiguous bytes)
@@ -121,6 +128,14 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
            | (1u << 7)               // A format  = BF16
            | (1u << 10)              // B format  = BF16
            | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// The same with MN-major ("transposed") operands: bit 15 = A is MN-major, bit 16 = B is MN-major.  An MN-major operand is the
+// second reading of a row-major image X[k][mn] (8 x 8 core matrices, mn contiguous inside a 16-byte row): its descriptor takes
+// LBO = byte stride between 8-row groups of k, SBO = 128 (next 8 mn), and one MMA (K = 16) advances the start address by 2 * LBO
+// (validated on B200 by tools/umma_mn_probe.cu, profiles/r02a_umma_mn_probe.txt).
+__host__ __device__ constexpr uint32_t instr_desc_bf16_major(int M, int N, int a_mn, int b_mn) {
+    return instr_desc_bf16(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread

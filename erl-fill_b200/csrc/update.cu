@@ -21,12 +21,16 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "ddpg_dropout.cuh"
 #include "mlp.cuh"
 #include "fused_mlp.cuh"
 
 namespace erlfill {
 using namespace mlp;
 using namespace fused;
+using ddrop::Drop;
+using ddrop::keep1;
+using ddrop::kDropScale;
 
 // ---- flat layouts (parameters() order) -------------------------------------------------------
 namespace AO { constexpr int EW = 0, W1 = 30, B1 = 670, W2 = 798, B2 = 17182, W3 = 17310, B3 = 25502, W4 = 25566, B4 = 26206, TOTAL = 26216; }
@@ -171,7 +175,7 @@ constexpr int kAPartEW = 0, kAPartB4 = 32, kAPartB3 = 48, kAPartB2 = 112, kAPart
 // memory (what the backward needs) when the pointers are set.  Warp w owns rows kRowsPerWarp*w ...
 constexpr int kRowsPerWarp = TM / (NTHR / 32);
 __device__ __forceinline__ void ln_act_tile(float *z_s, const float *gamma, const float *beta, int act, int row0, int B,
-                                            float *xhat_g, float *rstd_g, float *h_g) {
+                                            float *xhat_g, float *rstd_g, float *h_g, const Drop &dr, int site) {
     const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
     float gm[8], bt[8];
 #pragma unroll
@@ -198,6 +202,7 @@ __device__ __forceinline__ void ln_act_tile(float *z_s, const float *gamma, cons
             const float xh = (v[i] - mean) * rstd;
             float y = xh * gm[i] + bt[i];
             y = act == ACT_LEAKY ? (y > 0.f ? y : 0.1f * y) : fmaxf(y, 0.f);
+            if (dr.mode != ERLFILL_DROPOUT_OFF) y = keep1(dr, site, gr < B ? gr : 0, c, 256) ? y * kDropScale : 0.f;   // nn.Dropout(0.2), train()
             z_s[r * LDA + c] = y;
             if (gr < B) {
                 if (xhat_g) xhat_g[(size_t)gr * 256 + c] = xh;
@@ -211,6 +216,7 @@ __device__ __forceinline__ void ln_act_tile(float *z_s, const float *gamma, cons
 // Critic.forward for the CTA's rows (ddpg_agent.py:163-183).  The input row [state(2) | action(10) | emotion standardised(3) | 0]
 // is assembled here:  mode 0: (s, stored normalised action, e)   mode 1: (s', actions_ext, 0) [target]   mode 2: (s, actions_ext, e)
 struct CriticFwdArgs {
+    Drop drop;
     int B, mode, save;
     const float *batch, *actions_ext, *stats, *P;
     float *x0, *xhat1, *h1, *rstd1, *xhat2, *h2, *rstd2, *h3, *q;
@@ -238,14 +244,17 @@ __global__ void __launch_bounds__(NTHR) critic_fwd_kernel(const CriticFwdArgs a)
         for_each_out<256>(acc, 256, [&](int r, int c, float v) { bufB[r * LDA + c] = v + P[CO::B0 + c]; });
     }
     __syncthreads();
-    ln_act_tile(bufB, P + CO::G1, P + CO::BE1, ACT_LEAKY, row0, B, a.save ? a.xhat1 : nullptr, a.save ? a.rstd1 : nullptr, a.save ? a.h1 : nullptr);
+    const int site0 = a.mode == 0 ? 4 : (a.mode == 1 ? 2 : 8);       // dropout sites of this forward (ddpg_dropout.cuh)
+    ln_act_tile(bufB, P + CO::G1, P + CO::BE1, ACT_LEAKY, row0, B, a.save ? a.xhat1 : nullptr, a.save ? a.rstd1 : nullptr, a.save ? a.h1 : nullptr,
+                a.drop, site0);
     {   // Linear(256, 256) -> LayerNorm -> ReLU
         float acc[2][Cols<256>::NTW][4];
         dense<256, 256, false>(acc, bufB, P + CO::W4, 256, 256, 256, wst, 4);
         for_each_out<256>(acc, 256, [&](int r, int c, float v) { bufA[r * LDA + c] = v + P[CO::B4 + c]; });
     }
     __syncthreads();
-    ln_act_tile(bufA, P + CO::G2, P + CO::BE2, ACT_RELU, row0, B, a.save ? a.xhat2 : nullptr, a.save ? a.rstd2 : nullptr, a.save ? a.h2 : nullptr);
+    ln_act_tile(bufA, P + CO::G2, P + CO::BE2, ACT_RELU, row0, B, a.save ? a.xhat2 : nullptr, a.save ? a.rstd2 : nullptr, a.save ? a.h2 : nullptr,
+                a.drop, site0 + 1);
     {   // Linear(256, 128) -> ReLU
         float acc[2][Cols<128>::NTW][4];
         dense<256, 128, false>(acc, bufA, P + CO::W8, 256, 128, 256, wst, 4);
@@ -272,6 +281,7 @@ __global__ void __launch_bounds__(NTHR) critic_fwd_kernel(const CriticFwdArgs a)
 // Actor.forward for the CTA's rows (ddpg_agent.py:73-122) -> physical-unit actions.  Input row [state | emotion | 0]; mode 1:
 // (s', next_emotion broadcast) for the target.  keep: store what the backward needs.
 struct ActorFwdArgs {
+    Drop drop;
     int B, mode, keep, n_cond;
     const float *batch, *next_emotion, *P, *scale, *offset;
     float *out, *xa, *a1, *a2, *a3, *z4, *aux;
@@ -300,6 +310,7 @@ __global__ void __launch_bounds__(NTHR) actor_fwd_kernel(const ActorFwdArgs a) {
         for_each_out<128>(acc, 128, [&](int r, int c, float v) {
             v += P[AO::B1 + c];
             v = v > 0.f ? v : 0.1f * v;
+            if (a.drop.mode != ERLFILL_DROPOUT_OFF) v = keep1(a.drop, a.mode == 1 ? 0 : 6, row0 + r < B ? row0 + r : 0, c, 128) ? v * kDropScale : 0.f;
             bufB[r * LDA + c] = v;
             if (a.keep && row0 + r < B) a.a1[(size_t)(row0 + r) * 128 + c] = v;
         });
@@ -309,6 +320,7 @@ __global__ void __launch_bounds__(NTHR) actor_fwd_kernel(const ActorFwdArgs a) {
         dense<128, 128, false>(acc, bufB, P + AO::W2, 128, 128, 128, wst, 2);
         for_each_out<128>(acc, 128, [&](int r, int c, float v) {
             v = fmaxf(v + P[AO::B2 + c], 0.f);
+            if (a.drop.mode != ERLFILL_DROPOUT_OFF) v = keep1(a.drop, a.mode == 1 ? 1 : 7, row0 + r < B ? row0 + r : 0, c, 128) ? v * kDropScale : 0.f;
             bufA[r * LDA + c] = v;
             if (a.keep && row0 + r < B) a.a2[(size_t)(row0 + r) * 128 + c] = v;
         });
@@ -355,7 +367,7 @@ __global__ void __launch_bounds__(NTHR) actor_fwd_kernel(const ActorFwdArgs a) {
 // backward of (LayerNorm + activation) on the tile.  In: dh in d_s, xhat in x_s.  Out: dz in x_s (and global when dz_g),
 // per-CTA column sums [sum dz | sum dy*xhat | sum dy] to part[0:256 | 256:512 | 512:768] when part is set.
 __device__ __forceinline__ void ln_act_bwd_tile(float *d_s, float *x_s, float *stat_s, const float *gamma, const float *beta, int act,
-                                                const float *rstd_g, int row0, int B, float *dz_g, float *part) {
+                                                const float *rstd_g, int row0, int B, float *dz_g, float *part, const Drop &dr, int site) {
     const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
     float gmr[8], btr[8];
 #pragma unroll
@@ -371,6 +383,7 @@ __device__ __forceinline__ void ln_act_bwd_tile(float *d_s, float *x_s, float *s
             const float xh = x_s[r * LDA + c];
             const float y = xh * gmr[i] + btr[i];
             float g = d_s[r * LDA + c];
+            if (dr.mode != ERLFILL_DROPOUT_OFF) g = keep1(dr, site, row0 + r < B ? row0 + r : 0, c, 256) ? g * kDropScale : 0.f;
             g *= act == ACT_LEAKY ? (y > 0.f ? 1.f : 0.1f) : (y > 0.f ? 1.f : 0.f);
             d_s[r * LDA + c] = g;                                  // dy
             const float dxh = g * gmr[i];
@@ -410,7 +423,8 @@ __device__ __forceinline__ void ln_act_bwd_tile(float *d_s, float *x_s, float *s
 // the CTA's rows.  grads != 0: also dz1/dz2/dz3 to global (operands of the weight-gradient GEMMs) and the per-CTA column
 // partial sums (bias, LayerNorm and head gradients) to cpart[cta].  dx0 -> g16 [B][16].
 struct CriticBwdArgs {
-    int B, grads;
+    Drop drop;
+    int B, grads, site0;
     float dq_const;
     const float *P, *dq, *h3, *xhat2, *rstd2, *xhat1, *rstd1;
     float *dz3, *dz2, *dz1, *g16, *cpart;
@@ -467,7 +481,7 @@ __global__ void __launch_bounds__(NTHR) critic_bwd_kernel(const CriticBwdArgs a)
     cp_async_wait<1>();                              // xhat2 tile (the older group)
     __syncthreads();
     ln_act_bwd_tile(bufB, bufC, stat_s, P + CO::G2, P + CO::BE2, ACT_RELU, a.rstd2, row0, B, a.grads ? a.dz2 : nullptr,
-                    part ? part + kCPartB : nullptr);
+                    part ? part + kCPartB : nullptr, a.drop, a.site0 + 1);
     {   // dh1 = dz2 W4
         float acc[2][Cols<256>::NTW][4];
         dense<256, 256, true>(acc, bufC, P + CO::W4, 256, 256, 256, wst, 4);
@@ -475,7 +489,7 @@ __global__ void __launch_bounds__(NTHR) critic_bwd_kernel(const CriticBwdArgs a)
     }
     __syncthreads();                                 // (dense drained every cp.async group, the xhat1 tile included)
     ln_act_bwd_tile(bufB, bufA, stat_s, P + CO::G1, P + CO::BE1, ACT_LEAKY, a.rstd1, row0, B, a.grads ? a.dz1 : nullptr,
-                    part ? part + kCPartA : nullptr);
+                    part ? part + kCPartA : nullptr, a.drop, a.site0);
     {   // dx0[:, :15] = dz1 W0
         float acc[2][1][4];
         dense<256, 16, true>(acc, bufA, P + CO::W0, 15, 15, 256, wst, 0);
@@ -489,6 +503,7 @@ __global__ void __launch_bounds__(NTHR) critic_bwd_kernel(const CriticBwdArgs a)
 // -0.03 * mean_rows(std_unbiased(out, dim=1)) -> dz4 .. dz1 to global (operands of the weight-gradient GEMMs) and the per-CTA
 // partial sums of d(emotion_weights) and the bias gradients to apart[cta].
 struct ActorBwdArgs {
+    Drop drop;
     int B;
     const float *P, *g16, *out, *aux, *xa, *scale, *z4, *a3, *a2, *a1;
     float *gz4, *ga64, *ga128a, *ga128b, *apart;
@@ -567,7 +582,8 @@ __global__ void __launch_bounds__(NTHR) actor_bwd_kernel(const ActorBwdArgs a) {
         dense<64, 128, true>(acc, bufB, P + AO::W3, 128, 128, 64, wst, 2);
         for_each_out<128>(acc, 128, [&](int r, int c, float v) {
             const int gr = row0 + r;
-            v = (gr < B && a.a2[(size_t)gr * 128 + c] > 0.f) ? v : 0.f;
+            // a2 is the dropped activation: > 0 only where the unit was kept and relu passed; kept units carry the 1 / 0.8 scale
+            v = (gr < B && a.a2[(size_t)gr * 128 + c] > 0.f) ? (a.drop.mode != ERLFILL_DROPOUT_OFF ? v * kDropScale : v) : 0.f;
             bufA[r * LDA + c] = v;
             if (gr < B) a.ga128a[(size_t)gr * 128 + c] = v;
         });
@@ -583,7 +599,8 @@ __global__ void __launch_bounds__(NTHR) actor_bwd_kernel(const ActorBwdArgs a) {
         dense<128, 128, true>(acc, bufA, P + AO::W2, 128, 128, 128, wst, 2);
         for_each_out<128>(acc, 128, [&](int r, int c, float v) {
             const int gr = row0 + r;
-            v = gr < B ? (a.a1[(size_t)gr * 128 + c] > 0.f ? v : 0.1f * v) : 0.f;
+            v = gr < B ? (a.a1[(size_t)gr * 128 + c] > 0.f ? v : 0.1f * v) : 0.f;      // kept units keep the sign of z1
+            if (a.drop.mode != ERLFILL_DROPOUT_OFF) v = (gr < B && keep1(a.drop, 6, gr, c, 128)) ? v * kDropScale : 0.f;
             bufB[r * LDA + c] = v;
             if (gr < B) a.ga128b[(size_t)gr * 128 + c] = v;
         });
@@ -641,14 +658,14 @@ static cudaError_t fused_smem_optin() {
     done = true;
     return cudaSuccess;
 }
-static void critic_forward(cudaStream_t st, const Ws &w, int B, int mode, const float *batch, const float *actions_ext, const float *P,
+static void critic_forward(cudaStream_t st, const Ws &w, const Drop &dr, int B, int mode, const float *batch, const float *actions_ext, const float *P,
                            float *q_out, bool save) {
-    const CriticFwdArgs a{B, mode, save ? 1 : 0, batch, actions_ext, w.stats, P, w.x0, w.xhat1, w.h1, w.rstd1, w.xhat2, w.h2, w.rstd2, w.h3, q_out};
+    const CriticFwdArgs a{dr, B, mode, save ? 1 : 0, batch, actions_ext, w.stats, P, w.x0, w.xhat1, w.h1, w.rstd1, w.xhat2, w.h2, w.rstd2, w.h3, q_out};
     critic_fwd_kernel<<<n_tiles(B), NTHR, kFusedSmem, st>>>(a);
 }
-static void actor_forward(cudaStream_t st, const Ws &w, int B, int mode, const float *batch, const float *next_emotion, const float *P,
+static void actor_forward(cudaStream_t st, const Ws &w, const Drop &dr, int B, int mode, const float *batch, const float *next_emotion, const float *P,
                           const float *scale, const float *offset, float *out, bool keep, int n_cond) {
-    const ActorFwdArgs a{B, mode, keep ? 1 : 0, n_cond, batch, next_emotion, P, scale, offset, out, w.xa, w.a1, w.a2, w.a3, w.z4, w.aux};
+    const ActorFwdArgs a{dr, B, mode, keep ? 1 : 0, n_cond, batch, next_emotion, P, scale, offset, out, w.xa, w.a1, w.a2, w.a3, w.z4, w.aux};
     actor_fwd_kernel<<<n_tiles(B), NTHR, kFusedSmem, st>>>(a);
 }
 // the grouped weight-gradient GEMMs and the one reduction launch that finishes every parameter gradient of a network
@@ -682,6 +699,16 @@ struct GradPlan {
     }
 };
 
+// the tcgen05 path (update_tc.cu) keeps its weight images, scratch and partials behind this workspace
+namespace utc {
+struct Head { float *cgrad, *agrad, *cred, *ared, *stats, *scal, *ssq, *step; };
+size_t tail_bytes(int B);
+int pack_images(const erlfill_ddpg_nets *n, uint8_t *tail_base, int B, cudaStream_t st);
+int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const float *d_batch, const float *d_next_emotion, const Head &w,
+                uint8_t *tail_base, int phases, float *d_report, cudaStream_t st);
+}  // namespace utc
+static size_t exact_bytes(int batch) { return (carve(nullptr, nullptr, batch) * sizeof(float) + 255) & ~(size_t)255; }
+
 }  // namespace erlfill
 
 using namespace erlfill;
@@ -690,10 +717,15 @@ extern "C" {
 
 size_t erlfill_ddpg_workspace_bytes(int batch) {
     if (batch < 2) return 0;
-    return carve(nullptr, nullptr, batch) * sizeof(float);
+    return exact_bytes(batch) + utc::tail_bytes(batch);
 }
 
-int erlfill_ddpg_update_launches(int fast) { return fast ? 0 : 24; }
+int erlfill_ddpg_pack_images(const erlfill_ddpg_nets *n, void *d_workspace, int batch, void *stream) {
+    if (!n || !d_workspace || batch < 2 || !n->actor || !n->actor_target || !n->critic || !n->critic_target) return ERLFILL_ERR_ARG;
+    return utc::pack_images(n, (uint8_t *)d_workspace + exact_bytes(batch), batch, (cudaStream_t)stream);
+}
+
+int erlfill_ddpg_update_launches(int fast) { return fast ? 6 : 24; }
 
 int erlfill_ddpg_grad_buckets(void *d_workspace, int batch, float **critic_grad, int *critic_len, float **actor_grad, int *actor_len) {
     if (!d_workspace || batch < 2) return ERLFILL_ERR_ARG;
@@ -749,18 +781,31 @@ int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h,
         if (rc != ERLFILL_OK) return rc;
     }
 
+    if (h->precision == ERLFILL_PRECISION_FAST) {
+        const utc::Head hd{w.cgrad, w.agrad, w.cred, w.ared, w.stats, w.scal, w.ssq, w.step};
+        return utc::update_fast(n, h, d_batch, d_next_emotion, hd, (uint8_t *)d_workspace + exact_bytes(B), phases, d_report, st);
+    }
+    if (h->precision != ERLFILL_PRECISION_EXACT) return ERLFILL_ERR_ARG;
+    Drop dr;
+    dr.mode = h->dropout_mode;
+    dr.k0 = (uint32_t)h->seed; dr.k1 = (uint32_t)(h->seed >> 32); dr.update_idx = h->update_idx; dr.row_base = h->rank << 20;
+    if (dr.mode == ERLFILL_DROPOUT_MASK && !h->masks) return ERLFILL_ERR_ARG;
+    for (int s = 0; s < 10; ++s) {
+        dr.m[s] = dr.mode == ERLFILL_DROPOUT_MASK ? h->masks->keep[s] : nullptr;
+        if (dr.mode == ERLFILL_DROPOUT_MASK && !dr.m[s]) return ERLFILL_ERR_ARG;
+    }
     ERLFILL_CUDA_TRY(fused_smem_optin());
     const int nt = n_tiles(B);
 
     if (phases & ERLFILL_PHASE_CRITIC_GRAD) {
         emotion_stats_kernel<<<1, 1024, 0, st>>>(B, d_batch, w.stats, w.cgrad + CO::TOTAL);
         // target: a' = actor_target(s', e'), Q' = critic_target(s', a', 0)
-        actor_forward(st, w, B, 1, d_batch, d_next_emotion, n->actor_target, n->scale, n->offset, w.atgt, false, h->n_cond);
-        critic_forward(st, w, B, 1, d_batch, w.atgt, n->critic_target, w.tq, false);
+        actor_forward(st, w, dr, B, 1, d_batch, d_next_emotion, n->actor_target, n->scale, n->offset, w.atgt, false, h->n_cond);
+        critic_forward(st, w, dr, B, 1, d_batch, w.atgt, n->critic_target, w.tq, false);
         // Q(s, a_norm, e) and its gradient
-        critic_forward(st, w, B, 0, d_batch, nullptr, n->critic, w.q, true);
+        critic_forward(st, w, dr, B, 0, d_batch, nullptr, n->critic, w.q, true);
         critic_loss_kernel<<<1, 1024, 0, st>>>(B, d_batch, w.q, w.tq, h->gamma, w.dq, w.scal + 4);
-        const CriticBwdArgs ba{B, 1, 0.f, n->critic, w.dq, w.h3, w.xhat2, w.rstd2, w.xhat1, w.rstd1, w.dz3, w.dz2, w.dz1, w.g16, w.cpart};
+        const CriticBwdArgs ba{dr, B, 1, 4, 0.f, n->critic, w.dq, w.h3, w.xhat2, w.rstd2, w.xhat1, w.rstd1, w.dz3, w.dz2, w.dz1, w.g16, w.cpart};
         critic_bwd_kernel<<<nt, NTHR, kFusedSmem, st>>>(ba);
         float *G = w.cgrad;
         GradPlan gp;
@@ -782,14 +827,14 @@ int erlfill_ddpg_update(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h,
                                                                   w.ssq, w.scal + 2, h->max_grad_norm, w.step, h->tau);
     }
     if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
-        actor_forward(st, w, B, 0, d_batch, d_next_emotion, n->actor, n->scale, n->offset, w.aout, true, h->n_cond);
-        critic_forward(st, w, B, 2, d_batch, w.aout, n->critic, w.q2, true);
+        actor_forward(st, w, dr, B, 0, d_batch, d_next_emotion, n->actor, n->scale, n->offset, w.aout, true, h->n_cond);
+        critic_forward(st, w, dr, B, 2, d_batch, w.aout, n->critic, w.q2, true);
         actor_loss_kernel<<<1 + kActorTensors, 1024, 0, st>>>(B, w.q2, w.aout, n->actor, w.scal + 5, w.scal + 6);
         // d(-mean q2)/dq2 = -1/B (the +-1e6 clamp is inactive): input gradient of the critic only -> w.g16
-        const CriticBwdArgs ba{B, 0, -1.0f / (float)B, n->critic, nullptr, w.h3, w.xhat2, w.rstd2, w.xhat1, w.rstd1, nullptr, nullptr, nullptr,
+        const CriticBwdArgs ba{dr, B, 0, 8, -1.0f / (float)B, n->critic, nullptr, w.h3, w.xhat2, w.rstd2, w.xhat1, w.rstd1, nullptr, nullptr, nullptr,
                                w.g16, nullptr};
         critic_bwd_kernel<<<nt, NTHR, kFusedSmem, st>>>(ba);
-        const ActorBwdArgs ab{B, n->actor, w.g16, w.aout, w.aux, w.xa, n->scale, w.z4, w.a3, w.a2, w.a1, w.gz4, w.ga64, w.ga128a, w.ga128b, w.apart};
+        const ActorBwdArgs ab{dr, B, n->actor, w.g16, w.aout, w.aux, w.xa, n->scale, w.z4, w.a3, w.a2, w.a1, w.gz4, w.ga64, w.ga128a, w.ga128b, w.apart};
         actor_bwd_kernel<<<nt, NTHR, kFusedSmem, st>>>(ab);
         float *G = w.agrad;
         GradPlan gp;

@@ -1,0 +1,1032 @@
+// update_tc.cu — the tcgen05 ("fast") ER-DDPG minibatch update: DDPGAgent.learn, DifferentModules/ddpg_agent.py:422-512,
+// rows U1-U5 of SURVEY.md section 8a, with train()-mode dropout (the reference never calls .eval() on this path).
+//
+// Six launches per update (erlfill_ddpg_update with hyper->precision == ERLFILL_PRECISION_FAST):
+//   CRITIC_GRAD   ddpg_critic_grad_tc   B/128 CTAs: target chain actor_target -> critic_target, Q(s, a), SmoothL1, the whole critic
+//                                       backward incl. the weight-gradient GEMMs (per-CTA partials)
+//                 grad_reduce_kernel    partials -> flat gradient bucket (CTA order, deterministic) + clip-norm partials
+//   CRITIC_APPLY  apply_kernel          emotion-driven lr, clip_grad_norm_(5), Adam, refresh of the critic's bf16 weight images
+//   ACTOR_GRAD    ddpg_actor_grad_tc    actor forward, Q(s, actor(s)) with the UPDATED critic, critic input gradient, actor backward
+//                 grad_reduce_kernel    (+ the L2-norm regulariser's gradient)
+//   ACTOR_APPLY   apply_kernel          clip, Adam, both soft target updates, all target / actor images, report
+// Building blocks and the operand-image scheme: update_tc.cuh.  Numerics: bf16 operands, fp32 accumulation, fp32 master weights,
+// LayerNorm / losses / optimiser in fp32 (stated tolerance against the fp32 reference: tests/test_update_tc_gpu.py); the exact
+// 3xTF32 path of update.cu stays the 1e-4 parity path.
+#include "update_tc.cuh"
+
+#include "mlp.cuh"
+
+namespace erlfill {
+namespace utc {
+
+constexpr int ACT_LEAKY = 0, ACT_RELU = 1;
+
+// ---- per-CTA global scratch (bytes) ----------------------------------------------------------------------------------
+namespace SC {
+constexpr size_t X0IMG = 0, H1IMG = X0IMG + 12288, H2IMG = H1IMG + 65536, XHAT1 = H2IMG + 65536, XHAT2 = XHAT1 + 131072,
+                 RSTD1 = XHAT2 + 131072, RSTD2 = RSTD1 + 512, KEEP = RSTD2 + 512 /* [2][128][8] words */, XAIMG = KEEP + 8192,
+                 A1IMG = XAIMG + 12288, A2IMG = A1IMG + 32768, A3IMG = A2IMG + 32768, ABITS = A3IMG + 16384 /* [128][16] words */,
+                 AUX = ABITS + 8192 /* [128][64] floats */, BYTES = AUX + 32768;
+}
+
+struct Args {
+    int B, n_cond;
+    float gamma;
+    const float *batch, *next_emotion;
+    const float *actor, *actor_t, *critic, *critic_t;            // fp32 master parameters (small vectors are read from these)
+    const uint8_t *img_actor, *img_actor_t, *img_critic, *img_critic_t;
+    const float *scale, *offset;
+    uint8_t *scratch;                                            // [n_cta][SC::BYTES]
+    float *cpart, *apart;                                        // [n_cta][CP::SIZE], [n_cta][AP::SIZE]
+    float *mean_out;                                             // 3 batch emotion means (tail of the critic gradient bucket)
+    float *scal;                                                 // scal[6 .. 15): L2 norms of the nine actor tensors
+    Drop drop;
+};
+
+__constant__ int c_actor_seg[10] = {0, 30, 670, 798, 17182, 17310, 25502, 25566, 26206, 26216};
+
+// ---- common prologue / epilogue of the two phase kernels ---------------------------------------------------------------
+__device__ __forceinline__ void setup(uint8_t *smem, uint64_t *bars, uint32_t *tmem_slot, int tid, int warp) {
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bars + BW_FULL + s, 1); mbar_init(bars + BW_EMPTY + s, 1); }
+        mbar_init(bars + B_HFULL, 1); mbar_init(bars + B_HFREE, 1); mbar_init(bars + B_DFULL, 1); mbar_init(bars + B_GFULL, 1);
+        mbar_init(bars + B_GFREE, NEPI / 32); mbar_init(bars + B_AREADY, NEPI / 32);
+        mbar_fence_init();
+    }
+    if (warp == W_ISSUER) tmem_alloc(tmem_slot, 512);
+    // operand images start finite: the MN-major reads of narrow images and ragged tiles touch bytes nobody writes
+    for (int i = tid; i < (SM_RING) / 16; i += NTHR) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+}
+
+// batch mean / unbiased std of the three emotion columns (Critic.forward, ddpg_agent.py:176), by the epilogue threads of every CTA
+__device__ __forceinline__ void emotion_stats(Epi &e, const float *batch, float *mean_out) {
+    float *st = e.stat();
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int r = e.tid; r < e.B; r += NEPI)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s[c] += __ldg(batch + (size_t)r * ERLFILL_REC + 16 + c);
+    float *scr = st + 16;                                        // [16 warps][3]
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const float t = warp_sum(s[c]); if (e.lane == 0) scr[(e.tid >> 5) * 3 + c] = t; }
+    bar_epi();
+    if (e.tid < 3) { float t = 0.f; for (int w = 0; w < NEPI / 32; ++w) t += scr[w * 3 + e.tid]; st[e.tid] = t / (float)e.B; }
+    bar_epi();
+    float q[3] = {0.f, 0.f, 0.f};
+    for (int r = e.tid; r < e.B; r += NEPI)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { const float d = __ldg(batch + (size_t)r * ERLFILL_REC + 16 + c) - st[c]; q[c] = fmaf(d, d, q[c]); }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const float t = warp_sum(q[c]); if (e.lane == 0) scr[(e.tid >> 5) * 3 + c] = t; }
+    bar_epi();
+    if (e.tid < 3) {
+        float t = 0.f;
+        for (int w = 0; w < NEPI / 32; ++w) t += scr[w * 3 + e.tid];
+        st[3 + e.tid] = sqrtf(t / (float)(e.B - 1));
+        if (mean_out && blockIdx.x == 0) mean_out[e.tid] = st[e.tid];
+    }
+    bar_epi();
+}
+
+// x[16] -> the K = 48 first-layer operand [x_hi | x_lo | x_hi] of this thread's row (image of 48 features), optionally copied to global
+__device__ __forceinline__ void store_split_input(const Epi &e, const float (&x)[16], uint8_t *gimg) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        hi[j] = __bfloat162float(__float2bfloat16(x[j]));
+        lo[j] = x[j] - hi[j];
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        e.img_store8(e.img_a(), 48, g * 8, hi + g * 8);
+        e.img_store8(e.img_a(), 48, 16 + g * 8, lo + g * 8);
+        e.img_store8(e.img_a(), 48, 32 + g * 8, hi + g * 8);
+        if (gimg) { e.img_store8(gimg, 48, g * 8, hi + g * 8); e.img_store8(gimg, 48, 16 + g * 8, lo + g * 8); e.img_store8(gimg, 48, 32 + g * 8, hi + g * 8); }
+    }
+}
+
+// Actor head on the 16 accumulator columns of the last layer (ddpg_agent.py:104-122): out[10] in physical units.
+// aux (optional) [64] floats of this row: z4[10] base[10] raw[10] alpha[10] out[10] (what the backward needs).
+__device__ __forceinline__ void actor_head(const float (&z16)[16], const float *P, float cur, float cons, float anx, const float *scale,
+                                           const float *offset, float (&out)[10], float *aux) {
+    float alpha = 0.1f + 0.9f * anx;
+    alpha *= (1.0f - 0.5f * cons);
+    alpha *= (1.0f + 0.5f * cur);
+    alpha = fminf(fmaxf(alpha, 0.01f), 1.0f);
+#pragma unroll
+    for (int c = 0; c < 10; ++c) {
+        const float z = z16[c] + __ldg(P + AO::B4 + c);
+        const float base = z / (1.0f + fabsf(z));
+        float em = cur * __ldg(P + AO::EW + c);
+        em = fmaf(cons, __ldg(P + AO::EW + 10 + c), em);
+        em = fmaf(anx, __ldg(P + AO::EW + 20 + c), em);
+        const float raw = tanhf(em * 1.5f);
+        const float om = 1.0f - fabsf(base);
+        const float sf = base > 0.f ? -1.0f : (base < 0.f ? 1.0f : 0.0f);
+        out[c] = (base + alpha * raw * sf * (om * om)) * __ldg(scale + c) + __ldg(offset + c);
+        if (aux) { aux[c] = z; aux[10 + c] = base; aux[20 + c] = raw; aux[30 + c] = alpha; aux[40 + c] = out[c]; }
+    }
+}
+
+// Hidden layer with N = 128 outputs (32 columns per thread): z = D (+ bias) -> activation -> dropout -> image of 128 features.
+// pos_out / keep_out: bit j = (z > 0) / kept, of column wg * 32 + j.
+__device__ __forceinline__ void epi_hidden128(Epi &e, const float *bias, int act, const Drop &dr, int site, uint8_t *gimg, uint32_t *pos_out,
+                                              uint32_t *keep_out) {
+    float v[32];
+    const int c0 = e.wg * 32;
+    tmem_ld32w(e.td(c0), v);
+    const uint32_t keep = keep32(dr, site, e.mrow(), c0, 128);
+    uint32_t pos = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float z = v[j] + (bias ? __ldg(bias + c0 + j) : 0.f);
+        pos |= (z > 0.f ? 1u : 0u) << j;
+        z = act == ACT_LEAKY ? (z > 0.f ? z : 0.1f * z) : fmaxf(z, 0.f);
+        v[j] = ((keep >> j) & 1u) ? z * (dr.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale) : 0.f;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        e.img_store8(e.img_a(), 128, c0 + g * 8, v + g * 8);
+        if (gimg) e.img_store8(gimg, 128, c0 + g * 8, v + g * 8);
+    }
+    if (pos_out) *pos_out = pos;
+    if (keep_out) *keep_out = keep;
+}
+
+// LayerNorm(256) + activation + dropout of the critic (64 columns per thread) -> image of 256 features.
+// save: xhat (fp32 [128][256]), rstd [128], keep words [128][8], image copy — what the backward and the weight gradients read.
+__device__ __forceinline__ void epi_ln256(Epi &e, const float *bias, const float *gamma, const float *beta, int act, const Drop &dr, int site,
+                                          float *xhat_g, float *rstd_g, uint32_t *keep_g, uint8_t *gimg) {
+    float v[64];
+    const int c0 = e.wg * 64;
+    {
+        float t[32];
+        tmem_ld32w(e.td(c0), t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = t[j] + (bias ? __ldg(bias + c0 + j) : 0.f);
+        tmem_ld32w(e.td(c0 + 32), t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[32 + j] = t[j] + (bias ? __ldg(bias + c0 + 32 + j) : 0.f);
+    }
+    float s = 0.f, dummy = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) s += v[j];
+    e.row_allreduce2(s, dummy);
+    const float mean = s * (1.0f / 256.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+    dummy = 0.f;
+    e.row_allreduce2(q, dummy);
+    const float rstd = rsqrtf(q * (1.0f / 256.0f) + 1e-5f);
+    const uint32_t k0 = keep32(dr, site, e.mrow(), c0, 256), k1 = keep32(dr, site, e.mrow(), c0 + 32, 256);
+    const float ds = dr.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        float h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int j = g * 8 + i, c = c0 + j;
+            const float xh = (v[j] - mean) * rstd;
+            v[j] = xh;
+            float y = xh * __ldg(gamma + c) + __ldg(beta + c);
+            y = act == ACT_LEAKY ? (y > 0.f ? y : 0.1f * y) : fmaxf(y, 0.f);
+            const uint32_t kb = j < 32 ? (k0 >> j) & 1u : (k1 >> (j - 32)) & 1u;
+            h[i] = kb ? y * ds : 0.f;
+        }
+        e.img_store8(e.img_a(), 256, c0 + g * 8, h);
+        if (gimg) e.img_store8(gimg, 256, c0 + g * 8, h);
+    }
+    if (xhat_g) {
+        float4 *dst = reinterpret_cast<float4 *>(xhat_g + (size_t)e.r * 256 + c0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (e.wg == 0) rstd_g[e.r] = rstd;
+        keep_g[e.r * 8 + e.wg * 2] = k0;
+        keep_g[e.r * 8 + e.wg * 2 + 1] = k1;
+    }
+}
+
+// critic layer 8 (N = 128, 32 columns per thread): h3 = relu(D + b8), q = clamp(h3 . w10 + b10): every thread of the row gets q
+__device__ __forceinline__ float epi_head(Epi &e, const float *P, float (&h3)[32]) {
+    const int c0 = e.wg * 32;
+    tmem_ld32w(e.td(c0), h3);
+    float part = 0.f, dummy = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        h3[j] = fmaxf(h3[j] + __ldg(P + CO::B8 + c0 + j), 0.f);
+        part = fmaf(h3[j], __ldg(P + CO::W10 + c0 + j), part);
+    }
+    e.row_allreduce2(part, dummy);
+    return fminf(fmaxf(part + __ldg(P + CO::B10), -1e6f), 1e6f);
+}
+
+// dz3 (this thread's 32 columns) -> image of 128 features
+__device__ __forceinline__ void store_img128(const Epi &e, const float (&v)[32]) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) e.img_store8(e.img_a(), 128, e.wg * 32 + g * 8, v + g * 8);
+}
+
+// Backward of (LayerNorm(256) + activation + dropout): D holds dh (gradient of the dropped activation); writes dz (gradient of
+// the LayerNorm input) as the image of 256 features.  part != nullptr: per-CTA column sums [sum dz | sum dy xhat | sum dy].
+__device__ __forceinline__ void epi_ln256_bwd(Epi &e, const float *gamma, const float *beta, int act, const Drop &dr, const float *xhat_g,
+                                              const float *rstd_g, const uint32_t *keep_g, float *part) {
+    const int c0 = e.wg * 64;
+    const float ds = dr.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale;
+    const uint32_t kw[2] = {keep_g[e.r * 8 + e.wg * 2], keep_g[e.r * 8 + e.wg * 2 + 1]};
+    const float rstd = rstd_g[e.r];
+    float s1 = 0.f, s2 = 0.f;
+    // pass 1: dy = dh * keep/0.8 * act'(y); row sums of dy*gamma and dy*gamma*xhat; column sums of dy*xhat and dy
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        float dh[32], a[32], b[32];
+        tmem_ld32w(e.td(c0 + 32 * h), dh);
+        const float4 *xp = reinterpret_cast<const float4 *>(xhat_g + (size_t)e.r * 256 + c0 + 32 * h);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 x4 = xp[j4];
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = j4 * 4 + i, c = c0 + 32 * h + j;
+                const float gm = __ldg(gamma + c), y = xs[i] * gm + __ldg(beta + c);
+                float g = ((kw[h] >> j) & 1u) ? dh[j] * ds : 0.f;
+                g *= act == ACT_LEAKY ? (y > 0.f ? 1.f : 0.1f) : (y > 0.f ? 1.f : 0.f);
+                const float dxh = g * gm;
+                s1 += dxh;
+                s2 = fmaf(dxh, xs[i], s2);
+                a[j] = g * xs[i];
+                b[j] = g;
+            }
+        }
+        if (part) { e.colsum_stage(1, c0 + 32 * h, a); e.colsum_stage(2, c0 + 32 * h, b); }
+    }
+    e.row_allreduce2(s1, s2);
+    s1 *= (1.0f / 256.0f); s2 *= (1.0f / 256.0f);
+    // pass 2: dz = rstd * (dy*gamma - s1 - xhat*s2)
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        float dh[32], dz[32];
+        tmem_ld32w(e.td(c0 + 32 * h), dh);
+        const float4 *xp = reinterpret_cast<const float4 *>(xhat_g + (size_t)e.r * 256 + c0 + 32 * h);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 x4 = xp[j4];
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = j4 * 4 + i, c = c0 + 32 * h + j;
+                const float gm = __ldg(gamma + c), y = xs[i] * gm + __ldg(beta + c);
+                float g = ((kw[h] >> j) & 1u) ? dh[j] * ds : 0.f;
+                g *= act == ACT_LEAKY ? (y > 0.f ? 1.f : 0.1f) : (y > 0.f ? 1.f : 0.f);
+                dz[j] = rstd * (g * gm - s1 - xs[i] * s2);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) e.img_store8(e.img_a(), 256, c0 + 32 * h + g * 8, dz + g * 8);
+        if (part) e.colsum_stage(0, c0 + 32 * h, dz);
+    }
+    if (part) {
+        bar_epi();
+        e.colsum_finish(0, 256, part);
+        e.colsum_finish(1, 256, part + 256);
+        e.colsum_finish(2, 256, part + 512);
+        bar_epi();
+    }
+}
+
+// Drain of one weight-gradient block: TMEM lane r = output feature m0 + r, `n` accumulator columns -> dst[(m0 + r) * ld + col].
+__device__ __forceinline__ void drain_g(Epi &e, float *dst, int ld, int n, int rows_valid) {
+    e.wait_g();
+    if (n >= 128) {
+        const int cpw = n / NWG;
+        for (int c = 0; c < cpw; c += 32) {
+            float v[32];
+            tmem_ld32w(e.tg(e.wg * cpw + c), v);
+            if (e.r < rows_valid) {
+                float4 *o = reinterpret_cast<float4 *>(dst + (size_t)e.r * ld + e.wg * cpw + c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        }
+    } else {            // n = 64 (16 columns per warpgroup) or n = 16 (warpgroup 0 only)
+        if (n == 64 || e.wg == 0) {
+            float v[16];
+            const int c = n == 64 ? e.wg * 16 : 0;
+            tmem_ld16w(e.tg(c), v);
+            if (e.r < rows_valid) {
+                float4 *o = reinterpret_cast<float4 *>(dst + (size_t)e.r * ld + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        }
+    }
+    e.g_free();
+}
+
+#define UTC_ROLE_PROLOGUE                                                                                      \
+    extern __shared__ __align__(128) uint8_t smem[];                                                            \
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);                                               \
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_TMEM);                                         \
+    const int tid = threadIdx.x;                                                                                \
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);                                                     \
+    setup(smem, bars, tmem_slot, tid, warp);                                                                    \
+    const uint32_t tbase = *tmem_slot;                                                                          \
+    uint8_t *scr = a.scratch + (size_t)blockIdx.x * SC::BYTES;
+
+#define UTC_ROLE_EPILOGUE                                                                                      \
+    tc_fence_before();                                                                                          \
+    __syncthreads();                                                                                            \
+    if (warp == W_ISSUER) tmem_dealloc(tbase, 512);
+
+// =====================================================================================================================
+// CRITIC_GRAD
+// =====================================================================================================================
+template <int ROLE>
+__device__ __forceinline__ void critic_program(Pipe &p, const Args &a, const uint8_t *scr) {
+    // target chain: actor_target, critic_target
+    gemm_fwd<ROLE>(p, a.img_actor_t + AI::W1, 128, 48);
+    gemm_fwd<ROLE>(p, a.img_actor_t + AI::W2, 128, 128);
+    gemm_fwd<ROLE>(p, a.img_actor_t + AI::W3, 64, 128);
+    gemm_fwd<ROLE>(p, a.img_actor_t + AI::W4, 16, 64);
+    gemm_fwd<ROLE>(p, a.img_critic_t + CI::W0, 256, 48);
+    gemm_fwd<ROLE>(p, a.img_critic_t + CI::W4, 256, 256);
+    gemm_fwd<ROLE>(p, a.img_critic_t + CI::W8, 128, 256);
+    // Q(s, a_norm, e)
+    gemm_fwd<ROLE>(p, a.img_critic + CI::W0, 256, 48);
+    gemm_fwd<ROLE>(p, a.img_critic + CI::W4, 256, 256);
+    gemm_fwd<ROLE>(p, a.img_critic + CI::W8, 128, 256);
+    // backward: dh2 = dz3 W8, dW8 = dz3^T h2
+    load_h<ROLE>(p, scr + SC::H2IMG, 65536);
+    gemm_bwd<ROLE>(p, a.img_critic + CI::W8, 128, 256, 256);
+    wgrad<ROLE>(p, 128, 0, 256, 256, true, false, true);
+    // dh1 = dz2 W4, dW4 = dz2^T h1
+    load_h<ROLE>(p, scr + SC::H1IMG, 65536);
+    gemm_bwd<ROLE>(p, a.img_critic + CI::W4, 256, 256, 256);
+    wgrad<ROLE>(p, 256, 0, 256, 256, true, false, false);
+    wgrad<ROLE>(p, 256, 128, 256, 256, false, false, true);
+    // dW0 = dz1^T x0
+    load_h<ROLE>(p, scr + SC::X0IMG, 12288);
+    wgrad<ROLE>(p, 256, 0, 48, 16, true, true, false);
+    wgrad<ROLE>(p, 256, 128, 48, 16, false, false, true);
+}
+
+__global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
+    UTC_ROLE_PROLOGUE
+    if (warp == W_PRODUCER) {
+        if (elect_one()) { Pipe p{smem, bars, tbase}; critic_program<ROLE_PRODUCER>(p, a, scr); }
+        __syncwarp();
+    } else if (warp == W_ISSUER) {
+        if (elect_one()) { Pipe p{smem, bars, tbase}; critic_program<ROLE_ISSUER>(p, a, scr); }
+        __syncwarp();
+    } else {
+        Epi e{smem, bars, tbase, tid, tid >> 7, tid & 127, tid & 31, (tid >> 5) & 3, (uint32_t)(((tid >> 5) & 3) * 32) << 16};
+        e.row0 = blockIdx.x * TR; e.B = a.B;
+        const int grow = e.row0 + e.r;
+        const bool valid = e.valid();
+        const float *row = a.batch + (size_t)(valid ? grow : 0) * ERLFILL_REC;
+        float *part = a.cpart + (size_t)blockIdx.x * CP::SIZE;
+        emotion_stats(e, a.batch, a.mean_out);
+        const float *st = e.stat();
+        const int cid = (a.n_cond > 1 && valid) ? (int)__ldg(row + 19) : 0;
+        const float *scale = a.scale + cid * 10, *offset = a.offset + cid * 10;
+        // ---- target: a' = actor_target(s', e'), Q' = critic_target(s', a', 0) ----
+        const float ne0 = __ldg(a.next_emotion), ne1 = __ldg(a.next_emotion + 1), ne2 = __ldg(a.next_emotion + 2);
+        if (e.wg == 0) {
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = 0.f;
+            if (valid) { x[0] = __ldg(row + 13); x[1] = __ldg(row + 14); x[2] = ne0; x[3] = ne1; x[4] = ne2; }
+            x[15] = 1.0f;
+            store_split_input(e, x, nullptr);
+        }
+        e.a_ready();
+        e.wait_d(); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 0, nullptr, nullptr, nullptr); e.a_ready();
+        e.wait_d(); epi_hidden128(e, a.actor_t + AO::B2, ACT_RELU, a.drop, 1, nullptr, nullptr, nullptr); e.a_ready();
+        e.wait_d();
+        {   // Linear(128, 64) -> ReLU: 16 columns per thread
+            float v[16];
+            tmem_ld16w(e.td(e.wg * 16), v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + __ldg(a.actor_t + AO::B3 + e.wg * 16 + j), 0.f);
+            e.img_store8(e.img_a(), 64, e.wg * 16, v);
+            e.img_store8(e.img_a(), 64, e.wg * 16 + 8, v + 8);
+        }
+        e.a_ready();
+        e.wait_d();
+        if (e.wg == 0) {
+            float z[16], out[10], x[16];
+            tmem_ld16w(e.td(0), z);
+            actor_head(z, a.actor_t, ne0, ne1, ne2, scale, offset, out, nullptr);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = 0.f;
+            if (valid) {
+                x[0] = __ldg(row + 13); x[1] = __ldg(row + 14);
+#pragma unroll
+                for (int c = 0; c < 10; ++c) x[2 + c] = out[c];
+            }
+            x[15] = 1.0f;                                       // the standardised emotion of identical rows is exactly 0
+            store_split_input(e, x, nullptr);
+        }
+        e.a_ready();
+        e.wait_d(); epi_ln256(e, nullptr, a.critic_t + CO::G1, a.critic_t + CO::BE1, ACT_LEAKY, a.drop, 2, nullptr, nullptr, nullptr, nullptr); e.a_ready();
+        e.wait_d(); epi_ln256(e, a.critic_t + CO::B4, a.critic_t + CO::G2, a.critic_t + CO::BE2, ACT_RELU, a.drop, 3, nullptr, nullptr, nullptr, nullptr); e.a_ready();
+        e.wait_d();
+        float tq;
+        { float h3[32]; tq = epi_head(e, a.critic_t, h3); }
+        // ---- Q(s, a_norm, e) ----
+        if (e.wg == 0) {
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = 0.f;
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) x[j] = __ldg(row + j);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) x[12 + c] = (__ldg(row + 16 + c) - st[c]) / (st[3 + c] + 1e-6f);
+            }
+            x[15] = 1.0f;
+            store_split_input(e, x, scr + SC::X0IMG);
+        }
+        e.a_ready();
+        e.wait_d();
+        epi_ln256(e, nullptr, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, 4, reinterpret_cast<float *>(scr + SC::XHAT1),
+                  reinterpret_cast<float *>(scr + SC::RSTD1), reinterpret_cast<uint32_t *>(scr + SC::KEEP), scr + SC::H1IMG);
+        e.a_ready();
+        e.wait_d();
+        epi_ln256(e, a.critic + CO::B4, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, 5, reinterpret_cast<float *>(scr + SC::XHAT2),
+                  reinterpret_cast<float *>(scr + SC::RSTD2), reinterpret_cast<uint32_t *>(scr + SC::KEEP) + 1024, scr + SC::H2IMG);
+        __threadfence();                                        // the saved images are read back through the async proxy (bulk copies)
+        e.a_ready();
+        e.wait_d();
+        {
+            float h3[32], dz3[32], gw[32];
+            const float q = epi_head(e, a.critic, h3);
+            // SmoothL1 (beta = 1, mean) against y = 0.01 r + (1 - d) gamma Q'   (ddpg_agent.py:445, 470-473)
+            float g = 0.f, l = 0.f;
+            if (valid) {
+                const float y = __ldg(row + 12) * 0.01f + (1.0f - __ldg(row + 15)) * a.gamma * tq;
+                const float d = q - y, ad = fabsf(d);
+                l = ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+                g = ad < 1.0f ? d : (d > 0.f ? 1.f : -1.f);
+                if (fabsf(q) >= 1e6f) g = 0.f;                  // the clamp blocks the gradient outside (-1e6, 1e6)
+                g /= (float)a.B;
+            }
+            const int c0 = e.wg * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                dz3[j] = h3[j] > 0.f ? g * __ldg(a.critic + CO::W10 + c0 + j) : 0.f;
+                gw[j] = g * h3[j];
+            }
+            store_img128(e, dz3);
+            e.a_ready();
+            e.colsum_stage(0, c0, dz3);                         // db8
+            e.colsum_stage(1, c0, gw);                          // dW10
+            if (e.wg == 0) {                                    // db10 = sum g, loss = sum l over the CTA's rows
+                const float sg = warp_sum(g), sl = warp_sum(l);
+                if (e.lane == 0) { e.cs()[(2 * 4 + e.wq) * 256] = sg; e.cs()[(2 * 4 + e.wq) * 256 + 1] = sl; }
+            }
+            bar_epi();
+            e.colsum_finish(0, 128, part + CP::VC);
+            e.colsum_finish(1, 128, part + CP::VC + 128);
+            if (e.tid == 0) {
+                const float *c = e.cs() + 2 * 4 * 256;
+                part[CP::VC + 256] = (c[0] + c[256]) + (c[512] + c[768]);
+                part[CP::LOSS] = (c[1] + c[257]) + (c[513] + c[769]);
+            }
+            bar_epi();
+        }
+        // ---- backward ----
+        drain_g(e, part + CP::W8, 256, 256, 128);
+        e.wait_d();
+        epi_ln256_bwd(e, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, reinterpret_cast<const float *>(scr + SC::XHAT2),
+                      reinterpret_cast<const float *>(scr + SC::RSTD2), reinterpret_cast<const uint32_t *>(scr + SC::KEEP) + 1024, part + CP::VB);
+        e.a_ready();
+        drain_g(e, part + CP::W4, 256, 256, 128);
+        drain_g(e, part + CP::W4 + 128 * 256, 256, 256, 128);
+        e.wait_d();
+        epi_ln256_bwd(e, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, reinterpret_cast<const float *>(scr + SC::XHAT1),
+                      reinterpret_cast<const float *>(scr + SC::RSTD1), reinterpret_cast<const uint32_t *>(scr + SC::KEEP), part + CP::VA);
+        e.a_ready();
+        drain_g(e, part + CP::W0, 16, 16, 128);
+        drain_g(e, part + CP::W0 + 128 * 16, 16, 16, 128);
+    }
+    UTC_ROLE_EPILOGUE
+}
+
+// =====================================================================================================================
+// ACTOR_GRAD
+// =====================================================================================================================
+template <int ROLE>
+__device__ __forceinline__ void actor_program(Pipe &p, const Args &a, const uint8_t *scr) {
+    gemm_fwd<ROLE>(p, a.img_actor + AI::W1, 128, 48);
+    gemm_fwd<ROLE>(p, a.img_actor + AI::W2, 128, 128);
+    gemm_fwd<ROLE>(p, a.img_actor + AI::W3, 64, 128);
+    gemm_fwd<ROLE>(p, a.img_actor + AI::W4, 16, 64);
+    gemm_fwd<ROLE>(p, a.img_critic + CI::W0, 256, 48);
+    gemm_fwd<ROLE>(p, a.img_critic + CI::W4, 256, 256);
+    gemm_fwd<ROLE>(p, a.img_critic + CI::W8, 128, 256);
+    // input gradient of the critic
+    gemm_bwd<ROLE>(p, a.img_critic + CI::W8, 128, 256, 256);
+    gemm_bwd<ROLE>(p, a.img_critic + CI::W4, 256, 256, 256);
+    gemm_bwd<ROLE>(p, a.img_critic + CI::W0, 256, 48, 16);
+    // actor backward
+    load_h<ROLE>(p, scr + SC::A3IMG, 16384);
+    gemm_bwd<ROLE>(p, a.img_actor + AI::W4, 16, 64, 64);
+    wgrad<ROLE>(p, 16, 0, 64, 64, true, false, true);
+    load_h<ROLE>(p, scr + SC::A2IMG, 32768);
+    gemm_bwd<ROLE>(p, a.img_actor + AI::W3, 64, 128, 128);
+    wgrad<ROLE>(p, 64, 0, 128, 128, true, false, true);
+    load_h<ROLE>(p, scr + SC::A1IMG, 32768);
+    gemm_bwd<ROLE>(p, a.img_actor + AI::W2, 128, 128, 128);
+    wgrad<ROLE>(p, 128, 0, 128, 128, true, false, true);
+    load_h<ROLE>(p, scr + SC::XAIMG, 12288);
+    wgrad<ROLE>(p, 128, 0, 48, 16, true, true, true);
+}
+
+__global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
+    UTC_ROLE_PROLOGUE
+    if (warp == W_PRODUCER) {
+        if (elect_one()) { Pipe p{smem, bars, tbase}; actor_program<ROLE_PRODUCER>(p, a, scr); }
+        __syncwarp();
+    } else if (warp == W_ISSUER) {
+        if (elect_one()) { Pipe p{smem, bars, tbase}; actor_program<ROLE_ISSUER>(p, a, scr); }
+        __syncwarp();
+    } else {
+        Epi e{smem, bars, tbase, tid, tid >> 7, tid & 127, tid & 31, (tid >> 5) & 3, (uint32_t)(((tid >> 5) & 3) * 32) << 16};
+        e.row0 = blockIdx.x * TR; e.B = a.B;
+        const int grow = e.row0 + e.r;
+        const bool valid = e.valid();
+        const float *row = a.batch + (size_t)(valid ? grow : 0) * ERLFILL_REC;
+        float *part = a.apart + (size_t)blockIdx.x * AP::SIZE;
+        uint32_t *abits = reinterpret_cast<uint32_t *>(scr + SC::ABITS) + e.r * 16;     // [pos1 x4 | keep1 x4 | pos2 x4 | keep2 x4]; pos3 in keep words of ...
+        float *aux = reinterpret_cast<float *>(scr + SC::AUX) + e.r * 64;
+        // L2 norms of the nine actor tensors (actor_loss += 1e-4 sum ||theta_t||, ddpg_agent.py:490-494), spread over the CTAs
+        for (int t = blockIdx.x; t < 9; t += gridDim.x) {
+            float qn = 0.f;
+            for (int i = c_actor_seg[t] + e.tid; i < c_actor_seg[t + 1]; i += NEPI) { const float w = __ldg(a.actor + i); qn = fmaf(w, w, qn); }
+            qn = warp_sum(qn);
+            float *scr_s = e.stat() + 16;
+            if (e.lane == 0) scr_s[e.tid >> 5] = qn;
+            bar_epi();
+            if (e.tid == 0) { float tt = 0.f; for (int w = 0; w < NEPI / 32; ++w) tt += scr_s[w]; a.scal[6 + t] = sqrtf(tt); }
+            bar_epi();
+        }
+        emotion_stats(e, a.batch, nullptr);
+        const float *st = e.stat();
+        const int cid = (a.n_cond > 1 && valid) ? (int)__ldg(row + 19) : 0;
+        const float *scale = a.scale + cid * 10, *offset = a.offset + cid * 10;
+        const float e0 = valid ? __ldg(row + 16) : 0.f, e1 = valid ? __ldg(row + 17) : 0.f, e2 = valid ? __ldg(row + 18) : 0.f;
+        // ---- a = actor(s, e) ----
+        if (e.wg == 0) {
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = 0.f;
+            if (valid) { x[0] = __ldg(row); x[1] = __ldg(row + 1); x[2] = e0; x[3] = e1; x[4] = e2; }
+            x[15] = 1.0f;
+            store_split_input(e, x, scr + SC::XAIMG);
+        }
+        e.a_ready();
+        e.wait_d(); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 6, scr + SC::A1IMG, abits + e.wg, abits + 4 + e.wg); e.a_ready();
+        e.wait_d(); epi_hidden128(e, a.actor + AO::B2, ACT_RELU, a.drop, 7, scr + SC::A2IMG, abits + 8 + e.wg, abits + 12 + e.wg); e.a_ready();
+        e.wait_d();
+        uint32_t pos3 = 0;                                     // relu'(z3) bits of this thread's 16 columns (kept in a register until the backward)
+        {
+            float v[16];
+            tmem_ld16w(e.td(e.wg * 16), v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                v[j] = fmaxf(v[j] + __ldg(a.actor + AO::B3 + e.wg * 16 + j), 0.f);
+                pos3 |= (v[j] > 0.f ? 1u : 0u) << j;
+            }
+            e.img_store8(e.img_a(), 64, e.wg * 16, v);
+            e.img_store8(e.img_a(), 64, e.wg * 16 + 8, v + 8);
+            e.img_store8(scr + SC::A3IMG, 64, e.wg * 16, v);
+            e.img_store8(scr + SC::A3IMG, 64, e.wg * 16 + 8, v + 8);
+        }
+        e.a_ready();
+        e.wait_d();
+        if (e.wg == 0) {
+            float z[16], out[10], x[16];
+            tmem_ld16w(e.td(0), z);
+            actor_head(z, a.actor, e0, e1, e2, scale, offset, out, aux);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = 0.f;
+            float sd = 0.f;
+            if (valid) {
+                x[0] = __ldg(row); x[1] = __ldg(row + 1);
+                float mean = 0.f;
+#pragma unroll
+                for (int c = 0; c < 10; ++c) { x[2 + c] = out[c]; mean += out[c]; }
+                mean *= 0.1f;
+                float var = 0.f;
+#pragma unroll
+                for (int c = 0; c < 10; ++c) { const float d = out[c] - mean; var = fmaf(d, d, var); }
+                sd = sqrtf(var / 9.0f);                        // torch.std(action_out, dim=1): unbiased
+#pragma unroll
+                for (int c = 0; c < 3; ++c) x[12 + c] = (__ldg(row + 16 + c) - st[c]) / (st[3 + c] + 1e-6f);
+            }
+            x[15] = 1.0f;
+            store_split_input(e, x, nullptr);
+            const float ssd = warp_sum(sd);
+            if (e.lane == 0) e.cs()[(2 * 4 + e.wq) * 256 + 2] = ssd;
+        }
+        __threadfence();
+        e.a_ready();
+        // ---- Q(s, a, e) with the updated critic ----
+        e.wait_d();
+        epi_ln256(e, nullptr, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, 8, reinterpret_cast<float *>(scr + SC::XHAT1),
+                  reinterpret_cast<float *>(scr + SC::RSTD1), reinterpret_cast<uint32_t *>(scr + SC::KEEP), nullptr);
+        e.a_ready();
+        e.wait_d();
+        epi_ln256(e, a.critic + CO::B4, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, 9, reinterpret_cast<float *>(scr + SC::XHAT2),
+                  reinterpret_cast<float *>(scr + SC::RSTD2), reinterpret_cast<uint32_t *>(scr + SC::KEEP) + 1024, nullptr);
+        e.a_ready();
+        e.wait_d();
+        {
+            float h3[32], dz3[32];
+            const float q2 = epi_head(e, a.critic, h3);
+            const float g = valid ? -1.0f / (float)a.B : 0.f;  // d(-mean Q)/dQ; the +-1e6 clamp is inactive
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dz3[j] = h3[j] > 0.f ? g * __ldg(a.critic + CO::W10 + e.wg * 32 + j) : 0.f;
+            store_img128(e, dz3);
+            e.a_ready();
+            if (e.wg == 0) {
+                const float sq = warp_sum(valid ? q2 : 0.f);
+                if (e.lane == 0) e.cs()[(2 * 4 + e.wq) * 256 + 3] = sq;
+            }
+            bar_epi();
+            if (e.tid == 0) {
+                const float *c = e.cs() + 2 * 4 * 256;
+                part[AP::SSTD] = (c[2] + c[258]) + (c[514] + c[770]);
+                part[AP::SQ] = (c[3] + c[259]) + (c[515] + c[771]);
+            }
+            bar_epi();
+        }
+        e.wait_d();
+        epi_ln256_bwd(e, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, reinterpret_cast<const float *>(scr + SC::XHAT2),
+                      reinterpret_cast<const float *>(scr + SC::RSTD2), reinterpret_cast<const uint32_t *>(scr + SC::KEEP) + 1024, nullptr);
+        e.a_ready();
+        e.wait_d();
+        epi_ln256_bwd(e, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, reinterpret_cast<const float *>(scr + SC::XHAT1),
+                      reinterpret_cast<const float *>(scr + SC::RSTD1), reinterpret_cast<const uint32_t *>(scr + SC::KEEP), nullptr);
+        e.a_ready();
+        e.wait_d();
+        // ---- actor backward ----
+        if (e.wg == 0) {
+            float g16[16], dz4[16], prod[32];
+            tmem_ld16w(e.td(0), g16);                           // dQ/dx0: columns 2..11 are dQ/da
+#pragma unroll
+            for (int j = 0; j < 32; ++j) prod[j] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dz4[j] = 0.f;
+            if (valid) {
+                float mean = 0.f;
+#pragma unroll
+                for (int c = 0; c < 10; ++c) mean += aux[40 + c];
+                mean *= 0.1f;
+                float var = 0.f;
+#pragma unroll
+                for (int c = 0; c < 10; ++c) { const float d = aux[40 + c] - mean; var = fmaf(d, d, var); }
+                const float sd = sqrtf(var / 9.0f);
+#pragma unroll
+                for (int c = 0; c < 10; ++c) {
+                    float go = g16[2 + c] + (-0.03f / (float)a.B) * (aux[40 + c] - mean) / (9.0f * sd);     // d(-0.03 mean_rows std)/d out
+                    const float gr_ = go * __ldg(scale + c);
+                    const float z = aux[c], base = aux[10 + c], raw = aux[20 + c], alpha = aux[30 + c];
+                    const float om = 1.0f - fabsf(base);
+                    const float sf = base > 0.f ? -1.0f : (base < 0.f ? 1.0f : 0.0f);
+                    const float dbase = gr_ * (1.0f + 2.0f * alpha * raw * om * (sf * sf));
+                    const float den = 1.0f + fabsf(z);
+                    dz4[c] = dbase / (den * den);
+                    const float de = gr_ * alpha * sf * (om * om) * (1.0f - raw * raw) * 1.5f;
+                    prod[c] = e0 * de; prod[10 + c] = e1 * de; prod[20 + c] = e2 * de;
+                }
+            }
+            e.img_store8(e.img_a(), 16, 0, dz4);
+            e.img_store8(e.img_a(), 16, 8, dz4 + 8);
+            float db4[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) db4[j] = j < 16 ? dz4[j] : 0.f;
+            e.colsum_stage(0, 0, prod);                         // d emotion_weights [3][10]
+            e.colsum_stage(1, 0, db4);
+        }
+        e.a_ready();
+        bar_epi();
+        e.colsum_finish(0, 32, part + AP::EW);
+        e.colsum_finish(1, 16, part + AP::B4);
+        bar_epi();
+        drain_g(e, part + AP::W4, 64, 64, 16);
+        e.wait_d();
+        {   // da3 = dz4 W4, relu'
+            float v[16], s[32];
+            tmem_ld16w(e.td(e.wg * 16), v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = ((pos3 >> j) & 1u) ? v[j] : 0.f;
+            e.img_store8(e.img_a(), 64, e.wg * 16, v);
+            e.img_store8(e.img_a(), 64, e.wg * 16 + 8, v + 8);
+            e.a_ready();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s[j] = j < 16 ? v[j] : 0.f;
+            // 16 columns per warpgroup: stage at column 32 * wg (lanes 16..31 carry zeros), finish picks 16 of every 32
+            e.colsum_stage(0, e.wg * 32, s);
+            bar_epi();
+            if (e.tid < 64) {
+                const float *c = e.cs() + (e.tid >> 4) * 32 + (e.tid & 15);
+                part[AP::B3 + e.tid] = (c[0] + c[256]) + (c[512] + c[768]);
+            }
+            bar_epi();
+        }
+        drain_g(e, part + AP::W3, 128, 128, 64);
+        e.wait_d();
+        {   // da2 = dz3 W3, dropout (site 7), relu'
+            float v[32];
+            tmem_ld32w(e.td(e.wg * 32), v);
+            const uint32_t pos = abits[8 + e.wg], keep = abits[12 + e.wg];
+            const float ds = a.drop.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (((pos & keep) >> j) & 1u) ? v[j] * ds : 0.f;
+            store_img128(e, v);
+            e.a_ready();
+            e.colsum_stage(0, e.wg * 32, v);
+            bar_epi();
+            e.colsum_finish(0, 128, part + AP::B2);
+            bar_epi();
+        }
+        drain_g(e, part + AP::W2, 128, 128, 128);
+        e.wait_d();
+        {   // da1 = dz2 W2, dropout (site 6), leaky'
+            float v[32];
+            tmem_ld32w(e.td(e.wg * 32), v);
+            const uint32_t pos = abits[e.wg], keep = abits[4 + e.wg];
+            const float ds = a.drop.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * ds * (((pos >> j) & 1u) ? 1.0f : 0.1f) : 0.f;
+            store_img128(e, v);
+            e.a_ready();
+            e.colsum_stage(0, e.wg * 32, v);
+            bar_epi();
+            e.colsum_finish(0, 128, part + AP::B1);
+            bar_epi();
+        }
+        drain_g(e, part + AP::W1, 16, 16, 128);
+    }
+    UTC_ROLE_EPILOGUE
+}
+
+}  // namespace utc
+}  // namespace erlfill
+
+// =====================================================================================================================
+// partial reduction, optimiser, weight images, host side
+// =====================================================================================================================
+namespace erlfill {
+namespace utc {
+
+__device__ __forceinline__ int critic_part_index(int i) {
+    if (i < CO::B0) return CP::W0 + (i / 15) * 16 + i % 15;
+    if (i < CO::W4) return CP::VA + (i - CO::B0);
+    if (i < CO::B4) return CP::W4 + (i - CO::W4);
+    if (i < CO::W8) return CP::VB + (i - CO::B4);
+    if (i < CO::B8) return CP::W8 + (i - CO::W8);
+    return CP::VC + (i - CO::B8);
+}
+__device__ __forceinline__ int actor_part_index(int i) {
+    if (i < AO::W1) return AP::EW + i;
+    if (i < AO::B1) return AP::W1 + ((i - AO::W1) / 5) * 16 + (i - AO::W1) % 5;
+    if (i < AO::W2) return AP::B1 + (i - AO::B1);
+    if (i < AO::B2) return AP::W2 + (i - AO::W2);
+    if (i < AO::W3) return AP::B2 + (i - AO::B2);
+    if (i < AO::B3) return AP::W3 + (i - AO::W3);
+    if (i < AO::W4) return AP::B3 + (i - AO::B3);
+    if (i < AO::B4) return AP::W4 + (i - AO::W4);
+    return AP::B4 + (i - AO::B4);
+}
+
+// G[i] = sum over the CTAs' partials in CTA order (+ the L2-norm regulariser's gradient 1e-4 theta / ||theta_tensor|| for the actor);
+// block b also leaves the sum of squares of its slice (clip_grad_norm_) and block 0 the loss value.
+template <bool kActor>
+__global__ void __launch_bounds__(512) grad_reduce_kernel(int n_cta, int B, const float *part, const float *theta, float *scal, float *G, float *ssq) {
+    __shared__ float scratch[32];
+    constexpr int n = kActor ? AO::TOTAL : CO::TOTAL, psize = kActor ? AP::SIZE : CP::SIZE;
+    const int per = (n + mlp::kSumsqBlocks - 1) / mlp::kSumsqBlocks;
+    const int i0 = blockIdx.x * per, i1 = min(n, i0 + per);
+    float ss = 0.f;
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const float *p = part + (kActor ? actor_part_index(i) : critic_part_index(i));
+        float s = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < n_cta; ++c) s += p[(size_t)c * psize];
+        if (kActor) {
+            int t = 0;
+            while (i >= c_actor_seg[t + 1]) ++t;
+            s += 1e-4f * theta[i] / scal[6 + t];
+        }
+        G[i] = s;
+        ss = fmaf(s, s, ss);
+    }
+    const float t = mlp::block_sum(ss, scratch);
+    if (threadIdx.x == 0) ssq[blockIdx.x] = t;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (kActor) {
+            float sq = 0.f, sd = 0.f;
+            for (int c = 0; c < n_cta; ++c) { sq += part[(size_t)c * psize + AP::SQ]; sd += part[(size_t)c * psize + AP::SSTD]; }
+            scal[5] = -sq / (float)B - 0.03f * sd / (float)B;
+        } else {
+            float l = 0.f;
+            for (int c = 0; c < n_cta; ++c) l += part[(size_t)c * psize + CP::LOSS];
+            scal[4] = l / (float)B;
+        }
+    }
+}
+
+// ---- weight images -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void put_bf16(uint8_t *img, uint32_t off, float v) { *reinterpret_cast<__nv_bfloat16 *>(img + off) = __float2bfloat16(v); }
+// first-layer weight (row n, input k < 16) -> [W_hi | W_hi | W_lo] at columns k, 16 + k, 32 + k
+__device__ __forceinline__ void put_split(uint8_t *img, int n, int k, int rows, float v) {
+    const float hi = __bfloat162float(__float2bfloat16(v));
+    put_bf16(img, wimg_off(n, k, rows, 48), hi);
+    put_bf16(img, wimg_off(n, 16 + k, rows, 48), hi);
+    put_bf16(img, wimg_off(n, 32 + k, rows, 48), v - hi);
+}
+__device__ __forceinline__ void critic_image_store(uint8_t *img, int i, float v) {
+    if (i < CO::B0) put_split(img + CI::W0, i / 15, i % 15, 256, v);
+    else if (i < CO::G1) put_split(img + CI::W0, i - CO::B0, 15, 256, v);                 // bias: column 15 against the column of ones
+    else if (i >= CO::W4 && i < CO::B4) put_bf16(img + CI::W4, wimg_off((i - CO::W4) >> 8, (i - CO::W4) & 255, 256, 256), v);
+    else if (i >= CO::W8 && i < CO::B8) put_bf16(img + CI::W8, wimg_off((i - CO::W8) >> 8, (i - CO::W8) & 255, 128, 256), v);
+}
+__device__ __forceinline__ void actor_image_store(uint8_t *img, int i, float v) {
+    if (i < AO::W1) return;
+    if (i < AO::B1) put_split(img + AI::W1, (i - AO::W1) / 5, (i - AO::W1) % 5, 128, v);
+    else if (i < AO::W2) put_split(img + AI::W1, i - AO::B1, 15, 128, v);
+    else if (i < AO::B2) put_bf16(img + AI::W2, wimg_off((i - AO::W2) >> 7, (i - AO::W2) & 127, 128, 128), v);
+    else if (i >= AO::W3 && i < AO::B3) put_bf16(img + AI::W3, wimg_off((i - AO::W3) >> 7, (i - AO::W3) & 127, 64, 128), v);
+    else if (i >= AO::W4 && i < AO::B4) put_bf16(img + AI::W4, wimg_off((i - AO::W4) >> 6, (i - AO::W4) & 63, 16, 64), v);
+}
+__global__ void pack_images_kernel(const float *actor, const float *actor_t, const float *critic, const float *critic_t, uint8_t *img_actor,
+                                   uint8_t *img_actor_t, uint8_t *img_critic, uint8_t *img_critic_t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < CO::TOTAL) { critic_image_store(img_critic, i, critic[i]); critic_image_store(img_critic_t, i, critic_t[i]); }
+    if (i < AO::TOTAL) { actor_image_store(img_actor, i, actor[i]); actor_image_store(img_actor_t, i, actor_t[i]); }
+}
+
+// ---- optimiser ---------------------------------------------------------------------------------------------------------
+// step[0..1] = (double) lr_decay_rate ** train_step, step[2] = 1 - 0.9^t, step[3] = sqrt(1 - 0.999^t)   (update.cu: set_step_kernel)
+__device__ __forceinline__ float adam_elem(float &p, float &m, float &v, float g, float coef, float lr, float bc1, float bc2_sqrt) {
+    const float gi = g * coef;
+    const float mi = m + (gi - m) * 0.1f;
+    const float vi = v * 0.999f + 0.001f * gi * gi;
+    m = mi; v = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + 1e-8f;
+    p = p - (lr / bc1) * (mi / denom);
+    return p;
+}
+__device__ __forceinline__ float clip_coef(const float *ssq, float max_norm) {
+    float ss = 0.f;
+#pragma unroll 8
+    for (int b = 0; b < mlp::kSumsqBlocks; ++b) ss += ssq[b];
+    return fminf(max_norm / (sqrtf(ss) + 1e-6f), 1.0f);
+}
+// CRITIC_APPLY: emotion-driven learning rates (ddpg_agent.py:447-462), clip_grad_norm_(5), Adam, image refresh
+__global__ void critic_apply_kernel(float *p, float *m, float *v, const float *G, const float *ssq, const float *step, double critic_lr, double actor_lr,
+                                    float max_norm, float *scal, uint8_t *img) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double decay = *reinterpret_cast<const double *>(step);
+    const double cur = G[CO::TOTAL], cons = G[CO::TOTAL + 1], anx = G[CO::TOTAL + 2];
+    const double af = 1.0 + 0.8 * cur - 0.4 * cons + 0.2 * anx, cf = 1.0 - 0.3 * anx + 0.6 * cons;
+    const float lr_c = (float)fmin(fmax(critic_lr * cf * decay, critic_lr * 0.1), critic_lr * 3);
+    if (i == 0) { scal[2] = lr_c; scal[3] = (float)fmin(fmax(actor_lr * af * decay, actor_lr * 0.1), actor_lr * 3); }
+    if (i >= CO::TOTAL) return;
+    const float coef = clip_coef(ssq, max_norm);
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_elem(pi, mi, vi, G[i], coef, lr_c, step[2], step[3]);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    critic_image_store(img, i, pi);
+}
+// ACTOR_APPLY: clip, Adam, both soft target updates (ddpg_agent.py:501-507), all remaining images, report
+__global__ void actor_apply_kernel(float *p, float *pt, float *m, float *v, const float *G, const float *ssq, const float *step, float max_norm,
+                                   float tau, const float *critic, float *critic_t, float *scal, uint8_t *img_actor, uint8_t *img_actor_t,
+                                   uint8_t *img_critic_t, float *report) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < AO::TOTAL) {
+        const float coef = clip_coef(ssq, max_norm);
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_elem(pi, mi, vi, G[i], coef, scal[3], step[2], step[3]);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+        const float ti = tau * pi + (1.0f - tau) * pt[i];
+        pt[i] = ti;
+        actor_image_store(img_actor, i, pi);
+        actor_image_store(img_actor_t, i, ti);
+    }
+    if (i < CO::TOTAL) {
+        const float ti = tau * critic[i] + (1.0f - tau) * critic_t[i];
+        critic_t[i] = ti;
+        critic_image_store(img_critic_t, i, ti);
+    }
+    if (i == 0 && report) {
+        float l2 = 0.f;
+        for (int t = 0; t < 9; ++t) l2 += scal[6 + t];
+        report[0] = scal[4]; report[1] = scal[5] + 1e-4f * l2; report[2] = scal[2]; report[3] = scal[3];
+    }
+}
+
+// ---- fast-path workspace tail (behind the exact path's workspace, so buckets / exchange buffers keep their addresses) -------------
+struct Tail {
+    uint8_t *img_actor, *img_actor_t, *img_critic, *img_critic_t, *scratch;
+    float *cpart, *apart;
+    uint32_t *img_valid;
+};
+static size_t up256(size_t n) { return (n + 255) & ~(size_t)255; }
+static int n_cta(int B) { return (B + TR - 1) / TR; }
+size_t tail_bytes(int B) {
+    const size_t c = (size_t)n_cta(B);
+    return 256 + 2 * up256(AI::BYTES) + 2 * up256(CI::BYTES) + up256(c * SC::BYTES) + up256(c * CP::SIZE * 4) + up256(c * AP::SIZE * 4);
+}
+static void carve_tail(Tail &t, uint8_t *base, int B) {
+    const size_t c = (size_t)n_cta(B);
+    size_t o = 0;
+    t.img_valid = reinterpret_cast<uint32_t *>(base); o += 256;
+    t.img_actor = base + o; o += up256(AI::BYTES);
+    t.img_actor_t = base + o; o += up256(AI::BYTES);
+    t.img_critic = base + o; o += up256(CI::BYTES);
+    t.img_critic_t = base + o; o += up256(CI::BYTES);
+    t.scratch = base + o; o += up256(c * SC::BYTES);
+    t.cpart = reinterpret_cast<float *>(base + o); o += up256(c * CP::SIZE * 4);
+    t.apart = reinterpret_cast<float *>(base + o);
+}
+
+static cudaError_t smem_optin() {
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(ddpg_critic_grad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ddpg_actor_grad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess) return e;
+    done = true;
+    return cudaSuccess;
+}
+
+int pack_images(const erlfill_ddpg_nets *n, uint8_t *tail_base, int B, cudaStream_t st) {
+    Tail t;
+    carve_tail(t, tail_base, B);
+    ERLFILL_CUDA_TRY(cudaMemsetAsync(t.img_actor, 0, 2 * up256(AI::BYTES) + 2 * up256(CI::BYTES), st));
+    pack_images_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, n->actor_target, n->critic, n->critic_target, t.img_actor, t.img_actor_t,
+                                                                t.img_critic, t.img_critic_t);
+    ERLFILL_CUDA_TRY(cudaGetLastError());
+    return ERLFILL_OK;
+}
+
+// the workspace head the two paths share (update.cu)
+struct Head { float *cgrad, *agrad, *cred, *ared, *stats, *scal, *ssq, *step; };
+
+int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const float *d_batch, const float *d_next_emotion, const Head &w,
+                uint8_t *tail_base, int phases, float *d_report, cudaStream_t st) {
+    const int B = h->batch, nc = n_cta(B);
+    ERLFILL_CUDA_TRY(smem_optin());
+    Tail t;
+    carve_tail(t, tail_base, B);
+    Args a;
+    a.B = B; a.n_cond = h->n_cond; a.gamma = h->gamma;
+    a.batch = d_batch; a.next_emotion = d_next_emotion;
+    a.actor = n->actor; a.actor_t = n->actor_target; a.critic = n->critic; a.critic_t = n->critic_target;
+    a.img_actor = t.img_actor; a.img_actor_t = t.img_actor_t; a.img_critic = t.img_critic; a.img_critic_t = t.img_critic_t;
+    a.scale = n->scale; a.offset = n->offset;
+    a.scratch = t.scratch; a.cpart = t.cpart; a.apart = t.apart;
+    a.mean_out = w.cgrad + CO::TOTAL;
+    a.scal = w.scal;
+    a.drop.mode = h->dropout_mode;
+    a.drop.k0 = (uint32_t)h->seed; a.drop.k1 = (uint32_t)(h->seed >> 32);
+    a.drop.update_idx = h->update_idx; a.drop.row_base = h->rank << 20;
+    for (int s = 0; s < 10; ++s) a.drop.m[s] = (h->dropout_mode == ERLFILL_DROPOUT_MASK && h->masks) ? h->masks->keep[s] : nullptr;
+    if (h->dropout_mode == ERLFILL_DROPOUT_MASK) {
+        if (!h->masks) return ERLFILL_ERR_ARG;
+        for (int s = 0; s < 10; ++s) if (!h->masks->keep[s]) return ERLFILL_ERR_ARG;
+    }
+    const bool reduced = (phases & ERLFILL_PHASE_REDUCED) != 0;
+    if (phases & ERLFILL_PHASE_CRITIC_GRAD) {
+        ddpg_critic_grad_tc<<<nc, NTHR, SMEM_BYTES, st>>>(a);
+        grad_reduce_kernel<false><<<mlp::kSumsqBlocks, 512, 0, st>>>(nc, B, t.cpart, nullptr, w.scal, w.cgrad, w.ssq);
+    }
+    if (phases & ERLFILL_PHASE_CRITIC_APPLY) {
+        const float *G = reduced ? w.cred : w.cgrad;
+        critic_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->critic, n->critic_m, n->critic_v, G, w.ssq, w.step, h->critic_lr, h->actor_lr,
+                                                                     h->max_grad_norm, w.scal, t.img_critic);
+    }
+    if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
+        ddpg_actor_grad_tc<<<nc, NTHR, SMEM_BYTES, st>>>(a);
+        grad_reduce_kernel<true><<<mlp::kSumsqBlocks, 512, 0, st>>>(nc, B, t.apart, n->actor, w.scal, w.agrad, w.ssq + mlp::kSumsqBlocks);
+    }
+    if (phases & ERLFILL_PHASE_ACTOR_APPLY) {
+        const float *G = reduced ? w.ared : w.agrad;
+        actor_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, n->actor_target, n->actor_m, n->actor_v, G, w.ssq + mlp::kSumsqBlocks, w.step,
+                                                                    h->max_grad_norm, h->tau, n->critic, n->critic_target, w.scal, t.img_actor,
+                                                                    t.img_actor_t, t.img_critic_t, d_report);
+    }
+    ERLFILL_CUDA_TRY(cudaGetLastError());
+    return ERLFILL_OK;
+}
+
+}  // namespace utc
+}  // namespace erlfill

@@ -107,7 +107,7 @@ class DDPGLearner:
     """Flat-buffer ER-DDPG networks + optimiser state and the fused update (DDPGAgent.learn)."""
 
     def __init__(self, actor_sd, critic_sd, device="cuda", batch_size=128, gamma=0.99, tau=0.01, actor_lr=1e-4,
-                 critic_lr=1e-3, lr_decay_rate=0.999, precision="exact"):
+                 critic_lr=1e-3, lr_decay_rate=0.999, precision="exact", dropout="off", seed=0, rank=0):
         self.device = torch.device(device)
         d = self.device
         self.actor = FlatNet(ACTOR_LAYOUT, L.ACTOR_PARAMS, d)
@@ -129,6 +129,14 @@ class DDPGLearner:
         if precision not in ("exact", "fast"):
             raise L.ErlfillError("DDPGLearner: precision must be 'exact' (3xTF32, 1e-4 parity) or 'fast' (tcgen05 bf16 operands)")
         self.precision = precision
+        # dropout of the four networks inside learn(): "off" = module.eval(); "philox" = train() mode (what the reference runs:
+        # it never calls .eval() on this path), keep-masks from the counter-based generator; update(masks=...) injects them
+        if dropout not in ("off", "philox"):
+            raise L.ErlfillError("DDPGLearner: dropout must be 'off' or 'philox'")
+        self.dropout = dropout
+        self.seed, self.rank = int(seed), int(rank)
+        self.updates = 0                 # update index: Philox counter word of the dropout masks
+        self._images_ok = False          # bf16 weight images of the fast path match the fp32 parameters
         self.batch_size = batch_size
         self.use_graph = True
         self._graphs = {}
@@ -153,6 +161,7 @@ class DDPGLearner:
             # captured graphs hold the old workspace's address (and the old allocation may be reused by anything)
             self._graphs.clear()
             self._warm.clear()
+            self._images_ok = False
         return self._ws
 
     def precision_name(self):
@@ -194,7 +203,17 @@ class DDPGLearner:
                               L.ptr(v["hidden.7.weight"]), L.ptr(v["hidden.7.bias"]), L.ptr(v["emotion_weights"]),
                               L.ptr(self.scale), L.ptr(self.offset))
 
-    def update(self, batch, next_emotion, train_step, phases=L.PHASE_ALL, allreduce=None, graph=None):
+    def params_changed(self):
+        """Call after writing the flat parameter buffers from outside (checkpoint load, load_weights): the fast path's bf16
+        weight images are rebuilt before the next update."""
+        self._images_ok = False
+
+    def _pack_images(self, nets, ws, B):
+        with torch.cuda.device(self.device):
+            L.check(L.lib().erlfill_ddpg_pack_images(C.byref(nets), L.ptr(ws), C.c_int(B), L.stream_ptr()), "erlfill_ddpg_pack_images")
+        self._images_ok = True
+
+    def update(self, batch, next_emotion, train_step, phases=L.PHASE_ALL, allreduce=None, graph=None, masks=None):
         """One learn() on a gathered batch [B,20].  allreduce(tensor): optional in-place averaging callback
         applied to the critic bucket and then the actor bucket (data-parallel).
 
@@ -214,9 +233,27 @@ class DDPGLearner:
                           L.ptr(self.critic_v), L.ptr(self.scale_tab if multi else self.scale),
                           L.ptr(self.offset_tab if multi else self.offset))
         decay = self.lr_decay_rate ** train_step
+        fast = self.precision == "fast"
+        if fast and not self._images_ok:
+            self._pack_images(nets, ws, B)
+        mstruct = None
+        if masks is not None:            # ten uint8 keep arrays (include/erlfill.h: erlfill_ddpg_masks), parity runs only
+            mstruct = L.DDPGMasks()
+            self._mask_refs = [m.contiguous() for m in masks]
+            for i, m in enumerate(self._mask_refs):
+                mstruct.keep[i] = m.data_ptr()
+            graph = False
+        dmode = L.DROPOUT_MASK if masks is not None else (L.DROPOUT_PHILOX if self.dropout == "philox" else L.DROPOUT_OFF)
+        if dmode == L.DROPOUT_PHILOX:
+            graph = False                # the update index is a by-value launch parameter
+        if phases & L.PHASE_CRITIC_GRAD:
+            self.updates += 1
+        upd_idx = (self.updates - 1) & 0xFFFFFFFF      # one index per update, whichever way its phases are called
 
         def run(ph, adam_step):
-            hyper = L.DDPGHyper(B, adam_step, self.gamma, self.tau, 5.0, self.n_cond, self.critic_lr, self.actor_lr, decay)
+            hyper = L.DDPGHyper(B, adam_step, self.gamma, self.tau, 5.0, self.n_cond, self.critic_lr, self.actor_lr, decay,
+                                L.PRECISION_FAST if fast else L.PRECISION_EXACT, dmode, self.seed, upd_idx, self.rank,
+                                C.cast(C.pointer(mstruct), C.c_void_p) if mstruct is not None else None)
             with torch.cuda.device(self.device):
                 L.check(L.lib().erlfill_ddpg_update(C.byref(nets), C.byref(hyper), L.ptr(batch), L.ptr(next_emotion), L.ptr(ws),
                                                     C.c_int(ph), L.ptr(self.report), L.stream_ptr()), "erlfill_ddpg_update")

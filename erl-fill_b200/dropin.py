@@ -399,6 +399,9 @@ class DDPGAgent:
         self.actor_target = ActorFacade("Actor", lr.actor_target, lr.scale, lr.offset)
         self.critic = NetFacade("Critic", lr.critic, CRITIC_SD_ORDER)
         self.critic_target = NetFacade("Critic", lr.critic_target, CRITIC_SD_ORDER)
+        for f in (self.actor, self.actor_target, self.critic, self.critic_target):      # fast path: rebuild the bf16 weight images after a load
+            prev = getattr(f, "_on_load", None)
+            f._on_load = (lambda prev=prev: (prev() if prev is not None else None, lr.params_changed())[1])
         self.actor_optim = AdamFacade(lr.actor, lr.actor_m, lr.actor_v, self.actor_lr, lambda: lr.adam_step)
         self.critic_optim = AdamFacade(lr.critic, lr.critic_m, lr.critic_v, self.critic_lr, lambda: lr.adam_step)
         self.emotion = EmotionModuleNone(self.device)

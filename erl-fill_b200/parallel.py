@@ -137,6 +137,7 @@ class PeerExchange:
         self._learner = learner
         learner._graphs.clear()
         learner._warm.clear()
+        learner._images_ok = False       # the fast path's weight images live in the (new) workspace
         dist.barrier(group=group)        # every rank has mapped every block before the first exchange
 
     def exchange(self, which):

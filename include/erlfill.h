@@ -320,6 +320,17 @@ typedef struct {
     const float *scale, *offset;                       /* actor scale_params / offset_params [10] */
 } erlfill_ddpg_nets;
 
+/* Injected keep-masks (uint8 0/1) of the ten Dropout(0.2) layers one learn() evaluates, in at::dropout's draw order:
+ * keep[0,1] actor_target [B][128], keep[2,3] critic_target [B][256], keep[4,5] critic(s, a) [B][256], keep[6,7] actor [B][128],
+ * keep[8,9] critic(s, actor(s)) [B][256]   (ddpg_agent.py:40,43,150,155 through :468-483). */
+typedef struct { const uint8_t *keep[10]; } erlfill_ddpg_masks;
+
+typedef enum { ERLFILL_PRECISION_EXACT = 0,  /* 3xTF32 tensor-core GEMMs (mma.sync), fp32-level results: the 1e-4 parity path */
+               ERLFILL_PRECISION_FAST = 1    /* tcgen05 bf16 operands, fp32 accumulation in tensor memory, fp32 master weights / LayerNorm /
+                                              * optimiser; first layers hi/lo split (physical-unit inputs).  Six launches per update.  Needs
+                                              * erlfill_ddpg_pack_images after every external change of the parameters. */
+} erlfill_precision;
+
 typedef struct {
     int32_t batch;
     int32_t adam_step;        /* 1-based optimiser step of this update; 0 = scalars already uploaded by erlfill_ddpg_set_step */
@@ -327,6 +338,11 @@ typedef struct {
     int32_t n_cond;           /* <= 1: nets->scale / offset are [10]; > 1: [n_cond][10] tables indexed by column 19 of each record */
     double critic_lr, actor_lr;   /* base rates (1e-3, 1e-4) */
     double lr_decay;              /* lr_decay_rate ** train_step (ddpg_agent.py:455) */
+    int32_t precision;            /* erlfill_precision */
+    int32_t dropout_mode;         /* erlfill_dropout_mode: OFF = module.eval(); PHILOX / MASK = train() mode as the reference runs it */
+    uint64_t seed;                /* Philox key of the dropout masks */
+    uint32_t update_idx, rank;    /* Philox counter words: update index, data-parallel rank (row id = rank << 20 | minibatch row) */
+    const erlfill_ddpg_masks *masks;   /* ERLFILL_DROPOUT_MASK only */
 } erlfill_ddpg_hyper;
 
 typedef enum { ERLFILL_PHASE_CRITIC_GRAD = 1, ERLFILL_PHASE_CRITIC_APPLY = 2, ERLFILL_PHASE_ACTOR_GRAD = 4,
@@ -346,7 +362,11 @@ int erlfill_ddpg_grad_buckets(void *d_workspace, int batch, float **critic_grad,
  * erlfill_ddpg_update does this itself when hyper->adam_step >= 1; call it separately and pass hyper->adam_step = 0 to
  * replay one captured CUDA graph of the update for every step (the graph then contains no per-step constants). */
 int erlfill_ddpg_set_step(void *d_workspace, int batch, int adam_step, double lr_decay, void *stream);
-/* U1-U5 — DDPGAgent.learn (ddpg_agent.py:422-512), dropout off.  d_batch [B][ERLFILL_REC] gathered records,
+/* (Re)builds the bf16 weight images of the four networks inside the workspace from the fp32 parameters (ERLFILL_PRECISION_FAST).
+ * Call once after construction and after every external change of nets->* (checkpoint load, load_weights); the update keeps
+ * the images current by itself. */
+int erlfill_ddpg_pack_images(const erlfill_ddpg_nets *nets, void *d_workspace, int batch, void *stream);
+/* U1-U5 — DDPGAgent.learn (ddpg_agent.py:422-512).  d_batch [B][ERLFILL_REC] gathered records,
  * d_next_emotion [3] the agent's fresh emotion (:466).  d_report (optional) [4] = critic_loss, actor_loss,
  * critic_lr, actor_lr. */
 int erlfill_ddpg_update(const erlfill_ddpg_nets *nets, const erlfill_ddpg_hyper *hyper, const float *d_batch,

@@ -510,6 +510,80 @@ def gen_learn():
     print("learn: critic_loss", closs, "actor_loss", aloss, "lrs", lrs)
 
 
+def gen_learn_train():
+    """U2-U5 in the mode the reference actually runs: DDPGAgent.learn() x3 with actor / critic / both targets in train()
+    (Dropout(0.2) active in all five forwards, ddpg_agent.py:40,43,150,155).  torch is re-seeded before every learn() and the ten
+    keep-masks it drew are re-drawn from the same seed in at::dropout's order (empty_like(x).bernoulli_(0.8)): actor_target (2),
+    critic_target (2), critic (2), actor (2), critic (2).  The EmotionTransformer is put in eval() so that get_emotion() inside
+    learn() (:466) draws nothing from torch's generator; its output is recorded and injected on the other side."""
+    import torch
+    env, agent = _build_agent(0)
+    agent.emotion.transformer.eval()
+    torch.backends.mha.set_fastpath_enabled(False)
+    for m in (agent.actor, agent.actor_target, agent.critic, agent.critic_target):
+        m.train()
+    g = np.random.RandomState(19)
+    B = 128
+    agent.batch_size = B
+    n_buf = 600
+    buf = dict(states=(g.rand(n_buf, 2) * 5).astype(np.float32), actions=(g.rand(n_buf, 10) * 2 - 1).astype(np.float32),
+               rewards=g.uniform(-3000, 6000, n_buf), next_states=(g.rand(n_buf, 2) * 5).astype(np.float32),
+               dones=(g.rand(n_buf) < 0.05), emotions=g.rand(n_buf, 3).astype(np.float32))
+    for i in range(n_buf):
+        agent.memory.buffer.append((buf["states"][i], buf["actions"][i], float(buf["rewards"][i]),
+                                    buf["next_states"][i], bool(buf["dones"][i]), buf["emotions"][i], float("nan")))
+        agent.memory.priorities.append(1e-4)
+    for t in range(25):
+        agent.emotion.update(float(g.uniform(-2000, 4000)), (g.rand(2) - 0.5).astype(np.float32))
+    out = {}
+    out.update(_sd(agent.actor, "a0."))
+    out.update(_sd(agent.critic, "c0."))
+    for k, v in buf.items():
+        out["buf_" + k] = np.asarray(v)
+    agent.train_step = 3
+    np.random.seed(77)
+    idx_all, closs, aloss, lrs, next_emotions = [], [], [], [], []
+    orig_choice = np.random.choice
+    orig_get = agent.emotion.get_emotion
+
+    def tap_choice(n, size, p=None):
+        r = orig_choice(n, size, p=p)
+        idx_all.append(np.array(r))
+        return r
+
+    def tap_get():
+        e = orig_get()
+        next_emotions.append(np.array(e))
+        return e
+    np.random.choice = tap_choice
+    agent.emotion.get_emotion = tap_get
+    shapes = [((B, 128), 0.2)] * 2 + [((B, 256), 0.2)] * 4 + [((B, 128), 0.2)] * 2 + [((B, 256), 0.2)] * 2
+    try:
+        for it in range(3):
+            torch.manual_seed(500 + it)
+            loss = agent.learn()
+            closs.append(loss["critic_loss"]); aloss.append(loss["actor_loss"])
+            lrs.append((agent.critic_optim.param_groups[0]["lr"], agent.actor_optim.param_groups[0]["lr"]))
+            masks = _replay_masks(500 + it, shapes)
+            for s, m in enumerate(masks):
+                out[f"mask{it}_{s}"] = np.packbits(m.numpy().astype(np.uint8), axis=-1)
+            out.update(_sd(agent.actor, f"a{it + 1}."))
+            out.update(_sd(agent.critic, f"c{it + 1}."))
+            out.update(_sd(agent.actor_target, f"at{it + 1}."))
+            out.update(_sd(agent.critic_target, f"ct{it + 1}."))
+    finally:
+        np.random.choice = orig_choice
+    out["idx"] = np.array(idx_all)
+    out["critic_loss"] = np.array(closs)
+    out["actor_loss"] = np.array(aloss)
+    out["lrs"] = np.array(lrs)
+    out["next_emotion"] = np.array(next_emotions)
+    out["train_step"] = 3
+    out["meta"] = _meta("U2-U5 DDPGAgent.learn x3, train()-mode nets (dropout masks replayed), B=128, injected buffer")
+    np.savez_compressed(os.path.join(GOLD, "learn_train_golden.npz"), **out)
+    print("learn_train: critic_loss", closs, "actor_loss", aloss, "lrs", lrs)
+
+
 # ----------------------------------------------------------------------------------------
 def gen_td3sac():
     """T1 vectors: TD3Agent.train_step() x4 and SACAgent.update() x3 of the unmodified reference on an injected
@@ -807,4 +881,4 @@ if __name__ == "__main__":
     os.chdir("/tmp")
     for w in which:
         {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion, "nets": gen_nets, "learn": gen_learn, "td3sac": gen_td3sac, "loop": gen_loop, "esac": gen_esac,
-         "onboard": gen_onboard}[w]()
+         "onboard": gen_onboard, "learn_train": gen_learn_train}[w]()

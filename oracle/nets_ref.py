@@ -34,8 +34,53 @@ def _drop(x, mask, p):
 
 
 # ---------------------------------------------------------------------------------------------
-def actor_forward(W, state, emotion, masks=None, return_base=False):
-    """masks: None or (m1[B,128], m2[B,128]) keep-masks of the two Dropout(0.2) layers."""
+# Emulation of the rounding points of the tcgen05 ("fast") update path (csrc/update_tc.cu): every GEMM operand is rounded to bf16,
+# products are accumulated in fp32; everything else (LayerNorm, activations, losses, bias / LayerNorm gradients, optimiser) is fp32.
+# It pins the kernel's LOGIC tightly; the distance of this emulation from the plain fp32 functions is the price of bf16 operands.
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+class _Bf16Linear(torch.autograd.Function):
+    """y = bf(x) bf(W)^T + b;  dX = bf(dY) bf(W);  dW = bf(dY)^T bf(x);  db = sum dY (fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        xb, Wb = _bf(x), _bf(W)
+        ctx.save_for_backward(xb, Wb)
+        return xb @ Wb.t() + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, Wb = ctx.saved_tensors
+        dyb = _bf(dy)
+        return dyb @ Wb, dyb.t() @ xb, dy.sum(0)
+
+
+class _SplitLinear(torch.autograd.Function):
+    """First layers: the forward is the hi/lo-split product (fp32-accurate to ~2^-16); the gradients use the bf16 hi parts only."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        ctx.save_for_backward(_bf(x), _bf(W))
+        return x @ W.t() + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, Wb = ctx.saved_tensors
+        dyb = _bf(dy)
+        return dyb @ Wb, dyb.t() @ xb, dy.sum(0)
+
+
+def _lin(x, W, b, emu, first=False):
+    if not emu:
+        return F.linear(x, W, b)
+    return (_SplitLinear if first else _Bf16Linear).apply(x, W, b)
+
+
+# ---------------------------------------------------------------------------------------------
+def actor_forward(W, state, emotion, masks=None, return_base=False, emu=False):
+    """masks: None or (m1[B,128], m2[B,128]) keep-masks of the two Dropout(0.2) layers.  emu: bf16-operand emulation (see _lin)."""
     if emotion.dim() == 1:
         emotion = emotion.unsqueeze(0)
     if state.dim() == 1:
@@ -44,13 +89,13 @@ def actor_forward(W, state, emotion, masks=None, return_base=False):
         emotion = emotion.expand(state.size(0), -1)
     m1, m2 = masks if masks is not None else (None, None)
     x = torch.cat([state, emotion], dim=1)
-    x = F.linear(x, W["input_layer.weight"], W["input_layer.bias"])
+    x = _lin(x, W["input_layer.weight"], W["input_layer.bias"], emu, first=True)
     x = F.leaky_relu(x, 0.1)
     x = _drop(x, m1, ACTOR_P)
-    x = F.relu(F.linear(x, W["hidden.2.weight"], W["hidden.2.bias"]))
+    x = F.relu(_lin(x, W["hidden.2.weight"], W["hidden.2.bias"], emu))
     x = _drop(x, m2, ACTOR_P)
-    x = F.relu(F.linear(x, W["hidden.5.weight"], W["hidden.5.bias"]))
-    x = F.linear(x, W["hidden.7.weight"], W["hidden.7.bias"])
+    x = F.relu(_lin(x, W["hidden.5.weight"], W["hidden.5.bias"], emu))
+    x = _lin(x, W["hidden.7.weight"], W["hidden.7.bias"], emu)
     base = F.softsign(x)
     curiosity, conserv, anxiety = emotion[:, 0:1], emotion[:, 1:2], emotion[:, 2:3]
     raw_effect = torch.tanh((emotion @ W["emotion_weights"]) * 1.5)
@@ -65,7 +110,7 @@ def actor_forward(W, state, emotion, masks=None, return_base=False):
     return (out, base) if return_base else out
 
 
-def critic_forward(W, state, action, emotion, masks=None, pre_normalized=None):
+def critic_forward(W, state, action, emotion, masks=None, pre_normalized=None, emu=False):
     """masks: None or (m1[B,256], m2[B,256]).  Emotion is standardised with BATCH statistics
     (unbiased std), ddpg_agent.py:176 — B = 1 gives NaN; all-equal rows give (e-mean)/1e-6, i.e. torch's
     summation rounding noise amplified by 1e6 (0 in exact arithmetic).  pre_normalized: use this tensor as
@@ -76,13 +121,13 @@ def critic_forward(W, state, action, emotion, masks=None, pre_normalized=None):
     else:
         emotion = (emotion - emotion.mean(dim=0, keepdim=True)) / (emotion.std(dim=0, keepdim=True) + 1e-6)
     x = torch.cat([state, action, emotion], dim=1)
-    x = F.linear(x, W["net.0.weight"], W["net.0.bias"])
+    x = _lin(x, W["net.0.weight"], W["net.0.bias"], emu, first=True)
     x = F.layer_norm(x, (256,), W["net.1.weight"], W["net.1.bias"], 1e-5)
     x = _drop(F.leaky_relu(x, 0.1), m1, CRITIC_P)
-    x = F.linear(x, W["net.4.weight"], W["net.4.bias"])
+    x = _lin(x, W["net.4.weight"], W["net.4.bias"], emu)
     x = F.layer_norm(x, (256,), W["net.5.weight"], W["net.5.bias"], 1e-5)
     x = _drop(F.relu(x), m2, CRITIC_P)
-    x = F.relu(F.linear(x, W["net.8.weight"], W["net.8.bias"]))
+    x = F.relu(_lin(x, W["net.8.weight"], W["net.8.bias"], emu))
     q = F.linear(x, W["net.10.weight"], W["net.10.bias"])
     return torch.clamp(q, -1e6, 1e6)
 
@@ -155,13 +200,14 @@ def adam_step(params, grads, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8):
 
 def ddpg_learn(actor, actor_t, critic, critic_t, opt, batch, next_emotion, train_step,
                masks=None, gamma=0.99, tau=0.01, actor_lr=1e-4, critic_lr=1e-3, lr_decay=0.999,
-               exact_target_emotion=False):
+               exact_target_emotion=False, emu=False, debug=None):
     """One DDPGAgent.learn() (ddpg_agent.py:436-512) on explicit tensors.
 
     actor/actor_t/critic/critic_t: weight dicts (updated in place); opt: {"am","av","cm","cv","step"}
     Adam state; batch: dict(states[B,2], actions[B,10] normalised, rewards[B], next_states[B,2],
     dones[B], emotions[B,3]); next_emotion[3] = the fresh get_emotion() of :466.
     masks: None (eval) or dict with keys at_/ct_/c_/a_/c2_ -> mask pairs for the five forwards.
+    emu: emulate the bf16 operand rounding of the tcgen05 update path (see _lin).
     Returns (critic_loss, actor_loss, lrs)."""
     mk = masks or {}
     s, a, r = batch["states"], batch["actions"], batch["rewards"].unsqueeze(1) * 0.01
@@ -174,15 +220,18 @@ def ddpg_learn(actor, actor_t, critic, critic_t, opt, batch, next_emotion, train
     a_lr = float(min(max(actor_lr * actor_factor * decay, actor_lr * 0.1), actor_lr * 3))
     with torch.no_grad():
         ne = next_emotion.view(1, 3).expand(s2.size(0), -1)
-        a2 = actor_forward(actor_t, s2, ne, mk.get("at"))
+        a2 = actor_forward(actor_t, s2, ne, mk.get("at"), emu=emu)
         tq = critic_forward(critic_t, s2, a2, ne, mk.get("ct"),
-                            pre_normalized=torch.zeros_like(ne) if exact_target_emotion else None)
+                            pre_normalized=torch.zeros_like(ne) if exact_target_emotion else None, emu=emu)
         y = r + (1 - d) * gamma * tq
     cp = [critic[k].clone().requires_grad_(True) for k in CRITIC_PARAM_ORDER]
     cw = dict(zip(CRITIC_PARAM_ORDER, cp))
-    q = critic_forward(cw, s, a, e, mk.get("c"))
+    q = critic_forward(cw, s, a, e, mk.get("c"), emu=emu)
     critic_loss = F.smooth_l1_loss(q, y)
     cg = torch.autograd.grad(critic_loss, cp)
+    if debug is not None:
+        debug["critic_grad"] = torch.cat([g.reshape(-1) for g in cg]).clone()
+        debug["q"], debug["y"] = q.detach().clone(), y.clone()
     cg, _ = _clip_grad_norm_(list(cg), 5.0)
     opt["step"] += 1
     new_c = adam_step([p.detach() for p in cp], cg, opt["cm"], opt["cv"], opt["step"], c_lr)
@@ -191,14 +240,17 @@ def ddpg_learn(actor, actor_t, critic, critic_t, opt, batch, next_emotion, train
     ap = [actor[k].clone().requires_grad_(True) for k in ACTOR_PARAM_ORDER]
     aw = dict(zip(ACTOR_PARAM_ORDER, ap))
     aw["scale_params"], aw["offset_params"] = actor["scale_params"], actor["offset_params"]
-    act_out = actor_forward(aw, s, e, mk.get("a"))
-    actor_loss = -critic_forward(critic, s, act_out, e, mk.get("c2")).mean()
+    act_out = actor_forward(aw, s, e, mk.get("a"), emu=emu)
+    actor_loss = -critic_forward(critic, s, act_out, e, mk.get("c2"), emu=emu).mean()
     actor_loss = actor_loss - 0.03 * torch.std(act_out, dim=1).mean()
     l2 = torch.tensor(0.0)
     for p in ap:
         l2 = l2 + torch.norm(p, p=2)
     actor_loss = actor_loss + 1e-4 * l2
     ag = torch.autograd.grad(actor_loss, ap)
+    if debug is not None:
+        debug["actor_grad"] = torch.cat([g.reshape(-1) for g in ag]).clone()
+        debug["action_out"] = act_out.detach().clone()
     ag, _ = _clip_grad_norm_(list(ag), 5.0)
     new_a = adam_step([p.detach() for p in ap], ag, opt["am"], opt["av"], opt["step"], a_lr)
     for k, p in zip(ACTOR_PARAM_ORDER, new_a):

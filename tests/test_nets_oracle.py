@@ -105,6 +105,45 @@ def test_learn_three_updates(golden_dir):
             torch.testing.assert_close(critic_t[k], T(g[f"ct{it + 1}.{k}"]), rtol=2e-4, atol=5e-6)
 
 
+def golden_masks(g, it, B=128):
+    """The ten keep-masks of update `it` of tests/golden/learn_train_golden.npz as the oracle's dict and as a flat list."""
+    widths = [128, 128, 256, 256, 256, 256, 128, 128, 256, 256]
+    ms = [torch.from_numpy(np.unpackbits(g[f"mask{it}_{s}"], axis=-1)[:, :w].astype(np.float32)) for s, w in enumerate(widths)]
+    return {"at": (ms[0], ms[1]), "ct": (ms[2], ms[3]), "c": (ms[4], ms[5]), "a": (ms[6], ms[7]), "c2": (ms[8], ms[9])}, ms
+
+
+def test_learn_train_mode_three_updates(golden_dir):
+    """The mode the reference really runs: all four networks in train() — Dropout(0.2) active in the five forwards of learn().
+    The oracle with the replayed masks reproduces the reference's losses, learning rates and parameters."""
+    g = np.load(os.path.join(golden_dir, "learn_train_golden.npz"))
+    actor, critic = load_weights(g, "a0."), load_weights(g, "c0.")
+    actor_t = {k: v.clone() for k, v in actor.items()}
+    critic_t = {k: v.clone() for k, v in critic.items()}
+    opt = {"am": [torch.zeros_like(actor[k]) for k in R.ACTOR_PARAM_ORDER],
+           "av": [torch.zeros_like(actor[k]) for k in R.ACTOR_PARAM_ORDER],
+           "cm": [torch.zeros_like(critic[k]) for k in R.CRITIC_PARAM_ORDER],
+           "cv": [torch.zeros_like(critic[k]) for k in R.CRITIC_PARAM_ORDER], "step": 0}
+    for it in range(3):
+        idx = g["idx"][it]
+        batch = {"states": T(g["buf_states"][idx]), "actions": T(g["buf_actions"][idx]),
+                 "rewards": T(g["buf_rewards"][idx]).float(), "next_states": T(g["buf_next_states"][idx]),
+                 "dones": T(g["buf_dones"][idx]).float(), "emotions": T(g["buf_emotions"][idx])}
+        masks, _ = golden_masks(g, it)
+        cl, al, (c_lr, a_lr) = R.ddpg_learn(actor, actor_t, critic, critic_t, opt, batch, T(g["next_emotion"][it]),
+                                            int(g["train_step"]), masks=masks)
+        assert abs(cl - g["critic_loss"][it]) <= 2e-5 * abs(g["critic_loss"][it])
+        assert abs(al - g["actor_loss"][it]) <= 2e-5 * abs(g["actor_loss"][it])
+        assert abs(c_lr - g["lrs"][it][0]) < 1e-12 and abs(a_lr - g["lrs"][it][1]) < 1e-12
+        for k in R.ACTOR_PARAM_ORDER:
+            torch.testing.assert_close(actor[k], T(g[f"a{it + 1}.{k}"]), rtol=2e-4, atol=2e-6)
+            torch.testing.assert_close(actor_t[k], T(g[f"at{it + 1}.{k}"]), rtol=2e-4, atol=2e-6)
+        for k in R.CRITIC_PARAM_ORDER:
+            torch.testing.assert_close(critic[k], T(g[f"c{it + 1}.{k}"]), rtol=2e-4, atol=5e-6)
+            torch.testing.assert_close(critic_t[k], T(g[f"ct{it + 1}.{k}"]), rtol=2e-4, atol=5e-6)
+    e = np.load(os.path.join(golden_dir, "learn_golden.npz"))
+    assert abs(g["critic_loss"][0] - e["critic_loss"][0]) > 1e-3          # a different algorithm from the eval()-mode one
+
+
 def test_init_reproduces_reference_construction(G):
     """erl-fill_b200/init.py consumes torch's RNG in the reference's order: same seed, same weights."""
     import erlfill_b200

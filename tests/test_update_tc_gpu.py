@@ -1,0 +1,199 @@
+"""GPU: the tcgen05 ("fast") ER-DDPG update (csrc/update_tc.cu, ERLFILL_PRECISION_FAST) and train()-mode dropout in both update paths.
+
+Bars (each stated where it is asserted):
+  * fast path vs a torch emulation of ITS OWN rounding points (bf16 GEMM operands, fp32 everything else: oracle/nets_ref.py `emu=True`):
+    raw gradients 1e-2 of their scale (an operand that sits on a bf16 rounding boundary may round the other way), losses 1e-3 relative — this pins the kernel's logic;
+  * fast path vs the plain fp32 restatement (which is pinned on the reference's own learn(), tests/test_nets_oracle.py): the STATED bf16
+    tolerance — losses 2e-2 relative, gradients 3e-2 of their scale (cosine > 0.999), parameters after Adam within 2.2 lr of the fp32
+    result (Adam's first steps move every element by about lr, whatever the gradient's size);
+  * exact path with injected dropout masks vs the REFERENCE's train()-mode learn() x3 (tests/golden/learn_train_golden.npz): the
+    existing 1e-4 bars;  Philox masks rebuilt on the host (oracle/philox.py) give the same update as injecting them."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import nets_ref as R  # noqa: E402  (checker only)
+from oracle import philox as PH  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+T = torch.from_numpy
+
+
+def _w(g, prefix):
+    return {k[len(prefix):]: T(np.asarray(g[k])).float() for k in g.files if k.startswith(prefix)}
+
+
+def _opt(actor, critic):
+    return {"am": [torch.zeros_like(actor[k]) for k in R.ACTOR_PARAM_ORDER], "av": [torch.zeros_like(actor[k]) for k in R.ACTOR_PARAM_ORDER],
+            "cm": [torch.zeros_like(critic[k]) for k in R.CRITIC_PARAM_ORDER], "cv": [torch.zeros_like(critic[k]) for k in R.CRITIC_PARAM_ORDER],
+            "step": 0}
+
+
+def _batch(g, idx):
+    rows = np.zeros((len(idx), 20), np.float32)
+    rows[:, 0:2] = g["buf_states"][idx]; rows[:, 2:12] = g["buf_actions"][idx]; rows[:, 12] = g["buf_rewards"][idx]
+    rows[:, 13:15] = g["buf_next_states"][idx]; rows[:, 15] = g["buf_dones"][idx]; rows[:, 16:19] = g["buf_emotions"][idx]
+    bd = {"states": T(rows[:, 0:2].copy()), "actions": T(rows[:, 2:12].copy()), "rewards": T(rows[:, 12].copy()),
+          "next_states": T(rows[:, 13:15].copy()), "dones": T(rows[:, 15].copy()), "emotions": T(rows[:, 16:19].copy())}
+    return torch.tensor(rows, device="cuda"), bd
+
+
+def _learner(g, precision, dropout="off", batch=128):
+    from erlfill_b200 import ddpg
+    return ddpg.DDPGLearner(_w(g, "a0."), _w(g, "c0."), batch_size=batch, precision=precision, dropout=dropout, seed=99)
+
+
+def _flat(d, order):
+    return torch.cat([d[k].reshape(-1) for k in order])
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def _mask_dict(ms):
+    f = [T(m.astype(np.float32)) if isinstance(m, np.ndarray) else m.float().cpu() for m in ms]
+    return {"at": (f[0], f[1]), "ct": (f[2], f[3]), "c": (f[4], f[5]), "a": (f[6], f[7]), "c2": (f[8], f[9])}
+
+
+@pytest.mark.parametrize("B,dropout", [(128, "off"), (300, "off"), (128, "mask"), (256, "mask")])
+def test_fast_update_matches_its_emulation_and_the_fp32_oracle(B, dropout):
+    from erlfill_b200 import _lib as L
+    g = np.load(os.path.join(GOLD, "learn_golden.npz"))
+    rng = np.random.RandomState(B)
+    lrn = _learner(g, "fast", batch=B)
+    actor, critic = _w(g, "a0."), _w(g, "c0.")
+    st = {m: ({k: v.clone() for k, v in actor.items()}, {k: v.clone() for k, v in actor.items()},
+              {k: v.clone() for k, v in critic.items()}, {k: v.clone() for k, v in critic.items()}, _opt(actor, critic)) for m in ("emu", "f32")}
+    for it in range(3):
+        idx = rng.randint(0, 600, B)
+        batch, bd = _batch(g, idx)
+        ne = T(g["next_emotion"][it]).float()
+        masks_np = [(rng.rand(B, w) < 0.8).astype(np.uint8) for w in PH.DDPG_SITE_WIDTHS] if dropout == "mask" else None
+        masks_dev = [torch.tensor(m, device="cuda") for m in masks_np] if masks_np else None
+        md = _mask_dict(masks_np) if masks_np else None
+        dbg = {}
+        res = {}
+        for m in ("emu", "f32"):
+            a, at, c, ct, opt = st[m]
+            dbg[m] = {}
+            res[m] = R.ddpg_learn(a, at, c, ct, opt, bd, ne, 7, masks=md, exact_target_emotion=True, emu=(m == "emu"), debug=dbg[m])
+        # phase by phase, so that the raw gradients can be looked at
+        ned = ne.cuda()
+        lrn.update(batch, ned, 7, phases=L.PHASE_CRITIC_GRAD, masks=masks_dev)
+        cg = lrn.grad_buckets(B)[0][:L.CRITIC_PARAMS].cpu()
+        lrn.update(batch, ned, 7, phases=L.PHASE_CRITIC_APPLY, masks=masks_dev)
+        lrn.update(batch, ned, 7, phases=L.PHASE_ACTOR_GRAD, masks=masks_dev)
+        ag = lrn.grad_buckets(B)[1][:L.ACTOR_PARAMS].cpu()
+        rep = lrn.update(batch, ned, 7, phases=L.PHASE_ACTOR_APPLY, masks=masks_dev).cpu().numpy()
+        torch.cuda.synchronize()
+        tag = "B=%d %s update %d" % (B, dropout, it)
+        print(tag, "critic grad vs emu %.2e vs f32 %.2e | actor grad vs emu %.2e vs f32 %.2e | losses %s emu %s f32 %s" % (
+            _rel(cg, dbg["emu"]["critic_grad"]), _rel(cg, dbg["f32"]["critic_grad"]), _rel(ag, dbg["emu"]["actor_grad"]),
+            _rel(ag, dbg["f32"]["actor_grad"]), rep[:2], res["emu"][:2], res["f32"][:2]))
+        # the kernel's logic: against the emulation of its own rounding points
+        assert _rel(cg, dbg["emu"]["critic_grad"]) < 1e-2, tag
+        assert _rel(ag, dbg["emu"]["actor_grad"]) < 1e-2, tag
+        np.testing.assert_allclose(rep[0], res["emu"][0], rtol=1e-3, err_msg=tag)
+        np.testing.assert_allclose(rep[1], res["emu"][1], rtol=1e-3, err_msg=tag)
+        np.testing.assert_allclose(rep[2:], res["f32"][2], rtol=1e-6)
+        # the stated bf16 tolerance: against the fp32 restatement of the reference
+        assert _rel(cg, dbg["f32"]["critic_grad"]) < 3e-2 and _rel(ag, dbg["f32"]["actor_grad"]) < 3e-2, tag
+        for x, y in ((cg, dbg["f32"]["critic_grad"]), (ag, dbg["f32"]["actor_grad"])):
+            assert float(torch.dot(x, y) / (x.norm() * y.norm())) > 0.999, tag
+        np.testing.assert_allclose(rep[0], res["f32"][0], rtol=2e-2, err_msg=tag)
+        np.testing.assert_allclose(rep[1], res["f32"][1], rtol=2e-2, err_msg=tag)
+        c_lr, a_lr = res["f32"][2]
+        for name, flat, ref, lr in (("actor", lrn.actor.flat, _flat(st["f32"][0], R.ACTOR_PARAM_ORDER), a_lr),
+                                    ("critic", lrn.critic.flat, _flat(st["f32"][2], R.CRITIC_PARAM_ORDER), c_lr),
+                                    ("actor_target", lrn.actor_target.flat, _flat(st["f32"][1], R.ACTOR_PARAM_ORDER), a_lr),
+                                    ("critic_target", lrn.critic_target.flat, _flat(st["f32"][3], R.CRITIC_PARAM_ORDER), c_lr)):
+            d = (flat.cpu() - ref).abs()
+            assert float(d.max()) <= 2.2 * lr * (it + 1), (tag, name, float(d.max()), lr)
+        # the next update must see THIS path's parameters in the oracles too (no drift between the three trajectories)
+        for m in ("emu", "f32"):
+            a, at, c, ct, opt = st[m]
+            for dst, src, order in ((a, lrn.actor, R.ACTOR_PARAM_ORDER), (at, lrn.actor_target, R.ACTOR_PARAM_ORDER),
+                                    (c, lrn.critic, R.CRITIC_PARAM_ORDER), (ct, lrn.critic_target, R.CRITIC_PARAM_ORDER)):
+                sd = src.state_dict()
+                for k in order:
+                    dst[k] = sd[k].cpu().clone()
+            flat_m = lambda t, order, d: [t[o:o + d[k].numel()].view_as(d[k]).cpu().clone() for k, o in zip(order, np.cumsum([0] + [d[k].numel() for k in order])[:-1])]
+            opt["am"], opt["av"] = flat_m(lrn.actor_m, R.ACTOR_PARAM_ORDER, a), flat_m(lrn.actor_v, R.ACTOR_PARAM_ORDER, a)
+            opt["cm"], opt["cv"] = flat_m(lrn.critic_m, R.CRITIC_PARAM_ORDER, c), flat_m(lrn.critic_v, R.CRITIC_PARAM_ORDER, c)
+
+
+def test_fast_update_whole_call_and_graph_replay_equal_the_phased_calls():
+    from erlfill_b200 import _lib as L
+    g = np.load(os.path.join(GOLD, "learn_golden.npz"))
+    a, b, c = _learner(g, "fast"), _learner(g, "fast"), _learner(g, "fast")
+    c.use_graph = False
+    ne = T(g["next_emotion"][0]).float().cuda()
+    batch, _ = _batch(g, g["idx"][0])
+    for it in range(4):
+        for ph in (L.PHASE_CRITIC_GRAD, L.PHASE_CRITIC_APPLY, L.PHASE_ACTOR_GRAD, L.PHASE_ACTOR_APPLY):
+            ra = a.update(batch, ne, 7, phases=ph)
+        rb = b.update(batch, ne, 7)          # eager the first time, one captured graph afterwards
+        rc = c.update(batch, ne, 7)
+        torch.cuda.synchronize()
+        assert torch.equal(ra, rb) and torch.equal(ra, rc), it
+        for x, y, z in ((a.actor, b.actor, c.actor), (a.critic, b.critic, c.critic), (a.actor_target, b.actor_target, c.actor_target),
+                        (a.critic_target, b.critic_target, c.critic_target)):
+            assert torch.equal(x.flat, y.flat) and torch.equal(x.flat, z.flat), it      # ordered reductions: bit-reproducible
+
+
+def test_exact_update_train_mode_matches_the_reference():
+    """Injected masks, exact (3xTF32) path, against the reference's own train()-mode learn() x3."""
+    g = np.load(os.path.join(GOLD, "learn_train_golden.npz"))
+    lrn = _learner(g, "exact")
+    widths = PH.DDPG_SITE_WIDTHS
+    for it in range(3):
+        batch, _ = _batch(g, g["idx"][it])
+        masks = [torch.tensor(np.unpackbits(g[f"mask{it}_{s}"], axis=-1)[:, :w].copy(), device="cuda") for s, w in enumerate(widths)]
+        rep = lrn.update(batch, T(g["next_emotion"][it]).float().cuda(), int(g["train_step"]), masks=masks).cpu().numpy()
+        # losses: the reference standardises the target's identical emotion rows into summation noise (+-0.36),
+        # the kernels define them as exactly 0 -> the same 2e-2 / 1e-3 bars as the eval()-mode test (tests/test_update_gpu.py)
+        np.testing.assert_allclose(rep[0], g["critic_loss"][it], rtol=2e-2)
+        np.testing.assert_allclose(rep[1], g["actor_loss"][it], rtol=1e-3)
+        np.testing.assert_allclose(rep[2:], g["lrs"][it], rtol=1e-6)
+    # against the oracle with the SAME definition of the target emotion: 1e-4
+    lrn = _learner(g, "exact")
+    actor, critic = _w(g, "a0."), _w(g, "c0.")
+    actor_t, critic_t = {k: v.clone() for k, v in actor.items()}, {k: v.clone() for k, v in critic.items()}
+    opt = _opt(actor, critic)
+    for it in range(3):
+        batch, bd = _batch(g, g["idx"][it])
+        ms = [np.unpackbits(g[f"mask{it}_{s}"], axis=-1)[:, :w].copy() for s, w in enumerate(widths)]
+        cl, al, _ = R.ddpg_learn(actor, actor_t, critic, critic_t, opt, bd, T(g["next_emotion"][it]).float(), int(g["train_step"]),
+                                 masks=_mask_dict(ms), exact_target_emotion=True)
+        rep = lrn.update(batch, T(g["next_emotion"][it]).float().cuda(), int(g["train_step"]),
+                         masks=[torch.tensor(m, device="cuda") for m in ms]).cpu().numpy()
+        np.testing.assert_allclose(rep[0], cl, rtol=1e-4)
+        np.testing.assert_allclose(rep[1], al, rtol=1e-4)
+        for name, flat, ref in (("actor", lrn.actor.flat, _flat(actor, R.ACTOR_PARAM_ORDER)), ("critic", lrn.critic.flat, _flat(critic, R.CRITIC_PARAM_ORDER))):
+            d = (flat.cpu() - ref).abs()
+            assert float((d > 1e-5 + 5e-3 * ref.abs()).float().mean()) < 0.02, (name, it)
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_philox_dropout_equals_injecting_the_same_masks(precision):
+    """ERLFILL_DROPOUT_PHILOX: the keep-masks are a pure function of (seed, update index, rank, row, site, column); rebuilt on the
+    host with numpy (oracle/philox.py) and injected, they give the same update bit for bit."""
+    g = np.load(os.path.join(GOLD, "learn_golden.npz"))
+    a, b = _learner(g, precision, dropout="philox"), _learner(g, precision)
+    ne = T(g["next_emotion"][0]).float().cuda()
+    for it in range(2):
+        batch, _ = _batch(g, g["idx"][it])
+        ra = a.update(batch, ne, 7)
+        masks = [torch.tensor(m, device="cuda") for m in PH.ddpg_keep_masks(99, it, 0, 128)]
+        rb = b.update(batch, ne, 7, masks=masks)
+        torch.cuda.synchronize()
+        assert torch.equal(ra, rb), (precision, it, ra, rb)
+        assert torch.equal(a.actor.flat, b.actor.flat) and torch.equal(a.critic.flat, b.critic.flat)
+    off = _learner(g, precision)
+    r0 = off.update(_batch(g, g["idx"][0])[0], ne, 7)
+    assert abs(float(r0[0]) - float(a.report[0])) > 1e-4          # dropout is really on
