@@ -466,7 +466,7 @@ def wl_update(args, rank, world, device, timer):
         "timing": dict(TIMING, exchange="none" if world == 1 else args.exchange, dropout=args.dropout, precision=args.update_precision,
                        note="value counts per-GPU minibatch updates; sync_steps_per_sec the optimiser steps on the global batch"),
         "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": B * 80, "d2h_bytes_per_step": 16},
-        "gpu_launches": (2 + agent.learner.launches_per_update(world > 1)) * args.steps,      # sample + gather + the update
+        "gpu_launches": (1 + agent.learner.launches_per_update(world > 1)) * args.steps,      # sample_gather + the update
         "dp_check": dp,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
@@ -653,7 +653,7 @@ def wl_erddpg(args, rank, world, device, timer):
         "ticks_per_sec": ticks_all / (total_ms * 1e-3), "mean_ticks_per_env_step": ticks_all / units,
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": obs_host.numel() * 4,
                 "d2h_bytes_per_step": n * 13 + 16},
-        "gpu_launches": (agent.launches_per_rollout_step() + 2 + agent.learner.launches_per_update(world > 1)) * args.steps,
+        "gpu_launches": (agent.launches_per_rollout_step() + 1 + agent.learner.launches_per_update(world > 1)) * args.steps,
         "roofline": _transformer_roofline(agent, n, tf_ms, total_ms / args.steps),
     }
 

@@ -90,7 +90,8 @@ class DDPGHyper(C.Structure):
     _fields_ = [("batch", C.c_int32), ("adam_step", C.c_int32), ("gamma", C.c_float), ("tau", C.c_float),
                 ("max_grad_norm", C.c_float), ("n_cond", C.c_int32), ("critic_lr", C.c_double),
                 ("actor_lr", C.c_double), ("lr_decay", C.c_double), ("precision", C.c_int32), ("dropout_mode", C.c_int32),
-                ("seed", C.c_uint64), ("update_idx", C.c_uint32), ("rank", C.c_uint32), ("masks", C.c_void_p)]
+                ("seed", C.c_uint64), ("update_idx", C.c_uint32), ("rank", C.c_uint32), ("masks", C.c_void_p),
+                ("d_stats_partials", C.c_void_p), ("n_stats_partials", C.c_int32), ("_pad2", C.c_int32)]
 
 
 class TD3Nets(C.Structure):
@@ -136,7 +137,8 @@ EXPORTS = [
     "erlfill_env_step_fused_max_envs",
     "erlfill_actor_forward", "erlfill_actor_forward_cond", "erlfill_replay_insert_cond", "erlfill_emotion_update", "erlfill_episode_end", "erlfill_emotion_forward",
     "erlfill_emotion_tc_image_bytes", "erlfill_emotion_tc_pack", "erlfill_emotion_forward_tc",
-    "erlfill_replay_insert", "erlfill_replay_sample", "erlfill_replay_gather",
+    "erlfill_replay_insert", "erlfill_replay_sample", "erlfill_replay_gather", "erlfill_replay_sample_gather",
+    "erlfill_replay_sample_gather_blocks",
     "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_set_step", "erlfill_ddpg_update", "erlfill_ddpg_pack_images",
     "erlfill_ddpg_exchange_buffers", "erlfill_ddpg_update_launches", "erlfill_ddpg_peer_launches", "erlfill_peer_ctrl_bytes", "erlfill_peer_alloc", "erlfill_peer_open", "erlfill_peer_close",
     "erlfill_peer_free", "erlfill_ddpg_peer_allreduce", "erlfill_peer_error",

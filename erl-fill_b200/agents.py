@@ -14,6 +14,8 @@ its own emotion history; with dropout off one transformer call per step serves a
 get_emotion() call sites (they differ only by their dropout draws); learn()'s fresh emotion (:466) is the mean of
 e_{t+1} over this rank's envs (N = 1: the reference's value); train_step = 1 + completed episodes // N.
 """
+import ctypes as C
+
 import torch
 
 from . import _lib as L
@@ -51,6 +53,7 @@ class VecERDDPG:
         self.next_emotion = torch.zeros(3, dtype=torch.float32, device=d)
         self.idx = torch.zeros(batch_size, dtype=torch.int64, device=d)
         self.batch = torch.zeros(batch_size, L.REC, dtype=torch.float32, device=d)
+        self._stats_partials = torch.zeros(L.lib().erlfill_replay_sample_gather_blocks(C.c_int(batch_size)), 8, dtype=torch.float32, device=d)
         self.episodes = torch.zeros(1, dtype=torch.int64, device=d)
         self.train_step = 1
         self.t = 0
@@ -131,10 +134,12 @@ class VecERDDPG:
         """R2 + U1-U5 on a fresh minibatch; returns the device report [critic_loss, actor_loss, critic_lr, actor_lr]."""
         if len(self.memory) < self.batch_size:
             return None
-        self.memory.sample_indices(self.batch_size, self.seed, self.updates, stream_id=self.rank, out=self.idx)
-        self.memory.gather(self.idx, out=self.batch)
+        # one launch: index draw + assembly (+ the emotion sums Critic.forward's batch standardisation needs)
+        self.memory.sample_gather(self.batch_size, self.seed, self.updates, stream_id=self.rank, out=self.batch, idx_out=self.idx,
+                                  stats_out=self._stats_partials)
         torch.mean(self.emotion, dim=0, out=self.next_emotion)
-        rep = self.learner.update(self.batch, self.next_emotion, self.train_step, allreduce=allreduce)
+        rep = self.learner.update(self.batch, self.next_emotion, self.train_step, allreduce=allreduce,
+                                  stats_partials=self._stats_partials if self.learner.precision == "fast" else None)
         self.updates += 1
         return rep
 

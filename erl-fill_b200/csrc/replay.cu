@@ -143,6 +143,39 @@ __global__ void replay_gather_kernel(int batch, const float *d_buf, const int64_
     reinterpret_cast<uint4 *>(d_out)[g] = v;
 }
 
+// R2 fused: index draw + minibatch assembly in one launch.  Block = 64 samples x 5 sixteen-byte parts.  Optionally the block also
+// leaves the six sums  sum(e_c - 0.5), sum((e_c - 0.5)^2)  of the emotion columns of its 64 records (fixed order inside the block):
+// Critic.forward standardises the emotion with BATCH statistics (ddpg_agent.py:176), and the update kernels then only add the blocks'
+// sums instead of re-reading the whole minibatch (erlfill_ddpg_hyper::d_stats_partials).
+constexpr int kSgSamples = 64;
+__global__ void __launch_bounds__(kSgSamples * 5) replay_sample_gather_kernel(int batch, int64_t n_valid, uint32_t k0, uint32_t k1, uint32_t update_idx,
+                                                                               uint32_t stream_id, const float *d_buf, int64_t *d_idx, float *d_out,
+                                                                               float *d_stats) {
+    __shared__ float sh[kSgSamples][6];
+    const int sl = threadIdx.x / 5, part = threadIdx.x % 5;
+    const int i = blockIdx.x * kSgSamples + sl;
+    float4 v = make_float4(0.5f, 0.5f, 0.5f, 0.f);
+    if (i < batch) {
+        const uint4 r = philox4x32_10(k0, k1, (uint32_t)(i >> 2), update_idx, stream_id, STREAM_SAMPLE);
+        const uint32_t x = (i & 3) == 0 ? r.x : ((i & 3) == 1 ? r.y : ((i & 3) == 2 ? r.z : r.w));
+        const int64_t row = (int64_t)(((unsigned long long)x * (unsigned long long)n_valid) >> 32);   // floor(U * n)
+        if (part == 0 && d_idx) d_idx[i] = row;
+        v = __ldg(reinterpret_cast<const float4 *>(d_buf) + row * (ERLFILL_REC / 4) + part);
+        reinterpret_cast<float4 *>(d_out)[(size_t)i * (ERLFILL_REC / 4) + part] = v;
+    }
+    if (!d_stats) return;
+    if (part == 4) {
+        const float d0 = v.x - 0.5f, d1 = v.y - 0.5f, d2 = v.z - 0.5f;
+        sh[sl][0] = d0; sh[sl][1] = d1; sh[sl][2] = d2; sh[sl][3] = d0 * d0; sh[sl][4] = d1 * d1; sh[sl][5] = d2 * d2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float t = 0.f;
+        for (int q = 0; q < kSgSamples; ++q) t += sh[q][threadIdx.x];
+        d_stats[blockIdx.x * 8 + threadIdx.x] = t;
+    }
+}
+
 }  // namespace erlfill
 
 using namespace erlfill;
@@ -202,6 +235,18 @@ int erlfill_replay_sample(int batch, int64_t n_valid, uint64_t seed, uint32_t up
     const int block = 256, grid = (batch + block - 1) / block;
     replay_sample_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(batch, n_valid, (uint32_t)seed, (uint32_t)(seed >> 32),
                                                                    update_idx, stream_id, d_idx);
+    ERLFILL_CUDA_TRY(cudaGetLastError());
+    return ERLFILL_OK;
+}
+
+int erlfill_replay_sample_gather_blocks(int batch) { return batch > 0 ? (batch + kSgSamples - 1) / kSgSamples : 0; }
+
+int erlfill_replay_sample_gather(int batch, int64_t n_valid, uint64_t seed, uint32_t update_idx, uint32_t stream_id, const float *d_buf,
+                                 int64_t *d_idx, float *d_out, float *d_stats_partials, void *stream) {
+    if (batch <= 0 || n_valid <= 0 || n_valid > 0xFFFFFFFFLL || !d_buf || !d_out) return ERLFILL_ERR_ARG;
+    if (((uintptr_t)d_buf & 15u) || ((uintptr_t)d_out & 15u)) return ERLFILL_ERR_ARG;
+    replay_sample_gather_kernel<<<erlfill_replay_sample_gather_blocks(batch), kSgSamples * 5, 0, (cudaStream_t)stream>>>(
+        batch, n_valid, (uint32_t)seed, (uint32_t)(seed >> 32), update_idx, stream_id, d_buf, d_idx, d_out, d_stats_partials);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
 }

@@ -12,6 +12,8 @@
 // Building blocks and the operand-image scheme: update_tc.cuh.  Numerics: bf16 operands, fp32 accumulation, fp32 master weights,
 // LayerNorm / losses / optimiser in fp32 (stated tolerance against the fp32 reference: tests/test_update_tc_gpu.py); the exact
 // 3xTF32 path of update.cu stays the 1e-4 parity path.
+#include <stdlib.h>
+
 #include "update_tc.cuh"
 
 #include "mlp.cuh"
@@ -41,9 +43,24 @@ struct Args {
     float *mean_out;                                             // 3 batch emotion means (tail of the critic gradient bucket)
     float *scal;                                                 // scal[6 .. 15): L2 norms of the nine actor tensors
     Drop drop;
+    int prof;
+    // CRITIC_GRAD with the target chain on its own CTAs (grid = 2 x tiles, all co-resident): CTA tiles + t computes Q' of tile t, writes it
+    // to tq_g and raises tq_flag[t]; CTA t consumes it before the loss and lowers the flag again
+    int split;
+    float *tq_g;
+    uint32_t *tq_flag;
+    float *stats_g;              // [6] batch emotion mean / std, left by CRITIC_GRAD for ACTOR_GRAD (same minibatch)
+    float *stats_part;           // [tiles][8]
+    uint32_t *stats_ctr;         // [2]
+    const float *stats_ext;      // optional: the sums erlfill_replay_sample_gather left for this minibatch, n_stats_ext rows of 8
+    int n_stats_ext;
 };
 
 __constant__ int c_actor_seg[10] = {0, 30, 670, 798, 17182, 17310, 25502, 25566, 26206, 26216};
+
+// development profile (erlfill_debug_utc_profile): clock64 of CTA 0 at the numbered points of the two phase kernels
+__device__ long long g_utc_prof[2][128];
+#define UPROF(k, i) do { if (a.prof && blockIdx.x == 0 && e.tid == 0) g_utc_prof[k][i] = clock64(); } while (0)
 
 // ---- common prologue / epilogue of the two phase kernels ---------------------------------------------------------------
 __device__ __forceinline__ void setup(uint8_t *smem, uint64_t *bars, uint32_t *tmem_slot, int tid, int warp) {
@@ -54,8 +71,7 @@ __device__ __forceinline__ void setup(uint8_t *smem, uint64_t *bars, uint32_t *t
         mbar_fence_init();
     }
     if (warp == W_ISSUER) tmem_alloc(tmem_slot, 512);
-    // operand images start finite: the MN-major reads of narrow images and ragged tiles touch bytes nobody writes
-    for (int i = tid; i < (SM_RING) / 16; i += NTHR) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // (the MN-major reads of narrow images touch bytes nobody writes: they only feed accumulator lanes nobody reads)
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -63,22 +79,29 @@ __device__ __forceinline__ void setup(uint8_t *smem, uint64_t *bars, uint32_t *t
 }
 
 // batch mean / unbiased std of the three emotion columns (Critic.forward, ddpg_agent.py:176), by the epilogue threads of every CTA
+// (recomputing 3 x B values per CTA is cheaper than a grid-wide dependency); loads unrolled so that their latencies overlap
 __device__ __forceinline__ void emotion_stats(Epi &e, const float *batch, float *mean_out) {
     float *st = e.stat();
-    float s[3] = {0.f, 0.f, 0.f};
-    for (int r = e.tid; r < e.B; r += NEPI)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) s[c] += __ldg(batch + (size_t)r * ERLFILL_REC + 16 + c);
     float *scr = st + 16;                                        // [16 warps][3]
+    float s[3] = {0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int r = e.tid; r < e.B; r += NEPI) {
+        const float *p = batch + (size_t)r * ERLFILL_REC + 16;
+        s[0] += __ldg(p); s[1] += __ldg(p + 1); s[2] += __ldg(p + 2);
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) { const float t = warp_sum(s[c]); if (e.lane == 0) scr[(e.tid >> 5) * 3 + c] = t; }
     bar_epi();
     if (e.tid < 3) { float t = 0.f; for (int w = 0; w < NEPI / 32; ++w) t += scr[w * 3 + e.tid]; st[e.tid] = t / (float)e.B; }
     bar_epi();
+    const float m0 = st[0], m1 = st[1], m2 = st[2];
     float q[3] = {0.f, 0.f, 0.f};
-    for (int r = e.tid; r < e.B; r += NEPI)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { const float d = __ldg(batch + (size_t)r * ERLFILL_REC + 16 + c) - st[c]; q[c] = fmaf(d, d, q[c]); }
+#pragma unroll 8
+    for (int r = e.tid; r < e.B; r += NEPI) {
+        const float *p = batch + (size_t)r * ERLFILL_REC + 16;
+        const float d0 = __ldg(p) - m0, d1 = __ldg(p + 1) - m1, d2 = __ldg(p + 2) - m2;
+        q[0] = fmaf(d0, d0, q[0]); q[1] = fmaf(d1, d1, q[1]); q[2] = fmaf(d2, d2, q[2]);
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) { const float t = warp_sum(q[c]); if (e.lane == 0) scr[(e.tid >> 5) * 3 + c] = t; }
     bar_epi();
@@ -86,7 +109,57 @@ __device__ __forceinline__ void emotion_stats(Epi &e, const float *batch, float 
         float t = 0.f;
         for (int w = 0; w < NEPI / 32; ++w) t += scr[w * 3 + e.tid];
         st[3 + e.tid] = sqrtf(t / (float)(e.B - 1));
-        if (mean_out && blockIdx.x == 0) mean_out[e.tid] = st[e.tid];
+        if (mean_out) mean_out[e.tid] = st[e.tid];
+    }
+    bar_epi();
+}
+
+// The same statistics with the work shared by the CTAs of the grid (all co-resident: the split launch of CRITIC_GRAD): every CTA sums
+// (e - 0.5) and (e - 0.5)^2 over ITS 128 rows, publishes the six sums, and — once all tiles have arrived — adds the tiles' sums in tile
+// order (the same numbers on every CTA).  ctr[0] counts arrivals, ctr[1] departures; the last CTA to leave zeroes both for the next launch.
+__device__ __forceinline__ void grid_emotion_stats(Epi &e, const float *batch, float *part_g, uint32_t *ctr, int n_tiles, int tile, float *stats_out,
+                                                   float *mean_out) {
+    float *st = e.stat();
+    float *scr = st + 16;                                        // [4 warps][6]
+    if (e.wg == 0) {
+        float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (e.valid()) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(batch + (size_t)(e.row0 + e.r) * ERLFILL_REC + 16));
+            const float d0 = q.x - 0.5f, d1 = q.y - 0.5f, d2 = q.z - 0.5f;
+            v[0] = d0; v[1] = d1; v[2] = d2; v[3] = d0 * d0; v[4] = d1 * d1; v[5] = d2 * d2;
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { const float t = warp_sum(v[c]); if (e.lane == 0) scr[e.wq * 6 + c] = t; }
+    }
+    bar_epi();
+    if (e.tid == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) part_g[tile * 8 + c] = (scr[c] + scr[6 + c]) + (scr[12 + c] + scr[18 + c]);
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        const long long t0 = clock64();
+        bool ok = true;
+        while (*reinterpret_cast<volatile uint32_t *>(ctr) < (uint32_t)n_tiles) {
+            if (clock64() - t0 > 4000000000LL) { ok = false; break; }        // ~2 s: a CTA of the grid never became resident
+        }
+        __threadfence();
+        float sum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int t = 0; t < n_tiles; ++t)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) sum[c] += __ldcg(part_g + t * 8 + c);
+        const float n = (float)e.B;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float m = sum[c] / n;
+            st[c] = ok ? 0.5f + m : __int_as_float(0x7fc00000);
+            st[3 + c] = sqrtf(fmaxf(sum[3 + c] - sum[c] * m, 0.f) / (n - 1.0f));
+        }
+        if (tile == 0) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) stats_out[c] = st[c];
+            mean_out[0] = st[0]; mean_out[1] = st[1]; mean_out[2] = st[2];
+        }
+        if (atomicAdd(ctr + 1, 1u) == (uint32_t)n_tiles - 1u) { ctr[0] = 0u; ctr[1] = 0u; __threadfence(); }
     }
     bar_epi();
 }
@@ -109,7 +182,8 @@ __device__ __forceinline__ void store_split_input(const Epi &e, const float (&x)
 }
 
 // Actor head on the 16 accumulator columns of the last layer (ddpg_agent.py:104-122): out[10] in physical units.
-// aux (optional) [64] floats of this row: z4[10] base[10] raw[10] alpha[10] out[10] (what the backward needs).
+// aux (optional): 50 floats of this row at stride 128 ([k][row]: a warp's rows are contiguous): z4[10] base[10] raw[10] alpha[10] out[10]
+// (what the backward needs).
 __device__ __forceinline__ void actor_head(const float (&z16)[16], const float *P, float cur, float cons, float anx, const float *scale,
                                            const float *offset, float (&out)[10], float *aux) {
     float alpha = 0.1f + 0.9f * anx;
@@ -127,7 +201,7 @@ __device__ __forceinline__ void actor_head(const float (&z16)[16], const float *
         const float om = 1.0f - fabsf(base);
         const float sf = base > 0.f ? -1.0f : (base < 0.f ? 1.0f : 0.0f);
         out[c] = (base + alpha * raw * sf * (om * om)) * __ldg(scale + c) + __ldg(offset + c);
-        if (aux) { aux[c] = z; aux[10 + c] = base; aux[20 + c] = raw; aux[30 + c] = alpha; aux[40 + c] = out[c]; }
+        if (aux) { aux[c * TR] = z; aux[(10 + c) * TR] = base; aux[(20 + c) * TR] = raw; aux[(30 + c) * TR] = alpha; aux[(40 + c) * TR] = out[c]; }
     }
 }
 
@@ -156,58 +230,63 @@ __device__ __forceinline__ void epi_hidden128(Epi &e, const float *bias, int act
     if (keep_out) *keep_out = keep;
 }
 
-// LayerNorm(256) + activation + dropout of the critic (64 columns per thread) -> image of 256 features.
-// save: xhat (fp32 [128][256]), rstd [128], keep words [128][8], image copy — what the backward and the weight gradients read.
+// LayerNorm(256) + activation + dropout of the critic (64 columns per thread) -> image of 256 features.  Two passes over the
+// accumulators (statistics, then normalise) keep the register footprint at one 32-column chunk.
+// save: xhat (fp32, [64 float4 columns][128 rows]: a warp's 32 rows are 512 contiguous bytes), rstd [128], keep words [128][8], image
+// copy — what the backward and the weight gradients read.
 __device__ __forceinline__ void epi_ln256(Epi &e, const float *bias, const float *gamma, const float *beta, int act, const Drop &dr, int site,
                                           float *xhat_g, float *rstd_g, uint32_t *keep_g, uint8_t *gimg) {
-    float v[64];
     const int c0 = e.wg * 64;
-    {
-        float t[32];
-        tmem_ld32w(e.td(c0), t);
+    // pass 1: shifted sums of this thread's 64 columns -> (mean_w, M2_w); the four quarter statistics combine exactly (Chan et al.)
+    float k = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        float v[32];
+        tmem_ld32w(e.td(c0 + 32 * h), v);
+        if (bias) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = t[j] + (bias ? __ldg(bias + c0 + j) : 0.f);
-        tmem_ld32w(e.td(c0 + 32), t);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[32 + j] = t[j] + (bias ? __ldg(bias + c0 + 32 + j) : 0.f);
-    }
-    float s = 0.f, dummy = 0.f;
-#pragma unroll
-    for (int j = 0; j < 64; ++j) s += v[j];
-    e.row_allreduce2(s, dummy);
-    const float mean = s * (1.0f / 256.0f);
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < 64; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
-    dummy = 0.f;
-    e.row_allreduce2(q, dummy);
-    const float rstd = rsqrtf(q * (1.0f / 256.0f) + 1e-5f);
-    const uint32_t k0 = keep32(dr, site, e.mrow(), c0, 256), k1 = keep32(dr, site, e.mrow(), c0 + 32, 256);
-    const float ds = dr.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        float h[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int j = g * 8 + i, c = c0 + j;
-            const float xh = (v[j] - mean) * rstd;
-            v[j] = xh;
-            float y = xh * __ldg(gamma + c) + __ldg(beta + c);
-            y = act == ACT_LEAKY ? (y > 0.f ? y : 0.1f * y) : fmaxf(y, 0.f);
-            const uint32_t kb = j < 32 ? (k0 >> j) & 1u : (k1 >> (j - 32)) & 1u;
-            h[i] = kb ? y * ds : 0.f;
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(bias + c0 + 32 * h + j);
         }
-        e.img_store8(e.img_a(), 256, c0 + g * 8, h);
-        if (gimg) e.img_store8(gimg, 256, c0 + g * 8, h);
-    }
-    if (xhat_g) {
-        float4 *dst = reinterpret_cast<float4 *>(xhat_g + (size_t)e.r * 256 + c0);
+        if (h == 0) k = v[0];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        if (e.wg == 0) rstd_g[e.r] = rstd;
-        keep_g[e.r * 8 + e.wg * 2] = k0;
-        keep_g[e.r * 8 + e.wg * 2 + 1] = k1;
+        for (int j = 0; j < 32; ++j) { const float d = v[j] - k; s1 += d; s2 = fmaf(d, d, s2); }
     }
+    const float mean_w = k + s1 * (1.0f / 64.0f);
+    float a1 = mean_w, a2 = (s2 - s1 * s1 * (1.0f / 64.0f)) + 64.0f * mean_w * mean_w;       // M2_w + 64 mean_w^2
+    e.row_allreduce2(a1, a2);
+    const float mean = a1 * 0.25f;
+    const float var = fmaxf(a2 - 256.0f * mean * mean, 0.f) * (1.0f / 256.0f);
+    const float rstd = rsqrtf(var + 1e-5f);
+    const float ds = dr.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale;
+    // pass 2
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        float v[32];
+        tmem_ld32w(e.td(c0 + 32 * h), v);
+        const uint32_t kb = keep32(dr, site, e.mrow(), c0 + 32 * h, 256);
+        if (keep_g) keep_g[e.r * 8 + e.wg * 2 + h] = kb;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float hh[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int j = g * 8 + i, c = c0 + 32 * h + j;
+                const float xh = (v[j] + (bias ? __ldg(bias + c) : 0.f) - mean) * rstd;
+                v[j] = xh;
+                float y = xh * __ldg(gamma + c) + __ldg(beta + c);
+                y = act == ACT_LEAKY ? (y > 0.f ? y : 0.1f * y) : fmaxf(y, 0.f);
+                hh[i] = ((kb >> j) & 1u) ? y * ds : 0.f;
+            }
+            e.img_store8(e.img_a(), 256, c0 + 32 * h + g * 8, hh);
+            if (gimg) e.img_store8(gimg, 256, c0 + 32 * h + g * 8, hh);
+        }
+        if (xhat_g) {
+            float4 *dst = reinterpret_cast<float4 *>(xhat_g) + (size_t)((c0 + 32 * h) >> 2) * TR + e.r;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[(size_t)j * TR] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+    }
+    if (xhat_g && e.wg == 0) rstd_g[e.r] = rstd;
 }
 
 // critic layer 8 (N = 128, 32 columns per thread): h3 = relu(D + b8), q = clamp(h3 . w10 + b10): every thread of the row gets q
@@ -244,10 +323,10 @@ __device__ __forceinline__ void epi_ln256_bwd(Epi &e, const float *gamma, const 
     for (int h = 0; h < 2; ++h) {
         float dh[32], a[32], b[32];
         tmem_ld32w(e.td(c0 + 32 * h), dh);
-        const float4 *xp = reinterpret_cast<const float4 *>(xhat_g + (size_t)e.r * 256 + c0 + 32 * h);
+        const float4 *xp = reinterpret_cast<const float4 *>(xhat_g) + (size_t)((c0 + 32 * h) >> 2) * TR + e.r;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 x4 = xp[j4];
+            const float4 x4 = xp[(size_t)j4 * TR];
             const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -271,10 +350,10 @@ __device__ __forceinline__ void epi_ln256_bwd(Epi &e, const float *gamma, const 
     for (int h = 0; h < 2; ++h) {
         float dh[32], dz[32];
         tmem_ld32w(e.td(c0 + 32 * h), dh);
-        const float4 *xp = reinterpret_cast<const float4 *>(xhat_g + (size_t)e.r * 256 + c0 + 32 * h);
+        const float4 *xp = reinterpret_cast<const float4 *>(xhat_g) + (size_t)((c0 + 32 * h) >> 2) * TR + e.r;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 x4 = xp[j4];
+            const float4 x4 = xp[(size_t)j4 * TR];
             const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -298,31 +377,27 @@ __device__ __forceinline__ void epi_ln256_bwd(Epi &e, const float *gamma, const 
     }
 }
 
-// Drain of one weight-gradient block: TMEM lane r = output feature m0 + r, `n` accumulator columns -> dst[(m0 + r) * ld + col].
-__device__ __forceinline__ void drain_g(Epi &e, float *dst, int ld, int n, int rows_valid) {
+// Drain of one weight-gradient block: TMEM lane r = output feature m0 + r, `n` accumulator columns.  The block is stored as
+// [n / 4 float4 columns][128 rows][4] so that the 32 rows of a warp write 512 contiguous bytes (grad_reduce_kernel walks the same order).
+__device__ __forceinline__ void drain_g(Epi &e, float *dst, int n) {
     e.wait_g();
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
     if (n >= 128) {
         const int cpw = n / NWG;
         for (int c = 0; c < cpw; c += 32) {
             float v[32];
             tmem_ld32w(e.tg(e.wg * cpw + c), v);
-            if (e.r < rows_valid) {
-                float4 *o = reinterpret_cast<float4 *>(dst + (size_t)e.r * ld + e.wg * cpw + c);
+            float4 *o = d4 + (size_t)((e.wg * cpw + c) >> 2) * TR + e.r;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
+            for (int j = 0; j < 8; ++j) o[(size_t)j * TR] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-    } else {            // n = 64 (16 columns per warpgroup) or n = 16 (warpgroup 0 only)
-        if (n == 64 || e.wg == 0) {
-            float v[16];
-            const int c = n == 64 ? e.wg * 16 : 0;
-            tmem_ld16w(e.tg(c), v);
-            if (e.r < rows_valid) {
-                float4 *o = reinterpret_cast<float4 *>(dst + (size_t)e.r * ld + c);
+    } else if (n == 64 || e.wg == 0) {      // n = 64 (16 columns per warpgroup) or n = 16 (warpgroup 0 only)
+        float v[16];
+        const int c = n == 64 ? e.wg * 16 : 0;
+        tmem_ld16w(e.tg(c), v);
+        float4 *o = d4 + (size_t)(c >> 2) * TR + e.r;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-        }
+        for (int j = 0; j < 4; ++j) o[(size_t)j * TR] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
     e.g_free();
 }
@@ -335,7 +410,8 @@ __device__ __forceinline__ void drain_g(Epi &e, float *dst, int ld, int n, int r
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);                                                     \
     setup(smem, bars, tmem_slot, tid, warp);                                                                    \
     const uint32_t tbase = *tmem_slot;                                                                          \
-    uint8_t *scr = a.scratch + (size_t)blockIdx.x * SC::BYTES;
+    const uint8_t *scr_c = a.scratch + (size_t)blockIdx.x * SC::BYTES;                                         \
+    uint8_t *scr = const_cast<uint8_t *>(scr_c);
 
 #define UTC_ROLE_EPILOGUE                                                                                      \
     tc_fence_before();                                                                                          \
@@ -345,16 +421,19 @@ __device__ __forceinline__ void drain_g(Epi &e, float *dst, int ld, int n, int r
 // =====================================================================================================================
 // CRITIC_GRAD
 // =====================================================================================================================
+// part: 0 = the whole phase in one CTA, 1 = target chain only, 2 = everything but the target chain
 template <int ROLE>
-__device__ __forceinline__ void critic_program(Pipe &p, const Args &a, const uint8_t *scr) {
-    // target chain: actor_target, critic_target
-    gemm_fwd<ROLE>(p, a.img_actor_t + AI::W1, 128, 48);
-    gemm_fwd<ROLE>(p, a.img_actor_t + AI::W2, 128, 128);
-    gemm_fwd<ROLE>(p, a.img_actor_t + AI::W3, 64, 128);
-    gemm_fwd<ROLE>(p, a.img_actor_t + AI::W4, 16, 64);
-    gemm_fwd<ROLE>(p, a.img_critic_t + CI::W0, 256, 48);
-    gemm_fwd<ROLE>(p, a.img_critic_t + CI::W4, 256, 256);
-    gemm_fwd<ROLE>(p, a.img_critic_t + CI::W8, 128, 256);
+__device__ __forceinline__ void critic_program(Pipe &p, const Args &a, const uint8_t *scr, int part) {
+    if (part != 2) {    // target chain: actor_target, critic_target
+        gemm_fwd<ROLE>(p, a.img_actor_t + AI::W1, 128, 48);
+        gemm_fwd<ROLE>(p, a.img_actor_t + AI::W2, 128, 128);
+        gemm_fwd<ROLE>(p, a.img_actor_t + AI::W3, 64, 128);
+        gemm_fwd<ROLE>(p, a.img_actor_t + AI::W4, 16, 64);
+        gemm_fwd<ROLE>(p, a.img_critic_t + CI::W0, 256, 48);
+        gemm_fwd<ROLE>(p, a.img_critic_t + CI::W4, 256, 256);
+        gemm_fwd<ROLE>(p, a.img_critic_t + CI::W8, 128, 256);
+    }
+    if (part == 1) return;
     // Q(s, a_norm, e)
     gemm_fwd<ROLE>(p, a.img_critic + CI::W0, 256, 48);
     gemm_fwd<ROLE>(p, a.img_critic + CI::W4, 256, 256);
@@ -376,25 +455,54 @@ __device__ __forceinline__ void critic_program(Pipe &p, const Args &a, const uin
 
 __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
     UTC_ROLE_PROLOGUE
+    const int n_tiles = (a.B + TR - 1) / TR;
+    const int tile = a.split ? (int)blockIdx.x % n_tiles : (int)blockIdx.x;
+    const int chain = a.split ? ((int)blockIdx.x >= n_tiles ? 1 : 2) : 0;
+    scr = a.scratch + (size_t)tile * SC::BYTES;
     if (warp == W_PRODUCER) {
-        if (elect_one()) { Pipe p{smem, bars, tbase}; critic_program<ROLE_PRODUCER>(p, a, scr); }
+        if (elect_one()) { Pipe p{smem, bars, tbase}; critic_program<ROLE_PRODUCER>(p, a, scr, chain); }
         __syncwarp();
     } else if (warp == W_ISSUER) {
-        if (elect_one()) { Pipe p{smem, bars, tbase}; critic_program<ROLE_ISSUER>(p, a, scr); }
+        if (elect_one()) { Pipe p{smem, bars, tbase}; critic_program<ROLE_ISSUER>(p, a, scr, chain); }
         __syncwarp();
     } else {
         Epi e{smem, bars, tbase, tid, tid >> 7, tid & 127, tid & 31, (tid >> 5) & 3, (uint32_t)(((tid >> 5) & 3) * 32) << 16};
-        e.row0 = blockIdx.x * TR; e.B = a.B;
+        e.row0 = tile * TR; e.B = a.B;
         const int grow = e.row0 + e.r;
         const bool valid = e.valid();
         const float *row = a.batch + (size_t)(valid ? grow : 0) * ERLFILL_REC;
-        float *part = a.cpart + (size_t)blockIdx.x * CP::SIZE;
-        emotion_stats(e, a.batch, a.mean_out);
+        float *part = a.cpart + (size_t)tile * CP::SIZE;
+        UPROF(0, 0);
+        if (chain != 1 && a.stats_ext) {
+            // the minibatch came with its emotion sums: add the rows in order (identical on every CTA), no pass over the records
+            if (e.tid < 6) {
+                float t = 0.f;
+#pragma unroll 8
+                for (int q = 0; q < a.n_stats_ext; ++q) t += __ldg(a.stats_ext + q * 8 + e.tid);
+                e.stat()[16 + e.tid] = t;
+            }
+            bar_epi();
+            if (e.tid < 3) {
+                float *st_ = e.stat();
+                const float n = (float)a.B, m = st_[16 + e.tid] / n;
+                st_[e.tid] = 0.5f + m;
+                st_[3 + e.tid] = sqrtf(fmaxf(st_[19 + e.tid] - st_[16 + e.tid] * m, 0.f) / (n - 1.0f));
+            }
+            bar_epi();
+            if (tile == 0 && e.tid < 6) { a.stats_g[e.tid] = e.stat()[e.tid]; if (e.tid < 3) a.mean_out[e.tid] = e.stat()[e.tid]; }
+        } else if (chain == 2) grid_emotion_stats(e, a.batch, a.stats_part, a.stats_ctr, n_tiles, tile, a.stats_g, a.mean_out);
+        else if (chain == 0) {
+            emotion_stats(e, a.batch, tile == 0 ? a.mean_out : nullptr);
+            if (tile == 0 && e.tid < 6) a.stats_g[e.tid] = e.stat()[e.tid];
+        }
+        UPROF(0, 1);
         const float *st = e.stat();
         const int cid = (a.n_cond > 1 && valid) ? (int)__ldg(row + 19) : 0;
         const float *scale = a.scale + cid * 10, *offset = a.offset + cid * 10;
         // ---- target: a' = actor_target(s', e'), Q' = critic_target(s', a', 0) ----
         const float ne0 = __ldg(a.next_emotion), ne1 = __ldg(a.next_emotion + 1), ne2 = __ldg(a.next_emotion + 2);
+        float tq = 0.f;
+        if (chain != 2) {
         if (e.wg == 0) {
             float x[16];
 #pragma unroll
@@ -404,9 +512,10 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
             store_split_input(e, x, nullptr);
         }
         e.a_ready();
-        e.wait_d(); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 0, nullptr, nullptr, nullptr); e.a_ready();
-        e.wait_d(); epi_hidden128(e, a.actor_t + AO::B2, ACT_RELU, a.drop, 1, nullptr, nullptr, nullptr); e.a_ready();
-        e.wait_d();
+        UPROF(0, 2);
+        e.wait_d(); UPROF(0, 3); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 0, nullptr, nullptr, nullptr); e.a_ready(); UPROF(0, 4);
+        e.wait_d(); UPROF(0, 5); epi_hidden128(e, a.actor_t + AO::B2, ACT_RELU, a.drop, 1, nullptr, nullptr, nullptr); e.a_ready(); UPROF(0, 6);
+        e.wait_d(); UPROF(0, 7);
         {   // Linear(128, 64) -> ReLU: 16 columns per thread
             float v[16];
             tmem_ld16w(e.td(e.wg * 16), v);
@@ -416,7 +525,9 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
             e.img_store8(e.img_a(), 64, e.wg * 16 + 8, v + 8);
         }
         e.a_ready();
+        UPROF(0, 8);
         e.wait_d();
+        UPROF(0, 9);
         if (e.wg == 0) {
             float z[16], out[10], x[16];
             tmem_ld16w(e.td(0), z);
@@ -432,11 +543,20 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
             store_split_input(e, x, nullptr);
         }
         e.a_ready();
-        e.wait_d(); epi_ln256(e, nullptr, a.critic_t + CO::G1, a.critic_t + CO::BE1, ACT_LEAKY, a.drop, 2, nullptr, nullptr, nullptr, nullptr); e.a_ready();
-        e.wait_d(); epi_ln256(e, a.critic_t + CO::B4, a.critic_t + CO::G2, a.critic_t + CO::BE2, ACT_RELU, a.drop, 3, nullptr, nullptr, nullptr, nullptr); e.a_ready();
+        UPROF(0, 10);
+        e.wait_d(); UPROF(0, 11); epi_ln256(e, nullptr, a.critic_t + CO::G1, a.critic_t + CO::BE1, ACT_LEAKY, a.drop, 2, nullptr, nullptr, nullptr, nullptr); e.a_ready(); UPROF(0, 12);
+        e.wait_d(); UPROF(0, 13); epi_ln256(e, a.critic_t + CO::B4, a.critic_t + CO::G2, a.critic_t + CO::BE2, ACT_RELU, a.drop, 3, nullptr, nullptr, nullptr, nullptr); e.a_ready(); UPROF(0, 14);
         e.wait_d();
-        float tq;
+        UPROF(0, 15);
         { float h3[32]; tq = epi_head(e, a.critic_t, h3); }
+        UPROF(0, 16);
+        }
+        if (chain == 1) {        // hand Q' of this tile to the CTA that runs the rest of the phase
+            if (e.wg == 0 && valid) a.tq_g[grow] = tq;
+            __threadfence();
+            bar_epi();
+            if (e.tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.tq_flag + tile), "r"(1u) : "memory");
+        } else {
         // ---- Q(s, a_norm, e) ----
         if (e.wg == 0) {
             float x[16];
@@ -452,16 +572,37 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
             store_split_input(e, x, scr + SC::X0IMG);
         }
         e.a_ready();
+        UPROF(0, 17);
         e.wait_d();
+        UPROF(0, 18);
         epi_ln256(e, nullptr, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, 4, reinterpret_cast<float *>(scr + SC::XHAT1),
                   reinterpret_cast<float *>(scr + SC::RSTD1), reinterpret_cast<uint32_t *>(scr + SC::KEEP), scr + SC::H1IMG);
         e.a_ready();
+        UPROF(0, 19);
         e.wait_d();
+        UPROF(0, 20);
         epi_ln256(e, a.critic + CO::B4, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, 5, reinterpret_cast<float *>(scr + SC::XHAT2),
                   reinterpret_cast<float *>(scr + SC::RSTD2), reinterpret_cast<uint32_t *>(scr + SC::KEEP) + 1024, scr + SC::H2IMG);
         __threadfence();                                        // the saved images are read back through the async proxy (bulk copies)
         e.a_ready();
+        UPROF(0, 21);
+        if (chain == 2) {
+            if (e.tid == 0) {
+                uint32_t f;
+                const long long t0 = clock64();
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.tq_flag + tile) : "memory");
+                    if (clock64() - t0 > 4000000000LL) { e.stat()[8] = __int_as_float(0x7fc00000); break; }     // never a hang: poison instead
+                } while (f == 0u);
+                if (f != 0u) e.stat()[8] = 0.f;
+            }
+            bar_epi();
+            tq = valid ? __ldcg(a.tq_g + grow) + e.stat()[8] : 0.f;
+            bar_epi();
+            if (e.tid == 0) a.tq_flag[tile] = 0u;
+        }
         e.wait_d();
+        UPROF(0, 22);
         {
             float h3[32], dz3[32], gw[32];
             const float q = epi_head(e, a.critic, h3);
@@ -500,19 +641,30 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
             bar_epi();
         }
         // ---- backward ----
-        drain_g(e, part + CP::W8, 256, 256, 128);
+        UPROF(0, 23);
+        drain_g(e, part + CP::W8, 256);
+        UPROF(0, 24);
         e.wait_d();
+        UPROF(0, 25);
         epi_ln256_bwd(e, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, reinterpret_cast<const float *>(scr + SC::XHAT2),
                       reinterpret_cast<const float *>(scr + SC::RSTD2), reinterpret_cast<const uint32_t *>(scr + SC::KEEP) + 1024, part + CP::VB);
         e.a_ready();
-        drain_g(e, part + CP::W4, 256, 256, 128);
-        drain_g(e, part + CP::W4 + 128 * 256, 256, 256, 128);
+        UPROF(0, 26);
+        drain_g(e, part + CP::W4, 256);
+        UPROF(0, 27);
+        drain_g(e, part + CP::W4 + 128 * 256, 256);
+        UPROF(0, 28);
         e.wait_d();
+        UPROF(0, 29);
         epi_ln256_bwd(e, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, reinterpret_cast<const float *>(scr + SC::XHAT1),
                       reinterpret_cast<const float *>(scr + SC::RSTD1), reinterpret_cast<const uint32_t *>(scr + SC::KEEP), part + CP::VA);
         e.a_ready();
-        drain_g(e, part + CP::W0, 16, 16, 128);
-        drain_g(e, part + CP::W0 + 128 * 16, 16, 16, 128);
+        UPROF(0, 30);
+        drain_g(e, part + CP::W0, 16);
+        UPROF(0, 31);
+        drain_g(e, part + CP::W0 + 128 * 16, 16);
+        UPROF(0, 32);
+        }
     }
     UTC_ROLE_EPILOGUE
 }
@@ -563,7 +715,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
         const float *row = a.batch + (size_t)(valid ? grow : 0) * ERLFILL_REC;
         float *part = a.apart + (size_t)blockIdx.x * AP::SIZE;
         uint32_t *abits = reinterpret_cast<uint32_t *>(scr + SC::ABITS) + e.r * 16;     // [pos1 x4 | keep1 x4 | pos2 x4 | keep2 x4]; pos3 in keep words of ...
-        float *aux = reinterpret_cast<float *>(scr + SC::AUX) + e.r * 64;
+        float *aux = reinterpret_cast<float *>(scr + SC::AUX) + e.r;      // [64][128 rows]
         // L2 norms of the nine actor tensors (actor_loss += 1e-4 sum ||theta_t||, ddpg_agent.py:490-494), spread over the CTAs
         for (int t = blockIdx.x; t < 9; t += gridDim.x) {
             float qn = 0.f;
@@ -575,7 +727,9 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             if (e.tid == 0) { float tt = 0.f; for (int w = 0; w < NEPI / 32; ++w) tt += scr_s[w]; a.scal[6 + t] = sqrtf(tt); }
             bar_epi();
         }
-        emotion_stats(e, a.batch, nullptr);
+        UPROF(1, 0);
+        if (e.tid < 6) e.stat()[e.tid] = a.stats_g[e.tid];         // the statistics of this minibatch, left by CRITIC_GRAD
+        bar_epi();
         const float *st = e.stat();
         const int cid = (a.n_cond > 1 && valid) ? (int)__ldg(row + 19) : 0;
         const float *scale = a.scale + cid * 10, *offset = a.offset + cid * 10;
@@ -589,10 +743,10 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             x[15] = 1.0f;
             store_split_input(e, x, scr + SC::XAIMG);
         }
-        e.a_ready();
-        e.wait_d(); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 6, scr + SC::A1IMG, abits + e.wg, abits + 4 + e.wg); e.a_ready();
-        e.wait_d(); epi_hidden128(e, a.actor + AO::B2, ACT_RELU, a.drop, 7, scr + SC::A2IMG, abits + 8 + e.wg, abits + 12 + e.wg); e.a_ready();
-        e.wait_d();
+        e.a_ready(); UPROF(1, 1);
+        e.wait_d(); UPROF(1, 2); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 6, scr + SC::A1IMG, abits + e.wg, abits + 4 + e.wg); e.a_ready(); UPROF(1, 3);
+        e.wait_d(); UPROF(1, 4); epi_hidden128(e, a.actor + AO::B2, ACT_RELU, a.drop, 7, scr + SC::A2IMG, abits + 8 + e.wg, abits + 12 + e.wg); e.a_ready(); UPROF(1, 5);
+        e.wait_d(); UPROF(1, 6);
         uint32_t pos3 = 0;                                     // relu'(z3) bits of this thread's 16 columns (kept in a register until the backward)
         {
             float v[16];
@@ -607,8 +761,8 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             e.img_store8(scr + SC::A3IMG, 64, e.wg * 16, v);
             e.img_store8(scr + SC::A3IMG, 64, e.wg * 16 + 8, v + 8);
         }
-        e.a_ready();
-        e.wait_d();
+        e.a_ready(); UPROF(1, 7);
+        e.wait_d(); UPROF(1, 8);
         if (e.wg == 0) {
             float z[16], out[10], x[16];
             tmem_ld16w(e.td(0), z);
@@ -635,17 +789,17 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             if (e.lane == 0) e.cs()[(2 * 4 + e.wq) * 256 + 2] = ssd;
         }
         __threadfence();
-        e.a_ready();
+        e.a_ready(); UPROF(1, 9);
         // ---- Q(s, a, e) with the updated critic ----
-        e.wait_d();
+        e.wait_d(); UPROF(1, 10);
         epi_ln256(e, nullptr, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, 8, reinterpret_cast<float *>(scr + SC::XHAT1),
                   reinterpret_cast<float *>(scr + SC::RSTD1), reinterpret_cast<uint32_t *>(scr + SC::KEEP), nullptr);
-        e.a_ready();
-        e.wait_d();
+        e.a_ready(); UPROF(1, 11);
+        e.wait_d(); UPROF(1, 12);
         epi_ln256(e, a.critic + CO::B4, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, 9, reinterpret_cast<float *>(scr + SC::XHAT2),
                   reinterpret_cast<float *>(scr + SC::RSTD2), reinterpret_cast<uint32_t *>(scr + SC::KEEP) + 1024, nullptr);
-        e.a_ready();
-        e.wait_d();
+        e.a_ready(); UPROF(1, 13);
+        e.wait_d(); UPROF(1, 14);
         {
             float h3[32], dz3[32];
             const float q2 = epi_head(e, a.critic, h3);
@@ -653,7 +807,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) dz3[j] = h3[j] > 0.f ? g * __ldg(a.critic + CO::W10 + e.wg * 32 + j) : 0.f;
             store_img128(e, dz3);
-            e.a_ready();
+            e.a_ready(); UPROF(1, 15);
             if (e.wg == 0) {
                 const float sq = warp_sum(valid ? q2 : 0.f);
                 if (e.lane == 0) e.cs()[(2 * 4 + e.wq) * 256 + 3] = sq;
@@ -666,15 +820,15 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             }
             bar_epi();
         }
-        e.wait_d();
+        e.wait_d(); UPROF(1, 16);
         epi_ln256_bwd(e, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, reinterpret_cast<const float *>(scr + SC::XHAT2),
                       reinterpret_cast<const float *>(scr + SC::RSTD2), reinterpret_cast<const uint32_t *>(scr + SC::KEEP) + 1024, nullptr);
-        e.a_ready();
-        e.wait_d();
+        e.a_ready(); UPROF(1, 17);
+        e.wait_d(); UPROF(1, 18);
         epi_ln256_bwd(e, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, reinterpret_cast<const float *>(scr + SC::XHAT1),
                       reinterpret_cast<const float *>(scr + SC::RSTD1), reinterpret_cast<const uint32_t *>(scr + SC::KEEP), nullptr);
-        e.a_ready();
-        e.wait_d();
+        e.a_ready(); UPROF(1, 19);
+        e.wait_d(); UPROF(1, 20);
         // ---- actor backward ----
         if (e.wg == 0) {
             float g16[16], dz4[16], prod[32];
@@ -685,18 +839,19 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             for (int j = 0; j < 16; ++j) dz4[j] = 0.f;
             if (valid) {
                 float mean = 0.f;
+                float o10[10];
 #pragma unroll
-                for (int c = 0; c < 10; ++c) mean += aux[40 + c];
+                for (int c = 0; c < 10; ++c) { o10[c] = aux[(40 + c) * TR]; mean += o10[c]; }
                 mean *= 0.1f;
                 float var = 0.f;
 #pragma unroll
-                for (int c = 0; c < 10; ++c) { const float d = aux[40 + c] - mean; var = fmaf(d, d, var); }
+                for (int c = 0; c < 10; ++c) { const float d = o10[c] - mean; var = fmaf(d, d, var); }
                 const float sd = sqrtf(var / 9.0f);
 #pragma unroll
                 for (int c = 0; c < 10; ++c) {
-                    float go = g16[2 + c] + (-0.03f / (float)a.B) * (aux[40 + c] - mean) / (9.0f * sd);     // d(-0.03 mean_rows std)/d out
+                    float go = g16[2 + c] + (-0.03f / (float)a.B) * (o10[c] - mean) / (9.0f * sd);     // d(-0.03 mean_rows std)/d out
                     const float gr_ = go * __ldg(scale + c);
-                    const float z = aux[c], base = aux[10 + c], raw = aux[20 + c], alpha = aux[30 + c];
+                    const float z = aux[c * TR], base = aux[(10 + c) * TR], raw = aux[(20 + c) * TR], alpha = aux[(30 + c) * TR];
                     const float om = 1.0f - fabsf(base);
                     const float sf = base > 0.f ? -1.0f : (base < 0.f ? 1.0f : 0.0f);
                     const float dbase = gr_ * (1.0f + 2.0f * alpha * raw * om * (sf * sf));
@@ -714,13 +869,13 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             e.colsum_stage(0, 0, prod);                         // d emotion_weights [3][10]
             e.colsum_stage(1, 0, db4);
         }
-        e.a_ready();
+        e.a_ready(); UPROF(1, 21);
         bar_epi();
         e.colsum_finish(0, 32, part + AP::EW);
         e.colsum_finish(1, 16, part + AP::B4);
         bar_epi();
-        drain_g(e, part + AP::W4, 64, 64, 16);
-        e.wait_d();
+        drain_g(e, part + AP::W4, 64); UPROF(1, 22);
+        e.wait_d(); UPROF(1, 23);
         {   // da3 = dz4 W4, relu'
             float v[16], s[32];
             tmem_ld16w(e.td(e.wg * 16), v);
@@ -728,7 +883,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             for (int j = 0; j < 16; ++j) v[j] = ((pos3 >> j) & 1u) ? v[j] : 0.f;
             e.img_store8(e.img_a(), 64, e.wg * 16, v);
             e.img_store8(e.img_a(), 64, e.wg * 16 + 8, v + 8);
-            e.a_ready();
+            e.a_ready(); UPROF(1, 24);
 #pragma unroll
             for (int j = 0; j < 32; ++j) s[j] = j < 16 ? v[j] : 0.f;
             // 16 columns per warpgroup: stage at column 32 * wg (lanes 16..31 carry zeros), finish picks 16 of every 32
@@ -740,8 +895,8 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             }
             bar_epi();
         }
-        drain_g(e, part + AP::W3, 128, 128, 64);
-        e.wait_d();
+        drain_g(e, part + AP::W3, 128); UPROF(1, 25);
+        e.wait_d(); UPROF(1, 26);
         {   // da2 = dz3 W3, dropout (site 7), relu'
             float v[32];
             tmem_ld32w(e.td(e.wg * 32), v);
@@ -750,14 +905,14 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (((pos & keep) >> j) & 1u) ? v[j] * ds : 0.f;
             store_img128(e, v);
-            e.a_ready();
+            e.a_ready(); UPROF(1, 27);
             e.colsum_stage(0, e.wg * 32, v);
             bar_epi();
             e.colsum_finish(0, 128, part + AP::B2);
             bar_epi();
         }
-        drain_g(e, part + AP::W2, 128, 128, 128);
-        e.wait_d();
+        drain_g(e, part + AP::W2, 128); UPROF(1, 28);
+        e.wait_d(); UPROF(1, 29);
         {   // da1 = dz2 W2, dropout (site 6), leaky'
             float v[32];
             tmem_ld32w(e.td(e.wg * 32), v);
@@ -766,13 +921,13 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * ds * (((pos >> j) & 1u) ? 1.0f : 0.1f) : 0.f;
             store_img128(e, v);
-            e.a_ready();
+            e.a_ready(); UPROF(1, 30);
             e.colsum_stage(0, e.wg * 32, v);
             bar_epi();
             e.colsum_finish(0, 128, part + AP::B1);
             bar_epi();
         }
-        drain_g(e, part + AP::W1, 16, 16, 128);
+        drain_g(e, part + AP::W1, 16); UPROF(1, 31);
     }
     UTC_ROLE_EPILOGUE
 }
@@ -786,40 +941,48 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
 namespace erlfill {
 namespace utc {
 
-__device__ __forceinline__ int critic_part_index(int i) {
-    if (i < CO::B0) return CP::W0 + (i / 15) * 16 + i % 15;
-    if (i < CO::W4) return CP::VA + (i - CO::B0);
-    if (i < CO::B4) return CP::W4 + (i - CO::W4);
-    if (i < CO::W8) return CP::VB + (i - CO::B4);
-    if (i < CO::B8) return CP::W8 + (i - CO::W8);
-    return CP::VC + (i - CO::B8);
+// position p of a per-CTA partial -> flat gradient index (or -1 for padding).  Matrix blocks are [n / 4][128 rows][4] (drain_g).
+__device__ __forceinline__ void block_rc(int q, int &r, int &c) { r = (q & 511) >> 2; c = ((q >> 9) << 2) | (q & 3); }
+__device__ __forceinline__ int critic_flat_index(int p) {
+    int r, c;
+    if (p < CP::VA) { block_rc(p & 2047, r, c); return c < 15 ? CO::W0 + ((p >> 11) * 128 + r) * 15 + c : -1; }
+    if (p < CP::W4) return CO::B0 + (p - CP::VA);
+    if (p < CP::VB) { const int q = p - CP::W4; block_rc(q & 32767, r, c); return CO::W4 + ((q >> 15) * 128 + r) * 256 + c; }
+    if (p < CP::W8) return CO::B4 + (p - CP::VB);
+    if (p < CP::VC) { block_rc(p - CP::W8, r, c); return CO::W8 + r * 256 + c; }
+    return CO::B8 + (p - CP::VC);
 }
-__device__ __forceinline__ int actor_part_index(int i) {
-    if (i < AO::W1) return AP::EW + i;
-    if (i < AO::B1) return AP::W1 + ((i - AO::W1) / 5) * 16 + (i - AO::W1) % 5;
-    if (i < AO::W2) return AP::B1 + (i - AO::B1);
-    if (i < AO::B2) return AP::W2 + (i - AO::W2);
-    if (i < AO::W3) return AP::B2 + (i - AO::B2);
-    if (i < AO::B3) return AP::W3 + (i - AO::W3);
-    if (i < AO::W4) return AP::B3 + (i - AO::B3);
-    if (i < AO::B4) return AP::W4 + (i - AO::W4);
-    return AP::B4 + (i - AO::B4);
+__device__ __forceinline__ int actor_flat_index(int p) {
+    int r, c;
+    if (p < AP::W1) return p < 30 ? AO::EW + p : -1;
+    if (p < AP::B1) { block_rc(p - AP::W1, r, c); return c < 5 ? AO::W1 + r * 5 + c : -1; }
+    if (p < AP::W2) return AO::B1 + (p - AP::B1);
+    if (p < AP::B2) { block_rc(p - AP::W2, r, c); return AO::W2 + r * 128 + c; }
+    if (p < AP::W3) return AO::B2 + (p - AP::B2);
+    if (p < AP::B3) { block_rc(p - AP::W3, r, c); return r < 64 ? AO::W3 + r * 128 + c : -1; }
+    if (p < AP::W4) return AO::B3 + (p - AP::B3);
+    if (p < AP::B4) { block_rc(p - AP::W4, r, c); return r < 10 ? AO::W4 + r * 64 + c : -1; }
+    return p - AP::B4 < 10 ? AO::B4 + (p - AP::B4) : -1;
 }
 
 // G[i] = sum over the CTAs' partials in CTA order (+ the L2-norm regulariser's gradient 1e-4 theta / ||theta_tensor|| for the actor);
-// block b also leaves the sum of squares of its slice (clip_grad_norm_) and block 0 the loss value.
+// the blocks walk the partial layout (coalesced reads), block b also leaves the sum of squares of its slice (clip_grad_norm_) and
+// block 0 the loss value.
+constexpr int kRedBlocks = 4 * mlp::kSumsqBlocks;      // 256 blocks: the reduction is L2-latency bound, so it wants every SM
 template <bool kActor>
-__global__ void __launch_bounds__(512) grad_reduce_kernel(int n_cta, int B, const float *part, const float *theta, float *scal, float *G, float *ssq) {
+__global__ void __launch_bounds__(256) grad_reduce_kernel(int n_cta, int B, const float *part, const float *theta, float *scal, float *G, float *ssq) {
     __shared__ float scratch[32];
-    constexpr int n = kActor ? AO::TOTAL : CO::TOTAL, psize = kActor ? AP::SIZE : CP::SIZE;
-    const int per = (n + mlp::kSumsqBlocks - 1) / mlp::kSumsqBlocks;
-    const int i0 = blockIdx.x * per, i1 = min(n, i0 + per);
+    constexpr int np = kActor ? AP::SQ : CP::LOSS, psize = kActor ? AP::SIZE : CP::SIZE;
+    const int per = (np + kRedBlocks - 1) / kRedBlocks;
+    const int p0 = blockIdx.x * per, p1 = min(np, p0 + per);
     float ss = 0.f;
-    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        const float *p = part + (kActor ? actor_part_index(i) : critic_part_index(i));
+    for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+        const int i = kActor ? actor_flat_index(p) : critic_flat_index(p);
+        if (i < 0) continue;
+        const float *q = part + p;
         float s = 0.f;
 #pragma unroll 8
-        for (int c = 0; c < n_cta; ++c) s += p[(size_t)c * psize];
+        for (int c = 0; c < n_cta; ++c) s += q[(size_t)c * psize];
         if (kActor) {
             int t = 0;
             while (i >= c_actor_seg[t + 1]) ++t;
@@ -884,15 +1047,16 @@ __device__ __forceinline__ float adam_elem(float &p, float &m, float &v, float g
     p = p - (lr / bc1) * (mi / denom);
     return p;
 }
-__device__ __forceinline__ float clip_coef(const float *ssq, float max_norm) {
+// n_ssq sum-of-squares partials: kRedBlocks from grad_reduce_kernel, mlp::kSumsqBlocks from the peer exchange (REDUCED)
+__device__ __forceinline__ float clip_coef(const float *ssq, int n_ssq, float max_norm) {
     float ss = 0.f;
 #pragma unroll 8
-    for (int b = 0; b < mlp::kSumsqBlocks; ++b) ss += ssq[b];
+    for (int b = 0; b < n_ssq; ++b) ss += ssq[b];
     return fminf(max_norm / (sqrtf(ss) + 1e-6f), 1.0f);
 }
 // CRITIC_APPLY: emotion-driven learning rates (ddpg_agent.py:447-462), clip_grad_norm_(5), Adam, image refresh
-__global__ void critic_apply_kernel(float *p, float *m, float *v, const float *G, const float *ssq, const float *step, double critic_lr, double actor_lr,
-                                    float max_norm, float *scal, uint8_t *img) {
+__global__ void critic_apply_kernel(float *p, float *m, float *v, const float *G, const float *ssq, int n_ssq, const float *step, double critic_lr,
+                                    double actor_lr, float max_norm, float *scal, uint8_t *img) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const double decay = *reinterpret_cast<const double *>(step);
     const double cur = G[CO::TOTAL], cons = G[CO::TOTAL + 1], anx = G[CO::TOTAL + 2];
@@ -900,19 +1064,19 @@ __global__ void critic_apply_kernel(float *p, float *m, float *v, const float *G
     const float lr_c = (float)fmin(fmax(critic_lr * cf * decay, critic_lr * 0.1), critic_lr * 3);
     if (i == 0) { scal[2] = lr_c; scal[3] = (float)fmin(fmax(actor_lr * af * decay, actor_lr * 0.1), actor_lr * 3); }
     if (i >= CO::TOTAL) return;
-    const float coef = clip_coef(ssq, max_norm);
+    const float coef = clip_coef(ssq, n_ssq, max_norm);
     float pi = p[i], mi = m[i], vi = v[i];
     adam_elem(pi, mi, vi, G[i], coef, lr_c, step[2], step[3]);
     p[i] = pi; m[i] = mi; v[i] = vi;
     critic_image_store(img, i, pi);
 }
 // ACTOR_APPLY: clip, Adam, both soft target updates (ddpg_agent.py:501-507), all remaining images, report
-__global__ void actor_apply_kernel(float *p, float *pt, float *m, float *v, const float *G, const float *ssq, const float *step, float max_norm,
+__global__ void actor_apply_kernel(float *p, float *pt, float *m, float *v, const float *G, const float *ssq, int n_ssq, const float *step, float max_norm,
                                    float tau, const float *critic, float *critic_t, float *scal, uint8_t *img_actor, uint8_t *img_actor_t,
                                    uint8_t *img_critic_t, float *report) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < AO::TOTAL) {
-        const float coef = clip_coef(ssq, max_norm);
+        const float coef = clip_coef(ssq, n_ssq, max_norm);
         float pi = p[i], mi = m[i], vi = v[i];
         adam_elem(pi, mi, vi, G[i], coef, scal[3], step[2], step[3]);
         p[i] = pi; m[i] = mi; v[i] = vi;
@@ -936,26 +1100,30 @@ __global__ void actor_apply_kernel(float *p, float *pt, float *m, float *v, cons
 // ---- fast-path workspace tail (behind the exact path's workspace, so buckets / exchange buffers keep their addresses) -------------
 struct Tail {
     uint8_t *img_actor, *img_actor_t, *img_critic, *img_critic_t, *scratch;
-    float *cpart, *apart;
-    uint32_t *img_valid;
+    float *cpart, *apart, *tq_g, *stats_part, *ssq_fine;      // ssq_fine: [2][kRedBlocks]
+    uint32_t *flags;            // tq_flag per tile, then the two counters of grid_emotion_stats
 };
 static size_t up256(size_t n) { return (n + 255) & ~(size_t)255; }
 static int n_cta(int B) { return (B + TR - 1) / TR; }
 size_t tail_bytes(int B) {
     const size_t c = (size_t)n_cta(B);
-    return 256 + 2 * up256(AI::BYTES) + 2 * up256(CI::BYTES) + up256(c * SC::BYTES) + up256(c * CP::SIZE * 4) + up256(c * AP::SIZE * 4);
+    return up256((c + 2) * 4) + up256(c * 32) + 2 * up256(AI::BYTES) + 2 * up256(CI::BYTES) + up256(c * SC::BYTES) + up256(c * CP::SIZE * 4) + up256(c * AP::SIZE * 4) +
+           up256((size_t)B * 4) + up256(2 * 4 * 64 * 4);
 }
 static void carve_tail(Tail &t, uint8_t *base, int B) {
     const size_t c = (size_t)n_cta(B);
     size_t o = 0;
-    t.img_valid = reinterpret_cast<uint32_t *>(base); o += 256;
+    t.flags = reinterpret_cast<uint32_t *>(base); o += up256((c + 2) * 4);
+    t.stats_part = reinterpret_cast<float *>(base + o); o += up256(c * 32);
     t.img_actor = base + o; o += up256(AI::BYTES);
     t.img_actor_t = base + o; o += up256(AI::BYTES);
     t.img_critic = base + o; o += up256(CI::BYTES);
     t.img_critic_t = base + o; o += up256(CI::BYTES);
     t.scratch = base + o; o += up256(c * SC::BYTES);
     t.cpart = reinterpret_cast<float *>(base + o); o += up256(c * CP::SIZE * 4);
-    t.apart = reinterpret_cast<float *>(base + o);
+    t.apart = reinterpret_cast<float *>(base + o); o += up256(c * AP::SIZE * 4);
+    t.tq_g = reinterpret_cast<float *>(base + o); o += up256((size_t)B * 4);
+    t.ssq_fine = reinterpret_cast<float *>(base + o);
 }
 
 static cudaError_t smem_optin() {
@@ -971,6 +1139,7 @@ static cudaError_t smem_optin() {
 int pack_images(const erlfill_ddpg_nets *n, uint8_t *tail_base, int B, cudaStream_t st) {
     Tail t;
     carve_tail(t, tail_base, B);
+    ERLFILL_CUDA_TRY(cudaMemsetAsync(t.flags, 0, up256(((size_t)n_cta(B) + 2) * 4), st));
     ERLFILL_CUDA_TRY(cudaMemsetAsync(t.img_actor, 0, 2 * up256(AI::BYTES) + 2 * up256(CI::BYTES), st));
     pack_images_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, n->actor_target, n->critic, n->critic_target, t.img_actor, t.img_actor_t,
                                                                 t.img_critic, t.img_critic_t);
@@ -999,29 +1168,42 @@ int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const f
     a.drop.mode = h->dropout_mode;
     a.drop.k0 = (uint32_t)h->seed; a.drop.k1 = (uint32_t)(h->seed >> 32);
     a.drop.update_idx = h->update_idx; a.drop.row_base = h->rank << 20;
+    {
+        static int prof_env = -1;
+        if (prof_env < 0) { const char *pe = getenv("ERLFILL_UTC_PROF"); prof_env = (pe && pe[0] == '1') ? 1 : 0; }
+        a.prof = prof_env;
+    }
     for (int s = 0; s < 10; ++s) a.drop.m[s] = (h->dropout_mode == ERLFILL_DROPOUT_MASK && h->masks) ? h->masks->keep[s] : nullptr;
     if (h->dropout_mode == ERLFILL_DROPOUT_MASK) {
         if (!h->masks) return ERLFILL_ERR_ARG;
         for (int s = 0; s < 10; ++s) if (!h->masks->keep[s]) return ERLFILL_ERR_ARG;
     }
+    a.tq_g = t.tq_g; a.tq_flag = t.flags;
+    a.stats_g = w.stats; a.stats_part = t.stats_part; a.stats_ctr = t.flags + nc;
+    a.stats_ext = h->n_stats_partials > 0 ? h->d_stats_partials : nullptr; a.n_stats_ext = h->n_stats_partials;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    a.split = (2 * nc <= sms) ? 1 : 0;        // both halves of every tile must be resident at once (one CTA per SM)
     const bool reduced = (phases & ERLFILL_PHASE_REDUCED) != 0;
     if (phases & ERLFILL_PHASE_CRITIC_GRAD) {
-        ddpg_critic_grad_tc<<<nc, NTHR, SMEM_BYTES, st>>>(a);
-        grad_reduce_kernel<false><<<mlp::kSumsqBlocks, 512, 0, st>>>(nc, B, t.cpart, nullptr, w.scal, w.cgrad, w.ssq);
+        ddpg_critic_grad_tc<<<a.split ? 2 * nc : nc, NTHR, SMEM_BYTES, st>>>(a);
+        grad_reduce_kernel<false><<<kRedBlocks, 256, 0, st>>>(nc, B, t.cpart, nullptr, w.scal, w.cgrad, t.ssq_fine);
     }
     if (phases & ERLFILL_PHASE_CRITIC_APPLY) {
         const float *G = reduced ? w.cred : w.cgrad;
-        critic_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->critic, n->critic_m, n->critic_v, G, w.ssq, w.step, h->critic_lr, h->actor_lr,
+        critic_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->critic, n->critic_m, n->critic_v, G, reduced ? w.ssq : t.ssq_fine,
+                                                                     reduced ? mlp::kSumsqBlocks : kRedBlocks, w.step, h->critic_lr, h->actor_lr,
                                                                      h->max_grad_norm, w.scal, t.img_critic);
     }
     if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
         ddpg_actor_grad_tc<<<nc, NTHR, SMEM_BYTES, st>>>(a);
-        grad_reduce_kernel<true><<<mlp::kSumsqBlocks, 512, 0, st>>>(nc, B, t.apart, n->actor, w.scal, w.agrad, w.ssq + mlp::kSumsqBlocks);
+        grad_reduce_kernel<true><<<kRedBlocks, 256, 0, st>>>(nc, B, t.apart, n->actor, w.scal, w.agrad, t.ssq_fine + kRedBlocks);
     }
     if (phases & ERLFILL_PHASE_ACTOR_APPLY) {
         const float *G = reduced ? w.ared : w.agrad;
-        actor_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, n->actor_target, n->actor_m, n->actor_v, G, w.ssq + mlp::kSumsqBlocks, w.step,
-                                                                    h->max_grad_norm, h->tau, n->critic, n->critic_target, w.scal, t.img_actor,
+        actor_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, n->actor_target, n->actor_m, n->actor_v, G,
+                                                                    reduced ? w.ssq + mlp::kSumsqBlocks : t.ssq_fine + kRedBlocks,
+                                                                    reduced ? mlp::kSumsqBlocks : kRedBlocks, w.step, h->max_grad_norm, h->tau, n->critic, n->critic_target, w.scal, t.img_actor,
                                                                     t.img_actor_t, t.img_critic_t, d_report);
     }
     ERLFILL_CUDA_TRY(cudaGetLastError());
@@ -1030,3 +1212,8 @@ int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const f
 
 }  // namespace utc
 }  // namespace erlfill
+
+// development only (not declared in include/erlfill.h): copies the in-kernel profile of CTA 0 (ERLFILL_UTC_PROF=1)
+extern "C" int erlfill_debug_utc_profile(long long *out /*[2][128]*/) {
+    return cudaMemcpyFromSymbol(out, erlfill::utc::g_utc_prof, sizeof(long long) * 256) == cudaSuccess ? 0 : -2;
+}

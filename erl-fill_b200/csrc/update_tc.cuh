@@ -77,12 +77,15 @@ namespace AI { constexpr uint32_t W1 = 0, W2 = W1 + 128 * 48 * 2, W3 = W2 + 128 
 namespace AO { constexpr int EW = 0, W1 = 30, B1 = 670, W2 = 798, B2 = 17182, W3 = 17310, B3 = 25502, W4 = 25566, B4 = 26206, TOTAL = 26216; }
 namespace CO { constexpr int W0 = 0, B0 = 3840, G1 = 4096, BE1 = 4352, W4 = 4608, B4 = 70144, G2 = 70400, BE2 = 70656, W8 = 70912, B8 = 103680, W10 = 103808, B10 = 103936, TOTAL = 103937; }
 
-// per-CTA gradient partials (floats).  critic: the matrices keep the flat layout except W0, which has 16 columns.
-namespace CP { constexpr int W0 = 0, VA = 4096 /* db0 dgamma1 dbeta1 */, W4 = VA + 768, VB = W4 + 65536 /* db4 dgamma2 dbeta2 */,
-               W8 = VB + 768, VC = W8 + 32768 /* db8 dW10 db10 */, LOSS = VC + 257, SIZE = ((LOSS + 1 + 3) / 4) * 4; }
-// actor: EW(32) | W1 [128][16] | B1 | W2 | B2 | W3 | B3 | W4 [16][64] | B4(16) | sum q2 | sum std
-namespace AP { constexpr int EW = 0, W1 = 32, B1 = W1 + 128 * 16, W2 = B1 + 128, B2 = W2 + 128 * 128, W3 = B2 + 128, B3 = W3 + 64 * 128,
-               W4 = B3 + 64, B4 = W4 + 16 * 64, SQ = B4 + 16, SSTD = SQ + 1, SIZE = ((SSTD + 1 + 3) / 4) * 4; }
+// per-CTA gradient partials (floats).  A matrix is a sequence of 128-output-row blocks, each stored [n / 4 float4 columns][128 rows][4]
+// (the order the weight-gradient accumulators are drained in: update_tc.cu, drain_g).
+// critic: W0 2 blocks x 16 columns | db0 dgamma1 dbeta1 | W4 2 blocks x 256 | db4 dgamma2 dbeta2 | W8 1 block x 256 | db8 dW10 db10 | loss
+namespace CP { constexpr int W0 = 0, VA = 4096, W4 = VA + 768, VB = W4 + 65536, W8 = VB + 768, VC = W8 + 32768, LOSS = VC + 257,
+               SIZE = ((LOSS + 1 + 3) / 4) * 4; }
+// actor: EW(32) | W1 block x 16 | B1 | W2 block x 128 | B2 | W3 block x 128 (64 rows used) | B3 | W4 block x 64 (10 rows used) | B4(16) | sum q2 | sum std
+namespace AP { constexpr int EW = 0, W1 = 32, B1 = W1 + 128 * 16, W2 = B1 + 128, B2 = W2 + 128 * 128, W3 = B2 + 128, B3 = W3 + 128 * 128,
+               W4 = B3 + 64, B4 = W4 + 128 * 64, SQ = B4 + 16, SSTD = SQ + 1, SIZE = ((SSTD + 1 + 3) / 4) * 4; }
+static_assert(CP::VA == 2 * 2048 && CP::VB - CP::W4 == 2 * 32768 && CP::VC - CP::W8 == 32768, "critic partial blocks");
 
 // ---- small helpers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }

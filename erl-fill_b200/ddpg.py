@@ -93,6 +93,18 @@ class ReplayBuffer:
                                                   L.stream_ptr()), "erlfill_replay_sample")
         return out
 
+    def sample_gather(self, batch, seed, update_idx, stream_id=0, out=None, idx_out=None, stats_out=None):
+        """R2 in one launch (index draw + assembly); stats_out: optional float32[blocks, 8] buffer for the emotion sums the fast
+        update path consumes (returned as the second value)."""
+        if out is None:
+            out = torch.empty(batch, L.REC, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().erlfill_replay_sample_gather(C.c_int(batch), C.c_int64(self.size), C.c_uint64(seed),
+                                                         C.c_uint32(update_idx & 0xFFFFFFFF), C.c_uint32(stream_id), L.ptr(self.buf),
+                                                         L.ptr(idx_out), L.ptr(out), L.ptr(stats_out), L.stream_ptr()),
+                    "erlfill_replay_sample_gather")
+        return out, stats_out
+
     def gather(self, idx, out=None):
         b = idx.shape[0]
         if out is None:
@@ -213,7 +225,7 @@ class DDPGLearner:
             L.check(L.lib().erlfill_ddpg_pack_images(C.byref(nets), L.ptr(ws), C.c_int(B), L.stream_ptr()), "erlfill_ddpg_pack_images")
         self._images_ok = True
 
-    def update(self, batch, next_emotion, train_step, phases=L.PHASE_ALL, allreduce=None, graph=None, masks=None):
+    def update(self, batch, next_emotion, train_step, phases=L.PHASE_ALL, allreduce=None, graph=None, masks=None, stats_partials=None):
         """One learn() on a gathered batch [B,20].  allreduce(tensor): optional in-place averaging callback
         applied to the critic bucket and then the actor bucket (data-parallel).
 
@@ -253,14 +265,15 @@ class DDPGLearner:
         def run(ph, adam_step):
             hyper = L.DDPGHyper(B, adam_step, self.gamma, self.tau, 5.0, self.n_cond, self.critic_lr, self.actor_lr, decay,
                                 L.PRECISION_FAST if fast else L.PRECISION_EXACT, dmode, self.seed, upd_idx, self.rank,
-                                C.cast(C.pointer(mstruct), C.c_void_p) if mstruct is not None else None)
+                                C.cast(C.pointer(mstruct), C.c_void_p) if mstruct is not None else None,
+                                L.ptr(stats_partials), 0 if stats_partials is None else int(stats_partials.shape[0]), 0)
             with torch.cuda.device(self.device):
                 L.check(L.lib().erlfill_ddpg_update(C.byref(nets), C.byref(hyper), L.ptr(batch), L.ptr(next_emotion), L.ptr(ws),
                                                     C.c_int(ph), L.ptr(self.report), L.stream_ptr()), "erlfill_ddpg_update")
 
         # everything a captured graph bakes in: buffer addresses (the workspace included) and the by-value hyper-parameters
         key = (B, batch.data_ptr(), next_emotion.data_ptr(), ws.data_ptr(), id(allreduce), self.gamma, self.tau, self.critic_lr,
-               self.actor_lr, self.n_cond, self.precision)
+               self.actor_lr, self.n_cond, self.precision, 0 if stats_partials is None else stats_partials.data_ptr())
         if graph and key not in self._graphs and key not in self._warm:
             self._warm.add(key)          # first update on these buffers runs eagerly (module loading outside a capture)
             graph = False

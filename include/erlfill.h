@@ -304,6 +304,14 @@ int erlfill_replay_sample(int batch, int64_t n_valid, uint64_t seed, uint32_t up
 /* R2 — minibatch assembly (ddpg_agent.py:434-442): d_out[b][:] = d_buf[d_idx[b]][:]. */
 int erlfill_replay_gather(int batch, const float *d_buf, const int64_t *d_idx, float *d_out, void *stream);
 
+/* R2 in one launch: the index draw of erlfill_replay_sample followed by the assembly of erlfill_replay_gather (same indices, same rows).
+ * d_idx (optional) receives the indices.  d_stats_partials (optional): [erlfill_replay_sample_gather_blocks(batch)][8] floats, per block
+ * of 64 samples the sums  sum(e_c - 0.5) | sum((e_c - 0.5)^2)  of the three emotion columns — the by-product that lets
+ * erlfill_ddpg_update skip its own pass over the minibatch for the batch statistics of Critic.forward (ddpg_agent.py:176). */
+int erlfill_replay_sample_gather_blocks(int batch);
+int erlfill_replay_sample_gather(int batch, int64_t n_valid, uint64_t seed, uint32_t update_idx, uint32_t stream_id, const float *d_buf,
+                                 int64_t *d_idx, float *d_out, float *d_stats_partials, void *stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* ER-DDPG update                                                                              */
 /* ------------------------------------------------------------------------------------------ */
@@ -343,6 +351,9 @@ typedef struct {
     uint64_t seed;                /* Philox key of the dropout masks */
     uint32_t update_idx, rank;    /* Philox counter words: update index, data-parallel rank (row id = rank << 20 | minibatch row) */
     const erlfill_ddpg_masks *masks;   /* ERLFILL_DROPOUT_MASK only */
+    /* optional (ERLFILL_PRECISION_FAST): the emotion sums erlfill_replay_sample_gather left for THIS minibatch, n_stats_partials rows of 8 */
+    const float *d_stats_partials;
+    int32_t n_stats_partials, _pad2;
 } erlfill_ddpg_hyper;
 
 typedef enum { ERLFILL_PHASE_CRITIC_GRAD = 1, ERLFILL_PHASE_CRITIC_APPLY = 2, ERLFILL_PHASE_ACTOR_GRAD = 4,

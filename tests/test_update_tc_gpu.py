@@ -197,3 +197,33 @@ def test_philox_dropout_equals_injecting_the_same_masks(precision):
     off = _learner(g, precision)
     r0 = off.update(_batch(g, g["idx"][0])[0], ne, 7)
     assert abs(float(r0[0]) - float(a.report[0])) > 1e-4          # dropout is really on
+
+
+def test_sample_gather_is_sample_then_gather_and_its_emotion_sums_feed_the_update():
+    from erlfill_b200 import _lib as L
+    from erlfill_b200.ddpg import ReplayBuffer
+    g = np.load(os.path.join(GOLD, "learn_golden.npz"))
+    mem = ReplayBuffer(5000)
+    gen = torch.Generator().manual_seed(3)
+    rows = torch.rand(5000, 20, generator=gen)
+    rows[:, 2:12] = rows[:, 2:12] * 2 - 1; rows[:, 12] = rows[:, 12] * 9000 - 3000; rows[:, 15] = (rows[:, 15] < 0.05).float()
+    mem.buf.copy_(rows.cuda()); mem.size = mem.inserted = 5000
+    B = 300
+    idx = mem.sample_indices(B, 7, 3, stream_id=2)
+    ref = mem.gather(idx)
+    nblk = L.lib().erlfill_replay_sample_gather_blocks(B)
+    idx2 = torch.empty(B, dtype=torch.int64, device="cuda")
+    out, st = mem.sample_gather(B, 7, 3, stream_id=2, idx_out=idx2, stats_out=torch.zeros(nblk, 8, device="cuda"))
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref) and torch.equal(idx2, idx)                    # bit-exact: the same Philox draw, the same rows
+    e = ref[:, 16:19].double().cpu() - 0.5
+    np.testing.assert_allclose(st.sum(0)[:3].cpu().numpy(), e.sum(0).numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(st.sum(0)[3:6].cpu().numpy(), (e * e).sum(0).numpy(), rtol=1e-5)
+    # the update fed with these sums equals the update that walks the minibatch itself (statistics agree to ~1e-7)
+    a, b = _learner(g, "fast", batch=B), _learner(g, "fast", batch=B)
+    ne = T(g["next_emotion"][0]).float().cuda()
+    ra = a.update(out, ne, 7, graph=False).clone()
+    rb = b.update(out, ne, 7, graph=False, stats_partials=st).clone()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(ra.cpu().numpy(), rb.cpu().numpy(), rtol=1e-5)
+    assert float((a.critic.flat - b.critic.flat).abs().max()) < 1e-4 and float((a.actor.flat - b.actor.flat).abs().max()) < 1e-5
