@@ -136,7 +136,7 @@ EXPORTS = [
     "erlfill_env_reset", "erlfill_env_reset_from_replay", "erlfill_env_step", "erlfill_env_step_counted", "erlfill_env_step_set_mode",
     "erlfill_env_step_fused_max_envs",
     "erlfill_actor_forward", "erlfill_actor_forward_cond", "erlfill_replay_insert_cond", "erlfill_emotion_update", "erlfill_episode_end", "erlfill_emotion_forward",
-    "erlfill_emotion_tc_image_bytes", "erlfill_emotion_tc_pack", "erlfill_emotion_forward_tc",
+    "erlfill_emotion_tc_image_bytes", "erlfill_emotion_tc_pack", "erlfill_emotion_forward_tc", "erlfill_emotion_forward_tc_train",
     "erlfill_replay_insert", "erlfill_replay_sample", "erlfill_replay_gather", "erlfill_replay_sample_gather",
     "erlfill_replay_sample_gather_blocks",
     "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_set_step", "erlfill_ddpg_update", "erlfill_ddpg_pack_images",

@@ -17,6 +17,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tf_dropout.cuh"
 
 namespace erlfill {
 
@@ -54,10 +55,9 @@ __device__ __forceinline__ float keep_scale(const TfArgs &a, uint32_t gid, uint3
     bool keep;
     if (a.dropout_mode == ERLFILL_DROPOUT_MASK) keep = mask_ptr[mask_idx] != 0;
     else {
-        const uint4 r = philox4x32_10((uint32_t)a.seed, (uint32_t)(a.seed >> 32), gid, a.call_idx, idx >> 2,
-                                      STREAM_DROPOUT + 8u + site);
-        const uint32_t x = (idx & 3) == 0 ? r.x : ((idx & 3) == 1 ? r.y : ((idx & 3) == 2 ? r.z : r.w));
-        keep = (float)(x >> 8) * (1.0f / 16777216.0f) >= 0.3f;
+        // the mask definition shared with the tensor-core kernel: tf_dropout.cuh
+        const uint4 r = tfdrop::block8((uint32_t)a.seed, (uint32_t)(a.seed >> 32), gid, a.call_idx, site, idx >> 3);
+        keep = tfdrop::keep_elem(r, (int)(idx & 7u));
     }
     return keep ? (1.0f / (1.0f - 0.3f)) : 0.0f;
 }

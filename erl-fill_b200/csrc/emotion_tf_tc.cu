@@ -1,5 +1,6 @@
 // emotion_tf_tc.cu — M2: EmotionTransformer.forward (EmotionModule.py:48-71) batched over envs on the sm_100a
-// tensor cores (tcgen05.mma, accumulators in tensor memory), dropout off (module.eval()).
+// tensor cores (tcgen05.mma, accumulators in tensor memory); dropout off (module.eval()), or train() mode as the reference runs it
+// (it never calls .eval() on this path): keep-masks from Philox or injected by the caller (tf_dropout.cuh), template kDrop.
 //
 // Same network as emotion_tf.cu (the exact fp32 twin): embedding Linear(3,32) + positions -> 4 x post-norm
 // TransformerEncoderLayer(d=32, 4 heads x 8, FFN 32->2048->32 ReLU, LayerNorm eps 1e-5) -> last token ->
@@ -32,6 +33,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tf_dropout.cuh"
 #include "umma.cuh"
 
 namespace erlfill {
@@ -121,7 +123,11 @@ struct TcArgs {
     const float *d_seq;
     float *d_out;
     int n, S, n_groups;
+    // train() mode (kDrop != 0)
+    uint32_t k0, k1, call_idx, row_id_base;
+    erlfill_transformer_masks masks;
 };
+constexpr int DROP_OFF = 0, DROP_PHILOX = 1, DROP_MASK = 2;
 
 // development profile: clock64 ticks of block 0 / thread 0 per phase (see erlfill_debug_tc_profile)
 __device__ unsigned long long g_tc_prof[16];
@@ -219,6 +225,7 @@ struct Sched {
     __device__ bool flush_after_group(int it, int n_it) const { return pending + kTiles * EPT > TAIL_ROWS || it == n_it - 1; }
 };
 
+template <int kDrop>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);
@@ -422,7 +429,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
         // ---- first half of a layer: x -> q|k|v (tensor core) -> attention on register fragments -> bf16 rows of o.
         //      park == false: o goes to the tile's operand image for the out_proj that follows;
         //      park == true (last layer): only each env's last-token row is kept, in the tail image at row sc.pending + t*6 + env ----
-        auto first_half = [&](bool park) {
+        // global ids of the tile's six envs (Philox counter word / mask row) in the current group
+        int grp_env0 = 0;
+        auto first_half = [&](bool park, int l) {
             store_row_tmem(tT + TM_X, x);
             tc_fence_before();
             __syncwarp();
@@ -547,6 +556,30 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
                                 sum1 += p2 + p3;
                                 pa[nt][1] = pack_bf16x2(p2, p3);
                             } else pa[nt][1] = 0u;
+                            if (kDrop != DROP_OFF) {
+                                // dropout on the attention probabilities (the sums above stay those of the undropped softmax): the pair
+                                // (query i, keys j, j + 1) sits in one half-word pair of one Philox block since its element index is even
+                                const int env_g = grp_env0 + e;
+                                const int j = nt * 8 + 2 * tq;
+#pragma unroll
+                                for (int hf = 0; hf < 2; ++hf) {
+                                    if (hf == 1 && lo_rows_only) continue;
+                                    const int i = mt * 16 + g8 + 8 * hf;
+                                    uint32_t m = 0xffffffffu;
+                                    if (i < Se && j < Se && env_g < a.n) {
+                                        if (kDrop == DROP_PHILOX) {
+                                            const uint32_t idx = (uint32_t)((h * SMAX + i) * SMAX + j);
+                                            const uint4 rr = tfdrop::block8(a.k0, a.k1, a.row_id_base + (uint32_t)env_g, a.call_idx, 4u * l, idx >> 3);
+                                            const uint32_t lane4 = (idx & 7u) >> 1;
+                                            m = tfdrop::pair_mask(lane4 == 0 ? rr.x : (lane4 == 1 ? rr.y : (lane4 == 2 ? rr.z : rr.w)));
+                                        } else {
+                                            const uint8_t *mp = a.masks.attn + ((((size_t)l * a.n + env_g) * 4 + h) * a.S + i) * a.S + j;
+                                            m = (mp[0] ? 0xffffu : 0u) | ((j + 1 < Se && mp[1]) ? 0xffff0000u : 0u);
+                                        }
+                                    }
+                                    pa[nt][hf] &= m;
+                                }
+                            }
                         }
                         sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
                         if (!lo_rows_only) {
@@ -557,12 +590,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
                         for (int ks = 0; ks < 3; ++ks) mma_16x8x8(o, pa[ks][0], pa[ks][1], vb[ks]);
                         // rows past the env's 20 tokens belong to the next env: not stored
                         const int q0 = mt * 16 + g8;
+                        const float dsc = kDrop != DROP_OFF ? tfdrop::kScale : 1.0f;      // kept probabilities carry 1 / 0.7
                         if (q0 < SMAX) {
-                            const float i0 = fast_rcp(sum0);
+                            const float i0 = fast_rcp(sum0) * dsc;
                             store_o(q0, o[0] * i0, o[1] * i0);
                         }
                         if (!lo_rows_only) {
-                            const float i1 = fast_rcp(sum1);
+                            const float i1 = fast_rcp(sum1) * dsc;
                             store_o(q0 + 8, o[2] * i1, o[3] * i1);
                         }
                     }
@@ -574,6 +608,24 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
         };
 
         // ---- second half of a layer on this thread's row: out_proj + residual + LayerNorm1, FFN, + residual + LayerNorm2 ----
+        // drow_env / drow_s: the env (index in this call) and token of the row this thread processes in second_half (-1: padding row)
+        int drow_env = -1, drow_s = 0;
+        // 32 keep bits (features 0..31) of this row at site 4l + which (1: dropout1, 3: dropout2)
+        auto keep32_row = [&](int l, int which) -> uint32_t {
+            if (kDrop == DROP_OFF || drow_env < 0) return 0xffffffffu;
+            uint32_t bits = 0;
+            if (kDrop == DROP_PHILOX) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    bits |= tfdrop::keep_bits8(tfdrop::block8(a.k0, a.k1, a.row_id_base + (uint32_t)drow_env, a.call_idx, 4u * l + which,
+                                                              (uint32_t)(drow_s * 4 + q))) << (8 * q);
+            } else {
+                const uint8_t *mp = (which == 1 ? a.masks.d1 : a.masks.d2) + (((size_t)l * a.n + drow_env) * a.S + drow_s) * D;
+#pragma unroll
+                for (int d = 0; d < D; ++d) bits |= (mp[d] ? 1u : 0u) << d;
+            }
+            return bits;
+        };
         auto second_half = [&](int l) {
             const uint32_t par = sc.nB & 1u;
             const float *lw = misc + l * MISC_LAYER;
@@ -586,8 +638,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
                 uint32_t ro[32];
                 tmem_ld32(tT + TM_Y, ro);
                 tmem_wait_ld();
+                if (kDrop == DROP_OFF) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) x[d] += __uint_as_float(ro[d]);
+                    for (int d = 0; d < D; ++d) x[d] += __uint_as_float(ro[d]);
+                } else {
+                    const uint32_t kb = keep32_row(l, 1);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) x[d] += ((kb >> d) & 1u) ? __uint_as_float(ro[d]) * tfdrop::kScale : 0.f;
+                }
             }
             layer_norm32(x, lw, lw + D);
             store_row_tmem(tT + TM_X, x);
@@ -598,6 +656,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
                 const uint32_t g = sc.nB * NCH + c, hb = g % NHB;
+                // dropout on the hidden activation: packed word w of the chunk holds units 64c + 2w, 2w + 1 = the two halves of word w % 4
+                // of the row's Philox block s * 256 + 8c + w / 4.  The masks do not depend on H: they are drawn BEFORE waiting for the
+                // chunk's MMA, in the time the row owner would otherwise idle.  (The 1 / 0.7 scale is applied to Y, which is linear in P.)
+                uint32_t dm[32];
+                if (kDrop == DROP_PHILOX && drow_env >= 0) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint4 rr = tfdrop::block8(a.k0, a.k1, a.row_id_base + (uint32_t)drow_env, a.call_idx, 4u * l + 2u,
+                                                        (uint32_t)(drow_s * (FF / 8) + c * (CH / 8) + q));
+                        dm[4 * q] = tfdrop::pair_mask(rr.x); dm[4 * q + 1] = tfdrop::pair_mask(rr.y);
+                        dm[4 * q + 2] = tfdrop::pair_mask(rr.z); dm[4 * q + 3] = tfdrop::pair_mask(rr.w);
+                    }
+                }
                 mbar_wait(b + B_H + hb, (g / NHB) & 1u);
                 tc_fence_after();
                 uint32_t h0[32], h1[32], p[32];
@@ -608,6 +679,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
                 for (int j = 0; j < 16; ++j) {
                     p[j] = pack_relu_bf16x2(__uint_as_float(h0[2 * j]), __uint_as_float(h0[2 * j + 1]));
                     p[16 + j] = pack_relu_bf16x2(__uint_as_float(h1[2 * j]), __uint_as_float(h1[2 * j + 1]));
+                }
+                if (kDrop == DROP_PHILOX && drow_env >= 0) {
+#pragma unroll
+                    for (int w = 0; w < 32; ++w) p[w] &= dm[w];
+                } else if (kDrop == DROP_MASK && drow_env >= 0) {
+                    const uint8_t *mp = a.masks.ff + (((size_t)l * a.n + drow_env) * a.S + drow_s) * FF + c * CH;
+#pragma unroll
+                    for (int w = 0; w < 32; ++w) p[w] &= (mp[2 * w] ? 0xffffu : 0u) | (mp[2 * w + 1] ? 0xffff0000u : 0u);
                 }
                 tmem_st32(tT + hb * CH, p);
                 tmem_wait_st();
@@ -622,13 +701,21 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
                 uint32_t ry[32];
                 tmem_ld32(tT + TM_Y, ry);
                 tmem_wait_ld();
+                if (kDrop == DROP_OFF) {
 #pragma unroll
-                for (int d4 = 0; d4 < D; d4 += 4) {
-                    const float4 b2 = *reinterpret_cast<const float4 *>(lw + 4 * D + d4);
-                    x[d4 + 0] += __uint_as_float(ry[d4 + 0]) + b2.x;
-                    x[d4 + 1] += __uint_as_float(ry[d4 + 1]) + b2.y;
-                    x[d4 + 2] += __uint_as_float(ry[d4 + 2]) + b2.z;
-                    x[d4 + 3] += __uint_as_float(ry[d4 + 3]) + b2.w;
+                    for (int d4 = 0; d4 < D; d4 += 4) {
+                        const float4 b2 = *reinterpret_cast<const float4 *>(lw + 4 * D + d4);
+                        x[d4 + 0] += __uint_as_float(ry[d4 + 0]) + b2.x;
+                        x[d4 + 1] += __uint_as_float(ry[d4 + 1]) + b2.y;
+                        x[d4 + 2] += __uint_as_float(ry[d4 + 2]) + b2.z;
+                        x[d4 + 3] += __uint_as_float(ry[d4 + 3]) + b2.w;
+                    }
+                } else {
+                    // Y = W2 (keep o relu(h)): the FFN dropout's 1 / 0.7 first, then the bias, then dropout2 (with its own 1 / 0.7)
+                    const uint32_t kb = keep32_row(l, 3);
+#pragma unroll
+                    for (int d = 0; d < D; ++d)
+                        x[d] += ((kb >> d) & 1u) ? (__uint_as_float(ry[d]) * tfdrop::kScale + lw[4 * D + d]) * tfdrop::kScale : 0.f;
                 }
             }
             layer_norm32(x, lw + 2 * D, lw + 3 * D);
@@ -678,9 +765,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
             // the previous group's attention (last reader of slen) finished before this point: every warp of the tile has since
             // passed a barrier that all four warps arrive on after their attention
             if (r < ROWS && s_pos == 0) slen[e_loc] = S;
+            grp_env0 = (group * kTiles + t) * EPT;
+            drow_env = (env_ok && s_pos < S) ? env : -1;
+            drow_s = s_pos;
 
             for (int l = 0; l < NL - 1; ++l) {
-                first_half(false);
+                first_half(false, l);
                 second_half(l);
             }
             // last layer: park the residual stream of each env's last token (and which env it is); the attention parks its o row
@@ -689,15 +779,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
                 float4 *dst = reinterpret_cast<float4 *>(xtail + pr * XT_LD);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-                envtail[pr] = (env_ok && S > 0) ? env : -1;
+                envtail[pr] = (env_ok && S > 0) ? (env | ((S - 1) << 24)) : -1;      // env (< 2^24) and the token index of the parked row
             }
-            first_half(true);
+            first_half(true, NL - 1);
             sc.pending += kTiles * EPT;
             if (sc.flush_after_group(it, n_it)) {
                 // ---- tail pass: second half of the last layer on the parked rows; thread r of tile t takes parked row t*128 + r ----
                 asm volatile("bar.sync %0, %1;" ::"r"(kTiles + 1), "r"(kTiles * 128) : "memory");     // all parked rows written
                 const int pr = t * 128 + r;
-                const int penv = pr < sc.pending ? envtail[pr] : -1;
+                const int ptag = pr < sc.pending ? envtail[pr] : -1;
+                const int penv = ptag < 0 ? -1 : (ptag & 0xffffff);
+                drow_env = penv; drow_s = ptag < 0 ? 0 : (ptag >> 24);
                 {
                     const float4 *src = reinterpret_cast<const float4 *>(xtail + pr * XT_LD);
 #pragma unroll
@@ -827,13 +919,23 @@ int erlfill_emotion_tc_pack(const erlfill_transformer_weights *w, void *d_image,
 
 int erlfill_emotion_forward_tc(const void *d_image, int n_env, const float *d_seq, int seq_len,
                                const erlfill_emotion_state *emo, float *d_out, void *stream) {
-    if (!d_image || n_env <= 0 || !d_out) return ERLFILL_ERR_ARG;
+    return erlfill_emotion_forward_tc_train(d_image, n_env, d_seq, seq_len, emo, ERLFILL_DROPOUT_OFF, 0, 0, 0, nullptr, d_out, stream);
+}
+
+int erlfill_emotion_forward_tc_train(const void *d_image, int n_env, const float *d_seq, int seq_len, const erlfill_emotion_state *emo,
+                                     int dropout_mode, uint64_t seed, uint32_t call_idx, uint32_t row_id_base,
+                                     const erlfill_transformer_masks *masks, float *d_out, void *stream) {
+    if (!d_image || n_env <= 0 || n_env >= (1 << 24) || !d_out) return ERLFILL_ERR_ARG;
+    if (dropout_mode < ERLFILL_DROPOUT_OFF || dropout_mode > ERLFILL_DROPOUT_MASK) return ERLFILL_ERR_ARG;
+    if (dropout_mode == ERLFILL_DROPOUT_MASK && (!masks || !masks->attn || !masks->d1 || !masks->ff || !masks->d2 || !d_seq)) return ERLFILL_ERR_ARG;
     if (!d_seq && (!emo || !emo->d_history || !emo->d_hist_len || !emo->d_hist_head)) return ERLFILL_ERR_ARG;
     if (d_seq && (seq_len < 1 || seq_len > tc::SMAX)) return ERLFILL_ERR_ARG;
     tc::TcArgs a;
     a.img = static_cast<const uint8_t *>(d_image);
     if (emo) a.emo = *emo; else a.emo = erlfill_emotion_state{};
     a.d_seq = d_seq; a.d_out = d_out; a.n = n_env; a.S = d_seq ? seq_len : tc::SMAX;
+    a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32); a.call_idx = call_idx; a.row_id_base = row_id_base;
+    if (masks) a.masks = *masks; else a.masks = erlfill_transformer_masks{};
     a.n_groups = (n_env + tc::kTiles * tc::EPT - 1) / (tc::kTiles * tc::EPT);
     static int n_sm[64] = {};
     int dev = 0;
@@ -842,12 +944,16 @@ int erlfill_emotion_forward_tc(const void *d_image, int n_env, const float *d_se
     if (!n_sm[dev]) {
         int v = 0;
         ERLFILL_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
-        ERLFILL_CUDA_TRY(cudaFuncSetAttribute(tc::emotion_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        ERLFILL_CUDA_TRY(cudaFuncSetAttribute(tc::emotion_forward_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        ERLFILL_CUDA_TRY(cudaFuncSetAttribute(tc::emotion_forward_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        ERLFILL_CUDA_TRY(cudaFuncSetAttribute(tc::emotion_forward_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         n_sm[dev] = v;
     }
     const int max_ctas = n_sm[dev] * tc::kCtasPerSm;
     const int grid = a.n_groups < max_ctas ? a.n_groups : max_ctas;
-    tc::emotion_forward_tc_kernel<<<grid, tc::kThreads, tc::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    if (dropout_mode == ERLFILL_DROPOUT_OFF) tc::emotion_forward_tc_kernel<0><<<grid, tc::kThreads, tc::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    else if (dropout_mode == ERLFILL_DROPOUT_PHILOX) tc::emotion_forward_tc_kernel<1><<<grid, tc::kThreads, tc::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    else tc::emotion_forward_tc_kernel<2><<<grid, tc::kThreads, tc::SMEM_BYTES, (cudaStream_t)stream>>>(a);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
 }

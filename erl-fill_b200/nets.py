@@ -141,14 +141,17 @@ def emotion_forward(params, seq=None, emo=None, dropout=L.DROPOUT_OFF, masks=Non
         out = torch.empty(n, 3, dtype=torch.float32, device=dev)
     es = emo.struct() if emo is not None else None
     if precision == "bf16":
-        # tensor-core path (tcgen05, bf16 operands / fp32 accumulate): eval() semantics only
-        if dropout != L.DROPOUT_OFF or masks is not None:
-            raise L.ErlfillError("emotion_forward(precision='bf16') implements dropout off only; use the fp32 path")
+        # tensor-core path (tcgen05, bf16 operands / fp32 accumulate); train()-mode dropout draws the same masks as the fp32 kernel
         img = params.tc_image()
+        ms = None
+        if masks is not None:
+            ms = L.TransformerMasks(L.ptr(masks["attn"]), L.ptr(masks["d1"]), L.ptr(masks["ff"]), L.ptr(masks["d2"]))
         with torch.cuda.device(dev):
-            L.check(L.lib().erlfill_emotion_forward_tc(L.ptr(img), C.c_int(n), L.ptr(seq), C.c_int(S),
-                                                       C.byref(es) if es is not None else None, L.ptr(out),
-                                                       L.stream_ptr()), "erlfill_emotion_forward_tc")
+            L.check(L.lib().erlfill_emotion_forward_tc_train(L.ptr(img), C.c_int(n), L.ptr(seq), C.c_int(S),
+                                                             C.byref(es) if es is not None else None, C.c_int(dropout),
+                                                             C.c_uint64(seed), C.c_uint32(call_idx), C.c_uint32(row_id_base),
+                                                             C.byref(ms) if ms is not None else None, L.ptr(out), L.stream_ptr()),
+                    "erlfill_emotion_forward_tc_train")
         return out
     if precision != "fp32":
         raise L.ErlfillError(f"emotion_forward: unknown precision {precision!r}")

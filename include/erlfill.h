@@ -264,7 +264,7 @@ int erlfill_emotion_forward(const erlfill_transformer_weights *w, int n_env, con
                             uint32_t row_id_base, const erlfill_transformer_masks *masks, float *d_out, void *stream);
 
 /* M2 on the tensor cores (tcgen05.mma, bf16 operands, fp32 accumulation in tensor memory; attention, LayerNorm and
- * the residual stream stay fp32), dropout off only (module.eval()): the batched rollout's get_emotion().  Same
+ * the residual stream stay fp32), dropout off (module.eval()): the batched rollout's get_emotion().  Same
  * sequence sources as erlfill_emotion_forward.  The parameters are packed once per weight change into a device
  * image of erlfill_emotion_tc_image_bytes() bytes (16-byte aligned, caller-owned).  Stated tolerance against the
  * fp32 path: 1e-2 absolute on the [0,1] outputs (tests/test_emotion_tc_gpu.py; measured ~2e-3). */
@@ -272,6 +272,13 @@ size_t erlfill_emotion_tc_image_bytes(void);
 int erlfill_emotion_tc_pack(const erlfill_transformer_weights *w, void *d_image, void *stream);
 int erlfill_emotion_forward_tc(const void *d_image, int n_env, const float *d_seq, int seq_len,
                                const erlfill_emotion_state *emo, float *d_out, void *stream);
+/* The same in train() mode — what the reference actually runs: it never calls .eval() on the transformer (EmotionModule.py:9,35), so
+ * the four dropout layers of every encoder layer (attention probabilities, dropout1, FFN hidden, dropout2; p = 0.3) are active in
+ * every get_emotion().  dropout_mode / seed / call_idx / row_id_base / masks as in erlfill_emotion_forward: PHILOX draws the SAME
+ * masks as the fp32 kernel (csrc/tf_dropout.cuh), MASK takes the caller's (d_seq required).  n_env < 2^24. */
+int erlfill_emotion_forward_tc_train(const void *d_image, int n_env, const float *d_seq, int seq_len,
+                                     const erlfill_emotion_state *emo, int dropout_mode, uint64_t seed, uint32_t call_idx,
+                                     uint32_t row_id_base, const erlfill_transformer_masks *masks, float *d_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Replay buffer: [capacity][ERLFILL_REC] binary32 rows                                        */

@@ -1,7 +1,7 @@
 """GPU parity of the tensor-core EmotionTransformer (emotion_tf_tc.cu: tcgen05.mma, bf16 operands, fp32
 accumulation) through the C ABI.
 
-Two checks, both with dropout off (the only mode this kernel implements):
+Checks with dropout off (module.eval()), and at the end of the file train() mode (injected masks, Philox masks):
   1. against a torch emulation of the kernel's own arithmetic (same bf16 rounding points: activations entering
      each projection, q/k/v and the softmax probabilities, the ReLU'd hidden activation, every weight; biases as
      hi+lo bf16 pairs): atol 2e-4 -- this
@@ -142,4 +142,63 @@ def test_tc_history_ring_sources(G):
     emo.hist_len[::3] = 0
     a = nets.emotion_forward(P, emo=emo, precision="bf16")
     b = nets.emotion_forward(P, emo=emo)
+    assert (a - b).abs().max().item() <= BF16_ATOL
+
+
+# ---- train() mode: the four dropout layers of every encoder layer (the reference never calls .eval(), EmotionModule.py:9,35) -------------
+def _masks_from_golden(G):
+    attn = np.stack([G[f"trans_attn{l}"] for l in range(4)])
+    d1 = np.stack([G[f"trans_d1_{l}"] for l in range(4)])
+    ff = np.stack([np.unpackbits(G[f"trans_ff{l}"], axis=-1)[..., :2048] for l in range(4)])
+    d2 = np.stack([G[f"trans_d2_{l}"] for l in range(4)])
+    return {k: torch.from_numpy(np.ascontiguousarray(v.astype(np.uint8))).cuda() for k, v in dict(attn=attn, d1=d1, ff=ff, d2=d2).items()}
+
+
+def test_tc_train_mode_with_the_references_own_masks(G):
+    """The reference module's train()-mode output with its dropout masks replayed (oracle/gen_golden.py nets): the tensor-core
+    kernel with the same masks injected, at the stated bf16 tolerance; the fp32 kernel beside it."""
+    from erlfill_b200 import nets, _lib as L
+    W = load_weights(G, "trans.")
+    P = nets.TransformerParams(W)
+    seq = T(G["seqs"]).contiguous()
+    masks = _masks_from_golden(G)
+    out = nets.emotion_forward(P, seq=seq, dropout=L.DROPOUT_MASK, masks=masks, precision="bf16").cpu().numpy()
+    f32 = nets.emotion_forward(P, seq=seq, dropout=L.DROPOUT_MASK, masks=masks).cpu().numpy()
+    err = np.abs(out - G["trans_train"]).max()
+    print("train mode: max |tc - reference| = %.2e, |tc - fp32 kernel| = %.2e" % (err, np.abs(out - f32).max()))
+    assert err <= BF16_ATOL
+    assert np.abs(G["trans_train"] - G["trans_eval"]).max() > 5 * BF16_ATOL      # the masks matter far more than the tolerance
+
+
+def test_tc_philox_dropout_draws_the_fp32_kernels_masks(G):
+    """ERLFILL_DROPOUT_PHILOX: both kernels draw the masks of csrc/tf_dropout.cuh, so with the same (seed, call index, row ids) the
+    tensor-core output equals the exact fp32 kernel's within the bf16 tolerance — across groups, ragged tails and partial histories."""
+    from erlfill_b200 import nets, _lib as L
+    W = load_weights(G, "trans.")
+    P = nets.TransformerParams(W)
+    g = torch.Generator().manual_seed(9)
+    for n in (1, 13, 148 * 12 + 7):
+        seq = torch.rand(n, 20, 3, generator=g).cuda()
+        kw = dict(dropout=L.DROPOUT_PHILOX, seed=0xABCDEF12345, call_idx=77, row_id_base=1000)
+        a = nets.emotion_forward(P, seq=seq, precision="bf16", **kw)
+        b = nets.emotion_forward(P, seq=seq, **kw)
+        err = (a - b).abs().max().item()
+        assert torch.isfinite(a).all() and err <= BF16_ATOL, (n, err)
+        assert torch.equal(a, nets.emotion_forward(P, seq=seq, precision="bf16", **kw))          # deterministic
+        ev = nets.emotion_forward(P, seq=seq, precision="bf16")
+        kw2 = dict(kw, call_idx=78)
+        assert (a - ev).abs().max().item() > 5 * BF16_ATOL or n == 1
+        assert (a - nets.emotion_forward(P, seq=seq, precision="bf16", **kw2)).abs().max().item() > 1e-3
+    # history-ring source with mixed sequence lengths (S = 1 rows draw no masks they should not)
+    n = 29
+    emo = nets.EmotionStateVec(n)
+    rng = np.random.RandomState(2)
+    zeros = torch.zeros(n, 2, device="cuda")
+    for t in range(23):
+        nets.emotion_update(emo, torch.tensor(rng.uniform(-3, 3, n), dtype=torch.float32, device="cuda"), zeros,
+                            torch.tensor(rng.uniform(-1, 1, (n, 2)), dtype=torch.float32, device="cuda"))
+    emo.hist_len[::3] = 0
+    kw = dict(dropout=L.DROPOUT_PHILOX, seed=5, call_idx=3, row_id_base=64)
+    a = nets.emotion_forward(P, emo=emo, precision="bf16", **kw)
+    b = nets.emotion_forward(P, emo=emo, **kw)
     assert (a - b).abs().max().item() <= BF16_ATOL
