@@ -371,9 +371,28 @@ def wl_rollout(args, rank, world, device, timer):
     # the dominant kernel (emotion transformer) timed alone
     tf_ms = _kernel_ms(timer, agent._emotion_forward)
     units = n * world * args.steps
+    # the other dropout mode of configs[2] ("report both .eval() and Philox-mask mode"), same envs, fewer steps
+    other = "philox" if args.dropout == "off" else "off"
+    del agent
+    torch.cuda.empty_cache()
+    a2 = type(args)(**vars(args)); a2.dropout = other
+    env2, agent2 = _make_agent(a2, rank, device, n, 128, 1024)
+    for _ in range(3):
+        agent2.rollout_step(store=False, replay_reset=False)
+    k2 = max(3, args.steps // 4)
+    ms2, _ = timer.run(lambda: agent2.rollout_step(store=False, replay_reset=False), k2)
+    tf2 = _kernel_ms(timer, agent2._emotion_forward, reps=3)
+    other_mode = {"dropout": other, "value": n * world * k2 / (ms2 * 1e-3), "unit": "env-steps/s", "ms_per_step": ms2 / k2, "steps": k2,
+                  "transformer_kernel_ms": tf2,
+                  "note": "philox = train() mode, the mode the reference runs (it never calls .eval() on this path): four dropout layers per "
+                          "encoder layer + two in the actor, keep-masks from Philox-4x32-10 (16 random bits per mask bit, csrc/tf_dropout.cuh); "
+                          "the transformer kernel is then bound by the integer pipe that draws 163,840 mask bits per env and call, not by the tensor pipe"}
+    env, agent = env2, agent2       # (the roofline object below describes the headline mode: its kernel time was taken above)
+    agent.emotion_precision = args.emotion_precision
     return {
         "metric": "env_steps_per_sec", "value": units / (total_ms * 1e-3), "unit": "env-steps/s",
         "dtype": "f64 simulator, %s transformer, f32 actor" % agent.emotion_precision,
+        "other_dropout_mode": other_mode,
         "ms_per_step": total_ms / args.steps, "wall_s_timed_region": wall,
         "config": workload_config("rollout", args, world),
         "timing": dict(TIMING, sim_mode=args.sim_mode, dropout=args.dropout,

@@ -151,10 +151,14 @@ DETAIL_COLUMNS = ["Condition", "Episode", "Reward", "WeightErr", "Time", "SlowWe
 def write_results_csv(path, detail):
     """`df_detail.to_csv(..., index=False, encoding="utf-8-sig")` (experiment_runner.py:595-596)."""
     with open(path, "w", newline="", encoding="utf-8-sig") as f:
-        w = csv.DictWriter(f, fieldnames=DETAIL_COLUMNS)
+        w = csv.DictWriter(f, fieldnames=DETAIL_COLUMNS, lineterminator="\n")
         w.writeheader()
+        # pandas infers one dtype per column: a column whose values are all np.float32 (SlowWeight: the clipped action) stays binary32
+        # and prints with the shortest binary32 repr ('24944.707'); any other numeric column becomes binary64, so a np.float32 reward in
+        # a column that also holds Python floats prints as its exact binary64 value (2985.782470703125, not '2985.7825')
+        f32_cols = {k for k in DETAIL_COLUMNS if detail and all(isinstance(r[k], np.float32) for r in detail)}
         for row in detail:
-            w.writerow(row)
+            w.writerow({k: (v if isinstance(v, (str, int)) else (str(v) if k in f32_cols else float(v))) for k, v in row.items()})
 
 
 def write_summary(path, results):

@@ -875,10 +875,74 @@ def gen_esac():
     print("esac:", out["res"].tolist())
 
 
+def gen_exp3():
+    """Row N4: the reference's OWN evaluation loop and result files.  `experiment_runner.run_experiment_3(train=False, algo='er_ddpg')`
+    (experiment_runner.py:397-611) is run unmodified on a checkpoint written by the reference's own `train_ddpg` + `agent.save`: ten
+    test episodes per condition with `act(state, add_noise=False)`, `analysis_outputs/exp3/test_results_er_ddpg_<cond>.csv` and
+    `logs/exp3_summary.log`.  Two taps only: `DDPGAgent.load` also switches the loaded modules to eval() (the reference leaves dropout
+    on in its test loop, which no second implementation can reproduce draw for draw), and `DDPGAgent.act` records (state, action)."""
+    import shutil
+    import tempfile
+    import torch
+    ref_shim.install()
+    import experiment_runner as ER
+    work = tempfile.mkdtemp(prefix="erlfill_exp3_")
+    os.chdir(work)
+    random.seed(0); np.random.seed(0); torch.manual_seed(0)
+    # a short reference training run, saved with the reference's own save()
+    cfg = BOUNDS["variant_25kg"]
+    with _quiet():
+        env = ER.MultiConditionWeightEnv({**{k: cfg[k] for k in ("target_weight", "target_weight_err", "target_time")},
+                                          "bounds": dict(cfg["bounds"])})
+        agent = ER.DDPGAgent(env, "cpu", use_td_error=True)
+        agent.emotion = ER.EmotionModule("cpu")
+        env.attach_agent(agent)
+        agent.batch_size = 16
+        ER.train_ddpg(env, agent, episodes=2, max_steps=12, log_prefix="exp3_gold")
+        os.makedirs("saved_models/exp3_er_ddpg", exist_ok=True)
+        for key in ("variant_25kg", "variant_20kg", "variant_15kg"):
+            agent.save(f"saved_models/exp3_er_ddpg/{key}_final.pth")
+    ck = torch.load("saved_models/exp3_er_ddpg/variant_25kg_final.pth", map_location="cpu", weights_only=False)
+    out = {}
+    for part in ("actor", "critic", "emotion_transformer"):
+        for k, v in ck[part].items():
+            out[f"ck.{part}.{k}"] = v.numpy()
+    taps = []
+    orig_load, orig_act = ER.DDPGAgent.load, ER.DDPGAgent.act
+
+    def load_eval(self, filename):
+        orig_load(self, filename)
+        for m in (self.actor, self.critic, self.emotion.transformer):
+            m.eval()
+
+    def act_tap(self, state, add_noise=True):
+        a = orig_act(self, state, add_noise)
+        taps.append((np.array(state, np.float32), np.array(a, np.float32)))
+        return a
+    ER.DDPGAgent.load, ER.DDPGAgent.act = load_eval, act_tap
+    try:
+        random.seed(2024); np.random.seed(2024); torch.manual_seed(2024)
+        with _quiet():
+            ER.run_experiment_3(train=False, max_steps=8, device="cpu", algo="er_ddpg")
+    finally:
+        ER.DDPGAgent.load, ER.DDPGAgent.act = orig_load, orig_act
+    out["states"] = np.stack([t[0] for t in taps]); out["actions"] = np.stack([t[1] for t in taps])
+    for key in ("variant_25kg", "variant_20kg", "variant_15kg"):
+        out["csv_" + key] = np.frombuffer(open(f"analysis_outputs/exp3/test_results_er_ddpg_{key}.csv", "rb").read(), np.uint8)
+    out["summary"] = np.frombuffer(open("logs/exp3_summary.log", "rb").read(), np.uint8)
+    out["seed"], out["max_steps"] = 2024, 8
+    out["meta"] = _meta("N4 run_experiment_3(train=False, er_ddpg): test loop, per-condition CSVs, summary log")
+    np.savez_compressed(os.path.join(GOLD, "exp3_golden.npz"), **out)
+    print("exp3:", len(taps), "test steps;", open("logs/exp3_summary.log").read())
+    os.chdir("/tmp")
+    shutil.rmtree(work, ignore_errors=True)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["sim", "env", "emotion"]
     os.chdir("/tmp")
     for w in which:
         {"sim": gen_sim, "env": gen_env, "emotion": gen_emotion, "nets": gen_nets, "learn": gen_learn, "td3sac": gen_td3sac, "loop": gen_loop, "esac": gen_esac,
-         "onboard": gen_onboard, "learn_train": gen_learn_train}[w]()
+         "onboard": gen_onboard, "learn_train": gen_learn_train,
+         "exp3": gen_exp3}[w]()
