@@ -780,7 +780,8 @@ def run_ours(args):
             a2.n_env, a2.steps = n_env, steps
             o = wl[name](a2, rank, world, device, timer)
             o.pop("_issue", None)
-            others.append({k: o[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "e2e", "gpu_launches", "roofline", "config")
+            others.append({k: o[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "e2e", "gpu_launches", "roofline", "config", "timing",
+                                             "dp_check", "sync_steps_per_sec", "issue_roofline")
                            if k in o} | {"steps": steps})
     if rank == 0:
         issue = out.pop("_issue", None)
