@@ -1047,12 +1047,20 @@ __device__ __forceinline__ float adam_elem(float &p, float &m, float &v, float g
     p = p - (lr / bc1) * (mi / denom);
     return p;
 }
-// n_ssq sum-of-squares partials: kRedBlocks from grad_reduce_kernel, mlp::kSumsqBlocks from the peer exchange (REDUCED)
+// n_ssq sum-of-squares partials: kRedBlocks from grad_reduce_kernel, mlp::kSumsqBlocks from the peer exchange (REDUCED).  Warp 0 of the
+// block adds them (lane l takes partials l, l + 32, ..., then a butterfly: the same order in every block and on every rank) and
+// every thread reads the coefficient from shared memory; all threads of the block must call this.
 __device__ __forceinline__ float clip_coef(const float *ssq, int n_ssq, float max_norm) {
-    float ss = 0.f;
-#pragma unroll 8
-    for (int b = 0; b < n_ssq; ++b) ss += ssq[b];
-    return fminf(max_norm / (sqrtf(ss) + 1e-6f), 1.0f);
+    __shared__ float s_coef;
+    if (threadIdx.x < 32) {
+        float ss = 0.f;
+        for (int b = threadIdx.x; b < n_ssq; b += 32) ss += ssq[b];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (threadIdx.x == 0) s_coef = fminf(max_norm / (sqrtf(ss) + 1e-6f), 1.0f);
+    }
+    __syncthreads();
+    return s_coef;
 }
 // CRITIC_APPLY: emotion-driven learning rates (ddpg_agent.py:447-462), clip_grad_norm_(5), Adam, image refresh
 __global__ void critic_apply_kernel(float *p, float *m, float *v, const float *G, const float *ssq, int n_ssq, const float *step, double critic_lr,
@@ -1063,8 +1071,8 @@ __global__ void critic_apply_kernel(float *p, float *m, float *v, const float *G
     const double af = 1.0 + 0.8 * cur - 0.4 * cons + 0.2 * anx, cf = 1.0 - 0.3 * anx + 0.6 * cons;
     const float lr_c = (float)fmin(fmax(critic_lr * cf * decay, critic_lr * 0.1), critic_lr * 3);
     if (i == 0) { scal[2] = lr_c; scal[3] = (float)fmin(fmax(actor_lr * af * decay, actor_lr * 0.1), actor_lr * 3); }
-    if (i >= CO::TOTAL) return;
     const float coef = clip_coef(ssq, n_ssq, max_norm);
+    if (i >= CO::TOTAL) return;
     float pi = p[i], mi = m[i], vi = v[i];
     adam_elem(pi, mi, vi, G[i], coef, lr_c, step[2], step[3]);
     p[i] = pi; m[i] = mi; v[i] = vi;
@@ -1075,8 +1083,8 @@ __global__ void actor_apply_kernel(float *p, float *pt, float *m, float *v, cons
                                    float tau, const float *critic, float *critic_t, float *scal, uint8_t *img_actor, uint8_t *img_actor_t,
                                    uint8_t *img_critic_t, float *report) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float coef = clip_coef(ssq, n_ssq, max_norm);
     if (i < AO::TOTAL) {
-        const float coef = clip_coef(ssq, n_ssq, max_norm);
         float pi = p[i], mi = m[i], vi = v[i];
         adam_elem(pi, mi, vi, G[i], coef, scal[3], step[2], step[3]);
         p[i] = pi; m[i] = mi; v[i] = vi;
