@@ -18,14 +18,16 @@ struct Drop {
 };
 constexpr float kDropScale = 1.25f;
 constexpr uint32_t kDropThresh = 13107u;
-// keep bits of columns [c0, c0 + 32) of global row `grow` at dropout site `site` of width `width` (bit j = column c0 + j)
-__device__ __forceinline__ uint32_t keep32(const Drop &d, int site, int grow_local, int c0, int width) {
-    if (d.mode == ERLFILL_DROPOUT_OFF) return 0xffffffffu;
+// keep bits of the W = 8 / 16 / 32 columns [c0, c0 + W) (c0 % 8 == 0) of global row `grow` at dropout site `site` of width `width`
+// (bit j = column c0 + j)
+template <int W>
+__device__ __forceinline__ uint32_t keep_bits(const Drop &d, int site, int grow_local, int c0, int width) {
+    if (d.mode == ERLFILL_DROPOUT_OFF) return W == 32 ? 0xffffffffu : ((1u << (W & 31)) - 1u);
     uint32_t bits = 0;
     if (d.mode == ERLFILL_DROPOUT_MASK) {
         const uint8_t *p = d.m[site] + (size_t)grow_local * width + c0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < W / 8; ++q) {
             const uint2 w = *reinterpret_cast<const uint2 *>(p + 8 * q);
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
@@ -36,7 +38,7 @@ __device__ __forceinline__ uint32_t keep32(const Drop &d, int site, int grow_loc
         return bits;
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < W / 8; ++q) {
         const uint4 r = philox4x32_10(d.k0, d.k1, d.row_base + (uint32_t)grow_local, d.update_idx, (uint32_t)((c0 >> 3) + q),
                                       STREAM_DROPOUT + 16u + (uint32_t)site);
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
@@ -48,6 +50,7 @@ __device__ __forceinline__ uint32_t keep32(const Drop &d, int site, int grow_loc
     }
     return bits;
 }
+__device__ __forceinline__ uint32_t keep32(const Drop &d, int site, int grow_local, int c0, int width) { return keep_bits<32>(d, site, grow_local, c0, width); }
 
 // one element (the exact path's scattered fragment layout)
 __device__ __forceinline__ bool keep1(const Drop &d, int site, int grow_local, int c, int width) {

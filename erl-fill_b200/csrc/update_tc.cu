@@ -23,12 +23,12 @@ namespace utc {
 
 constexpr int ACT_LEAKY = 0, ACT_RELU = 1;
 
-// ---- per-CTA global scratch (bytes) ----------------------------------------------------------------------------------
+// ---- per-tile global scratch (bytes), shared by the two CTAs of the pair (each writes its own columns) ------------------------
 namespace SC {
 constexpr size_t X0IMG = 0, H1IMG = X0IMG + 12288, H2IMG = H1IMG + 65536, XHAT1 = H2IMG + 65536, XHAT2 = XHAT1 + 131072,
                  RSTD1 = XHAT2 + 131072, RSTD2 = RSTD1 + 512, KEEP = RSTD2 + 512 /* [2][128][8] words */, XAIMG = KEEP + 8192,
-                 A1IMG = XAIMG + 12288, A2IMG = A1IMG + 32768, A3IMG = A2IMG + 32768, ABITS = A3IMG + 16384 /* [128][16] words */,
-                 AUX = ABITS + 8192 /* [128][64] floats */, BYTES = AUX + 32768;
+                 A1IMG = XAIMG + 12288, A2IMG = A1IMG + 32768, A3IMG = A2IMG + 32768, ABITS = A3IMG + 16384 /* [128][32] words */,
+                 AUX = ABITS + 16384 /* [2 CTAs][64][128] floats */, BYTES = AUX + 65536;
 }
 
 struct Args {
@@ -38,14 +38,14 @@ struct Args {
     const float *actor, *actor_t, *critic, *critic_t;            // fp32 master parameters (small vectors are read from these)
     const uint8_t *img_actor, *img_actor_t, *img_critic, *img_critic_t;
     const float *scale, *offset;
-    uint8_t *scratch;                                            // [n_cta][SC::BYTES]
-    float *cpart, *apart;                                        // [n_cta][CP::SIZE], [n_cta][AP::SIZE]
+    uint8_t *scratch;                                            // [tiles][SC::BYTES]
+    float *cpart, *apart;                                        // [tiles][CP::SIZE], [tiles][AP::SIZE]
     float *mean_out;                                             // 3 batch emotion means (tail of the critic gradient bucket)
     float *scal;                                                 // scal[6 .. 15): L2 norms of the nine actor tensors
     Drop drop;
     int prof;
-    // CRITIC_GRAD with the target chain on its own CTAs (grid = 2 x tiles, all co-resident): CTA tiles + t computes Q' of tile t, writes it
-    // to tq_g and raises tq_flag[t]; CTA t consumes it before the loss and lowers the flag again
+    // CRITIC_GRAD with the target chain on its own pairs (grid = 2 x 2 x tiles CTAs, all co-resident): pair tiles + t computes Q' of tile
+    // t, writes it to tq_g and raises tq_flag[2 t + c] for CTA c of pair t, which consumes it before the loss and lowers its flag again
     int split;
     float *tq_g;
     uint32_t *tq_flag;
@@ -67,7 +67,10 @@ __device__ __forceinline__ void setup(uint8_t *smem, uint64_t *bars, uint32_t *t
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bars + BW_FULL + s, 1); mbar_init(bars + BW_EMPTY + s, 1); }
         mbar_init(bars + B_HFULL, 1); mbar_init(bars + B_HFREE, 1); mbar_init(bars + B_DFULL, 1); mbar_init(bars + B_GFULL, 1);
-        mbar_init(bars + B_GFREE, NEPI / 32); mbar_init(bars + B_AREADY, NEPI / 32);
+        mbar_init(bars + B_GFREE, NEPI / 32);
+        mbar_init(bars + B_AREADY, 2 * NEPI / 32);               // the epilogue warps of both CTAs
+        mbar_init(bars + B_AFREE, 2);                            // the issuers of both CTAs
+        mbar_init(bars + B_XRED, 2 * NEPI / 32); mbar_init(bars + B_XRED + 1, 2 * NEPI / 32);
         mbar_fence_init();
     }
     if (warp == W_ISSUER) tmem_alloc(tmem_slot, 512);
@@ -75,6 +78,7 @@ __device__ __forceinline__ void setup(uint8_t *smem, uint64_t *bars, uint32_t *t
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                                          // the peer's barriers exist before anything arrives on them
     tc_fence_after();
 }
 
@@ -114,14 +118,15 @@ __device__ __forceinline__ void emotion_stats(Epi &e, const float *batch, float 
     bar_epi();
 }
 
-// The same statistics with the work shared by the CTAs of the grid (all co-resident: the split launch of CRITIC_GRAD): every CTA sums
-// (e - 0.5) and (e - 0.5)^2 over ITS 128 rows, publishes the six sums, and — once all tiles have arrived — adds the tiles' sums in tile
-// order (the same numbers on every CTA).  ctr[0] counts arrivals, ctr[1] departures; the last CTA to leave zeroes both for the next launch.
+// The same statistics with the work shared by the tiles of the grid (all co-resident: the split launch of CRITIC_GRAD): CTA 0 of every
+// pair sums (e - 0.5) and (e - 0.5)^2 over the tile's 128 rows and publishes the six sums; once all tiles have arrived, BOTH CTAs add
+// the tiles' sums in tile order (the same numbers everywhere).  ctr[0] counts arrivals (one per tile), ctr[1] departures (two per
+// tile); the last CTA to leave zeroes both for the next launch.
 __device__ __forceinline__ void grid_emotion_stats(Epi &e, const float *batch, float *part_g, uint32_t *ctr, int n_tiles, int tile, float *stats_out,
                                                    float *mean_out) {
     float *st = e.stat();
     float *scr = st + 16;                                        // [4 warps][6]
-    if (e.wg == 0) {
+    if (e.cr == 0 && e.wg == 0) {
         float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (e.valid()) {
             const float4 q = __ldg(reinterpret_cast<const float4 *>(batch + (size_t)(e.row0 + e.r) * ERLFILL_REC + 16));
@@ -133,10 +138,12 @@ __device__ __forceinline__ void grid_emotion_stats(Epi &e, const float *batch, f
     }
     bar_epi();
     if (e.tid == 0) {
+        if (e.cr == 0) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) part_g[tile * 8 + c] = (scr[c] + scr[6 + c]) + (scr[12 + c] + scr[18 + c]);
-        __threadfence();
-        atomicAdd(ctr, 1u);
+            for (int c = 0; c < 6; ++c) part_g[tile * 8 + c] = (scr[c] + scr[6 + c]) + (scr[12 + c] + scr[18 + c]);
+            __threadfence();
+            atomicAdd(ctr, 1u);
+        }
         const long long t0 = clock64();
         bool ok = true;
         while (*reinterpret_cast<volatile uint32_t *>(ctr) < (uint32_t)n_tiles) {
@@ -154,17 +161,18 @@ __device__ __forceinline__ void grid_emotion_stats(Epi &e, const float *batch, f
             st[c] = ok ? 0.5f + m : __int_as_float(0x7fc00000);
             st[3 + c] = sqrtf(fmaxf(sum[3 + c] - sum[c] * m, 0.f) / (n - 1.0f));
         }
-        if (tile == 0) {
+        if (tile == 0 && e.cr == 0) {
 #pragma unroll
             for (int c = 0; c < 6; ++c) stats_out[c] = st[c];
             mean_out[0] = st[0]; mean_out[1] = st[1]; mean_out[2] = st[2];
         }
-        if (atomicAdd(ctr + 1, 1u) == (uint32_t)n_tiles - 1u) { ctr[0] = 0u; ctr[1] = 0u; __threadfence(); }
+        if (atomicAdd(ctr + 1, 1u) == 2u * (uint32_t)n_tiles - 1u) { ctr[0] = 0u; ctr[1] = 0u; __threadfence(); }
     }
     bar_epi();
 }
 
-// x[16] -> the K = 48 first-layer operand [x_hi | x_lo | x_hi] of this thread's row (image of 48 features), optionally copied to global
+// x[16] -> the K = 48 first-layer operand [x_hi | x_lo | x_hi] of this thread's row (image of 48 features) in THIS CTA's IMG_A (both
+// CTAs of the pair build the narrow input images themselves), optionally copied to global
 __device__ __forceinline__ void store_split_input(const Epi &e, const float (&x)[16], uint8_t *gimg) {
     float hi[16], lo[16];
 #pragma unroll
@@ -205,97 +213,103 @@ __device__ __forceinline__ void actor_head(const float (&z16)[16], const float *
     }
 }
 
-// Hidden layer with N = 128 outputs (32 columns per thread): z = D (+ bias) -> activation -> dropout -> image of 128 features.
-// pos_out / keep_out: bit j = (z > 0) / kept, of column wg * 32 + j.
+// Hidden layer with N = 128 outputs (this CTA's 64: 16 columns per thread): z = D (+ bias) -> activation -> dropout -> image of 128
+// features in both CTAs.  pos_out / keep_out: bit j = (z > 0) / kept, of feature cr * 64 + wg * 16 + j.
 __device__ __forceinline__ void epi_hidden128(Epi &e, const float *bias, int act, const Drop &dr, int site, uint8_t *gimg, uint32_t *pos_out,
                                               uint32_t *keep_out) {
-    float v[32];
-    const int c0 = e.wg * 32;
-    tmem_ld32w(e.td(c0), v);
-    const uint32_t keep = keep32(dr, site, e.mrow(), c0, 128);
+    float v[16];
+    const int cl = e.wg * 16, c0 = e.cr * 64 + cl;
+    tmem_ld16w(e.td(cl), v);
+    const uint32_t keep = ddrop::keep_bits<16>(dr, site, e.mrow(), c0, 128);
     uint32_t pos = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < 16; ++j) {
         float z = v[j] + (bias ? __ldg(bias + c0 + j) : 0.f);
         pos |= (z > 0.f ? 1u : 0u) << j;
         z = act == ACT_LEAKY ? (z > 0.f ? z : 0.1f * z) : fmaxf(z, 0.f);
         v[j] = ((keep >> j) & 1u) ? z * (dr.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale) : 0.f;
     }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        e.img_store8(e.img_a(), 128, c0 + g * 8, v + g * 8);
-        if (gimg) e.img_store8(gimg, 128, c0 + g * 8, v + g * 8);
-    }
+    e.wait_afree();
+    e.img_store8_pair(128, c0, v, gimg);
+    e.img_store8_pair(128, c0 + 8, v + 8, gimg);
     if (pos_out) *pos_out = pos;
     if (keep_out) *keep_out = keep;
 }
 
-// LayerNorm(256) + activation + dropout of the critic (64 columns per thread) -> image of 256 features.  Two passes over the
-// accumulators (statistics, then normalise) keep the register footprint at one 32-column chunk.
+// Linear(128, 64) -> ReLU (this CTA's 32 columns: 8 per thread) -> image of 64 features in both CTAs; returns the relu' bits
+__device__ __forceinline__ uint32_t epi_hidden64(Epi &e, const float *bias, uint8_t *gimg) {
+    float v[8];
+    const int cl = e.wg * 8, c0 = e.cr * 32 + cl;
+    tmem_ld8w(e.td(cl), v);
+    uint32_t pos = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        v[j] = fmaxf(v[j] + __ldg(bias + c0 + j), 0.f);
+        pos |= (v[j] > 0.f ? 1u : 0u) << j;
+    }
+    e.wait_afree();
+    e.img_store8_pair(64, c0, v, gimg);
+    return pos;
+}
+
+// LayerNorm(256) + activation + dropout of the critic (this CTA's 128 columns: 32 per thread, held in registers across the exchange
+// of the row statistics) -> image of 256 features in both CTAs.
 // save: xhat (fp32, [64 float4 columns][128 rows]: a warp's 32 rows are 512 contiguous bytes), rstd [128], keep words [128][8], image
 // copy — what the backward and the weight gradients read.
 __device__ __forceinline__ void epi_ln256(Epi &e, const float *bias, const float *gamma, const float *beta, int act, const Drop &dr, int site,
                                           float *xhat_g, float *rstd_g, uint32_t *keep_g, uint8_t *gimg) {
-    const int c0 = e.wg * 64;
-    // pass 1: shifted sums of this thread's 64 columns -> (mean_w, M2_w); the four quarter statistics combine exactly (Chan et al.)
-    float k = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-        float v[32];
-        tmem_ld32w(e.td(c0 + 32 * h), v);
-        if (bias) {
+    const int cl = e.wg * 32, c0 = e.cr * 128 + cl;
+    float v[32];
+    tmem_ld32w(e.td(cl), v);
+    if (bias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(bias + c0 + 32 * h + j);
-        }
-        if (h == 0) k = v[0];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = v[j] - k; s1 += d; s2 = fmaf(d, d, s2); }
+        for (int j = 0; j < 32; ++j) v[j] += __ldg(bias + c0 + j);
     }
-    const float mean_w = k + s1 * (1.0f / 64.0f);
-    float a1 = mean_w, a2 = (s2 - s1 * s1 * (1.0f / 64.0f)) + 64.0f * mean_w * mean_w;       // M2_w + 64 mean_w^2
+    // shifted sums of this thread's 32 columns -> (mean_w, M2_w); the eight statistics of the row combine exactly (Chan et al.)
+    const float k = v[0];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float d = v[j] - k; s1 += d; s2 = fmaf(d, d, s2); }
+    const float mean_w = k + s1 * (1.0f / 32.0f);
+    float a1 = mean_w, a2 = (s2 - s1 * s1 * (1.0f / 32.0f)) + 32.0f * mean_w * mean_w;       // M2_w + 32 mean_w^2
     e.row_allreduce2(a1, a2);
-    const float mean = a1 * 0.25f;
+    const float mean = a1 * 0.125f;
     const float var = fmaxf(a2 - 256.0f * mean * mean, 0.f) * (1.0f / 256.0f);
     const float rstd = rsqrtf(var + 1e-5f);
     const float ds = dr.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale;
-    // pass 2
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-        float v[32];
-        tmem_ld32w(e.td(c0 + 32 * h), v);
-        const uint32_t kb = keep32(dr, site, e.mrow(), c0 + 32 * h, 256);
-        if (keep_g) keep_g[e.r * 8 + e.wg * 2 + h] = kb;
+    const uint32_t kb = keep32(dr, site, e.mrow(), c0, 256);
+    if (keep_g) keep_g[e.r * 8 + (c0 >> 5)] = kb;
+    e.wait_afree();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            float hh[8];
+    for (int g = 0; g < 4; ++g) {
+        float hh[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int j = g * 8 + i, c = c0 + 32 * h + j;
-                const float xh = (v[j] + (bias ? __ldg(bias + c) : 0.f) - mean) * rstd;
-                v[j] = xh;
-                float y = xh * __ldg(gamma + c) + __ldg(beta + c);
-                y = act == ACT_LEAKY ? (y > 0.f ? y : 0.1f * y) : fmaxf(y, 0.f);
-                hh[i] = ((kb >> j) & 1u) ? y * ds : 0.f;
-            }
-            e.img_store8(e.img_a(), 256, c0 + 32 * h + g * 8, hh);
-            if (gimg) e.img_store8(gimg, 256, c0 + 32 * h + g * 8, hh);
+        for (int i = 0; i < 8; ++i) {
+            const int j = g * 8 + i, c = c0 + j;
+            const float xh = (v[j] - mean) * rstd;
+            v[j] = xh;
+            float y = xh * __ldg(gamma + c) + __ldg(beta + c);
+            y = act == ACT_LEAKY ? (y > 0.f ? y : 0.1f * y) : fmaxf(y, 0.f);
+            hh[i] = ((kb >> j) & 1u) ? y * ds : 0.f;
         }
-        if (xhat_g) {
-            float4 *dst = reinterpret_cast<float4 *>(xhat_g) + (size_t)((c0 + 32 * h) >> 2) * TR + e.r;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[(size_t)j * TR] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
+        e.img_store8_pair(256, c0 + g * 8, hh, gimg);
     }
-    if (xhat_g && e.wg == 0) rstd_g[e.r] = rstd;
+    if (xhat_g) {
+        float4 *dst = reinterpret_cast<float4 *>(xhat_g) + (size_t)(c0 >> 2) * TR + e.r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[(size_t)j * TR] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (e.wg == 0 && e.cr == 0) rstd_g[e.r] = rstd;
+    }
 }
 
-// critic layer 8 (N = 128, 32 columns per thread): h3 = relu(D + b8), q = clamp(h3 . w10 + b10): every thread of the row gets q
-__device__ __forceinline__ float epi_head(Epi &e, const float *P, float (&h3)[32]) {
-    const int c0 = e.wg * 32;
-    tmem_ld32w(e.td(c0), h3);
+// critic layer 8 (N = 128, this CTA's 64: 16 columns per thread): h3 = relu(D + b8), q = clamp(h3 . w10 + b10): every thread of the
+// row, in both CTAs, gets q
+__device__ __forceinline__ float epi_head(Epi &e, const float *P, float (&h3)[16]) {
+    const int cl = e.wg * 16, c0 = e.cr * 64 + cl;
+    tmem_ld16w(e.td(cl), h3);
     float part = 0.f, dummy = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < 16; ++j) {
         h3[j] = fmaxf(h3[j] + __ldg(P + CO::B8 + c0 + j), 0.f);
         part = fmaf(h3[j], __ldg(P + CO::W10 + c0 + j), part);
     }
@@ -303,36 +317,30 @@ __device__ __forceinline__ float epi_head(Epi &e, const float *P, float (&h3)[32
     return fminf(fmaxf(part + __ldg(P + CO::B10), -1e6f), 1e6f);
 }
 
-// dz3 (this thread's 32 columns) -> image of 128 features
-__device__ __forceinline__ void store_img128(const Epi &e, const float (&v)[32]) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) e.img_store8(e.img_a(), 128, e.wg * 32 + g * 8, v + g * 8);
-}
-
-// Backward of (LayerNorm(256) + activation + dropout): D holds dh (gradient of the dropped activation); writes dz (gradient of
-// the LayerNorm input) as the image of 256 features.  part != nullptr: per-CTA column sums [sum dz | sum dy xhat | sum dy].
+// Backward of (LayerNorm(256) + activation + dropout): D holds dh (gradient of the dropped activation) of this CTA's 128 columns;
+// writes dz (gradient of the LayerNorm input) into the image of 256 features of both CTAs.  part != nullptr: per-tile column sums
+// [sum dz | sum dy xhat | sum dy] of this CTA's columns.
 __device__ __forceinline__ void epi_ln256_bwd(Epi &e, const float *gamma, const float *beta, int act, const Drop &dr, const float *xhat_g,
                                               const float *rstd_g, const uint32_t *keep_g, float *part) {
-    const int c0 = e.wg * 64;
+    const int cl = e.wg * 32, c0 = e.cr * 128 + cl;
     const float ds = dr.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale;
-    const uint32_t kw[2] = {keep_g[e.r * 8 + e.wg * 2], keep_g[e.r * 8 + e.wg * 2 + 1]};
+    const uint32_t kw = keep_g[e.r * 8 + (c0 >> 5)];
     const float rstd = rstd_g[e.r];
+    const float4 *xp = reinterpret_cast<const float4 *>(xhat_g) + (size_t)(c0 >> 2) * TR + e.r;
     float s1 = 0.f, s2 = 0.f;
     // pass 1: dy = dh * keep/0.8 * act'(y); row sums of dy*gamma and dy*gamma*xhat; column sums of dy*xhat and dy
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
+    {
         float dh[32], a[32], b[32];
-        tmem_ld32w(e.td(c0 + 32 * h), dh);
-        const float4 *xp = reinterpret_cast<const float4 *>(xhat_g) + (size_t)((c0 + 32 * h) >> 2) * TR + e.r;
+        tmem_ld32w(e.td(cl), dh);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
             const float4 x4 = xp[(size_t)j4 * TR];
             const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int j = j4 * 4 + i, c = c0 + 32 * h + j;
+                const int j = j4 * 4 + i, c = c0 + j;
                 const float gm = __ldg(gamma + c), y = xs[i] * gm + __ldg(beta + c);
-                float g = ((kw[h] >> j) & 1u) ? dh[j] * ds : 0.f;
+                float g = ((kw >> j) & 1u) ? dh[j] * ds : 0.f;
                 g *= act == ACT_LEAKY ? (y > 0.f ? 1.f : 0.1f) : (y > 0.f ? 1.f : 0.f);
                 const float dxh = g * gm;
                 s1 += dxh;
@@ -341,61 +349,68 @@ __device__ __forceinline__ void epi_ln256_bwd(Epi &e, const float *gamma, const 
                 b[j] = g;
             }
         }
-        if (part) { e.colsum_stage(1, c0 + 32 * h, a); e.colsum_stage(2, c0 + 32 * h, b); }
+        if (part) { e.colsum_stage<32>(1, cl, a); e.colsum_stage<32>(2, cl, b); }
     }
     e.row_allreduce2(s1, s2);
     s1 *= (1.0f / 256.0f); s2 *= (1.0f / 256.0f);
     // pass 2: dz = rstd * (dy*gamma - s1 - xhat*s2)
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
+    {
         float dh[32], dz[32];
-        tmem_ld32w(e.td(c0 + 32 * h), dh);
-        const float4 *xp = reinterpret_cast<const float4 *>(xhat_g) + (size_t)((c0 + 32 * h) >> 2) * TR + e.r;
+        tmem_ld32w(e.td(cl), dh);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
             const float4 x4 = xp[(size_t)j4 * TR];
             const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int j = j4 * 4 + i, c = c0 + 32 * h + j;
+                const int j = j4 * 4 + i, c = c0 + j;
                 const float gm = __ldg(gamma + c), y = xs[i] * gm + __ldg(beta + c);
-                float g = ((kw[h] >> j) & 1u) ? dh[j] * ds : 0.f;
+                float g = ((kw >> j) & 1u) ? dh[j] * ds : 0.f;
                 g *= act == ACT_LEAKY ? (y > 0.f ? 1.f : 0.1f) : (y > 0.f ? 1.f : 0.f);
                 dz[j] = rstd * (g * gm - s1 - xs[i] * s2);
             }
         }
+        e.wait_afree();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) e.img_store8(e.img_a(), 256, c0 + 32 * h + g * 8, dz + g * 8);
-        if (part) e.colsum_stage(0, c0 + 32 * h, dz);
+        for (int g = 0; g < 4; ++g) e.img_store8_pair(256, c0 + g * 8, dz + g * 8);
+        if (part) e.colsum_stage<32>(0, cl, dz);
     }
     if (part) {
         bar_epi();
-        e.colsum_finish(0, 256, part);
-        e.colsum_finish(1, 256, part + 256);
-        e.colsum_finish(2, 256, part + 512);
+        e.colsum_finish(0, 128, part + e.cr * 128);
+        e.colsum_finish(1, 128, part + 256 + e.cr * 128);
+        e.colsum_finish(2, 128, part + 512 + e.cr * 128);
         bar_epi();
     }
 }
 
-// Drain of one weight-gradient block: TMEM lane r = output feature m0 + r, `n` accumulator columns.  The block is stored as
-// [n / 4 float4 columns][128 rows][4] so that the 32 rows of a warp write 512 contiguous bytes (grad_reduce_kernel walks the same order).
-__device__ __forceinline__ void drain_g(Epi &e, float *dst, int n) {
+// Drain of one weight-gradient block: TMEM lane r = output feature m0 + r, this CTA's `n` accumulator columns = the columns
+// [col0, col0 + n) of the block.  The block is stored as [columns / 4][128 rows][4] so that the 32 rows of a warp write 512 contiguous
+// bytes (grad_reduce_kernel walks the same order).  dst == nullptr: the accumulators are only released (a block both CTAs computed).
+__device__ __forceinline__ void drain_g(Epi &e, float *dst, int n, int col0) {
     e.wait_g();
-    float4 *d4 = reinterpret_cast<float4 *>(dst);
-    if (n >= 128) {
+    float4 *d4 = reinterpret_cast<float4 *>(dst) + (size_t)(col0 >> 2) * TR + e.r;
+    if (dst == nullptr) {
+    } else if (n >= 128) {
         const int cpw = n / NWG;
         for (int c = 0; c < cpw; c += 32) {
             float v[32];
             tmem_ld32w(e.tg(e.wg * cpw + c), v);
-            float4 *o = d4 + (size_t)((e.wg * cpw + c) >> 2) * TR + e.r;
+            float4 *o = d4 + (size_t)((e.wg * cpw + c) >> 2) * TR;
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[(size_t)j * TR] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+    } else if (n == 32) {                   // 8 columns per warpgroup
+        float v[8];
+        tmem_ld8w(e.tg(e.wg * 8), v);
+        float4 *o = d4 + (size_t)(e.wg * 2) * TR;
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[TR] = make_float4(v[4], v[5], v[6], v[7]);
     } else if (n == 64 || e.wg == 0) {      // n = 64 (16 columns per warpgroup) or n = 16 (warpgroup 0 only)
         float v[16];
         const int c = n == 64 ? e.wg * 16 : 0;
         tmem_ld16w(e.tg(c), v);
-        float4 *o = d4 + (size_t)(c >> 2) * TR + e.r;
+        float4 *o = d4 + (size_t)(c >> 2) * TR;
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[(size_t)j * TR] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
@@ -408,27 +423,36 @@ __device__ __forceinline__ void drain_g(Epi &e, float *dst, int n) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_TMEM);                                         \
     const int tid = threadIdx.x;                                                                                \
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);                                                     \
+    const uint32_t cr = cluster_ctarank();                                                                      \
+    const int pair = (int)blockIdx.x >> 1;                                                                      \
     setup(smem, bars, tmem_slot, tid, warp);                                                                    \
-    const uint32_t tbase = *tmem_slot;                                                                          \
-    const uint8_t *scr_c = a.scratch + (size_t)blockIdx.x * SC::BYTES;                                         \
-    uint8_t *scr = const_cast<uint8_t *>(scr_c);
+    const uint32_t tbase = *tmem_slot;
+
+// the last image's a_free has arrived from both issuers (nothing of the peer is still in flight towards this CTA), then both CTAs leave together
+#define UTC_EPI_DONE mbar_wait_cluster(bars + B_AFREE, (e.img_n - 1) & 1u);
 
 #define UTC_ROLE_EPILOGUE                                                                                      \
     tc_fence_before();                                                                                          \
     __syncthreads();                                                                                            \
+    cluster_sync_all();                                                                                         \
     if (warp == W_ISSUER) tmem_dealloc(tbase, 512);
+
+#define UTC_MAKE_EPI                                                                                                                       \
+    Epi e{smem, bars, tbase, tid, tid >> 7, tid & 127, tid & 31, (tid >> 5) & 3, (uint32_t)(((tid >> 5) & 3) * 32) << 16, (int)cr,            \
+          mapa_u32(smem_u32(smem), cr ^ 1u)};
 
 // =====================================================================================================================
 // CRITIC_GRAD
 // =====================================================================================================================
-// part: 0 = the whole phase in one CTA, 1 = target chain only, 2 = everything but the target chain
+// part: 0 = the whole phase in one pair, 1 = target chain only, 2 = everything but the target chain
 template <int ROLE>
 __device__ __forceinline__ void critic_program(Pipe &p, const Args &a, const uint8_t *scr, int part) {
+    const int cr = (int)p.cr;
     if (part != 2) {    // target chain: actor_target, critic_target
         gemm_fwd<ROLE>(p, a.img_actor_t + AI::W1, 128, 48);
         gemm_fwd<ROLE>(p, a.img_actor_t + AI::W2, 128, 128);
         gemm_fwd<ROLE>(p, a.img_actor_t + AI::W3, 64, 128);
-        gemm_fwd<ROLE>(p, a.img_actor_t + AI::W4, 16, 64);
+        gemm_fwd<ROLE>(p, a.img_actor_t + AI::W4, 16, 64, false);
         gemm_fwd<ROLE>(p, a.img_critic_t + CI::W0, 256, 48);
         gemm_fwd<ROLE>(p, a.img_critic_t + CI::W4, 256, 256);
         gemm_fwd<ROLE>(p, a.img_critic_t + CI::W8, 128, 256);
@@ -438,35 +462,33 @@ __device__ __forceinline__ void critic_program(Pipe &p, const Args &a, const uin
     gemm_fwd<ROLE>(p, a.img_critic + CI::W0, 256, 48);
     gemm_fwd<ROLE>(p, a.img_critic + CI::W4, 256, 256);
     gemm_fwd<ROLE>(p, a.img_critic + CI::W8, 128, 256);
-    // backward: dh2 = dz3 W8, dW8 = dz3^T h2
+    // backward: dh2 = dz3 W8 (this CTA's 128 inputs), dW8 = dz3^T h2 (this CTA's 128 input columns)
     load_h<ROLE>(p, scr + SC::H2IMG, 65536);
-    gemm_bwd<ROLE>(p, a.img_critic + CI::W8, 128, 256, 256);
-    wgrad<ROLE>(p, 128, 0, 256, 256, true, false, true);
-    // dh1 = dz2 W4, dW4 = dz2^T h1
+    gemm_bwd<ROLE>(p, a.img_critic + CI::W8, 128, 256, 256, true, false);
+    wgrad<ROLE>(p, 128, 0, 256, cr * 128, 128, true, false, true, true);
+    // dh1 = dz2 W4, dW4 = dz2^T h1 (this CTA's block of 128 output rows)
     load_h<ROLE>(p, scr + SC::H1IMG, 65536);
-    gemm_bwd<ROLE>(p, a.img_critic + CI::W4, 256, 256, 256);
-    wgrad<ROLE>(p, 256, 0, 256, 256, true, false, false);
-    wgrad<ROLE>(p, 256, 128, 256, 256, false, false, true);
-    // dW0 = dz1^T x0
+    gemm_bwd<ROLE>(p, a.img_critic + CI::W4, 256, 256, 256, true, false);
+    wgrad<ROLE>(p, 256, cr * 128, 256, 0, 256, true, false, true, true);
+    // dW0 = dz1^T x0 (this CTA's block of 128 output rows)
     load_h<ROLE>(p, scr + SC::X0IMG, 12288);
-    wgrad<ROLE>(p, 256, 0, 48, 16, true, true, false);
-    wgrad<ROLE>(p, 256, 128, 48, 16, false, false, true);
+    wgrad<ROLE>(p, 256, cr * 128, 48, 0, 16, true, true, true, true);
 }
 
 __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
     UTC_ROLE_PROLOGUE
     const int n_tiles = (a.B + TR - 1) / TR;
-    const int tile = a.split ? (int)blockIdx.x % n_tiles : (int)blockIdx.x;
-    const int chain = a.split ? ((int)blockIdx.x >= n_tiles ? 1 : 2) : 0;
-    scr = a.scratch + (size_t)tile * SC::BYTES;
+    const int tile = a.split ? pair % n_tiles : pair;
+    const int chain = a.split ? (pair >= n_tiles ? 1 : 2) : 0;
+    uint8_t *scr = a.scratch + (size_t)tile * SC::BYTES;
     if (warp == W_PRODUCER) {
-        if (elect_one()) { Pipe p{smem, bars, tbase}; critic_program<ROLE_PRODUCER>(p, a, scr, chain); }
+        if (elect_one()) { Pipe p{smem, bars, tbase, cr}; critic_program<ROLE_PRODUCER>(p, a, scr, chain); }
         __syncwarp();
     } else if (warp == W_ISSUER) {
-        if (elect_one()) { Pipe p{smem, bars, tbase}; critic_program<ROLE_ISSUER>(p, a, scr, chain); }
+        if (elect_one()) { Pipe p{smem, bars, tbase, cr}; critic_program<ROLE_ISSUER>(p, a, scr, chain); }
         __syncwarp();
     } else {
-        Epi e{smem, bars, tbase, tid, tid >> 7, tid & 127, tid & 31, (tid >> 5) & 3, (uint32_t)(((tid >> 5) & 3) * 32) << 16};
+        UTC_MAKE_EPI
         e.row0 = tile * TR; e.B = a.B;
         const int grow = e.row0 + e.r;
         const bool valid = e.valid();
@@ -489,11 +511,11 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
                 st_[3 + e.tid] = sqrtf(fmaxf(st_[19 + e.tid] - st_[16 + e.tid] * m, 0.f) / (n - 1.0f));
             }
             bar_epi();
-            if (tile == 0 && e.tid < 6) { a.stats_g[e.tid] = e.stat()[e.tid]; if (e.tid < 3) a.mean_out[e.tid] = e.stat()[e.tid]; }
+            if (tile == 0 && cr == 0 && e.tid < 6) { a.stats_g[e.tid] = e.stat()[e.tid]; if (e.tid < 3) a.mean_out[e.tid] = e.stat()[e.tid]; }
         } else if (chain == 2) grid_emotion_stats(e, a.batch, a.stats_part, a.stats_ctr, n_tiles, tile, a.stats_g, a.mean_out);
         else if (chain == 0) {
-            emotion_stats(e, a.batch, tile == 0 ? a.mean_out : nullptr);
-            if (tile == 0 && e.tid < 6) a.stats_g[e.tid] = e.stat()[e.tid];
+            emotion_stats(e, a.batch, tile == 0 && cr == 0 ? a.mean_out : nullptr);
+            if (tile == 0 && cr == 0 && e.tid < 6) a.stats_g[e.tid] = e.stat()[e.tid];
         }
         UPROF(0, 1);
         const float *st = e.stat();
@@ -503,6 +525,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
         const float ne0 = __ldg(a.next_emotion), ne1 = __ldg(a.next_emotion + 1), ne2 = __ldg(a.next_emotion + 2);
         float tq = 0.f;
         if (chain != 2) {
+        e.wait_afree();
         if (e.wg == 0) {
             float x[16];
 #pragma unroll
@@ -516,18 +539,12 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
         e.wait_d(); UPROF(0, 3); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 0, nullptr, nullptr, nullptr); e.a_ready(); UPROF(0, 4);
         e.wait_d(); UPROF(0, 5); epi_hidden128(e, a.actor_t + AO::B2, ACT_RELU, a.drop, 1, nullptr, nullptr, nullptr); e.a_ready(); UPROF(0, 6);
         e.wait_d(); UPROF(0, 7);
-        {   // Linear(128, 64) -> ReLU: 16 columns per thread
-            float v[16];
-            tmem_ld16w(e.td(e.wg * 16), v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + __ldg(a.actor_t + AO::B3 + e.wg * 16 + j), 0.f);
-            e.img_store8(e.img_a(), 64, e.wg * 16, v);
-            e.img_store8(e.img_a(), 64, e.wg * 16 + 8, v + 8);
-        }
+        epi_hidden64(e, a.actor_t + AO::B3, nullptr);
         e.a_ready();
         UPROF(0, 8);
         e.wait_d();
         UPROF(0, 9);
+        e.wait_afree();
         if (e.wg == 0) {
             float z[16], out[10], x[16];
             tmem_ld16w(e.td(0), z);
@@ -548,16 +565,17 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
         e.wait_d(); UPROF(0, 13); epi_ln256(e, a.critic_t + CO::B4, a.critic_t + CO::G2, a.critic_t + CO::BE2, ACT_RELU, a.drop, 3, nullptr, nullptr, nullptr, nullptr); e.a_ready(); UPROF(0, 14);
         e.wait_d();
         UPROF(0, 15);
-        { float h3[32]; tq = epi_head(e, a.critic_t, h3); }
+        { float h3[16]; tq = epi_head(e, a.critic_t, h3); }
         UPROF(0, 16);
         }
-        if (chain == 1) {        // hand Q' of this tile to the CTA that runs the rest of the phase
-            if (e.wg == 0 && valid) a.tq_g[grow] = tq;
+        if (chain == 1) {        // hand Q' of this tile to the pair that runs the rest of the phase
+            if (cr == 0 && e.wg == 0 && valid) a.tq_g[grow] = tq;
             __threadfence();
             bar_epi();
-            if (e.tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.tq_flag + tile), "r"(1u) : "memory");
+            if (cr == 0 && e.tid < 2) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.tq_flag + 2 * tile + e.tid), "r"(1u) : "memory");
         } else {
         // ---- Q(s, a_norm, e) ----
+        e.wait_afree();
         if (e.wg == 0) {
             float x[16];
 #pragma unroll
@@ -569,7 +587,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
                 for (int c = 0; c < 3; ++c) x[12 + c] = (__ldg(row + 16 + c) - st[c]) / (st[3 + c] + 1e-6f);
             }
             x[15] = 1.0f;
-            store_split_input(e, x, scr + SC::X0IMG);
+            store_split_input(e, x, cr == 0 ? scr + SC::X0IMG : nullptr);
         }
         e.a_ready();
         UPROF(0, 17);
@@ -577,13 +595,14 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
         UPROF(0, 18);
         epi_ln256(e, nullptr, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, 4, reinterpret_cast<float *>(scr + SC::XHAT1),
                   reinterpret_cast<float *>(scr + SC::RSTD1), reinterpret_cast<uint32_t *>(scr + SC::KEEP), scr + SC::H1IMG);
+        __threadfence();                                        // the saved images are read back through the async proxy (bulk copies), by both CTAs
         e.a_ready();
         UPROF(0, 19);
         e.wait_d();
         UPROF(0, 20);
         epi_ln256(e, a.critic + CO::B4, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, 5, reinterpret_cast<float *>(scr + SC::XHAT2),
                   reinterpret_cast<float *>(scr + SC::RSTD2), reinterpret_cast<uint32_t *>(scr + SC::KEEP) + 1024, scr + SC::H2IMG);
-        __threadfence();                                        // the saved images are read back through the async proxy (bulk copies)
+        __threadfence();
         e.a_ready();
         UPROF(0, 21);
         if (chain == 2) {
@@ -591,7 +610,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
                 uint32_t f;
                 const long long t0 = clock64();
                 do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.tq_flag + tile) : "memory");
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.tq_flag + 2 * tile + cr) : "memory");
                     if (clock64() - t0 > 4000000000LL) { e.stat()[8] = __int_as_float(0x7fc00000); break; }     // never a hang: poison instead
                 } while (f == 0u);
                 if (f != 0u) e.stat()[8] = 0.f;
@@ -599,12 +618,12 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
             bar_epi();
             tq = valid ? __ldcg(a.tq_g + grow) + e.stat()[8] : 0.f;
             bar_epi();
-            if (e.tid == 0) a.tq_flag[tile] = 0u;
+            if (e.tid == 0) a.tq_flag[2 * tile + cr] = 0u;
         }
         e.wait_d();
         UPROF(0, 22);
         {
-            float h3[32], dz3[32], gw[32];
+            float h3[16], dz3[16], gw[16];
             const float q = epi_head(e, a.critic, h3);
             // SmoothL1 (beta = 1, mean) against y = 0.01 r + (1 - d) gamma Q'   (ddpg_agent.py:445, 470-473)
             float g = 0.f, l = 0.f;
@@ -616,24 +635,26 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
                 if (fabsf(q) >= 1e6f) g = 0.f;                  // the clamp blocks the gradient outside (-1e6, 1e6)
                 g /= (float)a.B;
             }
-            const int c0 = e.wg * 32;
+            const int cl = e.wg * 16, c0 = (int)cr * 64 + cl;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 dz3[j] = h3[j] > 0.f ? g * __ldg(a.critic + CO::W10 + c0 + j) : 0.f;
                 gw[j] = g * h3[j];
             }
-            store_img128(e, dz3);
+            e.wait_afree();
+            e.img_store8_pair(128, c0, dz3);
+            e.img_store8_pair(128, c0 + 8, dz3 + 8);
             e.a_ready();
-            e.colsum_stage(0, c0, dz3);                         // db8
-            e.colsum_stage(1, c0, gw);                          // dW10
-            if (e.wg == 0) {                                    // db10 = sum g, loss = sum l over the CTA's rows
+            e.colsum_stage<16>(0, cl, dz3);                     // db8
+            e.colsum_stage<16>(1, cl, gw);                      // dW10
+            if (e.wg == 0) {                                    // db10 = sum g, loss = sum l over the tile's rows
                 const float sg = warp_sum(g), sl = warp_sum(l);
                 if (e.lane == 0) { e.cs()[(2 * 4 + e.wq) * 256] = sg; e.cs()[(2 * 4 + e.wq) * 256 + 1] = sl; }
             }
             bar_epi();
-            e.colsum_finish(0, 128, part + CP::VC);
-            e.colsum_finish(1, 128, part + CP::VC + 128);
-            if (e.tid == 0) {
+            e.colsum_finish(0, 64, part + CP::VC + cr * 64);
+            e.colsum_finish(1, 64, part + CP::VC + 128 + cr * 64);
+            if (e.tid == 0 && cr == 0) {
                 const float *c = e.cs() + 2 * 4 * 256;
                 part[CP::VC + 256] = (c[0] + c[256]) + (c[512] + c[768]);
                 part[CP::LOSS] = (c[1] + c[257]) + (c[513] + c[769]);
@@ -642,7 +663,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
         }
         // ---- backward ----
         UPROF(0, 23);
-        drain_g(e, part + CP::W8, 256);
+        drain_g(e, part + CP::W8, 128, cr * 128);
         UPROF(0, 24);
         e.wait_d();
         UPROF(0, 25);
@@ -650,9 +671,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
                       reinterpret_cast<const float *>(scr + SC::RSTD2), reinterpret_cast<const uint32_t *>(scr + SC::KEEP) + 1024, part + CP::VB);
         e.a_ready();
         UPROF(0, 26);
-        drain_g(e, part + CP::W4, 256);
-        UPROF(0, 27);
-        drain_g(e, part + CP::W4 + 128 * 256, 256);
+        drain_g(e, part + CP::W4 + cr * 128 * 256, 256, 0);
         UPROF(0, 28);
         e.wait_d();
         UPROF(0, 29);
@@ -660,11 +679,10 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
                       reinterpret_cast<const float *>(scr + SC::RSTD1), reinterpret_cast<const uint32_t *>(scr + SC::KEEP), part + CP::VA);
         e.a_ready();
         UPROF(0, 30);
-        drain_g(e, part + CP::W0, 16);
-        UPROF(0, 31);
-        drain_g(e, part + CP::W0 + 128 * 16, 16);
+        drain_g(e, part + CP::W0 + cr * 128 * 16, 16, 0);
         UPROF(0, 32);
         }
+        UTC_EPI_DONE
     }
     UTC_ROLE_EPILOGUE
 }
@@ -674,48 +692,52 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
 // =====================================================================================================================
 template <int ROLE>
 __device__ __forceinline__ void actor_program(Pipe &p, const Args &a, const uint8_t *scr) {
+    const int cr = (int)p.cr;
     gemm_fwd<ROLE>(p, a.img_actor + AI::W1, 128, 48);
     gemm_fwd<ROLE>(p, a.img_actor + AI::W2, 128, 128);
     gemm_fwd<ROLE>(p, a.img_actor + AI::W3, 64, 128);
-    gemm_fwd<ROLE>(p, a.img_actor + AI::W4, 16, 64);
+    gemm_fwd<ROLE>(p, a.img_actor + AI::W4, 16, 64, false);
     gemm_fwd<ROLE>(p, a.img_critic + CI::W0, 256, 48);
     gemm_fwd<ROLE>(p, a.img_critic + CI::W4, 256, 256);
     gemm_fwd<ROLE>(p, a.img_critic + CI::W8, 128, 256);
     // input gradient of the critic
-    gemm_bwd<ROLE>(p, a.img_critic + CI::W8, 128, 256, 256);
-    gemm_bwd<ROLE>(p, a.img_critic + CI::W4, 256, 256, 256);
-    gemm_bwd<ROLE>(p, a.img_critic + CI::W0, 256, 48, 16);
-    // actor backward
+    gemm_bwd<ROLE>(p, a.img_critic + CI::W8, 128, 256, 256, true, true);
+    gemm_bwd<ROLE>(p, a.img_critic + CI::W4, 256, 256, 256, true, true);
+    gemm_bwd<ROLE>(p, a.img_critic + CI::W0, 256, 48, 16, false, true);
+    // actor backward: every weight gradient is one block of output rows, the pair splits its input columns (dW1: 16 columns, both CTAs)
     load_h<ROLE>(p, scr + SC::A3IMG, 16384);
-    gemm_bwd<ROLE>(p, a.img_actor + AI::W4, 16, 64, 64);
-    wgrad<ROLE>(p, 16, 0, 64, 64, true, false, true);
+    gemm_bwd<ROLE>(p, a.img_actor + AI::W4, 16, 64, 64, true, false);
+    wgrad<ROLE>(p, 16, 0, 64, cr * 32, 32, true, false, true, true);
     load_h<ROLE>(p, scr + SC::A2IMG, 32768);
-    gemm_bwd<ROLE>(p, a.img_actor + AI::W3, 64, 128, 128);
-    wgrad<ROLE>(p, 64, 0, 128, 128, true, false, true);
+    gemm_bwd<ROLE>(p, a.img_actor + AI::W3, 64, 128, 128, true, false);
+    wgrad<ROLE>(p, 64, 0, 128, cr * 64, 64, true, false, true, true);
     load_h<ROLE>(p, scr + SC::A1IMG, 32768);
-    gemm_bwd<ROLE>(p, a.img_actor + AI::W2, 128, 128, 128);
-    wgrad<ROLE>(p, 128, 0, 128, 128, true, false, true);
+    gemm_bwd<ROLE>(p, a.img_actor + AI::W2, 128, 128, 128, true, false);
+    wgrad<ROLE>(p, 128, 0, 128, cr * 64, 64, true, false, true, true);
     load_h<ROLE>(p, scr + SC::XAIMG, 12288);
-    wgrad<ROLE>(p, 128, 0, 48, 16, true, true, true);
+    wgrad<ROLE>(p, 128, 0, 48, 0, 16, true, true, true, true);
 }
 
 __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
     UTC_ROLE_PROLOGUE
+    const int tile = pair;
+    uint8_t *scr = a.scratch + (size_t)tile * SC::BYTES;
     if (warp == W_PRODUCER) {
-        if (elect_one()) { Pipe p{smem, bars, tbase}; actor_program<ROLE_PRODUCER>(p, a, scr); }
+        if (elect_one()) { Pipe p{smem, bars, tbase, cr}; actor_program<ROLE_PRODUCER>(p, a, scr); }
         __syncwarp();
     } else if (warp == W_ISSUER) {
-        if (elect_one()) { Pipe p{smem, bars, tbase}; actor_program<ROLE_ISSUER>(p, a, scr); }
+        if (elect_one()) { Pipe p{smem, bars, tbase, cr}; actor_program<ROLE_ISSUER>(p, a, scr); }
         __syncwarp();
     } else {
-        Epi e{smem, bars, tbase, tid, tid >> 7, tid & 127, tid & 31, (tid >> 5) & 3, (uint32_t)(((tid >> 5) & 3) * 32) << 16};
-        e.row0 = blockIdx.x * TR; e.B = a.B;
+        UTC_MAKE_EPI
+        e.row0 = tile * TR; e.B = a.B;
         const int grow = e.row0 + e.r;
         const bool valid = e.valid();
         const float *row = a.batch + (size_t)(valid ? grow : 0) * ERLFILL_REC;
-        float *part = a.apart + (size_t)blockIdx.x * AP::SIZE;
-        uint32_t *abits = reinterpret_cast<uint32_t *>(scr + SC::ABITS) + e.r * 16;     // [pos1 x4 | keep1 x4 | pos2 x4 | keep2 x4]; pos3 in keep words of ...
-        float *aux = reinterpret_cast<float *>(scr + SC::AUX) + e.r;      // [64][128 rows]
+        float *part = a.apart + (size_t)tile * AP::SIZE;
+        // [row][32 words]: pos1 x8 | keep1 x8 | pos2 x8 | keep2 x8, word (4 cr + wg) = this thread's 16 columns
+        uint32_t *abits = reinterpret_cast<uint32_t *>(scr + SC::ABITS) + e.r * 32 + (cr * 4 + e.wg);
+        float *aux = reinterpret_cast<float *>(scr + SC::AUX) + (size_t)cr * 64 * TR + e.r;      // [64][128 rows], one copy per CTA
         // L2 norms of the nine actor tensors (actor_loss += 1e-4 sum ||theta_t||, ddpg_agent.py:490-494), spread over the CTAs
         for (int t = blockIdx.x; t < 9; t += gridDim.x) {
             float qn = 0.f;
@@ -735,34 +757,24 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
         const float *scale = a.scale + cid * 10, *offset = a.offset + cid * 10;
         const float e0 = valid ? __ldg(row + 16) : 0.f, e1 = valid ? __ldg(row + 17) : 0.f, e2 = valid ? __ldg(row + 18) : 0.f;
         // ---- a = actor(s, e) ----
+        e.wait_afree();
         if (e.wg == 0) {
             float x[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = 0.f;
             if (valid) { x[0] = __ldg(row); x[1] = __ldg(row + 1); x[2] = e0; x[3] = e1; x[4] = e2; }
             x[15] = 1.0f;
-            store_split_input(e, x, scr + SC::XAIMG);
+            store_split_input(e, x, cr == 0 ? scr + SC::XAIMG : nullptr);
         }
         e.a_ready(); UPROF(1, 1);
-        e.wait_d(); UPROF(1, 2); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 6, scr + SC::A1IMG, abits + e.wg, abits + 4 + e.wg); e.a_ready(); UPROF(1, 3);
-        e.wait_d(); UPROF(1, 4); epi_hidden128(e, a.actor + AO::B2, ACT_RELU, a.drop, 7, scr + SC::A2IMG, abits + 8 + e.wg, abits + 12 + e.wg); e.a_ready(); UPROF(1, 5);
+        e.wait_d(); UPROF(1, 2); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 6, scr + SC::A1IMG, abits, abits + 8); e.a_ready(); UPROF(1, 3);
+        e.wait_d(); UPROF(1, 4); epi_hidden128(e, a.actor + AO::B2, ACT_RELU, a.drop, 7, scr + SC::A2IMG, abits + 16, abits + 24); e.a_ready(); UPROF(1, 5);
         e.wait_d(); UPROF(1, 6);
-        uint32_t pos3 = 0;                                     // relu'(z3) bits of this thread's 16 columns (kept in a register until the backward)
-        {
-            float v[16];
-            tmem_ld16w(e.td(e.wg * 16), v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                v[j] = fmaxf(v[j] + __ldg(a.actor + AO::B3 + e.wg * 16 + j), 0.f);
-                pos3 |= (v[j] > 0.f ? 1u : 0u) << j;
-            }
-            e.img_store8(e.img_a(), 64, e.wg * 16, v);
-            e.img_store8(e.img_a(), 64, e.wg * 16 + 8, v + 8);
-            e.img_store8(scr + SC::A3IMG, 64, e.wg * 16, v);
-            e.img_store8(scr + SC::A3IMG, 64, e.wg * 16 + 8, v + 8);
-        }
+        // relu'(z3) bits of this thread's 8 columns (kept in a register until the backward)
+        const uint32_t pos3 = epi_hidden64(e, a.actor + AO::B3, scr + SC::A3IMG);
         e.a_ready(); UPROF(1, 7);
         e.wait_d(); UPROF(1, 8);
+        e.wait_afree();
         if (e.wg == 0) {
             float z[16], out[10], x[16];
             tmem_ld16w(e.td(0), z);
@@ -801,19 +813,22 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
         e.a_ready(); UPROF(1, 13);
         e.wait_d(); UPROF(1, 14);
         {
-            float h3[32], dz3[32];
+            float h3[16], dz3[16];
             const float q2 = epi_head(e, a.critic, h3);
             const float g = valid ? -1.0f / (float)a.B : 0.f;  // d(-mean Q)/dQ; the +-1e6 clamp is inactive
+            const int c0 = (int)cr * 64 + e.wg * 16;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dz3[j] = h3[j] > 0.f ? g * __ldg(a.critic + CO::W10 + e.wg * 32 + j) : 0.f;
-            store_img128(e, dz3);
+            for (int j = 0; j < 16; ++j) dz3[j] = h3[j] > 0.f ? g * __ldg(a.critic + CO::W10 + c0 + j) : 0.f;
+            e.wait_afree();
+            e.img_store8_pair(128, c0, dz3);
+            e.img_store8_pair(128, c0 + 8, dz3 + 8);
             e.a_ready(); UPROF(1, 15);
             if (e.wg == 0) {
                 const float sq = warp_sum(valid ? q2 : 0.f);
                 if (e.lane == 0) e.cs()[(2 * 4 + e.wq) * 256 + 3] = sq;
             }
             bar_epi();
-            if (e.tid == 0) {
+            if (e.tid == 0 && cr == 0) {
                 const float *c = e.cs() + 2 * 4 * 256;
                 part[AP::SSTD] = (c[2] + c[258]) + (c[514] + c[770]);
                 part[AP::SQ] = (c[3] + c[259]) + (c[515] + c[771]);
@@ -830,6 +845,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
         e.a_ready(); UPROF(1, 19);
         e.wait_d(); UPROF(1, 20);
         // ---- actor backward ----
+        e.wait_afree();
         if (e.wg == 0) {
             float g16[16], dz4[16], prod[32];
             tmem_ld16w(e.td(0), g16);                           // dQ/dx0: columns 2..11 are dQ/da
@@ -866,68 +882,72 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             float db4[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) db4[j] = j < 16 ? dz4[j] : 0.f;
-            e.colsum_stage(0, 0, prod);                         // d emotion_weights [3][10]
-            e.colsum_stage(1, 0, db4);
+            e.colsum_stage<32>(0, 0, prod);                     // d emotion_weights [3][10]
+            e.colsum_stage<32>(1, 0, db4);
         }
         e.a_ready(); UPROF(1, 21);
         bar_epi();
-        e.colsum_finish(0, 32, part + AP::EW);
-        e.colsum_finish(1, 16, part + AP::B4);
+        if (cr == 0) {
+            e.colsum_finish(0, 32, part + AP::EW);
+            e.colsum_finish(1, 16, part + AP::B4);
+        }
         bar_epi();
-        drain_g(e, part + AP::W4, 64); UPROF(1, 22);
+        drain_g(e, part + AP::W4, 32, cr * 32); UPROF(1, 22);
         e.wait_d(); UPROF(1, 23);
-        {   // da3 = dz4 W4, relu'
-            float v[16], s[32];
-            tmem_ld16w(e.td(e.wg * 16), v);
+        {   // da3 = dz4 W4 (this CTA's 32 inputs, 8 per thread), relu'
+            float v[8];
+            const int cl = e.wg * 8, c0 = (int)cr * 32 + cl;
+            tmem_ld8w(e.td(cl), v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = ((pos3 >> j) & 1u) ? v[j] : 0.f;
-            e.img_store8(e.img_a(), 64, e.wg * 16, v);
-            e.img_store8(e.img_a(), 64, e.wg * 16 + 8, v + 8);
+            for (int j = 0; j < 8; ++j) v[j] = ((pos3 >> j) & 1u) ? v[j] : 0.f;
+            e.wait_afree();
+            e.img_store8_pair(64, c0, v);
             e.a_ready(); UPROF(1, 24);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s[j] = j < 16 ? v[j] : 0.f;
-            // 16 columns per warpgroup: stage at column 32 * wg (lanes 16..31 carry zeros), finish picks 16 of every 32
-            e.colsum_stage(0, e.wg * 32, s);
+            e.colsum_stage<8>(0, cl, v);
             bar_epi();
-            if (e.tid < 64) {
-                const float *c = e.cs() + (e.tid >> 4) * 32 + (e.tid & 15);
-                part[AP::B3 + e.tid] = (c[0] + c[256]) + (c[512] + c[768]);
-            }
+            e.colsum_finish(0, 32, part + AP::B3 + cr * 32);
             bar_epi();
         }
-        drain_g(e, part + AP::W3, 128); UPROF(1, 25);
+        drain_g(e, part + AP::W3, 64, cr * 64); UPROF(1, 25);
         e.wait_d(); UPROF(1, 26);
-        {   // da2 = dz3 W3, dropout (site 7), relu'
-            float v[32];
-            tmem_ld32w(e.td(e.wg * 32), v);
-            const uint32_t pos = abits[8 + e.wg], keep = abits[12 + e.wg];
+        {   // da2 = dz3 W3 (this CTA's 64 inputs, 16 per thread), dropout (site 7), relu'
+            float v[16];
+            const int cl = e.wg * 16, c0 = (int)cr * 64 + cl;
+            tmem_ld16w(e.td(cl), v);
+            const uint32_t pos = abits[16], keep = abits[24];
             const float ds = a.drop.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (((pos & keep) >> j) & 1u) ? v[j] * ds : 0.f;
-            store_img128(e, v);
+            for (int j = 0; j < 16; ++j) v[j] = (((pos & keep) >> j) & 1u) ? v[j] * ds : 0.f;
+            e.wait_afree();
+            e.img_store8_pair(128, c0, v);
+            e.img_store8_pair(128, c0 + 8, v + 8);
             e.a_ready(); UPROF(1, 27);
-            e.colsum_stage(0, e.wg * 32, v);
+            e.colsum_stage<16>(0, cl, v);
             bar_epi();
-            e.colsum_finish(0, 128, part + AP::B2);
+            e.colsum_finish(0, 64, part + AP::B2 + cr * 64);
             bar_epi();
         }
-        drain_g(e, part + AP::W2, 128); UPROF(1, 28);
+        drain_g(e, part + AP::W2, 64, cr * 64); UPROF(1, 28);
         e.wait_d(); UPROF(1, 29);
         {   // da1 = dz2 W2, dropout (site 6), leaky'
-            float v[32];
-            tmem_ld32w(e.td(e.wg * 32), v);
-            const uint32_t pos = abits[e.wg], keep = abits[4 + e.wg];
+            float v[16];
+            const int cl = e.wg * 16, c0 = (int)cr * 64 + cl;
+            tmem_ld16w(e.td(cl), v);
+            const uint32_t pos = abits[0], keep = abits[8];
             const float ds = a.drop.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * ds * (((pos >> j) & 1u) ? 1.0f : 0.1f) : 0.f;
-            store_img128(e, v);
+            for (int j = 0; j < 16; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * ds * (((pos >> j) & 1u) ? 1.0f : 0.1f) : 0.f;
+            e.wait_afree();
+            e.img_store8_pair(128, c0, v);
+            e.img_store8_pair(128, c0 + 8, v + 8);
             e.a_ready(); UPROF(1, 30);
-            e.colsum_stage(0, e.wg * 32, v);
+            e.colsum_stage<16>(0, cl, v);
             bar_epi();
-            e.colsum_finish(0, 128, part + AP::B1);
+            e.colsum_finish(0, 64, part + AP::B1 + cr * 64);
             bar_epi();
         }
-        drain_g(e, part + AP::W1, 16); UPROF(1, 31);
+        drain_g(e, cr == 0 ? part + AP::W1 : nullptr, 16, 0); UPROF(1, 31);
+        UTC_EPI_DONE
     }
     UTC_ROLE_EPILOGUE
 }
@@ -1109,19 +1129,19 @@ __global__ void actor_apply_kernel(float *p, float *pt, float *m, float *v, cons
 struct Tail {
     uint8_t *img_actor, *img_actor_t, *img_critic, *img_critic_t, *scratch;
     float *cpart, *apart, *tq_g, *stats_part, *ssq_fine;      // ssq_fine: [2][kRedBlocks]
-    uint32_t *flags;            // tq_flag per tile, then the two counters of grid_emotion_stats
+    uint32_t *flags;            // two tq_flags per tile, then the two counters of grid_emotion_stats
 };
 static size_t up256(size_t n) { return (n + 255) & ~(size_t)255; }
 static int n_cta(int B) { return (B + TR - 1) / TR; }
 size_t tail_bytes(int B) {
     const size_t c = (size_t)n_cta(B);
-    return up256((c + 2) * 4) + up256(c * 32) + 2 * up256(AI::BYTES) + 2 * up256(CI::BYTES) + up256(c * SC::BYTES) + up256(c * CP::SIZE * 4) + up256(c * AP::SIZE * 4) +
+    return up256((2 * c + 2) * 4) + up256(c * 32) + 2 * up256(AI::BYTES) + 2 * up256(CI::BYTES) + up256(c * SC::BYTES) + up256(c * CP::SIZE * 4) + up256(c * AP::SIZE * 4) +
            up256((size_t)B * 4) + up256(2 * 4 * 64 * 4);
 }
 static void carve_tail(Tail &t, uint8_t *base, int B) {
     const size_t c = (size_t)n_cta(B);
     size_t o = 0;
-    t.flags = reinterpret_cast<uint32_t *>(base); o += up256((c + 2) * 4);
+    t.flags = reinterpret_cast<uint32_t *>(base); o += up256((2 * c + 2) * 4);
     t.stats_part = reinterpret_cast<float *>(base + o); o += up256(c * 32);
     t.img_actor = base + o; o += up256(AI::BYTES);
     t.img_actor_t = base + o; o += up256(AI::BYTES);
@@ -1134,20 +1154,46 @@ static void carve_tail(Tail &t, uint8_t *base, int B) {
     t.ssq_fine = reinterpret_cast<float *>(base + o);
 }
 
-static cudaError_t smem_optin() {
+// Both phase kernels run as clusters of two CTAs (one pair per 128-row tile).
+static void pair_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute &attr, int n_ctas, cudaStream_t st) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3((unsigned)n_ctas);
+    cfg.blockDim = dim3(NTHR);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+}
+static cudaError_t launch_pairs(void (*kernel)(const Args), int n_ctas, const Args &a, cudaStream_t st) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr;
+    pair_config(cfg, attr, n_ctas, st);
+    return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+// shared-memory opt-in; *max_pairs = how many pairs of ddpg_critic_grad_tc the device keeps resident at once (0 if the query fails)
+static cudaError_t pair_setup(int *max_pairs) {
     static bool done = false;
-    if (done) return cudaSuccess;
-    cudaError_t e;
-    if ((e = cudaFuncSetAttribute(ddpg_critic_grad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ddpg_actor_grad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess) return e;
-    done = true;
+    static int pairs = 0;
+    if (!done) {
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(ddpg_critic_grad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ddpg_actor_grad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess) return e;
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute attr;
+        pair_config(cfg, attr, 2, nullptr);
+        if (cudaOccupancyMaxActiveClusters(&pairs, ddpg_critic_grad_tc, &cfg) != cudaSuccess) { pairs = 0; (void)cudaGetLastError(); }
+        done = true;
+    }
+    *max_pairs = pairs;
     return cudaSuccess;
 }
 
 int pack_images(const erlfill_ddpg_nets *n, uint8_t *tail_base, int B, cudaStream_t st) {
     Tail t;
     carve_tail(t, tail_base, B);
-    ERLFILL_CUDA_TRY(cudaMemsetAsync(t.flags, 0, up256(((size_t)n_cta(B) + 2) * 4), st));
+    ERLFILL_CUDA_TRY(cudaMemsetAsync(t.flags, 0, up256((2 * (size_t)n_cta(B) + 2) * 4), st));
     ERLFILL_CUDA_TRY(cudaMemsetAsync(t.img_actor, 0, 2 * up256(AI::BYTES) + 2 * up256(CI::BYTES), st));
     pack_images_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, n->actor_target, n->critic, n->critic_target, t.img_actor, t.img_actor_t,
                                                                 t.img_critic, t.img_critic_t);
@@ -1161,7 +1207,8 @@ struct Head { float *cgrad, *agrad, *cred, *ared, *stats, *scal, *ssq, *step; };
 int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const float *d_batch, const float *d_next_emotion, const Head &w,
                 uint8_t *tail_base, int phases, float *d_report, cudaStream_t st) {
     const int B = h->batch, nc = n_cta(B);
-    ERLFILL_CUDA_TRY(smem_optin());
+    int max_pairs = 0;
+    ERLFILL_CUDA_TRY(pair_setup(&max_pairs));
     Tail t;
     carve_tail(t, tail_base, B);
     Args a;
@@ -1187,14 +1234,12 @@ int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const f
         for (int s = 0; s < 10; ++s) if (!h->masks->keep[s]) return ERLFILL_ERR_ARG;
     }
     a.tq_g = t.tq_g; a.tq_flag = t.flags;
-    a.stats_g = w.stats; a.stats_part = t.stats_part; a.stats_ctr = t.flags + nc;
+    a.stats_g = w.stats; a.stats_part = t.stats_part; a.stats_ctr = t.flags + 2 * nc;
     a.stats_ext = h->n_stats_partials > 0 ? h->d_stats_partials : nullptr; a.n_stats_ext = h->n_stats_partials;
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    a.split = (2 * nc <= sms) ? 1 : 0;        // both halves of every tile must be resident at once (one CTA per SM)
+    a.split = (2 * nc <= max_pairs) ? 1 : 0;  // the pairs of both chains of every tile must be resident at once (one CTA per SM)
     const bool reduced = (phases & ERLFILL_PHASE_REDUCED) != 0;
     if (phases & ERLFILL_PHASE_CRITIC_GRAD) {
-        ddpg_critic_grad_tc<<<a.split ? 2 * nc : nc, NTHR, SMEM_BYTES, st>>>(a);
+        ERLFILL_CUDA_TRY(launch_pairs(ddpg_critic_grad_tc, 2 * (a.split ? 2 * nc : nc), a, st));
         grad_reduce_kernel<false><<<kRedBlocks, 256, 0, st>>>(nc, B, t.cpart, nullptr, w.scal, w.cgrad, t.ssq_fine);
     }
     if (phases & ERLFILL_PHASE_CRITIC_APPLY) {
@@ -1204,7 +1249,7 @@ int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const f
                                                                      h->max_grad_norm, w.scal, t.img_critic);
     }
     if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
-        ddpg_actor_grad_tc<<<nc, NTHR, SMEM_BYTES, st>>>(a);
+        ERLFILL_CUDA_TRY(launch_pairs(ddpg_actor_grad_tc, 2 * nc, a, st));
         grad_reduce_kernel<true><<<kRedBlocks, 256, 0, st>>>(nc, B, t.apart, n->actor, w.scal, w.agrad, t.ssq_fine + kRedBlocks);
     }
     if (phases & ERLFILL_PHASE_ACTOR_APPLY) {
