@@ -197,6 +197,28 @@ __device__ __forceinline__ void mma_commit_mc(uint64_t *bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
+// push `bytes` of this CTA's shared memory into the peer's (async proxy on both sides); completion is counted in bytes on the PEER's
+// mbarrier (both destination and barrier are shared::cluster addresses).  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_caddr, const void *src, uint32_t bytes, uint32_t bar_caddr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_caddr), "r"(smem_u32(src)),
+                 "r"(bytes), "r"(bar_caddr)
+                 : "memory");
+}
+// 8 bytes into the peer's shared memory, counted on the peer's mbarrier (no fence on the writer's side)
+__device__ __forceinline__ void st_async_f32x2(uint32_t dst_caddr, float a, float b, uint32_t bar_caddr) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(dst_caddr), "f"(a), "f"(b), "r"(bar_caddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
 // every thread of every CTA of the cluster
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -25,10 +25,9 @@ constexpr int ACT_LEAKY = 0, ACT_RELU = 1;
 
 // ---- per-tile global scratch (bytes), shared by the two CTAs of the pair (each writes its own columns) ------------------------
 namespace SC {
-constexpr size_t X0IMG = 0, H1IMG = X0IMG + 12288, H2IMG = H1IMG + 65536, XHAT1 = H2IMG + 65536, XHAT2 = XHAT1 + 131072,
-                 RSTD1 = XHAT2 + 131072, RSTD2 = RSTD1 + 512, KEEP = RSTD2 + 512 /* [2][128][8] words */, XAIMG = KEEP + 8192,
-                 A1IMG = XAIMG + 12288, A2IMG = A1IMG + 32768, A3IMG = A2IMG + 32768, ABITS = A3IMG + 16384 /* [128][32] words */,
-                 AUX = ABITS + 16384 /* [2 CTAs][64][128] floats */, BYTES = AUX + 65536;
+constexpr size_t X0IMG = 0, H1IMG = X0IMG + 12288, H2IMG = H1IMG + 65536, XAIMG = H2IMG + 65536, A1IMG = XAIMG + 12288, A2IMG = A1IMG + 32768,
+                 A3IMG = A2IMG + 32768, ABITS = A3IMG + 16384 /* [128][32] words */, AUX = ABITS + 16384 /* [2 CTAs][64][128] floats */,
+                 BYTES = AUX + 65536;
 }
 
 struct Args {
@@ -68,9 +67,10 @@ __device__ __forceinline__ void setup(uint8_t *smem, uint64_t *bars, uint32_t *t
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bars + BW_FULL + s, 1); mbar_init(bars + BW_EMPTY + s, 1); }
         mbar_init(bars + B_HFULL, 1); mbar_init(bars + B_HFREE, 1); mbar_init(bars + B_DFULL, 1); mbar_init(bars + B_GFULL, 1);
         mbar_init(bars + B_GFREE, NEPI / 32);
-        mbar_init(bars + B_AREADY, 2 * NEPI / 32);               // the epilogue warps of both CTAs
+        mbar_init(bars + B_AREADY, 1);                           // one local arrival (+ the bytes of the peer's half)
         mbar_init(bars + B_AFREE, 2);                            // the issuers of both CTAs
-        mbar_init(bars + B_XRED, 2 * NEPI / 32); mbar_init(bars + B_XRED + 1, 2 * NEPI / 32);
+        mbar_init(bars + B_XRED, NEPI / 32); mbar_init(bars + B_XRED1, NEPI / 32);      // local warps (+ the bytes of the peer's partials)
+        mbar_init(bars + B_HPUB, 2 * NEPI / 32);                 // the epilogue warps of both CTAs
         mbar_fence_init();
     }
     if (warp == W_ISSUER) tmem_alloc(tmem_slot, 512);
@@ -253,17 +253,21 @@ __device__ __forceinline__ uint32_t epi_hidden64(Epi &e, const float *bias, uint
 }
 
 // LayerNorm(256) + activation + dropout of the critic (this CTA's 128 columns: 32 per thread, held in registers across the exchange
-// of the row statistics) -> image of 256 features in both CTAs.
-// save: xhat (fp32, [64 float4 columns][128 rows]: a warp's 32 rows are 512 contiguous bytes), rstd [128], keep words [128][8], image
-// copy — what the backward and the weight gradients read.
+// of the row statistics) -> image of 256 features, then a_ready.
+// save != nullptr: what the backward needs stays on chip — xhat (fp32) goes to this thread's TMEM lane (columns TM_X1 / TM_X2 of layer
+// 0 / 1), rstd and the keep word to save[0..1] (registers of the caller); gimg: global copy of the image for the weight-gradient
+// GEMM.  Both are written AFTER a_ready, off the critical path.
 __device__ __forceinline__ void epi_ln256(Epi &e, const float *bias, const float *gamma, const float *beta, int act, const Drop &dr, int site,
-                                          float *xhat_g, float *rstd_g, uint32_t *keep_g, uint8_t *gimg) {
+                                          int layer, uint32_t *save, uint8_t *gimg) {
     const int cl = e.wg * 32, c0 = e.cr * 128 + cl;
     float v[32];
     tmem_ld32w(e.td(cl), v);
     if (bias) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __ldg(bias + c0 + j);
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + c0) + j4);
+            v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+        }
     }
     // shifted sums of this thread's 32 columns -> (mean_w, M2_w); the eight statistics of the row combine exactly (Chan et al.)
     const float k = v[0];
@@ -278,27 +282,41 @@ __device__ __forceinline__ void epi_ln256(Epi &e, const float *bias, const float
     const float rstd = rsqrtf(var + 1e-5f);
     const float ds = dr.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale;
     const uint32_t kb = keep32(dr, site, e.mrow(), c0, 256);
-    if (keep_g) keep_g[e.r * 8 + (c0 >> 5)] = kb;
-    e.wait_afree();
+    uint32_t packed[16];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        float hh[8];
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4 *>(gamma + c0) + j4), b4 = __ldg(reinterpret_cast<const float4 *>(beta + c0) + j4);
+        const float gm[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+        float hh[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int j = g * 8 + i, c = c0 + j;
+        for (int i = 0; i < 4; ++i) {
+            const int j = j4 * 4 + i;
             const float xh = (v[j] - mean) * rstd;
             v[j] = xh;
-            float y = xh * __ldg(gamma + c) + __ldg(beta + c);
+            float y = xh * gm[i] + be[i];
             y = act == ACT_LEAKY ? (y > 0.f ? y : 0.1f * y) : fmaxf(y, 0.f);
             hh[i] = ((kb >> j) & 1u) ? y * ds : 0.f;
         }
-        e.img_store8_pair(256, c0 + g * 8, hh, gimg);
+        packed[2 * j4] = pack_bf16x2(hh[0], hh[1]);
+        packed[2 * j4 + 1] = pack_bf16x2(hh[2], hh[3]);
     }
-    if (xhat_g) {
-        float4 *dst = reinterpret_cast<float4 *>(xhat_g) + (size_t)(c0 >> 2) * TR + e.r;
+    e.wait_afree();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[(size_t)j * TR] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        if (e.wg == 0 && e.cr == 0) rstd_g[e.r] = rstd;
+    for (int g = 0; g < 4; ++g) e.img_store_pair_q(256, c0 + g * 8, make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]));
+    e.a_ready(256);
+    if (gimg) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4 *>(gimg + img_off(e.r, c0 + g * 8, 256)) = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+    }
+    if (save) {
+        uint32_t xw[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xw[j] = __float_as_uint(v[j]);
+        tmem_st32(e.tx(layer, cl), xw);
+        tmem_wait_st();
+        save[0] = __float_as_uint(rstd);
+        save[1] = kb;
     }
 }
 
@@ -318,35 +336,41 @@ __device__ __forceinline__ float epi_head(Epi &e, const float *P, float (&h3)[16
 }
 
 // Backward of (LayerNorm(256) + activation + dropout): D holds dh (gradient of the dropped activation) of this CTA's 128 columns;
-// writes dz (gradient of the LayerNorm input) into the image of 256 features of both CTAs.  part != nullptr: per-tile column sums
-// [sum dz | sum dy xhat | sum dy] of this CTA's columns.
-__device__ __forceinline__ void epi_ln256_bwd(Epi &e, const float *gamma, const float *beta, int act, const Drop &dr, const float *xhat_g,
-                                              const float *rstd_g, const uint32_t *keep_g, float *part) {
+// writes dz (gradient of the LayerNorm input) into the image of 256 features, then a_ready.  xhat comes back from this thread's TMEM
+// lane, rstd / keep word from save[0..1] (epi_ln256).  part != nullptr: per-tile column sums [sum dz | sum dy xhat | sum dy] of this
+// CTA's columns (stored after a_ready).
+__device__ __forceinline__ void epi_ln256_bwd(Epi &e, const float *gamma, const float *beta, int act, const Drop &dr, int layer, const uint32_t *save,
+                                              float *part) {
     const int cl = e.wg * 32, c0 = e.cr * 128 + cl;
     const float ds = dr.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale;
-    const uint32_t kw = keep_g[e.r * 8 + (c0 >> 5)];
-    const float rstd = rstd_g[e.r];
-    const float4 *xp = reinterpret_cast<const float4 *>(xhat_g) + (size_t)(c0 >> 2) * TR + e.r;
+    const uint32_t kw = save[1];
+    const float rstd = __uint_as_float(save[0]);
+    const float4 *gp = reinterpret_cast<const float4 *>(gamma + c0), *bp = reinterpret_cast<const float4 *>(beta + c0);
     float s1 = 0.f, s2 = 0.f;
     // pass 1: dy = dh * keep/0.8 * act'(y); row sums of dy*gamma and dy*gamma*xhat; column sums of dy*xhat and dy
     {
         float dh[32], a[32], b[32];
         tmem_ld32w(e.td(cl), dh);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 x4 = xp[(size_t)j4 * TR];
-            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+        for (int g8 = 0; g8 < 4; ++g8) {
+            float xs[8];
+            tmem_ld8w(e.tx(layer, cl + 8 * g8), xs);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int j = j4 * 4 + i, c = c0 + j;
-                const float gm = __ldg(gamma + c), y = xs[i] * gm + __ldg(beta + c);
-                float g = ((kw >> j) & 1u) ? dh[j] * ds : 0.f;
-                g *= act == ACT_LEAKY ? (y > 0.f ? 1.f : 0.1f) : (y > 0.f ? 1.f : 0.f);
-                const float dxh = g * gm;
-                s1 += dxh;
-                s2 = fmaf(dxh, xs[i], s2);
-                a[j] = g * xs[i];
-                b[j] = g;
+            for (int h = 0; h < 2; ++h) {
+                const float4 g4 = __ldg(gp + 2 * g8 + h), b4 = __ldg(bp + 2 * g8 + h);
+                const float gm[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = g8 * 8 + h * 4 + i;
+                    const float x = xs[h * 4 + i], y = x * gm[i] + be[i];
+                    float g = ((kw >> j) & 1u) ? dh[j] * ds : 0.f;
+                    g *= act == ACT_LEAKY ? (y > 0.f ? 1.f : 0.1f) : (y > 0.f ? 1.f : 0.f);
+                    const float dxh = g * gm[i];
+                    s1 += dxh;
+                    s2 = fmaf(dxh, x, s2);
+                    a[j] = g * x;
+                    b[j] = g;
+                }
             }
         }
         if (part) { e.colsum_stage<32>(1, cl, a); e.colsum_stage<32>(2, cl, b); }
@@ -358,21 +382,27 @@ __device__ __forceinline__ void epi_ln256_bwd(Epi &e, const float *gamma, const 
         float dh[32], dz[32];
         tmem_ld32w(e.td(cl), dh);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 x4 = xp[(size_t)j4 * TR];
-            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+        for (int g8 = 0; g8 < 4; ++g8) {
+            float xs[8];
+            tmem_ld8w(e.tx(layer, cl + 8 * g8), xs);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int j = j4 * 4 + i, c = c0 + j;
-                const float gm = __ldg(gamma + c), y = xs[i] * gm + __ldg(beta + c);
-                float g = ((kw >> j) & 1u) ? dh[j] * ds : 0.f;
-                g *= act == ACT_LEAKY ? (y > 0.f ? 1.f : 0.1f) : (y > 0.f ? 1.f : 0.f);
-                dz[j] = rstd * (g * gm - s1 - xs[i] * s2);
+            for (int h = 0; h < 2; ++h) {
+                const float4 g4 = __ldg(gp + 2 * g8 + h), b4 = __ldg(bp + 2 * g8 + h);
+                const float gm[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = g8 * 8 + h * 4 + i;
+                    const float x = xs[h * 4 + i], y = x * gm[i] + be[i];
+                    float g = ((kw >> j) & 1u) ? dh[j] * ds : 0.f;
+                    g *= act == ACT_LEAKY ? (y > 0.f ? 1.f : 0.1f) : (y > 0.f ? 1.f : 0.f);
+                    dz[j] = rstd * (g * gm[i] - s1 - x * s2);
+                }
             }
         }
         e.wait_afree();
 #pragma unroll
         for (int g = 0; g < 4; ++g) e.img_store8_pair(256, c0 + g * 8, dz + g * 8);
+        e.a_ready(256);
         if (part) e.colsum_stage<32>(0, cl, dz);
     }
     if (part) {
@@ -469,7 +499,8 @@ __device__ __forceinline__ void critic_program(Pipe &p, const Args &a, const uin
     // dh1 = dz2 W4, dW4 = dz2^T h1 (this CTA's block of 128 output rows)
     load_h<ROLE>(p, scr + SC::H1IMG, 65536);
     gemm_bwd<ROLE>(p, a.img_critic + CI::W4, 256, 256, 256, true, false);
-    wgrad<ROLE>(p, 256, cr * 128, 256, 0, 256, true, false, true, true);
+    wgrad<ROLE>(p, 256, cr * 128, 256, 0, 128, true, false, false, false);      // two column halves: 128 accumulator columns at a time
+    wgrad<ROLE>(p, 256, cr * 128, 256, 128, 128, false, false, true, true);
     // dW0 = dz1^T x0 (this CTA's block of 128 output rows)
     load_h<ROLE>(p, scr + SC::X0IMG, 12288);
     wgrad<ROLE>(p, 256, cr * 128, 48, 0, 16, true, true, true, true);
@@ -496,12 +527,14 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
         float *part = a.cpart + (size_t)tile * CP::SIZE;
         UPROF(0, 0);
         if (chain != 1 && a.stats_ext) {
-            // the minibatch came with its emotion sums: add the rows in order (identical on every CTA), no pass over the records
-            if (e.tid < 6) {
+            // the minibatch came with its emotion sums: warp c adds column c of the rows (lane l takes rows l, l + 32, ..., then a butterfly:
+            // the same order on every CTA), no pass over the records
+            if (e.tid < 6 * 32) {
+                const int c = e.tid >> 5;
                 float t = 0.f;
-#pragma unroll 8
-                for (int q = 0; q < a.n_stats_ext; ++q) t += __ldg(a.stats_ext + q * 8 + e.tid);
-                e.stat()[16 + e.tid] = t;
+                for (int q = e.lane; q < a.n_stats_ext; q += 32) t += __ldg(a.stats_ext + q * 8 + c);
+                t = warp_sum(t);
+                if (e.lane == 0) e.stat()[16 + c] = t;
             }
             bar_epi();
             if (e.tid < 3) {
@@ -534,13 +567,13 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
             x[15] = 1.0f;
             store_split_input(e, x, nullptr);
         }
-        e.a_ready();
+        e.a_ready_local();
         UPROF(0, 2);
-        e.wait_d(); UPROF(0, 3); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 0, nullptr, nullptr, nullptr); e.a_ready(); UPROF(0, 4);
-        e.wait_d(); UPROF(0, 5); epi_hidden128(e, a.actor_t + AO::B2, ACT_RELU, a.drop, 1, nullptr, nullptr, nullptr); e.a_ready(); UPROF(0, 6);
+        e.wait_d(); UPROF(0, 3); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 0, nullptr, nullptr, nullptr); e.a_ready(128); UPROF(0, 4);
+        e.wait_d(); UPROF(0, 5); epi_hidden128(e, a.actor_t + AO::B2, ACT_RELU, a.drop, 1, nullptr, nullptr, nullptr); e.a_ready(128); UPROF(0, 6);
         e.wait_d(); UPROF(0, 7);
         epi_hidden64(e, a.actor_t + AO::B3, nullptr);
-        e.a_ready();
+        e.a_ready(64);
         UPROF(0, 8);
         e.wait_d();
         UPROF(0, 9);
@@ -559,10 +592,10 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
             x[15] = 1.0f;                                       // the standardised emotion of identical rows is exactly 0
             store_split_input(e, x, nullptr);
         }
-        e.a_ready();
+        e.a_ready_local();
         UPROF(0, 10);
-        e.wait_d(); UPROF(0, 11); epi_ln256(e, nullptr, a.critic_t + CO::G1, a.critic_t + CO::BE1, ACT_LEAKY, a.drop, 2, nullptr, nullptr, nullptr, nullptr); e.a_ready(); UPROF(0, 12);
-        e.wait_d(); UPROF(0, 13); epi_ln256(e, a.critic_t + CO::B4, a.critic_t + CO::G2, a.critic_t + CO::BE2, ACT_RELU, a.drop, 3, nullptr, nullptr, nullptr, nullptr); e.a_ready(); UPROF(0, 14);
+        e.wait_d(); UPROF(0, 11); epi_ln256(e, nullptr, a.critic_t + CO::G1, a.critic_t + CO::BE1, ACT_LEAKY, a.drop, 2, 0, nullptr, nullptr); UPROF(0, 12);
+        e.wait_d(); UPROF(0, 13); epi_ln256(e, a.critic_t + CO::B4, a.critic_t + CO::G2, a.critic_t + CO::BE2, ACT_RELU, a.drop, 3, 1, nullptr, nullptr); UPROF(0, 14);
         e.wait_d();
         UPROF(0, 15);
         { float h3[16]; tq = epi_head(e, a.critic_t, h3); }
@@ -589,21 +622,17 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
             x[15] = 1.0f;
             store_split_input(e, x, cr == 0 ? scr + SC::X0IMG : nullptr);
         }
-        e.a_ready();
+        e.a_ready_local();
         UPROF(0, 17);
         e.wait_d();
         UPROF(0, 18);
-        epi_ln256(e, nullptr, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, 4, reinterpret_cast<float *>(scr + SC::XHAT1),
-                  reinterpret_cast<float *>(scr + SC::RSTD1), reinterpret_cast<uint32_t *>(scr + SC::KEEP), scr + SC::H1IMG);
-        __threadfence();                                        // the saved images are read back through the async proxy (bulk copies), by both CTAs
-        e.a_ready();
+        uint32_t sv1[2], sv2[2];                                // rstd / keep word of this thread's row and columns, LayerNorm 1 / 2
+        epi_ln256(e, nullptr, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, 4, 0, sv1, scr + SC::H1IMG);
         UPROF(0, 19);
         e.wait_d();
         UPROF(0, 20);
-        epi_ln256(e, a.critic + CO::B4, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, 5, reinterpret_cast<float *>(scr + SC::XHAT2),
-                  reinterpret_cast<float *>(scr + SC::RSTD2), reinterpret_cast<uint32_t *>(scr + SC::KEEP) + 1024, scr + SC::H2IMG);
-        __threadfence();
-        e.a_ready();
+        epi_ln256(e, a.critic + CO::B4, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, 5, 1, sv2, scr + SC::H2IMG);
+        e.publish_saved();
         UPROF(0, 21);
         if (chain == 2) {
             if (e.tid == 0) {
@@ -644,7 +673,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
             e.wait_afree();
             e.img_store8_pair(128, c0, dz3);
             e.img_store8_pair(128, c0 + 8, dz3 + 8);
-            e.a_ready();
+            e.a_ready(128);
             e.colsum_stage<16>(0, cl, dz3);                     // db8
             e.colsum_stage<16>(1, cl, gw);                      // dW10
             if (e.wg == 0) {                                    // db10 = sum g, loss = sum l over the tile's rows
@@ -667,17 +696,15 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
         UPROF(0, 24);
         e.wait_d();
         UPROF(0, 25);
-        epi_ln256_bwd(e, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, reinterpret_cast<const float *>(scr + SC::XHAT2),
-                      reinterpret_cast<const float *>(scr + SC::RSTD2), reinterpret_cast<const uint32_t *>(scr + SC::KEEP) + 1024, part + CP::VB);
-        e.a_ready();
+        epi_ln256_bwd(e, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, 1, sv2, part + CP::VB);
         UPROF(0, 26);
-        drain_g(e, part + CP::W4 + cr * 128 * 256, 256, 0);
+        drain_g(e, part + CP::W4 + cr * 128 * 256, 128, 0);
+        UPROF(0, 27);
+        drain_g(e, part + CP::W4 + cr * 128 * 256, 128, 128);
         UPROF(0, 28);
         e.wait_d();
         UPROF(0, 29);
-        epi_ln256_bwd(e, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, reinterpret_cast<const float *>(scr + SC::XHAT1),
-                      reinterpret_cast<const float *>(scr + SC::RSTD1), reinterpret_cast<const uint32_t *>(scr + SC::KEEP), part + CP::VA);
-        e.a_ready();
+        epi_ln256_bwd(e, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, 0, sv1, part + CP::VA);
         UPROF(0, 30);
         drain_g(e, part + CP::W0 + cr * 128 * 16, 16, 0);
         UPROF(0, 32);
@@ -766,13 +793,13 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             x[15] = 1.0f;
             store_split_input(e, x, cr == 0 ? scr + SC::XAIMG : nullptr);
         }
-        e.a_ready(); UPROF(1, 1);
-        e.wait_d(); UPROF(1, 2); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 6, scr + SC::A1IMG, abits, abits + 8); e.a_ready(); UPROF(1, 3);
-        e.wait_d(); UPROF(1, 4); epi_hidden128(e, a.actor + AO::B2, ACT_RELU, a.drop, 7, scr + SC::A2IMG, abits + 16, abits + 24); e.a_ready(); UPROF(1, 5);
+        e.a_ready_local(); UPROF(1, 1);
+        e.wait_d(); UPROF(1, 2); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 6, scr + SC::A1IMG, abits, abits + 8); e.a_ready(128); UPROF(1, 3);
+        e.wait_d(); UPROF(1, 4); epi_hidden128(e, a.actor + AO::B2, ACT_RELU, a.drop, 7, scr + SC::A2IMG, abits + 16, abits + 24); e.a_ready(128); UPROF(1, 5);
         e.wait_d(); UPROF(1, 6);
         // relu'(z3) bits of this thread's 8 columns (kept in a register until the backward)
         const uint32_t pos3 = epi_hidden64(e, a.actor + AO::B3, scr + SC::A3IMG);
-        e.a_ready(); UPROF(1, 7);
+        e.a_ready(64); e.publish_saved(); UPROF(1, 7);
         e.wait_d(); UPROF(1, 8);
         e.wait_afree();
         if (e.wg == 0) {
@@ -800,17 +827,15 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             const float ssd = warp_sum(sd);
             if (e.lane == 0) e.cs()[(2 * 4 + e.wq) * 256 + 2] = ssd;
         }
-        __threadfence();
-        e.a_ready(); UPROF(1, 9);
+        e.a_ready_local(); UPROF(1, 9);
         // ---- Q(s, a, e) with the updated critic ----
         e.wait_d(); UPROF(1, 10);
-        epi_ln256(e, nullptr, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, 8, reinterpret_cast<float *>(scr + SC::XHAT1),
-                  reinterpret_cast<float *>(scr + SC::RSTD1), reinterpret_cast<uint32_t *>(scr + SC::KEEP), nullptr);
-        e.a_ready(); UPROF(1, 11);
+        uint32_t sv1[2], sv2[2];
+        epi_ln256(e, nullptr, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, 8, 0, sv1, nullptr);
+        UPROF(1, 11);
         e.wait_d(); UPROF(1, 12);
-        epi_ln256(e, a.critic + CO::B4, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, 9, reinterpret_cast<float *>(scr + SC::XHAT2),
-                  reinterpret_cast<float *>(scr + SC::RSTD2), reinterpret_cast<uint32_t *>(scr + SC::KEEP) + 1024, nullptr);
-        e.a_ready(); UPROF(1, 13);
+        epi_ln256(e, a.critic + CO::B4, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, 9, 1, sv2, nullptr);
+        UPROF(1, 13);
         e.wait_d(); UPROF(1, 14);
         {
             float h3[16], dz3[16];
@@ -822,7 +847,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             e.wait_afree();
             e.img_store8_pair(128, c0, dz3);
             e.img_store8_pair(128, c0 + 8, dz3 + 8);
-            e.a_ready(); UPROF(1, 15);
+            e.a_ready(128); UPROF(1, 15);
             if (e.wg == 0) {
                 const float sq = warp_sum(valid ? q2 : 0.f);
                 if (e.lane == 0) e.cs()[(2 * 4 + e.wq) * 256 + 3] = sq;
@@ -836,13 +861,11 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             bar_epi();
         }
         e.wait_d(); UPROF(1, 16);
-        epi_ln256_bwd(e, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, reinterpret_cast<const float *>(scr + SC::XHAT2),
-                      reinterpret_cast<const float *>(scr + SC::RSTD2), reinterpret_cast<const uint32_t *>(scr + SC::KEEP) + 1024, nullptr);
-        e.a_ready(); UPROF(1, 17);
+        epi_ln256_bwd(e, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, 1, sv2, nullptr);
+        UPROF(1, 17);
         e.wait_d(); UPROF(1, 18);
-        epi_ln256_bwd(e, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, reinterpret_cast<const float *>(scr + SC::XHAT1),
-                      reinterpret_cast<const float *>(scr + SC::RSTD1), reinterpret_cast<const uint32_t *>(scr + SC::KEEP), nullptr);
-        e.a_ready(); UPROF(1, 19);
+        epi_ln256_bwd(e, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, 0, sv1, nullptr);
+        UPROF(1, 19);
         e.wait_d(); UPROF(1, 20);
         // ---- actor backward ----
         e.wait_afree();
@@ -885,7 +908,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             e.colsum_stage<32>(0, 0, prod);                     // d emotion_weights [3][10]
             e.colsum_stage<32>(1, 0, db4);
         }
-        e.a_ready(); UPROF(1, 21);
+        e.a_ready_local(); UPROF(1, 21);
         bar_epi();
         if (cr == 0) {
             e.colsum_finish(0, 32, part + AP::EW);
@@ -902,7 +925,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             for (int j = 0; j < 8; ++j) v[j] = ((pos3 >> j) & 1u) ? v[j] : 0.f;
             e.wait_afree();
             e.img_store8_pair(64, c0, v);
-            e.a_ready(); UPROF(1, 24);
+            e.a_ready(64); UPROF(1, 24);
             e.colsum_stage<8>(0, cl, v);
             bar_epi();
             e.colsum_finish(0, 32, part + AP::B3 + cr * 32);
@@ -921,7 +944,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             e.wait_afree();
             e.img_store8_pair(128, c0, v);
             e.img_store8_pair(128, c0 + 8, v + 8);
-            e.a_ready(); UPROF(1, 27);
+            e.a_ready(128); UPROF(1, 27);
             e.colsum_stage<16>(0, cl, v);
             bar_epi();
             e.colsum_finish(0, 64, part + AP::B2 + cr * 64);
@@ -940,7 +963,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             e.wait_afree();
             e.img_store8_pair(128, c0, v);
             e.img_store8_pair(128, c0 + 8, v + 8);
-            e.a_ready(); UPROF(1, 30);
+            e.a_ready(128); UPROF(1, 30);
             e.colsum_stage<16>(0, cl, v);
             bar_epi();
             e.colsum_finish(0, 64, part + AP::B1 + cr * 64);

@@ -10,11 +10,14 @@
 //
 //   roles      16 epilogue warps per CTA (4 warpgroups; warpgroup g of CTA c owns the eighth [(4c + g) N/8, +N/8) of the columns of
 //              every row, thread r of a warpgroup owns row r = TMEM lane r), 1 MMA-issuer warp, 1 bulk-copy producer warp.
-//   pair sync  a_ready: every epilogue warp fences its generic-proxy writes (local + remote) for the async proxy and arrives on the
-//              barrier of BOTH CTAs (count 32); a_free: each issuer multicasts a tcgen05.commit to both CTAs after its last MMA that
-//              reads the current image, and the epilogues wait for both before they overwrite it; row statistics (LayerNorm, head)
-//              are exchanged as 8 partials per row through both CTAs' shared memory behind an mbarrier
-//              (tools/umma_pair_probe.cu, profiles/r02f_umma_pair_probe.txt).
+//   pair sync  a_ready: the epilogue threads write their half of the image into their OWN shared memory, fence it for the async proxy
+//              and meet at a named barrier; 16 threads then push the half to the peer with cp.async.bulk shared::cta ->
+//              shared::cluster (one 8-row group each), counted in bytes on the peer's a_ready barrier, which the peer's issuer waits on:
+//              no remote generic stores, no cluster-scope fences on the epilogue's critical path.  a_free: each issuer multicasts
+//              a tcgen05.commit to both CTAs after its last MMA that reads the current image, and the epilogues wait for both before
+//              they overwrite it.  Row statistics (LayerNorm, head) are exchanged as 8 partials per row with st.async (8 bytes per
+//              thread, counted on the peer's mbarrier).  Saved global images are published once per kernel (h_pub) before the
+//              producers bulk-load them (tools/umma_pair_probe.cu, profiles/r02f_umma_pair_probe.txt).
 //   operands   activations / gradients are written by the row owners as bf16 "images" in the canonical no-swizzle K-major
 //              core-matrix layout (8 rows x 16 bytes) into shared memory (IMG_A).  The SAME image is the K-major A operand of the
 //              next layer and the MN-major operand of the weight-gradient GEMM dW = dZ^T X (K = rows); the SAME weight image
@@ -57,15 +60,17 @@ constexpr int SM_CS = SM_RED + 2 * 2 * NWG * TR * 2 * 4; // float cs[3][4 warps]
 constexpr int SM_ROW = SM_CS + 3 * 4 * 256 * 4;        // float rowv[4][TR]: per-row scalars handed between layers (tq, dq, ...)
 constexpr int SM_STAT = SM_ROW + 4 * TR * 4;           // float stat[8]: batch emotion statistics; scratch[64]
 constexpr int SM_BAR = SM_STAT + 128 * 4;
-constexpr int NBAR = 2 * NSTAGE + 9;                   // w_full[2] w_empty[2] h_full h_free d_full g_full g_free a_ready a_free xred[2]
+constexpr int NBAR = 2 * NSTAGE + 10;                  // w_full[2] w_empty[2] h_full h_free d_full g_full g_free a_ready a_free xred[2] h_pub
 constexpr int SM_TMEM = SM_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = SM_TMEM + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory plan exceeds the 227 KB opt-in limit");
 
-enum { BW_FULL = 0, BW_EMPTY = NSTAGE, B_HFULL = 2 * NSTAGE, B_HFREE, B_DFULL, B_GFULL, B_GFREE, B_AREADY, B_AFREE, B_XRED };
+enum { BW_FULL = 0, BW_EMPTY = NSTAGE, B_HFULL = 2 * NSTAGE, B_HFREE, B_DFULL, B_GFULL, B_GFREE, B_AREADY, B_AFREE, B_XRED, B_XRED1, B_HPUB };
 constexpr uint16_t PAIR_MASK = 3;
 
-constexpr uint32_t TM_D = 0, TM_G = 256;               // TMEM columns: main accumulators | weight-gradient accumulators
+// TMEM columns: main accumulators (this CTA's <= 128 output columns) | xhat of LayerNorm 1 | weight-gradient accumulators (<= 128
+// columns per block) | xhat of LayerNorm 2   (xhat: what the LayerNorm backward needs, kept on chip from the forward)
+constexpr uint32_t TM_D = 0, TM_X1 = 128, TM_G = 256, TM_X2 = 384;
 
 // ---- image geometry ------------------------------------------------------------------------------------------------
 // activation image of F features: element (row r, feature f)
@@ -188,7 +193,7 @@ __device__ __forceinline__ void ring_consume_end(Pipe &p, uint32_t stage) {
 
 // The image in IMG_A is complete in BOTH CTAs (issuer side of Epi::a_ready).
 __device__ __forceinline__ void wait_a_ready(Pipe &p) {
-    mbar_wait_cluster(p.bar(B_AREADY), p.a_n & 1u);
+    mbar_wait(p.bar(B_AREADY), p.a_n & 1u);
     ++p.a_n;
     tc_fence_after();
 }
@@ -255,6 +260,7 @@ __device__ __forceinline__ void gemm_bwd(Pipe &p, const uint8_t *wimg, int Kout,
 template <int ROLE>
 __device__ __forceinline__ void load_h(Pipe &p, const uint8_t *src, uint32_t bytes) {
     if (ROLE != ROLE_PRODUCER) return;
+    if (p.h_n == 0) mbar_wait_cluster(p.bar(B_HPUB), 0);            // the epilogues of both CTAs have published the saved images (Epi::publish_saved)
     mbar_wait(p.bar(B_HFREE), (p.h_n & 1u) ^ 1u);
     mbar_arrive_expect_tx(p.bar(B_HFULL), bytes);
     bulk_g2s(p.smem + SM_IMG_H, src, bytes, p.bar(B_HFULL));
@@ -302,6 +308,7 @@ struct Epi {
     __device__ int mrow() const { return row0 + r < B ? row0 + r : 0; }      // row index that is always in range (mask / counter lookups)
     __device__ uint32_t td(int col) const { return tbase + TM_D + lane_base + (uint32_t)col; }
     __device__ uint32_t tg(int col) const { return tbase + TM_G + lane_base + (uint32_t)col; }
+    __device__ uint32_t tx(int layer, int col) const { return tbase + (layer ? TM_X2 : TM_X1) + lane_base + (uint32_t)col; }
     __device__ uint32_t peer_bar(int i) const { return peer + (uint32_t)(SM_BAR + i * 8); }
 
     // Before the first store of a new image into IMG_A: the MMAs of BOTH CTAs have read the previous one (Pipe: image_consumed).
@@ -310,13 +317,33 @@ struct Epi {
         if (img_n > 0) mbar_wait_cluster(bars + B_AFREE, (img_n - 1) & 1u);
         ++img_n;
     }
-    // the image in IMG_A of both CTAs is complete as far as this warp is concerned (generic-proxy writes fenced for the async proxy:
-    // shared, peer shared and the global copies the bulk loads read back) and this thread's TMEM reads have retired
-    __device__ void a_ready() {
-        asm volatile("fence.proxy.async;" ::: "memory");
+    // The image of F features in IMG_A is complete on this CTA's side: generic-proxy writes fenced for the async proxy, TMEM reads
+    // retired, all epilogue threads met.  Then this CTA's half [cr F/2, +F/2) goes to the peer (one bulk copy per 8-row group, counted
+    // on the peer's barrier) and this CTA's barrier expects the peer's half.
+    __device__ void a_ready(int F) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
+        bar_epi();
+        const uint32_t half = (uint32_t)F * 8u;                   // bytes of F / 2 features of 8 rows
+        if (tid < TR / 8) {
+            const uint32_t o = (uint32_t)SM_IMG_A + (uint32_t)tid * 2u * half + (uint32_t)cr * half;
+            bulk_s2peer(peer + o, smem + o, half, peer_bar(B_AREADY));
+        }
+        if (tid == 0) mbar_arrive_expect_tx(bars + B_AREADY, (uint32_t)(TR / 8) * half);
+    }
+    // the same for an image this CTA built alone (the narrow input images, dz4): nothing is exchanged
+    __device__ void a_ready_local() {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        bar_epi();
+        if (tid == 0) mbar_arrive(bars + B_AREADY);
+    }
+    // Once per kernel, after the last global store of a saved image / input image: every warp of both CTAs releases its stores at
+    // cluster scope (and fences them for the async proxy); the producers wait for all 32 warps before the first bulk load (load_h).
+    __device__ void publish_saved() {
+        asm volatile("fence.proxy.async.global;" ::: "memory");
         __syncwarp();
-        if (lane == 0) { mbar_arrive_cluster(smem_u32(bars + B_AREADY)); mbar_arrive_cluster(peer_bar(B_AREADY)); }
+        if (lane == 0) { mbar_arrive_cluster(peer_bar(B_HPUB)); mbar_arrive_cluster(smem_u32(bars + B_HPUB)); }
     }
     __device__ void wait_d() { mbar_wait(bars + B_DFULL, d_n & 1u); ++d_n; tc_fence_after(); }
     __device__ void wait_g() { mbar_wait(bars + B_GFULL, g_n & 1u); ++g_n; tc_fence_after(); }
@@ -326,17 +353,19 @@ struct Epi {
         if (lane == 0) mbar_arrive(bars + B_GFREE);
     }
     // sum of (a, b) over the 2 x 4 warpgroups' threads of this row; every thread of the row — in both CTAs — gets the same totals
-    // (added in (CTA, warpgroup) order).  Two buffers and two barriers alternate, so a warp that runs ahead cannot disturb the
-    // exchange the others are still reading.
+    // (added in (CTA, warpgroup) order).  The partial goes into this CTA's buffer with a plain store and into the peer's with
+    // st.async, counted on the peer's barrier (16 warp arrivals + 512 x 8 bytes).  Two buffers and two barriers alternate, so a warp
+    // that runs ahead cannot disturb the exchange the others are still reading.
     __device__ void row_allreduce2(float &a, float &b) {
         const uint32_t buf = red_n & 1u, par = (red_n >> 1) & 1u;
         ++red_n;
         const uint32_t o = (buf * (2 * NWG * TR) + (uint32_t)((cr * NWG + wg) * TR + r)) * 2u;
         float *rd = red();
         *reinterpret_cast<float2 *>(rd + o) = make_float2(a, b);
-        st_cluster_f32x2(peer + (uint32_t)SM_RED + o * 4u, a, b);
+        st_async_f32x2(peer + (uint32_t)SM_RED + o * 4u, a, b, peer_bar(B_XRED + (int)buf));
         __syncwarp();
-        if (lane == 0) { mbar_arrive_cluster(smem_u32(bars + B_XRED + buf)); mbar_arrive_cluster(peer_bar(B_XRED + (int)buf)); }
+        if (tid == 0) mbar_arrive_expect_tx(bars + B_XRED + buf, (uint32_t)NEPI * 8u);
+        else if (lane == 0) mbar_arrive(bars + B_XRED + buf);
         mbar_wait_cluster(bars + B_XRED + buf, par);
         float sa = 0.f, sb = 0.f;
 #pragma unroll
@@ -346,21 +375,21 @@ struct Epi {
         }
         a = sa; b = sb;
     }
-    // 8 consecutive features [f0, f0 + 8) of this thread's row into an image of F features: a global copy / this CTA's IMG_A only ...
+    // 8 consecutive features [f0, f0 + 8) of this thread's row into an image of F features: a global copy, or this CTA's IMG_A (the
+    // peer receives this CTA's half with a_ready)
     __device__ void img_store8(uint8_t *img, int F, int f0, const float *v) const {
         uint4 q;
         q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
         *reinterpret_cast<uint4 *>(img + img_off(r, f0, F)) = q;
     }
-    // ... or IMG_A of both CTAs (and optionally a global copy)
     __device__ void img_store8_pair(int F, int f0, const float *v, uint8_t *gimg = nullptr) const {
         uint4 q;
         q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
         const uint32_t o = img_off(r, f0, F);
         *reinterpret_cast<uint4 *>(smem + SM_IMG_A + o) = q;
-        st_cluster_v4(peer + (uint32_t)SM_IMG_A + o, q);
         if (gimg) *reinterpret_cast<uint4 *>(gimg + o) = q;
     }
+    __device__ void img_store_pair_q(int F, int f0, uint4 q) const { *reinterpret_cast<uint4 *>(smem + SM_IMG_A + img_off(r, f0, F)) = q; }
     // column sums over the tile's 128 rows, stage 1: v[W] are this thread's values for the CTA-local columns [c0, c0 + W)
     // -> cs[slot][wq][c0 + column]
     template <int W>

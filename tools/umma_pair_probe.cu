@@ -23,27 +23,12 @@ __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("m
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 q) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+// push `bytes` of this CTA's shared memory to the peer's (async proxy on both sides), completion counted on the peer's mbarrier
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster, const void *src, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster), "r"(smem_u32(src)),
+                 "r"(bytes), "r"(bar_cluster) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-// arrive on the mbarrier at the same shared-memory offset in every CTA of `mask` once all MMAs issued so far have completed
-__device__ __forceinline__ void mma_commit_mc(uint64_t *bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
+template <int kPush>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(160) probe(const uint8_t *X0, const uint8_t *Wimg, float *Xout, long long *cycles) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *sA = smem, *sB = smem + M * F * 2;           // A image [128][F]; B = this CTA's NH weight rows [NH][F]
@@ -55,7 +40,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(160) probe(const uin
     // weight rows [cr NH, +NH): contiguous in the K-major image (row groups of 8)
     for (int i = tid; i < NH * F * 2 / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(Wimg + (size_t)cr * NH * F * 2)[i];
-    if (tid == 0) { mbar_init(&bar_d, 1); mbar_init(&bar_a, 8); mbar_init(&bar_free, 2); mbar_fence_init(); }
+    if (tid == 0) { mbar_init(&bar_d, 1); mbar_init(&bar_a, kPush ? 1 : 8); mbar_init(&bar_free, 2); mbar_fence_init(); }
     if (warp == 4) tmem_alloc(&tmem_slot, 64);
     asm volatile("fence.proxy.async;" ::: "memory");
     tc_fence_before();
@@ -101,13 +86,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(160) probe(const uin
                     q.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); q.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
                     const uint32_t o = (row >> 3) * (F >> 3) * 128 + ((cr * NH + c * 16 + g * 8) >> 3) * 128 + (row & 7) * 16;
                     *reinterpret_cast<uint4 *>(sA + o) = q;
-                    st_cluster_v4(peerA + o, q);
+                    if (!kPush) st_cluster_v4(peerA + o, q);
                 }
             }
-            asm volatile("fence.proxy.async;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { mbar_arrive_cluster(smem_u32(&bar_a)); mbar_arrive_cluster(peer_bar); }
+            if (kPush) {
+                // local half complete -> one bulk copy per 8-row group pushes it into the peer's image; the peer's a_ready counts the bytes
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tc_fence_before();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const uint32_t half_bytes = (NH / 8) * 128;
+                if (tid < M / 8) {
+                    const uint32_t o = tid * (F >> 3) * 128 + (cr * NH >> 3) * 128;
+                    bulk_s2peer(peerA + o, sA + o, half_bytes, peer_bar);
+                }
+                if (tid == 0) mbar_arrive_expect_tx(&bar_a, (M / 8) * half_bytes);
+            } else {
+                asm volatile("fence.proxy.async;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive_cluster(smem_u32(&bar_a)); mbar_arrive_cluster(peer_bar); }
+            }
         }
     }
     const long long t1 = clock64();
@@ -139,11 +137,13 @@ int main() {
     cudaMalloc(&dX, Xi.size()); cudaMalloc(&dW, Wi.size()); cudaMalloc(&dO, M * F * 4); cudaMalloc(&dC, 16 * 8);
     cudaMemcpy(dX, Xi.data(), Xi.size(), cudaMemcpyHostToDevice); cudaMemcpy(dW, Wi.data(), Wi.size(), cudaMemcpyHostToDevice);
     const int smem = M * F * 2 + NH * F * 2;
-    cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int rc = 0;
-    for (int rep = 0; rep < 3; ++rep) {
+    cudaFuncSetAttribute(probe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int rep = 0; rep < 6; ++rep) {
         cudaMemset(dO, 0, M * F * 4);
-        probe<<<2, 160, smem>>>(dX, dW, dO, dC);
+        if (rep & 1) probe<1><<<2, 160, smem>>>(dX, dW, dO, dC); else probe<0><<<2, 160, smem>>>(dX, dW, dO, dC);
+        printf("%s: ", (rep & 1) ? "bulk push " : "remote st ");
         cudaError_t e = cudaDeviceSynchronize();
         std::vector<float> O(M * F); long long cyc[2];
         cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost); cudaMemcpy(cyc, dC, 16, cudaMemcpyDeviceToHost);

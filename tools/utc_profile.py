@@ -29,16 +29,16 @@ L.lib().erlfill_debug_utc_profile(out)
 t = np.array(out[:128], dtype=np.int64)
 names = ["start", "stats", "T0 img", "T1 mma", "T1 epi", "T2 mma", "T2 epi", "T3 mma", "T3 epi", "T4 mma", "T4 head", "T5 mma", "T5 ln", "T6 mma", "T6 ln", "T7 mma",
          "T7 head", "C0 img", "C1 mma", "C1 ln+save", "C2 mma", "C2 ln+save", "C3 mma", "C3 loss", "dW8 drain", "B3 mma", "B3 lnbwd", "dW4a drain", "dW4b drain",
-         "B2 mma", "B2 lnbwd", "dW0a", "dW0b"]
-print("B = %d, ddpg_critic_grad_tc: cycles since kernel start / delta (CTA 0; the target chain T* runs on its own CTAs in the split launch)" % B)
+         "B2 mma", "B2 lnbwd", "(unused)", "dW0 drain"]
+print("B = %d, ddpg_critic_grad_tc: cycles since kernel start / delta (CTA 0 of pair 0; the target chain T* runs on its own pairs in the split launch)" % B)
 for i in range(1, 33):
-    if t[i] > 0 and t[i - 1] > 0:
-        print("%2d %-12s %9d %8d" % (i, names[i], t[i] - t[0], t[i] - t[i - 1]))
-    elif t[i] > 0:
-        print("%2d %-12s %9d" % (i, names[i], t[i] - t[0]))
+    prev = max([t[j] for j in range(i) if t[j] > 0] or [0])
+    if t[i] > 0 and prev > 0:
+        print("%2d %-12s %9d %8d" % (i, names[i], t[i] - t[0], t[i] - prev))
 t = np.array(out[128:256], dtype=np.int64)
 an = ["start", "A0 img", "A1 mma", "A1 epi", "A2 mma", "A2 epi", "A3 mma", "A3 epi", "A4 mma", "A4 head", "C1 mma", "C1 ln", "C2 mma", "C2 ln", "C3 mma", "C3 dz3",
       "B3 mma", "B3 lnbwd", "B2 mma", "B2 lnbwd", "dx0 mma", "dz4", "dW4 drain", "da3 mma", "da3", "dW3 drain", "da2 mma", "da2", "dW2 drain", "da1 mma", "da1", "dW1 drain"]
 print("ddpg_actor_grad_tc")
 for i in range(1, 32):
     print("%2d %-12s %9d %8d" % (i, an[i], t[i] - t[0], t[i] - t[i - 1]))
+
