@@ -82,6 +82,25 @@ __device__ __forceinline__ void setup(uint8_t *smem, uint64_t *bars, uint32_t *t
     tc_fence_after();
 }
 
+// The small fp32 vectors the epilogues read (biases, LayerNorm gamma / beta, head weights) into L1 while the first layers run: their
+// first touch would otherwise cost every epilogue an L2 round trip.
+__device__ __forceinline__ void prefetch_floats(const float *p, int n, int t, int &t0) {
+    const int lines = (n * 4 + 127) / 128 + 1, i = t - t0;
+    if (i >= 0 && i < lines) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i * 32));
+    t0 += lines;
+}
+__device__ __forceinline__ void prefetch_critic_vectors(const float *P, int tid, int &t0) {
+    prefetch_floats(P + CO::G1, CO::W4 - CO::G1, tid, t0);
+    prefetch_floats(P + CO::B4, CO::W8 - CO::B4, tid, t0);
+    prefetch_floats(P + CO::B8, CO::TOTAL - CO::B8, tid, t0);
+}
+__device__ __forceinline__ void prefetch_actor_vectors(const float *P, int tid, int &t0) {
+    prefetch_floats(P + AO::EW, 30, tid, t0);
+    prefetch_floats(P + AO::B2, 128, tid, t0);
+    prefetch_floats(P + AO::B3, 64, tid, t0);
+    prefetch_floats(P + AO::B4, 10, tid, t0);
+}
+
 // batch mean / unbiased std of the three emotion columns (Critic.forward, ddpg_agent.py:176), by the epilogue threads of every CTA
 // (recomputing 3 x B values per CTA is cheaper than a grid-wide dependency); loads unrolled so that their latencies overlap
 __device__ __forceinline__ void emotion_stats(Epi &e, const float *batch, float *mean_out) {
@@ -525,6 +544,11 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
         const bool valid = e.valid();
         const float *row = a.batch + (size_t)(valid ? grow : 0) * ERLFILL_REC;
         float *part = a.cpart + (size_t)tile * CP::SIZE;
+        {
+            int t0 = 0;
+            if (chain != 2) { prefetch_actor_vectors(a.actor_t, e.tid, t0); prefetch_critic_vectors(a.critic_t, e.tid, t0); }
+            if (chain != 1) prefetch_critic_vectors(a.critic, e.tid, t0);
+        }
         UPROF(0, 0);
         if (chain != 1 && a.stats_ext) {
             // the minibatch came with its emotion sums: warp c adds column c of the rows (lane l takes rows l, l + 32, ..., then a butterfly:
@@ -690,22 +714,23 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
             }
             bar_epi();
         }
-        // ---- backward ----
+        // ---- backward ----  (every weight-gradient block is drained right AFTER the next image has been handed over, while the next
+        // input-gradient GEMM runs; the order keeps every drain ahead of the a_free its successor's GEMMs depend on)
         UPROF(0, 23);
-        drain_g(e, part + CP::W8, 128, cr * 128);
-        UPROF(0, 24);
         e.wait_d();
         UPROF(0, 25);
         epi_ln256_bwd(e, a.critic + CO::G2, a.critic + CO::BE2, ACT_RELU, a.drop, 1, sv2, part + CP::VB);
         UPROF(0, 26);
+        drain_g(e, part + CP::W8, 128, cr * 128);
+        UPROF(0, 24);
         drain_g(e, part + CP::W4 + cr * 128 * 256, 128, 0);
         UPROF(0, 27);
-        drain_g(e, part + CP::W4 + cr * 128 * 256, 128, 128);
-        UPROF(0, 28);
         e.wait_d();
         UPROF(0, 29);
         epi_ln256_bwd(e, a.critic + CO::G1, a.critic + CO::BE1, ACT_LEAKY, a.drop, 0, sv1, part + CP::VA);
         UPROF(0, 30);
+        drain_g(e, part + CP::W4 + cr * 128 * 256, 128, 128);
+        UPROF(0, 28);
         drain_g(e, part + CP::W0 + cr * 128 * 16, 16, 0);
         UPROF(0, 32);
         }
@@ -765,6 +790,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
         // [row][32 words]: pos1 x8 | keep1 x8 | pos2 x8 | keep2 x8, word (4 cr + wg) = this thread's 16 columns
         uint32_t *abits = reinterpret_cast<uint32_t *>(scr + SC::ABITS) + e.r * 32 + (cr * 4 + e.wg);
         float *aux = reinterpret_cast<float *>(scr + SC::AUX) + (size_t)cr * 64 * TR + e.r;      // [64][128 rows], one copy per CTA
+        { int t0 = 0; prefetch_actor_vectors(a.actor, e.tid, t0); prefetch_critic_vectors(a.critic, e.tid, t0); }
         // L2 norms of the nine actor tensors (actor_loss += 1e-4 sum ||theta_t||, ddpg_agent.py:490-494), spread over the CTAs
         for (int t = blockIdx.x; t < 9; t += gridDim.x) {
             float qn = 0.f;
@@ -915,7 +941,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             e.colsum_finish(1, 16, part + AP::B4);
         }
         bar_epi();
-        drain_g(e, part + AP::W4, 32, cr * 32); UPROF(1, 22);
+        // (each weight-gradient block is drained after the NEXT image has been handed over, while the next GEMM runs)
         e.wait_d(); UPROF(1, 23);
         {   // da3 = dz4 W4 (this CTA's 32 inputs, 8 per thread), relu'
             float v[8];
@@ -931,7 +957,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             e.colsum_finish(0, 32, part + AP::B3 + cr * 32);
             bar_epi();
         }
-        drain_g(e, part + AP::W3, 64, cr * 64); UPROF(1, 25);
+        drain_g(e, part + AP::W4, 32, cr * 32); UPROF(1, 22);
         e.wait_d(); UPROF(1, 26);
         {   // da2 = dz3 W3 (this CTA's 64 inputs, 16 per thread), dropout (site 7), relu'
             float v[16];
@@ -950,7 +976,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             e.colsum_finish(0, 64, part + AP::B2 + cr * 64);
             bar_epi();
         }
-        drain_g(e, part + AP::W2, 64, cr * 64); UPROF(1, 28);
+        drain_g(e, part + AP::W3, 64, cr * 64); UPROF(1, 25);
         e.wait_d(); UPROF(1, 29);
         {   // da1 = dz2 W2, dropout (site 6), leaky'
             float v[16];
@@ -969,6 +995,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             e.colsum_finish(0, 64, part + AP::B1 + cr * 64);
             bar_epi();
         }
+        drain_g(e, part + AP::W2, 64, cr * 64); UPROF(1, 28);
         drain_g(e, cr == 0 ? part + AP::W1 : nullptr, 16, 0); UPROF(1, 31);
         UTC_EPI_DONE
     }
@@ -1011,28 +1038,46 @@ __device__ __forceinline__ int actor_flat_index(int p) {
 // G[i] = sum over the CTAs' partials in CTA order (+ the L2-norm regulariser's gradient 1e-4 theta / ||theta_tensor|| for the actor);
 // the blocks walk the partial layout (coalesced reads), block b also leaves the sum of squares of its slice (clip_grad_norm_) and
 // block 0 the loss value.
-constexpr int kRedBlocks = 4 * mlp::kSumsqBlocks;      // 256 blocks: the reduction is L2-latency bound, so it wants every SM
+// Four threads share one group of four consecutive positions: thread k adds the 16-byte loads of the tiles k, k + 4, ... (in order), the
+// four sums combine as (s0 + s1) + (s2 + s3) — a fixed order, no atomics — and thread k finishes component k of the group.
+constexpr int kRedThreads = 256, kRedGroups = kRedThreads / 4;
+constexpr int red_blocks(bool actor) { return ((actor ? AP::SQ : CP::LOSS) + 3) / 4 / kRedGroups + 1; }
+constexpr int kRedBlocksMax = red_blocks(false);
 template <bool kActor>
-__global__ void __launch_bounds__(256) grad_reduce_kernel(int n_cta, int B, const float *part, const float *theta, float *scal, float *G, float *ssq) {
+__global__ void __launch_bounds__(kRedThreads) grad_reduce_kernel(int n_cta, int B, const float *part, const float *theta, float *scal, float *G, float *ssq) {
     __shared__ float scratch[32];
     constexpr int np = kActor ? AP::SQ : CP::LOSS, psize = kActor ? AP::SIZE : CP::SIZE;
-    const int per = (np + kRedBlocks - 1) / kRedBlocks;
-    const int p0 = blockIdx.x * per, p1 = min(np, p0 + per);
+    constexpr int nq = (np + 3) / 4;
+    const int k = threadIdx.x & 3, q = blockIdx.x * kRedGroups + (threadIdx.x >> 2);
     float ss = 0.f;
-    for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
-        const int i = kActor ? actor_flat_index(p) : critic_flat_index(p);
-        if (i < 0) continue;
-        const float *q = part + p;
-        float s = 0.f;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < nq) {
+        const float4 *src = reinterpret_cast<const float4 *>(part) + q;
 #pragma unroll 8
-        for (int c = 0; c < n_cta; ++c) s += q[(size_t)c * psize];
-        if (kActor) {
-            int t = 0;
-            while (i >= c_actor_seg[t + 1]) ++t;
-            s += 1e-4f * theta[i] / scal[6 + t];
+        for (int c = k; c < n_cta; c += 4) {
+            const float4 v = __ldcg(src + (size_t)c * (psize / 4));
+            s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
         }
-        G[i] = s;
-        ss = fmaf(s, s, ss);
+    }
+    float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sv[j] += __shfl_xor_sync(0xffffffffu, sv[j], 1);
+        sv[j] += __shfl_xor_sync(0xffffffffu, sv[j], 2);
+    }
+    const int p = 4 * q + k;
+    if (q < nq && p < np) {
+        const int i = kActor ? actor_flat_index(p) : critic_flat_index(p);
+        if (i >= 0) {
+            float sum = k == 0 ? sv[0] : (k == 1 ? sv[1] : (k == 2 ? sv[2] : sv[3]));
+            if (kActor) {
+                int t = 0;
+                while (i >= c_actor_seg[t + 1]) ++t;
+                sum += 1e-4f * theta[i] / scal[6 + t];
+            }
+            G[i] = sum;
+            ss = sum * sum;
+        }
     }
     const float t = mlp::block_sum(ss, scratch);
     if (threadIdx.x == 0) ssq[blockIdx.x] = t;
@@ -1090,7 +1135,7 @@ __device__ __forceinline__ float adam_elem(float &p, float &m, float &v, float g
     p = p - (lr / bc1) * (mi / denom);
     return p;
 }
-// n_ssq sum-of-squares partials: kRedBlocks from grad_reduce_kernel, mlp::kSumsqBlocks from the peer exchange (REDUCED).  Warp 0 of the
+// n_ssq sum-of-squares partials: red_blocks() from grad_reduce_kernel, mlp::kSumsqBlocks from the peer exchange (REDUCED).  Warp 0 of the
 // block adds them (lane l takes partials l, l + 32, ..., then a butterfly: the same order in every block and on every rank) and
 // every thread reads the coefficient from shared memory; all threads of the block must call this.
 __device__ __forceinline__ float clip_coef(const float *ssq, int n_ssq, float max_norm) {
@@ -1151,7 +1196,7 @@ __global__ void actor_apply_kernel(float *p, float *pt, float *m, float *v, cons
 // ---- fast-path workspace tail (behind the exact path's workspace, so buckets / exchange buffers keep their addresses) -------------
 struct Tail {
     uint8_t *img_actor, *img_actor_t, *img_critic, *img_critic_t, *scratch;
-    float *cpart, *apart, *tq_g, *stats_part, *ssq_fine;      // ssq_fine: [2][kRedBlocks]
+    float *cpart, *apart, *tq_g, *stats_part, *ssq_fine;      // ssq_fine: [2][kRedBlocksMax]
     uint32_t *flags;            // two tq_flags per tile, then the two counters of grid_emotion_stats
 };
 static size_t up256(size_t n) { return (n + 255) & ~(size_t)255; }
@@ -1159,7 +1204,7 @@ static int n_cta(int B) { return (B + TR - 1) / TR; }
 size_t tail_bytes(int B) {
     const size_t c = (size_t)n_cta(B);
     return up256((2 * c + 2) * 4) + up256(c * 32) + 2 * up256(AI::BYTES) + 2 * up256(CI::BYTES) + up256(c * SC::BYTES) + up256(c * CP::SIZE * 4) + up256(c * AP::SIZE * 4) +
-           up256((size_t)B * 4) + up256(2 * 4 * 64 * 4);
+           up256((size_t)B * 4) + up256(2 * kRedBlocksMax * 4);
 }
 static void carve_tail(Tail &t, uint8_t *base, int B) {
     const size_t c = (size_t)n_cta(B);
@@ -1263,23 +1308,23 @@ int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const f
     const bool reduced = (phases & ERLFILL_PHASE_REDUCED) != 0;
     if (phases & ERLFILL_PHASE_CRITIC_GRAD) {
         ERLFILL_CUDA_TRY(launch_pairs(ddpg_critic_grad_tc, 2 * (a.split ? 2 * nc : nc), a, st));
-        grad_reduce_kernel<false><<<kRedBlocks, 256, 0, st>>>(nc, B, t.cpart, nullptr, w.scal, w.cgrad, t.ssq_fine);
+        grad_reduce_kernel<false><<<red_blocks(false), kRedThreads, 0, st>>>(nc, B, t.cpart, nullptr, w.scal, w.cgrad, t.ssq_fine);
     }
     if (phases & ERLFILL_PHASE_CRITIC_APPLY) {
         const float *G = reduced ? w.cred : w.cgrad;
         critic_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->critic, n->critic_m, n->critic_v, G, reduced ? w.ssq : t.ssq_fine,
-                                                                     reduced ? mlp::kSumsqBlocks : kRedBlocks, w.step, h->critic_lr, h->actor_lr,
+                                                                     reduced ? mlp::kSumsqBlocks : red_blocks(false), w.step, h->critic_lr, h->actor_lr,
                                                                      h->max_grad_norm, w.scal, t.img_critic);
     }
     if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
         ERLFILL_CUDA_TRY(launch_pairs(ddpg_actor_grad_tc, 2 * nc, a, st));
-        grad_reduce_kernel<true><<<kRedBlocks, 256, 0, st>>>(nc, B, t.apart, n->actor, w.scal, w.agrad, t.ssq_fine + kRedBlocks);
+        grad_reduce_kernel<true><<<red_blocks(true), kRedThreads, 0, st>>>(nc, B, t.apart, n->actor, w.scal, w.agrad, t.ssq_fine + kRedBlocksMax);
     }
     if (phases & ERLFILL_PHASE_ACTOR_APPLY) {
         const float *G = reduced ? w.ared : w.agrad;
         actor_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, n->actor_target, n->actor_m, n->actor_v, G,
-                                                                    reduced ? w.ssq + mlp::kSumsqBlocks : t.ssq_fine + kRedBlocks,
-                                                                    reduced ? mlp::kSumsqBlocks : kRedBlocks, w.step, h->max_grad_norm, h->tau, n->critic, n->critic_target, w.scal, t.img_actor,
+                                                                    reduced ? w.ssq + mlp::kSumsqBlocks : t.ssq_fine + kRedBlocksMax,
+                                                                    reduced ? mlp::kSumsqBlocks : red_blocks(true), w.step, h->max_grad_norm, h->tau, n->critic, n->critic_target, w.scal, t.img_actor,
                                                                     t.img_actor_t, t.img_critic_t, d_report);
     }
     ERLFILL_CUDA_TRY(cudaGetLastError());
