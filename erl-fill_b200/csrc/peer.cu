@@ -50,7 +50,9 @@ __global__ void peer_signal_kernel(const PeerArgs a) {
     for (int p = 0; p < a.world; ++p) st_release_sys(&a.ctrl[p]->flag[a.which][a.rank], e);
 }
 
-__global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerArgs a) {
+constexpr int kPeerThreads = 256;      // the thread / slice geometry of mlp::sumsq_kernel: the norm partials add up in the same order as on the NCCL path
+constexpr int kPeerChunks = 7;         // elements per thread whose loads are all issued before the first use (the NVLink round trips overlap)
+__global__ void __launch_bounds__(kPeerThreads) peer_reduce_kernel(const PeerArgs a) {
     __shared__ float scratch[32];
     PeerCtrl *mine = a.ctrl[a.rank];
     if (threadIdx.x < a.world) {
@@ -74,12 +76,25 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerArgs a) {
     const int i0 = blockIdx.x * per, i1 = blockIdx.x == mlp::kSumsqBlocks - 1 ? a.n : min(a.n_norm, i0 + per);
     const float inv = 1.0f / (float)a.world;
     float ss = 0.f;
-    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        float s = 0.f;
-        for (int q = 0; q < a.world; ++q) s += __ldcg(a.bucket[q] + i);
-        s *= inv;
-        a.out[i] = s;
-        if (i < a.n_norm) ss = fmaf(s, s, ss);
+    for (int base = i0 + threadIdx.x; base < i1; base += kPeerChunks * kPeerThreads) {
+        float v[kPeerChunks][ERLFILL_MAX_PEERS];
+#pragma unroll
+        for (int k = 0; k < kPeerChunks; ++k) {
+            const int i = base + k * kPeerThreads;
+#pragma unroll
+            for (int q = 0; q < ERLFILL_MAX_PEERS; ++q) v[k][q] = (i < i1 && q < a.world) ? __ldcg(a.bucket[q] + i) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kPeerChunks; ++k) {
+            const int i = base + k * kPeerThreads;
+            if (i >= i1) break;
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < ERLFILL_MAX_PEERS; ++q) s += v[k][q];                                        // rank order; absent ranks add +0
+            s *= inv;
+            a.out[i] = s;
+            if (i < a.n_norm) ss = fmaf(s, s, ss);
+        }
     }
     const float t = mlp::block_sum(ss, scratch);
     if (threadIdx.x == 0) a.ssq[blockIdx.x] = t;
@@ -175,7 +190,7 @@ int erlfill_ddpg_peer_allreduce(const erlfill_peer_group *g, int batch, int whic
     a.timeout_cycles = timeout_cycles;
     cudaStream_t st = (cudaStream_t)stream;
     peer_signal_kernel<<<1, 1, 0, st>>>(a);
-    peer_reduce_kernel<<<mlp::kSumsqBlocks, 256, 0, st>>>(a);
+    peer_reduce_kernel<<<mlp::kSumsqBlocks, kPeerThreads, 0, st>>>(a);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
 }

@@ -59,6 +59,9 @@ __constant__ int c_actor_seg[10] = {0, 30, 670, 798, 17182, 17310, 25502, 25566,
 
 // development profile (erlfill_debug_utc_profile): clock64 of CTA 0 at the numbered points of the two phase kernels
 __device__ long long g_utc_prof[2][128];
+__device__ long long g_utc_cta[2][256][4];       // per CTA: globaltimer at entry, after setup, at the end of the epilogue role, at exit
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define UCTA(k, i) do { if (a.prof && threadIdx.x == 0 && blockIdx.x < 256) g_utc_cta[k][blockIdx.x][i] = gtimer(); } while (0)
 #define UPROF(k, i) do { if (a.prof && blockIdx.x == 0 && e.tid == 0) g_utc_prof[k][i] = clock64(); } while (0)
 
 // ---- common prologue / epilogue of the two phase kernels ---------------------------------------------------------------
@@ -526,7 +529,9 @@ __device__ __forceinline__ void critic_program(Pipe &p, const Args &a, const uin
 }
 
 __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
+    UCTA(0, 0);
     UTC_ROLE_PROLOGUE
+    UCTA(0, 1);
     const int n_tiles = (a.B + TR - 1) / TR;
     const int tile = a.split ? pair % n_tiles : pair;
     const int chain = a.split ? (pair >= n_tiles ? 1 : 2) : 0;
@@ -735,8 +740,10 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
         UPROF(0, 32);
         }
         UTC_EPI_DONE
+        UCTA(0, 2);
     }
     UTC_ROLE_EPILOGUE
+    UCTA(0, 3);
 }
 
 // =====================================================================================================================
@@ -771,7 +778,9 @@ __device__ __forceinline__ void actor_program(Pipe &p, const Args &a, const uint
 }
 
 __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
+    UCTA(1, 0);
     UTC_ROLE_PROLOGUE
+    UCTA(1, 1);
     const int tile = pair;
     uint8_t *scr = a.scratch + (size_t)tile * SC::BYTES;
     if (warp == W_PRODUCER) {
@@ -998,8 +1007,10 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
         drain_g(e, part + AP::W2, 64, cr * 64); UPROF(1, 28);
         drain_g(e, cr == 0 ? part + AP::W1 : nullptr, 16, 0); UPROF(1, 31);
         UTC_EPI_DONE
+        UCTA(1, 2);
     }
     UTC_ROLE_EPILOGUE
+    UCTA(1, 3);
 }
 
 }  // namespace utc
@@ -1335,6 +1346,9 @@ int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const f
 }  // namespace erlfill
 
 // development only (not declared in include/erlfill.h): copies the in-kernel profile of CTA 0 (ERLFILL_UTC_PROF=1)
+extern "C" int erlfill_debug_utc_cta(long long *out /*[2][256][4]*/) {
+    return cudaMemcpyFromSymbol(out, erlfill::utc::g_utc_cta, sizeof(long long) * 2048) == cudaSuccess ? 0 : -2;
+}
 extern "C" int erlfill_debug_utc_profile(long long *out /*[2][128]*/) {
     return cudaMemcpyFromSymbol(out, erlfill::utc::g_utc_prof, sizeof(long long) * 256) == cudaSuccess ? 0 : -2;
 }

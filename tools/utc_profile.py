@@ -24,6 +24,13 @@ ne = torch.tensor([0.4, 0.5, 0.2], device="cuda")
 for _ in range(3):
     lrn.update(batch, ne, 1)
 torch.cuda.synchronize()
+if os.environ.get("UTC_COLD") == "1":      # the update as bench.py times it: on a cold L2
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush.fill_(1)
+    torch.cuda.synchronize()
+    lrn.update(batch, ne, 1)
+    torch.cuda.synchronize()
+    print("COLD L2")
 out = (C.c_longlong * 256)()
 L.lib().erlfill_debug_utc_profile(out)
 t = np.array(out[:128], dtype=np.int64)
@@ -42,3 +49,16 @@ print("ddpg_actor_grad_tc")
 for i in range(1, 32):
     print("%2d %-12s %9d %8d" % (i, an[i], t[i] - t[0], t[i] - t[i - 1]))
 
+
+cta = (C.c_longlong * 2048)()
+L.lib().erlfill_debug_utc_cta(cta)
+c = np.array(cta[:], dtype=np.int64).reshape(2, 256, 4)
+for k, name in ((0, "critic"), (1, "actor")):
+    used = c[k][:, 0] > 0
+    t0 = c[k][used, 0].min()
+    d = (c[k][used] - t0) / 1000.0
+    print("%s kernel, %d CTAs, microseconds since the first CTA entered: entry min/max %.1f/%.1f  after setup %.1f/%.1f  epilogue done %.1f/%.1f  exit %.1f/%.1f"
+          % (name, used.sum(), d[:, 0].min(), d[:, 0].max(), d[:, 1].min(), d[:, 1].max(), d[:, 2].min(), d[:, 2].max(), d[:, 3].min(), d[:, 3].max()))
+    if k == 0:
+        n = used.sum() // 2
+        print("   critic-chain CTAs epilogue done %.1f..%.1f, target-chain CTAs %.1f..%.1f" % (d[:n, 2].min(), d[:n, 2].max(), d[n:, 2].min(), d[n:, 2].max()))
