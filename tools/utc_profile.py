@@ -24,9 +24,14 @@ ne = torch.tensor([0.4, 0.5, 0.2], device="cuda")
 for _ in range(3):
     lrn.update(batch, ne, 1)
 torch.cuda.synchronize()
-if os.environ.get("UTC_COLD") == "1":      # the update as bench.py times it: on a cold L2
+if os.environ.get("UTC_COLD") in ("1", "2"):      # the update as bench.py times it: on a cold L2 (1: L2 full of dirty lines, 2: clean lines)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     flush.fill_(1)
+    torch.cuda.synchronize()
+    if os.environ.get("UTC_COLD") == "2":
+        big = torch.ones(256 << 18, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        print(float(big.sum()))
     torch.cuda.synchronize()
     lrn.update(batch, ne, 1)
     torch.cuda.synchronize()
