@@ -27,7 +27,7 @@ constexpr int ACT_LEAKY = 0, ACT_RELU = 1;
 namespace SC {
 constexpr size_t X0IMG = 0, H1IMG = X0IMG + 12288, H2IMG = H1IMG + 65536, XAIMG = H2IMG + 65536, A1IMG = XAIMG + 12288, A2IMG = A1IMG + 32768,
                  A3IMG = A2IMG + 32768, ABITS = A3IMG + 16384 /* [128][32] words */, AUX = ABITS + 16384 /* [2 CTAs][64][128] floats */,
-                 BYTES = AUX + 65536;
+                 XCIMG = AUX + 65536 /* critic input image (s, actor(s), e) */, POS3 = XCIMG + 12288 /* [2 CTAs][512] words */, BYTES = POS3 + 4096;
 }
 
 struct Args {
@@ -496,7 +496,16 @@ __device__ __forceinline__ void drain_g(Epi &e, float *dst, int n, int col0) {
 // =====================================================================================================================
 // CRITIC_GRAD
 // =====================================================================================================================
-// part: 0 = the whole phase in one pair, 1 = target chain only, 2 = everything but the target chain
+// a = actor(s, e) of ACTOR_GRAD does not depend on the critic update: it runs inside CRITIC_GRAD, on the pairs of the target chain once
+// they have handed over Q' (they finish long before the critic chain's backward), or at the end of the unsplit phase
+template <int ROLE>
+__device__ __forceinline__ void actor_forward_program(Pipe &p, const Args &a) {
+    gemm_fwd<ROLE>(p, a.img_actor + AI::W1, 128, 48);
+    gemm_fwd<ROLE>(p, a.img_actor + AI::W2, 128, 128);
+    gemm_fwd<ROLE>(p, a.img_actor + AI::W3, 64, 128);
+    gemm_fwd<ROLE>(p, a.img_actor + AI::W4, 16, 64, false);
+}
+// part: 0 = the whole phase in one pair, 1 = target chain (+ the actor forward), 2 = everything but the target chain
 template <int ROLE>
 __device__ __forceinline__ void critic_program(Pipe &p, const Args &a, const uint8_t *scr, int part) {
     const int cr = (int)p.cr;
@@ -509,7 +518,7 @@ __device__ __forceinline__ void critic_program(Pipe &p, const Args &a, const uin
         gemm_fwd<ROLE>(p, a.img_critic_t + CI::W4, 256, 256);
         gemm_fwd<ROLE>(p, a.img_critic_t + CI::W8, 128, 256);
     }
-    if (part == 1) return;
+    if (part == 1) { actor_forward_program<ROLE>(p, a); return; }
     // Q(s, a_norm, e)
     gemm_fwd<ROLE>(p, a.img_critic + CI::W0, 256, 48);
     gemm_fwd<ROLE>(p, a.img_critic + CI::W4, 256, 256);
@@ -526,6 +535,7 @@ __device__ __forceinline__ void critic_program(Pipe &p, const Args &a, const uin
     // dW0 = dz1^T x0 (this CTA's block of 128 output rows)
     load_h<ROLE>(p, scr + SC::X0IMG, 12288);
     wgrad<ROLE>(p, 256, cr * 128, 48, 0, 16, true, true, true, true);
+    if (part == 0) actor_forward_program<ROLE>(p, a);
 }
 
 __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
@@ -551,11 +561,11 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
         float *part = a.cpart + (size_t)tile * CP::SIZE;
         {
             int t0 = 0;
-            if (chain != 2) { prefetch_actor_vectors(a.actor_t, e.tid, t0); prefetch_critic_vectors(a.critic_t, e.tid, t0); }
+            if (chain != 2) { prefetch_actor_vectors(a.actor_t, e.tid, t0); prefetch_critic_vectors(a.critic_t, e.tid, t0); prefetch_actor_vectors(a.actor, e.tid, t0); }
             if (chain != 1) prefetch_critic_vectors(a.critic, e.tid, t0);
         }
         UPROF(0, 0);
-        if (chain != 1 && a.stats_ext) {
+        if (a.stats_ext) {
             // the minibatch came with its emotion sums: warp c adds column c of the rows (lane l takes rows l, l + 32, ..., then a butterfly:
             // the same order on every CTA), no pass over the records
             if (e.tid < 6 * 32) {
@@ -573,7 +583,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
                 st_[3 + e.tid] = sqrtf(fmaxf(st_[19 + e.tid] - st_[16 + e.tid] * m, 0.f) / (n - 1.0f));
             }
             bar_epi();
-            if (tile == 0 && cr == 0 && e.tid < 6) { a.stats_g[e.tid] = e.stat()[e.tid]; if (e.tid < 3) a.mean_out[e.tid] = e.stat()[e.tid]; }
+            if (chain != 1 && tile == 0 && cr == 0 && e.tid < 6) { a.stats_g[e.tid] = e.stat()[e.tid]; if (e.tid < 3) a.mean_out[e.tid] = e.stat()[e.tid]; }
         } else if (chain == 2) grid_emotion_stats(e, a.batch, a.stats_part, a.stats_ctr, n_tiles, tile, a.stats_g, a.mean_out);
         else if (chain == 0) {
             emotion_stats(e, a.batch, tile == 0 && cr == 0 ? a.mean_out : nullptr);
@@ -583,6 +593,71 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
         const float *st = e.stat();
         const int cid = (a.n_cond > 1 && valid) ? (int)__ldg(row + 19) : 0;
         const float *scale = a.scale + cid * 10, *offset = a.offset + cid * 10;
+        // ---- a = actor(s, e) for ACTOR_GRAD (actor_forward_program): operand images, activation bits, head values and the critic input
+        // (s, a, e) go to the tile's scratch ----
+        auto actor_forward = [&]() {
+        uint32_t *abits = reinterpret_cast<uint32_t *>(scr + SC::ABITS) + e.r * 32 + (cr * 4 + e.wg);
+        float *aux = reinterpret_cast<float *>(scr + SC::AUX) + (size_t)cr * 64 * TR + e.r;
+        const float e0 = valid ? __ldg(row + 16) : 0.f, e1 = valid ? __ldg(row + 17) : 0.f, e2 = valid ? __ldg(row + 18) : 0.f;
+        e.wait_afree();
+        if (e.wg == 0) {
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = 0.f;
+            if (valid) { x[0] = __ldg(row); x[1] = __ldg(row + 1); x[2] = e0; x[3] = e1; x[4] = e2; }
+            x[15] = 1.0f;
+            store_split_input(e, x, cr == 0 ? scr + SC::XAIMG : nullptr);
+        }
+        e.a_ready_local();
+        e.wait_d(); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 6, scr + SC::A1IMG, abits, abits + 8); e.a_ready(128);
+        e.wait_d(); epi_hidden128(e, a.actor + AO::B2, ACT_RELU, a.drop, 7, scr + SC::A2IMG, abits + 16, abits + 24); e.a_ready(128);
+        e.wait_d();
+        // relu'(z3) bits of this thread's 8 columns: the backward in ACTOR_GRAD runs on the same thread of the same CTA rank
+        reinterpret_cast<uint32_t *>(scr + SC::POS3)[cr * NEPI + e.tid] = epi_hidden64(e, a.actor + AO::B3, scr + SC::A3IMG);
+        e.a_ready(64);
+        e.wait_d();
+        // the head: both CTAs (ACTOR_GRAD's backward reads this CTA rank's copy of aux), the critic input and the std sum by CTA 0
+        if (e.wg == 0) {
+            float z[16], out[10], x[16];
+            tmem_ld16w(e.td(0), z);
+            actor_head(z, a.actor, e0, e1, e2, scale, offset, out, aux);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = 0.f;
+            float sd = 0.f;
+            if (valid) {
+                x[0] = __ldg(row); x[1] = __ldg(row + 1);
+                float mean = 0.f;
+#pragma unroll
+                for (int c = 0; c < 10; ++c) { x[2 + c] = out[c]; mean += out[c]; }
+                mean *= 0.1f;
+                float var = 0.f;
+#pragma unroll
+                for (int c = 0; c < 10; ++c) { const float d = out[c] - mean; var = fmaf(d, d, var); }
+                sd = sqrtf(var / 9.0f);                        // torch.std(action_out, dim=1): unbiased
+#pragma unroll
+                for (int c = 0; c < 3; ++c) x[12 + c] = (__ldg(row + 16 + c) - st[c]) / (st[3 + c] + 1e-6f);
+            }
+            x[15] = 1.0f;
+            if (cr == 0) {      // the critic input of ACTOR_GRAD, as the K = 48 split image, to global only
+                float hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { hi[j] = __bfloat162float(__float2bfloat16(x[j])); lo[j] = x[j] - hi[j]; }
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    e.img_store8(scr + SC::XCIMG, 48, g * 8, hi + g * 8);
+                    e.img_store8(scr + SC::XCIMG, 48, 16 + g * 8, lo + g * 8);
+                    e.img_store8(scr + SC::XCIMG, 48, 32 + g * 8, hi + g * 8);
+                }
+            }
+            const float ssd = warp_sum(sd);
+            if (e.lane == 0) e.cs()[(2 * 4 + e.wq) * 256 + 2] = ssd;
+        }
+        bar_epi();
+        if (cr == 0 && e.tid == 0) {
+            const float *c = e.cs() + 2 * 4 * 256;
+            a.apart[(size_t)tile * AP::SIZE + AP::SSTD] = (c[2] + c[258]) + (c[514] + c[770]);
+        }
+        };
         // ---- target: a' = actor_target(s', e'), Q' = critic_target(s', a', 0) ----
         const float ne0 = __ldg(a.next_emotion), ne1 = __ldg(a.next_emotion + 1), ne2 = __ldg(a.next_emotion + 2);
         float tq = 0.f;
@@ -635,6 +710,8 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
             __threadfence();
             bar_epi();
             if (cr == 0 && e.tid < 2) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.tq_flag + 2 * tile + e.tid), "r"(1u) : "memory");
+            if (!a.stats_ext) emotion_stats(e, a.batch, nullptr);      // without the fused sampler: this pair's own pass, after Q' is on its way
+            actor_forward();
         } else {
         // ---- Q(s, a_norm, e) ----
         e.wait_afree();
@@ -738,6 +815,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
         UPROF(0, 28);
         drain_g(e, part + CP::W0 + cr * 128 * 16, 16, 0);
         UPROF(0, 32);
+        if (chain == 0) actor_forward();
         }
         UTC_EPI_DONE
         UCTA(0, 2);
@@ -752,10 +830,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
 template <int ROLE>
 __device__ __forceinline__ void actor_program(Pipe &p, const Args &a, const uint8_t *scr) {
     const int cr = (int)p.cr;
-    gemm_fwd<ROLE>(p, a.img_actor + AI::W1, 128, 48);
-    gemm_fwd<ROLE>(p, a.img_actor + AI::W2, 128, 128);
-    gemm_fwd<ROLE>(p, a.img_actor + AI::W3, 64, 128);
-    gemm_fwd<ROLE>(p, a.img_actor + AI::W4, 16, 64, false);
+    // (a = actor(s, e) ran inside CRITIC_GRAD: actor_forward_program)
     gemm_fwd<ROLE>(p, a.img_critic + CI::W0, 256, 48);
     gemm_fwd<ROLE>(p, a.img_critic + CI::W4, 256, 256);
     gemm_fwd<ROLE>(p, a.img_critic + CI::W8, 128, 256);
@@ -812,56 +887,16 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             bar_epi();
         }
         UPROF(1, 0);
-        if (e.tid < 6) e.stat()[e.tid] = a.stats_g[e.tid];         // the statistics of this minibatch, left by CRITIC_GRAD
-        bar_epi();
-        const float *st = e.stat();
         const int cid = (a.n_cond > 1 && valid) ? (int)__ldg(row + 19) : 0;
-        const float *scale = a.scale + cid * 10, *offset = a.offset + cid * 10;
+        const float *scale = a.scale + cid * 10;
         const float e0 = valid ? __ldg(row + 16) : 0.f, e1 = valid ? __ldg(row + 17) : 0.f, e2 = valid ? __ldg(row + 18) : 0.f;
-        // ---- a = actor(s, e) ----
+        // ---- a = actor(s, e) ran inside CRITIC_GRAD (actor_forward_program): the critic input image (s, a, e) comes from the tile's scratch,
+        // the saved operand images / activation bits / head values of the actor are read where the backward needs them ----
+        e.publish_saved();                                      // nothing to publish in this kernel: opens the producers' first bulk load
+        const uint32_t pos3 = reinterpret_cast<const uint32_t *>(scr + SC::POS3)[cr * NEPI + e.tid];
         e.wait_afree();
-        if (e.wg == 0) {
-            float x[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = 0.f;
-            if (valid) { x[0] = __ldg(row); x[1] = __ldg(row + 1); x[2] = e0; x[3] = e1; x[4] = e2; }
-            x[15] = 1.0f;
-            store_split_input(e, x, cr == 0 ? scr + SC::XAIMG : nullptr);
-        }
-        e.a_ready_local(); UPROF(1, 1);
-        e.wait_d(); UPROF(1, 2); epi_hidden128(e, nullptr, ACT_LEAKY, a.drop, 6, scr + SC::A1IMG, abits, abits + 8); e.a_ready(128); UPROF(1, 3);
-        e.wait_d(); UPROF(1, 4); epi_hidden128(e, a.actor + AO::B2, ACT_RELU, a.drop, 7, scr + SC::A2IMG, abits + 16, abits + 24); e.a_ready(128); UPROF(1, 5);
-        e.wait_d(); UPROF(1, 6);
-        // relu'(z3) bits of this thread's 8 columns (kept in a register until the backward)
-        const uint32_t pos3 = epi_hidden64(e, a.actor + AO::B3, scr + SC::A3IMG);
-        e.a_ready(64); e.publish_saved(); UPROF(1, 7);
-        e.wait_d(); UPROF(1, 8);
-        e.wait_afree();
-        if (e.wg == 0) {
-            float z[16], out[10], x[16];
-            tmem_ld16w(e.td(0), z);
-            actor_head(z, a.actor, e0, e1, e2, scale, offset, out, aux);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = 0.f;
-            float sd = 0.f;
-            if (valid) {
-                x[0] = __ldg(row); x[1] = __ldg(row + 1);
-                float mean = 0.f;
-#pragma unroll
-                for (int c = 0; c < 10; ++c) { x[2 + c] = out[c]; mean += out[c]; }
-                mean *= 0.1f;
-                float var = 0.f;
-#pragma unroll
-                for (int c = 0; c < 10; ++c) { const float d = out[c] - mean; var = fmaf(d, d, var); }
-                sd = sqrtf(var / 9.0f);                        // torch.std(action_out, dim=1): unbiased
-#pragma unroll
-                for (int c = 0; c < 3; ++c) x[12 + c] = (__ldg(row + 16 + c) - st[c]) / (st[3 + c] + 1e-6f);
-            }
-            x[15] = 1.0f;
-            store_split_input(e, x, nullptr);
-            const float ssd = warp_sum(sd);
-            if (e.lane == 0) e.cs()[(2 * 4 + e.wq) * 256 + 2] = ssd;
-        }
+        for (int i = e.tid; i < 12288 / 16; i += NEPI)
+            reinterpret_cast<uint4 *>(e.img_a())[i] = __ldcg(reinterpret_cast<const uint4 *>(scr + SC::XCIMG) + i);
         e.a_ready_local(); UPROF(1, 9);
         // ---- Q(s, a, e) with the updated critic ----
         e.wait_d(); UPROF(1, 10);
@@ -890,8 +925,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
             bar_epi();
             if (e.tid == 0 && cr == 0) {
                 const float *c = e.cs() + 2 * 4 * 256;
-                part[AP::SSTD] = (c[2] + c[258]) + (c[514] + c[770]);
-                part[AP::SQ] = (c[3] + c[259]) + (c[515] + c[771]);
+                part[AP::SQ] = (c[3] + c[259]) + (c[515] + c[771]);      // (AP::SSTD was left by the actor forward in CRITIC_GRAD)
             }
             bar_epi();
         }
