@@ -60,7 +60,9 @@ def _mask_dict(ms):
     return {"at": (f[0], f[1]), "ct": (f[2], f[3]), "c": (f[4], f[5]), "a": (f[6], f[7]), "c2": (f[8], f[9])}
 
 
-@pytest.mark.parametrize("B,dropout", [(128, "off"), (300, "off"), (128, "mask"), (256, "mask")])
+# 4096: the bench size (32 tiles: 64 pairs, the target chain on its own pairs); 5000: more tiles than resident pairs -> every pair runs
+# target chain, critic chain and the actor forward itself (the unsplit schedule), with a ragged last tile
+@pytest.mark.parametrize("B,dropout", [(128, "off"), (300, "off"), (128, "mask"), (256, "mask"), (4096, "mask"), (5000, "off")])
 def test_fast_update_matches_its_emulation_and_the_fp32_oracle(B, dropout):
     from erlfill_b200 import _lib as L
     g = np.load(os.path.join(GOLD, "learn_golden.npz"))
