@@ -2,7 +2,7 @@
 //
 // Every rank's update workspace lives in one cudaMalloc block that the other ranks of the node map with CUDA IPC
 // (erlfill_peer_alloc / erlfill_peer_open).  Between the *_GRAD and *_APPLY phases each rank launches
-//   peer_signal_kernel   one thread: epoch += 1, then store the epoch into flag[which][my rank] of EVERY rank's control block
+//   peer_signal_kernel   epoch += 1, then one thread per peer stores the epoch into flag[which][my rank] of that rank's control block
 //   peer_reduce_kernel   wait until all `world` flags of the own control block reached the epoch, then ONE pass: read the
 //                        bucket of every rank in rank order over NVLink (one-shot all-reduce: 8 x 0.42 MB at world 8), average,
 //                        write the reduced bucket locally and the 64 sum-of-squares partials clip_grad_norm_ needs
@@ -42,12 +42,20 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
     return v;
 }
 
+// one thread per peer: the system-scope release of a flag store waits for this GPU's earlier writes to be visible to that peer, about
+// a microsecond over NVLink — eight of them back to back in one thread were most of the exchange's cost at world 8
 __global__ void peer_signal_kernel(const PeerArgs a) {
+    __shared__ uint32_t s_epoch;
     PeerCtrl *mine = a.ctrl[a.rank];
-    const uint32_t e = mine->epoch[a.which] + 1;
-    mine->epoch[a.which] = e;
-    __threadfence_system();                                  // this rank's gradients (earlier kernels) before the flags
-    for (int p = 0; p < a.world; ++p) st_release_sys(&a.ctrl[p]->flag[a.which][a.rank], e);
+    if (threadIdx.x == 0) {
+        s_epoch = mine->epoch[a.which] + 1;
+        mine->epoch[a.which] = s_epoch;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < a.world) {
+        __threadfence_system();                              // this rank's gradients (earlier kernels) before the flag
+        st_release_sys(&a.ctrl[threadIdx.x]->flag[a.which][a.rank], s_epoch);
+    }
 }
 
 constexpr int kPeerThreads = 256;      // the thread / slice geometry of mlp::sumsq_kernel: the norm partials add up in the same order as on the NCCL path
@@ -189,7 +197,7 @@ int erlfill_ddpg_peer_allreduce(const erlfill_peer_group *g, int batch, int whic
     }
     a.timeout_cycles = timeout_cycles;
     cudaStream_t st = (cudaStream_t)stream;
-    peer_signal_kernel<<<1, 1, 0, st>>>(a);
+    peer_signal_kernel<<<1, 32, 0, st>>>(a);
     peer_reduce_kernel<<<mlp::kSumsqBlocks, kPeerThreads, 0, st>>>(a);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
