@@ -16,8 +16,8 @@
 
 namespace erlfill {
 
-constexpr int kRows = 64;          // rows per tile
-constexpr int kThreads = 256;
+constexpr int kRows = 96;          // rows per tile: 12 warps share the staged weights (105 KB) — 8 warps per SM issued at 45 %
+constexpr int kThreads = 384;      // (a warp owns 8 rows x 128 columns of layers 1-2; 209 KB of shared memory in all)
 constexpr int kH = 128;            // hidden width
 constexpr int kH3 = 64;
 
@@ -45,10 +45,10 @@ constexpr int oB3 = oB2 + kH;
 constexpr int oB4 = oB3 + kH3;                 // [16]
 constexpr int oEW = oB4 + 16;                  // [3][16]
 constexpr int oSC = oEW + 48;                  // scale[16], offset[16]
-constexpr int oX = oSC + 32;                   // [64][8]  state(2) emotion(3)
-constexpr int oHa = oX + kRows * 8;            // [64][132]
+constexpr int oX = oSC + 32;                   // [kRows][8]  state(2) emotion(3)
+constexpr int oHa = oX + kRows * 8;            // [kRows][132]
 constexpr int kLd = kH + 4;                    // padded row stride (keeps 16 B alignment, breaks conflicts)
-constexpr int oHb = oHa + kRows * kLd;         // [64][132]
+constexpr int oHb = oHa + kRows * kLd;         // [kRows][132]
 constexpr int kSmemFloats = oHb + kRows * kLd;
 
 __device__ __forceinline__ bool keep_philox(uint32_t k0, uint32_t k1, uint32_t row, uint32_t call, uint32_t col,
