@@ -235,8 +235,8 @@ __device__ __forceinline__ void actor_head(const float (&z16)[16], const float *
     }
 }
 
-// Hidden layer with N = 128 outputs (this CTA's 64: 16 columns per thread): z = D (+ bias) -> activation -> dropout -> image of 128
-// features in both CTAs.  pos_out / keep_out: bit j = (z > 0) / kept, of feature cr * 64 + wg * 16 + j.
+// Hidden layer with N = 128 outputs (this CTA's 64: 16 columns per thread): z = D (+ bias) -> activation -> dropout -> this CTA's half of the image of 128
+// features (the peer gets it with a_ready).  pos_out / keep_out: bit j = (z > 0) / kept, of feature cr * 64 + wg * 16 + j.
 __device__ __forceinline__ void epi_hidden128(Epi &e, const float *bias, int act, const Drop &dr, int site, uint8_t *gimg, uint32_t *pos_out,
                                               uint32_t *keep_out) {
     float v[16];
@@ -252,13 +252,13 @@ __device__ __forceinline__ void epi_hidden128(Epi &e, const float *bias, int act
         v[j] = ((keep >> j) & 1u) ? z * (dr.mode == ERLFILL_DROPOUT_OFF ? 1.0f : kDropScale) : 0.f;
     }
     e.wait_afree();
-    e.img_store8_pair(128, c0, v, gimg);
-    e.img_store8_pair(128, c0 + 8, v + 8, gimg);
+    e.img_store8_a(128, c0, v, gimg);
+    e.img_store8_a(128, c0 + 8, v + 8, gimg);
     if (pos_out) *pos_out = pos;
     if (keep_out) *keep_out = keep;
 }
 
-// Linear(128, 64) -> ReLU (this CTA's 32 columns: 8 per thread) -> image of 64 features in both CTAs; returns the relu' bits
+// Linear(128, 64) -> ReLU (this CTA's 32 columns: 8 per thread) -> this CTA's half of the image of 64 features; returns the relu' bits
 __device__ __forceinline__ uint32_t epi_hidden64(Epi &e, const float *bias, uint8_t *gimg) {
     float v[8];
     const int cl = e.wg * 8, c0 = e.cr * 32 + cl;
@@ -270,7 +270,7 @@ __device__ __forceinline__ uint32_t epi_hidden64(Epi &e, const float *bias, uint
         pos |= (v[j] > 0.f ? 1u : 0u) << j;
     }
     e.wait_afree();
-    e.img_store8_pair(64, c0, v, gimg);
+    e.img_store8_a(64, c0, v, gimg);
     return pos;
 }
 
@@ -324,7 +324,7 @@ __device__ __forceinline__ void epi_ln256(Epi &e, const float *bias, const float
     }
     e.wait_afree();
 #pragma unroll
-    for (int g = 0; g < 4; ++g) e.img_store_pair_q(256, c0 + g * 8, make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]));
+    for (int g = 0; g < 4; ++g) e.img_store_a_q(256, c0 + g * 8, make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]));
     e.a_ready(256);
     if (gimg) {
 #pragma unroll
@@ -423,7 +423,7 @@ __device__ __forceinline__ void epi_ln256_bwd(Epi &e, const float *gamma, const 
         }
         e.wait_afree();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) e.img_store8_pair(256, c0 + g * 8, dz + g * 8);
+        for (int g = 0; g < 4; ++g) e.img_store8_a(256, c0 + g * 8, dz + g * 8);
         e.a_ready(256);
         if (part) e.colsum_stage<32>(0, cl, dz);
     }
@@ -777,8 +777,8 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_critic_grad_tc(const Args a) {
                 gw[j] = g * h3[j];
             }
             e.wait_afree();
-            e.img_store8_pair(128, c0, dz3);
-            e.img_store8_pair(128, c0 + 8, dz3 + 8);
+            e.img_store8_a(128, c0, dz3);
+            e.img_store8_a(128, c0 + 8, dz3 + 8);
             e.a_ready(128);
             e.colsum_stage<16>(0, cl, dz3);                     // db8
             e.colsum_stage<16>(1, cl, gw);                      // dW10
@@ -915,8 +915,8 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) dz3[j] = h3[j] > 0.f ? g * __ldg(a.critic + CO::W10 + c0 + j) : 0.f;
             e.wait_afree();
-            e.img_store8_pair(128, c0, dz3);
-            e.img_store8_pair(128, c0 + 8, dz3 + 8);
+            e.img_store8_a(128, c0, dz3);
+            e.img_store8_a(128, c0 + 8, dz3 + 8);
             e.a_ready(128); UPROF(1, 15);
             if (e.wg == 0) {
                 const float sq = warp_sum(valid ? q2 : 0.f);
@@ -993,7 +993,7 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = ((pos3 >> j) & 1u) ? v[j] : 0.f;
             e.wait_afree();
-            e.img_store8_pair(64, c0, v);
+            e.img_store8_a(64, c0, v);
             e.a_ready(64); UPROF(1, 24);
             e.colsum_stage<8>(0, cl, v);
             bar_epi();
@@ -1011,8 +1011,8 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = (((pos & keep) >> j) & 1u) ? v[j] * ds : 0.f;
             e.wait_afree();
-            e.img_store8_pair(128, c0, v);
-            e.img_store8_pair(128, c0 + 8, v + 8);
+            e.img_store8_a(128, c0, v);
+            e.img_store8_a(128, c0 + 8, v + 8);
             e.a_ready(128); UPROF(1, 27);
             e.colsum_stage<16>(0, cl, v);
             bar_epi();
@@ -1030,8 +1030,8 @@ __global__ void __launch_bounds__(NTHR, 1) ddpg_actor_grad_tc(const Args a) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * ds * (((pos >> j) & 1u) ? 1.0f : 0.1f) : 0.f;
             e.wait_afree();
-            e.img_store8_pair(128, c0, v);
-            e.img_store8_pair(128, c0 + 8, v + 8);
+            e.img_store8_a(128, c0, v);
+            e.img_store8_a(128, c0 + 8, v + 8);
             e.a_ready(128); UPROF(1, 30);
             e.colsum_stage<16>(0, cl, v);
             bar_epi();

@@ -375,21 +375,21 @@ struct Epi {
         }
         a = sa; b = sb;
     }
-    // 8 consecutive features [f0, f0 + 8) of this thread's row into an image of F features: a global copy, or this CTA's IMG_A (the
-    // peer receives this CTA's half with a_ready)
+    // 8 consecutive features [f0, f0 + 8) of this thread's row into an image of F features: any image (a global copy) ...
     __device__ void img_store8(uint8_t *img, int F, int f0, const float *v) const {
         uint4 q;
         q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
         *reinterpret_cast<uint4 *>(img + img_off(r, f0, F)) = q;
     }
-    __device__ void img_store8_pair(int F, int f0, const float *v, uint8_t *gimg = nullptr) const {
+    // ... or this CTA's IMG_A (the peer receives this CTA's half with a_ready), optionally with a global copy
+    __device__ void img_store8_a(int F, int f0, const float *v, uint8_t *gimg = nullptr) const {
         uint4 q;
         q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
         const uint32_t o = img_off(r, f0, F);
         *reinterpret_cast<uint4 *>(smem + SM_IMG_A + o) = q;
         if (gimg) *reinterpret_cast<uint4 *>(gimg + o) = q;
     }
-    __device__ void img_store_pair_q(int F, int f0, uint4 q) const { *reinterpret_cast<uint4 *>(smem + SM_IMG_A + img_off(r, f0, F)) = q; }
+    __device__ void img_store_a_q(int F, int f0, uint4 q) const { *reinterpret_cast<uint4 *>(smem + SM_IMG_A + img_off(r, f0, F)) = q; }
     // column sums over the tile's 128 rows, stage 1: v[W] are this thread's values for the CTA-local columns [c0, c0 + W)
     // -> cs[slot][wq][c0 + column]
     template <int W>
