@@ -1139,6 +1139,23 @@ __global__ void __launch_bounds__(kRedThreads) grad_reduce_kernel(int n_cta, int
     }
 }
 
+// The clip-norm partials of a gradient bucket that may have changed since grad_reduce_kernel wrote it (an APPLY phase called on its own:
+// the caller averaged the bucket over the ranks in between, e.g. ncclAllReduce).  Same thread <-> element mapping and block sum as
+// grad_reduce_kernel, so an unchanged bucket gives bit-identical partials.
+template <bool kActor>
+__global__ void __launch_bounds__(kRedThreads) grad_ssq_kernel(const float *G, float *ssq) {
+    __shared__ float scratch[32];
+    constexpr int np = kActor ? AP::SQ : CP::LOSS;
+    const int p = 4 * (blockIdx.x * kRedGroups + (threadIdx.x >> 2)) + (threadIdx.x & 3);
+    float ss = 0.f;
+    if (p < np) {
+        const int i = kActor ? actor_flat_index(p) : critic_flat_index(p);
+        if (i >= 0) { const float g = G[i]; ss = g * g; }
+    }
+    const float t = mlp::block_sum(ss, scratch);
+    if (threadIdx.x == 0) ssq[blockIdx.x] = t;
+}
+
 // ---- weight images -----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void put_bf16(uint8_t *img, uint32_t off, float v) { *reinterpret_cast<__nv_bfloat16 *>(img + off) = __float2bfloat16(v); }
 // first-layer weight (row n, input k < 16) -> [W_hi | W_hi | W_lo] at columns k, 16 + k, 32 + k
@@ -1356,6 +1373,8 @@ int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const f
         grad_reduce_kernel<false><<<red_blocks(false), kRedThreads, 0, st>>>(nc, B, t.cpart, nullptr, w.scal, w.cgrad, t.ssq_fine);
     }
     if (phases & ERLFILL_PHASE_CRITIC_APPLY) {
+        if (!reduced && !(phases & ERLFILL_PHASE_CRITIC_GRAD))
+            grad_ssq_kernel<false><<<red_blocks(false), kRedThreads, 0, st>>>(w.cgrad, t.ssq_fine);
         const float *G = reduced ? w.cred : w.cgrad;
         critic_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->critic, n->critic_m, n->critic_v, G, reduced ? w.ssq : t.ssq_fine,
                                                                      reduced ? mlp::kSumsqBlocks : red_blocks(false), w.step, h->critic_lr, h->actor_lr,
@@ -1366,6 +1385,8 @@ int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const f
         grad_reduce_kernel<true><<<red_blocks(true), kRedThreads, 0, st>>>(nc, B, t.apart, n->actor, w.scal, w.agrad, t.ssq_fine + kRedBlocksMax);
     }
     if (phases & ERLFILL_PHASE_ACTOR_APPLY) {
+        if (!reduced && !(phases & ERLFILL_PHASE_ACTOR_GRAD))
+            grad_ssq_kernel<true><<<red_blocks(true), kRedThreads, 0, st>>>(w.agrad, t.ssq_fine + kRedBlocksMax);
         const float *G = reduced ? w.ared : w.agrad;
         actor_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, n->actor_target, n->actor_m, n->actor_v, G,
                                                                     reduced ? w.ssq + mlp::kSumsqBlocks : t.ssq_fine + kRedBlocksMax,

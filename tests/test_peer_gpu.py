@@ -16,18 +16,22 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
-def test_peer_exchange_matches_nccl_allreduce():
-    world = min(torch.cuda.device_count(), 8)
+def _dp_check(world, precision):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tools", "dp_check.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=180, cwd=ROOT)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=180, cwd=ROOT, env=dict(os.environ, DP_CHECK_PRECISION=precision))
     line = [l for l in p.stdout.splitlines() if l.startswith("DP_CHECK ")]
     assert p.returncode == 0 and line, p.stdout[-2000:] + p.stderr[-4000:]
     res = json.loads(line[-1][len("DP_CHECK "):])
     assert len(res) == world
-    for r in res:
-        assert r["peer_error"] == 0 and r["same_across_ranks"] and r["exchange_same_across_ranks"], r
+    return res
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+def test_peer_exchange_matches_nccl_allreduce():
+    world = min(torch.cuda.device_count(), 8)
+    for r in _dp_check(world, "exact"):
+        assert r["peer_error"] == 0 and r["same_across_ranks"] and r["nccl_same_across_ranks"] and r["exchange_same_across_ranks"], r
         # the exchange itself: the averaged bucket equals ncclAllReduce / world up to fp32 summation order (world 2: a + b is
         # commutative, so bit-exact), and the fused sum-of-squares partials add up to the norm of the reduced gradient
         assert r["exchange_max_abs_diff"] <= (0.0 if world == 2 else 1e-6 * r["exchange_scale"]), r
@@ -35,3 +39,16 @@ def test_peer_exchange_matches_nccl_allreduce():
         if world == 2:      # identical gradients -> identical trajectories; beyond 2 ranks Adam amplifies the summation-order noise
             assert r["max_abs_diff_critic_vs_nccl"] == 0.0 and r["max_abs_diff_actor_vs_nccl"] == 0.0, r
             assert r["max_abs_diff_report_vs_nccl"] <= 1e-6, r
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+def test_fast_update_is_data_parallel_on_both_exchange_paths():
+    """The tcgen05 update under both exchanges: replicas bit-identical across ranks on the peer path AND on the NCCL path (an APPLY
+    phase called after an all-reduce must clip with the norm of the averaged bucket, not the one its GRAD phase left), and the two
+    trajectories agree to fp32 summation order of the norm (different partial geometries)."""
+    world = min(torch.cuda.device_count(), 8)
+    for r in _dp_check(world, "fast"):
+        assert r["peer_error"] == 0 and r["same_across_ranks"] and r["nccl_same_across_ranks"] and r["exchange_same_across_ranks"], r
+        assert r["exchange_max_abs_diff"] <= (0.0 if world == 2 else 1e-6 * r["exchange_scale"]), r
+        assert r["sumsq_rel_diff"] <= 1e-5, r
+        assert r["max_abs_diff_critic_vs_nccl"] <= 2e-4 and r["max_abs_diff_actor_vs_nccl"] <= 2e-5, r

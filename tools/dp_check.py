@@ -22,6 +22,7 @@ def main():
     dev = torch.device("cuda", local)
     parallel.init("nccl", dev)
     B = int(os.environ.get("DP_CHECK_BATCH", 512))
+    precision = os.environ.get("DP_CHECK_PRECISION", "exact")          # "fast": the tcgen05 update (its own norm-partial geometry)
     bounds = E.conditions.EXPERIMENT_3["variant_25kg"]["bounds"]
     a_sd, c_sd, _ = init.er_ddpg_state_dicts(bounds, seed=3, with_transformer=False)     # identical replicas
     g = torch.Generator().manual_seed(100 + rank)                                          # different minibatch per rank
@@ -37,7 +38,7 @@ def main():
     out = {}
     learners = {}
     # (1) the exchange itself: one CRITIC_GRAD phase, then the peer all-reduce against ncclAllReduce of the same buckets
-    lr0 = ddpg.DDPGLearner(a_sd, c_sd, device=dev, batch_size=B)
+    lr0 = ddpg.DDPGLearner(a_sd, c_sd, device=dev, batch_size=B, precision=precision)
     ex0 = parallel.PeerExchange(lr0, B)
     lr0.update(batch, ne, 3, phases=L.PHASE_CRITIC_GRAD, graph=False)
     ex0.exchange(0)
@@ -56,7 +57,7 @@ def main():
     out["exchange_same_across_ranks"] = all(bool(torch.equal(g, gathered[0])) for g in gathered)
     # (2) whole updates: replicas stay bit-identical; the NCCL path for comparison and timing
     for mode in ("nccl", "peer"):
-        lr = ddpg.DDPGLearner(a_sd, c_sd, device=dev, batch_size=B)
+        lr = ddpg.DDPGLearner(a_sd, c_sd, device=dev, batch_size=B, precision=precision)
         ex = parallel.GradSync(world) if mode == "nccl" else parallel.PeerExchange(lr, B)
         reps = []
         for it in range(4):                       # the first runs eagerly, the rest replay the captured graph
@@ -81,11 +82,18 @@ def main():
     refa = lp.actor.flat.clone()
     dist.broadcast(refa, src=0)
     same_across_ranks &= bool(torch.equal(refa, lp.actor.flat))
+    # ... and on the NCCL path too (every rank must clip with the norm of the AVERAGED gradient)
+    nccl_same = True
+    for t in (ln.critic.flat, ln.actor.flat):
+        r0 = t.clone()
+        dist.broadcast(r0, src=0)
+        nccl_same &= bool(torch.equal(r0, t))
     d_c = float((ln.critic.flat - lp.critic.flat).abs().max())
     d_a = float((ln.actor.flat - lp.actor.flat).abs().max())
     d_rep = float((rn - rp).abs().max())
     ex.close()
-    res = {"rank": rank, "world": world, "batch": B, "peer_error": err, "same_across_ranks": same_across_ranks,
+    res = {"rank": rank, "world": world, "batch": B, "precision": precision, "peer_error": err, "same_across_ranks": same_across_ranks,
+           "nccl_same_across_ranks": nccl_same,
            "max_abs_diff_critic_vs_nccl": d_c, "max_abs_diff_actor_vs_nccl": d_a, "max_abs_diff_report_vs_nccl": d_rep,
            "nccl_ms_per_update": out["nccl_ms"], "peer_ms_per_update": out["peer_ms"],
            "exchange_max_abs_diff": out["exchange_max_abs_diff"], "exchange_scale": out["exchange_scale"],
