@@ -91,7 +91,7 @@ class DDPGHyper(C.Structure):
                 ("max_grad_norm", C.c_float), ("n_cond", C.c_int32), ("critic_lr", C.c_double),
                 ("actor_lr", C.c_double), ("lr_decay", C.c_double), ("precision", C.c_int32), ("dropout_mode", C.c_int32),
                 ("seed", C.c_uint64), ("update_idx", C.c_uint32), ("rank", C.c_uint32), ("masks", C.c_void_p),
-                ("d_stats_partials", C.c_void_p), ("n_stats_partials", C.c_int32), ("_pad2", C.c_int32)]
+                ("d_stats_partials", C.c_void_p), ("n_stats_partials", C.c_int32), ("_pad2", C.c_int32), ("peer", C.c_void_p)]
 
 
 class TD3Nets(C.Structure):
@@ -141,7 +141,7 @@ EXPORTS = [
     "erlfill_replay_sample_gather_blocks",
     "erlfill_ddpg_workspace_bytes", "erlfill_ddpg_grad_buckets", "erlfill_ddpg_set_step", "erlfill_ddpg_update", "erlfill_ddpg_pack_images",
     "erlfill_ddpg_exchange_buffers", "erlfill_ddpg_update_launches", "erlfill_ddpg_peer_launches", "erlfill_peer_ctrl_bytes", "erlfill_peer_alloc", "erlfill_peer_open", "erlfill_peer_close",
-    "erlfill_peer_free", "erlfill_ddpg_peer_allreduce", "erlfill_peer_error",
+    "erlfill_peer_free", "erlfill_ddpg_peer_allreduce", "erlfill_ddpg_peer_allreduce_fast", "erlfill_peer_error",
     "erlfill_t1_workspace_bytes", "erlfill_t1_act_workspace_bytes", "erlfill_t1_grad_buckets", "erlfill_td3_act",
     "erlfill_td3_update", "erlfill_sac_act", "erlfill_sac_update",
     "erlfill_esac_workspace_bytes", "erlfill_esac_act_workspace_bytes", "erlfill_esac_grad_buckets", "erlfill_esac_act",

@@ -6,6 +6,8 @@
 //   peer_reduce_kernel   wait until all `world` flags of the own control block reached the epoch, then ONE pass: read the
 //                        bucket of every rank in rank order over NVLink (one-shot all-reduce: 8 x 0.42 MB at world 8), average,
 //                        write the reduced bucket locally and the 64 sum-of-squares partials clip_grad_norm_ needs
+// (the tcgen05 update raises the flags from the last block of its grad_reduce_kernel instead — peer.cuh — and uses
+//   peer_reduce_fine_kernel  the same with one element per thread and one norm partial per 256 elements: erlfill_ddpg_peer_allreduce_fast)
 // so the exchange replaces ncclAllReduce + scale + sumsq (3 launches, 2 of them collective-latency bound) and every rank
 // adds the same values in the same order: replicas stay bit-identical.  Buckets are only rewritten by the next update's
 // *_GRAD phase, which a rank reaches after the OTHER bucket's exchange — i.e. after every peer has finished reading this one
@@ -18,14 +20,9 @@
 
 #include "common.cuh"
 #include "mlp.cuh"
+#include "peer.cuh"
 
 namespace erlfill {
-
-struct PeerCtrl {                  // one per rank, at the tail of its peer allocation (zero-initialised)
-    uint32_t flag[2][ERLFILL_MAX_PEERS];
-    uint32_t epoch[2];
-    uint32_t error;
-};
 
 struct PeerArgs {
     int world, rank, which, n, n_norm;
@@ -35,28 +32,9 @@ struct PeerArgs {
     float *out, *ssq;
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // one thread per peer: the system-scope release of a flag store waits for this GPU's earlier writes to be visible to that peer, about
 // a microsecond over NVLink — eight of them back to back in one thread were most of the exchange's cost at world 8
-__global__ void peer_signal_kernel(const PeerArgs a) {
-    __shared__ uint32_t s_epoch;
-    PeerCtrl *mine = a.ctrl[a.rank];
-    if (threadIdx.x == 0) {
-        s_epoch = mine->epoch[a.which] + 1;
-        mine->epoch[a.which] = s_epoch;
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < a.world) {
-        __threadfence_system();                              // this rank's gradients (earlier kernels) before the flag
-        st_release_sys(&a.ctrl[threadIdx.x]->flag[a.which][a.rank], s_epoch);
-    }
-}
+__global__ void peer_signal_kernel(const PeerSig s) { peer_signal_block(s); }
 
 constexpr int kPeerThreads = 256;      // the thread / slice geometry of mlp::sumsq_kernel: the norm partials add up in the same order as on the NCCL path
 constexpr int kPeerChunks = 7;         // elements per thread whose loads are all issued before the first use (the NVLink round trips overlap)
@@ -103,6 +81,43 @@ __global__ void __launch_bounds__(kPeerThreads) peer_reduce_kernel(const PeerArg
             a.out[i] = s;
             if (i < a.n_norm) ss = fmaf(s, s, ss);
         }
+    }
+    const float t = mlp::block_sum(ss, scratch);
+    if (threadIdx.x == 0) a.ssq[blockIdx.x] = t;
+}
+
+// The fast path's reduce: one element per thread (all ranks' loads in flight at once), one norm partial per block — the tcgen05
+// update's apply kernels add any number of partials.
+__global__ void __launch_bounds__(kPeerFineThreads) peer_reduce_fine_kernel(const PeerArgs a) {
+    __shared__ float scratch[32];
+    PeerCtrl *mine = a.ctrl[a.rank];
+    if (threadIdx.x < a.world) {
+        const uint32_t e = *reinterpret_cast<volatile uint32_t *>(&mine->epoch[a.which]);
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(&mine->flag[a.which][threadIdx.x]) - e) < 0) {
+            if (clock64() - t0 > a.timeout_cycles) { atomicExch(&mine->error, 1u); break; }
+            __nanosleep(40);
+        }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * kPeerFineThreads + threadIdx.x;
+    if (*reinterpret_cast<volatile uint32_t *>(&mine->error) != 0u) {       // sticky: see peer_reduce_kernel
+        const float nan = __int_as_float(0x7fc00000);
+        if (i < a.n) a.out[i] = nan;
+        if (threadIdx.x == 0) a.ssq[blockIdx.x] = nan;
+        return;
+    }
+    float ss = 0.f;
+    if (i < a.n) {
+        float v[ERLFILL_MAX_PEERS];
+#pragma unroll
+        for (int q = 0; q < ERLFILL_MAX_PEERS; ++q) v[q] = q < a.world ? __ldcg(a.bucket[q] + i) : 0.f;
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < ERLFILL_MAX_PEERS; ++q) s += v[q];                  // rank order; absent ranks add +0
+        s *= 1.0f / (float)a.world;
+        a.out[i] = s;
+        if (i < a.n_norm) ss = s * s;
     }
     const float t = mlp::block_sum(ss, scratch);
     if (threadIdx.x == 0) a.ssq[blockIdx.x] = t;
@@ -165,14 +180,16 @@ int erlfill_peer_error(const erlfill_peer_group *g, int *error_out) {
     return ERLFILL_OK;
 }
 
-int erlfill_ddpg_peer_launches(void) { return 4; }       // 2 x (signal, reduce) per update, minus nothing: the APPLY phases skip their sumsq kernels
+int erlfill_ddpg_peer_launches(int fast) { return fast ? 2 : 4; }       // exact: 2 x (signal, reduce); fast: 2 x reduce (the signal rides on grad_reduce_kernel)
 
-int erlfill_ddpg_peer_allreduce(const erlfill_peer_group *g, int batch, int which, void *stream) {
+static int peer_allreduce_impl(const erlfill_peer_group *g, int batch, int which, bool fine, bool signalled, void *stream) {
     if (!g || g->world < 1 || g->world > ERLFILL_MAX_PEERS || g->rank < 0 || g->rank >= g->world || (which != 0 && which != 1) ||
         batch < 2)
         return ERLFILL_ERR_ARG;
     PeerArgs a;
-    a.world = g->world; a.rank = g->rank; a.which = which;
+    PeerSig sig;
+    a.world = sig.world = g->world; a.rank = sig.rank = g->rank; a.which = sig.which = which;
+    sig.done = nullptr;
     for (int p = 0; p < g->world; ++p) {
         if (!g->ws[p] || !g->ctrl[p]) return ERLFILL_ERR_ARG;
         float *cg, *ag, *cr, *ar, *ssq;
@@ -180,12 +197,12 @@ int erlfill_ddpg_peer_allreduce(const erlfill_peer_group *g, int batch, int whic
         const int rc = erlfill_ddpg_exchange_buffers(g->ws[p], batch, &cg, &cl, &ag, &al, &cr, &ar, &ssq);
         if (rc != ERLFILL_OK) return rc;
         a.bucket[p] = which == 0 ? cg : ag;
-        a.ctrl[p] = (PeerCtrl *)g->ctrl[p];
+        a.ctrl[p] = sig.ctrl[p] = (PeerCtrl *)g->ctrl[p];
         if (p == g->rank) {
             a.n = which == 0 ? cl : al;
             a.n_norm = which == 0 ? ERLFILL_CRITIC_PARAMS : ERLFILL_ACTOR_PARAMS;
             a.out = which == 0 ? cr : ar;
-            a.ssq = ssq + which * mlp::kSumsqBlocks;
+            a.ssq = fine ? ddpg_ssq_fine(g->ws[p], batch, which) : ssq + which * mlp::kSumsqBlocks;
         }
     }
     static long long timeout_cycles = 0;
@@ -197,10 +214,18 @@ int erlfill_ddpg_peer_allreduce(const erlfill_peer_group *g, int batch, int whic
     }
     a.timeout_cycles = timeout_cycles;
     cudaStream_t st = (cudaStream_t)stream;
-    peer_signal_kernel<<<1, 32, 0, st>>>(a);
-    peer_reduce_kernel<<<mlp::kSumsqBlocks, kPeerThreads, 0, st>>>(a);
+    if (!signalled) peer_signal_kernel<<<1, 32, 0, st>>>(sig);
+    if (fine) peer_reduce_fine_kernel<<<ddpg_fine_blocks(which), kPeerFineThreads, 0, st>>>(a);
+    else peer_reduce_kernel<<<mlp::kSumsqBlocks, kPeerThreads, 0, st>>>(a);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
+}
+
+int erlfill_ddpg_peer_allreduce(const erlfill_peer_group *g, int batch, int which, void *stream) {
+    return peer_allreduce_impl(g, batch, which, false, false, stream);
+}
+int erlfill_ddpg_peer_allreduce_fast(const erlfill_peer_group *g, int batch, int which, void *stream) {
+    return peer_allreduce_impl(g, batch, which, true, true, stream);
 }
 
 }  // extern "C"

@@ -24,6 +24,7 @@
 #include "ddpg_dropout.cuh"
 #include "mlp.cuh"
 #include "fused_mlp.cuh"
+#include "peer.cuh"
 
 namespace erlfill {
 using namespace mlp;
@@ -706,8 +707,15 @@ size_t tail_bytes(int B);
 int pack_images(const erlfill_ddpg_nets *n, uint8_t *tail_base, int B, cudaStream_t st);
 int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const float *d_batch, const float *d_next_emotion, const Head &w,
                 uint8_t *tail_base, int phases, float *d_report, cudaStream_t st);
+float *tail_ssq_fine(uint8_t *tail_base, int B, int which);
+unsigned int *tail_peer_done(uint8_t *tail_base, int B, int which);
+int peer_fine_blocks(int which);
 }  // namespace utc
 static size_t exact_bytes(int batch) { return (carve(nullptr, nullptr, batch) * sizeof(float) + 255) & ~(size_t)255; }
+// peer.cuh: what the fast path's exchange needs of the workspace
+int ddpg_fine_blocks(int which) { return utc::peer_fine_blocks(which); }
+float *ddpg_ssq_fine(void *d_workspace, int batch, int which) { return utc::tail_ssq_fine((uint8_t *)d_workspace + exact_bytes(batch), batch, which); }
+unsigned int *ddpg_peer_done(void *d_workspace, int batch, int which) { return utc::tail_peer_done((uint8_t *)d_workspace + exact_bytes(batch), batch, which); }
 
 }  // namespace erlfill
 

@@ -17,6 +17,7 @@
 #include "update_tc.cuh"
 
 #include "mlp.cuh"
+#include "peer.cuh"
 
 namespace erlfill {
 namespace utc {
@@ -1088,8 +1089,9 @@ __device__ __forceinline__ int actor_flat_index(int p) {
 constexpr int kRedThreads = 256, kRedGroups = kRedThreads / 4;
 constexpr int red_blocks(bool actor) { return ((actor ? AP::SQ : CP::LOSS) + 3) / 4 / kRedGroups + 1; }
 constexpr int kRedBlocksMax = red_blocks(false);
-template <bool kActor>
-__global__ void __launch_bounds__(kRedThreads) grad_reduce_kernel(int n_cta, int B, const float *part, const float *theta, float *scal, float *G, float *ssq) {
+template <bool kActor, bool kSignal>
+__global__ void __launch_bounds__(kRedThreads) grad_reduce_kernel(int n_cta, int B, const float *part, const float *theta, float *scal, float *G, float *ssq,
+                                                                  const PeerSig sig) {
     __shared__ float scratch[32];
     constexpr int np = kActor ? AP::SQ : CP::LOSS, psize = kActor ? AP::SIZE : CP::SIZE;
     constexpr int nq = (np + 3) / 4;
@@ -1137,6 +1139,7 @@ __global__ void __launch_bounds__(kRedThreads) grad_reduce_kernel(int n_cta, int
             scal[4] = l / (float)B;
         }
     }
+    if (kSignal) peer_signal_when_grid_done(sig);      // data-parallel: this rank's bucket is complete -> raise its flags on every peer
 }
 
 // The clip-norm partials of a gradient bucket that may have changed since grad_reduce_kernel wrote it (an APPLY phase called on its own:
@@ -1259,19 +1262,19 @@ __global__ void actor_apply_kernel(float *p, float *pt, float *m, float *v, cons
 struct Tail {
     uint8_t *img_actor, *img_actor_t, *img_critic, *img_critic_t, *scratch;
     float *cpart, *apart, *tq_g, *stats_part, *ssq_fine;      // ssq_fine: [2][kRedBlocksMax]
-    uint32_t *flags;            // two tq_flags per tile, then the two counters of grid_emotion_stats
+    uint32_t *flags;            // two tq_flags per tile, the two counters of grid_emotion_stats, the two arrival counters of the peer signal
 };
 static size_t up256(size_t n) { return (n + 255) & ~(size_t)255; }
 static int n_cta(int B) { return (B + TR - 1) / TR; }
 size_t tail_bytes(int B) {
     const size_t c = (size_t)n_cta(B);
-    return up256((2 * c + 2) * 4) + up256(c * 32) + 2 * up256(AI::BYTES) + 2 * up256(CI::BYTES) + up256(c * SC::BYTES) + up256(c * CP::SIZE * 4) + up256(c * AP::SIZE * 4) +
+    return up256((2 * c + 4) * 4) + up256(c * 32) + 2 * up256(AI::BYTES) + 2 * up256(CI::BYTES) + up256(c * SC::BYTES) + up256(c * CP::SIZE * 4) + up256(c * AP::SIZE * 4) +
            up256((size_t)B * 4) + up256(2 * kRedBlocksMax * 4);
 }
 static void carve_tail(Tail &t, uint8_t *base, int B) {
     const size_t c = (size_t)n_cta(B);
     size_t o = 0;
-    t.flags = reinterpret_cast<uint32_t *>(base); o += up256((2 * c + 2) * 4);
+    t.flags = reinterpret_cast<uint32_t *>(base); o += up256((2 * c + 4) * 4);
     t.stats_part = reinterpret_cast<float *>(base + o); o += up256(c * 32);
     t.img_actor = base + o; o += up256(AI::BYTES);
     t.img_actor_t = base + o; o += up256(AI::BYTES);
@@ -1323,13 +1326,28 @@ static cudaError_t pair_setup(int *max_pairs) {
 int pack_images(const erlfill_ddpg_nets *n, uint8_t *tail_base, int B, cudaStream_t st) {
     Tail t;
     carve_tail(t, tail_base, B);
-    ERLFILL_CUDA_TRY(cudaMemsetAsync(t.flags, 0, up256((2 * (size_t)n_cta(B) + 2) * 4), st));
+    ERLFILL_CUDA_TRY(cudaMemsetAsync(t.flags, 0, up256((2 * (size_t)n_cta(B) + 4) * 4), st));
     ERLFILL_CUDA_TRY(cudaMemsetAsync(t.img_actor, 0, 2 * up256(AI::BYTES) + 2 * up256(CI::BYTES), st));
     pack_images_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, n->actor_target, n->critic, n->critic_target, t.img_actor, t.img_actor_t,
                                                                 t.img_critic, t.img_critic_t);
     ERLFILL_CUDA_TRY(cudaGetLastError());
     return ERLFILL_OK;
 }
+
+// what peer.cu needs of the tail (peer.cuh): the fast exchange's norm partials and the signal's arrival counters
+float *tail_ssq_fine(uint8_t *tail_base, int B, int which) {
+    Tail t;
+    carve_tail(t, tail_base, B);
+    return t.ssq_fine + which * kRedBlocksMax;
+}
+unsigned int *tail_peer_done(uint8_t *tail_base, int B, int which) {
+    Tail t;
+    carve_tail(t, tail_base, B);
+    return t.flags + 2 * n_cta(B) + 2 + which;
+}
+constexpr int fine_blocks(int which) { return ((which == 0 ? CO::TOTAL + 3 : AO::TOTAL) + kPeerFineThreads - 1) / kPeerFineThreads; }
+static_assert(fine_blocks(0) <= kRedBlocksMax && fine_blocks(1) <= kRedBlocksMax, "ssq_fine holds the fast exchange's norm partials");
+int peer_fine_blocks(int which) { return fine_blocks(which); }
 
 // the workspace head the two paths share (update.cu)
 struct Head { float *cgrad, *agrad, *cred, *ared, *stats, *scal, *ssq, *step; };
@@ -1368,29 +1386,45 @@ int update_fast(const erlfill_ddpg_nets *n, const erlfill_ddpg_hyper *h, const f
     a.stats_ext = h->n_stats_partials > 0 ? h->d_stats_partials : nullptr; a.n_stats_ext = h->n_stats_partials;
     a.split = (2 * nc <= max_pairs) ? 1 : 0;  // the pairs of both chains of every tile must be resident at once (one CTA per SM)
     const bool reduced = (phases & ERLFILL_PHASE_REDUCED) != 0;
+    // REDUCED: the partials of erlfill_ddpg_peer_allreduce_fast (hyper->peer set) or of erlfill_ddpg_peer_allreduce (64 slices)
+    const bool fine = reduced && h->peer != nullptr;
+    PeerSig sig{};                                           // world == 0: no exchange
+    if (h->peer) {
+        const erlfill_peer_group *g = (const erlfill_peer_group *)h->peer;
+        if (g->world < 1 || g->world > ERLFILL_MAX_PEERS || g->rank < 0 || g->rank >= g->world) return ERLFILL_ERR_ARG;
+        sig.world = g->world; sig.rank = g->rank;
+        for (int p = 0; p < g->world; ++p) {
+            if (!g->ctrl[p]) return ERLFILL_ERR_ARG;
+            sig.ctrl[p] = (PeerCtrl *)g->ctrl[p];
+        }
+    }
     if (phases & ERLFILL_PHASE_CRITIC_GRAD) {
         ERLFILL_CUDA_TRY(launch_pairs(ddpg_critic_grad_tc, 2 * (a.split ? 2 * nc : nc), a, st));
-        grad_reduce_kernel<false><<<red_blocks(false), kRedThreads, 0, st>>>(nc, B, t.cpart, nullptr, w.scal, w.cgrad, t.ssq_fine);
+        sig.which = 0; sig.done = t.flags + 2 * nc + 2;
+        if (sig.world > 0) grad_reduce_kernel<false, true><<<red_blocks(false), kRedThreads, 0, st>>>(nc, B, t.cpart, nullptr, w.scal, w.cgrad, t.ssq_fine, sig);
+        else grad_reduce_kernel<false, false><<<red_blocks(false), kRedThreads, 0, st>>>(nc, B, t.cpart, nullptr, w.scal, w.cgrad, t.ssq_fine, sig);
     }
     if (phases & ERLFILL_PHASE_CRITIC_APPLY) {
         if (!reduced && !(phases & ERLFILL_PHASE_CRITIC_GRAD))
             grad_ssq_kernel<false><<<red_blocks(false), kRedThreads, 0, st>>>(w.cgrad, t.ssq_fine);
         const float *G = reduced ? w.cred : w.cgrad;
-        critic_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->critic, n->critic_m, n->critic_v, G, reduced ? w.ssq : t.ssq_fine,
-                                                                     reduced ? mlp::kSumsqBlocks : red_blocks(false), w.step, h->critic_lr, h->actor_lr,
+        critic_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->critic, n->critic_m, n->critic_v, G, reduced && !fine ? w.ssq : t.ssq_fine,
+                                                                     fine ? fine_blocks(0) : (reduced ? mlp::kSumsqBlocks : red_blocks(false)), w.step, h->critic_lr, h->actor_lr,
                                                                      h->max_grad_norm, w.scal, t.img_critic);
     }
     if (phases & ERLFILL_PHASE_ACTOR_GRAD) {
         ERLFILL_CUDA_TRY(launch_pairs(ddpg_actor_grad_tc, 2 * nc, a, st));
-        grad_reduce_kernel<true><<<red_blocks(true), kRedThreads, 0, st>>>(nc, B, t.apart, n->actor, w.scal, w.agrad, t.ssq_fine + kRedBlocksMax);
+        sig.which = 1; sig.done = t.flags + 2 * nc + 3;
+        if (sig.world > 0) grad_reduce_kernel<true, true><<<red_blocks(true), kRedThreads, 0, st>>>(nc, B, t.apart, n->actor, w.scal, w.agrad, t.ssq_fine + kRedBlocksMax, sig);
+        else grad_reduce_kernel<true, false><<<red_blocks(true), kRedThreads, 0, st>>>(nc, B, t.apart, n->actor, w.scal, w.agrad, t.ssq_fine + kRedBlocksMax, sig);
     }
     if (phases & ERLFILL_PHASE_ACTOR_APPLY) {
         if (!reduced && !(phases & ERLFILL_PHASE_ACTOR_GRAD))
             grad_ssq_kernel<true><<<red_blocks(true), kRedThreads, 0, st>>>(w.agrad, t.ssq_fine + kRedBlocksMax);
         const float *G = reduced ? w.ared : w.agrad;
         actor_apply_kernel<<<(CO::TOTAL + 255) / 256, 256, 0, st>>>(n->actor, n->actor_target, n->actor_m, n->actor_v, G,
-                                                                    reduced ? w.ssq + mlp::kSumsqBlocks : t.ssq_fine + kRedBlocksMax,
-                                                                    reduced ? mlp::kSumsqBlocks : red_blocks(true), w.step, h->max_grad_norm, h->tau, n->critic, n->critic_target, w.scal, t.img_actor,
+                                                                    reduced && !fine ? w.ssq + mlp::kSumsqBlocks : t.ssq_fine + kRedBlocksMax,
+                                                                    fine ? fine_blocks(1) : (reduced ? mlp::kSumsqBlocks : red_blocks(true)), w.step, h->max_grad_norm, h->tau, n->critic, n->critic_target, w.scal, t.img_actor,
                                                                     t.img_actor_t, t.img_critic_t, d_report);
     }
     ERLFILL_CUDA_TRY(cudaGetLastError());

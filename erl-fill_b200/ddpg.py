@@ -183,7 +183,7 @@ class DDPGLearner:
     def launches_per_update(self, data_parallel=False):
         """Kernels of liberlfill.so per erlfill_ddpg_update(PHASE_ALL) (+ the two peer exchanges when data-parallel)."""
         n = int(L.lib().erlfill_ddpg_update_launches(C.c_int(1 if self.precision == "fast" else 0)))
-        return n + (int(L.lib().erlfill_ddpg_peer_launches()) if data_parallel else 0)
+        return n + (int(L.lib().erlfill_ddpg_peer_launches(C.c_int(1 if self.precision == "fast" else 0))) if data_parallel else 0)
 
     def grad_buckets(self, batch):
         """(critic_bucket, actor_bucket) tensors aliasing the gradient buckets in the workspace."""
@@ -262,11 +262,16 @@ class DDPGLearner:
             self.updates += 1
         upd_idx = (self.updates - 1) & 0xFFFFFFFF      # one index per update, whichever way its phases are called
 
+        # data-parallel over peer memory (parallel.PeerExchange attaches itself to the learner): the fast path's X_GRAD phases raise this
+        # rank's "bucket ready" flags themselves, whichever way the phases are called
+        px = allreduce if getattr(allreduce, "peer", False) else getattr(self, "_peer_exchange", None)
+
         def run(ph, adam_step):
             hyper = L.DDPGHyper(B, adam_step, self.gamma, self.tau, 5.0, self.n_cond, self.critic_lr, self.actor_lr, decay,
                                 L.PRECISION_FAST if fast else L.PRECISION_EXACT, dmode, self.seed, upd_idx, self.rank,
                                 C.cast(C.pointer(mstruct), C.c_void_p) if mstruct is not None else None,
-                                L.ptr(stats_partials), 0 if stats_partials is None else int(stats_partials.shape[0]), 0)
+                                L.ptr(stats_partials), 0 if stats_partials is None else int(stats_partials.shape[0]), 0,
+                                C.cast(C.pointer(px.g), C.c_void_p) if (fast and px is not None) else None)
             with torch.cuda.device(self.device):
                 L.check(L.lib().erlfill_ddpg_update(C.byref(nets), C.byref(hyper), L.ptr(batch), L.ptr(next_emotion), L.ptr(ws),
                                                     C.c_int(ph), L.ptr(self.report), L.stream_ptr()), "erlfill_ddpg_update")

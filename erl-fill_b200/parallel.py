@@ -135,6 +135,7 @@ class PeerExchange:
         learner._ws_batch = self.batch
         learner._ws_shared = True
         self._learner = learner
+        learner._peer_exchange = self
         learner._graphs.clear()
         learner._warm.clear()
         learner._images_ok = False       # the fast path's weight images live in the (new) workspace
@@ -142,8 +143,12 @@ class PeerExchange:
 
     def exchange(self, which):
         L = self.L
-        L.check(L.lib().erlfill_ddpg_peer_allreduce(C.byref(self.g), C.c_int(self.batch), C.c_int(which), L.stream_ptr()),
-                "erlfill_ddpg_peer_allreduce")
+        if getattr(self._learner, "precision", "exact") == "fast":      # the X_GRAD phase has signalled already (hyper.peer)
+            L.check(L.lib().erlfill_ddpg_peer_allreduce_fast(C.byref(self.g), C.c_int(self.batch), C.c_int(which), L.stream_ptr()),
+                    "erlfill_ddpg_peer_allreduce_fast")
+        else:
+            L.check(L.lib().erlfill_ddpg_peer_allreduce(C.byref(self.g), C.c_int(self.batch), C.c_int(which), L.stream_ptr()),
+                    "erlfill_ddpg_peer_allreduce")
 
     def error(self):
         e = C.c_int()
@@ -161,6 +166,7 @@ class PeerExchange:
             ln = getattr(self, "_learner", None)
             if ln is not None:          # the learner must not keep pointing at the freed block
                 ln._ws, ln._ws_batch, ln._ws_shared = None, 0, False
+                ln._peer_exchange = None
                 ln._graphs.clear(); ln._warm.clear()
             self.L.lib().erlfill_peer_free(C.c_void_p(self._base))
             self._base = None

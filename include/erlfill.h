@@ -361,6 +361,9 @@ typedef struct {
     /* optional (ERLFILL_PRECISION_FAST): the emotion sums erlfill_replay_sample_gather left for THIS minibatch, n_stats_partials rows of 8 */
     const float *d_stats_partials;
     int32_t n_stats_partials, _pad2;
+    /* optional (ERLFILL_PRECISION_FAST, data-parallel): the peer group (erlfill_peer_group, below).  The X_GRAD phases then raise this
+     * rank's "bucket ready" flags themselves and the exchange is erlfill_ddpg_peer_allreduce_fast. */
+    const void *peer;
 } erlfill_ddpg_hyper;
 
 typedef enum { ERLFILL_PHASE_CRITIC_GRAD = 1, ERLFILL_PHASE_CRITIC_APPLY = 2, ERLFILL_PHASE_ACTOR_GRAD = 4,
@@ -421,8 +424,12 @@ int erlfill_peer_free(void *dptr);
  * gradient.  Call between X_GRAD and (X_APPLY | ERLFILL_PHASE_REDUCED); stream-ordered, graph-capturable, no host sync.
  * Every rank must make the same sequence of calls. */
 int erlfill_ddpg_peer_allreduce(const erlfill_peer_group *g, int batch, int which, void *stream);
-/* kernels the two exchanges of one update add (bench.py's gpu_launches claim) */
-int erlfill_ddpg_peer_launches(void);
+/* The exchange of the tcgen05 update (hyper->precision == ERLFILL_PRECISION_FAST with hyper->peer set): the X_GRAD phase has already
+ * signalled, so this is one launch — wait for the peers' flags, one element per thread, one norm partial per 256 elements (the
+ * geometry the fast path's X_APPLY | ERLFILL_PHASE_REDUCED expects). */
+int erlfill_ddpg_peer_allreduce_fast(const erlfill_peer_group *g, int batch, int which, void *stream);
+/* kernels the two exchanges of one update add (bench.py's gpu_launches claim): 4 (fast = 0: signal + reduce, twice) or 2 */
+int erlfill_ddpg_peer_launches(int fast);
 /* 1 in *error_out if a wait for a peer timed out (ERLFILL_PEER_TIMEOUT_S seconds, default 30) since the allocation; synchronises
  * the device.  A timed-out exchange also writes NaN into the reduced bucket and its norm partials, so the following APPLY phase
  * poisons this rank's parameters and update report instead of applying a stale sum. */
