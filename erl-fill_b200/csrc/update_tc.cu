@@ -1,14 +1,18 @@
 // update_tc.cu — the tcgen05 ("fast") ER-DDPG minibatch update: DDPGAgent.learn, DifferentModules/ddpg_agent.py:422-512,
 // rows U1-U5 of SURVEY.md section 8a, with train()-mode dropout (the reference never calls .eval() on this path).
 //
-// Six launches per update (erlfill_ddpg_update with hyper->precision == ERLFILL_PRECISION_FAST):
-//   CRITIC_GRAD   ddpg_critic_grad_tc   B/128 CTAs: target chain actor_target -> critic_target, Q(s, a), SmoothL1, the whole critic
-//                                       backward incl. the weight-gradient GEMMs (per-CTA partials)
-//                 grad_reduce_kernel    partials -> flat gradient bucket (CTA order, deterministic) + clip-norm partials
-//   CRITIC_APPLY  apply_kernel          emotion-driven lr, clip_grad_norm_(5), Adam, refresh of the critic's bf16 weight images
-//   ACTOR_GRAD    ddpg_actor_grad_tc    actor forward, Q(s, actor(s)) with the UPDATED critic, critic input gradient, actor backward
+// Six launches per update (erlfill_ddpg_update with hyper->precision == ERLFILL_PRECISION_FAST); the two phase kernels run as clusters
+// of two CTAs per 128-row tile (the pair splits the output columns of every layer: update_tc.cuh):
+//   CRITIC_GRAD   ddpg_critic_grad_tc   2 x B/128 pairs: one half runs the target chain actor_target -> critic_target and hands Q' over,
+//                                       then the forward of the CURRENT actor for ACTOR_GRAD (it does not depend on the critic update);
+//                                       the other half Q(s, a), SmoothL1 and the whole critic backward incl. the weight-gradient GEMMs
+//                                       (per-tile partials).  One pair does all of it when the tiles outnumber the resident pairs.
+//                 grad_reduce_kernel    partials -> flat gradient bucket (tile order, deterministic) + clip-norm partials
+//                                       (data-parallel: its last block raises this rank's bucket-ready flags on the peers, peer.cuh)
+//   CRITIC_APPLY  critic_apply_kernel   emotion-driven lr, clip_grad_norm_(5), Adam, refresh of the critic's bf16 weight images
+//   ACTOR_GRAD    ddpg_actor_grad_tc    B/128 pairs: Q(s, actor(s)) with the UPDATED critic, critic input gradient, actor backward
 //                 grad_reduce_kernel    (+ the L2-norm regulariser's gradient)
-//   ACTOR_APPLY   apply_kernel          clip, Adam, both soft target updates, all target / actor images, report
+//   ACTOR_APPLY   actor_apply_kernel    clip, Adam, both soft target updates, all target / actor images, report
 // Building blocks and the operand-image scheme: update_tc.cuh.  Numerics: bf16 operands, fp32 accumulation, fp32 master weights,
 // LayerNorm / losses / optimiser in fp32 (stated tolerance against the fp32 reference: tests/test_update_tc_gpu.py); the exact
 // 3xTF32 path of update.cu stays the 1e-4 parity path.
