@@ -546,6 +546,24 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
                         }
                         float sum0 = 0.f, sum1 = 0.f;
                         uint32_t pa[3][2];
+                        // dropout on the attention probabilities (the sums below stay those of the undropped softmax): the pair (query i,
+                        // keys j, j + 1) sits in one half-word pair of one Philox block since its element index is even.  The six blocks of
+                        // this thread's fragment are drawn unconditionally and back to back — six independent chains the scheduler can
+                        // interleave; one call at a time inside the range checks, the ten dependent rounds of every call were exposed
+                        // (31.7 k of the 92 k cycles of a train()-mode layer step).
+                        uint32_t am[3][2];
+                        if (kDrop == DROP_PHILOX) {
+                            const uint32_t env_g = (uint32_t)(grp_env0 + e);
+#pragma unroll
+                            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                                for (int hf = 0; hf < 2; ++hf) {
+                                    const uint32_t idx = (uint32_t)((h * SMAX + (mt * 16 + g8 + 8 * hf)) * SMAX + nt * 8 + 2 * tq);
+                                    const uint4 rr = tfdrop::block8(a.k0, a.k1, a.row_id_base + env_g, a.call_idx, 4u * l, idx >> 3);
+                                    const uint32_t lane4 = (idx & 7u) >> 1;
+                                    am[nt][hf] = tfdrop::pair_mask(lane4 == 0 ? rr.x : (lane4 == 1 ? rr.y : (lane4 == 2 ? rr.z : rr.w)));
+                                }
+                        }
 #pragma unroll
                         for (int nt = 0; nt < 3; ++nt) {
                             const float p0 = fast_exp2(scr[mt][nt][0] - mx0), p1 = fast_exp2(scr[mt][nt][1] - mx0);
@@ -557,8 +575,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
                                 pa[nt][1] = pack_bf16x2(p2, p3);
                             } else pa[nt][1] = 0u;
                             if (kDrop != DROP_OFF) {
-                                // dropout on the attention probabilities (the sums above stay those of the undropped softmax): the pair
-                                // (query i, keys j, j + 1) sits in one half-word pair of one Philox block since its element index is even
                                 const int env_g = grp_env0 + e;
                                 const int j = nt * 8 + 2 * tq;
 #pragma unroll
@@ -567,12 +583,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
                                     const int i = mt * 16 + g8 + 8 * hf;
                                     uint32_t m = 0xffffffffu;
                                     if (i < Se && j < Se && env_g < a.n) {
-                                        if (kDrop == DROP_PHILOX) {
-                                            const uint32_t idx = (uint32_t)((h * SMAX + i) * SMAX + j);
-                                            const uint4 rr = tfdrop::block8(a.k0, a.k1, a.row_id_base + (uint32_t)env_g, a.call_idx, 4u * l, idx >> 3);
-                                            const uint32_t lane4 = (idx & 7u) >> 1;
-                                            m = tfdrop::pair_mask(lane4 == 0 ? rr.x : (lane4 == 1 ? rr.y : (lane4 == 2 ? rr.z : rr.w)));
-                                        } else {
+                                        if (kDrop == DROP_PHILOX) m = am[nt][hf];
+                                        else {
                                             const uint8_t *mp = a.masks.attn + ((((size_t)l * a.n + env_g) * 4 + h) * a.S + i) * a.S + j;
                                             m = (mp[0] ? 0xffffu : 0u) | ((j + 1 < Se && mp[1]) ? 0xffff0000u : 0u);
                                         }

@@ -7,7 +7,9 @@ import torch
 import erlfill_b200  # noqa: F401
 from erlfill_b200 import nets
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 65536
+from erlfill_b200 import _lib as L0
+DROP = L0.DROPOUT_PHILOX if "--philox" in sys.argv else L0.DROPOUT_OFF        # --philox: train() mode
 G = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "nets_golden.npz"))
 W = {k[len("trans."):]: torch.from_numpy(np.array(G[k])) for k in G.files if k.startswith("trans.")}
 P = nets.TransformerParams(W)
@@ -18,13 +20,13 @@ from erlfill_b200 import _lib as L
 prof = (C.c_ulonglong * 16)()
 for prec, reps in (("bf16", 10),) + ((("fp32", 2),) if "--fp32" in sys.argv else ()):
     for _ in range(2):
-        nets.emotion_forward(P, seq=seq, precision=prec, out=out)
+        nets.emotion_forward(P, seq=seq, precision=prec, out=out, dropout=DROP, seed=5)
     torch.cuda.synchronize()
     L.lib().erlfill_debug_tc_profile(None, 1)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps):
-        nets.emotion_forward(P, seq=seq, precision=prec, out=out)
+        nets.emotion_forward(P, seq=seq, precision=prec, out=out, dropout=DROP, seed=5)
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
