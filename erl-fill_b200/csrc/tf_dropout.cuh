@@ -5,7 +5,8 @@
 // 4l + 2 FFN hidden (after relu), 4l + 3 dropout2 (after linear2).  Element index inside a site:
 //   attention (head h, query i, key j): (h * 20 + i) * 20 + j        dropout1 / dropout2 (token s, feature c): s * 32 + c
 //   FFN hidden (token s, unit u): s * 2048 + u
-// One Philox-4x32-10 call covers 8 consecutive elements: counter (global env id, call index, element / 8, STREAM_DROPOUT + 8 + site);
+// One Philox-4x32-7 call (common.cuh: the fewest rounds that pass BigCrush; these masks are never rebuilt outside the two kernels, and
+// drawing them bounds the train()-mode kernel) covers 8 consecutive elements: counter (global env id, call index, element / 8, STREAM_DROPOUT + 8 + site);
 // its eight 16-bit halves h decide  keep = ((h & 0x7fff) >= 9830), i.e. P(drop) = 9830 / 32768 = 0.29999.  The low 15 bits are used so
 // that two halves can be compared at once with one 32-bit add (no carry between the halves) — the packed form the tensor-core kernel
 // needs, where one 32-bit word holds two bf16 activations.  Kept values are scaled by 1 / 0.7 like at::dropout.
@@ -19,7 +20,7 @@ constexpr uint32_t kT15 = 9830u;
 constexpr float kScale = 1.0f / (1.0f - 0.3f);
 
 __device__ __forceinline__ uint4 block8(uint32_t k0, uint32_t k1, uint32_t gid, uint32_t call_idx, uint32_t site, uint32_t block) {
-    return philox4x32_10(k0, k1, gid, call_idx, block, STREAM_DROPOUT + 8u + site);
+    return philox4x32_r<7>(k0, k1, gid, call_idx, block, STREAM_DROPOUT + 8u + site);
 }
 // keep flag of element `lane8` (0..7) of a block
 __device__ __forceinline__ bool keep_elem(const uint4 &r, int lane8) {
