@@ -385,7 +385,7 @@ def wl_rollout(args, rank, world, device, timer):
     other_mode = {"dropout": other, "value": n * world * k2 / (ms2 * 1e-3), "unit": "env-steps/s", "ms_per_step": ms2 / k2, "steps": k2,
                   "transformer_kernel_ms": tf2,
                   "note": "philox = train() mode, the mode the reference runs (it never calls .eval() on this path): four dropout layers per "
-                          "encoder layer + two in the actor, keep-masks from Philox-4x32-10 (16 random bits per mask bit, csrc/tf_dropout.cuh); "
+                          "encoder layer + two in the actor, keep-masks from Philox (16 random bits per mask bit; 4x32-7 in the transformer, csrc/tf_dropout.cuh, 4x32-10 in the actor); "
                           "the transformer kernel is then bound by the integer pipe that draws 163,840 mask bits per env and call, not by the tensor pipe"}
     env, agent = env2, agent2       # (the roofline object below describes the headline mode: its kernel time was taken above)
     agent.emotion_precision = args.emotion_precision
