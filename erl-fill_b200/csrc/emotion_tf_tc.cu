@@ -553,16 +553,27 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) emotion_forward_tc_kerne
                         // (31.7 k of the 92 k cycles of a train()-mode layer step).
                         uint32_t am[3][2];
                         if (kDrop == DROP_PHILOX) {
+                            // The four threads of a quad hold the 24 consecutive elements (query row i, keys 0..23) of the site: element
+                            // index R .. R + 23 with R = (h * 20 + i) * 20, R % 8 in {0, 4} — three or four Philox blocks.  Lane tq of the
+                            // quad draws block R / 8 + tq (one call per row instead of three), the words travel by shuffle: thread tq
+                            // needs word (R % 8) / 2 + 4 nt + tq of the quad's 16.
                             const uint32_t env_g = (uint32_t)(grp_env0 + e);
+                            const int qbase = lane & ~3;
 #pragma unroll
-                            for (int nt = 0; nt < 3; ++nt)
+                            for (int hf = 0; hf < 2; ++hf) {
+                                const uint32_t R = (uint32_t)((h * SMAX + (mt * 16 + g8 + 8 * hf)) * SMAX);
+                                const uint4 rr = tfdrop::block8(a.k0, a.k1, a.row_id_base + env_g, a.call_idx, 4u * l, (R >> 3) + (uint32_t)tq);
+                                const uint32_t off = (R & 7u) >> 1;
 #pragma unroll
-                                for (int hf = 0; hf < 2; ++hf) {
-                                    const uint32_t idx = (uint32_t)((h * SMAX + (mt * 16 + g8 + 8 * hf)) * SMAX + nt * 8 + 2 * tq);
-                                    const uint4 rr = tfdrop::block8(a.k0, a.k1, a.row_id_base + env_g, a.call_idx, 4u * l, idx >> 3);
-                                    const uint32_t lane4 = (idx & 7u) >> 1;
-                                    am[nt][hf] = tfdrop::pair_mask(lane4 == 0 ? rr.x : (lane4 == 1 ? rr.y : (lane4 == 2 ? rr.z : rr.w)));
+                                for (int nt = 0; nt < 3; ++nt) {
+                                    const uint32_t W = off + 4u * nt + (uint32_t)tq;          // word of the quad's 16
+                                    const int src = qbase + (int)(W >> 2);
+                                    const uint32_t w0 = __shfl_sync(0xffffffffu, rr.x, src), w1 = __shfl_sync(0xffffffffu, rr.y, src);
+                                    const uint32_t w2 = __shfl_sync(0xffffffffu, rr.z, src), w3 = __shfl_sync(0xffffffffu, rr.w, src);
+                                    const uint32_t ws = W & 3u;
+                                    am[nt][hf] = tfdrop::pair_mask(ws == 0 ? w0 : (ws == 1 ? w1 : (ws == 2 ? w2 : w3)));
                                 }
+                            }
                         }
 #pragma unroll
                         for (int nt = 0; nt < 3; ++nt) {
